@@ -1,0 +1,240 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (via oracle/ref_shim) in this container.
+
+    python -m oracle.make_golden            # needs /root/reference ; writes tests/golden/
+
+Each fixture stores the case recipe (so tests can rebuild weights and batch from seeds with oracle/synth.py)
+and the REFERENCE's outputs: sub-sampled logits, per-row logsumexp, loss / nll / ntokens, per-parameter
+gradient norms, updated BatchNorm running statistics, beam-search tokens and scores.  While generating, the
+oracle restatement (oracle/ofa_oracle.py) is run on the same inputs and must agree, otherwise this script fails.
+TEST INFRASTRUCTURE ONLY.
+"""
+import copy
+import json
+import os
+import random
+import sys
+
+import torch
+
+from . import synth, ref_harness as rh, ofa_oracle as oo
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+COL_STRIDE = 37
+
+# name -> recipe.  "tasks" is a list of make_batch kwargs (one entry = single-task sample).
+CASES = {
+    # BASELINE.json configs[0] / SURVEY.md 8(d) C1
+    "c1_tiny": dict(arch="ofa_tiny", cfg={}, tasks=[dict(bsz=2, src_len=32, tgt_len=32, img=256, seed=0)],
+                    crit=dict(label_smoothing=0.1)),
+    "micro_pad": dict(arch="ofa_micro", cfg=dict(vocab_size=4099),
+                      tasks=[dict(bsz=3, src_len=21, tgt_len=13, img=64, seed=1, vocab=4099, n_pad=4)],
+                      crit=dict(label_smoothing=0.1)),
+    "micro_text_only": dict(arch="ofa_micro", cfg=dict(vocab_size=4099),
+                            tasks=[dict(bsz=2, src_len=40, tgt_len=9, seed=2, vocab=4099, with_image=False)],
+                            crit=dict(label_smoothing=0.1)),
+    "micro_nomask_row": dict(arch="ofa_micro", cfg=dict(vocab_size=4099),
+                             tasks=[dict(bsz=2, src_len=17, tgt_len=8, img=64, seed=3, vocab=4099)],
+                             crit=dict(label_smoothing=0.1), patch_masks=[True, False]),
+    "micro_constraint": dict(arch="ofa_micro", cfg=dict(vocab_size=4099),
+                             tasks=[dict(bsz=2, src_len=24, tgt_len=20, img=64, seed=4, vocab=4099,
+                                         target_prefix_pad=12, constraint=True)],
+                             crit=dict(label_smoothing=0.1)),
+    "micro_rdrop_sample": dict(arch="ofa_micro", cfg=dict(vocab_size=4099),
+                               tasks=[dict(bsz=2, src_len=19, tgt_len=7, img=96, seed=5, vocab=4099)],
+                               crit=dict(label_smoothing=0.1, use_rdrop=True, reg_alpha=1.0),
+                               sample_patch_num=10, py_seed=11),
+    "micro_multitask_rdrop": dict(arch="ofa_micro", cfg=dict(vocab_size=4099),
+                                  tasks=[dict(bsz=2, src_len=19, tgt_len=7, img=96, seed=6, vocab=4099),
+                                         dict(bsz=2, src_len=30, tgt_len=28, img=96, seed=7, vocab=4099,
+                                              target_prefix_pad=20, constraint=True),
+                                         dict(bsz=2, src_len=25, tgt_len=6, seed=8, vocab=4099, with_image=False)],
+                                  crit=dict(label_smoothing=0.1, use_rdrop=True, reg_alpha=1.0,
+                                            sample_patch_num=9), py_seed=12),
+    "micro_plainflags": dict(arch="ofa_micro",
+                             cfg=dict(vocab_size=4099, scale_attn=False, scale_fc=False, scale_heads=False,
+                                      disable_entangle=False),
+                             tasks=[dict(bsz=2, src_len=15, tgt_len=11, img=64, seed=9, vocab=4099)],
+                             crit=dict(label_smoothing=0.0)),
+    "micro_frozenbn_eval": dict(arch="ofa_micro", cfg=dict(vocab_size=4099, freeze_resnet=True),
+                                tasks=[dict(bsz=2, src_len=15, tgt_len=11, img=64, seed=10, vocab=4099)],
+                                crit=dict(label_smoothing=0.1), eval_mode=True),
+}
+GEN_CASES = {
+    "gen_micro": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.1,
+                      batch=dict(bsz=3, src_len=9, tgt_len=2, img=64, seed=20, vocab=4099, n_pad=2),
+                      gen=dict(beam_size=5, max_len_a=0, max_len_b=8, min_len=1)),
+    "gen_micro_ngram": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.1,
+                            batch=dict(bsz=2, src_len=9, tgt_len=2, img=64, seed=21, vocab=4099, n_pad=0),
+                            gen=dict(beam_size=3, max_len_a=0, max_len_b=10, min_len=2, no_repeat_ngram_size=2)),
+    # BASELINE.json configs[4] scaled to ofa_tiny / batch 2 (the oracle finishes in seconds)
+    "gen_tiny": dict(arch="ofa_tiny", cfg={}, emb_std=0.1,
+                     batch=dict(bsz=2, src_len=8, tgt_len=2, img=256, seed=22, n_pad=0),
+                     gen=dict(beam_size=5, max_len_a=0, max_len_b=16, min_len=1)),
+}
+
+
+def build_samples(case):
+    samples = []
+    for kw in case["tasks"]:
+        s = synth.make_batch(**kw)
+        if "patch_masks" in case:
+            s["net_input"]["patch_masks"] = torch.tensor(case["patch_masks"])
+        samples.append(s)
+    return samples
+
+
+def tie(sd):
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    sd["decoder.embed_tokens.weight"] = sd["encoder.embed_tokens.weight"]
+    sd["decoder.output_projection.weight"] = sd["encoder.embed_tokens.weight"]
+    return sd
+
+
+def run_train_case(name, case):
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0)
+    model, task = rh.build_model(cfg, sd)
+    train = not case.get("eval_mode", False)
+    model.train(train)
+    ck = dict(case["crit"])
+    crit = rh.build_criterion(task, **ck)
+    samples = build_samples(case)
+    spn = case.get("sample_patch_num")
+    ref_in = copy.deepcopy(samples)
+    if spn:
+        ref_in[0]["net_input"]["sample_patch_num"] = spn
+    if "py_seed" in case:
+        random.seed(case["py_seed"])
+    loss, ss, log = crit(model, ref_in if len(ref_in) > 1 else ref_in[0])
+    (loss / ss).backward()
+    loss = loss.detach()
+    rs_after = {k: float(v.float().norm()) for k, v in model.state_dict().items() if "running_" in k}
+
+    # oracle on the same inputs (same python-random call sequence -> same patch orders)
+    sdo = tie(sd)
+    if "py_seed" in case:
+        random.seed(case["py_seed"])
+    stats = {}
+    ora_in = copy.deepcopy(samples)
+    if spn:
+        ora_in[0]["net_input"]["sample_patch_num"] = spn
+    l2, ss2, lg2 = oo.criterion_forward(
+        sdo, cfg, ora_in if len(ora_in) > 1 else ora_in[0], epsilon=ck["label_smoothing"],
+        use_rdrop=ck.get("use_rdrop", False), reg_alpha=ck.get("reg_alpha", 1.0),
+        sample_patch_num=ck.get("sample_patch_num", 0), training=train, stats_out=stats)
+    (l2 / ss2).backward()
+    assert ss == ss2, (ss, ss2)
+    rel = abs(loss.item() - l2.item()) / abs(loss.item())
+    assert rel < 1e-5, (name, loss.item(), l2.item())
+
+    gnorm = {}
+    for n, p in model.named_parameters():
+        gnorm[n] = float(p.grad.float().norm()) if p.grad is not None else None
+    worst = 0.0
+    for n, g in gnorm.items():
+        go = sdo[n].grad
+        if g is None:
+            assert go is None or float(go.norm()) == 0.0, n
+            continue
+        if n.endswith("k_proj.bias") or n.endswith("pos_k_linear.bias"):
+            continue  # mathematically zero (softmax shift invariance): pure rounding noise
+        worst = max(worst, abs(g - float(go.norm())) / (g + 1e-12))
+    assert worst < 2e-3, (name, worst)
+    total = sum(g * g for n, g in gnorm.items() if g is not None) ** 0.5
+
+    # reference logits for the (last) single-task forward, eval of the same weights without rdrop dup
+    fx = {"recipe": json.dumps({k: v for k, v in case.items()}), "loss": float(loss), "sample_size": ss,
+          "grad_norms": gnorm, "grad_norm_total": total}
+    if "tasks" in lg2:
+        fx["task_loss"] = [float(t["loss"]) for t in lg2["tasks"]]
+        fx["task_ntokens"] = [int(t["ntokens"]) for t in lg2["tasks"]]
+        fx["patch_orders"] = [t["patch_orders"] for t in lg2["tasks"]]
+        fx["loss_v1"] = float(log["loss_v1"])
+    else:
+        fx["nll_loss"] = float(log["nll_loss"])
+        fx["patch_orders"] = lg2["patch_orders"]
+        # reference logits (forward again so masks in-place edits of the criterion do not leak)
+        with torch.no_grad():
+            if "py_seed" in case:
+                random.seed(case["py_seed"])
+            ni = copy.deepcopy(samples[0]["net_input"])
+            if ck.get("use_rdrop"):
+                ni = oo._rdrop(ni)
+            if spn:
+                ni["sample_patch_num"] = spn * (2 if ck.get("use_rdrop") else 1)
+            # NB: R-Drop doubles sample_patch_num as well; replay exactly what the criterion did
+            if ck.get("use_rdrop") and spn:
+                pass
+            logits = model(**ni)[0].float()
+        fx["logits_sub"] = logits[:, :, ::COL_STRIDE].contiguous()
+        fx["logits_lse"] = torch.logsumexp(logits, -1)
+        d = (lg2["logits"].detach() - logits).abs().max().item() if lg2["logits"].shape == logits.shape else -1
+        print("   logits oracle-vs-ref maxabs", d)
+    if train and not cfg.freeze_resnet:
+        rs = rs_after
+        fx["bn_running_norms"] = rs
+        if stats and len(samples) == 1 and not ck.get("use_rdrop"):
+            w = max(abs(float(stats[k].norm()) - rs[k]) / rs[k] for k in stats)
+            assert w < 1e-4, ("bn running stats", w)
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print("%-24s loss %.6f ss %s gnorm %.4f  oracle rel-loss %.1e worst grad-norm rel %.1e" %
+          (name, float(loss), ss, total, rel, worst))
+
+
+def run_gen_case(name, case):
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0, emb_std=case["emb_std"])
+    model, task = rh.build_model(cfg, sd)
+    model.eval()
+    sample = synth.make_batch(**case["batch"])
+    gen = rh.build_generator(model, task, **case["gen"])
+    hyp = gen.generate([model], copy.deepcopy(sample))
+    g = dict(case["gen"])
+    ours = oo.generate(sd, cfg, sample["net_input"], beam=g["beam_size"], max_len_a=g["max_len_a"],
+                       max_len_b=g["max_len_b"], min_len=g["min_len"],
+                       no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0))
+    fx = {"recipe": json.dumps(case), "tokens": [], "scores": [], "pos_scores": []}
+    for s in range(len(hyp)):
+        assert len(hyp[s]) == len(ours[s])
+        fx["tokens"].append([h["tokens"].clone() for h in hyp[s]])
+        fx["scores"].append([float(h["score"]) for h in hyp[s]])
+        fx["pos_scores"].append([h["positional_scores"].clone() for h in hyp[s]])
+        for a, b in zip(hyp[s], ours[s]):
+            assert torch.equal(a["tokens"], b["tokens"]), (name, s, a["tokens"], b["tokens"])
+            assert abs(float(a["score"]) - float(b["score"])) < 1e-5
+    gaps = [fx["scores"][s][0] - fx["scores"][s][1] for s in range(len(hyp))]
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print("%-24s %d sentences, best hypo %s  score gaps %s" % (
+        name, len(hyp), hyp[0][0]["tokens"].tolist(), ["%.3f" % x for x in gaps]))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    only = sys.argv[1:]
+    # state-dict contract: names, order, shapes, dtypes for every arch
+    names = {}
+    for arch in ("ofa_tiny", "ofa_base") + (() if only else ("ofa_medium", "ofa_large")):
+        cfg = synth.make_cfg(arch)
+        model, _ = rh.build_model(cfg)
+        msd = model.state_dict()
+        spec = synth.state_spec(cfg)
+        assert list(msd.keys()) == list(spec.keys()), arch
+        for k, v in msd.items():
+            assert tuple(v.shape) == tuple(spec[k][0]), (arch, k)
+        names[arch] = {"n_entries": len(msd), "n_params": sum(p.numel() for p in model.parameters()),
+                       "entries": [[k, list(v.shape), str(v.dtype)] for k, v in msd.items()]}
+        print(arch, names[arch]["n_entries"], names[arch]["n_params"])
+        del model
+    with open(os.path.join(OUT, "state_dict_spec.json"), "w") as f:
+        json.dump(names, f)
+    for name, case in CASES.items():
+        if not only or name in only:
+            run_train_case(name, case)
+    for name, case in GEN_CASES.items():
+        if not only or name in only:
+            run_gen_case(name, case)
+
+
+if __name__ == "__main__":
+    main()

