@@ -1,0 +1,111 @@
+/* C ABI of libofa_b200.so -- the sm_100a kernels behind Musketeer's OFA forward/backward hot path.
+ *
+ * Boundary: the reference is pure Python; its drop-in surface is the fairseq `ofa` model plugin
+ * (models/ofa/ofa.py:25-171).  The reference has no FFI of its own, so this header is the binding one level below
+ * that plugin: each entry point replaces the ATen/cuBLAS call sites named beside it.  Plain pointers and sizes only
+ * (device pointers unless noted), an explicit CUDA stream, `int` status (0 = ok, message via ofa_last_error()).
+ * No entry point allocates or frees device memory or synchronises the device; callers own every buffer.
+ * dtype codes: 0 = float32, 1 = bfloat16.                                                                         */
+#ifndef OFA_B200_H_
+#define OFA_B200_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ofa_last_error(void);
+int ofa_abi_version(void);
+
+/* ---- GEMM: every nn.Linear on the path, forward / dgrad / wgrad --------------------------------------------------
+ * D[b](m,n) = act((sum_k A[b](m,k) B[b](n,k) + bias[n]) * alpha) + resid[b](m,n);  A,B bf16, fp32 accumulate (tcgen05).
+ * a_mn_major=0: A stored row-major [M][K] (lda);  =1: stored [K][M].  Same for B with N.  out_dtype: D/bias/resid type.
+ * replaces: unify_multihead_attention.py:213-232,399 (q/k/v/out proj), unify_transformer_layer.py:280-284,557-561
+ * (fc1/fc2), unify_transformer.py:739 (image_proj), :906-911,1303-1316 (pos q/k), :1577-1583 (tied output proj)
+ * and their autograd transposes.                                                                                    */
+int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, long long lda, long long ldb,
+                  long long ldd, long long stride_a, long long stride_b, long long stride_d, int a_mn_major,
+                  int b_mn_major, int out_dtype, const void* bias, float alpha, int act, const void* resid,
+                  long long ldr, long long stride_r, void* stream);
+
+/* fp32 -> three bf16 terms laid out as six K-blocks (fp32 parity mode operands for ofa_gemm_bf16) */
+int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, long long ldo, long long blk_stride,
+                    int pattern, void* stream);
+
+/* ---- LayerNorm (fairseq.modules.LayerNorm call sites: unify_transformer_layer.py:259-283,466-560;
+ * unify_transformer.py:731-747,898-904,951,1300,1486-1493,1567).  y = LN(f(x))*gamma+beta (+resid), f = id | gelu      */
+int ofa_layernorm_fwd(const void* x, const void* gamma, const void* beta, const void* resid, void* y, float* mean,
+                      float* rstd, int rows, int C, float eps, int gelu_in, int dtype, void* stream);
+int ofa_layernorm_bwd_nparts(int rows); /* host helper: workspace = 2 * nparts * C floats */
+int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
+                      void* dgamma, void* dbeta, float* workspace, int rows, int C, int gelu_in, int dtype,
+                      void* stream);
+
+/* ---- glue -------------------------------------------------------------------------------------------------------- */
+int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace /* 64*C floats */, int dtype,
+               void* stream); /* bias gradients */
+int ofa_embed_gather(const long long* idx, const void* table, const void* addvec, void* out, long long ldo, int rows,
+                     int C, int dtype, void* stream); /* unify_transformer.py:725-730,885,1450,1475 */
+int ofa_embed_scatter_add(const long long* idx, const void* dout, long long ldo, void* dtable, int rows, int C,
+                          long long skip_idx, int dtype, void* stream);
+int ofa_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);
+int ofa_mask_rows(void* x, const unsigned char* rowmask, int rows, int C, int dtype, void* stream); /* :892-893 */
+int ofa_gelu(const void* x, const void* dy, void* out, long long n, int backward, int dtype, void* stream);
+
+/* ---- label-smoothed CE (+R-Drop KL): loss rows and d(logits) in one kernel, gradient written in place --------------
+ * replaces criterions/label_smoothed_cross_entropy.py:81-126,228-260.                                                */
+int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* target, const unsigned char* cmask,
+                      const float* conf, int rows_per_sample, int R, int V, long long pad_idx, float eps, int cs,
+                      int ce, int rdrop, float reg_alpha, float* loss_rows, float* nll_rows, float* kl_rows, int dtype,
+                      void* stream);
+int ofa_scale_rows(void* x, long long ld, int R, int V, const float* scale, const unsigned char* row_keep, int dtype,
+                   void* stream);
+
+/* ---- attention with OFA position biases (unify_multihead_attention.py:345-398; bias assembly of
+ * unify_transformer.py:640-658,906-933,1282-1318,1519-1529 computed in-kernel) ------------------------------------- */
+typedef struct {
+  const float* tok_lut;       /* [H][2*tok_max-1] text rel-pos bias by (i_t - j_t) + tok_max - 1, or NULL */
+  int tok_max;                /* 1024 */
+  int q_text_off, k_text_off; /* first text index on the query / key axis */
+  const float* img_lut;       /* [H][n_img_rel] image rel-pos bias, or NULL */
+  int n_img_rel;              /* (2*ibs-1)^2 + 3 */
+  int ibs;                    /* image bucket size (42) */
+  const int* q_pid;           /* [B][n_img_q] 1-based image position ids */
+  const int* k_pid;           /* [B][n_img_k] */
+  int n_img_q, n_img_k;       /* image tokens occupy [0, n_img) */
+} OfaAttnBias;
+
+typedef struct {
+  const void *q, *pq, *k, *pk, *v; /* [B, L, H, 64] views; q and pq pre-scaled */
+  void* o;                         /* [B, T, H, 64] */
+  float* lse;                      /* [B, H, T] */
+  long long ldq, ldpq, ldk, ldpk, ldv, ldo;       /* token strides (elements) */
+  long long bsq, bspq, bsk, bspk, bsv, bso;       /* batch strides (elements) */
+  int B, H, T, S;
+  int causal;                  /* mask j > i + q_pos_off */
+  int q_pos_off;               /* absolute position of query row 0 (incremental decoding) */
+  const unsigned char* kpm;    /* [B][S] key padding mask (1 = pad) or NULL */
+  const float* head_scale;     /* [H] c_attn or NULL */
+  int p_round_bf16;            /* SIMT path only: round P to bf16 before P.V (mimics the bf16 reference path) */
+  OfaAttnBias bias;
+} OfaAttnArgs;
+
+typedef struct {
+  const void* dout;                 /* [B, T, H, 64], strides as o */
+  void *dq, *dpq, *dk, *dpk, *dv;
+  long long lddq, lddpq, lddk, lddpk, lddv;
+  long long bsdq, bsdpq, bsdk, bsdpk, bsdv;
+  float* dtok_lut;                  /* [H][2*tok_max-1] fp32, pre-zeroed, accumulated */
+  float* dimg_lut;                  /* [H][n_img_rel]   fp32, pre-zeroed, accumulated */
+  float* delta;                     /* [B,H,T] workspace; sum over rows / c_attn[h] = d c_attn[h] */
+  float* P;                         /* SIMT path: [B,H,T,S] fp32 workspace */
+  float* dS;                        /* SIMT path: [B,H,T,S] fp32 workspace */
+} OfaAttnGrads;
+
+int ofa_attn_fwd_simt(const OfaAttnArgs* args, int dtype, void* stream);
+int ofa_attn_bwd_simt(const OfaAttnArgs* args, const OfaAttnGrads* grads, int dtype, void* stream);
+/* bf16, TMA + tcgen05/TMEM flash attention */
+int ofa_attn_fwd_tc(const OfaAttnArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

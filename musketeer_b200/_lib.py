@@ -1,0 +1,88 @@
+"""ctypes binding of libofa_b200.so (include/ofa_b200.h).  There is no fallback: if the library is missing or a
+call fails, this raises -- the product never routes around its CUDA kernels."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libofa_b200.so")
+
+_lib = None
+
+c_ll, c_i, c_f, c_p = C.c_longlong, C.c_int, C.c_float, C.c_void_p
+
+
+class OfaAttnBias(C.Structure):
+    _fields_ = [("tok_lut", c_p), ("tok_max", c_i), ("q_text_off", c_i), ("k_text_off", c_i),
+                ("img_lut", c_p), ("n_img_rel", c_i), ("ibs", c_i), ("q_pid", c_p), ("k_pid", c_p),
+                ("n_img_q", c_i), ("n_img_k", c_i)]
+
+
+class OfaAttnArgs(C.Structure):
+    _fields_ = [("q", c_p), ("pq", c_p), ("k", c_p), ("pk", c_p), ("v", c_p), ("o", c_p), ("lse", c_p),
+                ("ldq", c_ll), ("ldpq", c_ll), ("ldk", c_ll), ("ldpk", c_ll), ("ldv", c_ll), ("ldo", c_ll),
+                ("bsq", c_ll), ("bspq", c_ll), ("bsk", c_ll), ("bspk", c_ll), ("bsv", c_ll), ("bso", c_ll),
+                ("B", c_i), ("H", c_i), ("T", c_i), ("S", c_i), ("causal", c_i), ("q_pos_off", c_i),
+                ("kpm", c_p), ("head_scale", c_p), ("p_round_bf16", c_i), ("bias", OfaAttnBias)]
+
+
+class OfaAttnGrads(C.Structure):
+    _fields_ = [("dout", c_p), ("dq", c_p), ("dpq", c_p), ("dk", c_p), ("dpk", c_p), ("dv", c_p),
+                ("lddq", c_ll), ("lddpq", c_ll), ("lddk", c_ll), ("lddpk", c_ll), ("lddv", c_ll),
+                ("bsdq", c_ll), ("bsdpq", c_ll), ("bsdk", c_ll), ("bsdpk", c_ll), ("bsdv", c_ll),
+                ("dtok_lut", c_p), ("dimg_lut", c_p), ("delta", c_p), ("P", c_p), ("dS", c_p)]
+
+
+# name -> argtypes, exactly the prototypes of include/ofa_b200.h
+SIGNATURES = {
+    "ofa_abi_version": [],
+    "ofa_gemm_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_p, c_f,
+                      c_i, c_p, c_ll, c_ll, c_p],
+    "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
+    "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
+    "ofa_layernorm_bwd_nparts": [c_i],
+    "ofa_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "ofa_colsum": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p],
+    "ofa_embed_gather": [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p],
+    "ofa_embed_scatter_add": [c_p, c_p, c_ll, c_p, c_i, c_i, c_ll, c_i, c_p],
+    "ofa_add": [c_p, c_p, c_p, c_ll, c_i, c_p],
+    "ofa_mask_rows": [c_p, c_p, c_i, c_i, c_i, c_p],
+    "ofa_gelu": [c_p, c_p, c_p, c_ll, c_i, c_i, c_p],
+    "ofa_ls_ce_fwd_bwd": [c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_i,
+                          c_p],
+    "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p],
+    "ofa_attn_fwd_simt": [C.POINTER(OfaAttnArgs), c_i, c_p],
+    "ofa_attn_bwd_simt": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_i, c_p],
+    "ofa_attn_fwd_tc": [C.POINTER(OfaAttnArgs), c_p],
+}
+
+
+class OfaKernelError(RuntimeError):
+    pass
+
+
+def load(path=None):
+    """Load the shared library (building is `python -m musketeer_b200.build`).  Raises if it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise OfaKernelError(
+            "musketeer_b200: %s not found. Build it with `python -m musketeer_b200.build` "
+            "(there is no CPU / PyTorch fallback for the OFA hot path)." % path)
+    lib = C.CDLL(path)
+    lib.ofa_last_error.restype = C.c_char_p
+    lib.ofa_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = c_i
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise OfaKernelError("%s: %s" % (name, lib.ofa_last_error().decode()))

@@ -1,0 +1,86 @@
+"""AdjustLabelSmoothedCrossEntropyCriterion on the fused loss kernel.
+
+Mirrors criterions/label_smoothed_cross_entropy.py:129-275 (same constructor arguments, `forward(model, sample,
+update_num, reduce)` -> `(loss, sample_size, logging_output)` with the same logging keys, multi-task list recursion
+of :175-202, R-Drop sample duplication of :56-71 incl. the doubled `sample_patch_num`)."""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def construct_rdrop_sample(x):
+    if isinstance(x, dict):
+        return {k: construct_rdrop_sample(v) for k, v in x.items()}
+    if isinstance(x, torch.Tensor):
+        return x.repeat(2, *([1] * (x.dim() - 1)))
+    if isinstance(x, bool) or x is None:
+        return x
+    if isinstance(x, int):
+        return x * 2
+    if isinstance(x, np.ndarray):
+        return x.repeat(2)
+    raise NotImplementedError(type(x))
+
+
+class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
+    def __init__(self, task, sentence_avg=False, label_smoothing=0.0, ignore_prefix_size=0, ignore_eos=False,
+                 report_accuracy=False, drop_worst_ratio=0, drop_worst_after=0, use_rdrop=False, reg_alpha=1.0,
+                 sample_patch_num=196, constraint_range=None):
+        super().__init__()
+        self.task = task
+        self.padding_idx = task.target_dictionary.pad()
+        self.eos_idx = task.target_dictionary.eos()
+        self.sentence_avg = sentence_avg
+        self.eps = label_smoothing
+        self.ignore_prefix_size, self.ignore_eos = ignore_prefix_size, ignore_eos
+        self.report_accuracy = report_accuracy
+        self.drop_worst_ratio, self.drop_worst_after = drop_worst_ratio, drop_worst_after
+        self.use_rdrop, self.reg_alpha = use_rdrop, reg_alpha
+        self.sample_patch_num = sample_patch_num
+        self.constraint_range = None
+        if constraint_range is not None:
+            cs, ce = constraint_range.split(",")
+            self.constraint_range = (int(cs), int(ce))
+
+    def forward(self, model, sample, update_num=0, reduce=True):
+        if isinstance(sample, list) and len(sample) > 1:                               # :175-202
+            if self.sample_patch_num > 0:
+                sample[0]["net_input"]["sample_patch_num"] = self.sample_patch_num
+            loss_v1, ss1, log1 = self.forward(model, sample[0], update_num, reduce)
+            loss_v2, ss2, log2 = self.forward(model, sample[1:], update_num, reduce)
+            loss = loss_v1 / ss1 + loss_v2 / ss2
+            logging_output = {
+                "loss": loss.data, "loss_v1": loss_v1.data, "loss_v2": loss_v2.data,
+                "nll_loss": log1["nll_loss"].data / ss1 + log2["nll_loss"].data / ss2,
+                "ntokens": log1["ntokens"] + log2["ntokens"],
+                "nsentences": log1["nsentences"] + log2["nsentences"],
+                "sample_size": 1, "sample_size_v1": ss1, "sample_size_v2": ss2,
+            }
+            return loss, 1, logging_output
+        sample = sample[0] if isinstance(sample, list) else sample
+        if self.use_rdrop:
+            sample = construct_rdrop_sample(sample)
+        if self.drop_worst_ratio > 0 and update_num > self.drop_worst_after:
+            raise NotImplementedError("drop-worst (after update %d) is not wired into the fused loss yet"
+                                      % self.drop_worst_after)
+        logits, _ = model(**sample["net_input"], padded_logits=True)
+        target = sample["target"]
+        if self.ignore_prefix_size > 0:                                                 # :239-243
+            target = target.clone()
+            target[:, :self.ignore_prefix_size] = self.padding_idx
+        if self.ignore_eos:                                                             # :244-250
+            target = target.masked_fill(target.eq(self.eos_idx), self.padding_idx)
+        ntokens_t = target.ne(self.padding_idx).sum()
+        loss, nll_rows = ops.ls_cross_entropy(
+            logits, target, self.eps, self.padding_idx, cmask=sample.get("constraint_masks"), conf=sample.get("conf"),
+            crange=self.constraint_range, rdrop=self.use_rdrop, reg_alpha=self.reg_alpha)
+        ntokens = int(ntokens_t)          # the reference syncs here too (boolean-mask indexing, :258-260)
+        sample_size = sample["target"].size(0) if self.sentence_avg else ntokens
+        logging_output = {"loss": loss.data, "nll_loss": nll_rows.sum().data, "ntokens": sample["ntokens"],
+                          "nsentences": sample["nsentences"], "sample_size": sample_size}
+        return loss, sample_size, logging_output
+
+    @staticmethod
+    def logging_outputs_can_be_summed():
+        return True

@@ -1,0 +1,501 @@
+// HBM-bound row-wise kernels of the OFA hot path: LayerNorm fwd/bwd (warp-shuffle, 128-bit vectorised, optional
+// fused GELU prologue and residual epilogue), embedding gather / scatter-add, column sums (bias grads), the bf16x3
+// operand split used by the fp32 parity mode, and small elementwise helpers.
+//   reference call sites: fairseq LayerNorm uses in models/ofa/unify_transformer_layer.py:259-283,466-560 and
+//   unify_transformer.py:731-747,898-904,951,1300,1486-1493,1567; embeddings unify_transformer.py:725-744,885,1450,1475.
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+struct Vec8 {};  // 8 elements per thread-vector
+template <>
+struct Vec8<float> {
+  __device__ static void load(const float* p, float (&v)[8]) {
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ static void store(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward.  One warp per row, row cached in registers (NV vectors of 8 per lane), two-pass variance.
+//   y = LN(f(x)) * gamma + beta (+ resid),  f = identity | gelu
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                     const T* __restrict__ beta, const T* __restrict__ resid,
+                                                     T* __restrict__ y, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out, int rows, int C, float eps,
+                                                     int gelu_in) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const T* xr = x + (size_t)row * C;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < C) {
+      Vec8<T>::load(xr + c, v[i]);
+      if (gelu_in) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = gelu_erf(v[i][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < C) {
+      float g[8], b[8], o[8];
+      Vec8<T>::load(gamma + c, g);
+      Vec8<T>::load(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      if (resid) {
+        float r[8];
+        Vec8<T>::load(resid + (size_t)row * C + c, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      Vec8<T>::store(y + (size_t)row * C + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  Persistent CTAs loop over rows; dgamma/dbeta partials stay in registers and are written as
+// [gridDim.x, C] fp32 partials that ln_bwd_reduce_kernel sums.   dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) [* gelu'(x)]
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                     const T* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                     const float* __restrict__ rstd_in, T* __restrict__ dx,
+                                                     float* __restrict__ part_g, float* __restrict__ part_b, int rows,
+                                                     int C, int gelu_in) {
+  // one CTA per row at a time; thread t owns columns (i*128 + t)*8 .. +7 for every row -> param-grad partials need no
+  // cross-thread reduction.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float red[2][2][4];
+  float ag[NV][8], ab[NV][8], gm[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; gm[i][j] = 0.f; }
+    if (c < C) Vec8<T>::load(gamma + c, gm[i]);
+  }
+  int it = 0;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, it ^= 1) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float d[NV][8], raw[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 128 + threadIdx.x) * 8;
+      if (c < C) {
+        Vec8<T>::load(dy + (size_t)row * C + c, d[i]);
+        Vec8<T>::load(x + (size_t)row * C + c, raw[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float fx = gelu_in ? gelu_erf(raw[i][j]) : raw[i][j];
+          const float xh = (fx - mean) * rstd;
+          const float g = d[i][j] * gm[i][j];
+          s1 += g;
+          s2 += g * xh;
+          ag[i][j] += d[i][j] * xh;
+          ab[i][j] += d[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[it][0][warp] = s1; red[it][1][warp] = s2; }
+    __syncthreads();
+    s1 = (red[it][0][0] + red[it][0][1] + red[it][0][2] + red[it][0][3]) / C;
+    s2 = (red[it][1][0] + red[it][1][1] + red[it][1][2] + red[it][1][3]) / C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 128 + threadIdx.x) * 8;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float fx = gelu_in ? gelu_erf(raw[i][j]) : raw[i][j];
+          const float xh = (fx - mean) * rstd;
+          o[j] = rstd * (d[i][j] * gm[i][j] - s1 - xh * s2);
+          if (gelu_in) o[j] *= gelu_grad(raw[i][j]);
+        }
+        Vec8<T>::store(dx + (size_t)row * C + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < C) {
+      float* pg = part_g + (size_t)blockIdx.x * C + c;
+      float* pb = part_b + (size_t)blockIdx.x * C + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { pg[j] = ag[i][j]; pb[j] = ab[i][j]; }
+    }
+  }
+}
+
+template <typename T>
+__global__ void ln_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int nparts,
+                                     int C, T* __restrict__ dgamma, T* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float g = 0.f, b = 0.f;
+  for (int p = 0; p < nparts; ++p) { g += part_g[(size_t)p * C + c]; b += part_b[(size_t)p * C + c]; }
+  dgamma[c] = (T)g;
+  dbeta[c] = (T)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: out[c] = sum_r x[r, c]      (bias gradients)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long ld, int rows, int C,
+                                                             float* __restrict__ part) {
+  // block = 32 columns x 8 row-lanes; grid.x = column tiles, grid.y = row slices
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < C)
+    for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) s += (float)x[(size_t)r * ld + c];
+  __shared__ float red[8][33];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    part[(size_t)blockIdx.y * C + c] = t;
+  }
+}
+template <typename T>
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int C, T* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * C + c];
+  out[c] = (T)s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding gather (+ optional broadcast add vector, e.g. the type embedding row) and scatter-add backward
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_gather_kernel(const long long* __restrict__ idx, const T* __restrict__ table,
+                                    const T* __restrict__ addvec, T* __restrict__ out, long long ldo, int rows, int C) {
+  const int row = blockIdx.x;
+  const T* src = table + (size_t)idx[row] * C;
+  T* dst = out + (size_t)row * ldo;
+  for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+    float v[8];
+    Vec8<T>::load(src + c, v);
+    if (addvec) {
+      float a[8];
+      Vec8<T>::load(addvec + c, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += a[j];
+    }
+    Vec8<T>::store(dst + c, v);
+  }
+}
+__device__ __forceinline__ void atomic_add2(float* p, float a, float b) { atomicAdd(p, a); atomicAdd(p + 1, b); }
+__device__ __forceinline__ void atomic_add2(__nv_bfloat16* p, float a, float b) {
+  atomicAdd(reinterpret_cast<__nv_bfloat162*>(p), __floats2bfloat162_rn(a, b));
+}
+template <typename T>
+__global__ void embed_scatter_add_kernel(const long long* __restrict__ idx, const T* __restrict__ dout, long long ldo,
+                                         T* __restrict__ dtable, int rows, int C, long long skip_idx) {
+  const int row = blockIdx.x;
+  const long long id = idx[row];
+  if (id == skip_idx) return;  // padding_idx rows receive no gradient (nn.Embedding semantics)
+  const T* src = dout + (size_t)row * ldo;
+  T* dst = dtable + (size_t)id * C;
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) atomic_add2(dst + c, (float)src[c], (float)src[c + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> 3-way bf16 split (x = x0 + x1 + x2 to ~2^-24), laid out as 6 blocks for the K-concatenated GEMM:
+//   pattern 0 (A side): x0 x1 x2 x0 x1 x0      pattern 1 (B side): x0 x0 x0 x1 x1 x2
+//   out[blk * blk_stride + r * ldo + c]
+// ------------------------------------------------------------------------------------------------
+__global__ void split3_kernel(const float* __restrict__ x, long long ldx, int rows, int C, __nv_bfloat16* __restrict__ out,
+                              long long ldo, long long blk_stride, int pattern) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * C) return;
+  const int r = (int)(i / C), c = (int)(i % C);
+  const float v = x[(size_t)r * ldx + c];
+  const __nv_bfloat16 h0 = __float2bfloat16(v);
+  const float r1 = v - __bfloat162float(h0);
+  const __nv_bfloat16 h1 = __float2bfloat16(r1);
+  const __nv_bfloat16 h2 = __float2bfloat16(r1 - __bfloat162float(h1));
+  const __nv_bfloat16 pa[6] = {h0, h1, h2, h0, h1, h0};
+  const __nv_bfloat16 pb[6] = {h0, h0, h0, h1, h1, h2};
+  __nv_bfloat16* o = out + (size_t)r * ldo + c;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) o[b * blk_stride] = pattern ? pb[b] : pa[b];
+}
+
+// out = a + b  |  out = a * rowmask (zero padded rows)  -- glue that has no natural producer to fuse into yet
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float x[8], y[8];
+    Vec8<T>::load(a + i, x);
+    Vec8<T>::load(b + i, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    Vec8<T>::store(out + i, x);
+  } else {
+    for (long long k = i; k < n; ++k) out[k] = (T)((float)a[k] + (float)b[k]);
+  }
+}
+template <typename T>
+__global__ void mask_rows_kernel(T* __restrict__ x, const unsigned char* __restrict__ rowmask, int rows, int C) {
+  const int row = blockIdx.x;
+  if (!rowmask[row]) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) x[(size_t)row * C + c] = (T)0.f;
+}
+template <typename T>
+__global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (T)gelu_erf((float)x[i]);
+}
+template <typename T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = (T)((float)dy[i] * gelu_grad((float)x[i]));
+}
+
+template <typename T, int NV>
+int ln_fwd_launch(const void* x, const void* g, const void* b, const void* r, void* y, float* mean, float* rstd,
+                  int rows, int C, float eps, int gelu_in, cudaStream_t st) {
+  ln_fwd_kernel<T, NV><<<(rows + 3) / 4, 128, 0, st>>>((const T*)x, (const T*)g, (const T*)b, (const T*)r, (T*)y, mean,
+                                                       rstd, rows, C, eps, gelu_in);
+  OFA_LAUNCH_CHECK("ln_fwd_kernel");
+  return 0;
+}
+template <typename T, int NV>
+int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mean, const float* rstd, void* dx,
+                  float* pg, float* pb, int nparts, int rows, int C, int gelu_in, cudaStream_t st) {
+  ln_bwd_kernel<T, NV><<<nparts, 128, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows,
+                                               C, gelu_in);
+  OFA_LAUNCH_CHECK("ln_bwd_kernel");
+  return 0;
+}
+
+}  // namespace
+
+#define DISPATCH_NV(NVV, CALL)                                  \
+  switch (NVV) {                                                \
+    case 1: { constexpr int NV = 1; return CALL; }              \
+    case 2: { constexpr int NV = 2; return CALL; }              \
+    case 3: { constexpr int NV = 3; return CALL; }              \
+    case 4: { constexpr int NV = 4; return CALL; }              \
+    case 5: case 6: { constexpr int NV = 6; return CALL; }      \
+    case 7: case 8: { constexpr int NV = 8; return CALL; }      \
+    case 9: case 10: case 11: case 12: { constexpr int NV = 12; return CALL; } \
+    case 13: case 14: case 15: case 16: { constexpr int NV = 16; return CALL; } \
+    default: return ofa_set_error("layernorm: C=%d too wide (max 4096)", C); \
+  }
+
+#define DISPATCH_NV_BWD(NVV, CALL)                              \
+  switch (NVV) {                                                \
+    case 1: { constexpr int NV = 1; return CALL; }              \
+    case 2: { constexpr int NV = 2; return CALL; }              \
+    case 3: { constexpr int NV = 3; return CALL; }              \
+    case 4: { constexpr int NV = 4; return CALL; }              \
+    default: return ofa_set_error("layernorm bwd: C=%d too wide (max 4096)", C); \
+  }
+
+extern "C" int ofa_layernorm_fwd(const void* x, const void* gamma, const void* beta, const void* resid, void* y,
+                                 float* mean, float* rstd, int rows, int C, float eps, int gelu_in, int dtype,
+                                 void* stream) {
+  OFA_CHECK(rows > 0 && C > 0 && C % 8 == 0, "ofa_layernorm_fwd: rows=%d C=%d (C must be a multiple of 8)", rows, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = (C + 255) / 256;
+  if (dtype == OFA_BF16) {
+    DISPATCH_NV(nv, (ln_fwd_launch<__nv_bfloat16, NV>(x, gamma, beta, resid, y, mean, rstd, rows, C, eps, gelu_in, st)))
+  } else if (dtype == OFA_F32) {
+    DISPATCH_NV(nv, (ln_fwd_launch<float, NV>(x, gamma, beta, resid, y, mean, rstd, rows, C, eps, gelu_in, st)))
+  }
+  return ofa_set_error("ofa_layernorm_fwd: bad dtype %d", dtype);
+}
+
+extern "C" int ofa_layernorm_bwd_nparts(int rows) {
+  return rows < 592 ? rows : 592;  // 4 CTAs per SM on 148 SMs
+}
+
+extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+                                 const float* rstd, void* dx, void* dgamma, void* dbeta, float* workspace, int rows,
+                                 int C, int gelu_in, int dtype, void* stream) {
+  OFA_CHECK(rows > 0 && C > 0 && C % 8 == 0, "ofa_layernorm_bwd: rows=%d C=%d", rows, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nparts = ofa_layernorm_bwd_nparts(rows);
+  float* pg = workspace;
+  float* pb = workspace + (size_t)nparts * C;  // workspace: 2 * nparts * C floats
+  const int nv = (C + 1023) / 1024;
+  int rc = 1;
+  if (dtype == OFA_BF16) {
+    rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<__nv_bfloat16, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
+    if (rc) return rc;
+    ln_bwd_reduce_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+  } else if (dtype == OFA_F32) {
+    rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<float, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
+    if (rc) return rc;
+    ln_bwd_reduce_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta);
+  } else {
+    return ofa_set_error("ofa_layernorm_bwd: bad dtype %d", dtype);
+  }
+  OFA_LAUNCH_CHECK("ln_bwd_reduce_kernel");
+  return 0;
+}
+
+extern "C" int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace, int dtype,
+                          void* stream) {
+  OFA_CHECK(rows > 0 && C > 0, "ofa_colsum: rows=%d C=%d", rows, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  int ny = (rows + 63) / 64;
+  if (ny > 64) ny = 64;  // workspace: 64 * C floats
+  dim3 grid((C + 31) / 32, ny);
+  if (dtype == OFA_BF16) {
+    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, workspace);
+    colsum_final_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (__nv_bfloat16*)out);
+  } else if (dtype == OFA_F32) {
+    colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, C, workspace);
+    colsum_final_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (float*)out);
+  } else {
+    return ofa_set_error("ofa_colsum: bad dtype %d", dtype);
+  }
+  OFA_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+extern "C" int ofa_embed_gather(const long long* idx, const void* table, const void* addvec, void* out, long long ldo,
+                                int rows, int C, int dtype, void* stream) {
+  OFA_CHECK(rows > 0 && C % 8 == 0, "ofa_embed_gather: rows=%d C=%d", rows, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == OFA_BF16)
+    embed_gather_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(idx, (const __nv_bfloat16*)table, (const __nv_bfloat16*)addvec, (__nv_bfloat16*)out, ldo, rows, C);
+  else if (dtype == OFA_F32)
+    embed_gather_kernel<float><<<rows, 128, 0, st>>>(idx, (const float*)table, (const float*)addvec, (float*)out, ldo, rows, C);
+  else
+    return ofa_set_error("ofa_embed_gather: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("embed_gather_kernel");
+  return 0;
+}
+
+extern "C" int ofa_embed_scatter_add(const long long* idx, const void* dout, long long ldo, void* dtable, int rows,
+                                     int C, long long skip_idx, int dtype, void* stream) {
+  OFA_CHECK(rows > 0 && C % 2 == 0, "ofa_embed_scatter_add: rows=%d C=%d", rows, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == OFA_BF16)
+    embed_scatter_add_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(idx, (const __nv_bfloat16*)dout, ldo, (__nv_bfloat16*)dtable, rows, C, skip_idx);
+  else if (dtype == OFA_F32)
+    embed_scatter_add_kernel<float><<<rows, 128, 0, st>>>(idx, (const float*)dout, ldo, (float*)dtable, rows, C, skip_idx);
+  else
+    return ofa_set_error("ofa_embed_scatter_add: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("embed_scatter_add_kernel");
+  return 0;
+}
+
+extern "C" int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, long long ldo,
+                               long long blk_stride, int pattern, void* stream) {
+  OFA_CHECK(rows > 0 && C > 0, "ofa_split3_bf16: rows=%d C=%d", rows, C);
+  const long long n = (long long)rows * C;
+  split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, (__nv_bfloat16*)out, ldo, blk_stride, pattern);
+  OFA_LAUNCH_CHECK("split3_kernel");
+  return 0;
+}
+
+extern "C" int ofa_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
+  OFA_CHECK(n > 0, "ofa_add: n=%lld", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n + 2047) / 2048);
+  if (dtype == OFA_BF16) add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
+  else if (dtype == OFA_F32) add_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n);
+  else return ofa_set_error("ofa_add: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("add_kernel");
+  return 0;
+}
+
+extern "C" int ofa_mask_rows(void* x, const unsigned char* rowmask, int rows, int C, int dtype, void* stream) {
+  OFA_CHECK(rows > 0 && C > 0, "ofa_mask_rows: rows=%d C=%d", rows, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == OFA_BF16) mask_rows_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>((__nv_bfloat16*)x, rowmask, rows, C);
+  else if (dtype == OFA_F32) mask_rows_kernel<float><<<rows, 128, 0, st>>>((float*)x, rowmask, rows, C);
+  else return ofa_set_error("ofa_mask_rows: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("mask_rows_kernel");
+  return 0;
+}
+
+extern "C" int ofa_gelu(const void* x, const void* dy, void* out, long long n, int backward, int dtype, void* stream) {
+  OFA_CHECK(n > 0, "ofa_gelu: n=%lld", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == OFA_BF16) {
+    if (backward) gelu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)out, n);
+    else gelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n);
+  } else if (dtype == OFA_F32) {
+    if (backward) gelu_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)dy, (float*)out, n);
+    else gelu_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, n);
+  } else return ofa_set_error("ofa_gelu: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("gelu_kernel");
+  return 0;
+}

@@ -1,0 +1,622 @@
+"""B200-native OFA model: a drop-in for the reference's fairseq `ofa` model (models/ofa/ofa.py:25-171,
+models/ofa/unify_transformer.py:126-1745) whose forward/backward runs on the kernels of libofa_b200.so.
+
+Contract kept from the reference:
+  * `OFAModel.build_model(args, task)`, `forward(src_tokens, src_lengths, prev_output_tokens, patch_images, ...)`
+    -> `(logits [B,T,V], {"attn": [...], "inner_states": [...]})`, `.encoder(...)` -> dict of lists
+    (`encoder_out [N,B,d]`, `encoder_padding_mask [B,N]`, `position_embeddings [B,N,d]`, ...), `.decoder(...)`,
+    `reorder_encoder_out`, `get_normalized_probs`, `get_targets`, `max_positions`, `max_decoder_positions`,
+    `enc_timer/dec_timer/cls_timer` attributes (never synchronised here).
+  * state_dict keys / shapes / order identical to the reference (tests/golden/state_dict_spec.json), tied embedding.
+nn.Linear / nn.LayerNorm / nn.Embedding objects below are parameter holders only -- their torch forward is never
+called; arithmetic goes through `musketeer_b200.ops`.  Internally activations are batch-first [B, L, d].
+"""
+import math
+import random
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .resnet import ResNetStem
+
+DEFAULT_MAX_SOURCE_POSITIONS = 1024
+DEFAULT_MAX_TARGET_POSITIONS = 1024
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# integer tables (bit-exact restatements of unify_transformer.py:53-81; verified in tests against the reference dump)
+# ---------------------------------------------------------------------------------------------------------------------
+def make_token_bucket_position(bucket_size, max_position=DEFAULT_MAX_SOURCE_POSITIONS):
+    ctx = torch.arange(max_position, dtype=torch.long)[:, None]
+    mem = torch.arange(max_position, dtype=torch.long)[None, :]
+    rel = ctx - mem
+    sign = torch.sign(rel)
+    mid = bucket_size // 2
+    abs_pos = torch.where((rel < mid) & (rel > -mid), mid - 1, torch.abs(rel))
+    log_pos = torch.ceil(torch.log(abs_pos / mid) / math.log((max_position - 1) / mid) * (mid - 1)) + mid
+    log_pos = log_pos.int()
+    bucket = torch.where(abs_pos.le(mid), rel, log_pos * sign).long()
+    return bucket + bucket_size - 1
+
+
+def make_image_bucket_position(bucket_size, num_relative_distance):
+    n = bucket_size * bucket_size
+    r = torch.arange(n) // bucket_size
+    c = torch.arange(n) % bucket_size
+    t = torch.zeros(n + 1, n + 1, dtype=torch.long)
+    t[1:, 1:] = (r[:, None] - r[None, :] + bucket_size - 1) * (2 * bucket_size - 1) + \
+                (c[:, None] - c[None, :] + bucket_size - 1)
+    t[0, :] = num_relative_distance - 3
+    t[:, 0] = num_relative_distance - 2
+    t[0, 0] = num_relative_distance - 1
+    return t
+
+
+def Embedding(num_embeddings, embedding_dim, padding_idx=None, zero_init=False):
+    m = nn.Embedding(num_embeddings, embedding_dim, padding_idx=padding_idx)
+    nn.init.normal_(m.weight, mean=0, std=embedding_dim ** -0.5)
+    if padding_idx is not None:
+        nn.init.constant_(m.weight[padding_idx], 0)
+    if zero_init:
+        nn.init.constant_(m.weight, 0)
+    return m
+
+
+def Linear(in_features, out_features, bias=True):
+    m = nn.Linear(in_features, out_features, bias)
+    nn.init.xavier_uniform_(m.weight)
+    if bias:
+        nn.init.constant_(m.bias, 0.0)
+    return m
+
+
+def init_bert_params(module):
+    """fairseq init_bert_params (un-vendored): N(0, 0.02) Linear/Embedding weights, zero biases / pad row (ofa.py:33)."""
+    if isinstance(module, nn.Linear):
+        module.weight.data.normal_(mean=0.0, std=0.02)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    if isinstance(module, nn.Embedding):
+        module.weight.data.normal_(mean=0.0, std=0.02)
+        if module.padding_idx is not None:
+            module.weight.data[module.padding_idx].zero_()
+
+
+def _lin(mod, x, alpha=1.0, resid=None):
+    return ops.linear(x, mod.weight, mod.bias, alpha, resid)
+
+
+def _ln(mod, x, resid=None, gelu_in=False):
+    return ops.layer_norm(x, mod.weight, mod.bias, resid, gelu_in, mod.eps)
+
+
+def _unsupported(args, names):
+    for n in names:
+        if getattr(args, n, False):
+            raise NotImplementedError("musketeer_b200 OFA: option --%s is outside the hot-path scope (SURVEY.md 8)" %
+                                      n.replace("_", "-"))
+
+
+class MultiheadAttention(nn.Module):
+    """Parameter holder + call into ops.attention (unify_multihead_attention.py:20-409)."""
+
+    def __init__(self, embed_dim, num_heads, scale_factor=2.0, scale_heads=False, self_attention=False,
+                 encoder_decoder_attention=False):
+        super().__init__()
+        self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.head_dim = embed_dim // num_heads
+        if self.head_dim != 64:
+            raise NotImplementedError("attention kernels are built for head_dim 64 (all OFA archs but ofa_huge)")
+        self.scaling = float(self.head_dim * scale_factor) ** -0.5
+        self.self_attention, self.encoder_decoder_attention = self_attention, encoder_decoder_attention
+        self.c_attn = nn.Parameter(torch.ones((num_heads,)), requires_grad=True) if scale_heads else None
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+
+    def project_kv(self, key):
+        return _lin(self.k_proj, key), _lin(self.v_proj, key)
+
+    def forward(self, query, k, v, pq, pk, tok_lut, img_lut, cfg):
+        q = _lin(self.q_proj, query, alpha=self.scaling)
+        cfg = dict(cfg)
+        cfg["H"] = self.num_heads
+        return ops.attention(q, pq, k, pk, v, tok_lut, img_lut, self.c_attn, cfg)
+
+
+class _FFNMixin:
+    def _ffn(self, x):
+        r = x
+        u = _lin(self.fc1, _ln(self.final_layer_norm, x))
+        if self.ffn_layernorm is not None:
+            g = _ln(self.ffn_layernorm, u, gelu_in=True)   # GELU fused into the LN prologue
+        else:
+            g = ops.gelu(u)
+        return _lin(self.fc2, g, resid=r)                  # residual fused into the GEMM epilogue
+
+
+class TransformerEncoderLayer(nn.Module, _FFNMixin):
+    """unify_transformer_layer.py:110-293 (pre-LN; dropout / drop-path probabilities must be 0 in this round)."""
+
+    def __init__(self, args, drop_path_rate=0.0):
+        super().__init__()
+        d = args.encoder_embed_dim
+        self.self_attn = MultiheadAttention(d, args.encoder_attention_heads, args.attn_scale_factor,
+                                            getattr(args, "scale_heads", False), self_attention=True)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, args.encoder_ffn_embed_dim)
+        self.fc2 = nn.Linear(args.encoder_ffn_embed_dim, d)
+        self.attn_ln = nn.LayerNorm(d) if getattr(args, "scale_attn", False) else None
+        self.ffn_layernorm = nn.LayerNorm(args.encoder_ffn_embed_dim) if getattr(args, "scale_fc", False) else None
+        self.final_layer_norm = nn.LayerNorm(d)
+        self.drop_path_rate = drop_path_rate
+
+    def forward(self, x, pq, pk, tok_lut, img_lut, cfg):
+        h = _ln(self.self_attn_layer_norm, x)
+        k, v = self.self_attn.project_kv(h)
+        o = self.self_attn(h, k, v, pq, pk, tok_lut, img_lut, cfg)
+        if self.attn_ln is not None:
+            x = _ln(self.attn_ln, _lin(self.self_attn.out_proj, o), resid=x)
+        else:
+            x = _lin(self.self_attn.out_proj, o, resid=x)
+        return self._ffn(x)
+
+
+class TransformerDecoderLayer(nn.Module, _FFNMixin):
+    """unify_transformer_layer.py:296-582."""
+
+    def __init__(self, args, drop_path_rate=0.0):
+        super().__init__()
+        d = args.decoder_embed_dim
+        H = args.decoder_attention_heads
+        sh = getattr(args, "scale_heads", False)
+        self.self_attn = MultiheadAttention(d, H, args.attn_scale_factor, sh, self_attention=True)
+        sa = getattr(args, "scale_attn", False)
+        self.self_attn_ln = nn.LayerNorm(d) if sa else None
+        self.cross_attn_ln = nn.LayerNorm(d) if sa else None
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.encoder_attn = MultiheadAttention(d, H, args.attn_scale_factor, sh, encoder_decoder_attention=True)
+        self.encoder_attn_layer_norm = nn.LayerNorm(d)
+        self.ffn_layernorm = nn.LayerNorm(args.decoder_ffn_embed_dim) if getattr(args, "scale_fc", False) else None
+        self.fc1 = nn.Linear(d, args.decoder_ffn_embed_dim)
+        self.fc2 = nn.Linear(args.decoder_ffn_embed_dim, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+        self.drop_path_rate = drop_path_rate
+
+    def forward(self, x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg):
+        h = _ln(self.self_attn_layer_norm, x)
+        k, v = self_kv(self.self_attn, h)
+        o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg)
+        if self.self_attn_ln is not None:
+            x = _ln(self.self_attn_ln, _lin(self.self_attn.out_proj, o), resid=x)
+        else:
+            x = _lin(self.self_attn.out_proj, o, resid=x)
+        h = _ln(self.encoder_attn_layer_norm, x)
+        k, v = cross_kv(self.encoder_attn)
+        o = self.encoder_attn(h, k, v, cpq, cpk, None, None, cross_cfg)
+        if self.cross_attn_ln is not None:
+            x = _ln(self.cross_attn_ln, _lin(self.encoder_attn.out_proj, o), resid=x)
+        else:
+            x = _lin(self.encoder_attn.out_proj, o, resid=x)
+        return self._ffn(x)
+
+
+def _rel_bucket_1d(token_rp_bucket):
+    """bucket as a function of (i - j) only: index rel + 1023 for rel in [-1023, 1023]."""
+    n = token_rp_bucket.shape[0]
+    neg = token_rp_bucket[0, 1:].flip(0)      # rel = -(n-1) .. -1
+    pos = token_rp_bucket[:, 0]               # rel = 0 .. n-1
+    return torch.cat([neg, pos]).contiguous()
+
+
+def _tok_lut(table_weight, rel_bucket_1d):
+    return table_weight.index_select(0, rel_bucket_1d).t().float().contiguous()      # [H, 2n-1]
+
+
+def _img_lut(table_weight):
+    return table_weight.t().float().contiguous()                                     # [H, n_rel]
+
+
+class TransformerEncoder(nn.Module):
+    """unify_transformer.py:493-1072."""
+
+    def __init__(self, args, dictionary, embed_tokens):
+        super().__init__()
+        self.args = args
+        self.dictionary = dictionary
+        _unsupported(args, ["encoder_prompt", "adapter", "bitfit", "sync_bn", "interpolate_position",
+                            "entangle_position_embedding", "scale_resids"])
+        if args.dropout or args.attention_dropout or args.encoder_drop_path_rate or args.resnet_drop_path_rate:
+            raise NotImplementedError("dropout / drop-path > 0 is not wired into the fused epilogues yet "
+                                      "(parity and benchmark configs run with p = 0; DESIGN.md)")
+        self.register_buffer("version", torch.Tensor([3]))
+        d = embed_tokens.embedding_dim
+        self.padding_idx = embed_tokens.padding_idx
+        self.max_source_positions = args.max_source_positions
+        self.num_attention_heads = args.encoder_attention_heads
+        self.embed_tokens = embed_tokens
+        self.embed_scale = 1.0 if args.no_scale_embedding else math.sqrt(d)
+        if self.embed_scale != 1.0:
+            raise NotImplementedError("OFA archs set no_scale_embedding (ofa.py:405)")
+        self.layernorm_embedding = nn.LayerNorm(d) if getattr(args, "layernorm_embedding", False) else None
+        self.type_embedding = Embedding(2, d, padding_idx=None) if getattr(args, "add_type_embedding", False) else None
+        self.embed_images = ResNetStem(args.resnet_type, frozen_bn=getattr(args, "freeze_resnet", False))
+        self.image_proj = Linear(1024, d)
+        self.patch_layernorm_embedding = nn.LayerNorm(d) if getattr(args, "patch_layernorm_embedding", False) else None
+        self.embed_positions = Embedding(args.max_source_positions + 2, d)
+        self.embed_image_positions = Embedding(args.image_bucket_size ** 2 + 1, d)
+        self.pos_ln = nn.LayerNorm(d)
+        self.image_pos_ln = nn.LayerNorm(d)
+        self.pos_scaling = float(d / args.encoder_attention_heads * args.attn_scale_factor) ** -0.5
+        self.pos_q_linear = nn.Linear(d, d)
+        self.pos_k_linear = nn.Linear(d, d)
+        dpr = [x.item() for x in torch.linspace(0, args.encoder_drop_path_rate, args.encoder_layers)]
+        self.layers = nn.ModuleList([TransformerEncoderLayer(args, dpr[i]) for i in range(args.encoder_layers)])
+        self.num_layers = len(self.layers)
+        self.layer_norm = nn.LayerNorm(d) if args.encoder_normalize_before else None
+        if self.layer_norm is None:
+            raise NotImplementedError("post-LN encoders are outside the Musketeer flag set")
+        n_tok = 2 * args.token_bucket_size - 1
+        self.token_rel_pos_table_list = nn.ModuleList(
+            [Embedding(n_tok, self.num_attention_heads, zero_init=True) for _ in range(args.encoder_layers)])
+        n_img = (2 * args.image_bucket_size - 1) ** 2 + 3
+        self.image_rel_pos_table_list = nn.ModuleList(
+            [Embedding(n_img, self.num_attention_heads, zero_init=True) for _ in range(args.encoder_layers)])
+        self.patch_image_size = getattr(args, "patch_image_size", 384)
+        self.orig_patch_image_size = getattr(args, "orig_patch_image_size", 256)
+        self.register_buffer("token_rp_bucket", make_token_bucket_position(args.token_bucket_size))
+        self.register_buffer("image_rp_bucket", make_image_bucket_position(args.image_bucket_size, n_img))
+        self._rel1d = None
+        self.patch_orders_override = None   # tests: fix the random patch subset (reference uses python `random`)
+
+    def rel_bucket_1d(self):
+        if self._rel1d is None or self._rel1d.device != self.token_rp_bucket.device:
+            self._rel1d = _rel_bucket_1d(self.token_rp_bucket)
+        return self._rel1d
+
+    def get_patch_images_info(self, patch_images, sample_patch_num, device):
+        feat = self.embed_images(patch_images)                        # [B, h*w, 1024] (NHWC-flattened)
+        B = patch_images.size(0)
+        h, w = self.embed_images.last_hw
+        P = h * w
+        pid = (torch.arange(w, device=device).unsqueeze(0).expand(h, w) +
+               torch.arange(h, device=device).unsqueeze(1) * self.args.image_bucket_size + 1).reshape(-1)
+        pid = pid[None, :].expand(B, P)
+        pad = torch.zeros(B, P, dtype=torch.bool, device=device)
+        if sample_patch_num is not None:                              # unify_transformer.py:671-682
+            if self.patch_orders_override is not None:
+                orders = self.patch_orders_override.to(device)
+            else:
+                orders = torch.LongTensor([random.sample(range(P), k=sample_patch_num) for _ in range(B)]).to(device)
+            feat = feat.gather(1, orders.unsqueeze(2).expand(-1, -1, feat.size(2)))
+            P = sample_patch_num
+            pad = pad.gather(1, orders)
+            pid = pid.gather(1, orders)
+        return feat.contiguous(), P, pad, pid.contiguous()
+
+    def forward(self, src_tokens, src_lengths=None, patch_images=None, patch_images_2=None, patch_masks=None,
+                code_masks=None, return_all_hiddens=False, token_embeddings=None, sample_patch_num=None):
+        if patch_images_2 is not None or token_embeddings is not None:
+            raise NotImplementedError("patch_images_2 / token_embeddings are outside the hot-path scope")
+        dev = src_tokens.device
+        B, S = src_tokens.shape
+        d, H = self.embed_tokens.embedding_dim, self.num_attention_heads
+        w = self.embed_tokens.weight
+        P, pid = 0, None
+        pad_mask = src_tokens.eq(self.padding_idx)
+        type_w = self.type_embedding.weight if self.type_embedding is not None else None
+        # text embedding (+ type 0) -> LN                                            unify_transformer.py:725-733
+        x = ops.embedding(src_tokens, w, type_w[0] if type_w is not None else None, self.padding_idx)
+        if self.layernorm_embedding is not None:
+            x = _ln(self.layernorm_embedding, x)
+        pos = ops.embedding(torch.arange(S, device=dev), self.embed_positions.weight)        # [S, d]   :885
+        pos = _ln(self.pos_ln, pos).unsqueeze(0).expand(B, S, d)                             # :898
+        if patch_images is not None:
+            feat, P, img_pad, pid = self.get_patch_images_info(patch_images, sample_patch_num, dev)
+            img_pad = img_pad | (~patch_masks)[:, None]                                      # :872
+            bias = self.image_proj.bias + type_w[1] if type_w is not None else self.image_proj.bias
+            xi = ops.linear(feat.to(w.dtype), self.image_proj.weight, bias)                  # :739-744
+            if self.patch_layernorm_embedding is not None:
+                xi = _ln(self.patch_layernorm_embedding, xi)
+            x = torch.cat([xi, x], dim=1)
+            pad_mask = torch.cat([img_pad, pad_mask], dim=1)
+            ipos = _ln(self.image_pos_ln, ops.embedding(pid, self.embed_image_positions.weight))   # :695,900
+            pos = torch.cat([ipos, pos], dim=1)
+        pos = pos.contiguous()
+        x = ops.mask_rows(x, pad_mask)                                                       # :892-893
+        pq = _lin(self.pos_q_linear, pos, alpha=self.pos_scaling)                            # :906-911
+        pk = _lin(self.pos_k_linear, pos)
+        kpm = pad_mask.contiguous().view(torch.uint8)
+        cfg = {"causal": False, "kpm": kpm,
+               "bias": {"q_text_off": P, "k_text_off": P, "ibs": self.args.image_bucket_size,
+                        "q_pid": pid.int().contiguous() if pid is not None else None,
+                        "k_pid": None, "n_img_q": P, "n_img_k": P}}
+        cfg["bias"]["k_pid"] = cfg["bias"]["q_pid"]
+        rel1d = self.rel_bucket_1d()
+        states = []
+        for i, layer in enumerate(self.layers):
+            tok_lut = _tok_lut(self.token_rel_pos_table_list[i].weight, rel1d)
+            img_lut = _img_lut(self.image_rel_pos_table_list[i].weight) if P else None
+            x = layer(x, pq, pk, tok_lut, img_lut, cfg)
+            if return_all_hiddens:
+                states.append(x.transpose(0, 1))
+        x = _ln(self.layer_norm, x)
+        return {
+            "encoder_out": [x.transpose(0, 1)],            # T x B x C (view; the reference layout)
+            "encoder_padding_mask": [pad_mask],            # B x T
+            "encoder_embedding": [],
+            "encoder_states": states,
+            "src_tokens": [],
+            "src_lengths": [],
+            "position_embeddings": [pos],                  # B x T x C
+        }
+
+    def forward_torchscript(self, net_input):
+        return self.forward(**{k: v for k, v in net_input.items() if k != "prev_output_tokens"})
+
+    def reorder_encoder_out(self, encoder_out, new_order):
+        out = {}
+        for k, dim in (("encoder_out", 1), ("encoder_padding_mask", 0), ("encoder_embedding", 0), ("src_tokens", 0),
+                       ("src_lengths", 0), ("position_embeddings", 0)):
+            out[k] = [encoder_out[k][0].index_select(dim, new_order)] if len(encoder_out[k]) else []
+        out["encoder_states"] = [s.index_select(1, new_order) for s in encoder_out["encoder_states"]]
+        return out
+
+    def max_positions(self):
+        return self.max_source_positions
+
+
+class TransformerDecoder(nn.Module):
+    """unify_transformer.py:1075-1659."""
+
+    def __init__(self, args, dictionary, embed_tokens, no_encoder_attn=False):
+        super().__init__()
+        self.args = args
+        self.dictionary = dictionary
+        _unsupported(args, ["decoder_prompt", "adapter", "cross_self_attention", "no_cross_attention"])
+        if args.decoder_drop_path_rate:
+            raise NotImplementedError("drop-path > 0 is not wired into the fused epilogues yet")
+        self.register_buffer("version", torch.Tensor([3]))
+        d = args.decoder_embed_dim
+        self.embed_dim = d
+        self.num_attention_heads = args.decoder_attention_heads
+        self.padding_idx = embed_tokens.padding_idx
+        self.max_target_positions = args.max_target_positions
+        self.embed_tokens = embed_tokens
+        self.layernorm_embedding = nn.LayerNorm(d) if getattr(args, "layernorm_embedding", False) else None
+        self.window_size = args.code_image_size // 8
+        self.embed_positions = Embedding(args.max_target_positions + 2, d)
+        self.embed_image_positions = Embedding(args.image_bucket_size ** 2 + 1, d)
+        self.pos_ln = nn.LayerNorm(d)
+        self.image_pos_ln = nn.LayerNorm(d)
+        self.pos_scaling = float(d / self.num_attention_heads * args.attn_scale_factor) ** -0.5
+        self.self_pos_q_linear = nn.Linear(d, d)
+        self.self_pos_k_linear = nn.Linear(d, d)
+        self.cross_pos_q_linear = nn.Linear(d, d)
+        self.cross_pos_k_linear = nn.Linear(d, d)
+        self.code_layernorm_embedding = nn.LayerNorm(d) if getattr(args, "code_layernorm_embedding", False) else None
+        dpr = [x.item() for x in torch.linspace(0, args.decoder_drop_path_rate, args.decoder_layers)]
+        self.layers = nn.ModuleList([TransformerDecoderLayer(args, dpr[i]) for i in range(args.decoder_layers)])
+        self.num_layers = len(self.layers)
+        self.layer_norm = nn.LayerNorm(d) if args.decoder_normalize_before else None
+        if self.layer_norm is None:
+            raise NotImplementedError("post-LN decoders are outside the Musketeer flag set")
+        self.output_projection = nn.Linear(d, embed_tokens.weight.shape[0], bias=False)
+        self.output_projection.weight = self.embed_tokens.weight            # :1248-1254 (tied)
+        n_tok = 2 * args.token_bucket_size - 1
+        self.token_rel_pos_table_list = nn.ModuleList(
+            [Embedding(n_tok, self.num_attention_heads, zero_init=True) for _ in range(args.decoder_layers)])
+        n_img = (2 * args.image_bucket_size - 1) ** 2 + 3
+        ws = self.window_size
+        ipi = torch.arange(ws).unsqueeze(0).expand(ws, ws) + torch.arange(ws).unsqueeze(1) * args.image_bucket_size + 1
+        ipi = torch.cat([torch.tensor([0]), ipi.reshape(-1)])
+        ipi = torch.cat([ipi, torch.tensor([1024] * 769)])
+        self.image_rel_pos_table_list = nn.ModuleList(
+            [Embedding(n_img, self.num_attention_heads, zero_init=True) for _ in range(args.decoder_layers)])
+        self.register_buffer("token_rp_bucket", make_token_bucket_position(args.token_bucket_size))
+        self.register_buffer("image_rp_bucket", make_image_bucket_position(args.image_bucket_size, n_img))
+        self.register_buffer("image_position_idx", ipi)
+        self._rel1d = None
+
+    def rel_bucket_1d(self):
+        if self._rel1d is None or self._rel1d.device != self.token_rp_bucket.device:
+            self._rel1d = _rel_bucket_1d(self.token_rp_bucket)
+        return self._rel1d
+
+    def forward(self, prev_output_tokens, code_masks=None, encoder_out=None, incremental_state=None,
+                features_only=False, full_context_alignment=False, alignment_layer=None, alignment_heads=None,
+                src_lengths=None, return_all_hiddens=False, padded_logits=False):
+        x, extra = self.extract_features(prev_output_tokens, code_masks, encoder_out, incremental_state,
+                                         full_context_alignment)
+        if not features_only:
+            x = self.output_layer(x, padded=padded_logits)
+        return x, extra
+
+    def extract_features(self, prev_output_tokens, code_masks=None, encoder_out=None, incremental_state=None,
+                         full_context_alignment=False, alignment_layer=None, alignment_heads=None):
+        if code_masks is not None and bool(torch.any(code_masks)):
+            raise NotImplementedError("image-code targets (code_masks) are outside the hot-path scope")
+        if full_context_alignment:
+            raise NotImplementedError("full_context_alignment is outside the hot-path scope")
+        dev = prev_output_tokens.device
+        B, T = prev_output_tokens.shape
+        d, H = self.embed_dim, self.num_attention_heads
+        enc = encoder_out["encoder_out"][0].transpose(0, 1)                     # [B, N, d]
+        if not enc.is_contiguous():
+            enc = enc.contiguous()
+        enc_pad = encoder_out["encoder_padding_mask"][0]
+        src_pos = encoder_out["position_embeddings"][0]
+        incremental = incremental_state is not None
+        t0 = T - 1 if incremental else 0                                        # first query position
+        Tq = T - t0
+        # position embeddings; in incremental mode only the last row is needed for the queries, while the self-attention
+        # pos_k of earlier steps lives in the cache (the reference recomputes the whole prefix: :1449-1472)
+        tpe = ops.embedding(torch.arange(t0, T, device=dev), self.embed_positions.weight)      # [Tq, d]
+        tp = _ln(self.pos_ln, tpe).unsqueeze(0).expand(B, Tq, d).contiguous()
+        spq = _lin(self.self_pos_q_linear, tp, alpha=self.pos_scaling)
+        spk_new = _lin(self.self_pos_k_linear, tp)
+        cpq = _lin(self.cross_pos_q_linear, tp, alpha=self.pos_scaling)
+        toks = prev_output_tokens[:, t0:]
+        x = ops.embedding(toks.contiguous(), self.embed_tokens.weight, None, self.padding_idx)
+        if not self.args.disable_entangle:                                                     # :1483-1484
+            x = ops.add(x, tpe.unsqueeze(0).expand(B, Tq, d).contiguous())
+        if self.layernorm_embedding is not None:
+            x = _ln(self.layernorm_embedding, x)
+        if incremental:
+            st = incremental_state.setdefault("_ofa_b200", {})
+            if "cpk" not in st or st.get("enc_id") is not enc_pad:
+                st.clear()
+                st["enc_id"] = enc_pad
+                st["cpk"] = _lin(self.cross_pos_k_linear, src_pos.contiguous())
+                st["cross"] = [layer.encoder_attn.project_kv(enc) for layer in self.layers]
+                st["self_k"] = [None] * self.num_layers
+                st["self_v"] = [None] * self.num_layers
+                st["spk"] = None
+            cpk = st["cpk"]
+            st["spk"] = spk_new if st["spk"] is None else torch.cat([st["spk"], spk_new], dim=1)
+            spk = st["spk"]
+            self_kpm = None
+        else:
+            cpk = _lin(self.cross_pos_k_linear, src_pos.contiguous())
+            spk = spk_new
+            self_kpm = prev_output_tokens.eq(self.padding_idx).contiguous().view(torch.uint8)
+        rel1d = self.rel_bucket_1d()
+        self_cfg = {"causal": True, "kpm": self_kpm, "q_pos_off": t0,
+                    "bias": {"q_text_off": 0, "k_text_off": 0}}
+        cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}}
+        inner_states = [x.transpose(0, 1)]
+        for i, layer in enumerate(self.layers):
+            tok_lut = _tok_lut(self.token_rel_pos_table_list[i].weight, rel1d)
+
+            def self_kv(attn, h, i=i):
+                k, v = attn.project_kv(h)
+                if incremental:
+                    st = incremental_state["_ofa_b200"]
+                    st["self_k"][i] = k if st["self_k"][i] is None else torch.cat([st["self_k"][i], k], dim=1)
+                    st["self_v"][i] = v if st["self_v"][i] is None else torch.cat([st["self_v"][i], v], dim=1)
+                    return st["self_k"][i], st["self_v"][i]
+                return k, v
+
+            def cross_kv(attn, i=i):
+                if incremental:
+                    return incremental_state["_ofa_b200"]["cross"][i]
+                return attn.project_kv(enc)
+
+            x = layer(x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg)
+            inner_states.append(x.transpose(0, 1))
+        x = _ln(self.layer_norm, x)
+        return x, {"attn": [None], "inner_states": inner_states}
+
+    def output_layer(self, features, padded=False):
+        """Tied projection to the vocabulary (:1577-1583).  padded=True returns a [B,T,V] view whose row stride is
+        rounded up to 8 elements (16B-aligned rows for the fused loss kernel and the TMA-fed backward GEMMs)."""
+        return ops.linear(features, self.output_projection.weight, None, 1.0, None, padded)
+
+    def reorder_incremental_state_scripting(self, incremental_state, new_order):
+        st = incremental_state.get("_ofa_b200")
+        if not st:
+            return
+        for i in range(self.num_layers):
+            if st["self_k"][i] is not None:
+                st["self_k"][i] = st["self_k"][i].index_select(0, new_order)
+                st["self_v"][i] = st["self_v"][i].index_select(0, new_order)
+        if st["spk"] is not None:
+            st["spk"] = st["spk"].index_select(0, new_order)
+        if st["cpk"].size(0) == new_order.size(0):
+            st["cpk"] = st["cpk"].index_select(0, new_order)
+            st["cross"] = [(k.index_select(0, new_order), v.index_select(0, new_order)) for k, v in st["cross"]]
+
+    def get_normalized_probs(self, net_output, log_probs, sample=None):
+        logits = net_output[0]
+        return F.log_softmax(logits, dim=-1, dtype=torch.float32) if log_probs else \
+            F.softmax(logits, dim=-1, dtype=torch.float32)
+
+    def max_positions(self):
+        return self.max_target_positions
+
+
+class OFAModel(nn.Module):
+    """models/ofa/ofa.py:25-171.  Registered as fairseq model "ofa" by musketeer_b200.plugin when fairseq is present."""
+
+    def __init__(self, args, encoder, decoder):
+        super().__init__()
+        self.args = args
+        self.encoder, self.decoder = encoder, decoder
+        self.supports_align_args = True
+        self.apply(init_bert_params)
+        self.classification_heads = nn.ModuleDict()
+        if hasattr(self.encoder, "dictionary"):
+            self.eos = self.encoder.dictionary.eos()
+        self.enc_timer, self.dec_timer, self.cls_timer = [0, 0], [0, 0], [0, 0]
+
+    @classmethod
+    def build_model(cls, args, task):
+        from .archs import base_architecture
+        base_architecture(args)
+        if getattr(args, "max_source_positions", None) is None:
+            args.max_source_positions = DEFAULT_MAX_SOURCE_POSITIONS
+        if getattr(args, "max_target_positions", None) is None:
+            args.max_target_positions = DEFAULT_MAX_TARGET_POSITIONS
+        src_dict, tgt_dict = task.source_dictionary, task.target_dictionary
+        if not args.share_all_embeddings:
+            raise NotImplementedError("OFA is trained with --share-all-embeddings (train_musketeer.sh:127)")
+        if src_dict != tgt_dict:
+            raise ValueError("--share-all-embeddings requires a joined dictionary")
+        if args.encoder_embed_dim != args.decoder_embed_dim:
+            raise ValueError("--share-all-embeddings requires --encoder-embed-dim to match --decoder-embed-dim")
+        args.vocab_size = len(src_dict)
+        emb = Embedding(len(src_dict), args.encoder_embed_dim, src_dict.pad())
+        args.share_decoder_input_output_embed = True
+        if getattr(args, "freeze_encoder_embedding", False) or getattr(args, "freeze_decoder_embedding", False):
+            emb.weight.requires_grad = False
+        encoder = TransformerEncoder(args, src_dict, emb)
+        decoder = TransformerDecoder(args, tgt_dict, emb)
+        return cls(args, encoder, decoder)
+
+    def forward(self, src_tokens, src_lengths, prev_output_tokens, patch_images=None, patch_images_2=None,
+                patch_masks=None, code_masks=None, sample_patch_num=None, features_only=False,
+                classification_head_name=None, token_embeddings=None, return_all_hiddens=False, alignment_layer=None,
+                alignment_heads=None, task_name=None, padded_logits=False):
+        if classification_head_name is not None:
+            raise NotImplementedError("classification heads are outside the hot-path scope (SURVEY.md 8)")
+        encoder_out = self.encoder(src_tokens, src_lengths=src_lengths, patch_images=patch_images,
+                                   patch_masks=patch_masks, patch_images_2=patch_images_2,
+                                   token_embeddings=token_embeddings, return_all_hiddens=return_all_hiddens,
+                                   sample_patch_num=sample_patch_num)
+        self.enc_timer[1] += 1
+        x, extra = self.decoder(prev_output_tokens, code_masks=code_masks, encoder_out=encoder_out,
+                                features_only=features_only, alignment_layer=alignment_layer,
+                                alignment_heads=alignment_heads, src_lengths=src_lengths,
+                                return_all_hiddens=return_all_hiddens, padded_logits=padded_logits)
+        self.dec_timer[1] += 1
+        self.cls_timer[1] += 1
+        return x, extra
+
+    def get_normalized_probs(self, net_output, log_probs, sample=None):
+        return self.decoder.get_normalized_probs(net_output, log_probs, sample)
+
+    def get_targets(self, sample, net_output):
+        return sample["target"]
+
+    def max_positions(self):
+        return (self.encoder.max_positions(), self.decoder.max_positions())
+
+    def max_decoder_positions(self):
+        return self.decoder.max_positions()
+
+    def set_num_updates(self, num_updates):
+        pass
+
+    def upgrade_state_dict_named(self, state_dict, name):
+        """Checkpoint compatibility (ofa.py:216-318 subset): fill tied / buffer keys missing from old checkpoints."""
+        prefix = name + "." if name != "" else ""
+        own = self.state_dict()
+        for k, v in own.items():
+            if prefix + k not in state_dict:
+                state_dict[prefix + k] = v
+        return state_dict

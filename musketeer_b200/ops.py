@@ -1,0 +1,411 @@
+"""torch.autograd wrappers around the C ABI (include/ofa_b200.h).  PyTorch supplies device memory, streams and the
+autograd tape only; every arithmetic step of the hot path below runs in libofa_b200.so.
+
+Two numeric modes, selected by the activation dtype:
+  * bfloat16 : operands bf16, fp32 accumulation (tcgen05 GEMMs, flash attention) -- the training mode;
+  * float32  : "parity mode" -- GEMM operands are split into three bf16 terms (x = x0+x1+x2 to 2^-24) and contracted
+               as six K-blocks on the same tcgen05 kernel; attention runs on the exact SIMT kernels.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import OfaAttnArgs, OfaAttnBias, OfaAttnGrads, call
+
+F32, BF16 = 0, 1
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("musketeer_b200 kernels support float32 and bfloat16, got %s" % t.dtype)
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise _lib.OfaKernelError("musketeer_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------------------------
+def _split3(x2d, rows, cols, k_is_cols, pattern):
+    """fp32 [rows, cols] (row stride x2d.stride(0)) -> bf16 six-block operand.  k_is_cols: contraction runs along
+    columns (K-major operand) -> blocks side by side [rows, 6*Kp]; else along rows (MN-major) -> stacked [6*Kp, cols8]."""
+    if k_is_cols:
+        kp = _ceil8(cols)
+        out = torch.zeros(rows, 6 * kp, dtype=torch.bfloat16, device=x2d.device)
+        call("ofa_split3_bf16", _p(x2d), x2d.stride(0), rows, cols, _p(out), 6 * kp, kp, pattern, _st())
+        return out, 6 * kp, 6 * kp
+    kp = _ceil8(rows)
+    c8 = _ceil8(cols)
+    out = torch.zeros(6 * kp, c8, dtype=torch.bfloat16, device=x2d.device)
+    call("ofa_split3_bf16", _p(x2d), x2d.stride(0), rows, cols, _p(out), c8, kp * c8, pattern, _st())
+    return out, c8, 6 * kp
+
+
+def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, alpha=1.0, act=0, resid=None,
+         ldd=None):
+    """D[M,N] = act((A.B^T + bias) * alpha) + resid.   A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn);
+    2-D tensors with unit inner stride.  fp32 operands take the split path."""
+    _need_cuda(A)
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
+    out_dtype = out_dtype or A.dtype
+    if out is None:
+        ldd = ldd or N
+        out = torch.empty(M, ldd, dtype=out_dtype, device=A.device)
+    ldd = out.stride(0)
+    Kk = K
+    if A.dtype == torch.float32:
+        A, lda, Kk = _split3(A, A.shape[0], A.shape[1], not a_mn, 0)
+        B, ldb, Kb = _split3(B, B.shape[0], B.shape[1], not b_mn, 1)
+        assert Kb == Kk
+    else:
+        lda, ldb = A.stride(0), B.stride(0)
+    od = F32 if out_dtype == torch.float32 else BF16
+    if bias is not None:
+        assert bias.dtype == out_dtype
+    if resid is not None:
+        assert resid.dtype == out_dtype and resid.stride(-1) == 1
+    call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
+         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _st())
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, alpha, resid, out_pad):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        M, K = x2.shape
+        N = w.shape[0]
+        r2 = resid.reshape(-1, N) if resid is not None else None
+        ldd = _ceil8(N) if out_pad else N
+        y = gemm(x2, w, M, N, K, bias=b, alpha=alpha, resid=r2, ldd=ldd)
+        ctx.save_for_backward(x2, w)
+        ctx.alpha, ctx.has_b, ctx.has_r, ctx.shp = alpha, b is not None, resid is not None, shp
+        if ldd != N:
+            y = y[:, :N]
+        return y.reshape(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(-1, N)
+        if dy2.stride(-1) != 1 or (dy2.stride(0) % 8 != 0 and dy2.dtype == torch.bfloat16):
+            pad = torch.zeros(M, _ceil8(N), dtype=dy2.dtype, device=dy2.device)
+            pad[:, :N].copy_(dy2)
+            dy2 = pad[:, :N]
+        dx = dw = db = dr = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
+        if ctx.needs_input_grad[1]:
+            dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out_dtype=w.dtype)
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            db = colsum(dy2, alpha=ctx.alpha)
+        if ctx.has_r and ctx.needs_input_grad[4]:
+            dr = dy
+        return dx, dw, db, None, dr, None
+
+
+def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False):
+    """(x W^T + b) * alpha + resid   (nn.Linear forward/backward through ofa_gemm_bf16)."""
+    return _Linear.apply(x, w, b, alpha, resid, out_pad)
+
+
+def colsum(x2, alpha=1.0):
+    rows, Cc = x2.shape
+    out = torch.empty(Cc, dtype=x2.dtype, device=x2.device)
+    ws = torch.empty(64 * Cc, dtype=torch.float32, device=x2.device)
+    call("ofa_colsum", _p(x2), x2.stride(0), rows, Cc, _p(out), _p(ws), _dt(x2), _st())
+    if alpha != 1.0:
+        out = out * alpha
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm (+ fused GELU prologue / residual epilogue)
+# ---------------------------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, resid, gelu_in, eps):
+        _need_cuda(x)
+        shp = x.shape
+        Cc = shp[-1]
+        x2 = x.reshape(-1, Cc).contiguous()
+        rows = x2.shape[0]
+        r2 = resid.reshape(-1, Cc).contiguous() if resid is not None else None
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        call("ofa_layernorm_fwd", _p(x2), _p(gamma), _p(beta), _p(r2), _p(y), _p(mean), _p(rstd), rows, Cc, eps,
+             int(gelu_in), _dt(x2), _st())
+        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.gelu_in, ctx.shp, ctx.has_r = gelu_in, shp, resid is not None
+        return y.reshape(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma, mean, rstd = ctx.saved_tensors
+        rows, Cc = x2.shape
+        dy2 = dy.reshape(-1, Cc).contiguous()
+        dx = torch.empty_like(x2)
+        dg = torch.empty_like(gamma)
+        db = torch.empty_like(gamma)
+        nparts = _lib.load().ofa_layernorm_bwd_nparts(rows)
+        ws = torch.empty(2 * nparts * Cc, dtype=torch.float32, device=x2.device)
+        call("ofa_layernorm_bwd", _p(dy2), _p(x2), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), rows,
+             Cc, int(ctx.gelu_in), _dt(x2), _st())
+        return dx.reshape(ctx.shp), dg, db, (dy if ctx.has_r else None), None, None
+
+
+def layer_norm(x, gamma, beta, resid=None, gelu_in=False, eps=1e-5):
+    """LN(f(x)) * gamma + beta (+ resid), f = gelu if gelu_in."""
+    return _LayerNorm.apply(x, gamma, beta, resid, gelu_in, eps)
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("ofa_gelu", _p(x), _p(None), _p(y), x.numel(), 0, _dt(x), _st())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        call("ofa_gelu", _p(x), _p(dy), _p(dx), x.numel(), 1, _dt(x), _st())
+        return dx
+
+
+def gelu(x):
+    return _Gelu.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# embeddings and glue
+# ---------------------------------------------------------------------------------------------------------------------
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, table, addvec, padding_idx):
+        _need_cuda(table)
+        idx = idx.contiguous()
+        rows = idx.numel()
+        Cc = table.shape[1]
+        out = torch.empty(*idx.shape, Cc, dtype=table.dtype, device=table.device)
+        call("ofa_embed_gather", _p(idx), _p(table), _p(addvec), _p(out), Cc, rows, Cc, _dt(table), _st())
+        ctx.save_for_backward(idx)
+        ctx.tshape, ctx.pad, ctx.has_add = table.shape, padding_idx, addvec is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        Cc = ctx.tshape[1]
+        dt = da = None
+        if ctx.needs_input_grad[1]:
+            dt = torch.zeros(ctx.tshape, dtype=dout.dtype, device=dout.device)
+            call("ofa_embed_scatter_add", _p(idx), _p(dout), Cc, _p(dt), idx.numel(), Cc,
+                 -1 if ctx.pad is None else ctx.pad, _dt(dout), _st())
+        if ctx.has_add and ctx.needs_input_grad[2]:
+            da = colsum(dout.reshape(-1, Cc))
+        return None, dt, da, None
+
+
+def embedding(idx, table, addvec=None, padding_idx=None):
+    """table[idx] (+ addvec broadcast over rows); the padding row receives no gradient."""
+    return _Embedding.apply(idx, table, addvec, padding_idx)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        call("ofa_add", _p(a), _p(b), _p(out), a.numel(), _dt(a), _st())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+class _MaskRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rowmask):
+        x = x.contiguous().clone()
+        rm = rowmask.contiguous().view(torch.uint8)
+        call("ofa_mask_rows", _p(x), _p(rm), rm.numel(), x.shape[-1], _dt(x), _st())
+        ctx.save_for_backward(rm)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        (rm,) = ctx.saved_tensors
+        g = g.contiguous().clone()
+        call("ofa_mask_rows", _p(g), _p(rm), rm.numel(), g.shape[-1], _dt(g), _st())
+        return g, None
+
+
+def mask_rows(x, rowmask):
+    """x * (1 - rowmask[..., None])   (unify_transformer.py:892-893)"""
+    return _MaskRows.apply(x, rowmask)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------------
+def _fill_args(q, pq, k, pk, v, o, lse, H, causal, q_pos_off, kpm, head_scale, bias, p_round):
+    a = OfaAttnArgs()
+    B, T = q.shape[0], q.shape[1]
+    S = k.shape[1]
+    for name, t in (("q", q), ("pq", pq), ("k", k), ("pk", pk), ("v", v), ("o", o)):
+        assert t.stride(2) == 1, name
+        setattr(a, name, t.data_ptr())
+        setattr(a, "ld" + name, t.stride(1))
+        setattr(a, "bs" + name, t.stride(0))
+    a.lse = lse.data_ptr()
+    a.B, a.H, a.T, a.S = B, H, T, S
+    a.causal, a.q_pos_off = int(causal), int(q_pos_off)
+    a.kpm = kpm.data_ptr() if kpm is not None else None
+    a.head_scale = head_scale.data_ptr() if head_scale is not None else None
+    a.p_round_bf16 = int(p_round)
+    bz = OfaAttnBias()
+    bz.tok_max = 1024
+    bz.tok_lut = bias["tok_lut"].data_ptr() if bias.get("tok_lut") is not None else None
+    bz.q_text_off, bz.k_text_off = bias.get("q_text_off", 0), bias.get("k_text_off", 0)
+    bz.img_lut = bias["img_lut"].data_ptr() if bias.get("img_lut") is not None else None
+    bz.n_img_rel = bias["img_lut"].shape[1] if bias.get("img_lut") is not None else 0
+    bz.ibs = bias.get("ibs", 42)
+    bz.q_pid = bias["q_pid"].data_ptr() if bias.get("q_pid") is not None else None
+    bz.k_pid = bias["k_pid"].data_ptr() if bias.get("k_pid") is not None else None
+    bz.n_img_q, bz.n_img_k = bias.get("n_img_q", 0), bias.get("n_img_k", 0)
+    a.bias = bz
+    return a
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, pq, k, pk, v, tok_lut, img_lut, head_scale, cfg):
+        _need_cuda(q)
+        B, T, D = q.shape
+        H = cfg["H"]
+        o = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+        lse = torch.empty(B, H, T, dtype=torch.float32, device=q.device)
+        hs = head_scale.float().contiguous() if head_scale is not None else None
+        bias = dict(cfg["bias"])
+        bias["tok_lut"], bias["img_lut"] = tok_lut, img_lut
+        kpm = cfg.get("kpm")
+        a = _fill_args(q, pq, k, pk, v, o, lse, H, cfg["causal"], cfg.get("q_pos_off", 0), kpm, hs, bias,
+                       q.dtype == torch.bfloat16)
+        if q.dtype == torch.bfloat16 and cfg.get("use_tc", True):
+            call("ofa_attn_fwd_tc", C.byref(a), _st())
+        else:
+            call("ofa_attn_fwd_simt", C.byref(a), _dt(q), _st())
+        ctx.save_for_backward(q, pq, k, pk, v, o, lse, tok_lut, img_lut, hs, head_scale)
+        ctx.cfg, ctx.bias = cfg, bias
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, pq, k, pk, v, o, lse, tok_lut, img_lut, hs, head_scale = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, T, D = q.shape
+        S, H = k.shape[1], cfg["H"]
+        do = do.contiguous()
+        a = _fill_args(q, pq, k, pk, v, o, lse, H, cfg["causal"], cfg.get("q_pos_off", 0), cfg.get("kpm"), hs,
+                       ctx.bias, q.dtype == torch.bfloat16)
+        g = OfaAttnGrads()
+        dq, dpq = torch.empty(B, T, D, dtype=q.dtype, device=q.device), torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+        dk, dpk, dv = (torch.empty(B, S, D, dtype=q.dtype, device=q.device) for _ in range(3))
+        g.dout = do.data_ptr()
+        for name, t in (("dq", dq), ("dpq", dpq), ("dk", dk), ("dpk", dpk), ("dv", dv)):
+            setattr(g, name, t.data_ptr())
+            setattr(g, "ld" + name, t.stride(1))
+            setattr(g, "bs" + name, t.stride(0))
+        dtok = torch.zeros_like(tok_lut) if tok_lut is not None else None
+        dimg = torch.zeros_like(img_lut) if img_lut is not None else None
+        g.dtok_lut = dtok.data_ptr() if dtok is not None else None
+        g.dimg_lut = dimg.data_ptr() if dimg is not None else None
+        delta = torch.empty(B, H, T, dtype=torch.float32, device=q.device)
+        P = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
+        dS = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
+        g.delta, g.P, g.dS = delta.data_ptr(), P.data_ptr(), dS.data_ptr()
+        call("ofa_attn_bwd_simt", C.byref(a), C.byref(g), _dt(q), _st())
+        dhs = None
+        if head_scale is not None:
+            dhs = (delta.sum(dim=(0, 2)) / hs).to(head_scale.dtype)
+        return dq, dpq, dk, dpk, dv, dtok, dimg, dhs, None
+
+
+def attention(q, pq, k, pk, v, tok_lut, img_lut, head_scale, cfg):
+    """softmax(q k^T + pq pk^T + rel-pos LUT bias + masks) v * c_attn.   q/pq/k/pk/v: [B, L, H*64] (unit inner
+    stride); tok_lut [H, 2047] / img_lut [H, n_rel] fp32 (differentiable); cfg: H, causal, kpm, q_pos_off, bias{...}."""
+    return _Attention.apply(q, pq, k, pk, v, tok_lut, img_lut, head_scale, cfg)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused label-smoothed cross-entropy (+ R-Drop)
+# ---------------------------------------------------------------------------------------------------------------------
+class _LsCe(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, cmask, conf, eps, pad_idx, crange, rdrop, reg_alpha):
+        """logits [B,T,V] (row stride may be padded) are CONSUMED: the kernel overwrites the buffer with
+        d loss / d logits behind autograd's back (nothing upstream saves the logits; see decoder.output_layer)."""
+        _need_cuda(logits)
+        B, T, V = logits.shape
+        assert logits.stride(2) == 1 and logits.stride(0) == T * logits.stride(1)
+        R = B * T
+        tgt = target.contiguous()
+        loss_rows = torch.empty(R, dtype=torch.float32, device=logits.device)
+        nll_rows = torch.empty(R, dtype=torch.float32, device=logits.device)
+        kl_rows = torch.zeros(R // 2 if rdrop else 1, dtype=torch.float32, device=logits.device)
+        cm = cmask.contiguous().view(torch.uint8) if cmask is not None else None
+        cf = conf.float().contiguous() if conf is not None else None
+        cs, ce = crange if crange is not None else (-1, -1)
+        call("ofa_ls_ce_fwd_bwd", _p(logits), logits.stride(1), _p(tgt), _p(cm), _p(cf), T, R, V, pad_idx, eps, cs, ce,
+             int(rdrop), reg_alpha, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st())
+        ctx.dlogits = logits.detach()
+        ctx.mark_non_differentiable(nll_rows)
+        loss = loss_rows.sum() + (reg_alpha * kl_rows.sum() if rdrop else 0.0)
+        return loss, nll_rows
+
+    @staticmethod
+    def backward(ctx, gloss, gnll):
+        dlogits = ctx.dlogits
+        B, T, V = dlogits.shape
+        scale = gloss.float().reshape(1).contiguous()
+        call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(None), _dt(dlogits), _st())
+        return dlogits, None, None, None, None, None, None, None, None
+
+
+def ls_cross_entropy(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None, rdrop=False, reg_alpha=1.0):
+    """Sum over non-pad rows of the label-smoothed NLL (+ reg_alpha * symmetric KL between the two R-Drop halves).
+    Returns (loss, nll_rows).  `logits` is overwritten with its own gradient (one read + one write of M x V)."""
+    return _LsCe.apply(logits, target, cmask, conf, eps, pad_idx, crange, rdrop, reg_alpha)

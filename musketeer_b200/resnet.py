@@ -1,0 +1,91 @@
+"""3-stage bottleneck ResNet patch embedder (models/ofa/resnet.py:86-225, frozen_bn.py:7-80), same parameter names.
+
+Round-1 status (DESIGN.md "ResNet stem"): the convolutions and batch-norms still run through cuDNN / ATen library
+kernels (channels-last, model dtype); the implicit-GEMM tcgen05 convolution of SURVEY.md 8(a) row a3 is the next
+kernel to land.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+BLOCKS = {"resnet50": [3, 4, 6], "resnet101": [3, 4, 23], "resnet152": [3, 8, 36]}
+
+
+class FrozenBatchNorm2d(nn.Module):
+    def __init__(self, num_features, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.register_buffer("weight", torch.ones(num_features))
+        self.register_buffer("bias", torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features) - eps)
+
+    def forward(self, x):
+        scale = self.weight * (self.running_var + self.eps).rsqrt()
+        bias = self.bias - self.running_mean * scale
+        return x * scale.reshape(1, -1, 1, 1).to(x.dtype) + bias.reshape(1, -1, 1, 1).to(x.dtype)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride, downsample, norm):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = norm(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = norm(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = norm(planes * 4)
+        self.downsample = downsample
+
+    def forward(self, x):
+        idn = x
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = F.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        if self.downsample is not None:
+            idn = self.downsample(x)
+        return F.relu(idn + out)
+
+
+class ResNetStem(nn.Module):
+    def __init__(self, resnet_type, frozen_bn=False):
+        super().__init__()
+        norm = FrozenBatchNorm2d if frozen_bn else nn.BatchNorm2d
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = norm(64)
+        layers = BLOCKS[resnet_type]
+        self.layer1 = self._make_layer(64, layers[0], 1, norm)
+        self.layer2 = self._make_layer(128, layers[1], 2, norm)
+        self.layer3 = self._make_layer(256, layers[2], 2, norm)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        self.last_hw = None
+
+    def _make_layer(self, planes, blocks, stride, norm):
+        down = None
+        if stride != 1 or self.inplanes != planes * 4:
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False), norm(planes * 4))
+        seq = [Bottleneck(self.inplanes, planes, stride, down, norm)]
+        self.inplanes = planes * 4
+        for _ in range(1, blocks):
+            seq.append(Bottleneck(self.inplanes, planes, 1, None, norm))
+        return nn.Sequential(*seq)
+
+    def forward(self, x):
+        dt = self.conv1.weight.dtype
+        tf32 = torch.backends.cudnn.allow_tf32
+        if dt == torch.float32:
+            torch.backends.cudnn.allow_tf32 = False      # fp32 parity mode must not silently drop to TF32
+        try:
+            x = x.to(dt).contiguous(memory_format=torch.channels_last)
+            x = F.relu(self.bn1(self.conv1(x)))
+            x = F.max_pool2d(x, 3, 2, 1)
+            x = self.layer3(self.layer2(self.layer1(x)))
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        B, Cc, h, w = x.shape
+        self.last_hw = (h, w)
+        return x.permute(0, 2, 3, 1).reshape(B, h * w, Cc)

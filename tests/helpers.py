@@ -38,3 +38,47 @@ def tie(sd, requires_grad=True):
 
 
 ZERO_GRAD_SUFFIXES = ("k_proj.bias", "pos_k_linear.bias")  # mathematically zero (softmax shift invariance)
+
+
+class FakeDictionary:
+    """Stands in for the fairseq Dictionary the reference task hands to build_model (tasks/ofa_task.py:93-116)."""
+    def __init__(self, n): self.n = n
+    def __len__(self): return self.n
+    def pad(self): return 1
+    def eos(self): return 2
+    def bos(self): return 0
+    def unk(self): return 3
+    def __eq__(self, o): return isinstance(o, FakeDictionary) and o.n == self.n
+    def __ne__(self, o): return not self.__eq__(o)
+
+
+class FakeTask:
+    def __init__(self, n):
+        d = FakeDictionary(n)
+        self.source_dictionary = self.target_dictionary = self.tgt_dict = self.src_dict = d
+
+
+def build_product(cfg, sd, dtype=torch.float32, device="cuda"):
+    """Instantiate musketeer_b200.OFAModel for an oracle config and load the synthetic weights."""
+    from types import SimpleNamespace
+    from musketeer_b200 import OFAModel
+    args = SimpleNamespace(**vars(cfg))
+    args.no_scale_embedding = True
+    args.activation_fn = "gelu"
+    task = FakeTask(cfg.vocab_size)
+    model = OFAModel.build_model(args, task)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device=device, dtype=dtype)
+    return model, task
+
+
+def to_device(obj, device, float_dtype=None):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_floating_point() and float_dtype is not None:
+            return obj.to(device=device, dtype=float_dtype)
+        return obj.to(device)
+    if isinstance(obj, dict):
+        return {k: to_device(v, device, float_dtype) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [to_device(v, device, float_dtype) for v in obj]
+    return obj

@@ -1,0 +1,106 @@
+"""CPU-side checks: the C-ABI library exports what include/ofa_b200.h declares, the product's host logic
+(state-dict contract, integer tables, arch presets, loud failure without CUDA) -- no kernel is launched here."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import synth
+from tests.helpers import GOLDEN, build_product
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from musketeer_b200 import build
+    return build.build()
+
+
+def test_abi_exports_every_declared_symbol(lib_path):
+    hdr = open(os.path.join(ROOT, "include", "ofa_b200.h")).read()
+    declared = set(re.findall(r"\b(ofa_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ofa_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    from musketeer_b200 import _lib
+    lib = _lib.load()
+    assert set(_lib.SIGNATURES) | {"ofa_last_error"} == declared
+    assert lib.ofa_abi_version() == 1
+
+
+def test_sass_is_blackwell_native(lib_path):
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass      # tcgen05.mma
+    assert "UTMALDG" in sass      # TMA tensor loads
+    assert "LDTM" in sass         # tcgen05.ld
+    assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+@pytest.mark.parametrize("arch", ["ofa_tiny", "ofa_base"])
+def test_state_dict_contract(arch):
+    spec = json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))[arch]
+    cfg = synth.make_cfg(arch)
+    from types import SimpleNamespace
+    from musketeer_b200 import OFAModel
+    from tests.helpers import FakeTask
+    args = SimpleNamespace(**vars(cfg))
+    args.no_scale_embedding = True
+    model = OFAModel.build_model(args, FakeTask(cfg.vocab_size))
+    msd = model.state_dict()
+    assert list(msd.keys()) == [e[0] for e in spec["entries"]]
+    for (k, shape, dt) in spec["entries"]:
+        assert list(msd[k].shape) == shape, k
+        assert str(msd[k].dtype) == dt, k
+    assert sum(p.numel() for p in model.parameters()) == spec["n_params"]
+    assert model.decoder.output_projection.weight is model.encoder.embed_tokens.weight
+    assert model.decoder.embed_tokens.weight is model.encoder.embed_tokens.weight
+
+
+def test_bucket_tables_bit_exact():
+    from musketeer_b200.ofa import make_token_bucket_position, make_image_bucket_position, _rel_bucket_1d
+    t = make_token_bucket_position(256)
+    assert torch.equal(t, synth.token_bucket_table(256))
+    b = make_image_bucket_position(42, 83 * 83 + 3)
+    assert torch.equal(b, synth.image_bucket_table(42, 83 * 83 + 3))
+    r = _rel_bucket_1d(t)
+    i = torch.arange(1024)[:, None]
+    j = torch.arange(1024)[None, :]
+    assert torch.equal(r[(i - j) + 1023], t)      # the bucket is a function of i - j only
+
+
+def test_arch_presets():
+    from types import SimpleNamespace
+    from musketeer_b200 import ARCHS
+    want = {"ofa_tiny": (256, 4, 4, 4, "resnet50"), "ofa_medium": (512, 4, 4, 8, "resnet101"),
+            "ofa_base": (768, 6, 6, 12, "resnet101"), "ofa_large": (1024, 12, 12, 16, "resnet152"),
+            "ofa_huge": (1280, 24, 12, 16, "resnet152")}
+    for name, (d, le, ld, h, rn) in want.items():
+        a = SimpleNamespace()
+        ARCHS[name](a)
+        assert (a.encoder_embed_dim, a.encoder_layers, a.decoder_layers, a.encoder_attention_heads, a.resnet_type) == \
+            (d, le, ld, h, rn)
+        assert a.encoder_ffn_embed_dim == 4 * d and a.share_all_embeddings and a.attn_scale_factor == 2
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of computing without its kernels."""
+    from musketeer_b200 import ops, _lib
+    x = torch.randn(4, 64)
+    with pytest.raises(_lib.OfaKernelError):
+        ops.layer_norm(x, torch.ones(64), torch.zeros(64))
+    with pytest.raises(_lib.OfaKernelError):
+        ops.linear(x, torch.randn(8, 64))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "musketeer_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f

@@ -1,0 +1,242 @@
+"""Per-kernel parity on the GPU, through the C ABI (musketeer_b200.ops -> libofa_b200.so), against plain fp32 PyTorch
+restatements of the same op (and the oracle's loss).  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from musketeer_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (61, 59457 // 64, 256), (5, 72, 1000)])
+def test_gemm_bf16(a_mn, b_mn, M, N, K):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    Mp, Np, Kp = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    Ad = torch.zeros(K, Mp).cuda().bfloat16() if a_mn else torch.zeros(M, Kp).cuda().bfloat16()
+    Bd = torch.zeros(K, Np).cuda().bfloat16() if b_mn else torch.zeros(N, Kp).cuda().bfloat16()
+    if a_mn:
+        Ad[:, :M] = A.t().cuda().bfloat16()
+    else:
+        Ad[:, :K] = A.cuda().bfloat16()
+    if b_mn:
+        Bd[:, :N] = B.t().cuda().bfloat16()
+    else:
+        Bd[:, :K] = B.cuda().bfloat16()
+    Av = Ad[:, :M] if a_mn else Ad[:, :K]
+    Bv = Bd[:, :N] if b_mn else Bd[:, :K]
+    bias = torch.randn(N, generator=g).cuda()
+    resid = torch.randn(M, N, generator=g).cuda()
+    out = ops.gemm(Av, Bv, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, bias=bias, alpha=0.5, resid=resid)
+    Af = (Av.t() if a_mn else Av).float()
+    Bf = (Bv.t() if b_mn else Bv).float()
+    ref = (Af @ Bf.t() + bias) * 0.5 + resid
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * math.sqrt(K), err      # bf16 products are exact in fp32; only accumulation order differs
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 96, 128), (61, 259, 100), (200, 4099, 128)])
+def test_linear_fp32_split_fwd_bwd(M, N, K):
+    """fp32 parity mode: 3-way bf16 split on tensor cores must reach fp32-level accuracy (<= 2e-6 relative)."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(M, K, generator=g).cuda().requires_grad_()
+    w = (torch.randn(N, K, generator=g) * 0.05).cuda().requires_grad_()
+    b = torch.randn(N, generator=g).cuda().requires_grad_()
+    r = torch.randn(M, N, generator=g).cuda().requires_grad_()
+    y = ops.linear(x, w, b, 0.7, r)
+    dy = torch.randn(M, N, generator=g).cuda()
+    y.backward(dy)
+    x2, w2, b2, r2 = [t.detach().double().requires_grad_() for t in (x, w, b, r)]
+    y2 = (x2 @ w2.t() + b2) * 0.7 + r2
+    y2.backward(dy.double())
+    for got, ref in ((y, y2), (x.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad), (r.grad, r2.grad)):
+        rel = (got.double() - ref).abs().max().item() / ref.abs().max().item()
+        assert rel < 2e-6, rel
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,C,gelu", [(37, 128, False), (713, 768, False), (100, 3072, True), (9, 1024, True),
+                                         (50, 256, False)])
+def test_layernorm(dtype, rows, C, gelu):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=g).cuda().to(dtype).requires_grad_()
+    gm = (1 + 0.1 * torch.randn(C, generator=g)).cuda().to(dtype).requires_grad_()
+    bt = (0.1 * torch.randn(C, generator=g)).cuda().to(dtype).requires_grad_()
+    r = torch.randn(rows, C, generator=g).cuda().to(dtype).requires_grad_()
+    y = ops.layer_norm(x, gm, bt, resid=r, gelu_in=gelu)
+    dy = torch.randn(rows, C, generator=g).cuda().to(dtype)
+    y.backward(dy)
+    xf, gf, bf, rf = [t.detach().float().requires_grad_() for t in (x, gm, bt, r)]
+    h = F.gelu(xf) if gelu else xf
+    yr = F.layer_norm(h, (C,), gf, bf, 1e-5) + rf
+    yr.backward(dy.float())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (y.float() - yr).abs().max().item() < tol * 4
+    assert (x.grad.float() - xf.grad).abs().max().item() < tol * 8
+    assert (r.grad.float() - rf.grad).abs().max().item() < tol
+    # param grads are sums over rows: compare relative to their scale
+    for a, b in ((gm.grad, gf.grad), (bt.grad, bf.grad)):
+        assert (a.float() - b).abs().max().item() <= (tol if dtype == torch.float32 else 1e-2) * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_embedding(dtype):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    table = torch.randn(500, 64, generator=g).cuda().to(dtype).requires_grad_()
+    add = torch.randn(64, generator=g).cuda().to(dtype).requires_grad_()
+    idx = torch.randint(0, 500, (4, 9), generator=g).cuda()
+    idx[0, 0] = 1
+    out = ops.embedding(idx, table, add, padding_idx=1)
+    dy = torch.randn(4, 9, 64, generator=g).cuda().to(dtype)
+    out.backward(dy)
+    tf, af = table.detach().float().requires_grad_(), add.detach().float().requires_grad_()
+    ref = F.embedding(idx, tf, padding_idx=1) + af
+    ref.backward(dy.float())
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert (out.float() - ref).abs().max().item() <= tol
+    assert (table.grad.float() - tf.grad).abs().max().item() <= tol * 4
+    assert (add.grad.float() - af.grad).abs().max().item() <= tol * 40
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant", ["plain", "mask", "range", "rdrop", "rdrop_mask_conf"])
+def test_ls_cross_entropy(dtype, variant):
+    """Fused loss + in-place gradient against the oracle's restatement of label_smoothed_nll_loss (CPU fp32)."""
+    from oracle import ofa_oracle as oo
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B, T, V = 4, 7, 4099
+    logits = torch.randn(B, T, V, generator=g) * 2
+    target = torch.randint(4, V, (B, T), generator=g)
+    target[1, 5:] = 1
+    target[3, 3:] = 1
+    cmask = conf = crange = None
+    rdrop = variant.startswith("rdrop")
+    if rdrop:
+        logits[B // 2:] = logits[:B // 2] + 0.3 * torch.randn(B // 2, T, V, generator=g)
+        target[B // 2:] = target[:B // 2]
+    if variant in ("mask", "rdrop_mask_conf"):
+        cmask = torch.zeros(B, T, V, dtype=torch.bool)
+        cmask[:, :, torch.randint(4, V, (50,), generator=g)] = True
+        cmask.scatter_(2, target.unsqueeze(-1), True)
+        if rdrop:
+            cmask[B // 2:] = cmask[:B // 2]
+    if variant == "rdrop_mask_conf":
+        conf = torch.tensor([1.0, 0.6, 1.0, 0.6])
+    if variant == "range":
+        crange = (1000, 2000)
+        target = target.clamp(min=1000, max=1999).masked_fill(target.eq(1), 1)
+    lg = logits.to(dtype).float().requires_grad_()     # the oracle sees exactly the values the kernel sees
+    ref_loss, ref_nll, ref_n = oo.label_smoothed_loss(lg, target, 0.1, cmask, conf, rdrop, 1.0, constraint_range=crange)
+    ref_loss.backward()
+    Vp = (V + 7) // 8 * 8
+    buf = torch.zeros(B, T, Vp, dtype=dtype, device="cuda")
+    buf[:, :, :V] = logits.to(dtype).cuda()
+    view = buf[:, :, :V].requires_grad_()
+    loss, nll_rows = ops.ls_cross_entropy(view, target.cuda(), 0.1, 1, cmask=cmask.cuda() if cmask is not None else None,
+                                          conf=conf.cuda() if conf is not None else None, crange=crange, rdrop=rdrop)
+    (loss * 1.0).backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-5 * abs(ref_loss.item())
+    assert abs(nll_rows.sum().item() - ref_nll.item()) <= 2e-5 * abs(ref_nll.item())
+    got = view.grad.float().cpu()
+    tol = 2e-6 if dtype == torch.float32 else 4e-3       # bf16 gradient rounding (|g| <= 1)
+    assert (got - lg.grad).abs().max().item() <= tol
+
+
+def _attn_reference(q, pq, k, pk, v, H, tok_lut, img_lut, q_pid, k_pid, P_q, P_k, kpm, causal, q_off, cs, ibs=42):
+    """fp64 restatement with the bias tensor materialised the way unify_transformer.py:923-933 does."""
+    B, T, D = q.shape
+    S = k.shape[1]
+    hd = D // H
+    f = lambda t, L: t.double().view(B, L, H, hd).transpose(1, 2)
+    s = f(q, T) @ f(k, S).transpose(2, 3) + f(pq, T) @ f(pk, S).transpose(2, 3)
+    bias = torch.zeros(B, H, T, S, dtype=torch.float64, device=q.device)
+    ii = torch.arange(T, device=q.device)[:, None] + q_off
+    jj = torch.arange(S, device=q.device)[None, :]
+    if tok_lut is not None:
+        rel = (ii - P_q) - (jj - P_k) + 1023
+        ok = (ii >= P_q) & (jj >= P_k)
+        tb = tok_lut.double()[:, rel.clamp(0, 2046)]                   # [H, T, S]
+        bias += torch.where(ok[None], tb, torch.zeros_like(tb))[None]
+    if img_lut is not None and P_q > 0:
+        qp, kp = q_pid.long() - 1, k_pid.long() - 1
+        idx = ((qp // ibs)[:, :, None] - (kp // ibs)[:, None, :] + ibs - 1) * (2 * ibs - 1) + \
+              ((qp % ibs)[:, :, None] - (kp % ibs)[:, None, :] + ibs - 1)          # [B, Pq, Pk]
+        ib = img_lut.double()[:, idx].permute(1, 0, 2, 3)                          # [B, H, Pq, Pk]
+        bias[:, :, :P_q, :P_k] += ib
+    s = s + bias
+    if causal:
+        s = s.masked_fill((jj > ii)[None, None], float("-inf"))
+    if kpm is not None:
+        s = s.masked_fill(kpm.bool()[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    o = p @ f(v, S)
+    if cs is not None:
+        o = o * cs.double().view(1, H, 1, 1)
+    return o.transpose(1, 2).reshape(B, T, D)
+
+
+def _attn_inputs(B, T, S, H, P, dtype, seed, causal=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    D = H * 64
+    mk = lambda L, sc: (torch.randn(B, L, D, generator=g) * sc).cuda().to(dtype).requires_grad_()
+    q, pq, k, pk, v = mk(T, 0.3), mk(T, 0.3), mk(S, 1.0), mk(S, 1.0), mk(S, 1.0)
+    tok_lut = (torch.randn(H, 2047, generator=g) * 0.5).cuda().requires_grad_()
+    img_lut = (torch.randn(H, 83 * 83 + 3, generator=g) * 0.5).cuda().requires_grad_() if P else None
+    cs = (1 + 0.2 * torch.randn(H, generator=g)).cuda().to(dtype).requires_grad_()
+    pid = None
+    if P:
+        pid = torch.stack([torch.randperm(24 * 24, generator=g)[:P] for _ in range(B)])
+        pid = (pid // 24) * 42 + pid % 24 + 1
+        pid = pid.int().cuda()
+    kpm = torch.zeros(B, S, dtype=torch.uint8)
+    if not causal:
+        kpm[0, S - 3:] = 1
+        if B > 1 and P:
+            kpm[1, :P] = 1           # a sample without an image: all patches masked
+    kpm = kpm.cuda()
+    cfg = {"H": H, "causal": causal, "kpm": kpm, "q_pos_off": 0,
+           "bias": {"q_text_off": P, "k_text_off": P, "ibs": 42, "q_pid": pid, "k_pid": pid, "n_img_q": P, "n_img_k": P}}
+    return q, pq, k, pk, v, tok_lut, img_lut, cs, pid, kpm, cfg
+
+
+@pytest.mark.parametrize("dtype,use_tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)])
+@pytest.mark.parametrize("B,T,S,H,P,causal", [(2, 40, 40, 2, 16, False), (2, 33, 33, 4, 0, True),
+                                              (1, 200, 200, 2, 150, False), (2, 5, 77, 2, 0, False),
+                                              (1, 130, 130, 1, 0, True)])
+def test_attention_fwd_bwd(dtype, use_tc, B, T, S, H, P, causal):
+    ops = _ops()
+    cross = T != S
+    q, pq, k, pk, v, tok_lut, img_lut, cs, pid, kpm, cfg = _attn_inputs(B, T, S, H, 0 if cross else P, dtype, 7 + T, causal)
+    if cross:
+        tok_lut = None
+        P = 0
+    cfg["use_tc"] = use_tc
+    o = ops.attention(q, pq, k, pk, v, tok_lut, img_lut, cs, cfg)
+    do = torch.randn(o.shape, generator=torch.Generator(device="cpu").manual_seed(1)).cuda().to(dtype)
+    o.backward(do)
+    leaves = [q, pq, k, pk, v, cs] + ([tok_lut] if tok_lut is not None else []) + ([img_lut] if img_lut is not None else [])
+    ref_leaves = [t.detach().double().requires_grad_() for t in leaves]
+    rq, rpq, rk, rpk, rv, rcs = ref_leaves[:6]
+    rtok = ref_leaves[6] if tok_lut is not None else None
+    rimg = ref_leaves[-1] if img_lut is not None else None
+    ro = _attn_reference(rq, rpq, rk, rpk, rv, H, rtok, rimg, pid, pid, P, P, kpm, causal, 0, rcs)
+    ro.backward(do.double())
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert (o.double() - ro).abs().max().item() < tol, "forward"
+    for name, a, b in zip(["dq", "dpq", "dk", "dpk", "dv", "dc", "dtok", "dimg"], leaves, ref_leaves):
+        scale = max(1.0, b.grad.abs().max().item())
+        err = (a.grad.double() - b.grad).abs().max().item()
+        assert err < tol * 4 * scale, (name, err, scale)

@@ -1,0 +1,121 @@
+"""End-to-end parity of the CUDA path (musketeer_b200.OFAModel + criterion, through libofa_b200.so) against
+(1) the golden fixtures produced by the unmodified reference and (2) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 mode -- logits max-abs 1e-4, loss and gradient norms 1e-3 relative;
+bf16 mode -- logits max-abs 2e-2 (fp32 accumulation), loss 1e-2 relative (bf16 rounding of a ~V-way softmax)."""
+import copy
+import random
+
+import pytest
+import torch
+
+from oracle import ofa_oracle as oo, synth
+from tests.helpers import load_golden, build_case, build_product, tie, to_device, ZERO_GRAD_SUFFIXES
+
+pytestmark = pytest.mark.gpu
+
+TRAIN_CASES = ["micro_pad", "micro_text_only", "micro_nomask_row", "micro_constraint", "micro_rdrop_sample",
+               "micro_multitask_rdrop", "micro_plainflags", "micro_frozenbn_eval", "c1_tiny"]
+
+
+def _run_product(case, fx, dtype):
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    cfg, sd, samples = build_case(case)
+    model, task = build_product(cfg, sd, dtype=dtype)
+    model.train(not case.get("eval_mode", False))
+    ck = dict(case["crit"])
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(
+        task, False, ck["label_smoothing"], use_rdrop=ck.get("use_rdrop", False), reg_alpha=ck.get("reg_alpha", 1.0),
+        sample_patch_num=ck.get("sample_patch_num", 0))
+    inp = to_device(copy.deepcopy(samples), "cuda", dtype)
+    po = fx.get("patch_orders")
+    if case.get("sample_patch_num"):
+        inp[0]["net_input"]["sample_patch_num"] = case["sample_patch_num"]
+    # the reference draws patch subsets from python's global RNG; replay the recorded orders per forward
+    orders = po if isinstance(po, list) else [po]
+    orig_forward = model.encoder.forward
+    state = {"i": 0}
+
+    def fwd(*a, **k):
+        o = orders[state["i"]] if state["i"] < len(orders) else None
+        model.encoder.patch_orders_override = o
+        state["i"] += 1
+        return orig_forward(*a, **k)
+
+    model.encoder.forward = fwd
+    loss, ss, log = crit(model, inp if len(inp) > 1 else inp[0])
+    (loss / ss).backward()
+    return model, loss, ss, log, cfg, sd, samples
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_fp32_mode_matches_reference(name):
+    fx = load_golden(name)
+    case = fx["case"]
+    model, loss, ss, log, cfg, sd, samples = _run_product(case, fx, torch.float32)
+    assert ss == fx["sample_size"]
+    assert abs(float(loss.detach()) - fx["loss"]) <= 1e-3 * abs(fx["loss"]), (float(loss.detach()), fx["loss"])
+    tot = 0.0
+    worst = ("", 0.0)
+    for n, p in model.named_parameters():
+        g = fx["grad_norms"].get(n)
+        if g is None:
+            assert p.grad is None or float(p.grad.norm()) == 0.0, n
+            continue
+        assert p.grad is not None, n
+        gn = float(p.grad.float().norm())
+        tot += gn * gn
+        if n.endswith(ZERO_GRAD_SUFFIXES):
+            continue
+        rel = abs(gn - g) / (g + 1e-12)
+        if rel > worst[1]:
+            worst = (n, rel)
+    assert abs(tot ** 0.5 - fx["grad_norm_total"]) <= 1e-3 * fx["grad_norm_total"], (tot ** 0.5, fx["grad_norm_total"])
+    assert worst[1] <= 5e-3, worst
+
+
+@pytest.mark.parametrize("name", ["micro_pad", "micro_text_only", "micro_nomask_row", "micro_plainflags", "c1_tiny"])
+def test_fp32_logits_match_reference(name):
+    """Logits (sub-sampled columns + per-row logsumexp) against the reference's own output: max-abs 1e-4."""
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg, sd, samples = build_case(case)
+    model, task = build_product(cfg, sd, dtype=torch.float32)
+    model.train(not case.get("eval_mode", False))
+    ni = to_device(copy.deepcopy(samples[0]["net_input"]), "cuda")
+    with torch.no_grad():
+        logits, _ = model(**ni)
+    assert logits.shape == (ni["prev_output_tokens"].shape[0], ni["prev_output_tokens"].shape[1], cfg.vocab_size)
+    got = logits.float().cpu()
+    assert (got[:, :, ::37] - fx["logits_sub"]).abs().max().item() < 1e-4
+    assert (torch.logsumexp(got, -1) - fx["logits_lse"]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["micro_pad", "micro_constraint", "c1_tiny"])
+def test_bf16_mode_within_tolerance(name):
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg, sd, samples = build_case(case)
+    model, task = build_product(cfg, sd, dtype=torch.bfloat16)
+    model.train(True)
+    ni = to_device(copy.deepcopy(samples[0]["net_input"]), "cuda", torch.bfloat16)
+    with torch.no_grad():
+        logits, _ = model(**ni)
+    got = logits.float().cpu()
+    assert (got[:, :, ::37] - fx["logits_sub"]).abs().max().item() < 2e-2
+    model2, loss, ss, log, *_ = _run_product(case, fx, torch.bfloat16)
+    assert abs(float(loss.detach()) - fx["loss"]) <= 1e-2 * abs(fx["loss"])
+    tot = sum(float(p.grad.float().norm()) ** 2 for p in model2.parameters() if p.grad is not None) ** 0.5
+    assert abs(tot - fx["grad_norm_total"]) <= 5e-2 * fx["grad_norm_total"], (tot, fx["grad_norm_total"])
+
+
+def test_state_dict_contract():
+    """Parameter / buffer names, order and shapes equal the reference's."""
+    import json, os
+    from tests.helpers import GOLDEN
+    spec = json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))
+    cfg = synth.make_cfg("ofa_tiny")
+    sd = synth.synth_state_dict(cfg)
+    model, _ = build_product(cfg, sd, device="cpu")
+    msd = model.state_dict()
+    assert list(msd.keys()) == [e[0] for e in spec["ofa_tiny"]["entries"]]
