@@ -106,7 +106,7 @@ def attention(sd, p, cfg, query, key, H, bias, key_padding_mask=None, causal=Fal
     if bias is not None:
         w = w + bias[..., -S:]                                      # :350-351
     if causal:
-        w = w + torch.triu(torch.full((T, S), float("-inf")), 1 + S - T)   # :353-357, unify_transformer.py:1591-1603
+        w = w + torch.triu(torch.full((T, S), float("-inf"), dtype=w.dtype), 1 + S - T)   # :353-357, unify_transformer.py:1591-1603
     if key_padding_mask is not None:
         w = w.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))   # :363-375
     pr = F.softmax(w, dim=-1, dtype=torch.float32).type_as(w)       # :380-383

@@ -5,6 +5,6 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.used --format=csv > g
 for f in "$@"; do
   name=$(basename $f .py)
   echo "=== $f" | tee -a gpurun_out/ci.log
-  timeout -s KILL 900 python -m pytest $f -q -m gpu -x --no-header -p no:cacheprovider 2>&1 | tail -40 | tee -a gpurun_out/ci_$name.log
-  echo "exit: ${PIPESTATUS[0]}" | tee -a gpurun_out/ci.log
+  timeout -s KILL 900 python -m pytest $f -q -m gpu --no-header -p no:cacheprovider > gpurun_out/ci_$name.log 2>&1; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/ci_$name.log | tail -30
+  
 done
