@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: OFA-base Musketeer TEP multi-task training micro-step (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--task-batch b] [--impl reference]
+
+One "step" = one Musketeer micro-step: five sequential task forwards (caption / VQA / VG / SNLI-VE / gigaword, per-task
+batch b, 384x384 images) through the criterion + one backward, on random-init OFA-base in bf16 (synthetic data).
+`value` = samples/s with the batches resident in HBM; `e2e` = the same step including the pinned-host -> device copy of
+every batch and the device -> host read of the loss.  N > 1: one rank per GPU, batch-sharded (weak scaling), gradients
+all-reduced over NCCL by musketeer_b200.dp.GradReducer (bucketed, overlapped with backward).
+`--impl reference`: the reference's algorithm (the CPU oracle: the reference itself is pure Python/PyTorch and cannot
+travel to the GPU box) timed on the host cores on a bounded sample (per-task batch 1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--task-batch", type=int, default=8)
+    ap.add_argument("--arch", default="ofa_base")
+    ap.add_argument("--img", type=int, default=384)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--profile-kernels", type=int, default=1)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, idx):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+
+
+def cpu_reference(steps, warmup, arch, img):
+    """The reference's algorithm on the host cores (oracle port), per-task batch 1, forward + loss + backward."""
+    from oracle import ofa_oracle as oo, synth
+    from musketeer_b200.synthetic import make_tep_group
+    torch.set_num_threads(os.cpu_count())
+    cfg = synth.make_cfg(arch)
+    sd = synth.synth_state_dict(cfg, seed=0)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    sd["decoder.embed_tokens.weight"] = sd["encoder.embed_tokens.weight"]
+    sd["decoder.output_projection.weight"] = sd["encoder.embed_tokens.weight"]
+    times = []
+    for it in range(warmup + steps):
+        group = make_tep_group(1, img=img, seed=it)
+        t0 = time.perf_counter()
+        loss, ss, _ = oo.criterion_forward(sd, cfg, group, epsilon=0.1)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+    t = sum(times) / len(times)
+    return 5.0 / t, t, os.cpu_count()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    workload = "OFA-base Musketeer TEP 5-task micro-step (caption S137/T12, VQA S230/T232, VG S259/T5, SNLI-VE " \
+               "S250/T250, gigaword S185/T12), %dx%d images, per-task batch %d, fwd+loss+bwd" % (a.img, a.img, a.task_batch)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        v, t, cores = cpu_reference(max(1, a.steps), min(a.warmup, 1), a.arch, a.img)
+        print(json.dumps({
+            "impl": "reference", "metric": "OFA-base train samples/sec", "value": v, "unit": "samples/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload.replace("per-task batch %d" % a.task_batch, "per-task batch 1 (bounded CPU sample)")},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "one 5-task group at per-task batch 1, fp32, oracle port of the reference (pure-Python reference cannot travel)"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+    from musketeer_b200 import _lib, AdjustLabelSmoothedCrossEntropyCriterion
+    from musketeer_b200.synthetic import build_model, make_tep_group, to_device, batch_bytes
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    model, task = build_model(a.arch, dev, torch.bfloat16, seed=0)
+    model.train()
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, sample_patch_num=0)
+    reducer = None
+    if world > 1:
+        from musketeer_b200.dp import GradReducer
+        reducer = GradReducer(model, world)
+    n_batches = 2
+    host = [make_tep_group(a.task_batch, img=a.img, seed=rank * 1000 + i, pin=True) for i in range(n_batches)]
+    resident = [to_device(h, dev, torch.bfloat16) for h in host]
+    h2d = batch_bytes(host[0])
+
+    def step(group, e2e=False):
+        if e2e:
+            group = to_device(group, dev, torch.bfloat16)
+        for p in model.parameters():
+            p.grad = None
+        if reducer is not None:
+            reducer.prepare()
+        loss, ss, log = crit(model, [dict(g, net_input=dict(g["net_input"])) for g in group])
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        if e2e:
+            return float(loss.detach())     # device -> host read of the step's result
+        return loss
+
+    def timed(nsteps, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            step((host if e2e else resident)[i % n_batches], e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(a.warmup):
+        step(resident[i % n_batches])
+    torch.cuda.synchronize()
+    l0 = _lib.LAUNCHES
+    sampler = ClockSampler(local) if rank == 0 else None
+    if a.profile_kernels:
+        _lib.PROFILE = {}
+    ms = timed(a.steps, False)
+    prof = _lib.PROFILE
+    _lib.PROFILE = None
+    launches = _lib.LAUNCHES - l0
+    ms_e2e = timed(a.steps, True)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+
+    samples = 5 * a.task_batch * world
+    value = samples * a.steps / (ms / 1e3)
+    pk, pk_kind = peaks()
+    roof = None
+    if prof:
+        tot = {}
+        for name, recs in prof.items():
+            t = sum(r[0].elapsed_time(r[1]) for r in recs)
+            w = {}
+            for r in recs:
+                if r[2]:
+                    w[r[2][0]] = w.get(r[2][0], 0.0) + r[2][1]
+            tot[name] = (t, w, len(recs))
+        top = max(tot, key=lambda k: tot[k][0])
+        t, w, n = tot[top]
+        share = {k: round(v[0] / ms, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:6]}
+        if "flop" in w:
+            ach = w["flop"] / (t / 1e3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_kind + " (sustained: timed inside a long step)",
+                    "launches": n, "avg_launch_us": t * 1e3 / n, "share_of_step": share}
+        else:
+            ach = w.get("byte", 0.0) / (t / 1e3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind, "launches": n,
+                    "avg_launch_us": t * 1e3 / n, "share_of_step": share}
+        g = tot.get("ofa_gemm_bf16")
+        if g and top != "ofa_gemm_bf16":
+            roof["gemm_tflops"] = g[1].get("flop", 0.0) / (g[0] / 1e3) / 1e12
+    cpu = None
+    if a.cpu_baseline:
+        v, t, cores = cpu_reference(1, 1, a.arch, a.img)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "one 5-task group at per-task batch 1 (fp32 oracle port of the reference), %.1f s" % t}
+    print(json.dumps({
+        "metric": "OFA-base train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "arch": a.arch, "l2": "activations and weights per step exceed the 126 MB L2",
+                   "optimizer_step": "not in the timed region (SURVEY.md 8f next row)", "dropout": 0.0},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": samples * a.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
+        "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,8 +81,22 @@ def load(path=None):
     return lib
 
 
-def call(name, *args):
+LAUNCHES = 0          # number of C-ABI kernel entry calls (each launches >= 1 kernel of this library)
+PROFILE = None        # when a dict: name -> list of (start_event, end_event, work) recorded on the launching stream
+
+
+def call(name, *args, work=None):
+    global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    LAUNCHES += 1
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1, work))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise OfaKernelError("%s: %s" % (name, lib.ofa_last_error().decode()))

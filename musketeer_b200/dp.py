@@ -1,0 +1,102 @@
+"""Data-parallel gradient reduction for the OFA hot path.
+
+The reference reduces all gradients in one un-overlapped flat all-reduce after the last backward (fairseq
+LegacyDistributedDataParallel via trainer.py:848-852).  Here gradients are grouped into ~32 MB buckets in
+reverse-registration order (roughly the order autograd produces them); a bucket is all-reduced with NCCL on a side stream
+as soon as its last gradient has been accumulated, so the collective overlaps the remaining backward.  Gradients are
+pre-divided by the world size; parameters that received no gradient are reduced as zeros so every rank issues the same
+collectives (trainer.py --find-unused-parameters semantics).  `no_sync()` skips reduction for non-final micro-batches
+(trainer.py:755-773)."""
+import contextlib
+
+import torch
+import torch.distributed as dist
+
+
+class GradReducer:
+    def __init__(self, model, world_size, bucket_bytes=32 << 20, process_group=None):
+        self.world, self.pg = world_size, process_group
+        params = [p for p in model.parameters() if p.requires_grad]
+        seen, uniq = set(), []
+        for p in params:            # tied weights appear once
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(uniq):
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self.stream = torch.cuda.Stream() if torch.cuda.is_available() and uniq[0].is_cuda else None
+        self.sync = True
+        self._pending, self._flat, self._works = None, None, None
+        for p in uniq:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        old, self.sync = self.sync, False
+        try:
+            yield
+        finally:
+            self.sync = old
+
+    def prepare(self):
+        """Call before the backward whose gradients must be reduced."""
+        self._pending = [len(b) for b in self.buckets]
+        self._flat = [None] * len(self.buckets)
+        self._works = []
+        self._seen = set()
+
+    def _hook(self, p):
+        if not self.sync or self._pending is None or id(p) in self._seen:
+            return
+        self._seen.add(id(p))
+        bi = self.bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        ps = self.buckets[bi]
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in ps]
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            ctx = contextlib.nullcontext()
+        with ctx:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            flat.div_(self.world)
+            w = dist.all_reduce(flat, group=self.pg, async_op=True)
+        self._flat[bi] = (flat, grads)
+        self._works.append(w)
+
+    def finish(self):
+        """Wait for the in-flight buckets (== optimizer.all_reduce_grads in trainer.py:850) and scatter results back."""
+        if not self.sync or self._pending is None:
+            return
+        for bi, n in enumerate(self._pending):
+            if n > 0 and self._flat[bi] is None:      # buckets holding parameters that got no gradient this step
+                self._launch(bi)
+        for w in self._works:
+            w.wait()
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        for bi, item in enumerate(self._flat):
+            flat, grads = item
+            off = 0
+            for p, g in zip(self.buckets[bi], grads):
+                n = g.numel()
+                if p.grad is None:
+                    p.grad = flat[off:off + n].view_as(p).clone()
+                else:
+                    p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+        self._pending = None

@@ -83,7 +83,8 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
     if resid is not None:
         assert resid.dtype == out_dtype and resid.stride(-1) == 1
     call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
-         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _st())
+         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _st(),
+         work=("flop", 2.0 * M * N * K))
     return out
 
 
@@ -156,7 +157,7 @@ class _LayerNorm(torch.autograd.Function):
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         call("ofa_layernorm_fwd", _p(x2), _p(gamma), _p(beta), _p(r2), _p(y), _p(mean), _p(rstd), rows, Cc, eps,
-             int(gelu_in), _dt(x2), _st())
+             int(gelu_in), _dt(x2), _st(), work=("byte", (2 + (resid is not None)) * rows * Cc * x2.element_size()))
         ctx.save_for_backward(x2, gamma, mean, rstd)
         ctx.gelu_in, ctx.shp, ctx.has_r = gelu_in, shp, resid is not None
         return y.reshape(shp)
@@ -172,7 +173,7 @@ class _LayerNorm(torch.autograd.Function):
         nparts = _lib.load().ofa_layernorm_bwd_nparts(rows)
         ws = torch.empty(2 * nparts * Cc, dtype=torch.float32, device=x2.device)
         call("ofa_layernorm_bwd", _p(dy2), _p(x2), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), rows,
-             Cc, int(ctx.gelu_in), _dt(x2), _st())
+             Cc, int(ctx.gelu_in), _dt(x2), _st(), work=("byte", 3 * rows * Cc * x2.element_size()))
         return dx.reshape(ctx.shp), dg, db, (dy if ctx.has_r else None), None, None
 
 
@@ -325,9 +326,9 @@ class _Attention(torch.autograd.Function):
         a = _fill_args(q, pq, k, pk, v, o, lse, H, cfg["causal"], cfg.get("q_pos_off", 0), kpm, hs, bias,
                        q.dtype == torch.bfloat16)
         if q.dtype == torch.bfloat16 and cfg.get("use_tc", True):
-            call("ofa_attn_fwd_tc", C.byref(a), _st())
+            call("ofa_attn_fwd_tc", C.byref(a), _st(), work=("flop", 2.0 * B * H * T * k.shape[1] * 192))
         else:
-            call("ofa_attn_fwd_simt", C.byref(a), _dt(q), _st())
+            call("ofa_attn_fwd_simt", C.byref(a), _dt(q), _st(), work=("flop", 2.0 * B * H * T * k.shape[1] * 192))
         ctx.save_for_backward(q, pq, k, pk, v, o, lse, tok_lut, img_lut, hs, head_scale)
         ctx.cfg, ctx.bias = cfg, bias
         return o
@@ -357,7 +358,7 @@ class _Attention(torch.autograd.Function):
         P = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
         dS = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
         g.delta, g.P, g.dS = delta.data_ptr(), P.data_ptr(), dS.data_ptr()
-        call("ofa_attn_bwd_simt", C.byref(a), C.byref(g), _dt(q), _st())
+        call("ofa_attn_bwd_simt", C.byref(a), C.byref(g), _dt(q), _st(), work=("flop", 2.0 * B * H * T * S * 512))
         dhs = None
         if head_scale is not None:
             dhs = (delta.sum(dim=(0, 2)) / hs).to(head_scale.dtype)
@@ -390,7 +391,8 @@ class _LsCe(torch.autograd.Function):
         cf = conf.float().contiguous() if conf is not None else None
         cs, ce = crange if crange is not None else (-1, -1)
         call("ofa_ls_ce_fwd_bwd", _p(logits), logits.stride(1), _p(tgt), _p(cm), _p(cf), T, R, V, pad_idx, eps, cs, ce,
-             int(rdrop), reg_alpha, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st())
+             int(rdrop), reg_alpha, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st(),
+             work=("byte", 2 * R * V * logits.element_size()))
         ctx.dlogits = logits.detach()
         ctx.mark_non_differentiable(nll_rows)
         loss = loss_rows.sum() + (reg_alpha * kl_rows.sum() if rdrop else 0.0)
