@@ -53,6 +53,7 @@ SIGNATURES = {
     "ofa_attn_fwd_simt": [C.POINTER(OfaAttnArgs), c_i, c_p],
     "ofa_attn_bwd_simt": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_i, c_p],
     "ofa_attn_fwd_tc": [C.POINTER(OfaAttnArgs), c_p],
+    "ofa_attn_bwd_tc": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_p, c_p],
 }
 
 

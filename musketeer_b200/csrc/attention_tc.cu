@@ -215,6 +215,326 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------------------
+// One CTA = one (batch, head, 128-key tile); K', V stay in shared memory, dK' and dV accumulate in TMEM over the sweep of
+// 128-query tiles.  Per (q-tile, k-tile) pair five tcgen05 GEMMs:
+//   S = Q'K'^T, dP = dO V^T  ->  P = exp(S + bias - lse), dS = P o (c dP - delta)  (registers, 2 threads per query row)
+//   dV += P^T dO, dK' += dS^T Q', dQ'_partial = dS K'   (P / dS staged as bf16 in swizzled smem; the transposed uses
+//   read the same bytes through MN-major descriptors).  dQ' partials are reduced into an fp32 accumulator with
+//   red.global.add.v4.f32; relative-position table gradients are privatised in shared-memory histograms.
+constexpr int BK2 = 128;
+constexpr int kBwdThreads = 256;
+constexpr int kTokHist = 1024 + 128;
+constexpr int kImgHistMax = 83 * 83 + 3;
+
+struct BwdSmem {
+  uint8_t k[2][BK2 * 128];   // [k | pos_k][128 keys][128 B]
+  uint8_t v[BK2 * 128];      // [128 keys][64 x bf16]
+  uint8_t q[2][BQ * 128];    // [q | pos_q][128 rows][128 B]
+  uint8_t dout[BQ * 128];    // [128 rows][64 x bf16]
+  uint8_t p[2][BQ * 128];    // [64-key half][128 rows][128 B]
+  uint8_t ds[2][BQ * 128];
+  float hist_tok[kTokHist];
+  float hist_img[kImgHistMax + 1];
+  int kinfo[BK2];
+  uint64_t bar_kv, bar_q, bar_sp, bar_dq;
+  uint32_t tmem_addr;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmPQ,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmPK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, AttnArgs a,
+                   AttnGrads g, float* __restrict__ dq_acc /* [B,T,H,128] fp32 */) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int t = threadIdx.x, warp = t >> 5;
+  const int r = t & 127, hf = t >> 7;   // TMEM lane / query row inside the tile ; 64-column half
+  const int k0 = blockIdx.x * BK2, h = blockIdx.y, b = blockIdx.z;
+  const AttnBias& bz = a.bias;
+  const bool has_tok = bz.tok_lut != nullptr && g.dtok_lut != nullptr;
+  const bool has_img = bz.img_lut != nullptr && g.dimg_lut != nullptr;
+  const int nq_tiles = (a.T + BQ - 1) / BQ;
+  // causal: query rows i with i + q_pos_off < k0 see none of this tile's keys
+  int qt0 = 0;
+  if (a.causal) { const int first = k0 - a.q_pos_off; qt0 = first > 0 ? first / BQ : 0; }
+
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmPQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmPK);
+    tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(&sm.bar_kv, 1); mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_sp, 1); mbar_init(&sm.bar_dq, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&sm.tmem_addr);
+  for (int e = t; e < kTokHist; e += kBwdThreads) sm.hist_tok[e] = 0.f;
+  for (int e = t; e < kImgHistMax + 1; e += kBwdThreads) sm.hist_img[e] = 0.f;
+  if (t < BK2) {
+    const int j = k0 + t;
+    int info = 0;
+    if (j >= a.S || (a.kpm && a.kpm[(size_t)b * a.S + j])) info |= (int)0x80000000u;
+    if (bz.img_lut && j < bz.n_img_k) {
+      const int pid = bz.k_pid[(size_t)b * bz.n_img_k + j] - 1;
+      info |= 0x40000000 | ((pid % bz.ibs) << 8) | (pid / bz.ibs);
+    }
+    sm.kinfo[t] = info;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = sm.tmem_addr;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 384;
+
+  if (qt0 < nq_tiles && t == 0) {
+    mbar_expect_tx(&sm.bar_kv, 3 * BK2 * 128);
+    tma_load_4d(sm.k[0], &tmK, &sm.bar_kv, 0, h, k0, b);
+    tma_load_4d(sm.k[1], &tmPK, &sm.bar_kv, 0, h, k0, b);
+    tma_load_4d(sm.v, &tmV, &sm.bar_kv, 0, h, k0, b);
+    mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
+    tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, qt0 * BQ, b);
+    tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, qt0 * BQ, b);
+    tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, qt0 * BQ, b);
+  }
+  const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  const float* img_lut = bz.img_lut ? bz.img_lut + (size_t)h * bz.n_img_rel : nullptr;
+  const int w83 = 2 * bz.ibs - 1;
+  constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);    // S, dP
+  constexpr uint32_t id_dv = umma_idesc_bf16(128, 64, 1, 1);    // dV  = P^T dO
+  constexpr uint32_t id_dk = umma_idesc_bf16(128, 128, 1, 1);   // dK' = dS^T Q'
+  constexpr uint32_t id_dq = umma_idesc_bf16(128, 128, 0, 1);   // dQ' = dS K'
+  const int tok_base = k0 - bz.k_text_off + 127;                // hist_tok[(i_t - j_t) + tok_base]
+
+  int it = 0;
+  for (int qt = qt0; qt < nq_tiles; ++qt, ++it) {
+    const uint32_t ph = it & 1;
+    const int q0 = qt * BQ;
+    if (t == 0) {
+      if (it == 0) mbar_wait(&sm.bar_kv, 0);
+      mbar_wait(&sm.bar_q, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tm + COL_S, umma_smem_desc(smem_u32(sm.q[kb]) + ks * 32, 16, 1024),
+                   umma_smem_desc(smem_u32(sm.k[kb]) + ks * 32, 16, 1024), id_s, (kb | ks) != 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_f16(tm + COL_DP, umma_smem_desc(smem_u32(sm.dout) + ks * 32, 16, 1024),
+                 umma_smem_desc(smem_u32(sm.v) + ks * 32, 16, 1024), id_s, ks != 0);
+      umma_commit(&sm.bar_sp);
+    }
+    __syncwarp();
+    // per-row metadata
+    const int i = q0 + r;
+    const int iabs = i + a.q_pos_off;
+    const bool row_ok = i < a.T;
+    const size_t ridx = ((size_t)b * a.H + h) * a.T + (row_ok ? i : 0);
+    const float lse = a.lse[ridx];
+    const float delta = g.delta[ridx];
+    const bool q_text = bz.tok_lut && iabs >= bz.q_text_off;
+    const bool q_img = bz.img_lut && iabs < bz.n_img_q && row_ok;
+    int qr = 0, qc = 0;
+    if (q_img) {
+      const int pid = bz.q_pid[(size_t)b * bz.n_img_q + iabs] - 1;
+      qr = pid / bz.ibs; qc = pid % bz.ibs;
+    }
+    const int i_t = iabs - bz.q_text_off;
+    const float* tok_lut = bz.tok_lut ? bz.tok_lut + (size_t)h * (2 * bz.tok_max - 1) + i_t + bz.tok_max - 1 + bz.k_text_off : nullptr;
+
+    mbar_wait(&sm.bar_sp, ph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int col0 = hf * 64 + c * 32;
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tm + lane_off + COL_S + col0, rs);
+      tmem_ld32(tm + lane_off + COL_DP + col0, rp);
+      tmem_ld_wait();
+      float pv[32], dsv[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int jl = col0 + jj, j = k0 + jl;
+        const int info = sm.kinfo[jl];
+        float x = __uint_as_float(rs[jj]);
+        const bool tok_el = q_text && j >= bz.k_text_off;
+        int img_idx = -1;
+        if (tok_el) x += __ldg(tok_lut - j);
+        if (q_img && (info & 0x40000000)) {
+          img_idx = (qr - (info & 0xff) + bz.ibs - 1) * w83 + (qc - ((info >> 8) & 0xff) + bz.ibs - 1);
+          x += __ldg(img_lut + img_idx);
+        }
+        const bool masked = info < 0 || (a.causal && j > iabs) || !row_ok;
+        const float p = masked ? 0.f : __expf(x - lse);
+        const float ds = p * (__uint_as_float(rp[jj]) * cs - delta);
+        pv[jj] = p;
+        dsv[jj] = ds;
+        if (ds != 0.f) {
+          if (has_tok && tok_el) atomicAdd(&sm.hist_tok[i_t - (j - bz.k_text_off) + tok_base], ds);
+          if (has_img && img_idx >= 0) atomicAdd(&sm.hist_img[img_idx], ds);
+        }
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        const int chunk = c * 4 + c16;   // 16-byte chunk inside the 128-byte row of this half
+        const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sm.p[hf] + off) =
+            make_uint4(pack_bf16(pv[c16 * 8], pv[c16 * 8 + 1]), pack_bf16(pv[c16 * 8 + 2], pv[c16 * 8 + 3]),
+                       pack_bf16(pv[c16 * 8 + 4], pv[c16 * 8 + 5]), pack_bf16(pv[c16 * 8 + 6], pv[c16 * 8 + 7]));
+        *reinterpret_cast<uint4*>(sm.ds[hf] + off) =
+            make_uint4(pack_bf16(dsv[c16 * 8], dsv[c16 * 8 + 1]), pack_bf16(dsv[c16 * 8 + 2], dsv[c16 * 8 + 3]),
+                       pack_bf16(dsv[c16 * 8 + 4], dsv[c16 * 8 + 5]), pack_bf16(dsv[c16 * 8 + 6], dsv[c16 * 8 + 7]));
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+      const uint32_t acc = it != 0;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)   // dV[keys, hd] += P^T dO   (contraction over the 128 query rows, 16 per MMA)
+        umma_f16(tm + COL_DV, umma_smem_desc(smem_u32(sm.p[0]) + ks * 2048, BQ * 128, 1024),
+                 umma_smem_desc(smem_u32(sm.dout) + ks * 2048, 1024, 1024), id_dv, acc | (ks != 0));
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)   // dK'[keys, 128] += dS^T Q'
+        umma_f16(tm + COL_DK, umma_smem_desc(smem_u32(sm.ds[0]) + ks * 2048, BQ * 128, 1024),
+                 umma_smem_desc(smem_u32(sm.q[0]) + ks * 2048, BQ * 128, 1024), id_dk, acc | (ks != 0));
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)   // dQ'[rows, 128] = dS K'      (contraction over the 128 keys)
+        umma_f16(tm + COL_S, umma_smem_desc(smem_u32(sm.ds[ks >> 2]) + (ks & 3) * 32, 16, 1024),
+                 umma_smem_desc(smem_u32(sm.k[0]) + ks * 2048, BK2 * 128, 1024), id_dq, ks != 0);
+      umma_commit(&sm.bar_dq);
+    }
+    __syncwarp();
+    mbar_wait(&sm.bar_dq, ph);
+    tc_fence_after();
+    if (t == 0 && qt + 1 < nq_tiles) {   // Q' / dO / P / dS buffers are free again
+      mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
+      tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, q0 + BQ, b);
+      tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, q0 + BQ, b);
+      tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, q0 + BQ, b);
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t rq[32];
+      tmem_ld32(tm + lane_off + COL_S + hf * 64 + c * 32, rq);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dst = dq_acc + (((size_t)b * a.T + i) * a.H + h) * 128 + hf * 64 + c * 32;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          red_add_v4(dst + v4 * 4, __uint_as_float(rq[v4 * 4]), __uint_as_float(rq[v4 * 4 + 1]),
+                     __uint_as_float(rq[v4 * 4 + 2]), __uint_as_float(rq[v4 * 4 + 3]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // epilogue: dK' (hf 0: k part, hf 1: pos_k part), dV (32 columns per half), histograms
+  const int j = k0 + r;
+  if (it > 0) {
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t rk[32];
+      tmem_ld32(tm + lane_off + COL_DK + hf * 64 + c * 32, rk);
+      tmem_ld_wait();
+      if (j < a.S) {
+        __nv_bfloat16* dst = hf == 0 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD + c * 32
+                                     : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD + c * 32;
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4)
+          reinterpret_cast<uint4*>(dst)[v4] = make_uint4(
+              pack_bf16(__uint_as_float(rk[8 * v4]), __uint_as_float(rk[8 * v4 + 1])),
+              pack_bf16(__uint_as_float(rk[8 * v4 + 2]), __uint_as_float(rk[8 * v4 + 3])),
+              pack_bf16(__uint_as_float(rk[8 * v4 + 4]), __uint_as_float(rk[8 * v4 + 5])),
+              pack_bf16(__uint_as_float(rk[8 * v4 + 6]), __uint_as_float(rk[8 * v4 + 7])));
+      }
+    }
+    {
+      uint32_t rv[32];
+      tmem_ld32(tm + lane_off + COL_DV + hf * 32, rv);
+      tmem_ld_wait();
+      if (j < a.S) {
+        __nv_bfloat16* dst = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + hf * 32;
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4)
+          reinterpret_cast<uint4*>(dst)[v4] = make_uint4(
+              pack_bf16(__uint_as_float(rv[8 * v4]) * cs, __uint_as_float(rv[8 * v4 + 1]) * cs),
+              pack_bf16(__uint_as_float(rv[8 * v4 + 2]) * cs, __uint_as_float(rv[8 * v4 + 3]) * cs),
+              pack_bf16(__uint_as_float(rv[8 * v4 + 4]) * cs, __uint_as_float(rv[8 * v4 + 5]) * cs),
+              pack_bf16(__uint_as_float(rv[8 * v4 + 6]) * cs, __uint_as_float(rv[8 * v4 + 7]) * cs));
+      }
+    }
+  } else if (j < a.S) {   // causal tile with no visible query rows: zero gradients
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    __nv_bfloat16* d0 = hf == 0 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD
+                                : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD;
+    for (int v4 = 0; v4 < 8; ++v4) reinterpret_cast<uint4*>(d0)[v4] = z;
+    __nv_bfloat16* d1 = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + hf * 32;
+    for (int v4 = 0; v4 < 4; ++v4) reinterpret_cast<uint4*>(d1)[v4] = z;
+  }
+  __syncthreads();
+  if (has_tok) {
+    float* gt = g.dtok_lut + (size_t)h * (2 * bz.tok_max - 1);
+    for (int e = t; e < kTokHist; e += kBwdThreads) {
+      const float v = sm.hist_tok[e];
+      const int rel = e - tok_base + bz.tok_max - 1;
+      if (v != 0.f && rel >= 0 && rel < 2 * bz.tok_max - 1) atomicAdd(gt + rel, v);
+    }
+  }
+  if (has_img) {
+    float* gi = g.dimg_lut + (size_t)h * bz.n_img_rel;
+    for (int e = t; e < bz.n_img_rel && e < kImgHistMax; e += kBwdThreads) {
+      const float v = sm.hist_img[e];
+      if (v != 0.f) atomicAdd(gi + e, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tm);
+  }
+}
+
+// delta[b,h,i] = sum_d dOut . Out   (one warp per (b, i, h))
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                      long long ldo, long long bso, int B, int T, int H, float* __restrict__ delta) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * T * H) return;
+  const int h = gw % H, i = (gw / H) % T, b = gw / (H * T);
+  const size_t off = (size_t)b * bso + (size_t)i * ldo + h * HD + lane * 2;
+  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
+  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(out + off));
+  float s = x.x * y.x + x.y * y.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) delta[((size_t)b * H + h) * T + i] = s;
+}
+
+// dq_acc [B,T,H,128] fp32 -> dq, dpq [B,T,H*64] bf16
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                           __nv_bfloat16* __restrict__ dpq, long long lddq, long long bsdq,
+                                           long long lddpq, long long bsdpq, int B, int T, int H) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 elements
+  const long long total = (long long)B * T * H * 16;
+  if (idx >= total) return;
+  const int c8 = idx % 16, h = (idx / 16) % H, i = (idx / (16 * H)) % T, b = idx / (16LL * H * T);
+  const float4 x = reinterpret_cast<const float4*>(acc)[idx * 2], y = reinterpret_cast<const float4*>(acc)[idx * 2 + 1];
+  const uint4 pk = make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+  if (c8 < 8) *reinterpret_cast<uint4*>(dq + (size_t)b * bsdq + (size_t)i * lddq + h * HD + c8 * 8) = pk;
+  else *reinterpret_cast<uint4*>(dpq + (size_t)b * bsdpq + (size_t)i * lddpq + h * HD + (c8 - 8) * 8) = pk;
+}
+
 int make_qkv_tmap(CUtensorMap* tm, const void* p, int L, int H, int B, long long ld, long long bs, int box_rows) {
   // dims {64 (head dim), H, L, B}; box {64, 1, box_rows, 1}
   uint64_t dims[4] = {(uint64_t)HD, (uint64_t)H, (uint64_t)L, (uint64_t)B};
@@ -247,5 +567,41 @@ extern "C" int ofa_attn_fwd_tc(const AttnArgs* a, void* stream) {
   dim3 grid((a->T + BQ - 1) / BQ, a->H, a->B);
   attn_fwd_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tq, tpq, tk, tpk, tv, *a);
   OFA_LAUNCH_CHECK("attn_fwd_tc_kernel");
+  return 0;
+}
+
+// workspace: dq_acc = B*T*H*128 floats (zero-filled here), delta = B*H*T floats (g->delta)
+extern "C" int ofa_attn_bwd_tc(const AttnArgs* a, const AttnGrads* g, float* dq_acc, void* stream) {
+  OFA_CHECK(a->T > 0 && a->S > 0 && a->B > 0 && a->H > 0, "ofa_attn_bwd_tc: empty problem");
+  OFA_CHECK(a->pq && a->pk && g->delta && dq_acc, "ofa_attn_bwd_tc: pq/pk, delta and dq_acc are required");
+  OFA_CHECK(a->bias.ibs < 256 && a->bias.n_img_rel <= kImgHistMax, "ofa_attn_bwd_tc: image bucket table too large");
+  OFA_CHECK(a->T <= 1024, "ofa_attn_bwd_tc: T=%d exceeds max positions 1024", a->T);
+  OFA_CHECK(a->ldo % 8 == 0 && a->bso % 8 == 0 && g->lddk % 8 == 0 && g->lddpk % 8 == 0 && g->lddv % 8 == 0 &&
+                g->lddq % 8 == 0 && g->lddpq % 8 == 0, "ofa_attn_bwd_tc: strides must be multiples of 8 elements");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tq, tpq, tk, tpk, tv, tdo;
+  if (int e = make_qkv_tmap(&tq, a->q, a->T, a->H, a->B, a->ldq, a->bsq, BQ)) return e;
+  if (int e = make_qkv_tmap(&tpq, a->pq, a->T, a->H, a->B, a->ldpq, a->bspq, BQ)) return e;
+  if (int e = make_qkv_tmap(&tk, a->k, a->S, a->H, a->B, a->ldk, a->bsk, BK2)) return e;
+  if (int e = make_qkv_tmap(&tpk, a->pk, a->S, a->H, a->B, a->ldpk, a->bspk, BK2)) return e;
+  if (int e = make_qkv_tmap(&tv, a->v, a->S, a->H, a->B, a->ldv, a->bsv, BK2)) return e;
+  if (int e = make_qkv_tmap(&tdo, g->dout, a->T, a->H, a->B, a->ldo, a->bso, BQ)) return e;
+  static bool configured = false;
+  const int smem = (int)sizeof(BwdSmem) + 1024;
+  if (!configured) {
+    OFA_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const long long nrow = (long long)a->B * a->T * a->H;
+  OFA_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)nrow * 128 * sizeof(float), st));
+  attn_bwd_delta_kernel<<<(unsigned)((nrow * 32 + 255) / 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)g->dout, (const __nv_bfloat16*)a->o, a->ldo, a->bso, a->B, a->T, a->H, g->delta);
+  OFA_LAUNCH_CHECK("attn_bwd_delta_kernel");
+  dim3 grid((a->S + BK2 - 1) / BK2, a->H, a->B);
+  attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, st>>>(tq, tpq, tk, tpk, tv, tdo, *a, *g, dq_acc);
+  OFA_LAUNCH_CHECK("attn_bwd_tc_kernel");
+  attn_bwd_dq_convert_kernel<<<(unsigned)((nrow * 16 + 255) / 256), 256, 0, st>>>(
+      dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H);
+  OFA_LAUNCH_CHECK("attn_bwd_dq_convert_kernel");
   return 0;
 }

@@ -355,10 +355,15 @@ class _Attention(torch.autograd.Function):
         g.dtok_lut = dtok.data_ptr() if dtok is not None else None
         g.dimg_lut = dimg.data_ptr() if dimg is not None else None
         delta = torch.empty(B, H, T, dtype=torch.float32, device=q.device)
-        P = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
-        dS = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
-        g.delta, g.P, g.dS = delta.data_ptr(), P.data_ptr(), dS.data_ptr()
-        call("ofa_attn_bwd_simt", C.byref(a), C.byref(g), _dt(q), _st(), work=("flop", 2.0 * B * H * T * S * 512))
+        g.delta = delta.data_ptr()
+        if q.dtype == torch.bfloat16 and cfg.get("use_tc", True):
+            dq_acc = torch.empty(B * T * H * 128, dtype=torch.float32, device=q.device)
+            call("ofa_attn_bwd_tc", C.byref(a), C.byref(g), _p(dq_acc), _st(), work=("flop", 2.0 * B * H * T * S * 512))
+        else:
+            P = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
+            dS = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
+            g.P, g.dS = P.data_ptr(), dS.data_ptr()
+            call("ofa_attn_bwd_simt", C.byref(a), C.byref(g), _dt(q), _st(), work=("flop", 2.0 * B * H * T * S * 512))
         dhs = None
         if head_scale is not None:
             dhs = (delta.sum(dim=(0, 2)) / hs).to(head_scale.dtype)
