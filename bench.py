@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--profile-kernels", type=int, default=1)
+    ap.add_argument("--graph", type=int, default=1, help="replay the micro-step as a CUDA graph (0: eager launches)")
     return ap.parse_args()
 
 
@@ -151,19 +152,32 @@ def main():
     resident = [to_device(h, dev, torch.bfloat16) for h in host]
     h2d = batch_bytes(host[0])
 
-    def step(group, e2e=False):
-        if e2e:
-            group = to_device(group, dev, torch.bfloat16)
+    graphed = None
+    if a.graph:
+        from musketeer_b200.graphed import GraphedTrainStep
+        graphed = GraphedTrainStep(model, crit, dev, torch.bfloat16)
+
+    def eager_step(group):
         for p in model.parameters():
             p.grad = None
-        if reducer is not None:
-            reducer.prepare()
         loss, ss, log = crit(model, [dict(g, net_input=dict(g["net_input"])) for g in group])
         loss.backward()
+        return loss
+
+    def step(group, e2e=False, eager=False):
+        """group: device-resident batches (value) or pinned host batches (e2e: H2D copy inside the step, loss read back)."""
         if reducer is not None:
-            reducer.finish()
+            reducer.prepare()
+        if graphed is not None and not eager:
+            loss, _ = graphed(group)
+        else:
+            if e2e:
+                group = to_device(group, dev, torch.bfloat16)
+            loss = eager_step(group)
+        if reducer is not None:
+            reducer.reduce_all() if graphed is not None and not eager else reducer.finish()
         if e2e:
-            return float(loss.detach())     # device -> host read of the step's result
+            return float(loss)     # device -> host read of the step's result
         return loss
 
     def timed(nsteps, e2e):
@@ -188,14 +202,25 @@ def main():
     torch.cuda.synchronize()
     l0 = _lib.LAUNCHES
     sampler = ClockSampler(local) if rank == 0 else None
-    if a.profile_kernels:
-        _lib.PROFILE = {}
     ms = timed(a.steps, False)
-    prof = _lib.PROFILE
-    _lib.PROFILE = None
-    launches = _lib.LAUNCHES - l0
     ms_e2e = timed(a.steps, True)
     clocks = sampler.stop() if sampler else None
+    # kernel launches of one step (counted on an eager step: a graph replay re-issues exactly these launches)
+    l0 = _lib.LAUNCHES
+    step(resident[0], eager=True)
+    launches = (_lib.LAUNCHES - l0) * a.steps
+    # per-kernel CUDA-event timing: the same K steps repeated with an event pair around every C-ABI launch (eager, because
+    # events cannot bracket nodes inside a graph replay); used for the roofline object only, never for `value`
+    prof = None
+    if a.profile_kernels:
+        _lib.PROFILE = {}
+        torch.cuda.synchronize()
+        for i in range(a.steps):
+            step(resident[i % n_batches], eager=True)
+        torch.cuda.synchronize()
+        prof = _lib.PROFILE
+        _lib.PROFILE = None
+        ms_prof = sum(r[0].elapsed_time(r[1]) for recs in prof.values() for r in recs)
     if rank != 0:
         return
 
@@ -214,17 +239,17 @@ def main():
             tot[name] = (t, w, len(recs))
         top = max(tot, key=lambda k: tot[k][0])
         t, w, n = tot[top]
-        share = {k: round(v[0] / ms, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:6]}
+        share = {k: round(v[0] / ms_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:6]}
         if "flop" in w:
             ach = w["flop"] / (t / 1e3) / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_kind + " (sustained: timed inside a long step)",
-                    "launches": n, "avg_launch_us": t * 1e3 / n, "share_of_step": share}
+                    "launches": n, "avg_launch_us": t * 1e3 / n, "share_of_library_kernel_time": share}
         else:
             ach = w.get("byte", 0.0) / (t / 1e3) / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind, "launches": n,
-                    "avg_launch_us": t * 1e3 / n, "share_of_step": share}
+                    "avg_launch_us": t * 1e3 / n, "share_of_library_kernel_time": share}
         g = tot.get("ofa_gemm_bf16")
         if g and top != "ofa_gemm_bf16":
             roof["gemm_tflops"] = g[1].get("flop", 0.0) / (g[0] / 1e3) / 1e12
@@ -238,7 +263,8 @@ def main():
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "arch": a.arch, "l2": "activations and weights per step exceed the 126 MB L2",
-                   "optimizer_step": "not in the timed region (SURVEY.md 8f next row)", "dropout": 0.0},
+                   "optimizer_step": "not in the timed region (SURVEY.md 8f next row)", "dropout": 0.0,
+                   "launch": "CUDA graph replay" if a.graph else "eager"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": samples * a.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},

@@ -71,11 +71,13 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
             target[:, :self.ignore_prefix_size] = self.padding_idx
         if self.ignore_eos:                                                             # :244-250
             target = target.masked_fill(target.eq(self.eos_idx), self.padding_idx)
-        ntokens_t = target.ne(self.padding_idx).sum()
         loss, nll_rows = ops.ls_cross_entropy(
             logits, target, self.eps, self.padding_idx, cmask=sample.get("constraint_masks"), conf=sample.get("conf"),
             crange=self.constraint_range, rdrop=self.use_rdrop, reg_alpha=self.reg_alpha)
-        ntokens = int(ntokens_t)          # the reference syncs here too (boolean-mask indexing, :258-260)
+        if self.ignore_prefix_size > 0 or self.ignore_eos or "ntokens" not in sample:
+            ntokens = int(target.ne(self.padding_idx).sum())   # host sync, like the reference's boolean indexing (:258-260)
+        else:
+            ntokens = sample["ntokens"]    # the collater's count of non-pad target tokens: same number, no device sync
         sample_size = sample["target"].size(0) if self.sentence_avg else ntokens
         logging_output = {"loss": loss.data, "nll_loss": nll_rows.sum().data, "ntokens": sample["ntokens"],
                           "nsentences": sample["nsentences"], "sample_size": sample_size}

@@ -100,3 +100,11 @@ class GradReducer:
                     p.grad.copy_(flat[off:off + n].view_as(p))
                 off += n
         self._pending = None
+
+    def reduce_all(self):
+        """Reduce every bucket now (used after a CUDA-graph replay, where autograd hooks do not fire)."""
+        self.prepare()
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        self._pending = [0] * len(self.buckets)
+        self.finish()

@@ -1,0 +1,78 @@
+"""CUDA-graph training micro-step.  The OFA micro-step is ~3000 small kernel launches (five task forwards, one backward);
+replaying it as one graph removes the Python / launch overhead that otherwise hides the GPU work (the
+reference additionally blocks the host four times per forward).  One graph per shape signature; inputs are copied into
+static device buffers (pinned host -> device, asynchronous) before each replay.
+
+Constraints: shapes are static per signature (the Musketeer loader would bucket / pad lengths), no host-side randomness
+inside the step (patch sampling must come in as a `patch_orders` tensor), gradients live in the graph's memory pool and
+are overwritten by every replay (the optimizer reads them in place)."""
+import torch
+
+from .synthetic import map_tensors
+
+
+def _signature(obj):
+    if isinstance(obj, torch.Tensor):
+        return (tuple(obj.shape), str(obj.dtype))
+    if isinstance(obj, dict):
+        return tuple((k, _signature(v)) for k, v in sorted(obj.items()))
+    if isinstance(obj, (list, tuple)):
+        return tuple(_signature(v) for v in obj)
+    return obj if isinstance(obj, (int, float, bool, str, type(None))) else str(type(obj))
+
+
+def _copy_into(dst, src):
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_into(dst[k], src[k])
+    elif isinstance(dst, list):
+        for d, s in zip(dst, src):
+            _copy_into(d, s)
+
+
+class GraphedTrainStep:
+    def __init__(self, model, criterion, device, float_dtype, warmup=2):
+        self.model, self.criterion, self.device, self.float_dtype = model, criterion, device, float_dtype
+        self.warmup = warmup
+        self.cache = {}
+
+    def _run(self, static):
+        samples = [dict(s, net_input=dict(s["net_input"])) for s in static] if isinstance(static, list) else \
+            dict(static, net_input=dict(static["net_input"]))
+        loss, ss, log = self.criterion(self.model, samples)
+        loss.backward()
+        return loss, ss
+
+    def _capture(self, samples):
+        static = map_tensors(samples, lambda t: torch.empty(
+            t.shape, device=self.device, dtype=self.float_dtype if t.is_floating_point() else t.dtype))
+        _copy_into(static, samples)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                for p in self.model.parameters():
+                    p.grad = None
+                self._run(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in self.model.parameters():
+            p.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss, ss = self._run(static)
+        return {"graph": graph, "static": static, "loss": loss.detach(), "sample_size": ss}
+
+    def __call__(self, samples):
+        """samples: host (ideally pinned) or device tensors in the reference `sample` layout.  Returns (loss tensor, sample_size);
+        parameter .grad fields hold the gradients of this micro-step after the call."""
+        sig = _signature(samples)
+        e = self.cache.get(sig)
+        if e is None:
+            e = self.cache[sig] = self._capture(samples)
+        else:
+            _copy_into(e["static"], samples)
+        e["graph"].replay()
+        return e["loss"], e["sample_size"]
