@@ -199,6 +199,7 @@ def main():
 
     for i in range(a.warmup):
         step(resident[i % n_batches])
+        step(host[i % n_batches], e2e=True)      # also captures the graph for the host-dtype signature
     torch.cuda.synchronize()
     l0 = _lib.LAUNCHES
     sampler = ClockSampler(local) if rank == 0 else None

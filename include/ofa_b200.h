@@ -24,7 +24,9 @@ int ofa_abi_version(void);
 int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, long long lda, long long ldb,
                   long long ldd, long long stride_a, long long stride_b, long long stride_d, int a_mn_major,
                   int b_mn_major, int out_dtype, const void* bias, float alpha, int act, const void* resid,
-                  long long ldr, long long stride_r, void* stream);
+                  long long ldr, long long stride_r, void* workspace, long long workspace_bytes, void* stream);
+/* host helper: bytes of fp32 split-K scratch the call above wants for this problem (0 = none; passing less is legal) */
+long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch);
 
 /* fp32 -> three bf16 terms laid out as six K-blocks (fp32 parity mode operands for ofa_gemm_bf16) */
 int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, long long ldo, long long blk_stride,

@@ -36,7 +36,8 @@ class OfaAttnGrads(C.Structure):
 SIGNATURES = {
     "ofa_abi_version": [],
     "ofa_gemm_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_p, c_f,
-                      c_i, c_p, c_ll, c_ll, c_p],
+                      c_i, c_p, c_ll, c_ll, c_p, c_ll, c_p],
+    "ofa_gemm_workspace_bytes": [c_i, c_i, c_i, c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],
@@ -77,7 +78,7 @@ def load(path=None):
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = c_i
+        fn.restype = c_ll if name.endswith("_bytes") else c_i
     _lib = lib
     return lib
 

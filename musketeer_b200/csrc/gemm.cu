@@ -1,7 +1,12 @@
-// bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM), operands staged by TMA
-// into 128B-swizzled shared memory, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer, warps2-5 = epilogue.
+// bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores: persistent, warp-specialised, TMA + tcgen05 + TMEM.
 //
 //   D[b][m][n] = epi( sum_k A[b](m,k) * B[b](n,k) )          epi(v) = act((v + bias[n]) * alpha) + resid[m][n]
+//
+// One CTA per SM loops over 128 x BN output tiles (BN = 128 or 256).  warp0 = TMA producer (kStages-deep ring of
+// 128B-swizzled A/B stages), warp1 = single-thread tcgen05.mma issuer, warps2-5 = epilogue.  The fp32 accumulator is
+// double-buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i+1.  Problems with
+// few tiles and a long contraction (weight gradients: K = tokens) are split along K; the slices land in an fp32
+// workspace and a small kernel reduces them and applies the epilogue.
 //
 // Operand storage ("major"):  K-major  = row-major [rows=M|N][K]   (Linear forward: X[M,K], W[N,K])
 //                             MN-major = row-major [K][rows=M|N]   (dgrad: W as [N'=K][..]; wgrad: dY^T, X^T views)
@@ -12,29 +17,37 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 3;
-constexpr int kStageBytes = (BM * BK + BN * BK) * 2;  // 32 KiB
-constexpr int kTmemCols = 128;
+constexpr int BM = 128, BK = 64;
 constexpr int kThreads = 192;
+constexpr int kNumSMs = 148;
 
 struct GemmParams {
   void* D;
   const void* bias;    // [N] (OutT) or null
   const void* resid;   // [M, ldr] (OutT) or null
+  float* ws;           // split-K workspace [splits][batch][M][N] fp32 (splits > 1)
   long long ldd, ldr;  // elements
   long long batch_stride_d, batch_stride_r;
   int M, N, K;
+  int tiles_m, tiles_n, batch, splits, kb_per_split;
   float alpha;
   int act;  // 0 none, 1 gelu(erf)
 };
 
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+template <int BN>
 struct SmemLayout {
-  // tiles first (1024B aligned for SWIZZLE_128B), then barriers
-  uint8_t tiles[kStages][kStageBytes];
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
-  uint64_t tmem_full;
+  uint8_t tiles[Cfg<BN>::kStages][Cfg<BN>::kStageBytes];  // 1024B aligned (SWIZZLE_128B)
+  uint64_t full[Cfg<BN>::kStages];
+  uint64_t empty[Cfg<BN>::kStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
   uint32_t tmem_addr;
 };
 
@@ -45,50 +58,106 @@ __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p;
 template <>
 __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
-template <int A_MN, int B_MN, typename OutT>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+struct Work {
+  int mt, nt, bz, sp;
+};
+__device__ __forceinline__ Work decode(int w, const GemmParams& p) {
+  Work r;
+  r.nt = w % p.tiles_n;  // n fastest: CTAs running concurrently share the A row-block through L2
+  w /= p.tiles_n;
+  r.mt = w % p.tiles_m;
+  w /= p.tiles_m;
+  r.sp = w % p.splits;
+  r.bz = w / p.splits;
+  return r;
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_row32(OutT* dp, const float (&v)[32], int nvalid) {
+  const bool vec_ok = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
+  if (sizeof(OutT) == 2) {
+    if (vec_ok) {
+      uint4* d4 = reinterpret_cast<uint4*>(dp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        d4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dp);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) d[j] = __float2bfloat16(v[j]);
+    }
+  } else {
+    if (vec_ok) {
+      float4* d4 = reinterpret_cast<float4*>(dp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      float* d = reinterpret_cast<float*>(dp);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) d[j] = v[j];
+    }
+  }
+}
+
+template <int A_MN, int B_MN, typename OutT, int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using C = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  SmemLayout<BN>& sm =
+      *reinterpret_cast<SmemLayout<BN>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
-  const int nkb = (p.K + BK - 1) / BK;
+  const int total = p.tiles_m * p.tiles_n * p.batch * p.splits;
+  const int nkb_all = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
-    mbar_init(&sm.tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.tmem_full[i], 1);
+      mbar_init(&sm.tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(&sm.tmem_addr);
+  if (warp == 2) tmem_alloc<C::kTmemCols>(&sm.tmem_addr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = sm.tmem_addr;
+  const uint32_t tmem_base = sm.tmem_addr;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        mbar_wait(&sm.empty[s], (it & 1) ^ 1);
-        mbar_expect_tx(&sm.full[s], kStageBytes);
-        uint8_t* sa = sm.tiles[s];
-        uint8_t* sb = sa + BM * BK * 2;
-        if (A_MN) {
-          tma_load_3d(sa, &tmA, &sm.full[s], m0, kb * BK, bz);
-          tma_load_3d(sa + BK * 128, &tmA, &sm.full[s], m0 + 64, kb * BK, bz);
-        } else {
-          tma_load_3d(sa, &tmA, &sm.full[s], kb * BK, m0, bz);
-        }
-        if (B_MN) {
-          tma_load_3d(sb, &tmB, &sm.full[s], n0, kb * BK, bz);
-          tma_load_3d(sb + BK * 128, &tmB, &sm.full[s], n0 + 64, kb * BK, bz);
-        } else {
-          tma_load_3d(sb, &tmB, &sm.full[s], kb * BK, n0, bz);
+      int s = 0, ph = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const Work wk = decode(w, p);
+        const int m0 = wk.mt * BM, n0 = wk.nt * BN;
+        const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&sm.empty[s], ph ^ 1);
+          mbar_expect_tx(&sm.full[s], C::kStageBytes);
+          uint8_t* sa = sm.tiles[s];
+          uint8_t* sb = sa + BM * BK * 2;
+          if (A_MN) {
+            tma_load_3d(sa, &tmA, &sm.full[s], m0, kb * BK, wk.bz);
+            tma_load_3d(sa + BK * 128, &tmA, &sm.full[s], m0 + 64, kb * BK, wk.bz);
+          } else {
+            tma_load_3d(sa, &tmA, &sm.full[s], kb * BK, m0, wk.bz);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * BK * 128, &tmB, &sm.full[s], n0 + 64 * c, kb * BK, wk.bz);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) tma_load_3d(sb + c * 128 * 128, &tmB, &sm.full[s], kb * BK, n0 + 128 * c, wk.bz);
+          }
+          if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -96,121 +165,192 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        mbar_wait(&sm.full[s], it & 1);
+      int s = 0, ph = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const Work wk = decode(w, p);
+        const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        mbar_wait(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(sm.tiles[s]);
-        const uint32_t sb = sa + BM * BK * 2;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&sm.full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sm.tiles[s]);
+          const uint32_t sb = sa + BM * BK * 2;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 16 bf16 = 32 B inside the 128B swizzle span; MN-major: 16 k-rows = 2 swizzle atoms = 2048 B
-          const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
-          umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 bf16 = 32 B inside the 128B swizzle span; MN-major: 16 k-rows = 2 swizzle atoms = 2048 B.
+            // K-major B with BN = 256 is two 128-row boxes back to back: rows continue at the same 1024 B / 8-row pitch.
+            const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16(tmem_d, da, db, idesc, (kb != kb0) | (k != 0));
+          }
+          umma_commit(&sm.empty[s]);  // frees the smem stage when these MMAs retire
+          if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&sm.empty[s]);  // frees the smem stage when these MMAs retire
+        umma_commit(&sm.tmem_full[acc]);
       }
-      umma_commit(&sm.tmem_full);
     }
     __syncwarp();
   } else {
     // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(&sm.tmem_full, 0);
-    tc_fence_after();
-    OutT* D = reinterpret_cast<OutT*>(p.D) + (long long)bz * p.batch_stride_d;
-    const OutT* R = p.resid ? reinterpret_cast<const OutT*>(p.resid) + (long long)bz * p.batch_stride_r : nullptr;
-    const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const Work wk = decode(w, p);
+      const int m0 = wk.mt * BM, n0 = wk.nt * BN;
+      const int acc = it & 1;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      if (p.splits > 1) {
+        float* W = p.ws + ((size_t)(wk.sp * p.batch + wk.bz) * p.M) * p.N;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (row < p.M && nb < p.N) {
-        float v[32];
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_d + c * 32, r);
+          tmem_ld_wait();
+          const int nb = n0 + c * 32;
+          if (row < p.M && nb < p.N) {
+            float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int nvalid = min(32, p.N - nb);
-        if (bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += ld_as_float<OutT>(bias + nb + j);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (R) {
-          const OutT* rr = R + (long long)row * p.ldr + nb;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += ld_as_float<OutT>(rr + j);
-        }
-        OutT* dp = D + (long long)row * p.ldd + nb;
-        const bool vec_ok = (nvalid == 32) && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
-        if (sizeof(OutT) == 2) {
-          if (vec_ok) {
-            uint4* d4 = reinterpret_cast<uint4*>(dp);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              d4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          } else {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dp);
-            for (int j = 0; j < nvalid; ++j) d[j] = __float2bfloat16(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            store_row32<float>(W + (size_t)row * p.N + nb, v, min(32, p.N - nb));
           }
-        } else {
-          if (vec_ok) {
-            float4* d4 = reinterpret_cast<float4*>(dp);
+        }
+      } else {
+        OutT* D = reinterpret_cast<OutT*>(p.D) + (long long)wk.bz * p.batch_stride_d;
+        const OutT* R = p.resid ? reinterpret_cast<const OutT*>(p.resid) + (long long)wk.bz * p.batch_stride_r : nullptr;
+        const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_d + c * 32, r);
+          tmem_ld_wait();
+          const int nb = n0 + c * 32;
+          if (row < p.M && nb < p.N) {
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            float* d = reinterpret_cast<float*>(dp);
-            for (int j = 0; j < nvalid; ++j) d[j] = v[j];
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int nvalid = min(32, p.N - nb);
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += ld_as_float<OutT>(bias + nb + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (R) {
+              const OutT* rr = R + (long long)row * p.ldr + nb;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += ld_as_float<OutT>(rr + j);
+            }
+            store_row32<OutT>(D + (long long)row * p.ldd + nb, v, nvalid);
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);  // accumulator buffer may be overwritten
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_d);
+    tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
-template <int A_MN, int B_MN, typename OutT>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int batch, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<A_MN, B_MN, OutT>;
+// out[b][m][n] = epi(sum_sp ws[sp][b][m][n])
+template <typename OutT>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)p.M * p.N;
+  if (idx >= per * p.batch) return;
+  const int bz = (int)(idx / per);
+  const long long mn = idx % per;
+  const int m = (int)(mn / p.N), n = (int)(mn % p.N);
+  float v = 0.f;
+  for (int sp = 0; sp < p.splits; ++sp) v += p.ws[((size_t)(sp * p.batch + bz)) * per + mn];
+  if (p.bias) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.bias) + n);
+  v *= p.alpha;
+  if (p.act == 1) v = gelu_erf(v);
+  if (p.resid) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.resid) + (long long)bz * p.batch_stride_r + (long long)m * p.ldr + n);
+  reinterpret_cast<OutT*>(p.D)[(long long)bz * p.batch_stride_d + (long long)m * p.ldd + n] = (OutT)v;
+}
+
+template <int A_MN, int B_MN, typename OutT, int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<A_MN, B_MN, OutT, BN>;
   static bool configured = false;  // per template instantiation
-  const int smem = (int)sizeof(SmemLayout) + 1024;
+  const int smem = (int)sizeof(SmemLayout<BN>) + 1024;
   if (!configured) {
     OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
-  kern<<<grid, kThreads, smem, st>>>(ta, tb, p);
+  const int total = p.tiles_m * p.tiles_n * p.batch * p.splits;
+  kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, p);
   OFA_LAUNCH_CHECK("gemm_tc_kernel");
+  if (p.splits > 1) {
+    const long long n = (long long)p.M * p.N * p.batch;
+    splitk_reduce_kernel<OutT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    OFA_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
   return 0;
 }
 
+template <int A_MN, int B_MN, typename OutT>
+int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  return bn == 256 ? launch<A_MN, B_MN, OutT, 256>(ta, tb, p, st) : launch<A_MN, B_MN, OutT, 128>(ta, tb, p, st);
+}
+
+void plan(int M, int N, int K, int batch, int* bn, int* splits) {
+  const int tm = (M + BM - 1) / BM;
+  const int nkb = (K + BK - 1) / BK;
+  // 128 x 256 tiles only when they still give every SM at least two tiles
+  *bn = (N >= 512 && (long long)tm * ((N + 255) / 256) * batch >= 2 * kNumSMs) ? 256 : 128;
+  const long long tiles = (long long)tm * ((N + *bn - 1) / *bn) * batch;
+  int s = 1;
+  if (tiles * 2 <= kNumSMs && nkb >= 8) {
+    s = (int)(kNumSMs / tiles);
+    if (s > nkb / 4) s = nkb / 4;
+    if (s > 32) s = 32;
+    if (s < 1) s = 1;
+  }
+  *splits = s;
+}
+
 }  // namespace
+
+// host helper: bytes of fp32 split-K workspace ofa_gemm_bf16 wants for this problem (0 = none)
+extern "C" long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch) {
+  int bn, splits;
+  plan(M, N, K, batch, &bn, &splits);
+  return splits > 1 ? (long long)splits * batch * M * N * (long long)sizeof(float) : 0;
+}
 
 // see include/ofa_b200.h
 extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, long long lda,
                              long long ldb, long long ldd, long long stride_a, long long stride_b, long long stride_d,
                              int a_mn_major, int b_mn_major, int out_dtype, const void* bias, float alpha, int act,
-                             const void* resid, long long ldr, long long stride_r, void* stream) {
+                             const void* resid, long long ldr, long long stride_r, void* workspace,
+                             long long workspace_bytes, void* stream) {
   OFA_CHECK(M > 0 && N > 0 && K > 0 && batch > 0, "ofa_gemm_bf16: empty problem M=%d N=%d K=%d batch=%d", M, N, K, batch);
   OFA_CHECK(lda % 8 == 0 && ldb % 8 == 0, "ofa_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16B stride)");
   OFA_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "ofa_gemm_bf16: A/B must be 16B aligned");
   OFA_CHECK(stride_a % 8 == 0 && stride_b % 8 == 0, "ofa_gemm_bf16: batch strides must be multiples of 8 elements");
+  int bn, splits;
+  plan(M, N, K, batch, &bn, &splits);
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < (long long)splits * batch * M * N * (long long)sizeof(float)))
+    splits = 1;  // no workspace: run unsplit (still correct, just fewer CTAs)
   CUtensorMap ta, tb;
   {
     // K-major: dims {K, rows, batch}, box {64, 128, 1};  MN-major: dims {rows, K, batch}, box {64, 64, 1}
@@ -223,30 +363,34 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     strides[1] = (uint64_t)(batch > 1 ? stride_a : (long long)dims[1] * lda) * 2;
     if (int e = ofa_make_tmap(&ta, A, 3, dims, strides, box, 1, 2)) return e;
     if (b_mn_major) { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
-    else            { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = BN; }
+    else            { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = 128; }
     strides[0] = (uint64_t)ldb * 2;
     strides[1] = (uint64_t)(batch > 1 ? stride_b : (long long)dims[1] * ldb) * 2;
     if (int e = ofa_make_tmap(&tb, B, 3, dims, strides, box, 1, 2)) return e;
   }
   GemmParams p;
-  p.D = D; p.bias = bias; p.resid = resid; p.ldd = ldd; p.ldr = ldr;
+  p.D = D; p.bias = bias; p.resid = resid; p.ws = (float*)workspace; p.ldd = ldd; p.ldr = ldr;
   p.batch_stride_d = stride_d; p.batch_stride_r = stride_r;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
+  p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + bn - 1) / bn; p.batch = batch; p.splits = splits;
+  const int nkb = (K + BK - 1) / BK;
+  p.kb_per_split = (nkb + splits - 1) / splits;
+  p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty trailing slices
   cudaStream_t st = (cudaStream_t)stream;
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   if (out_dtype == OFA_BF16) {
     switch (sel) {
-      case 0: return launch<0, 0, __nv_bfloat16>(ta, tb, p, batch, st);
-      case 1: return launch<0, 1, __nv_bfloat16>(ta, tb, p, batch, st);
-      case 2: return launch<1, 0, __nv_bfloat16>(ta, tb, p, batch, st);
-      default: return launch<1, 1, __nv_bfloat16>(ta, tb, p, batch, st);
+      case 0: return launch_bn<0, 0, __nv_bfloat16>(bn, ta, tb, p, st);
+      case 1: return launch_bn<0, 1, __nv_bfloat16>(bn, ta, tb, p, st);
+      case 2: return launch_bn<1, 0, __nv_bfloat16>(bn, ta, tb, p, st);
+      default: return launch_bn<1, 1, __nv_bfloat16>(bn, ta, tb, p, st);
     }
   } else if (out_dtype == OFA_F32) {
     switch (sel) {
-      case 0: return launch<0, 0, float>(ta, tb, p, batch, st);
-      case 1: return launch<0, 1, float>(ta, tb, p, batch, st);
-      case 2: return launch<1, 0, float>(ta, tb, p, batch, st);
-      default: return launch<1, 1, float>(ta, tb, p, batch, st);
+      case 0: return launch_bn<0, 0, float>(bn, ta, tb, p, st);
+      case 1: return launch_bn<0, 1, float>(bn, ta, tb, p, st);
+      case 2: return launch_bn<1, 0, float>(bn, ta, tb, p, st);
+      default: return launch_bn<1, 1, float>(bn, ta, tb, p, st);
     }
   }
   return ofa_set_error("ofa_gemm_bf16: bad out_dtype %d", out_dtype);

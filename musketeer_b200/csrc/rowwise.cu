@@ -191,15 +191,25 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
   }
 }
 
+// sums the [nparts, C] fp32 partials: block = 32 columns x 8 partial-lanes, coalesced along columns
 template <typename T>
-__global__ void ln_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int nparts,
-                                     int C, T* __restrict__ dgamma, T* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float g = 0.f, b = 0.f;
-  for (int p = 0; p < nparts; ++p) { g += part_g[(size_t)p * C + c]; b += part_b[(size_t)p * C + c]; }
-  dgamma[c] = (T)g;
-  dbeta[c] = (T)b;
+__global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b,
+                                                            int nparts, int C, T* __restrict__ dgamma, T* __restrict__ dbeta) {
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const float* src = blockIdx.y ? part_b : part_g;
+  float s = 0.f;
+  if (c < C)
+    for (int p = py; p < nparts; p += 8) s += src[(size_t)p * C + c];
+  __shared__ float red[8][33];
+  red[py][cx] = s;
+  __syncthreads();
+  if (py == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    (blockIdx.y ? dbeta : dgamma)[c] = (T)t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,21 +217,36 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part_g, const flo
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long ld, int rows, int C,
-                                                             float* __restrict__ part) {
-  // block = 32 columns x 8 row-lanes; grid.x = column tiles, grid.y = row slices
+                                                             float* __restrict__ part, int vec_ok) {
+  // block = 32 lanes (8 consecutive columns each -> 256 columns) x 8 row-lanes; grid.x = column tiles, grid.y = row slices
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float s = 0.f;
-  if (c < C)
-    for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) s += (float)x[(size_t)r * ld + c];
-  __shared__ float red[8][33];
-  red[ry][cx] = s;
+  const int c = blockIdx.x * 256 + cx * 8;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (c < C) {
+    if (vec_ok && c + 8 <= C) {
+      for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8) {
+        float v[8];
+        Vec8<T>::load(x + (size_t)r * ld + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += v[j];
+      }
+    } else {
+      for (int r = blockIdx.y * 8 + ry; r < rows; r += gridDim.y * 8)
+        for (int j = 0; j < 8 && c + j < C; ++j) s[j] += (float)x[(size_t)r * ld + c + j];
+    }
+  }
+  __shared__ float red[8][32 * 8 + 8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cx * 8 + j] = s[j];
   __syncthreads();
-  if (ry == 0 && c < C) {
+  const int col = threadIdx.x;   // 256 threads -> 256 columns of this tile
+  if (blockIdx.x * 256 + col < C) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][cx];
-    part[(size_t)blockIdx.y * C + c] = t;
+    for (int i = 0; i < 8; ++i) t += red[i][col];
+    part[(size_t)blockIdx.y * C + blockIdx.x * 256 + col] = t;
   }
 }
 template <typename T>
@@ -395,11 +420,11 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   if (dtype == OFA_BF16) {
     rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<__nv_bfloat16, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
     if (rc) return rc;
-    ln_bwd_reduce_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+    ln_bwd_reduce_kernel<__nv_bfloat16><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
   } else if (dtype == OFA_F32) {
     rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<float, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
     if (rc) return rc;
-    ln_bwd_reduce_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta);
+    ln_bwd_reduce_kernel<float><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta);
   } else {
     return ofa_set_error("ofa_layernorm_bwd: bad dtype %d", dtype);
   }
@@ -411,14 +436,16 @@ extern "C" int ofa_colsum(const void* x, long long ld, int rows, int C, void* ou
                           void* stream) {
   OFA_CHECK(rows > 0 && C > 0, "ofa_colsum: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-  int ny = (rows + 63) / 64;
-  if (ny > 64) ny = 64;  // workspace: 64 * C floats
-  dim3 grid((C + 31) / 32, ny);
+  int ny = (rows + 31) / 32;
+  if (ny > 32) ny = 32;  // workspace: 64 * C floats
+  dim3 grid((C + 255) / 256, ny);
+  const int esz = dtype == OFA_BF16 ? 2 : 4;
+  const int vec_ok = (((uintptr_t)x & 15) == 0) && ((ld * esz) % 16 == 0);
   if (dtype == OFA_BF16) {
-    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, workspace);
+    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, workspace, vec_ok);
     colsum_final_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (__nv_bfloat16*)out);
   } else if (dtype == OFA_F32) {
-    colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, C, workspace);
+    colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, C, workspace, vec_ok && (ld * 4) % 32 == 0 && ((uintptr_t)x & 31) == 0);
     colsum_final_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (float*)out);
   } else {
     return ofa_set_error("ofa_colsum: bad dtype %d", dtype);

@@ -39,6 +39,9 @@ class GraphedTrainStep:
         self.cache = {}
 
     def _run(self, static):
+        # float inputs are cast to the model dtype on the device, inside the graph (trainer._prepare_sample semantics,
+        # trainer.py:1227-1244) -- the staging buffers keep the host dtype so the H2D copy is a plain DMA
+        static = map_tensors(static, lambda t: t.to(self.float_dtype) if t.is_floating_point() else t)
         samples = [dict(s, net_input=dict(s["net_input"])) for s in static] if isinstance(static, list) else \
             dict(static, net_input=dict(static["net_input"]))
         loss, ss, log = self.criterion(self.model, samples)
@@ -46,8 +49,7 @@ class GraphedTrainStep:
         return loss, ss
 
     def _capture(self, samples):
-        static = map_tensors(samples, lambda t: torch.empty(
-            t.shape, device=self.device, dtype=self.float_dtype if t.is_floating_point() else t.dtype))
+        static = map_tensors(samples, lambda t: torch.empty(t.shape, device=self.device, dtype=t.dtype))
         _copy_into(static, samples)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

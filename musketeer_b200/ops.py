@@ -82,8 +82,10 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
         assert bias.dtype == out_dtype
     if resid is not None:
         assert resid.dtype == out_dtype and resid.stride(-1) == 1
+    wsb = _lib.load().ofa_gemm_workspace_bytes(M, N, Kk, 1)
+    ws = torch.empty(wsb // 4, dtype=torch.float32, device=A.device) if wsb > 0 else None
     call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
-         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _st(),
+         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _p(ws), wsb, _st(),
          work=("flop", 2.0 * M * N * K))
     return out
 

@@ -15,7 +15,8 @@ def _ops():
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (61, 59457 // 64, 256), (5, 72, 1000)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (61, 59457 // 64, 256), (5, 72, 1000),
+                                   (4096, 3072, 768), (768, 768, 6680), (40, 768, 768), (2000, 4099, 256)])
 def test_gemm_bf16(a_mn, b_mn, M, N, K):
     ops = _ops()
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
