@@ -469,9 +469,7 @@ class TransformerDecoder(nn.Module):
             x = _ln(self.layernorm_embedding, x)
         if incremental:
             st = incremental_state.setdefault("_ofa_b200", {})
-            if "cpk" not in st or st.get("enc_id") is not enc_pad:
-                st.clear()
-                st["enc_id"] = enc_pad
+            if "cpk" not in st:       # first step: project the encoder side once (static_kv, :207-209,275-276)
                 st["cpk"] = _lin(self.cross_pos_k_linear, src_pos.contiguous())
                 st["cross"] = [layer.encoder_attn.project_kv(enc) for layer in self.layers]
                 st["self_k"] = [None] * self.num_layers

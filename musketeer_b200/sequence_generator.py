@@ -1,0 +1,202 @@
+"""Beam search over the incremental OFA decoder (models/sequence_generator.py:19-764 + fairseq BeamSearch.step as
+spelled out in models/search.py:109-144).  Same constructor arguments, `generate(models, sample, **kw)` signature and
+result layout (list over sentences of hypothesis dicts sorted by score: tokens / score / attention / alignment /
+positional_scores).  The per-step decoder work (one token per beam, KV appended to the cache, cross-attention K/V
+projected once) runs on the kernels of libofa_b200.so; the beam bookkeeping stays in torch index ops on the device.
+
+Out of scope here (raises): constraint tries, prefix tokens, image-code / box generation, LM fusion, ensembles > 1."""
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+class SequenceGenerator(torch.nn.Module):
+    def __init__(self, models, tgt_dict, beam_size=1, max_len_a=0, max_len_b=200, max_len=0, min_len=1,
+                 normalize_scores=True, len_penalty=1.0, unk_penalty=0.0, temperature=1.0, match_source_len=False,
+                 no_repeat_ngram_size=0, search_strategy=None, eos=None, symbols_to_strip_from_output=None,
+                 lm_model=None, lm_weight=1.0, constraint_trie=None, constraint_range=None, gen_code=False,
+                 gen_box=False, ignore_eos=False, zero_shot=False):
+        super().__init__()
+        models = list(models) if isinstance(models, (list, tuple)) else [models]
+        if len(models) != 1 or lm_model is not None:
+            raise NotImplementedError("ensembles / LM fusion are outside the hot-path scope")
+        if constraint_trie is not None or gen_code or gen_box or search_strategy is not None or match_source_len:
+            raise NotImplementedError("constraint tries, code/box generation and custom search strategies are outside "
+                                      "the hot-path scope (SURVEY.md 8f)")
+        self.model = models[0]
+        self.tgt_dict = tgt_dict
+        self.pad, self.unk, self.bos = tgt_dict.pad(), tgt_dict.unk(), tgt_dict.bos()
+        self.eos = tgt_dict.eos() if eos is None else eos
+        self.vocab_size = len(tgt_dict)
+        self.beam_size = min(beam_size, self.vocab_size - 1)
+        self.max_len_a, self.max_len_b, self.min_len = max_len_a, max_len_b, min_len
+        self.max_len = max_len or self.model.max_decoder_positions()
+        self.normalize_scores, self.len_penalty, self.unk_penalty = normalize_scores, len_penalty, unk_penalty
+        self.temperature = temperature
+        self.no_repeat_ngram_size = no_repeat_ngram_size
+        self.ignore_eos = ignore_eos
+        self.constraint_start = self.constraint_end = None
+        if constraint_range is not None:
+            cs, ce = constraint_range.split(",")
+            self.constraint_start, self.constraint_end = int(cs), int(ce)
+        assert temperature > 0, "--temperature must be greater than 0"
+        self.model.eval()
+
+    @torch.no_grad()
+    def forward(self, sample, prefix_tokens=None, bos_token=None):
+        return self._generate([self.model], sample, prefix_tokens, bos_token=bos_token)
+
+    @torch.no_grad()
+    def generate(self, models, sample, **kwargs):
+        return self._generate(models, sample, **kwargs)
+
+    def _ngram_block(self, tokens, lprobs, step):
+        n = self.no_repeat_ngram_size
+        if step + 2 - n < 0:
+            return lprobs
+        toks = tokens[:, :step + 1].tolist()
+        for r, gen in enumerate(toks):
+            key = gen[step + 2 - n: step + 1]
+            banned = [gen[i + n - 1] for i in range(len(gen) - n + 1) if gen[i:i + n - 1] == key]
+            if banned:
+                lprobs[r, banned] = -math.inf
+        return lprobs
+
+    def _generate(self, models, sample, prefix_tokens=None, constraints=None, bos_token=None):
+        if prefix_tokens is not None or constraints is not None:
+            raise NotImplementedError("prefix tokens / lexical constraints are outside the hot-path scope")
+        model = models[0] if isinstance(models, (list, tuple)) else models
+        net_input = sample["net_input"]
+        src_tokens = net_input["src_tokens"]
+        dev = src_tokens.device
+        bsz, src_len = src_tokens.shape[:2]
+        beam, V = self.beam_size, self.vocab_size
+        max_len = int(self.max_len_a * src_len + self.max_len_b)
+        assert self.min_len <= max_len, "min_len cannot be larger than max_len, please adjust these!"
+        enc = model.encoder.forward_torchscript(net_input)
+        order = torch.arange(bsz, device=dev).view(-1, 1).repeat(1, beam).view(-1)
+        enc = model.encoder.reorder_encoder_out(enc, order)
+        scores = torch.zeros(bsz * beam, max_len + 1, device=dev)
+        tokens = torch.full((bsz * beam, max_len + 2), self.pad, dtype=torch.long, device=dev)
+        tokens[:, 0] = self.bos
+        cands_to_ignore = torch.zeros(bsz, beam, dtype=torch.bool, device=dev)
+        finalized: List[List[Dict]] = [[] for _ in range(bsz)]
+        finished = [False] * bsz
+        num_remaining = bsz
+        cand_size = 2 * beam
+        bbsz_offsets = (torch.arange(bsz, device=dev) * beam).unsqueeze(1)
+        cand_offsets = torch.arange(cand_size, device=dev)
+        inc = {}
+        reorder_state = batch_idxs = None
+        for step in range(max_len + 1):
+            if reorder_state is not None:
+                if batch_idxs is not None:
+                    corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
+                    reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
+                model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
+                enc = model.encoder.reorder_encoder_out(enc, reorder_state)
+            logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
+            logits = logits[:, -1, :].float() / self.temperature
+            if self.constraint_start is not None:
+                logits[:, 4:self.constraint_start] = -math.inf
+                logits[:, self.constraint_end:] = -math.inf
+            lprobs = F.log_softmax(logits, dim=-1)
+            if step < self.min_len:
+                lprobs[:, self.eos] = -math.inf
+            lprobs[lprobs != lprobs] = -math.inf
+            lprobs[:, self.pad] = -math.inf
+            lprobs[:, self.unk] -= self.unk_penalty
+            if step >= max_len:
+                lprobs[:, :self.eos] = -math.inf
+                lprobs[:, self.eos + 1:] = -math.inf
+                if self.ignore_eos:
+                    lprobs[:, self.eos] = 1
+            if self.no_repeat_ngram_size > 0:
+                lprobs = self._ngram_block(tokens, lprobs, step)
+            lp3 = lprobs.view(bsz, -1, V)
+            if step == 0:
+                lp3 = lp3[:, ::beam, :].contiguous()
+            else:
+                lp3 = lp3 + scores.view(bsz, beam, -1)[:, :, step - 1].unsqueeze(-1)
+            flat = lp3.view(bsz, -1)
+            cand_scores, idx = torch.topk(flat, k=min(cand_size, flat.size(1) - 1))
+            cand_beams = idx // V
+            cand_indices = idx.fmod(V)
+            cand_bbsz_idx = cand_beams + bbsz_offsets
+            eos_mask = cand_indices.eq(self.eos) & cand_scores.ne(-math.inf)
+            eos_mask[:, :beam][cands_to_ignore] = False
+            eos_bbsz_idx = torch.masked_select(cand_bbsz_idx[:, :beam], eos_mask[:, :beam])
+            finalized_sents: List[int] = []
+            if eos_bbsz_idx.numel() > 0:
+                eos_scores = torch.masked_select(cand_scores[:, :beam], eos_mask[:, :beam])
+                finalized_sents = self._finalize(step, eos_bbsz_idx, eos_scores, tokens, scores, finalized, finished,
+                                                 beam, max_len)
+                num_remaining -= len(finalized_sents)
+            if num_remaining == 0:
+                break
+            assert step < max_len, f"{step} < {max_len}"
+            if len(finalized_sents) > 0:
+                new_bsz = bsz - len(finalized_sents)
+                batch_mask = torch.ones(bsz, dtype=torch.bool, device=dev)
+                batch_mask[finalized_sents] = False
+                batch_idxs = torch.arange(bsz, device=dev).masked_select(batch_mask)
+                eos_mask = eos_mask[batch_idxs]
+                cand_beams = cand_beams[batch_idxs]
+                bbsz_offsets = bbsz_offsets[:new_bsz]
+                cand_bbsz_idx = cand_beams + bbsz_offsets
+                cand_scores = cand_scores[batch_idxs]
+                cand_indices = cand_indices[batch_idxs]
+                cands_to_ignore = cands_to_ignore[batch_idxs]
+                scores = scores.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
+                tokens = tokens.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
+                bsz = new_bsz
+            else:
+                batch_idxs = None
+            eos_mask[:, :beam] = ~((~cands_to_ignore) & (~eos_mask[:, :beam]))
+            active_mask = eos_mask.long() * cand_size + cand_offsets[: eos_mask.size(1)]
+            new_ignore, active_hypos = torch.topk(active_mask, k=beam, dim=1, largest=False)
+            cands_to_ignore = new_ignore.ge(cand_size)[:, :beam]
+            active_bbsz_idx = torch.gather(cand_bbsz_idx, 1, active_hypos).view(-1)
+            tokens[:, :step + 1] = torch.index_select(tokens[:, :step + 1], 0, active_bbsz_idx)
+            tokens.view(bsz, beam, -1)[:, :, step + 1] = torch.gather(cand_indices, 1, active_hypos)
+            if step > 0:
+                scores[:, :step] = torch.index_select(scores[:, :step], 0, active_bbsz_idx)
+            scores.view(bsz, beam, -1)[:, :, step] = torch.gather(cand_scores, 1, active_hypos)
+            reorder_state = active_bbsz_idx
+        for s in range(len(finalized)):
+            sc = torch.tensor([float(h["score"]) for h in finalized[s]])
+            _, o = torch.sort(sc, descending=True)
+            finalized[s] = [finalized[s][i] for i in o]
+        return finalized
+
+    def _finalize(self, step, bbsz_idx, eos_scores, tokens, scores, finalized, finished, beam, max_len):
+        tokens_clone = tokens.index_select(0, bbsz_idx)[:, 1:step + 2].clone()
+        tokens_clone[:, step] = self.eos
+        pos_scores = scores.index_select(0, bbsz_idx)[:, :step + 1].clone()
+        pos_scores[:, step] = eos_scores
+        pos_scores[:, 1:] = pos_scores[:, 1:] - pos_scores[:, :-1]
+        if self.normalize_scores:
+            eos_scores = eos_scores / (step + 1) ** self.len_penalty
+        cum_unfin, prev = [], 0
+        for f in finished:
+            if f:
+                prev += 1
+            else:
+                cum_unfin.append(prev)
+        cum = torch.tensor(cum_unfin, dtype=torch.long, device=bbsz_idx.device)
+        unfin_idx = bbsz_idx // beam
+        sent = unfin_idx + cum.index_select(0, unfin_idx)
+        sent_l, unfin_l = sent.tolist(), unfin_idx.tolist()
+        for i in range(bbsz_idx.numel()):
+            if len(finalized[sent_l[i]]) < beam:
+                finalized[sent_l[i]].append({"tokens": tokens_clone[i], "score": eos_scores[i],
+                                             "attention": torch.empty(0), "alignment": torch.empty(0),
+                                             "positional_scores": pos_scores[i]})
+        newly = []
+        for s, u in sorted(set(zip(sent_l, unfin_l))):
+            if not finished[s] and (len(finalized[s]) == beam or step == max_len):
+                finished[s] = True
+                newly.append(u)
+        return newly

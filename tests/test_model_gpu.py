@@ -135,3 +135,41 @@ def test_state_dict_contract():
     model, _ = build_product(cfg, sd, device="cpu")
     msd = model.state_dict()
     assert list(msd.keys()) == [e[0] for e in spec["ofa_tiny"]["entries"]]
+
+
+@pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny"])
+def test_beam_search_tokens_bit_exact_fp32(name):
+    """fp32 mode: beam-search output token ids must equal the reference's bit for bit; scores within 1e-4."""
+    from musketeer_b200.sequence_generator import SequenceGenerator
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0, emb_std=case["emb_std"])
+    model, task = build_product(cfg, sd, dtype=torch.float32)
+    model.eval()
+    sample = to_device(synth.make_batch(**case["batch"]), "cuda")
+    gen = SequenceGenerator([model], task.target_dictionary, **case["gen"])
+    hyp = gen.generate([model], sample)
+    assert len(hyp) == len(fx["tokens"])
+    for s in range(len(hyp)):
+        assert len(hyp[s]) == len(fx["tokens"][s])
+        for h, t, sc in zip(hyp[s], fx["tokens"][s], fx["scores"][s]):
+            assert torch.equal(h["tokens"].cpu(), t), (s, h["tokens"].tolist(), t.tolist())
+            assert abs(float(h["score"]) - sc) < 1e-4
+
+
+def test_incremental_decoder_matches_teacher_forcing():
+    """Incremental decoding (KV cache) must reproduce the teacher-forced logits position by position (fp32, 1e-4)."""
+    fx = load_golden("micro_text_only")
+    cfg, sd, samples = build_case(fx["case"])
+    model, task = build_product(cfg, sd, dtype=torch.float32)
+    model.eval()
+    ni = to_device(copy.deepcopy(samples[0]["net_input"]), "cuda")
+    ni["prev_output_tokens"][ni["prev_output_tokens"].eq(1)] = 5      # no pads inside the decoded prefix
+    with torch.no_grad():
+        enc = model.encoder(ni["src_tokens"], src_lengths=ni["src_lengths"])
+        full, _ = model.decoder(ni["prev_output_tokens"], encoder_out=enc)
+        inc = {}
+        for t in range(ni["prev_output_tokens"].shape[1]):
+            step, _ = model.decoder(ni["prev_output_tokens"][:, :t + 1], encoder_out=enc, incremental_state=inc)
+            assert (step[:, -1].float() - full[:, t].float()).abs().max().item() < 1e-4, t
