@@ -51,6 +51,10 @@ int ofa_embed_scatter_add(const long long* idx, const void* dout, long long ldo,
 int ofa_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);
 int ofa_mask_rows(void* x, const unsigned char* rowmask, int rows, int C, int dtype, void* stream); /* :892-893 */
 int ofa_gelu(const void* x, const void* dy, void* out, long long n, int backward, int dtype, void* stream);
+/* y = resid + x * bernoulli_mask(seed) / (1-p) * row_scale[sample]: dropout + drop-path + residual in one pass
+ * (FairseqDropout + unify_transformer_layer.py:19-35,197-198); the backward is the same call on dy with resid = NULL */
+int ofa_dropout_residual(const void* x, const void* resid, void* y, long long n, int C, int rows_per_sample, float p,
+                         const float* row_scale, const unsigned long long* seed, int dtype, void* stream);
 
 /* ---- label-smoothed CE (+R-Drop KL): loss rows and d(logits) in one kernel, gradient written in place --------------
  * replaces criterions/label_smoothed_cross_entropy.py:81-126,228-260.                                                */

@@ -130,6 +130,20 @@ class MultiheadAttention(nn.Module):
 
 
 class _FFNMixin:
+    def _stochastic(self):
+        return self.training and (self.dropout_p > 0.0 or self.drop_path_rate > 0.0)
+
+    def _post_attn(self, attn, o, ln, x):
+        """residual + drop_path(dropout(ln(out_proj(o))))   (unify_transformer_layer.py:270-273,513-516,546-549)"""
+        if self._stochastic():
+            y = _lin(attn.out_proj, o)
+            if ln is not None:
+                y = _ln(ln, y)
+            return ops.dropout_residual(y, x, self.dropout_p, self.drop_path_rate, True)
+        if ln is not None:
+            return _ln(ln, _lin(attn.out_proj, o), resid=x)      # residual fused into the LN epilogue
+        return _lin(attn.out_proj, o, resid=x)                   # residual fused into the GEMM epilogue
+
     def _ffn(self, x):
         r = x
         u = _lin(self.fc1, _ln(self.final_layer_norm, x))
@@ -137,6 +151,8 @@ class _FFNMixin:
             g = _ln(self.ffn_layernorm, u, gelu_in=True)   # GELU fused into the LN prologue
         else:
             g = ops.gelu(u)
+        if self._stochastic():
+            return ops.dropout_residual(_lin(self.fc2, g), r, self.dropout_p, self.drop_path_rate, True)
         return _lin(self.fc2, g, resid=r)                  # residual fused into the GEMM epilogue
 
 
@@ -155,15 +171,13 @@ class TransformerEncoderLayer(nn.Module, _FFNMixin):
         self.ffn_layernorm = nn.LayerNorm(args.encoder_ffn_embed_dim) if getattr(args, "scale_fc", False) else None
         self.final_layer_norm = nn.LayerNorm(d)
         self.drop_path_rate = drop_path_rate
+        self.dropout_p = float(args.dropout)
 
     def forward(self, x, pq, pk, tok_lut, img_lut, cfg):
         h = _ln(self.self_attn_layer_norm, x)
         k, v = self.self_attn.project_kv(h)
         o = self.self_attn(h, k, v, pq, pk, tok_lut, img_lut, cfg)
-        if self.attn_ln is not None:
-            x = _ln(self.attn_ln, _lin(self.self_attn.out_proj, o), resid=x)
-        else:
-            x = _lin(self.self_attn.out_proj, o, resid=x)
+        x = self._post_attn(self.self_attn, o, self.attn_ln, x)
         return self._ffn(x)
 
 
@@ -187,22 +201,17 @@ class TransformerDecoderLayer(nn.Module, _FFNMixin):
         self.fc2 = nn.Linear(args.decoder_ffn_embed_dim, d)
         self.final_layer_norm = nn.LayerNorm(d)
         self.drop_path_rate = drop_path_rate
+        self.dropout_p = float(args.dropout)
 
     def forward(self, x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg):
         h = _ln(self.self_attn_layer_norm, x)
         k, v = self_kv(self.self_attn, h)
         o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg)
-        if self.self_attn_ln is not None:
-            x = _ln(self.self_attn_ln, _lin(self.self_attn.out_proj, o), resid=x)
-        else:
-            x = _lin(self.self_attn.out_proj, o, resid=x)
+        x = self._post_attn(self.self_attn, o, self.self_attn_ln, x)
         h = _ln(self.encoder_attn_layer_norm, x)
         k, v = cross_kv(self.encoder_attn)
         o = self.encoder_attn(h, k, v, cpq, cpk, None, None, cross_cfg)
-        if self.cross_attn_ln is not None:
-            x = _ln(self.cross_attn_ln, _lin(self.encoder_attn.out_proj, o), resid=x)
-        else:
-            x = _lin(self.encoder_attn.out_proj, o, resid=x)
+        x = self._post_attn(self.encoder_attn, o, self.cross_attn_ln, x)
         return self._ffn(x)
 
 
@@ -231,9 +240,10 @@ class TransformerEncoder(nn.Module):
         self.dictionary = dictionary
         _unsupported(args, ["encoder_prompt", "adapter", "bitfit", "sync_bn", "interpolate_position",
                             "entangle_position_embedding", "scale_resids"])
-        if args.dropout or args.attention_dropout or args.encoder_drop_path_rate or args.resnet_drop_path_rate:
-            raise NotImplementedError("dropout / drop-path > 0 is not wired into the fused epilogues yet "
-                                      "(parity and benchmark configs run with p = 0; DESIGN.md)")
+        if args.attention_dropout or getattr(args, "activation_dropout", 0) or getattr(args, "relu_dropout", 0):
+            raise NotImplementedError("attention / activation dropout are 0 in every Musketeer script and are not "
+                                      "implemented in the attention / FFN kernels")
+        self.dropout_p = float(args.dropout)
         self.register_buffer("version", torch.Tensor([3]))
         d = embed_tokens.embedding_dim
         self.padding_idx = embed_tokens.padding_idx
@@ -245,7 +255,8 @@ class TransformerEncoder(nn.Module):
             raise NotImplementedError("OFA archs set no_scale_embedding (ofa.py:405)")
         self.layernorm_embedding = nn.LayerNorm(d) if getattr(args, "layernorm_embedding", False) else None
         self.type_embedding = Embedding(2, d, padding_idx=None) if getattr(args, "add_type_embedding", False) else None
-        self.embed_images = ResNetStem(args.resnet_type, frozen_bn=getattr(args, "freeze_resnet", False))
+        self.embed_images = ResNetStem(args.resnet_type, frozen_bn=getattr(args, "freeze_resnet", False),
+                                       drop_path_rate=args.resnet_drop_path_rate)
         self.image_proj = Linear(1024, d)
         self.patch_layernorm_embedding = nn.LayerNorm(d) if getattr(args, "patch_layernorm_embedding", False) else None
         self.embed_positions = Embedding(args.max_source_positions + 2, d)
@@ -314,6 +325,7 @@ class TransformerEncoder(nn.Module):
         x = ops.embedding(src_tokens, w, type_w[0] if type_w is not None else None, self.padding_idx)
         if self.layernorm_embedding is not None:
             x = _ln(self.layernorm_embedding, x)
+        x = ops.dropout_residual(x, None, self.dropout_p, 0.0, self.training)                # :733
         pos = ops.embedding(torch.arange(S, device=dev), self.embed_positions.weight)        # [S, d]   :885
         pos = _ln(self.pos_ln, pos).unsqueeze(0).expand(B, S, d)                             # :898
         if patch_images is not None:
@@ -323,6 +335,7 @@ class TransformerEncoder(nn.Module):
             xi = ops.linear(feat.to(w.dtype), self.image_proj.weight, bias)                  # :739-744
             if self.patch_layernorm_embedding is not None:
                 xi = _ln(self.patch_layernorm_embedding, xi)
+            xi = ops.dropout_residual(xi, None, self.dropout_p, 0.0, self.training)          # :747
             x = torch.cat([xi, x], dim=1)
             pad_mask = torch.cat([img_pad, pad_mask], dim=1)
             ipos = _ln(self.image_pos_ln, ops.embedding(pid, self.embed_image_positions.weight))   # :695,900
@@ -379,8 +392,7 @@ class TransformerDecoder(nn.Module):
         self.args = args
         self.dictionary = dictionary
         _unsupported(args, ["decoder_prompt", "adapter", "cross_self_attention", "no_cross_attention"])
-        if args.decoder_drop_path_rate:
-            raise NotImplementedError("drop-path > 0 is not wired into the fused epilogues yet")
+        self.dropout_p = float(args.dropout)
         self.register_buffer("version", torch.Tensor([3]))
         d = args.decoder_embed_dim
         self.embed_dim = d
@@ -467,6 +479,7 @@ class TransformerDecoder(nn.Module):
             x = ops.add(x, tpe.unsqueeze(0).expand(B, Tq, d).contiguous())
         if self.layernorm_embedding is not None:
             x = _ln(self.layernorm_embedding, x)
+        x = ops.dropout_residual(x, None, self.dropout_p, 0.0, self.training)                  # :1495
         if incremental:
             st = incremental_state.setdefault("_ofa_b200", {})
             if "cpk" not in st:       # first step: project the encoder side once (static_kv, :207-209,275-276)

@@ -281,6 +281,43 @@ def mask_rows(x, rowmask):
     return _MaskRows.apply(x, rowmask)
 
 
+class _DropoutResidual(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, resid, p, row_scale, seed):
+        _need_cuda(x)
+        x = x.contiguous()
+        r = resid.contiguous() if resid is not None else None
+        y = torch.empty_like(x)
+        Cc = x.shape[-1]
+        rps = x.shape[-2] if x.dim() >= 3 else 1
+        call("ofa_dropout_residual", _p(x), _p(r), _p(y), x.numel(), Cc, rps, float(p), _p(row_scale), _p(seed), _dt(x), _st())
+        ctx.save_for_backward(row_scale, seed)
+        ctx.p, ctx.rps, ctx.has_r = p, rps, resid is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        row_scale, seed = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        call("ofa_dropout_residual", _p(dy), _p(None), _p(dx), dy.numel(), dy.shape[-1], ctx.rps, float(ctx.p),
+             _p(row_scale), _p(seed), _dt(dy), _st())
+        return dx, (dy if ctx.has_r else None), None, None, None
+
+
+def dropout_residual(x, resid=None, p=0.0, drop_path=0.0, training=True):
+    """resid + drop_path(dropout(x)).  x: [B, L, C]; the drop-path Bernoulli is per sample (dim 0), as in the reference
+    (mask shape (1, B, 1) on T x B x C).  Identity (plain add) when not training or both rates are 0."""
+    if not training or (p == 0.0 and drop_path == 0.0):
+        return add(x, resid) if resid is not None else x
+    row_scale = None
+    if drop_path > 0.0:
+        keep = 1.0 - drop_path
+        row_scale = torch.floor(keep + torch.rand(x.shape[0], device=x.device, dtype=torch.float32)) / keep
+    seed = torch.randint(0, 2 ** 62, (1,), device=x.device, dtype=torch.int64)
+    return _DropoutResidual.apply(x, resid, p, row_scale, seed)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # attention
 # ---------------------------------------------------------------------------------------------------------------------

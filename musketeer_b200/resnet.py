@@ -28,8 +28,9 @@ class FrozenBatchNorm2d(nn.Module):
 class Bottleneck(nn.Module):
     expansion = 4
 
-    def __init__(self, inplanes, planes, stride, downsample, norm):
+    def __init__(self, inplanes, planes, stride, downsample, norm, drop_path_rate=0.0):
         super().__init__()
+        self.drop_path_rate = drop_path_rate
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
         self.bn1 = norm(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
@@ -45,17 +46,22 @@ class Bottleneck(nn.Module):
         out = self.bn3(self.conv3(out))
         if self.downsample is not None:
             idn = self.downsample(x)
+        if self.drop_path_rate > 0.0 and self.training:        # resnet.py:5-20,130 (per-sample Bernoulli keep)
+            keep = 1.0 - self.drop_path_rate
+            m = torch.floor(keep + torch.rand(x.shape[0], 1, 1, 1, dtype=out.dtype, device=out.device))
+            out = out.div(keep) * m
         return F.relu(idn + out)
 
 
 class ResNetStem(nn.Module):
-    def __init__(self, resnet_type, frozen_bn=False):
+    def __init__(self, resnet_type, frozen_bn=False, drop_path_rate=0.0):
         super().__init__()
         norm = FrozenBatchNorm2d if frozen_bn else nn.BatchNorm2d
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = norm(64)
         layers = BLOCKS[resnet_type]
+        self.drop_path_rate = drop_path_rate
         self.layer1 = self._make_layer(64, layers[0], 1, norm)
         self.layer2 = self._make_layer(128, layers[1], 2, norm)
         self.layer3 = self._make_layer(256, layers[2], 2, norm)
@@ -70,8 +76,9 @@ class ResNetStem(nn.Module):
             down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False), norm(planes * 4))
         seq = [Bottleneck(self.inplanes, planes, stride, down, norm)]
         self.inplanes = planes * 4
-        for _ in range(1, blocks):
-            seq.append(Bottleneck(self.inplanes, planes, 1, None, norm))
+        dpr = [x.item() for x in torch.linspace(0, self.drop_path_rate, blocks)]      # resnet.py:203-207
+        for i in range(1, blocks):
+            seq.append(Bottleneck(self.inplanes, planes, 1, None, norm, dpr[i]))
         return nn.Sequential(*seq)
 
     def forward(self, x):

@@ -243,3 +243,30 @@ def test_attention_fwd_bwd(dtype, use_tc, B, T, S, H, P, causal):
         scale = max(1.0, b.grad.abs().max().item())
         err = (a.grad.double() - b.grad).abs().max().item()
         assert err < tol * 4 * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_droppath_residual(dtype):
+    """Stochastic op: keep-rate, 1/(1-p) scaling, per-sample drop-path, mask identical in forward and backward,
+    reproducible under torch.manual_seed; identity when not training."""
+    ops = _ops()
+    B, L, C, p, dp = 64, 50, 256, 0.1, 0.25
+    x = torch.ones(B, L, C, device="cuda", dtype=dtype).requires_grad_()
+    r = torch.zeros(B, L, C, device="cuda", dtype=dtype).requires_grad_()
+    torch.manual_seed(5)
+    y = ops.dropout_residual(x, r, p, dp, True)
+    y.backward(torch.ones_like(y))
+    yf = y.float()
+    sample_kept = yf.flatten(1).abs().sum(1) > 0
+    assert 0.5 < sample_kept.float().mean().item() < 0.95                       # E = 1 - dp = 0.75
+    kept = yf[sample_kept]
+    frac = (kept != 0).float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    val = kept[kept != 0]
+    assert (val - 1 / ((1 - p) * (1 - dp))).abs().max().item() < 1e-2
+    assert torch.equal(x.grad.float() != 0, yf != 0)                           # same mask in backward
+    assert torch.equal(r.grad, torch.ones_like(r))
+    torch.manual_seed(5)
+    y2 = ops.dropout_residual(x, r, p, dp, True)
+    assert torch.equal(y2, y)
+    assert torch.equal(ops.dropout_residual(x, r, p, dp, False), x + r)

@@ -173,3 +173,36 @@ def test_incremental_decoder_matches_teacher_forcing():
         for t in range(ni["prev_output_tokens"].shape[1]):
             step, _ = model.decoder(ni["prev_output_tokens"][:, :t + 1], encoder_out=enc, incremental_state=inc)
             assert (step[:, -1].float() - full[:, t].float()).abs().max().item() < 1e-4, t
+
+
+def test_training_with_dropout_and_droppath_runs():
+    """dropout 0.1 / drop-path 0.1 (train_musketeer.sh:61-62,143-147): finite loss and gradients, eval() is deterministic
+    and equals the p = 0 forward."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    fx = load_golden("micro_pad")
+    case = dict(fx["case"])
+    case["cfg"] = dict(case["cfg"], dropout=0.1, encoder_drop_path_rate=0.1, decoder_drop_path_rate=0.1,
+                       resnet_drop_path_rate=0.1)
+    cfg, sd, samples = build_case(case)
+    model, task = build_product(cfg, sd, dtype=torch.bfloat16)
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=True, sample_patch_num=0)
+    inp = to_device(copy.deepcopy(samples[0]), "cuda", torch.bfloat16)
+    model.train()
+    torch.manual_seed(0)
+    loss, ss, _ = crit(model, inp)
+    (loss / ss).backward()
+    assert torch.isfinite(loss).item()
+    assert all(torch.isfinite(p.grad).all().item() for p in model.parameters() if p.grad is not None)
+    # R-Drop with dropout: the two halves differ, so the KL term is positive
+    model.eval()
+    ni = to_device(copy.deepcopy(samples[0]["net_input"]), "cuda", torch.bfloat16)
+    with torch.no_grad():
+        a, _ = model(**ni)
+        b, _ = model(**ni)
+    assert torch.equal(a, b)
+    cfg0, sd0, _ = build_case(fx["case"])
+    m0, _ = build_product(cfg0, sd0, dtype=torch.bfloat16)
+    m0.eval()
+    with torch.no_grad():
+        c, _ = m0(**ni)
+    assert torch.equal(a, c)
