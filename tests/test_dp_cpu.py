@@ -1,0 +1,92 @@
+"""Data-parallel gradient reduction (musketeer_b200.dp.GradReducer) on CPU with the gloo backend, world size 2:
+bucketed all-reduce == mean of the per-rank gradients, tied weights reduced once, parameters without gradient reduced
+as zeros, no_sync() defers the reduction (trainer.py:755-773 semantics)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.a = torch.nn.Linear(16, 32)
+        self.b = torch.nn.Linear(32, 16)
+        self.unused = torch.nn.Parameter(torch.ones(7))
+        self.tied = torch.nn.Linear(16, 16, bias=False)
+        self.tied.weight = self.a.weight if False else self.tied.weight
+
+    def forward(self, x):
+        return self.tied(self.b(torch.relu(self.a(x)))).sum()
+
+
+def _worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from musketeer_b200.dp import GradReducer
+    model = _Toy()
+    red = GradReducer(model, world, bucket_bytes=1024)
+    assert len(red.buckets) > 2
+    torch.manual_seed(100 + rank)
+    x = torch.randn(8, 16)
+    # reference: local grads
+    model.zero_grad(set_to_none=True)
+    model(x).backward()
+    local = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    # reduced
+    model.zero_grad(set_to_none=True)
+    red.prepare()
+    model(x).backward()
+    red.finish()
+    out = {n: (p.grad.clone() if p.grad is not None else None) for n, p in model.named_parameters()}
+    # no_sync keeps local grads
+    model.zero_grad(set_to_none=True)
+    with red.no_sync():
+        red.prepare()
+        model(x).backward()
+        red.finish()
+    nosync = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    # reduce_all (CUDA-graph path: hooks do not fire)
+    model.zero_grad(set_to_none=True)
+    model(x).backward()
+    red.reduce_all()
+    allred = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    torch.save((local, out, nosync, allred), os.path.join(outdir, "r%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_world2(tmp_path):
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    res = {r: torch.load(os.path.join(str(tmp_path), "r%d.pt" % r)) for r in range(2)}
+    for n in res[0][0]:
+        mean = (res[0][0][n] + res[1][0][n]) / 2
+        for r in range(2):
+            assert torch.allclose(res[r][1][n], mean, atol=1e-6), n       # hook-driven bucketed reduce
+            assert torch.allclose(res[r][3][n], mean, atol=1e-6), n       # reduce_all
+            assert torch.allclose(res[r][2][n], res[r][0][n]), n          # no_sync: untouched local grads
+    for r in range(2):
+        assert res[r][1]["unused"] is not None and float(res[r][1]["unused"].abs().sum()) == 0.0
+        # both ranks hold identical gradients afterwards (trainer._check_grad_norms invariant, trainer.py:1397-1433)
+    for n in res[0][1]:
+        if res[0][1][n] is not None:
+            assert torch.equal(res[0][1][n], res[1][1][n]), n
