@@ -38,12 +38,12 @@ int ofa_layernorm_fwd(const void* x, const void* gamma, const void* beta, const 
                       float* rstd, int rows, int C, float eps, int gelu_in, int dtype, void* stream);
 int ofa_layernorm_bwd_nparts(int rows); /* host helper: workspace = 2 * nparts * C floats */
 int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
-                      void* dgamma, void* dbeta, float* workspace, int rows, int C, int gelu_in, int dtype,
-                      void* stream);
+                      void* dgamma, void* dbeta, float* workspace, int rows, int C, int gelu_in, int accumulate,
+                      int dtype, void* stream); /* accumulate=1: dgamma/dbeta += (gradient accumulation across micro-batches) */
 
 /* ---- glue -------------------------------------------------------------------------------------------------------- */
-int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace /* 64*C floats */, int dtype,
-               void* stream); /* bias gradients */
+int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace /* 64*C floats */, float alpha,
+               int accumulate, int dtype, void* stream); /* bias gradients: out = (accumulate ? out : 0) + alpha * colsum(x) */
 int ofa_embed_gather(const long long* idx, const void* table, const void* addvec, void* out, long long ldo, int rows,
                      int C, int dtype, void* stream); /* unify_transformer.py:725-730,885,1450,1475 */
 int ofa_embed_scatter_add(const long long* idx, const void* dout, long long ldo, void* dtable, int rows, int C,

@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
 // sums the [nparts, C] fp32 partials: block = 32 columns x 8 partial-lanes, coalesced along columns
 template <typename T>
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b,
-                                                            int nparts, int C, T* __restrict__ dgamma, T* __restrict__ dbeta) {
+                                                            int nparts, int C, T* __restrict__ dgamma, T* __restrict__ dbeta,
+                                                            int accumulate) {
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const float* src = blockIdx.y ? part_b : part_g;
@@ -208,7 +209,9 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restr
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][cx];
-    (blockIdx.y ? dbeta : dgamma)[c] = (T)t;
+    T* dst = (blockIdx.y ? dbeta : dgamma) + c;
+    if (accumulate) t += (float)*dst;
+    *dst = (T)t;
   }
 }
 
@@ -250,11 +253,14 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   }
 }
 template <typename T>
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int C, T* __restrict__ out) {
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int C, T* __restrict__ out, float alpha,
+                                    int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
   for (int p = 0; p < nparts; ++p) s += part[(size_t)p * C + c];
+  s *= alpha;
+  if (accumulate) s += (float)out[c];
   out[c] = (T)s;
 }
 
@@ -409,7 +415,7 @@ extern "C" int ofa_layernorm_bwd_nparts(int rows) {
 
 extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                                  const float* rstd, void* dx, void* dgamma, void* dbeta, float* workspace, int rows,
-                                 int C, int gelu_in, int dtype, void* stream) {
+                                 int C, int gelu_in, int accumulate, int dtype, void* stream) {
   OFA_CHECK(rows > 0 && C > 0 && C % 8 == 0, "ofa_layernorm_bwd: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
   const int nparts = ofa_layernorm_bwd_nparts(rows);
@@ -420,11 +426,11 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   if (dtype == OFA_BF16) {
     rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<__nv_bfloat16, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
     if (rc) return rc;
-    ln_bwd_reduce_kernel<__nv_bfloat16><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta);
+    ln_bwd_reduce_kernel<__nv_bfloat16><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
   } else if (dtype == OFA_F32) {
     rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<float, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
     if (rc) return rc;
-    ln_bwd_reduce_kernel<float><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta);
+    ln_bwd_reduce_kernel<float><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate);
   } else {
     return ofa_set_error("ofa_layernorm_bwd: bad dtype %d", dtype);
   }
@@ -432,8 +438,8 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   return 0;
 }
 
-extern "C" int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace, int dtype,
-                          void* stream) {
+extern "C" int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace, float alpha,
+                          int accumulate, int dtype, void* stream) {
   OFA_CHECK(rows > 0 && C > 0, "ofa_colsum: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
   int ny = (rows + 31) / 32;
@@ -443,10 +449,10 @@ extern "C" int ofa_colsum(const void* x, long long ld, int rows, int C, void* ou
   const int vec_ok = (((uintptr_t)x & 15) == 0) && ((ld * esz) % 16 == 0);
   if (dtype == OFA_BF16) {
     colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, workspace, vec_ok);
-    colsum_final_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (__nv_bfloat16*)out);
+    colsum_final_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (__nv_bfloat16*)out, alpha, accumulate);
   } else if (dtype == OFA_F32) {
     colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, C, workspace, vec_ok && (ld * 4) % 32 == 0 && ((uintptr_t)x & 31) == 0);
-    colsum_final_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (float*)out);
+    colsum_final_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (float*)out, alpha, accumulate);
   } else {
     return ofa_set_error("ofa_colsum: bad dtype %d", dtype);
   }

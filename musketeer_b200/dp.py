@@ -48,7 +48,9 @@ class GradReducer:
             self.sync = old
 
     def prepare(self):
-        """Call before the backward whose gradients must be reduced."""
+        """Call before the backward whose gradients must be reduced.  (Hook-driven overlap needs every accumulation to
+        go through autograd: set musketeer_b200.ops.FUSE_GRAD_ACCUM = False for eager multi-task steps; the CUDA-graph
+        path uses reduce_all() after the replay and keeps the fusion.)"""
         self._pending = [len(b) for b in self.buckets]
         self._flat = [None] * len(self.buckets)
         self._works = []

@@ -15,6 +15,19 @@ from ._lib import OfaAttnArgs, OfaAttnBias, OfaAttnGrads, call
 
 F32, BF16 = 0, 1
 
+# Gradient-accumulation fusion: when a parameter already holds a .grad (earlier task / micro-batch of the same update),
+# weight / bias / LayerNorm gradients are accumulated INTO it by the producing kernel (GEMM epilogue with resid = grad,
+# colsum / LN-reduce with accumulate=1) and autograd receives None -- this removes the ~3000 tiny AccumulateGrad add
+# kernels of a five-task Musketeer micro-step.  Disabled when gradient hooks must observe every accumulation (eager DDP).
+FUSE_GRAD_ACCUM = True
+
+
+def _acc_target(param):
+    g = param.grad
+    if FUSE_GRAD_ACCUM and g is not None and g.is_contiguous() and g.dtype == param.dtype:
+        return g
+    return None
+
 
 def _dt(t):
     if t.dtype == torch.float32:
@@ -101,6 +114,7 @@ class _Linear(torch.autograd.Function):
         ldd = _ceil8(N) if out_pad else N
         y = gemm(x2, w, M, N, K, bias=b, alpha=alpha, resid=r2, ldd=ldd)
         ctx.save_for_backward(x2, w)
+        ctx.bias_param = b
         ctx.alpha, ctx.has_b, ctx.has_r, ctx.shp = alpha, b is not None, resid is not None, shp
         if ldd != N:
             y = y[:, :N]
@@ -120,9 +134,17 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
         if ctx.needs_input_grad[1]:
-            dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out_dtype=w.dtype)
+            tgt = _acc_target(w)
+            if tgt is not None:
+                gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt, out_dtype=w.dtype, resid=tgt)
+            else:
+                dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out_dtype=w.dtype)
         if ctx.has_b and ctx.needs_input_grad[2]:
-            db = colsum(dy2, alpha=ctx.alpha)
+            tgt = _acc_target(ctx.bias_param)
+            if tgt is not None:
+                colsum(dy2, alpha=ctx.alpha, out=tgt, accumulate=True)
+            else:
+                db = colsum(dy2, alpha=ctx.alpha)
         if ctx.has_r and ctx.needs_input_grad[4]:
             dr = dy
         return dx, dw, db, None, dr, None
@@ -133,13 +155,12 @@ def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False):
     return _Linear.apply(x, w, b, alpha, resid, out_pad)
 
 
-def colsum(x2, alpha=1.0):
+def colsum(x2, alpha=1.0, out=None, accumulate=False):
     rows, Cc = x2.shape
-    out = torch.empty(Cc, dtype=x2.dtype, device=x2.device)
+    if out is None:
+        out = torch.empty(Cc, dtype=x2.dtype, device=x2.device)
     ws = torch.empty(64 * Cc, dtype=torch.float32, device=x2.device)
-    call("ofa_colsum", _p(x2), x2.stride(0), rows, Cc, _p(out), _p(ws), _dt(x2), _st())
-    if alpha != 1.0:
-        out = out * alpha
+    call("ofa_colsum", _p(x2), x2.stride(0), rows, Cc, _p(out), _p(ws), float(alpha), int(accumulate), _dt(x2), _st())
     return out
 
 
@@ -161,6 +182,7 @@ class _LayerNorm(torch.autograd.Function):
         call("ofa_layernorm_fwd", _p(x2), _p(gamma), _p(beta), _p(r2), _p(y), _p(mean), _p(rstd), rows, Cc, eps,
              int(gelu_in), _dt(x2), _st(), work=("byte", (2 + (resid is not None)) * rows * Cc * x2.element_size()))
         ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.beta_param = beta
         ctx.gelu_in, ctx.shp, ctx.has_r = gelu_in, shp, resid is not None
         return y.reshape(shp)
 
@@ -170,13 +192,15 @@ class _LayerNorm(torch.autograd.Function):
         rows, Cc = x2.shape
         dy2 = dy.reshape(-1, Cc).contiguous()
         dx = torch.empty_like(x2)
-        dg = torch.empty_like(gamma)
-        db = torch.empty_like(gamma)
+        tg, tb = _acc_target(gamma), _acc_target(ctx.beta_param)
+        acc = tg is not None and tb is not None
+        dg = tg if acc else torch.empty_like(gamma)
+        db = tb if acc else torch.empty_like(gamma)
         nparts = _lib.load().ofa_layernorm_bwd_nparts(rows)
         ws = torch.empty(2 * nparts * Cc, dtype=torch.float32, device=x2.device)
         call("ofa_layernorm_bwd", _p(dy2), _p(x2), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), rows,
-             Cc, int(ctx.gelu_in), _dt(x2), _st(), work=("byte", 3 * rows * Cc * x2.element_size()))
-        return dx.reshape(ctx.shp), dg, db, (dy if ctx.has_r else None), None, None
+             Cc, int(ctx.gelu_in), int(acc), _dt(x2), _st(), work=("byte", 3 * rows * Cc * x2.element_size()))
+        return dx.reshape(ctx.shp), (None if acc else dg), (None if acc else db), (dy if ctx.has_r else None), None, None
 
 
 def layer_norm(x, gamma, beta, resid=None, gelu_in=False, eps=1e-5):
@@ -219,6 +243,7 @@ class _Embedding(torch.autograd.Function):
         out = torch.empty(*idx.shape, Cc, dtype=table.dtype, device=table.device)
         call("ofa_embed_gather", _p(idx), _p(table), _p(addvec), _p(out), Cc, rows, Cc, _dt(table), _st())
         ctx.save_for_backward(idx)
+        ctx.table_param = table
         ctx.tshape, ctx.pad, ctx.has_add = table.shape, padding_idx, addvec is not None
         return out
 
@@ -229,9 +254,12 @@ class _Embedding(torch.autograd.Function):
         Cc = ctx.tshape[1]
         dt = da = None
         if ctx.needs_input_grad[1]:
-            dt = torch.zeros(ctx.tshape, dtype=dout.dtype, device=dout.device)
+            tgt = _acc_target(ctx.table_param)
+            dt = tgt if tgt is not None else torch.zeros(ctx.tshape, dtype=dout.dtype, device=dout.device)
             call("ofa_embed_scatter_add", _p(idx), _p(dout), Cc, _p(dt), idx.numel(), Cc,
                  -1 if ctx.pad is None else ctx.pad, _dt(dout), _st())
+            if tgt is not None:
+                dt = None
         if ctx.has_add and ctx.needs_input_grad[2]:
             da = colsum(dout.reshape(-1, Cc))
         return None, dt, da, None
