@@ -132,7 +132,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from musketeer_b200 import _lib, AdjustLabelSmoothedCrossEntropyCriterion
+    from musketeer_b200 import _lib, ops, AdjustLabelSmoothedCrossEntropyCriterion
     from musketeer_b200.synthetic import build_model, make_tep_group, to_device, batch_bytes
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
@@ -160,8 +160,9 @@ def main():
     def eager_step(group):
         for p in model.parameters():
             p.grad = None
-        loss, ss, log = crit(model, [dict(g, net_input=dict(g["net_input"])) for g in group])
-        loss.backward()
+        with ops.grad_accumulation(model):
+            loss, ss, log = crit(model, [dict(g, net_input=dict(g["net_input"])) for g in group])
+            loss.backward()
         return loss
 
     def step(group, e2e=False, eager=False):

@@ -44,8 +44,10 @@ class GraphedTrainStep:
         static = map_tensors(static, lambda t: t.to(self.float_dtype) if t.is_floating_point() else t)
         samples = [dict(s, net_input=dict(s["net_input"])) for s in static] if isinstance(static, list) else \
             dict(static, net_input=dict(static["net_input"]))
-        loss, ss, log = self.criterion(self.model, samples)
-        loss.backward()
+        from . import ops
+        with ops.grad_accumulation(self.model):
+            loss, ss, log = self.criterion(self.model, samples)
+            loss.backward()
         return loss, ss
 
     def _capture(self, samples):

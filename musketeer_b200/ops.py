@@ -15,43 +15,65 @@ from ._lib import OfaAttnArgs, OfaAttnBias, OfaAttnGrads, call
 
 F32, BF16 = 0, 1
 
-# Gradient-accumulation fusion: when a parameter already holds a .grad (earlier task / micro-batch of the same update),
-# weight / bias / LayerNorm gradients are accumulated INTO it by the producing kernel (GEMM epilogue with resid = grad,
-# colsum / LN-reduce with accumulate=1) and autograd receives None -- this removes the ~3000 tiny AccumulateGrad add
-# kernels of a five-task Musketeer micro-step.  Disabled when gradient hooks must observe every accumulation (eager DDP).
-FUSE_GRAD_ACCUM = True
+# Gradient-accumulation fusion.  A Musketeer micro-step sums five task losses and runs ONE backward, so every parameter
+# receives five gradient contributions that autograd adds pairwise (~3000 tiny add kernels, 8 ms at per-task batch 8).
+# Inside `with grad_accumulation(model):` the kernels that produce parameter gradients (wgrad GEMM epilogue, colsum,
+# LayerNorm reduce, embedding scatter-add) write / accumulate straight into one persistent buffer per parameter and hand
+# autograd `None`; on exit the buffers become `param.grad`.  Outside the context everything goes through autograd as usual
+# (required when gradient hooks must observe each accumulation, e.g. the eager DDP overlap path).
+class _GradAccumulator:
+    def __init__(self, model):
+        self.params = {id(p): p for p in model.parameters() if p.requires_grad}
+        self.buf = {}
+        self.written = set()
+
+    def target(self, param):
+        """-> (buffer, accumulate) for a registered leaf parameter, else (None, False)."""
+        k = id(param)
+        if k not in self.params:
+            return None, False
+        b = self.buf.get(k)
+        if b is None or b.shape != param.shape or b.dtype != param.dtype or b.device != param.device:
+            b = self.buf[k] = torch.empty_like(param, memory_format=torch.contiguous_format)
+        first = k not in self.written
+        self.written.add(k)
+        return b, not first
+
+    def finish(self):
+        for k in self.written:
+            p, b = self.params[k], self.buf[k]
+            p.grad = b if p.grad is None else p.grad + b
+        self.written = set()
+
+
+_ACC = None
+
+
+class grad_accumulation:
+    def __init__(self, model):
+        acc = getattr(model, "_ofa_grad_acc", None)
+        if acc is None:
+            acc = model._ofa_grad_acc = _GradAccumulator(model)
+        self.acc = acc
+
+    def __enter__(self):
+        global _ACC
+        self.prev, _ACC = _ACC, self.acc
+        self.acc.written = set()
+        return self.acc
+
+    def __exit__(self, et, ev, tb):
+        global _ACC
+        _ACC = self.prev
+        if et is None:
+            self.acc.finish()
+        return False
 
 
 def _acc_target(param):
-    g = param.grad
-    if FUSE_GRAD_ACCUM and g is not None and g.is_contiguous() and g.dtype == param.dtype:
-        return g
-    return None
-
-
-def _dt(t):
-    if t.dtype == torch.float32:
-        return F32
-    if t.dtype == torch.bfloat16:
-        return BF16
-    raise TypeError("musketeer_b200 kernels support float32 and bfloat16, got %s" % t.dtype)
-
-
-def _st():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-def _p(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-
-
-def _need_cuda(t):
-    if not t.is_cuda:
-        raise _lib.OfaKernelError("musketeer_b200 ops need CUDA tensors (no CPU fallback exists)")
-
-
-def _ceil8(n):
-    return (n + 7) // 8 * 8
+    if _ACC is None or param is None:
+        return None, False
+    return _ACC.target(param)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -134,15 +156,16 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
         if ctx.needs_input_grad[1]:
-            tgt = _acc_target(w)
+            tgt, accum = _acc_target(w)
             if tgt is not None:
-                gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt, out_dtype=w.dtype, resid=tgt)
+                gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt, out_dtype=w.dtype,
+                     resid=tgt if accum else None)
             else:
                 dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out_dtype=w.dtype)
         if ctx.has_b and ctx.needs_input_grad[2]:
-            tgt = _acc_target(ctx.bias_param)
+            tgt, accum = _acc_target(ctx.bias_param)
             if tgt is not None:
-                colsum(dy2, alpha=ctx.alpha, out=tgt, accumulate=True)
+                colsum(dy2, alpha=ctx.alpha, out=tgt, accumulate=accum)
             else:
                 db = colsum(dy2, alpha=ctx.alpha)
         if ctx.has_r and ctx.needs_input_grad[4]:
@@ -192,15 +215,16 @@ class _LayerNorm(torch.autograd.Function):
         rows, Cc = x2.shape
         dy2 = dy.reshape(-1, Cc).contiguous()
         dx = torch.empty_like(x2)
-        tg, tb = _acc_target(gamma), _acc_target(ctx.beta_param)
-        acc = tg is not None and tb is not None
-        dg = tg if acc else torch.empty_like(gamma)
-        db = tb if acc else torch.empty_like(gamma)
+        (tg, ag), (tb, ab) = _acc_target(gamma), _acc_target(ctx.beta_param)
+        fused = tg is not None and tb is not None and ag == ab
+        acc = fused and ag
+        dg = tg if fused else torch.empty_like(gamma)
+        db = tb if fused else torch.empty_like(gamma)
         nparts = _lib.load().ofa_layernorm_bwd_nparts(rows)
         ws = torch.empty(2 * nparts * Cc, dtype=torch.float32, device=x2.device)
         call("ofa_layernorm_bwd", _p(dy2), _p(x2), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), rows,
              Cc, int(ctx.gelu_in), int(acc), _dt(x2), _st(), work=("byte", 3 * rows * Cc * x2.element_size()))
-        return dx.reshape(ctx.shp), (None if acc else dg), (None if acc else db), (dy if ctx.has_r else None), None, None
+        return dx.reshape(ctx.shp), (None if fused else dg), (None if fused else db), (dy if ctx.has_r else None), None, None
 
 
 def layer_norm(x, gamma, beta, resid=None, gelu_in=False, eps=1e-5):
@@ -254,7 +278,9 @@ class _Embedding(torch.autograd.Function):
         Cc = ctx.tshape[1]
         dt = da = None
         if ctx.needs_input_grad[1]:
-            tgt = _acc_target(ctx.table_param)
+            tgt, accum = _acc_target(ctx.table_param)
+            if tgt is not None and not accum:
+                tgt.zero_()
             dt = tgt if tgt is not None else torch.zeros(ctx.tshape, dtype=dout.dtype, device=dout.device)
             call("ofa_embed_scatter_add", _p(idx), _p(dout), Cc, _p(dt), idx.numel(), Cc,
                  -1 if ctx.pad is None else ctx.pad, _dt(dout), _st())

@@ -210,3 +210,31 @@ def test_training_with_dropout_and_droppath_runs():
     torch.manual_seed(0)
     loss2, _, _ = crit(model, inp)
     assert abs(float(loss2.detach()) - float(loss.detach())) < 0.05 * abs(float(loss.detach()))   # same seed, BN stats moved
+
+
+def test_fused_grad_accumulation_matches_autograd():
+    """ops.grad_accumulation (producer kernels accumulate into one buffer per parameter) == plain autograd accumulation
+    on a three-task micro-step, fp32, to rounding."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion, ops
+    fx = load_golden("micro_multitask_rdrop")
+    case = fx["case"]
+    cfg, sd, samples = build_case(case)
+    grads = []
+    for fused in (False, True):
+        model, task = build_product(cfg, sd, dtype=torch.float32)
+        model.train()
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0)
+        inp = to_device(copy.deepcopy(samples), "cuda")
+        if fused:
+            with ops.grad_accumulation(model):
+                loss, ss, _ = crit(model, inp)
+                loss.backward()
+        else:
+            loss, ss, _ = crit(model, inp)
+            loss.backward()
+        grads.append({n: (p.grad.clone() if p.grad is not None else None) for n, p in model.named_parameters()})
+    for n in grads[0]:
+        a, b = grads[0][n], grads[1][n]
+        assert (a is None) == (b is None), n
+        if a is not None:
+            assert (a - b).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item()), n

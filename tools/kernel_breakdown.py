@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 
-from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion, ops
 from musketeer_b200.synthetic import build_model, make_tep_group, to_device
 
 ap = argparse.ArgumentParser()
@@ -26,8 +26,9 @@ group = to_device(make_tep_group(a.task_batch), dev, torch.bfloat16)
 def step():
     for p in model.parameters():
         p.grad = None
-    loss, _, _ = crit(model, [dict(g, net_input=dict(g["net_input"])) for g in group])
-    loss.backward()
+    with ops.grad_accumulation(model):
+        loss, _, _ = crit(model, [dict(g, net_input=dict(g["net_input"])) for g in group])
+        loss.backward()
 
 
 for _ in range(2):
