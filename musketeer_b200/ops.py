@@ -76,6 +76,31 @@ def _acc_target(param):
     return _ACC.target(param)
 
 
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("musketeer_b200 kernels support float32 and bfloat16, got %s" % t.dtype)
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise _lib.OfaKernelError("musketeer_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _ceil8(n):
+    return (n + 7) // 8 * 8
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GEMM
 # ---------------------------------------------------------------------------------------------------------------------
