@@ -56,6 +56,17 @@ int ofa_gelu(const void* x, const void* dy, void* out, long long n, int backward
 int ofa_dropout_residual(const void* x, const void* resid, void* y, long long n, int C, int rows_per_sample, float p,
                          const float* row_scale, const unsigned long long* seed, int dtype, void* stream);
 
+/* ---- BatchNorm2d (+ReLU, +residual) on NHWC activations viewed as [R = N*H*W, C]; training-mode batch statistics with
+ * running-stat update (momentum, unbiased variance), or eval / frozen mode (models/ofa/resnet.py:113-133,211-220,
+ * frozen_bn.py:36-57).  stats = 4*C floats (mean | rstd | scale | shift); mean and rstd feed the backward.            */
+long long ofa_batchnorm_workspace_floats(int C);
+int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* running_mean,
+                      void* running_var, long long R, int C, float eps, float momentum, int training, int relu,
+                      float* stats, float* workspace, int dtype, void* stream);
+int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* mean,
+                      const float* rstd, void* dx, void* dres, void* dgamma, void* dbeta, int accumulate, long long R,
+                      int C, int batch_stats, int relu, float* workspace, int dtype, void* stream);
+
 /* ---- label-smoothed CE (+R-Drop KL): loss rows and d(logits) in one kernel, gradient written in place --------------
  * replaces criterions/label_smoothed_cross_entropy.py:81-126,228-260.                                                */
 int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* target, const unsigned char* cmask,

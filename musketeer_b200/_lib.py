@@ -49,6 +49,9 @@ SIGNATURES = {
     "ofa_mask_rows": [c_p, c_p, c_i, c_i, c_i, c_p],
     "ofa_gelu": [c_p, c_p, c_p, c_ll, c_i, c_i, c_p],
     "ofa_dropout_residual": [c_p, c_p, c_p, c_ll, c_i, c_i, c_f, c_p, c_p, c_i, c_p],
+    "ofa_batchnorm_workspace_floats": [c_i],
+    "ofa_batchnorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_i, c_p],
+    "ofa_batchnorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_p],
     "ofa_ls_ce_fwd_bwd": [c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_i,
                           c_p],
     "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p],
@@ -79,7 +82,7 @@ def load(path=None):
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = c_ll if name.endswith("_bytes") else c_i
+        fn.restype = c_ll if name.endswith(("_bytes", "_floats")) else c_i
     _lib = lib
     return lib
 

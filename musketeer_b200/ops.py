@@ -360,6 +360,59 @@ def mask_rows(x, rowmask):
     return _MaskRows.apply(x, rowmask)
 
 
+class _BatchNorm(torch.autograd.Function):
+    """x: conv output, logically [N,C,H,W] in channels_last memory format (== [N*H*W, C] row-major)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, training, momentum, eps):
+        _need_cuda(x)
+        N, Cc, Hh, Ww = x.shape
+        x = x.contiguous(memory_format=torch.channels_last)
+        res = residual.contiguous(memory_format=torch.channels_last) if residual is not None else None
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        R = N * Hh * Ww
+        stats = torch.empty(4 * Cc, dtype=torch.float32, device=x.device)
+        ws = torch.empty(_lib.load().ofa_batchnorm_workspace_floats(Cc), dtype=torch.float32, device=x.device)
+        call("ofa_batchnorm_fwd", _p(x), _p(res), _p(y), _p(gamma), _p(beta), _p(running_mean), _p(running_var), R, Cc,
+             float(eps), float(momentum), int(training), int(relu), _p(stats), _p(ws), _dt(x), _st(),
+             work=("byte", (2 + training + (res is not None)) * R * Cc * x.element_size()))
+        ctx.save_for_backward(x, y if relu else None, gamma, stats)
+        ctx.beta_param = beta
+        ctx.relu, ctx.training, ctx.has_res = relu, training, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, stats = ctx.saved_tensors
+        N, Cc, Hh, Ww = x.shape
+        R = N * Hh * Ww
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
+        want_pg = ctx.needs_input_grad[1]
+        dg = db = None
+        fused = False
+        if want_pg:
+            (tg, ag), (tb, ab) = _acc_target(gamma), _acc_target(ctx.beta_param)
+            fused = tg is not None and tb is not None and ag == ab
+            dg = tg if fused else torch.empty_like(gamma)
+            db = tb if fused else torch.empty_like(gamma)
+        ws = torch.empty(_lib.load().ofa_batchnorm_workspace_floats(Cc), dtype=torch.float32, device=x.device)
+        call("ofa_batchnorm_bwd", _p(x), _p(dy), _p(y), _p(gamma), _p(stats), _p(stats[Cc:]), _p(dx), _p(dres), _p(dg), _p(db),
+             int(fused and ag), R, Cc, int(ctx.training), int(ctx.relu), _p(ws), _dt(x), _st(),
+             work=("byte", (4 + 2 * ctx.relu + ctx.has_res) * R * Cc * x.element_size()))
+        if fused or not want_pg:
+            dg = db = None
+        return dx, dg, db, None, None, dres, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1,
+               eps=1e-5):
+    """relu?(BN(x) + residual) on a channels_last [N,C,H,W] tensor; training=True uses batch statistics and updates the
+    running buffers in place (nn.BatchNorm2d semantics), False uses the running statistics (eval / FrozenBatchNorm2d)."""
+    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, residual, relu, training, momentum, eps)
+
+
 class _DropoutResidual(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, resid, p, row_scale, seed):

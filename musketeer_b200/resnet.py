@@ -1,11 +1,14 @@
 """3-stage bottleneck ResNet patch embedder (models/ofa/resnet.py:86-225, frozen_bn.py:7-80), same parameter names.
 
-Round-1 status (DESIGN.md "ResNet stem"): the convolutions and batch-norms still run through cuDNN / ATen library
-kernels (channels-last, model dtype); the implicit-GEMM tcgen05 convolution of SURVEY.md 8(a) row a3 is the next
-kernel to land.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
+Round-1 status (DESIGN.md "ResNet stem"): BatchNorm (+ReLU, +residual add, running-stat update, frozen / eval mode) runs
+on this library's fused NHWC kernels (ops.batch_norm); the convolutions and the 3x3 max-pool still go through cuDNN /
+ATen library kernels (channels-last, model dtype) -- the implicit-GEMM tcgen05 convolution of SURVEY.md 8(a) row a3 is
+the next kernel to land.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import ops
 
 BLOCKS = {"resnet50": [3, 4, 6], "resnet101": [3, 4, 23], "resnet152": [3, 8, 36]}
 
@@ -19,10 +22,21 @@ class FrozenBatchNorm2d(nn.Module):
         self.register_buffer("running_mean", torch.zeros(num_features))
         self.register_buffer("running_var", torch.ones(num_features) - eps)
 
-    def forward(self, x):
-        scale = self.weight * (self.running_var + self.eps).rsqrt()
-        bias = self.bias - self.running_mean * scale
-        return x * scale.reshape(1, -1, 1, 1).to(x.dtype) + bias.reshape(1, -1, 1, 1).to(x.dtype)
+    momentum = 0.0
+
+
+def _bn(mod, x, relu=False, residual=None):
+    """nn.BatchNorm2d (batch statistics when the module is in training mode) or FrozenBatchNorm2d, as holders."""
+    frozen = isinstance(mod, FrozenBatchNorm2d)
+    training = mod.training and not frozen
+    if training and mod.num_batches_tracked is not None:
+        mod.num_batches_tracked += 1
+    return ops.batch_norm(x, mod.weight, mod.bias, mod.running_mean, mod.running_var, residual, relu, training,
+                          0.1 if not frozen else 0.0, mod.eps)
+
+
+def _conv(mod, x):
+    return F.conv2d(x, mod.weight, None, mod.stride, mod.padding)
 
 
 class Bottleneck(nn.Module):
@@ -41,16 +55,16 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         idn = x
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = F.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
+        out = _bn(self.bn1, _conv(self.conv1, x), relu=True)
+        out = _bn(self.bn2, _conv(self.conv2, out), relu=True)
         if self.downsample is not None:
-            idn = self.downsample(x)
+            idn = _bn(self.downsample[1], _conv(self.downsample[0], x))
         if self.drop_path_rate > 0.0 and self.training:        # resnet.py:5-20,130 (per-sample Bernoulli keep)
+            out = _bn(self.bn3, _conv(self.conv3, out))
             keep = 1.0 - self.drop_path_rate
             m = torch.floor(keep + torch.rand(x.shape[0], 1, 1, 1, dtype=out.dtype, device=out.device))
-            out = out.div(keep) * m
-        return F.relu(idn + out)
+            return F.relu(idn + out.div(keep) * m)
+        return _bn(self.bn3, _conv(self.conv3, out), relu=True, residual=idn)   # relu(identity + bn3(conv3)) in one pass
 
 
 class ResNetStem(nn.Module):
@@ -88,7 +102,7 @@ class ResNetStem(nn.Module):
             torch.backends.cudnn.allow_tf32 = False      # fp32 parity mode must not silently drop to TF32
         try:
             x = x.to(dt).contiguous(memory_format=torch.channels_last)
-            x = F.relu(self.bn1(self.conv1(x)))
+            x = _bn(self.bn1, _conv(self.conv1, x), relu=True)
             x = F.max_pool2d(x, 3, 2, 1)
             x = self.layer3(self.layer2(self.layer1(x)))
         finally:

@@ -270,3 +270,41 @@ def test_dropout_droppath_residual(dtype):
     y2 = ops.dropout_residual(x, r, p, dp, True)
     assert torch.equal(y2, y)
     assert torch.equal(ops.dropout_residual(x, r, p, dp, False), x + r)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,C,H,W,relu,res,training", [(2, 64, 24, 24, True, False, True), (3, 256, 12, 12, True, True, True),
+                                                       (2, 1024, 6, 6, False, False, True), (2, 128, 9, 7, True, True, False)])
+def test_batchnorm_relu_residual(dtype, N, C, H, W, relu, res, training):
+    """Fused BN(+ReLU,+residual) vs nn.functional.batch_norm + relu in fp32: outputs, dx, dres, dgamma, dbeta, running stats."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(C + H)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    x = (mk(N, C, H, W) * 1.5 + 0.3).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    r = mk(N, C, H, W).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_() if res else None
+    gm = (1 + 0.2 * mk(C)).cuda().to(dtype).requires_grad_()
+    bt = (0.2 * mk(C)).cuda().to(dtype).requires_grad_()
+    rm = (0.1 * mk(C)).cuda().to(dtype)
+    rv = (1 + 0.1 * mk(C).abs()).cuda().to(dtype)
+    rm2, rv2 = rm.clone().float(), rv.clone().float()
+    y = ops.batch_norm(x, gm, bt, rm, rv, residual=r, relu=relu, training=training)
+    dy = mk(N, C, H, W).cuda().to(dtype).contiguous(memory_format=torch.channels_last)
+    y.backward(dy)
+    xf, gf, bf = [t.detach().float().requires_grad_() for t in (x, gm, bt)]
+    rf = r.detach().float().requires_grad_() if res else None
+    yr = F.batch_norm(xf, rm2, rv2, gf, bf, training, 0.1, 1e-5)
+    if res:
+        yr = yr + rf
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(dy.float())
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert (y.float() - yr).abs().max().item() < tol
+    assert (x.grad.float() - xf.grad).abs().max().item() < tol * 2
+    if res:
+        assert (r.grad.float() - rf.grad).abs().max().item() < tol
+    for a, b in ((gm.grad, gf.grad), (bt.grad, bf.grad)):
+        assert (a.float() - b).abs().max().item() <= (2e-4 if dtype == torch.float32 else 2e-2) * max(1.0, b.abs().max().item())
+    if training:
+        assert (rm.float() - rm2).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-2)
+        assert (rv.float() - rv2).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-2)
