@@ -90,6 +90,20 @@ __global__ void __launch_bounds__(kT) bn_reduce_kernel(const T* __restrict__ x, 
   }
 }
 
+// sum the [nparts][2][C] partials for channel c: 8 lanes per channel (threadIdx.x / 32), combined through shared memory
+__device__ __forceinline__ void sum_partials(const float* __restrict__ part, int nparts, int C, int c, float& s0, float& s1) {
+  __shared__ float r0[8][33], r1[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  float a = 0.f, b = 0.f;
+  if (c < C)
+    for (int p = py; p < nparts; p += 8) { a += part[((size_t)p * 2) * C + c]; b += part[((size_t)p * 2 + 1) * C + c]; }
+  r0[py][cx] = a; r1[py][cx] = b;
+  __syncthreads();
+  s0 = 0.f; s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0 += r0[i][cx]; s1 += r1[i][cx]; }
+}
+
 // forward finalize: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running-stat update
 template <typename T>
 __global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, long long R,
@@ -97,10 +111,10 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int npart
                                        float momentum, T* __restrict__ running_mean, T* __restrict__ running_var,
                                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                        float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s0 = 0.f, s1 = 0.f;
-  for (int p = 0; p < nparts; ++p) { s0 += part[((size_t)p * 2) * C + c]; s1 += part[((size_t)p * 2 + 1) * C + c]; }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  float s0, s1;
+  sum_partials(part, nparts, C, c, s0, s1);
+  if (c >= C || threadIdx.x >= 32) return;
   const float n = (float)R;
   const float mean = s0 / n;
   const float var = fmaxf(s1 / n - mean * mean, 0.f);
@@ -163,10 +177,10 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
                                        const T* __restrict__ gamma, const float* __restrict__ rstd, int batch_stats,
                                        T* __restrict__ dgamma, T* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s1 = 0.f, s2 = 0.f;
-  for (int p = 0; p < nparts; ++p) { s1 += part[((size_t)p * 2) * C + c]; s2 += part[((size_t)p * 2 + 1) * C + c]; }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  float s1, s2;
+  sum_partials(part, nparts, C, c, s1, s2);
+  if (c >= C || threadIdx.x >= 32) return;
   if (dgamma) {
     dgamma[c] = (T)(s2 + (accumulate ? (float)dgamma[c] : 0.f));
     dbeta[c] = (T)(s1 + (accumulate ? (float)dbeta[c] : 0.f));
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
 int nparts_for(long long R, int C) {
   const int rpi = kT / (C / 8);
   long long n = (R + rpi - 1) / rpi;
-  return (int)(n < 592 ? n : 592);
+  return (int)(n < 296 ? n : 296);   // 2 CTAs per SM
 }
 
 template <typename T>
@@ -219,7 +233,7 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
   if (training) {
     const int np = nparts_for(R, C);
     bn_reduce_kernel<T, 0><<<np, kT, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, R, C, 0, part);
-    bn_fwd_finalize_kernel<T><<<(C + 127) / 128, 128, 0, st>>>(part, np, C, R, (const T*)gamma, (const T*)beta, eps, momentum,
+    bn_fwd_finalize_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, np, C, R, (const T*)gamma, (const T*)beta, eps, momentum,
                                                              (T*)rm, (T*)rv, mean, rstd, scale, shift);
   } else {
     bn_eval_coeff_kernel<T><<<(C + 127) / 128, 128, 0, st>>>(C, (const T*)gamma, (const T*)beta, (const T*)rm, (const T*)rv,
@@ -238,7 +252,7 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
   float* ca = ws; float* cb = ws + C; float* cc = ws + 2 * C; float* part = ws + 3 * C;
   const int np = nparts_for(R, C);
   bn_reduce_kernel<T, 1><<<np, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, R, C, relu, part);
-  bn_bwd_finalize_kernel<T><<<(C + 127) / 128, 128, 0, st>>>(part, np, C, R, (const T*)gamma, rstd, batch_stats, (T*)dgamma,
+  bn_bwd_finalize_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, np, C, R, (const T*)gamma, rstd, batch_stats, (T*)dgamma,
                                                            (T*)dbeta, accumulate, ca, cb, cc);
   const long long n8 = R * C / 8;
   bn_bwd_apply_kernel<T><<<(unsigned)((n8 + kT - 1) / kT), kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, ca,
