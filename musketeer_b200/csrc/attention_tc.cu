@@ -14,17 +14,21 @@
 namespace {
 
 constexpr int BQ = 128, BKV = 64, HD = 64;
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;   // 2 threads per query row: 32 key columns / 32 output columns each
 constexpr int kTmemCols = 128;  // S: [0,64)  O_partial: [64,128)
+constexpr int kTokLut = 1024 + 128;
 
 struct TcSmem {
   uint8_t q[2][BQ * 128];   // [0: q, 1: pos_q][128 rows][128 B]   K-major, SWIZZLE_128B
   uint8_t k[2][BKV * 128];  // [0: k, 1: pos_k][64 keys][128 B]    K-major
   uint8_t v[BKV * 128];     // [64 keys][64 x bf16]                MN-major B operand of P.V
   uint8_t p[BQ * 128];      // [128 rows][64 keys x bf16]          K-major A operand of P.V
+  float tok_s[kTokLut];     // token rel-pos LUT staged for this query tile: index (r - j_t) + S_t - 1
+  float rowmax[2][BQ];      // per-tile partial row maxima of the two column halves
+  float rowsum[BQ];         // final exchange of the partial row sums
   uint64_t bar_q, bar_k, bar_v, bar_s, bar_o;
   uint32_t tmem_addr;
-  int kinfo[BKV];  // per key of the current tile: bit31 masked | bit30 image key | [8,16) col | [0,8) row
+  int kinfo[BKV];  // per key of the current tile: bit31 masked | bit30 image key | [0,16) kr*(2*ibs-1)+kc
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -40,9 +44,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int t = threadIdx.x, warp = t >> 5;
+  const int r = t & 127, hf = t >> 7;   // query row / TMEM lane ; column half
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (a.S + BKV - 1) / BKV;
   const AttnBias& bz = a.bias;
+  int ntiles = (a.S + BKV - 1) / BKV;
+  if (a.causal) {   // key tiles entirely above the diagonal of this query tile are skipped
+    const int last = q0 + BQ - 1 + a.q_pos_off;
+    ntiles = min(ntiles, last / BKV + 1);
+  }
+  const int w83 = 2 * bz.ibs - 1;
 
   if (t == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmPQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmPK);
@@ -52,11 +62,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<kTmemCols>(&sm.tmem_addr);
+  // token LUT slice for this query tile
+  const int S_t = a.S - bz.k_text_off;
+  const int i_t0 = q0 + a.q_pos_off - bz.q_text_off;
+  if (bz.tok_lut) {
+    for (int e = t; e < kTokLut; e += kThreads) {
+      const int rel = i_t0 + e - (S_t - 1) + bz.tok_max - 1;
+      sm.tok_s[e] = (rel >= 0 && rel < 2 * bz.tok_max - 1) ? bz.tok_lut[(size_t)h * (2 * bz.tok_max - 1) + rel] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = sm.tmem_addr + ((uint32_t)(warp * 32) << 16);
-  const uint32_t tmem_o = tmem_s + BKV;
+  const uint32_t tmem_s = sm.tmem_addr + ((uint32_t)((warp & 3) * 32) << 16) + hf * 32;
+  const uint32_t tmem_o = sm.tmem_addr + ((uint32_t)((warp & 3) * 32) << 16) + BKV + hf * 32;
 
   if (t == 0) {
     mbar_expect_tx(&sm.bar_q, 2 * BQ * 128);
@@ -70,39 +89,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 
   // per-row state
-  const int i = q0 + t;
+  const int i = q0 + r;
   const int iabs = i + a.q_pos_off;
+  const bool row_ok = i < a.T;
   const bool q_text = bz.tok_lut && iabs >= bz.q_text_off;
-  const bool q_img = bz.img_lut && iabs < bz.n_img_q && i < a.T;
-  int qr = 0, qc = 0;
+  const bool q_img = bz.img_lut && iabs < bz.n_img_q && row_ok;
+  int rowbase = 0;
   if (q_img) {
     const int pid = bz.q_pid[(size_t)b * bz.n_img_q + iabs] - 1;
-    qr = pid / bz.ibs; qc = pid % bz.ibs;
+    rowbase = (pid / bz.ibs + bz.ibs - 1) * w83 + (pid % bz.ibs + bz.ibs - 1);
   }
-  const float* tok_lut = bz.tok_lut ? bz.tok_lut + (size_t)h * (2 * bz.tok_max - 1) + (iabs - bz.q_text_off) + bz.tok_max - 1 +
-                                          bz.k_text_off : nullptr;  // index with -j
   const float* img_lut = bz.img_lut ? bz.img_lut + (size_t)h * bz.n_img_rel : nullptr;
-  const int w83 = 2 * bz.ibs - 1;
   constexpr float kLog2e = 1.4426950408889634f;
   float m = -CUDART_INF_F, l = 0.f;
-  float o[HD];
+  float o[32];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+  for (int d = 0; d < 32; ++d) o[d] = 0.f;
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
   constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);
+  const int col0 = hf * 32;
 
   for (int jt = 0; jt < ntiles; ++jt) {
     const int k0 = jt * BKV;
     const uint32_t ph = jt & 1;
     // key-side metadata for this tile
+    int my_masked = 0;
     if (t < BKV) {
       const int j = k0 + t;
       int info = 0;
-      if (j >= a.S || (a.kpm && a.kpm[(size_t)b * a.S + j])) info |= (int)0x80000000u;
+      if (j >= a.S || (a.kpm && a.kpm[(size_t)b * a.S + j])) { info |= (int)0x80000000u; my_masked = 1; }
       if (bz.img_lut && j < bz.n_img_k) {
         const int pid = bz.k_pid[(size_t)b * bz.n_img_k + j] - 1;
-        info |= 0x40000000 | ((pid % bz.ibs) << 8) | (pid / bz.ibs);
+        info |= 0x40000000 | ((pid / bz.ibs) * w83 + (pid % bz.ibs));
       }
       sm.kinfo[t] = info;
     }
@@ -118,7 +137,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    umma_smem_desc(smem_u32(sm.k[kb]) + ks * 32, 16, 1024), idesc_s, (kb | ks) != 0);
       umma_commit(&sm.bar_s);
     }
-    __syncthreads();  // kinfo visible; also reconverges warp 0
+    const bool keys_any_masked = __syncthreads_or(my_masked) != 0;   // kinfo visible; also reconverges warp 0
+    const bool keys_all_img = bz.img_lut != nullptr && (k0 + BKV <= bz.n_img_k);
+    const bool keys_all_txt = bz.tok_lut != nullptr && (k0 >= bz.k_text_off) && (bz.img_lut == nullptr || k0 >= bz.n_img_k);
+    const bool plain = !keys_any_masked && !(a.causal && k0 + col0 + 31 > iabs);
+    int mode = 3;
+    if (plain) {
+      if (q_text && keys_all_txt) mode = 1;
+      else if (q_img && keys_all_img) mode = 2;
+      else if ((keys_all_txt && !q_text) || (keys_all_img && !q_img) || (!bz.tok_lut && !bz.img_lut)) mode = 0;
+    }
+    const int tb = r + S_t - 1 - (k0 - bz.k_text_off) - col0;   // tok_s index of column col0; column jj -> tb - jj
     mbar_wait(&sm.bar_s, ph);
     tc_fence_after();
     if (t == 0 && jt + 1 < ntiles) {  // K' buffer is free: prefetch the next key tile under the softmax
@@ -126,36 +155,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_4d(sm.k[0], &tmK, &sm.bar_k, 0, h, k0 + BKV, b);
       tma_load_4d(sm.k[1], &tmPK, &sm.bar_k, 0, h, k0 + BKV, b);
     }
-    float s[BKV];
-#pragma unroll
-    for (int c = 0; c < BKV / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_s + c * 32, r);
+    float s[32];
+    {
+      uint32_t rr[32];
+      tmem_ld32(tmem_s, rr);
       tmem_ld_wait();
+      if (mode == 0) {
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int jl = c * 32 + jj, j = k0 + jl;
-        const int info = sm.kinfo[jl];
-        float x = __uint_as_float(r[jj]);
-        if (q_text && j >= bz.k_text_off) x += __ldg(tok_lut - j);
-        if (q_img && (info & 0x40000000)) {
-          const int kr = info & 0xff, kc = (info >> 8) & 0xff;
-          x += __ldg(img_lut + (qr - kr + bz.ibs - 1) * w83 + (qc - kc + bz.ibs - 1));
+        for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(rr[jj]);
+      } else if (mode == 1) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(rr[jj]) + sm.tok_s[tb - jj];
+      } else if (mode == 2) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          s[jj] = __uint_as_float(rr[jj]) + __ldg(img_lut + rowbase - (sm.kinfo[col0 + jj] & 0xffff));
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int jl = col0 + jj, j = k0 + jl;
+          const int info = sm.kinfo[jl];
+          float x = __uint_as_float(rr[jj]);
+          if (q_text && j >= bz.k_text_off) x += sm.tok_s[tb - jj];
+          if (q_img && (info & 0x40000000)) x += __ldg(img_lut + rowbase - (info & 0xffff));
+          if (info < 0 || (a.causal && j > iabs)) x = -CUDART_INF_F;
+          s[jj] = x;
         }
-        if (info < 0 || (a.causal && j > iabs)) x = -CUDART_INF_F;
-        s[jl] = x;
       }
     }
-    float mx = m;
+    float mx = s[0];
 #pragma unroll
-    for (int jl = 0; jl < BKV; ++jl) mx = fmaxf(mx, s[jl]);
+    for (int jj = 1; jj < 32; ++jj) mx = fmaxf(mx, s[jj]);
+    sm.rowmax[hf][r] = mx;
+    __syncthreads();
+    mx = fmaxf(m, fmaxf(sm.rowmax[0][r], sm.rowmax[1][r]));
     const float mu = (mx == -CUDART_INF_F) ? 0.f : mx;
     const float alpha = ex2((m - mu) * kLog2e);
     m = mx;
     float rs = 0.f;
     const float mneg = -mu * kLog2e;
 #pragma unroll
-    for (int c16 = 0; c16 < BKV / 8; ++c16) {
+    for (int c16 = 0; c16 < 4; ++c16) {
       float pv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -164,7 +204,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       const uint4 pk = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
                                   pack_bf16(pv[6], pv[7]));
-      *reinterpret_cast<uint4*>(sm.p + t * 128 + ((c16 ^ (t & 7)) << 4)) = pk;
+      *reinterpret_cast<uint4*>(sm.p + r * 128 + (((hf * 4 + c16) ^ (r & 7)) << 4)) = pk;
     }
     l = l * alpha + rs;
     fence_proxy_async();
@@ -186,26 +226,33 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_expect_tx(&sm.bar_v, BKV * 128);
       tma_load_4d(sm.v, &tmV, &sm.bar_v, 0, h, k0 + BKV, b);
     }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_o + c * 32, r);
+    {
+      uint32_t rr[32];
+      tmem_ld32(tmem_o, rr);
       tmem_ld_wait();
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) o[c * 32 + jj] = fmaf(o[c * 32 + jj], alpha, __uint_as_float(r[jj]));
+      for (int jj = 0; jj < 32; ++jj) o[jj] = fmaf(o[jj], alpha, __uint_as_float(rr[jj]));
     }
     tc_fence_before();
   }
 
-  if (i < a.T) {
+  // combine the two partial row sums, normalise, write this thread's 32 output columns
+  if (hf == 1) sm.rowsum[r] = l;
+  __syncthreads();
+  if (hf == 0) l += sm.rowsum[r];
+  __syncthreads();
+  if (hf == 0) sm.rowsum[r] = l;
+  __syncthreads();
+  l = sm.rowsum[r];
+  if (row_ok) {
     const float inv = (l > 0.f ? 1.f / l : 0.f) * (a.head_scale ? a.head_scale[h] : 1.f);
-    __nv_bfloat16* O = (__nv_bfloat16*)a.o + (size_t)b * a.bso + (size_t)i * a.ldo + h * HD;
+    __nv_bfloat16* O = (__nv_bfloat16*)a.o + (size_t)b * a.bso + (size_t)i * a.ldo + h * HD + hf * 32;
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < 4; ++c)
       reinterpret_cast<uint4*>(O)[c] =
           make_uint4(pack_bf16(o[8 * c] * inv, o[8 * c + 1] * inv), pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
                      pack_bf16(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_bf16(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
-    a.lse[((size_t)b * a.H + h) * a.T + i] = (m == -CUDART_INF_F ? 0.f : m) + logf(l);
+    if (hf == 0) a.lse[((size_t)b * a.H + h) * a.T + i] = (m == -CUDART_INF_F ? 0.f : m) + logf(l);
   }
   tc_fence_before();
   __syncthreads();
@@ -225,7 +272,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //   read the same bytes through MN-major descriptors).  dQ' partials are reduced into an fp32 accumulator with
 //   red.global.add.v4.f32; relative-position table gradients are privatised in shared-memory histograms.
 constexpr int BK2 = 128;
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;   // 4 threads per query row, 32 key columns each
 constexpr int kTokHist = 1024 + 128;
 constexpr int kImgHistMax = 83 * 83 + 3;
 
@@ -236,9 +283,10 @@ struct BwdSmem {
   uint8_t dout[BQ * 128];    // [128 rows][64 x bf16]
   uint8_t p[2][BQ * 128];    // [64-key half][128 rows][128 B]
   uint8_t ds[2][BQ * 128];
-  float hist_tok[kTokHist];
+  float hist_tok[kTokHist];  // d tok_lut, indexed (i_t - jl) + 127
+  float tok_s[kTokHist];     // tok_lut staged with the same indexing (valid when all keys of the tile are text)
   float hist_img[kImgHistMax + 1];
-  int kinfo[BK2];
+  int kinfo[BK2];            // bit31 masked | bit30 image key | [0,16) kr*(2*ibs-1)+kc
   uint64_t bar_kv, bar_q, bar_sp, bar_dq;
   uint32_t tmem_addr;
 };
@@ -255,12 +303,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int t = threadIdx.x, warp = t >> 5;
-  const int r = t & 127, hf = t >> 7;   // TMEM lane / query row inside the tile ; 64-column half
+  const int r = t & 127, qd = t >> 7;   // TMEM lane / query row inside the tile ; 32-column quarter of the key tile
+  const int hf = qd >> 1, ch = qd & 1;  // 64-key half of the P / dS staging tiles, 32-column chunk inside it
   const int k0 = blockIdx.x * BK2, h = blockIdx.y, b = blockIdx.z;
   const AttnBias& bz = a.bias;
   const bool has_tok = bz.tok_lut != nullptr && g.dtok_lut != nullptr;
   const bool has_img = bz.img_lut != nullptr && g.dimg_lut != nullptr;
   const int nq_tiles = (a.T + BQ - 1) / BQ;
+  const int w83 = 2 * bz.ibs - 1;
   // causal: query rows i with i + q_pos_off < k0 see none of this tile's keys
   int qt0 = 0;
   if (a.causal) { const int first = k0 - a.q_pos_off; qt0 = first > 0 ? first / BQ : 0; }
@@ -272,20 +322,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&sm.tmem_addr);
-  for (int e = t; e < kTokHist; e += kBwdThreads) sm.hist_tok[e] = 0.f;
+  // tile classification: the keys are stationary per CTA
+  const bool keys_all_img = bz.img_lut != nullptr && (k0 + BK2 <= bz.n_img_k);
+  const bool keys_all_txt = bz.tok_lut != nullptr && (k0 >= bz.k_text_off) && (bz.img_lut == nullptr || k0 >= bz.n_img_k);
+  const int tok_base = k0 - bz.k_text_off + 127;   // (i_t - j_t) = u - tok_base with u = i_t - jl + 127
+  for (int e = t; e < kTokHist; e += kBwdThreads) {
+    sm.hist_tok[e] = 0.f;
+    float lv = 0.f;
+    if (bz.tok_lut) {
+      const int rel = e - tok_base + bz.tok_max - 1;
+      if (rel >= 0 && rel < 2 * bz.tok_max - 1) lv = bz.tok_lut[(size_t)h * (2 * bz.tok_max - 1) + rel];
+    }
+    sm.tok_s[e] = lv;
+  }
   for (int e = t; e < kImgHistMax + 1; e += kBwdThreads) sm.hist_img[e] = 0.f;
+  int my_masked = 0;
   if (t < BK2) {
     const int j = k0 + t;
     int info = 0;
-    if (j >= a.S || (a.kpm && a.kpm[(size_t)b * a.S + j])) info |= (int)0x80000000u;
+    if (j >= a.S || (a.kpm && a.kpm[(size_t)b * a.S + j])) { info |= (int)0x80000000u; my_masked = 1; }
     if (bz.img_lut && j < bz.n_img_k) {
       const int pid = bz.k_pid[(size_t)b * bz.n_img_k + j] - 1;
-      info |= 0x40000000 | ((pid % bz.ibs) << 8) | (pid / bz.ibs);
+      info |= 0x40000000 | ((pid / bz.ibs) * w83 + (pid % bz.ibs));
     }
     sm.kinfo[t] = info;
   }
   tc_fence_before();
-  __syncthreads();
+  const bool keys_any_masked = __syncthreads_or(my_masked) != 0;
   tc_fence_after();
   const uint32_t tm = sm.tmem_addr;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -303,12 +366,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   const float cs = a.head_scale ? a.head_scale[h] : 1.f;
   const float* img_lut = bz.img_lut ? bz.img_lut + (size_t)h * bz.n_img_rel : nullptr;
-  const int w83 = 2 * bz.ibs - 1;
   constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);    // S, dP
   constexpr uint32_t id_dv = umma_idesc_bf16(128, 64, 1, 1);    // dV  = P^T dO
   constexpr uint32_t id_dk = umma_idesc_bf16(128, 128, 1, 1);   // dK' = dS^T Q'
   constexpr uint32_t id_dq = umma_idesc_bf16(128, 128, 0, 1);   // dQ' = dS K'
-  const int tok_base = k0 - bz.k_text_off + 127;                // hist_tok[(i_t - j_t) + tok_base]
+  const int col0 = qd * 32;
 
   int it = 0;
   for (int qt = qt0; qt < nq_tiles; ++qt, ++it) {
@@ -340,49 +402,83 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float delta = g.delta[ridx];
     const bool q_text = bz.tok_lut && iabs >= bz.q_text_off;
     const bool q_img = bz.img_lut && iabs < bz.n_img_q && row_ok;
-    int qr = 0, qc = 0;
+    int rowbase = 0;
     if (q_img) {
       const int pid = bz.q_pid[(size_t)b * bz.n_img_q + iabs] - 1;
-      qr = pid / bz.ibs; qc = pid % bz.ibs;
+      rowbase = (pid / bz.ibs + bz.ibs - 1) * w83 + (pid % bz.ibs + bz.ibs - 1);
     }
     const int i_t = iabs - bz.q_text_off;
-    const float* tok_lut = bz.tok_lut ? bz.tok_lut + (size_t)h * (2 * bz.tok_max - 1) + i_t + bz.tok_max - 1 + bz.k_text_off : nullptr;
+    const int tu = i_t + 127 - col0;   // tok_s / hist_tok index of column col0 for this row; column jj -> tu - jj
+    // fast paths need: no masked key in the tile, a valid row, and no causal cut inside this thread's 32 columns
+    const bool plain = !keys_any_masked && row_ok && !(a.causal && k0 + col0 + 31 > iabs);
+    int mode = 3;                                       // 3 = generic per-element path
+    if (plain) {
+      if (q_text && keys_all_txt) mode = 1;             // text x text: token LUT from shared memory
+      else if (q_img && keys_all_img) mode = 2;         // image x image: image LUT gather
+      else if ((keys_all_txt && !q_text) || (keys_all_img && !q_img) || (!bz.tok_lut && !bz.img_lut)) mode = 0;
+    }
 
     mbar_wait(&sm.bar_sp, ph);
     tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = hf * 64 + c * 32;
+    {
       uint32_t rs[32], rp[32];
       tmem_ld32(tm + lane_off + COL_S + col0, rs);
       tmem_ld32(tm + lane_off + COL_DP + col0, rp);
       tmem_ld_wait();
       float pv[32], dsv[32];
+      if (mode == 0) {
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int jl = col0 + jj, j = k0 + jl;
-        const int info = sm.kinfo[jl];
-        float x = __uint_as_float(rs[jj]);
-        const bool tok_el = q_text && j >= bz.k_text_off;
-        int img_idx = -1;
-        if (tok_el) x += __ldg(tok_lut - j);
-        if (q_img && (info & 0x40000000)) {
-          img_idx = (qr - (info & 0xff) + bz.ibs - 1) * w83 + (qc - ((info >> 8) & 0xff) + bz.ibs - 1);
-          x += __ldg(img_lut + img_idx);
+        for (int jj = 0; jj < 32; ++jj) {
+          const float p = __expf(__uint_as_float(rs[jj]) - lse);
+          pv[jj] = p;
+          dsv[jj] = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
         }
-        const bool masked = info < 0 || (a.causal && j > iabs) || !row_ok;
-        const float p = masked ? 0.f : __expf(x - lse);
-        const float ds = p * (__uint_as_float(rp[jj]) * cs - delta);
-        pv[jj] = p;
-        dsv[jj] = ds;
-        if (ds != 0.f) {
-          if (has_tok && tok_el) atomicAdd(&sm.hist_tok[i_t - (j - bz.k_text_off) + tok_base], ds);
-          if (has_img && img_idx >= 0) atomicAdd(&sm.hist_img[img_idx], ds);
+      } else if (mode == 1) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float p = __expf(__uint_as_float(rs[jj]) + sm.tok_s[tu - jj] - lse);
+          const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
+          pv[jj] = p;
+          dsv[jj] = ds;
+          if (has_tok) atomicAdd(&sm.hist_tok[tu - jj], ds);
+        }
+      } else if (mode == 2) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int idx = rowbase - (sm.kinfo[col0 + jj] & 0xffff);
+          const float p = __expf(__uint_as_float(rs[jj]) + __ldg(img_lut + idx) - lse);
+          const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
+          pv[jj] = p;
+          dsv[jj] = ds;
+          if (has_img) atomicAdd(&sm.hist_img[idx], ds);
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int jl = col0 + jj, j = k0 + jl;
+          const int info = sm.kinfo[jl];
+          float x = __uint_as_float(rs[jj]);
+          const bool tok_el = q_text && j >= bz.k_text_off;
+          int img_idx = -1;
+          if (tok_el) x += sm.tok_s[tu - jj];
+          if (q_img && (info & 0x40000000)) {
+            img_idx = rowbase - (info & 0xffff);
+            x += __ldg(img_lut + img_idx);
+          }
+          const bool masked = info < 0 || (a.causal && j > iabs) || !row_ok;
+          const float p = masked ? 0.f : __expf(x - lse);
+          const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
+          pv[jj] = p;
+          dsv[jj] = ds;
+          if (ds != 0.f) {
+            if (has_tok && tok_el) atomicAdd(&sm.hist_tok[tu - jj], ds);
+            if (has_img && img_idx >= 0) atomicAdd(&sm.hist_img[img_idx], ds);
+          }
         }
       }
 #pragma unroll
       for (int c16 = 0; c16 < 4; ++c16) {
-        const int chunk = c * 4 + c16;   // 16-byte chunk inside the 128-byte row of this half
+        const int chunk = ch * 4 + c16;   // 16-byte chunk inside the 128-byte row of this half
         const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(sm.p[hf] + off) =
             make_uint4(pack_bf16(pv[c16 * 8], pv[c16 * 8 + 1]), pack_bf16(pv[c16 * 8 + 2], pv[c16 * 8 + 3]),
@@ -421,13 +517,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, q0 + BQ, b);
       tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, q0 + BQ, b);
     }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t rq[32];
-      tmem_ld32(tm + lane_off + COL_S + hf * 64 + c * 32, rq);
+      tmem_ld32(tm + lane_off + COL_S + col0, rq);
       tmem_ld_wait();
       if (row_ok) {
-        float* dst = dq_acc + (((size_t)b * a.T + i) * a.H + h) * 128 + hf * 64 + c * 32;
+        float* dst = dq_acc + (((size_t)b * a.T + i) * a.H + h) * 128 + col0;
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
           red_add_v4(dst + v4 * 4, __uint_as_float(rq[v4 * 4]), __uint_as_float(rq[v4 * 4 + 1]),
@@ -438,18 +533,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
   }
 
-  // epilogue: dK' (hf 0: k part, hf 1: pos_k part), dV (32 columns per half), histograms
+  // epilogue: dK' (quarters 0-1: k part, 2-3: pos_k part), dV (16 columns per quarter), histograms
   const int j = k0 + r;
   if (it > 0) {
     tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t rk[32];
-      tmem_ld32(tm + lane_off + COL_DK + hf * 64 + c * 32, rk);
+      tmem_ld32(tm + lane_off + COL_DK + col0, rk);
       tmem_ld_wait();
       if (j < a.S) {
-        __nv_bfloat16* dst = hf == 0 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD + c * 32
-                                     : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD + c * 32;
+        __nv_bfloat16* dst = qd < 2 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD + qd * 32
+                                    : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD + (qd - 2) * 32;
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4)
           reinterpret_cast<uint4*>(dst)[v4] = make_uint4(
@@ -460,13 +554,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     {
-      uint32_t rv[32];
-      tmem_ld32(tm + lane_off + COL_DV + hf * 32, rv);
+      uint32_t rv[16];
+      tmem_ld16(tm + lane_off + COL_DV + qd * 16, rv);
       tmem_ld_wait();
       if (j < a.S) {
-        __nv_bfloat16* dst = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + hf * 32;
+        __nv_bfloat16* dst = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + qd * 16;
 #pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4)
+        for (int v4 = 0; v4 < 2; ++v4)
           reinterpret_cast<uint4*>(dst)[v4] = make_uint4(
               pack_bf16(__uint_as_float(rv[8 * v4]) * cs, __uint_as_float(rv[8 * v4 + 1]) * cs),
               pack_bf16(__uint_as_float(rv[8 * v4 + 2]) * cs, __uint_as_float(rv[8 * v4 + 3]) * cs),
@@ -476,11 +570,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (j < a.S) {   // causal tile with no visible query rows: zero gradients
     const uint4 z = make_uint4(0, 0, 0, 0);
-    __nv_bfloat16* d0 = hf == 0 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD
-                                : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD;
-    for (int v4 = 0; v4 < 8; ++v4) reinterpret_cast<uint4*>(d0)[v4] = z;
-    __nv_bfloat16* d1 = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + hf * 32;
-    for (int v4 = 0; v4 < 4; ++v4) reinterpret_cast<uint4*>(d1)[v4] = z;
+    __nv_bfloat16* d0 = qd < 2 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD + qd * 32
+                               : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD + (qd - 2) * 32;
+    for (int v4 = 0; v4 < 4; ++v4) reinterpret_cast<uint4*>(d0)[v4] = z;
+    __nv_bfloat16* d1 = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + qd * 16;
+    for (int v4 = 0; v4 < 2; ++v4) reinterpret_cast<uint4*>(d1)[v4] = z;
   }
   __syncthreads();
   if (has_tok) {
