@@ -116,78 +116,67 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, co
 // LayerNorm backward.  Persistent CTAs loop over rows; dgamma/dbeta partials stay in registers and are written as
 // [gridDim.x, C] fp32 partials that ln_bwd_reduce_kernel sums.   dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) [* gelu'(x)]
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NV>
-__global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T>
+__global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                      const T* __restrict__ gamma, const float* __restrict__ mean_in,
                                                      const float* __restrict__ rstd_in, T* __restrict__ dx,
                                                      float* __restrict__ part_g, float* __restrict__ part_b, int rows,
                                                      int C, int gelu_in) {
-  // one CTA per row at a time; thread t owns columns (i*128 + t)*8 .. +7 for every row -> param-grad partials need no
-  // cross-thread reduction.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float red[2][2][4];
-  float ag[NV][8], ab[NV][8], gm[NV][8];
+  // blockDim.x = ceil(C/8) rounded up to a warp: thread t owns columns 8t..8t+7 of every row this CTA visits, so the
+  // dgamma / dbeta partials need no cross-thread reduction; erf is evaluated once per element (GELU value and derivative).
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  __shared__ float red[2][2][16];
+  const int c = threadIdx.x * 8;
+  const bool act = c < C;
+  float ag[8], ab[8], gm[8];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 128 + threadIdx.x) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; gm[i][j] = 0.f; }
-    if (c < C) Vec8<T>::load(gamma + c, gm[i]);
-  }
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; gm[j] = 0.f; }
+  if (act) Vec8<T>::load(gamma + c, gm);
   int it = 0;
   for (int row = blockIdx.x; row < rows; row += gridDim.x, it ^= 1) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float d[NV][8], raw[NV][8];
+    float d[8], xh[8], gp[8];
     float s1 = 0.f, s2 = 0.f;
+    if (act) {
+      float raw[8];
+      Vec8<T>::load(dy + (size_t)row * C + c, d);
+      Vec8<T>::load(x + (size_t)row * C + c, raw);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 128 + threadIdx.x) * 8;
-      if (c < C) {
-        Vec8<T>::load(dy + (size_t)row * C + c, d[i]);
-        Vec8<T>::load(x + (size_t)row * C + c, raw[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float fx = gelu_in ? gelu_erf(raw[i][j]) : raw[i][j];
-          const float xh = (fx - mean) * rstd;
-          const float g = d[i][j] * gm[i][j];
-          s1 += g;
-          s2 += g * xh;
-          ag[i][j] += d[i][j] * xh;
-          ab[i][j] += d[i][j];
+      for (int j = 0; j < 8; ++j) {
+        float fx = raw[j];
+        gp[j] = 1.f;
+        if (gelu_in) {
+          const float cdf = 0.5f * (1.0f + erff(raw[j] * 0.70710678118654752440f));
+          fx = raw[j] * cdf;
+          gp[j] = cdf + raw[j] * 0.39894228040143267794f * __expf(-0.5f * raw[j] * raw[j]);
         }
+        xh[j] = (fx - mean) * rstd;
+        const float g = d[j] * gm[j];
+        s1 += g;
+        s2 += g * xh[j];
+        ag[j] += d[j] * xh[j];
+        ab[j] += d[j];
       }
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) { red[it][0][warp] = s1; red[it][1][warp] = s2; }
     __syncthreads();
-    s1 = (red[it][0][0] + red[it][0][1] + red[it][0][2] + red[it][0][3]) / C;
-    s2 = (red[it][1][0] + red[it][1][1] + red[it][1][2] + red[it][1][3]) / C;
+    s1 = 0.f; s2 = 0.f;
+    for (int w = 0; w < nwarp; ++w) { s1 += red[it][0][w]; s2 += red[it][1][w]; }
+    s1 /= C; s2 /= C;
+    if (act) {
+      float o[8];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 128 + threadIdx.x) * 8;
-      if (c < C) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float fx = gelu_in ? gelu_erf(raw[i][j]) : raw[i][j];
-          const float xh = (fx - mean) * rstd;
-          o[j] = rstd * (d[i][j] * gm[i][j] - s1 - xh * s2);
-          if (gelu_in) o[j] *= gelu_grad(raw[i][j]);
-        }
-        Vec8<T>::store(dx + (size_t)row * C + c, o);
-      }
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * gm[j] - s1 - xh[j] * s2) * gp[j];
+      Vec8<T>::store(dx + (size_t)row * C + c, o);
     }
   }
+  if (act) {
+    float* pg = part_g + (size_t)blockIdx.x * C + c;
+    float* pb = part_b + (size_t)blockIdx.x * C + c;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 128 + threadIdx.x) * 8;
-    if (c < C) {
-      float* pg = part_g + (size_t)blockIdx.x * C + c;
-      float* pb = part_b + (size_t)blockIdx.x * C + c;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { pg[j] = ag[i][j]; pb[j] = ab[i][j]; }
-    }
+    for (int j = 0; j < 8; ++j) { pg[j] = ag[j]; pb[j] = ab[j]; }
   }
 }
 
@@ -362,11 +351,12 @@ int ln_fwd_launch(const void* x, const void* g, const void* b, const void* r, vo
   OFA_LAUNCH_CHECK("ln_fwd_kernel");
   return 0;
 }
-template <typename T, int NV>
+template <typename T>
 int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mean, const float* rstd, void* dx,
                   float* pg, float* pb, int nparts, int rows, int C, int gelu_in, cudaStream_t st) {
-  ln_bwd_kernel<T, NV><<<nparts, 128, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows,
-                                               C, gelu_in);
+  const int threads = ((C / 8 + 31) / 32) * 32;
+  ln_bwd_kernel<T><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C,
+                                               gelu_in);
   OFA_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
 }
@@ -410,7 +400,7 @@ extern "C" int ofa_layernorm_fwd(const void* x, const void* gamma, const void* b
 }
 
 extern "C" int ofa_layernorm_bwd_nparts(int rows) {
-  return rows < 592 ? rows : 592;  // 4 CTAs per SM on 148 SMs
+  return rows < 1184 ? rows : 1184;  // 8 CTAs per SM on 148 SMs
 }
 
 extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
@@ -421,14 +411,14 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   const int nparts = ofa_layernorm_bwd_nparts(rows);
   float* pg = workspace;
   float* pb = workspace + (size_t)nparts * C;  // workspace: 2 * nparts * C floats
-  const int nv = (C + 1023) / 1024;
+  OFA_CHECK(C <= 4096, "ofa_layernorm_bwd: C=%d too wide (max 4096)", C);
   int rc = 1;
   if (dtype == OFA_BF16) {
-    rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<__nv_bfloat16, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
+    rc = ln_bwd_launch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st);
     if (rc) return rc;
     ln_bwd_reduce_kernel<__nv_bfloat16><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
   } else if (dtype == OFA_F32) {
-    rc = [&]() -> int { DISPATCH_NV_BWD(nv, (ln_bwd_launch<float, NV>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st))) }();
+    rc = ln_bwd_launch<float>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st);
     if (rc) return rc;
     ln_bwd_reduce_kernel<float><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate);
   } else {
