@@ -87,6 +87,7 @@ def load(path=None):
     return lib
 
 
+_SYNC_DEBUG = bool(int(os.environ.get("OFA_SYNC_DEBUG", "0")))
 LAUNCHES = 0          # number of C-ABI kernel entry calls (each launches >= 1 kernel of this library)
 PROFILE = None        # when a dict: name -> list of (start_event, end_event, work) recorded on the launching stream
 
@@ -106,3 +107,9 @@ def call(name, *args, work=None):
         rc = getattr(lib, name)(*args)
     if rc != 0:
         raise OfaKernelError("%s: %s" % (name, lib.ofa_last_error().decode()))
+    if _SYNC_DEBUG:      # debugging aid: surface asynchronous faults at the call that caused them
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise OfaKernelError("%s faulted asynchronously: %s" % (name, str(e).splitlines()[0]))

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
       for (int v = threadIdx.x; v < V; v += kThreads) xr[k][v] = (T)0.f;
       if (threadIdx.x == 0) { loss_out[r0 + k * half] = 0.f; nll_out[r0 + k * half] = 0.f; }
     }
-    if (threadIdx.x == 0 && kl_out) kl_out[r0] = 0.f;
+    if (rdrop && threadIdx.x == 0 && kl_out) kl_out[r0] = 0.f;   // kl_out has R/2 entries only under R-Drop
     return;
   }
   for (int k = 0; k < nrow; ++k) row_stats(xr[k], V, rc[k], sh, lse[k], sumx[k], cnt[k]);
