@@ -29,7 +29,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--task-batch", type=int, default=8)
+    ap.add_argument("--task-batch", type=int, default=16)
     ap.add_argument("--arch", default="ofa_base")
     ap.add_argument("--img", type=int, default=384)
     ap.add_argument("--impl", default="ours")
