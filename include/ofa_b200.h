@@ -63,8 +63,9 @@ long long ofa_batchnorm_workspace_floats(int C);
 int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* running_mean,
                       void* running_var, long long R, int C, float eps, float momentum, int training, int relu,
                       float* stats, float* workspace, int dtype, void* stream);
-int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* mean,
-                      const float* rstd, void* dx, void* dres, void* dgamma, void* dbeta, int accumulate, long long R,
+/* y may be NULL when relu && no residual: the mask is then recomputed from x with the forward's scale / shift */
+int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* stats, void* dx,
+                      void* dres, void* dgamma, void* dbeta, int accumulate, long long R,
                       int C, int batch_stats, int relu, float* workspace, int dtype, void* stream);
 
 /* ---- label-smoothed CE (+R-Drop KL): loss rows and d(logits) in one kernel, gradient written in place --------------

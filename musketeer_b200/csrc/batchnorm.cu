@@ -43,18 +43,23 @@ constexpr int kT = 256;
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kT) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                        const T* __restrict__ y, const float* __restrict__ mean,
-                                                       const float* __restrict__ rstd, long long R, int C, int relu,
+                                                       const float* __restrict__ rstd, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, long long R, int C, int relu,
                                                        float* __restrict__ part) {
   const int tpr = C / 8;                 // threads per row
   const int rpi = kT / tpr;              // rows per block iteration
   const int cx = threadIdx.x % tpr, ry = threadIdx.x / tpr;
   const int c0 = cx * 8;
-  float a[8], b[8], mu[8], rs[8];
+  float a[8], b[8], mu[8], rs[8], sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; mu[j] = 0.f; rs[j] = 1.f; }
+  for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; mu[j] = 0.f; rs[j] = 1.f; sc[j] = 0.f; sh[j] = 0.f; }
   if (MODE == 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; }
+    if (relu && !y) {   // no residual: the ReLU mask is recomputed from x, saving the read of y
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+    }
   }
   if (ry < rpi) {
     for (long long r = (long long)blockIdx.x * rpi + ry; r < R; r += (long long)gridDim.x * rpi) {
@@ -67,10 +72,15 @@ __global__ void __launch_bounds__(kT) bn_reduce_kernel(const T* __restrict__ x, 
         float g[8];
         V8<T>::load(dy + r * C + c0, g);
         if (relu) {
-          float yv[8];
-          V8<T>::load(y + r * C + c0, yv);
+          if (y) {
+            float yv[8];
+            V8<T>::load(y + r * C + c0, yv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+            for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a[j] += g[j]; b[j] += g[j] * (xv[j] - mu[j]) * rs[j]; }
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
                                                           const T* __restrict__ y, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const float* __restrict__ ca,
                                                           const float* __restrict__ cb, const float* __restrict__ cc,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                           T* __restrict__ dx, T* __restrict__ dres, long long n8, int C,
                                                           int relu) {
   const long long v = (long long)blockIdx.x * kT + threadIdx.x;
@@ -204,10 +215,15 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ 
   V8<T>::load(x + v * 8, xv);
   V8<T>::load(dy + v * 8, g);
   if (relu) {
-    float yv[8];
-    V8<T>::load(y + v * 8, yv);
+    if (y) {
+      float yv[8];
+      V8<T>::load(y + v * 8, yv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], scale[c0 + j], shift[c0 + j]) > 0.f ? g[j] : 0.f;
+    }
   }
   if (dres) V8<T>::store(dres + v * 8, g);
   float o[8];
@@ -232,7 +248,7 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
   float* mean = stats; float* rstd = stats + C; float* scale = stats + 2 * C; float* shift = stats + 3 * C; float* part = ws;
   if (training) {
     const int np = nparts_for(R, C);
-    bn_reduce_kernel<T, 0><<<np, kT, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, R, C, 0, part);
+    bn_reduce_kernel<T, 0><<<np, kT, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R, C, 0, part);
     bn_fwd_finalize_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, np, C, R, (const T*)gamma, (const T*)beta, eps, momentum,
                                                              (T*)rm, (T*)rv, mean, rstd, scale, shift);
   } else {
@@ -247,16 +263,16 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
 
 template <typename T>
 int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, const float* mean, const float* rstd,
-             void* dx, void* dres, void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats,
+             const float* scale, const float* shift, void* dx, void* dres, void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats,
              int relu, float* ws, cudaStream_t st) {
   float* ca = ws; float* cb = ws + C; float* cc = ws + 2 * C; float* part = ws + 3 * C;
   const int np = nparts_for(R, C);
-  bn_reduce_kernel<T, 1><<<np, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, R, C, relu, part);
+  bn_reduce_kernel<T, 1><<<np, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, scale, shift, R, C, relu, part);
   bn_bwd_finalize_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, np, C, R, (const T*)gamma, rstd, batch_stats, (T*)dgamma,
                                                            (T*)dbeta, accumulate, ca, cb, cc);
   const long long n8 = R * C / 8;
   bn_bwd_apply_kernel<T><<<(unsigned)((n8 + kT - 1) / kT), kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, ca,
-                                                                      cb, cc, (T*)dx, (T*)dres, n8, C, relu);
+                                                                      cb, cc, scale, shift, (T*)dx, (T*)dres, n8, C, relu);
   OFA_LAUNCH_CHECK("batchnorm backward");
   return 0;
 }
@@ -278,13 +294,15 @@ extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const 
   return ofa_set_error("ofa_batchnorm_fwd: bad dtype %d", dtype);
 }
 
-extern "C" int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* mean,
-                                 const float* rstd, void* dx, void* dres, void* dgamma, void* dbeta, int accumulate,
+extern "C" int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* stats,
+                                 void* dx, void* dres, void* dgamma, void* dbeta, int accumulate,
                                  long long R, int C, int batch_stats, int relu, float* workspace, int dtype,
                                  void* stream) {
   OFA_CHECK(R > 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0, "ofa_batchnorm_bwd: C=%d must be a power of two in [8, 2048]", C);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == OFA_BF16) return bwd_impl<__nv_bfloat16>(x, dy, y, gamma, mean, rstd, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
-  if (dtype == OFA_F32) return bwd_impl<float>(x, dy, y, gamma, mean, rstd, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
+  OFA_CHECK(!relu || y || stats, "ofa_batchnorm_bwd: relu needs y or the forward stats");
+  const float *mean = stats, *rstd = stats + C, *scale = stats + 2 * C, *shift = stats + 3 * C;
+  if (dtype == OFA_BF16) return bwd_impl<__nv_bfloat16>(x, dy, y, gamma, mean, rstd, scale, shift, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
+  if (dtype == OFA_F32) return bwd_impl<float>(x, dy, y, gamma, mean, rstd, scale, shift, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
   return ofa_set_error("ofa_batchnorm_bwd: bad dtype %d", dtype);
 }

@@ -30,6 +30,8 @@ struct GemmParams {
   long long batch_stride_d, batch_stride_r;
   int M, N, K;
   int tiles_m, tiles_n, batch, splits, kb_per_split;
+  int n_big;     // work items [0, n_big) are full 128 x BN tiles; the rest are 128 x 64 sub-tiles of the last tiles
+  int total;     // total work items
   float alpha;
   int act;  // 0 none, 1 gelu(erf)
 };
@@ -59,16 +61,30 @@ template <>
 __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 struct Work {
-  int mt, nt, bz, sp;
+  int m0, n0, bn, bz, sp;
 };
+// Tail splitting: with T tiles on P persistent CTAs the last T mod P tiles would occupy a whole extra round; they are
+// issued as 128 x 64 sub-tiles instead so the tail spreads over all SMs.
+template <int BN>
 __device__ __forceinline__ Work decode(int w, const GemmParams& p) {
   Work r;
-  r.nt = w % p.tiles_n;  // n fastest: CTAs running concurrently share the A row-block through L2
+  int sub = 0;
+  r.bn = BN;
+  if (w >= p.n_big) {
+    const int q = BN / 64;
+    const int u = w - p.n_big;
+    sub = u % q;
+    w = p.n_big + u / q;
+    r.bn = 64;
+  }
+  const int nt = w % p.tiles_n;  // n fastest: CTAs running concurrently share the A row-block through L2
   w /= p.tiles_n;
-  r.mt = w % p.tiles_m;
+  const int mt = w % p.tiles_m;
   w /= p.tiles_m;
   r.sp = w % p.splits;
   r.bz = w / p.splits;
+  r.m0 = mt * BM;
+  r.n0 = nt * BN + sub * 64;
   return r;
 }
 
@@ -110,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   SmemLayout<BN>& sm =
       *reinterpret_cast<SmemLayout<BN>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = p.tiles_m * p.tiles_n * p.batch * p.splits;
+  const int total = p.total;
   const int nkb_all = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -136,12 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       int s = 0, ph = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const Work wk = decode(w, p);
-        const int m0 = wk.mt * BM, n0 = wk.nt * BN;
+        const Work wk = decode<BN>(w, p);
+        const int m0 = wk.m0, n0 = wk.n0;
         const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
+        const int nchunk = wk.bn / 64;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&sm.empty[s], ph ^ 1);
-          mbar_expect_tx(&sm.full[s], C::kStageBytes);
+          mbar_expect_tx(&sm.full[s], (BM + wk.bn) * BK * 2);
           uint8_t* sa = sm.tiles[s];
           uint8_t* sb = sa + BM * BK * 2;
           if (A_MN) {
@@ -151,11 +168,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tma_load_3d(sa, &tmA, &sm.full[s], kb * BK, m0, wk.bz);
           }
           if (B_MN) {
-#pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * BK * 128, &tmB, &sm.full[s], n0 + 64 * c, kb * BK, wk.bz);
-          } else {
-#pragma unroll
-            for (int c = 0; c < BN / 128; ++c) tma_load_3d(sb + c * 128 * 128, &tmB, &sm.full[s], kb * BK, n0 + 128 * c, wk.bz);
+            for (int c = 0; c < nchunk; ++c) tma_load_3d(sb + c * BK * 128, &tmB, &sm.full[s], n0 + 64 * c, kb * BK, wk.bz);
+          } else {   // 64-row boxes stacked at the 1024 B / 8-row pitch
+            for (int c = 0; c < nchunk; ++c) tma_load_3d(sb + c * 64 * 128, &tmB, &sm.full[s], kb * BK, n0 + 64 * c, wk.bz);
           }
           if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
@@ -164,10 +179,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int s = 0, ph = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const Work wk = decode(w, p);
+        const Work wk = decode<BN>(w, p);
+        const uint32_t idesc = umma_idesc_bf16(BM, wk.bn, A_MN, B_MN);
         const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
         const int acc = it & 1;
         mbar_wait(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: 16 bf16 = 32 B inside the 128B swizzle span; MN-major: 16 k-rows = 2 swizzle atoms = 2048 B.
-            // K-major B with BN = 256 is two 128-row boxes back to back: rows continue at the same 1024 B / 8-row pitch.
+            // K-major B is a stack of 64-row boxes: rows continue at the same 1024 B / 8-row pitch.
             const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
             umma_f16(tmem_d, da, db, idesc, (kb != kb0) | (k != 0));
@@ -198,8 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int q = warp & 3;
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const Work wk = decode(w, p);
-      const int m0 = wk.mt * BM, n0 = wk.nt * BN;
+      const Work wk = decode<BN>(w, p);
+      const int m0 = wk.m0, n0 = wk.n0;
+      const int nch = wk.bn / 32;
       const int acc = it & 1;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
@@ -208,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (p.splits > 1) {
         float* W = p.ws + ((size_t)(wk.sp * p.batch + wk.bz) * p.M) * p.N;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < nch; ++c) {
           uint32_t r[32];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const OutT* R = p.resid ? reinterpret_cast<const OutT*>(p.resid) + (long long)wk.bz * p.batch_stride_r : nullptr;
         const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < nch; ++c) {
           uint32_t r[32];
           tmem_ld32(tmem_d + c * 32, r);
           tmem_ld_wait();
@@ -296,7 +312,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
     OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int total = p.tiles_m * p.tiles_n * p.batch * p.splits;
+  const int total = p.total;
   kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, p);
   OFA_LAUNCH_CHECK("gemm_tc_kernel");
   if (p.splits > 1) {
@@ -363,7 +379,7 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     strides[1] = (uint64_t)(batch > 1 ? stride_a : (long long)dims[1] * lda) * 2;
     if (int e = ofa_make_tmap(&ta, A, 3, dims, strides, box, 1, 2)) return e;
     if (b_mn_major) { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
-    else            { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = 128; }
+    else            { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = 64; }
     strides[0] = (uint64_t)ldb * 2;
     strides[1] = (uint64_t)(batch > 1 ? stride_b : (long long)dims[1] * ldb) * 2;
     if (int e = ofa_make_tmap(&tb, B, 3, dims, strides, box, 1, 2)) return e;
@@ -376,6 +392,17 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   const int nkb = (K + BK - 1) / BK;
   p.kb_per_split = (nkb + splits - 1) / splits;
   p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty trailing slices
+  {
+    const int tiles = p.tiles_m * p.tiles_n * batch * p.splits;
+    p.n_big = tiles;
+    p.total = tiles;
+    // tail splitting (plain problems only): the last (tiles mod SMs) tiles become 128 x 64 sub-tiles
+    const int rem = tiles % kNumSMs;
+    if (batch == 1 && p.splits == 1 && tiles > kNumSMs && rem > 0 && rem <= (kNumSMs * 3) / 4) {
+      p.n_big = tiles - rem;
+      p.total = p.n_big + rem * (bn / 64);
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   if (out_dtype == OFA_BF16) {

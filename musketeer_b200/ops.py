@@ -376,7 +376,8 @@ class _BatchNorm(torch.autograd.Function):
         call("ofa_batchnorm_fwd", _p(x), _p(res), _p(y), _p(gamma), _p(beta), _p(running_mean), _p(running_var), R, Cc,
              float(eps), float(momentum), int(training), int(relu), _p(stats), _p(ws), _dt(x), _st(),
              work=("byte", (2 + training + (res is not None)) * R * Cc * x.element_size()))
-        ctx.save_for_backward(x, y if relu else None, gamma, stats)
+        # with a residual the ReLU mask needs y; without one it is recomputed from x (saves a full read in the backward)
+        ctx.save_for_backward(x, y if (relu and res is not None) else None, gamma, stats)
         ctx.beta_param = beta
         ctx.relu, ctx.training, ctx.has_res = relu, training, residual is not None
         return y
@@ -398,7 +399,7 @@ class _BatchNorm(torch.autograd.Function):
             dg = tg if fused else torch.empty_like(gamma)
             db = tb if fused else torch.empty_like(gamma)
         ws = torch.empty(_lib.load().ofa_batchnorm_workspace_floats(Cc), dtype=torch.float32, device=x.device)
-        call("ofa_batchnorm_bwd", _p(x), _p(dy), _p(y), _p(gamma), _p(stats), _p(stats[Cc:]), _p(dx), _p(dres), _p(dg), _p(db),
+        call("ofa_batchnorm_bwd", _p(x), _p(dy), _p(y), _p(gamma), _p(stats), _p(dx), _p(dres), _p(dg), _p(db),
              int(fused and ag), R, Cc, int(ctx.training), int(ctx.relu), _p(ws), _dt(x), _st(),
              work=("byte", (4 + 2 * ctx.relu + ctx.has_res) * R * Cc * x.element_size()))
         if fused or not want_pg:
