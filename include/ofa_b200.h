@@ -27,6 +27,8 @@ int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   long long ldr, long long stride_r, void* workspace, long long workspace_bytes, void* stream);
 /* host helper: bytes of fp32 split-K scratch the call above wants for this problem (0 = none; passing less is legal) */
 long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch);
+/* A/B switch for the 2-CTA cluster variant (B operand TMA-multicast); returns the previous setting (default: on) */
+int ofa_gemm_set_pair_mode(int enabled);
 
 /* fp32 -> three bf16 terms laid out as six K-blocks (fp32 parity mode operands for ofa_gemm_bf16) */
 int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, long long ldo, long long blk_stride,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "ofa_gemm_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_p, c_f,
                       c_i, c_p, c_ll, c_ll, c_p, c_ll, c_p],
     "ofa_gemm_workspace_bytes": [c_i, c_i, c_i, c_i],
+    "ofa_gemm_set_pair_mode": [c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],

@@ -15,6 +15,8 @@
 // kernel without transposed copies.  fp32 "parity mode" feeds it 3-way bf16 splits concatenated along K (ops.py).
 #include "common.cuh"
 
+static int g_ofa_gemm_pair_enabled = 1;   // 2-CTA cluster variant on/off (ofa_gemm_set_pair_mode)
+
 namespace {
 
 constexpr int BM = 128, BK = 64;
@@ -65,26 +67,27 @@ struct Work {
 };
 // Tail splitting: with T tiles on P persistent CTAs the last T mod P tiles would occupy a whole extra round; they are
 // issued as 128 x 64 sub-tiles instead so the tail spreads over all SMs.
-template <int BN>
-__device__ __forceinline__ Work decode(int w, const GemmParams& p) {
+template <int BN, int PAIR>
+__device__ __forceinline__ Work decode(int w, const GemmParams& p, int crank) {
   Work r;
   int sub = 0;
   r.bn = BN;
+  constexpr int SUB = PAIR ? 128 : 64;   // a pair shares B in two halves, so its sub-tiles stay a multiple of 128 wide
   if (w >= p.n_big) {
-    const int q = BN / 64;
+    const int q = BN / SUB;
     const int u = w - p.n_big;
     sub = u % q;
     w = p.n_big + u / q;
-    r.bn = 64;
+    r.bn = SUB;
   }
   const int nt = w % p.tiles_n;  // n fastest: CTAs running concurrently share the A row-block through L2
   w /= p.tiles_n;
-  const int mt = w % p.tiles_m;
+  const int mt = w % p.tiles_m;  // PAIR: tiles_m counts row-tile PAIRS
   w /= p.tiles_m;
   r.sp = w % p.splits;
   r.bz = w / p.splits;
-  r.m0 = mt * BM;
-  r.n0 = nt * BN + sub * 64;
+  r.m0 = (PAIR ? 2 * mt + crank : mt) * BM;
+  r.n0 = nt * BN + sub * SUB;
   return r;
 }
 
@@ -118,10 +121,17 @@ __device__ __forceinline__ void store_row32(OutT* dp, const float (&v)[32], int 
   }
 }
 
-template <int A_MN, int B_MN, typename OutT, int BN>
+// PAIR = 1: launched as clusters of two CTAs that own vertically adjacent 128-row tiles of the same column tile.  The B
+// (weight) stage is shared: each CTA fetches half of it and TMA-multicasts it into both CTAs' shared memory, which halves
+// the L2 -> SM traffic of the B operand (the 128 x 256 single-CTA kernel saturates the ~12 TB/s L2 fabric at ~750
+// TFLOP/s).  A stage may be refilled only after BOTH CTAs' MMAs have consumed it: tcgen05.commit multicasts the release.
+template <int A_MN, int B_MN, typename OutT, int BN, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using C = Cfg<BN>;
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int wstart = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout<BN>& sm =
       *reinterpret_cast<SmemLayout<BN>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], PAIR ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.tmem_full[i], 1);
@@ -145,14 +155,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 2) tmem_alloc<C::kTmemCols>(&sm.tmem_addr);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_addr;
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0, ph = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const Work wk = decode<BN>(w, p);
+      for (int w = wstart; w < total; w += wstep) {
+        const Work wk = decode<BN, PAIR>(w, p, crank);
         const int m0 = wk.m0, n0 = wk.n0;
         const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
         const int nchunk = wk.bn / 64;
@@ -167,7 +178,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           } else {
             tma_load_3d(sa, &tmA, &sm.full[s], kb * BK, m0, wk.bz);
           }
-          if (B_MN) {
+          if (PAIR) {   // this CTA fetches chunks [crank*nchunk/2, (crank+1)*nchunk/2) for both CTAs
+            const int c_lo = crank * (nchunk >> 1), c_hi = c_lo + (nchunk >> 1);
+            if (B_MN) {
+              for (int c = c_lo; c < c_hi; ++c) tma_load_3d_mc(sb + c * BK * 128, &tmB, &sm.full[s], n0 + 64 * c, kb * BK, wk.bz, 3);
+            } else {
+              for (int c = c_lo; c < c_hi; ++c) tma_load_3d_mc(sb + c * 64 * 128, &tmB, &sm.full[s], kb * BK, n0 + 64 * c, wk.bz, 3);
+            }
+          } else if (B_MN) {
             for (int c = 0; c < nchunk; ++c) tma_load_3d(sb + c * BK * 128, &tmB, &sm.full[s], n0 + 64 * c, kb * BK, wk.bz);
           } else {   // 64-row boxes stacked at the 1024 B / 8-row pitch
             for (int c = 0; c < nchunk; ++c) tma_load_3d(sb + c * 64 * 128, &tmB, &sm.full[s], kb * BK, n0 + 64 * c, wk.bz);
@@ -180,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       int s = 0, ph = 0, it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const Work wk = decode<BN>(w, p);
+      for (int w = wstart; w < total; w += wstep, ++it) {
+        const Work wk = decode<BN, PAIR>(w, p, crank);
         const uint32_t idesc = umma_idesc_bf16(BM, wk.bn, A_MN, B_MN);
         const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
         const int acc = it & 1;
@@ -201,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
             umma_f16(tmem_d, da, db, idesc, (kb != kb0) | (k != 0));
           }
-          umma_commit(&sm.empty[s]);  // frees the smem stage when these MMAs retire
+          if (PAIR) umma_commit_mc(&sm.empty[s], 3);  // both CTAs' producers write into this stage of both CTAs
+          else umma_commit(&sm.empty[s]);             // frees the smem stage when these MMAs retire
           if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
         umma_commit(&sm.tmem_full[acc]);
@@ -212,8 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
     int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const Work wk = decode<BN>(w, p);
+    for (int w = wstart; w < total; w += wstep, ++it) {
+      const Work wk = decode<BN, PAIR>(w, p, crank);
       const int m0 = wk.m0, n0 = wk.n0;
       const int nch = wk.bn / 32;
       const int acc = it & 1;
@@ -279,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA may retire while the peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
@@ -303,9 +323,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
   reinterpret_cast<OutT*>(p.D)[(long long)bz * p.batch_stride_d + (long long)m * p.ldd + n] = (OutT)v;
 }
 
-template <int A_MN, int B_MN, typename OutT, int BN>
+template <int A_MN, int B_MN, typename OutT, int BN, int PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<A_MN, B_MN, OutT, BN>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, OutT, BN, PAIR>;
   static bool configured = false;  // per template instantiation
   const int smem = (int)sizeof(SmemLayout<BN>) + 1024;
   if (!configured) {
@@ -313,7 +333,24 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
     configured = true;
   }
   const int total = p.total;
-  kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, p);
+  if (PAIR) {
+    const int clusters = total < kNumSMs / 2 ? total : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  } else {
+    kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, p);
+  }
   OFA_LAUNCH_CHECK("gemm_tc_kernel");
   if (p.splits > 1) {
     const long long n = (long long)p.M * p.N * p.batch;
@@ -324,8 +361,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 }
 
 template <int A_MN, int B_MN, typename OutT>
-int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  return bn == 256 ? launch<A_MN, B_MN, OutT, 256>(ta, tb, p, st) : launch<A_MN, B_MN, OutT, 128>(ta, tb, p, st);
+int launch_bn(int bn, int pair, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (pair) return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 1>(ta, tb, p, st) : launch<A_MN, B_MN, OutT, 128, 1>(ta, tb, p, st);
+  return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 0>(ta, tb, p, st) : launch<A_MN, B_MN, OutT, 128, 0>(ta, tb, p, st);
 }
 
 void plan(int M, int N, int K, int batch, int* bn, int* splits) {
@@ -345,6 +383,13 @@ void plan(int M, int N, int K, int batch, int* bn, int* splits) {
 }
 
 }  // namespace
+
+// debugging / A-B switch for the CTA-pair (TMA multicast) variant; returns the previous setting
+extern "C" int ofa_gemm_set_pair_mode(int enabled) {
+  const int old = g_ofa_gemm_pair_enabled;
+  g_ofa_gemm_pair_enabled = enabled;
+  return old;
+}
 
 // host helper: bytes of fp32 split-K workspace ofa_gemm_bf16 wants for this problem (0 = none)
 extern "C" long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch) {
@@ -392,32 +437,38 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   const int nkb = (K + BK - 1) / BK;
   p.kb_per_split = (nkb + splits - 1) / splits;
   p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty trailing slices
+  // CTA pairs (B multicast) for plain problems with enough row tiles
+  const int pair = (batch == 1 && p.splits == 1 && p.tiles_m >= 2 && (long long)p.tiles_m * p.tiles_n >= kNumSMs &&
+                    g_ofa_gemm_pair_enabled) ? 1 : 0;
+  if (pair) p.tiles_m = (p.tiles_m + 1) / 2;
   {
+    const int workers = pair ? kNumSMs / 2 : kNumSMs;
     const int tiles = p.tiles_m * p.tiles_n * batch * p.splits;
     p.n_big = tiles;
     p.total = tiles;
-    // tail splitting (plain problems only): the last (tiles mod SMs) tiles become 128 x 64 sub-tiles
-    const int rem = tiles % kNumSMs;
-    if (batch == 1 && p.splits == 1 && tiles > kNumSMs && rem > 0 && rem <= (kNumSMs * 3) / 4) {
+    // tail splitting (plain problems only): the last (tiles mod workers) tiles are issued as narrower sub-tiles
+    const int rem = tiles % workers;
+    const int sub = pair ? 128 : 64;
+    if (batch == 1 && p.splits == 1 && tiles > workers && rem > 0 && rem <= (workers * 3) / 4 && bn > sub) {
       p.n_big = tiles - rem;
-      p.total = p.n_big + rem * (bn / 64);
+      p.total = p.n_big + rem * (bn / sub);
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   if (out_dtype == OFA_BF16) {
     switch (sel) {
-      case 0: return launch_bn<0, 0, __nv_bfloat16>(bn, ta, tb, p, st);
-      case 1: return launch_bn<0, 1, __nv_bfloat16>(bn, ta, tb, p, st);
-      case 2: return launch_bn<1, 0, __nv_bfloat16>(bn, ta, tb, p, st);
-      default: return launch_bn<1, 1, __nv_bfloat16>(bn, ta, tb, p, st);
+      case 0: return launch_bn<0, 0, __nv_bfloat16>(bn, pair, ta, tb, p, st);
+      case 1: return launch_bn<0, 1, __nv_bfloat16>(bn, pair, ta, tb, p, st);
+      case 2: return launch_bn<1, 0, __nv_bfloat16>(bn, pair, ta, tb, p, st);
+      default: return launch_bn<1, 1, __nv_bfloat16>(bn, pair, ta, tb, p, st);
     }
   } else if (out_dtype == OFA_F32) {
     switch (sel) {
-      case 0: return launch_bn<0, 0, float>(bn, ta, tb, p, st);
-      case 1: return launch_bn<0, 1, float>(bn, ta, tb, p, st);
-      case 2: return launch_bn<1, 0, float>(bn, ta, tb, p, st);
-      default: return launch_bn<1, 1, float>(bn, ta, tb, p, st);
+      case 0: return launch_bn<0, 0, float>(bn, pair, ta, tb, p, st);
+      case 1: return launch_bn<0, 1, float>(bn, pair, ta, tb, p, st);
+      case 2: return launch_bn<1, 0, float>(bn, pair, ta, tb, p, st);
+      default: return launch_bn<1, 1, float>(bn, pair, ta, tb, p, st);
     }
   }
   return ofa_set_error("ofa_gemm_bf16: bad out_dtype %d", out_dtype);

@@ -5,6 +5,8 @@ import torch
 from musketeer_b200 import ops
 
 SHAPES = [  # (name, M, N, K, a_mn, b_mn)
+    ("enc b16 fc1 fwd", 13360, 3072, 768, 0, 0), ("enc b16 fc2 fwd", 13360, 768, 3072, 0, 0),
+    ("enc b16 fc1 wgrad", 3072, 768, 13360, 1, 1),
     ("enc qkv fwd", 6680, 768, 768, 0, 0), ("enc fused-qkv fwd", 6680, 2304, 768, 0, 0),
     ("enc fc1 fwd", 6680, 3072, 768, 0, 0), ("enc fc2 fwd", 6680, 768, 3072, 0, 0),
     ("enc fc1 dgrad", 6680, 768, 3072, 0, 1), ("enc fc1 wgrad", 3072, 768, 6680, 1, 1),
@@ -12,7 +14,10 @@ SHAPES = [  # (name, M, N, K, a_mn, b_mn)
     ("logits fwd", 1856, 59457, 768, 0, 0), ("logits dgrad", 1856, 768, 59457, 0, 1),
     ("logits wgrad", 59457, 768, 1856, 1, 1),
 ]
+from musketeer_b200 import _lib
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+if len(sys.argv) > 1 and sys.argv[1] == "--no-pair":
+    _lib.load().ofa_gemm_set_pair_mode(0)
 for name, M, N, K, a_mn, b_mn in SHAPES:
     K8, M8, N8 = (K + 7) // 8 * 8, (M + 7) // 8 * 8, (N + 7) // 8 * 8
     A = torch.randn((K, M8) if a_mn else (M, K8), device="cuda").bfloat16()
