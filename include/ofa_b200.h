@@ -27,7 +27,8 @@ int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   long long ldr, long long stride_r, void* workspace, long long workspace_bytes, void* stream);
 /* host helper: bytes of fp32 split-K scratch the call above wants for this problem (0 = none; passing less is legal) */
 long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch);
-/* A/B switch for the 2-CTA cluster variant (B operand TMA-multicast); returns the previous setting (default: on) */
+/* kernel variant switch (A/B testing): 0 single-CTA tiles, 1 CTA pair with TMA-multicast B, 2 cta_group::2 MMA on
+ * 256x256 pair tiles (default); returns the previous setting */
 int ofa_gemm_set_pair_mode(int enabled);
 
 /* fp32 -> three bf16 terms laid out as six K-blocks (fp32 parity mode operands for ofa_gemm_bf16) */

@@ -15,7 +15,7 @@
 // kernel without transposed copies.  fp32 "parity mode" feeds it 3-way bf16 splits concatenated along K (ops.py).
 #include "common.cuh"
 
-static int g_ofa_gemm_pair_enabled = 1;   // 2-CTA cluster variant on/off (ofa_gemm_set_pair_mode)
+static int g_ofa_gemm_pair_enabled = 2;   // 0: single-CTA tiles, 1: pair with B multicast, 2: cta_group::2 MMA
 
 namespace {
 
@@ -305,6 +305,225 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a cluster of two CTAs (one SM pair) computes a 256 x 256 tile with ONE tcgen05.mma stream issued by
+// the leader CTA.  Each CTA stages its own 128 A rows and only HALF of the B tile (128 of the 256 n-rows); the tensor
+// cores read the other half from the peer SM's shared memory.  Per SM and 64-deep k-block that is 32 KB of L2 -> SM
+// traffic for 2 M MACs (64 B/clk at full MMA rate) instead of 48 KB (96 B/clk) for the single-CTA 128 x 256 tile, which
+// ncu showed pinned at ~52 % tensor-pipe activity by the SM's L2 read port (profiles/r01_ncu_gemm_*).
+// Barriers: TMA of both CTAs signals the LEADER's full[s]; tcgen05.commit multicasts to both CTAs' empty[s] / tmem_full;
+// the peer's epilogue warps arrive remotely on the leader's tmem_empty.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6;
+constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;   // A rows of this CTA + this CTA's half of B
+
+struct SmemLayout2 {
+  uint8_t tiles[kStages2][kStageBytes2];
+  uint64_t full[kStages2];      // used on the leader: 2 arrivals (one per CTA) + all TMA bytes of the pair
+  uint64_t empty[kStages2];     // per CTA, released by the leader's multicast commit
+  uint64_t tmem_full[2];        // per CTA, multicast commit after the last k-block
+  uint64_t tmem_empty[2];       // leader only: 4 local + 4 remote epilogue warps
+  uint32_t tmem_addr;
+};
+
+struct Work2 {
+  int m0, n0, bn;   // m0: first row of the PAIR tile (256 rows); bn: 256 or 128 (tail sub-tile)
+};
+__device__ __forceinline__ Work2 decode2(int w, const GemmParams& p) {
+  Work2 r;
+  int sub = 0;
+  r.bn = 256;
+  if (w >= p.n_big) {
+    const int u = w - p.n_big;
+    sub = u & 1;
+    w = p.n_big + (u >> 1);
+    r.bn = 128;
+  }
+  const int nt = w % p.tiles_n;
+  const int mt = w / p.tiles_n;
+  r.m0 = mt * 256;
+  r.n0 = nt * 256 + sub * 128;
+  return r;
+}
+
+template <int A_MN, int B_MN, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  SmemLayout2& sm = *reinterpret_cast<SmemLayout2*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  const int wstart = blockIdx.x >> 1, wstep = gridDim.x >> 1;
+  const int total = p.total;
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&sm.full[s], 2);
+      mbar_init(&sm.empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.tmem_full[i], 1);
+      mbar_init(&sm.tmem_empty[i], 8);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<512>(&sm.tmem_addr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_addr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int w = wstart; w < total; w += wstep) {
+        const Work2 wk = decode2(w, p);
+        const int m0 = wk.m0 + crank * 128;             // this CTA's A rows
+        const int nh = wk.bn >> 1;                      // n-rows of B held by each CTA
+        const int n0 = wk.n0 + crank * nh;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&sm.empty[s], ph ^ 1);
+          uint8_t* sa = sm.tiles[s];
+          uint8_t* sb = sa + BM * BK * 2;
+          if (leader) mbar_expect_tx(&sm.full[s], 2 * (BM + nh) * BK * 2);
+          else mbar_arrive_remote(&sm.full[s], 0);
+          if (A_MN) {
+            tma_load_3d_2sm(sa, &tmA, &sm.full[s], m0, kb * BK, 0);
+            tma_load_3d_2sm(sa + BK * 128, &tmA, &sm.full[s], m0 + 64, kb * BK, 0);
+          } else {
+            tma_load_3d_2sm(sa, &tmA, &sm.full[s], kb * BK, m0, 0);
+          }
+          for (int c = 0; c < nh / 64; ++c) {
+            if (B_MN) tma_load_3d_2sm(sb + c * BK * 128, &tmB, &sm.full[s], n0 + 64 * c, kb * BK, 0);
+            else tma_load_3d_2sm(sb + c * 64 * 128, &tmB, &sm.full[s], kb * BK, n0 + 64 * c, 0);
+          }
+          if (++s == kStages2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      int s = 0, ph = 0, it = 0;
+      for (int w = wstart; w < total; w += wstep, ++it) {
+        const Work2 wk = decode2(w, p);
+        const uint32_t idesc = umma_idesc_bf16(256, wk.bn, A_MN, B_MN);
+        const int acc = it & 1;
+        mbar_wait_cluster(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_cluster(&sm.full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sm.tiles[s]);
+          const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_2sm(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm_mc(&sm.empty[s], 3);
+          if (++s == kStages2) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm_mc(&sm.tmem_full[acc], 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    OutT* D = reinterpret_cast<OutT*>(p.D);
+    const OutT* R = reinterpret_cast<const OutT*>(p.resid);
+    const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
+    for (int w = wstart; w < total; w += wstep, ++it) {
+      const Work2 wk = decode2(w, p);
+      const int acc = it & 1;
+      const int row = wk.m0 + crank * 128 + q * 32 + lane;
+      mbar_wait_cluster(&sm.tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const int nch = wk.bn / 32;
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_d + c * 32, r);
+        tmem_ld_wait();
+        const int nb = wk.n0 + c * 32;
+        if (row < p.M && nb < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int nvalid = min(32, p.N - nb);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += ld_as_float<OutT>(bias + nb + j);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (R) {
+            const OutT* rr = R + (long long)row * p.ldr + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += ld_as_float<OutT>(rr + j);
+          }
+          store_row32<OutT>(D + (long long)row * p.ldd + nb, v, nvalid);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&sm.tmem_empty[acc]);
+        else mbar_arrive_remote(&sm.tmem_empty[acc], 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+template <int A_MN, int B_MN, typename OutT>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, OutT>;
+  static bool configured = false;
+  const int smem = (int)sizeof(SmemLayout2) + 1024;
+  if (!configured) {
+    OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int clusters = p.total < kNumSMs / 2 ? p.total : kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  OFA_LAUNCH_CHECK("gemm_tc2_kernel");
+  return 0;
+}
+
 // out[b][m][n] = epi(sum_sp ws[sp][b][m][n])
 template <typename OutT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
@@ -437,9 +656,41 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   const int nkb = (K + BK - 1) / BK;
   p.kb_per_split = (nkb + splits - 1) / splits;
   p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty trailing slices
-  // CTA pairs (B multicast) for plain problems with enough row tiles
+  // cta_group::2 (mode 2): 256 x 256 pair tiles for plain problems with at least one full round of pair tiles
+  if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && p.splits == 1 && N >= 256 &&
+      (long long)((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2) {
+    p.tiles_m = (M + 255) / 256;
+    p.tiles_n = (N + 255) / 256;
+    const int tiles = p.tiles_m * p.tiles_n, workers = kNumSMs / 2;
+    p.n_big = tiles;
+    p.total = tiles;
+    const int rem = tiles % workers;
+    if (tiles > workers && rem > 0 && rem <= (workers * 3) / 4) {
+      p.n_big = tiles - rem;
+      p.total = p.n_big + rem * 2;
+    }
+    cudaStream_t st2 = (cudaStream_t)stream;
+    const int sel2 = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+    if (out_dtype == OFA_BF16) {
+      switch (sel2) {
+        case 0: return launch2<0, 0, __nv_bfloat16>(ta, tb, p, st2);
+        case 1: return launch2<0, 1, __nv_bfloat16>(ta, tb, p, st2);
+        case 2: return launch2<1, 0, __nv_bfloat16>(ta, tb, p, st2);
+        default: return launch2<1, 1, __nv_bfloat16>(ta, tb, p, st2);
+      }
+    } else if (out_dtype == OFA_F32) {
+      switch (sel2) {
+        case 0: return launch2<0, 0, float>(ta, tb, p, st2);
+        case 1: return launch2<0, 1, float>(ta, tb, p, st2);
+        case 2: return launch2<1, 0, float>(ta, tb, p, st2);
+        default: return launch2<1, 1, float>(ta, tb, p, st2);
+      }
+    }
+    return ofa_set_error("ofa_gemm_bf16: bad out_dtype %d", out_dtype);
+  }
+  // CTA pairs with B multicast (mode 1) for plain problems with enough row tiles
   const int pair = (batch == 1 && p.splits == 1 && p.tiles_m >= 2 && (long long)p.tiles_m * p.tiles_n >= kNumSMs &&
-                    g_ofa_gemm_pair_enabled) ? 1 : 0;
+                    g_ofa_gemm_pair_enabled == 1) ? 1 : 0;
   if (pair) p.tiles_m = (p.tiles_m + 1) / 2;
   {
     const int workers = pair ? kNumSMs / 2 : kNumSMs;

@@ -15,9 +15,12 @@ SHAPES = [  # (name, M, N, K, a_mn, b_mn)
     ("logits wgrad", 59457, 768, 1856, 1, 1),
 ]
 from musketeer_b200 import _lib
+if "--one" in sys.argv:
+    SHAPES = SHAPES[:2]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-if len(sys.argv) > 1 and sys.argv[1] == "--no-pair":
-    _lib.load().ofa_gemm_set_pair_mode(0)
+for _m in (0, 1, 2):
+    if "--mode%d" % _m in sys.argv:
+        _lib.load().ofa_gemm_set_pair_mode(_m)
 for name, M, N, K, a_mn, b_mn in SHAPES:
     K8, M8, N8 = (K + 7) // 8 * 8, (M + 7) // 8 * 8, (N + 7) // 8 * 8
     A = torch.randn((K, M8) if a_mn else (M, K8), device="cuda").bfloat16()
