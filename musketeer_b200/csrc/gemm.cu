@@ -319,7 +319,7 @@ constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;   // A rows of this CTA +
 
 struct SmemLayout2 {
   uint8_t tiles[kStages2][kStageBytes2];
-  uint64_t full[kStages2];      // used on the leader: 2 arrivals (one per CTA) + all TMA bytes of the pair
+  uint64_t full[kStages2];      // used on the leader: its arrive.expect_tx + the TMA bytes of both CTAs
   uint64_t empty[kStages2];     // per CTA, released by the leader's multicast commit
   uint64_t tmem_full[2];        // per CTA, multicast commit after the last k-block
   uint64_t tmem_empty[2];       // leader only: 4 local + 4 remote epilogue warps
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages2; ++s) {
-      mbar_init(&sm.full[s], 2);
+      mbar_init(&sm.full[s], 1);     // the leader's arrive.expect_tx; the peer contributes bytes only
       mbar_init(&sm.empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -390,8 +390,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
           mbar_wait(&sm.empty[s], ph ^ 1);
           uint8_t* sa = sm.tiles[s];
           uint8_t* sb = sa + BM * BK * 2;
+          // The leader arms its barrier with the bytes of BOTH CTAs.  The peer only issues its loads: a remote arrive here
+          // would cost a MEMBAR.ALL.GPU per k-block (release.cluster) and serialise the peer's ring (seen in ncu).
           if (leader) mbar_expect_tx(&sm.full[s], 2 * (BM + nh) * BK * 2);
-          else mbar_arrive_remote(&sm.full[s], 0);
           if (A_MN) {
             tma_load_3d_2sm(sa, &tmA, &sm.full[s], m0, kb * BK, 0);
             tma_load_3d_2sm(sa + BK * 128, &tmA, &sm.full[s], m0 + 64, kb * BK, 0);
@@ -414,11 +415,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
         const Work2 wk = decode2(w, p);
         const uint32_t idesc = umma_idesc_bf16(256, wk.bn, A_MN, B_MN);
         const int acc = it & 1;
-        mbar_wait_cluster(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait_cluster(&sm.full[s], ph);
+          mbar_wait(&sm.full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(sm.tiles[s]);
           const uint32_t sb = sa + BM * BK * 2;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
       const Work2 wk = decode2(w, p);
       const int acc = it & 1;
       const int row = wk.m0 + crank * 128 + q * 32 + lane;
-      mbar_wait_cluster(&sm.tmem_full[acc], (it >> 1) & 1);
+      mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const int nch = wk.bn / 32;
