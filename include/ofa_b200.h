@@ -30,6 +30,9 @@ long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch);
 /* kernel variant switch (A/B testing): 0 single-CTA tiles, 1 CTA pair with TMA-multicast B, 2 cta_group::2 MMA on
  * 256x256 pair tiles (default); returns the previous setting */
 int ofa_gemm_set_pair_mode(int enabled);
+/* bf16 epilogue variant switch (A/B testing): 1 staged through shared memory + TMA store (default), 0 per-thread row
+ * stores; returns the previous setting */
+int ofa_gemm_set_tma_store(int enabled);
 
 /* fp32 -> three bf16 terms laid out as six K-blocks (fp32 parity mode operands for ofa_gemm_bf16) */
 int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, long long ldo, long long blk_stride,
@@ -70,6 +73,17 @@ int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma
 int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* stats, void* dx,
                       void* dres, void* dgamma, void* dbeta, int accumulate, long long R,
                       int C, int batch_stats, int relu, float* workspace, int dtype, void* stream);
+
+/* ---- fused optimizer step (trainer.py:863-898 multiply_grads -> clip_grad_norm -> optimizer.step,
+ * with the un-vendored fairseq Adam / FP16Optimizer arithmetic: fp32 master weights, decoupled weight decay
+ * p -= wd*lr*p, bias-corrected step size, global-norm clipping with coefficient clip/(norm+1e-6)).
+ * chunk_table: device array of n_chunks records {void* param; const void* grad; float* master; float* m; float* v;
+ * long long n;} (48 bytes each, n <= 65536 elements per chunk); partial_sqnorm: n_chunks floats of scratch;
+ * grad_norm_out: optional device float receiving the (scaled, unclipped) global gradient norm.  Two launches, no host
+ * synchronisation; clip_norm <= 0 disables clipping; step >= 1 is the 1-based update count.                         */
+int ofa_adam_step(const void* chunk_table, int n_chunks, float* partial_sqnorm, float* grad_norm_out, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, float clip_norm,
+                  int param_dtype, void* stream);
 
 /* ---- label-smoothed CE (+R-Drop KL): loss rows and d(logits) in one kernel, gradient written in place --------------
  * replaces criterions/label_smoothed_cross_entropy.py:81-126,228-260.                                                */

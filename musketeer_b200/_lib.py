@@ -39,6 +39,7 @@ SIGNATURES = {
                       c_i, c_p, c_ll, c_ll, c_p, c_ll, c_p],
     "ofa_gemm_workspace_bytes": [c_i, c_i, c_i, c_i],
     "ofa_gemm_set_pair_mode": [c_i],
+    "ofa_gemm_set_tma_store": [c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],
@@ -55,6 +56,7 @@ SIGNATURES = {
     "ofa_batchnorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_p],
     "ofa_ls_ce_fwd_bwd": [c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_i,
                           c_p],
+    "ofa_adam_step": [c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_p],
     "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p],
     "ofa_attn_fwd_simt": [C.POINTER(OfaAttnArgs), c_i, c_p],
     "ofa_attn_bwd_simt": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_i, c_p],

@@ -13,6 +13,11 @@ template <typename T>
 struct V8 {};
 template <>
 struct V8<float> {
+  struct Raw { float4 a, b; };
+  __device__ static Raw ldraw(const float* p) { Raw r; r.a = reinterpret_cast<const float4*>(p)[0]; r.b = reinterpret_cast<const float4*>(p)[1]; return r; }
+  __device__ static void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   __device__ static void load(const float* p, float (&v)[8]) {
     float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -24,6 +29,13 @@ struct V8<float> {
 };
 template <>
 struct V8<__nv_bfloat16> {
+  struct Raw { uint4 u; };
+  __device__ static Raw ldraw(const __nv_bfloat16* p) { Raw r; r.u = *reinterpret_cast<const uint4*>(p); return r; }
+  __device__ static void unpack(const Raw& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
   __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -38,241 +50,302 @@ struct V8<__nv_bfloat16> {
 
 constexpr int kT = 256;
 
-// per-channel partial sums.  MODE 0: (sum x, sum x^2).  MODE 1: (sum g, sum g*xhat) with g = dy * (relu ? y > 0 : 1).
-// block = (C/8 threads per row) x (256 / (C/8) rows); partials [gridDim.x][2][C]
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kT) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
-                                                       const T* __restrict__ y, const float* __restrict__ mean,
-                                                       const float* __restrict__ rstd, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, long long R, int C, int relu,
-                                                       float* __restrict__ part) {
-  const int tpr = C / 8;                 // threads per row
-  const int rpi = kT / tpr;              // rows per block iteration
-  const int cx = threadIdx.x % tpr, ry = threadIdx.x / tpr;
-  const int c0 = cx * 8;
-  float a[8], b[8], mu[8], rs[8], sc[8], sh[8];
+// Thread mapping shared by all four kernels: the channel axis is cut into slabs of CS = min(C, 256) channels
+// (blockIdx.y); inside a slab tpr = CS/8 threads cover one row (one 16-byte vector each) and the kT/tpr row-lanes of the
+// CTA walk the rows with stride gridDim.x * rpi, kUnroll rows in flight per thread.  A thread keeps its 8 channels for the
+// whole kernel, so per-channel coefficients live in registers instead of being re-read for every element.
+struct Map {
+  int tpr, rpi, cx, ry, c0;
+  long long r0, stride;
+};
+__device__ __forceinline__ Map make_map(int CS) {
+  Map m;
+  m.tpr = CS >> 3;
+  m.rpi = kT / m.tpr;
+  m.cx = threadIdx.x % m.tpr;
+  m.ry = threadIdx.x / m.tpr;
+  m.c0 = blockIdx.y * CS + m.cx * 8;
+  m.r0 = (long long)blockIdx.x * m.rpi + m.ry;
+  m.stride = (long long)gridDim.x * m.rpi;
+  return m;
+}
+
+// block-level reduction of per-thread (a[8], b[8]) over the row-lanes, then one atomicAdd per channel and CTA into
+// sums[0][C] / sums[1][C] (zeroed by the host wrapper).  fp32 atomics: the summation order varies run to run in the last
+// bits, as with the library BatchNorm this replaces.
+__device__ __forceinline__ void block_accumulate(const Map& m, int C, int CS, const float (&a)[8], const float (&b)[8],
+                                                 float* __restrict__ sums) {
+  __shared__ float sa[kT * 8], sb[kT * 8];   // [rpi][CS]
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; mu[j] = 0.f; rs[j] = 1.f; sc[j] = 0.f; sh[j] = 0.f; }
-  if (MODE == 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; }
-    if (relu && !y) {   // no residual: the ReLU mask is recomputed from x, saving the read of y
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
-    }
+  for (int j = 0; j < 8; ++j) {
+    sa[m.ry * CS + m.cx * 8 + j] = a[j];
+    sb[m.ry * CS + m.cx * 8 + j] = b[j];
   }
-  if (ry < rpi) {
-    for (long long r = (long long)blockIdx.x * rpi + ry; r < R; r += (long long)gridDim.x * rpi) {
-      float xv[8];
-      V8<T>::load(x + r * C + c0, xv);
-      if (MODE == 0) {
+  __syncthreads();
+  if ((int)threadIdx.x < CS) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int q = 0; q < m.rpi; ++q) { s0 += sa[q * CS + threadIdx.x]; s1 += sb[q * CS + threadIdx.x]; }
+    atomicAdd(sums + blockIdx.y * CS + threadIdx.x, s0);
+    atomicAdd(sums + C + blockIdx.y * CS + threadIdx.x, s1);
+  }
+}
+
+constexpr int kUnroll = 4;
+
+// forward statistics: sums[0][c] += sum x, sums[1][c] += sum x^2
+template <typename T>
+__global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x, long long R, int C, int CS,
+                                                      float* __restrict__ sums) {
+  const Map m = make_map(CS);
+  float a[8], b[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] += xv[j]; b[j] += xv[j] * xv[j]; }
-      } else {
-        float g[8];
-        V8<T>::load(dy + r * C + c0, g);
-        if (relu) {
-          if (y) {
-            float yv[8];
-            V8<T>::load(y + r * C + c0, yv);
+  for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
+  for (long long r = m.r0; r < R; r += kUnroll * m.stride) {
+    typename V8<T>::Raw raw[kUnroll];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-          } else {
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long ru = r + u * m.stride;
+      raw[u] = V8<T>::ldraw(x + (ru < R ? ru : m.r0) * C + m.c0);
+    }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-          }
-        }
+    for (int u = 0; u < kUnroll; ++u) {
+      if (r + u * m.stride < R) {
+        float xv[8];
+        V8<T>::unpack(raw[u], xv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] += g[j]; b[j] += g[j] * (xv[j] - mu[j]) * rs[j]; }
+        for (int j = 0; j < 8; ++j) { a[j] += xv[j]; b[j] = fmaf(xv[j], xv[j], b[j]); }
       }
     }
   }
-  __shared__ float sa[kT * 8], sb[kT * 8];   // 16 KB
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { sa[threadIdx.x * 8 + j] = a[j]; sb[threadIdx.x * 8 + j] = b[j]; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kT) {
-    const int tx = c / 8, j = c % 8;
-    float s0 = 0.f, s1 = 0.f;
-    for (int q = 0; q < rpi; ++q) { s0 += sa[(q * tpr + tx) * 8 + j]; s1 += sb[(q * tpr + tx) * 8 + j]; }
-    part[((size_t)blockIdx.x * 2 + 0) * C + c] = s0;
-    part[((size_t)blockIdx.x * 2 + 1) * C + c] = s1;
-  }
+  block_accumulate(m, C, CS, a, b, sums);
 }
 
-// sum the [nparts][2][C] partials for channel c: 8 lanes per channel (threadIdx.x / 32), combined through shared memory
-__device__ __forceinline__ void sum_partials(const float* __restrict__ part, int nparts, int C, int c, float& s0, float& s1) {
-  __shared__ float r0[8][33], r1[8][33];
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  float a = 0.f, b = 0.f;
-  if (c < C)
-    for (int p = py; p < nparts; p += 8) { a += part[((size_t)p * 2) * C + c]; b += part[((size_t)p * 2 + 1) * C + c]; }
-  r0[py][cx] = a; r1[py][cx] = b;
-  __syncthreads();
-  s0 = 0.f; s1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { s0 += r0[i][cx]; s1 += r1[i][cx]; }
-}
-
-// forward finalize: mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running-stat update
+// forward apply: y = relu?(x * scale_c + shift_c + res).  Every thread derives scale / shift of its 8 channels from the
+// sums (training) or the running statistics (eval / frozen); CTA column 0 also publishes mean | rstd | scale | shift for
+// the backward and updates the running statistics.
 template <typename T>
-__global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, long long R,
-                                       const T* __restrict__ gamma, const T* __restrict__ beta, float eps,
-                                       float momentum, T* __restrict__ running_mean, T* __restrict__ running_var,
-                                       float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                       float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  float s0, s1;
-  sum_partials(part, nparts, C, c, s0, s1);
-  if (c >= C || threadIdx.x >= 32) return;
-  const float n = (float)R;
-  const float mean = s0 / n;
-  const float var = fmaxf(s1 / n - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  mean_out[c] = mean;
-  rstd_out[c] = rstd;
-  const float sc = (float)gamma[c] * rstd;
-  scale[c] = sc;
-  shift[c] = (float)beta[c] - mean * sc;
-  if (running_mean) {
-    running_mean[c] = (T)((1.f - momentum) * (float)running_mean[c] + momentum * mean);
-    running_var[c] = (T)((1.f - momentum) * (float)running_var[c] + momentum * var * n / fmaxf(n - 1.f, 1.f));
-  }
-}
-
-// eval / frozen mode: scale / shift (and mean / rstd for the backward) from the running statistics
-template <typename T>
-__global__ void bn_eval_coeff_kernel(int C, const T* __restrict__ gamma, const T* __restrict__ beta,
-                                     const T* __restrict__ running_mean, const T* __restrict__ running_var, float eps,
-                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                     float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float mean = (float)running_mean[c];
-  const float rstd = rsqrtf((float)running_var[c] + eps);
-  mean_out[c] = mean;
-  rstd_out[c] = rstd;
-  const float sc = (float)gamma[c] * rstd;
-  scale[c] = sc;
-  shift[c] = (float)beta[c] - mean * sc;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kT) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res,
-                                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      T* __restrict__ y, long long n8, int C, int relu) {
-  const long long v = (long long)blockIdx.x * kT + threadIdx.x;
-  if (v >= n8) return;
-  const int c0 = (int)((v * 8) % C);
-  float xv[8];
-  V8<T>::load(x + v * 8, xv);
+__global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                      const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                      T* __restrict__ running_mean, T* __restrict__ running_var,
+                                                      const float* __restrict__ sums, float* __restrict__ stats,
+                                                      long long R, int C, int CS, float eps, float momentum, int training,
+                                                      int relu) {
+  const Map m = make_map(CS);
+  float sc[8], sh[8];
+  {
+    const float n = (float)R;
+    const bool publish = blockIdx.x == 0 && m.ry == 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) xv[j] = xv[j] * scale[c0 + j] + shift[c0 + j];
-  if (res) {
-    float rv[8];
-    V8<T>::load(res + v * 8, rv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] += rv[j];
-  }
-  if (relu) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] = fmaxf(xv[j], 0.f);
-  }
-  V8<T>::store(y + v * 8, xv);
-}
-
-// backward finalize: dgamma = s2, dbeta = s1 (optionally accumulated), coefficients for the apply pass
-template <typename T>
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, long long R,
-                                       const T* __restrict__ gamma, const float* __restrict__ rstd, int batch_stats,
-                                       T* __restrict__ dgamma, T* __restrict__ dbeta, int accumulate,
-                                       float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  float s1, s2;
-  sum_partials(part, nparts, C, c, s1, s2);
-  if (c >= C || threadIdx.x >= 32) return;
-  if (dgamma) {
-    dgamma[c] = (T)(s2 + (accumulate ? (float)dgamma[c] : 0.f));
-    dbeta[c] = (T)(s1 + (accumulate ? (float)dbeta[c] : 0.f));
-  }
-  ca[c] = (float)gamma[c] * rstd[c];
-  cb[c] = batch_stats ? s1 / (float)R : 0.f;
-  cc[c] = batch_stats ? s2 / (float)R : 0.f;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
-                                                          const T* __restrict__ y, const float* __restrict__ mean,
-                                                          const float* __restrict__ rstd, const float* __restrict__ ca,
-                                                          const float* __restrict__ cb, const float* __restrict__ cc,
-                                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                                          T* __restrict__ dx, T* __restrict__ dres, long long n8, int C,
-                                                          int relu) {
-  const long long v = (long long)blockIdx.x * kT + threadIdx.x;
-  if (v >= n8) return;
-  const int c0 = (int)((v * 8) % C);
-  float xv[8], g[8];
-  V8<T>::load(x + v * 8, xv);
-  V8<T>::load(dy + v * 8, g);
-  if (relu) {
-    if (y) {
-      float yv[8];
-      V8<T>::load(y + v * 8, yv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], scale[c0 + j], shift[c0 + j]) > 0.f ? g[j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const int c = m.c0 + j;
+      float mean, var;
+      if (training) {
+        mean = sums[c] / n;
+        var = fmaxf(sums[C + c] / n - mean * mean, 0.f);
+      } else {
+        mean = (float)running_mean[c];
+        var = (float)running_var[c];
+      }
+      const float rstd = rsqrtf(var + eps);
+      sc[j] = (float)gamma[c] * rstd;
+      sh[j] = (float)beta[c] - mean * sc[j];
+      if (publish) {
+        stats[c] = mean; stats[C + c] = rstd; stats[2 * C + c] = sc[j]; stats[3 * C + c] = sh[j];
+        if (training && running_mean) {
+          running_mean[c] = (T)((1.f - momentum) * (float)running_mean[c] + momentum * mean);
+          running_var[c] = (T)((1.f - momentum) * (float)running_var[c] + momentum * var * n / fmaxf(n - 1.f, 1.f));
+        }
+      }
     }
   }
-  if (dres) V8<T>::store(dres + v * 8, g);
-  float o[8];
+  for (long long r = m.r0; r < R; r += kUnroll * m.stride) {
+    typename V8<T>::Raw rx[kUnroll], rr[kUnroll];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float xh = (xv[j] - mean[c0 + j]) * rstd[c0 + j];
-    o[j] = ca[c0 + j] * (g[j] - cb[c0 + j] - xh * cc[c0 + j]);
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long ru = r + u * m.stride < R ? r + u * m.stride : m.r0;
+      rx[u] = V8<T>::ldraw(x + ru * C + m.c0);
+      if (res) rr[u] = V8<T>::ldraw(res + ru * C + m.c0);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long ru = r + u * m.stride;
+      if (ru < R) {
+        float xv[8], rv[8];
+        V8<T>::unpack(rx[u], xv);
+        if (res) V8<T>::unpack(rr[u], rv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = fmaf(xv[j], sc[j], sh[j]);
+          if (res) v += rv[j];
+          xv[j] = relu ? fmaxf(v, 0.f) : v;
+        }
+        V8<T>::store(y + ru * C + m.c0, xv);
+      }
+    }
   }
-  V8<T>::store(dx + v * 8, o);
 }
 
-int nparts_for(long long R, int C) {
-  const int rpi = kT / (C / 8);
-  long long n = (R + rpi - 1) / rpi;
-  return (int)(n < 296 ? n : 296);   // 2 CTAs per SM
+// backward statistics: sums[0][c] += sum g, sums[1][c] += sum g * xhat, g = dy * (relu ? y > 0 : 1).  Without a residual
+// the ReLU mask is recomputed from x with the forward's scale / shift (saves the read of y).
+template <typename T>
+__global__ void __launch_bounds__(kT, 3) bn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                          const T* __restrict__ y, const float* __restrict__ stats,
+                                                          long long R, int C, int CS, int relu, float* __restrict__ sums) {
+  const Map m = make_map(CS);
+  float a[8], b[8], sc[8], sh[8];   // b accumulates sum g*x; the xhat form follows from (b - mean*a) * rstd at the end
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = m.c0 + j;
+    a[j] = 0.f; b[j] = 0.f;
+    sc[j] = stats[2 * C + c]; sh[j] = stats[3 * C + c];
+  }
+  constexpr int U = 2;
+  for (long long r = m.r0; r < R; r += U * m.stride) {
+    typename V8<T>::Raw rx[U], rg[U], ry_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * m.stride < R ? r + u * m.stride : m.r0;
+      rx[u] = V8<T>::ldraw(x + ru * C + m.c0);
+      rg[u] = V8<T>::ldraw(dy + ru * C + m.c0);
+      if (relu && y) ry_[u] = V8<T>::ldraw(y + ru * C + m.c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u * m.stride < R) {
+        float xv[8], g[8], yv[8];
+        V8<T>::unpack(rx[u], xv);
+        V8<T>::unpack(rg[u], g);
+        if (relu && y) V8<T>::unpack(ry_[u], yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float gg = g[j];
+          if (relu) {
+            const float act = y ? yv[j] : fmaf(xv[j], sc[j], sh[j]);
+            gg = act > 0.f ? gg : 0.f;
+          }
+          a[j] += gg;
+          b[j] = fmaf(gg, xv[j], b[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = (b[j] - stats[m.c0 + j] * a[j]) * stats[C + m.c0 + j];
+  block_accumulate(m, C, CS, a, b, sums);
+}
+
+// backward apply: dx = ca*(g - s1/n - xhat*s2/n) = ca*g + A*x + B  with  ca = gamma*rstd, A = -ca*rstd*s2/n,
+// B = -ca*s1/n - A*mean  (eval / frozen statistics: A = B = 0);  dres = g.  CTA column 0 writes dgamma = s2, dbeta = s1.
+template <typename T>
+__global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                          const T* __restrict__ y, const T* __restrict__ gamma,
+                                                          const float* __restrict__ stats, const float* __restrict__ sums,
+                                                          T* __restrict__ dx, T* __restrict__ dres, T* __restrict__ dgamma,
+                                                          T* __restrict__ dbeta, int accumulate, long long R, int C, int CS,
+                                                          int batch_stats, int relu) {
+  const Map m = make_map(CS);
+  float ca[8], cA[8], cB[8], sc[8], sh[8];
+  {
+    const float inv_n = 1.f / (float)R;
+    const bool publish = blockIdx.x == 0 && m.ry == 0 && dgamma != nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = m.c0 + j;
+      const float mean = stats[c], rstd = stats[C + c];
+      sc[j] = stats[2 * C + c]; sh[j] = stats[3 * C + c];
+      const float s1 = sums ? sums[c] : 0.f, s2 = sums ? sums[C + c] : 0.f;
+      ca[j] = (float)gamma[c] * rstd;
+      cA[j] = batch_stats ? -ca[j] * rstd * s2 * inv_n : 0.f;
+      cB[j] = batch_stats ? -ca[j] * s1 * inv_n - cA[j] * mean : 0.f;
+      if (publish) {
+        dgamma[c] = (T)(s2 + (accumulate ? (float)dgamma[c] : 0.f));
+        dbeta[c] = (T)(s1 + (accumulate ? (float)dbeta[c] : 0.f));
+      }
+    }
+  }
+  constexpr int U = 2;
+  for (long long r = m.r0; r < R; r += U * m.stride) {
+    typename V8<T>::Raw rx[U], rg[U], ry_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * m.stride < R ? r + u * m.stride : m.r0;
+      rx[u] = V8<T>::ldraw(x + ru * C + m.c0);
+      rg[u] = V8<T>::ldraw(dy + ru * C + m.c0);
+      if (relu && y) ry_[u] = V8<T>::ldraw(y + ru * C + m.c0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ru = r + u * m.stride;
+      if (ru < R) {
+        float xv[8], g[8], yv[8];
+        V8<T>::unpack(rx[u], xv);
+        V8<T>::unpack(rg[u], g);
+        if (relu && y) V8<T>::unpack(ry_[u], yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float gg = g[j];
+          if (relu) {
+            const float act = y ? yv[j] : fmaf(xv[j], sc[j], sh[j]);
+            gg = act > 0.f ? gg : 0.f;
+          }
+          g[j] = gg;
+          xv[j] = fmaf(ca[j], gg, fmaf(cA[j], xv[j], cB[j]));
+        }
+        if (dres) V8<T>::store(dres + ru * C + m.c0, g);
+        V8<T>::store(dx + ru * C + m.c0, xv);
+      }
+    }
+  }
+}
+
+struct Grid {
+  int CS;
+  dim3 g;
+};
+Grid grid_for(long long R, int C, int unroll) {
+  Grid r;
+  r.CS = C < 256 ? C : 256;
+  const int slabs = C / r.CS;
+  const int rpi = kT / (r.CS / 8);
+  long long gx = (R + (long long)rpi * unroll - 1) / ((long long)rpi * unroll);
+  const long long cap = (148 * 6 + slabs - 1) / slabs;   // ~6 CTAs of 256 threads per SM in total
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  r.g = dim3((unsigned)gx, (unsigned)slabs);
+  return r;
 }
 
 template <typename T>
 int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* rm, void* rv,
              long long R, int C, float eps, float momentum, int training, int relu, float* stats, float* ws,
              cudaStream_t st) {
-  float* mean = stats; float* rstd = stats + C; float* scale = stats + 2 * C; float* shift = stats + 3 * C; float* part = ws;
+  float* sums = ws;
   if (training) {
-    const int np = nparts_for(R, C);
-    bn_reduce_kernel<T, 0><<<np, kT, 0, st>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R, C, 0, part);
-    bn_fwd_finalize_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, np, C, R, (const T*)gamma, (const T*)beta, eps, momentum,
-                                                             (T*)rm, (T*)rv, mean, rstd, scale, shift);
-  } else {
-    bn_eval_coeff_kernel<T><<<(C + 127) / 128, 128, 0, st>>>(C, (const T*)gamma, (const T*)beta, (const T*)rm, (const T*)rv,
-                                                           eps, mean, rstd, scale, shift);
+    OFA_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+    const Grid gs = grid_for(R, C, kUnroll);
+    bn_stats_kernel<T><<<gs.g, kT, 0, st>>>((const T*)x, R, C, gs.CS, sums);
   }
-  const long long n8 = R * C / 8;
-  bn_apply_kernel<T><<<(unsigned)((n8 + kT - 1) / kT), kT, 0, st>>>((const T*)x, (const T*)res, scale, shift, (T*)y, n8, C, relu);
+  const Grid ga = grid_for(R, C, kUnroll);
+  bn_apply_kernel<T><<<ga.g, kT, 0, st>>>((const T*)x, (const T*)res, (T*)y, (const T*)gamma, (const T*)beta, (T*)rm, (T*)rv,
+                                          sums, stats, R, C, ga.CS, eps, momentum, training, relu);
   OFA_LAUNCH_CHECK("batchnorm forward");
   return 0;
 }
 
 template <typename T>
-int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, const float* mean, const float* rstd,
-             const float* scale, const float* shift, void* dx, void* dres, void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats,
-             int relu, float* ws, cudaStream_t st) {
-  float* ca = ws; float* cb = ws + C; float* cc = ws + 2 * C; float* part = ws + 3 * C;
-  const int np = nparts_for(R, C);
-  bn_reduce_kernel<T, 1><<<np, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, scale, shift, R, C, relu, part);
-  bn_bwd_finalize_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(part, np, C, R, (const T*)gamma, rstd, batch_stats, (T*)dgamma,
-                                                           (T*)dbeta, accumulate, ca, cb, cc);
-  const long long n8 = R * C / 8;
-  bn_bwd_apply_kernel<T><<<(unsigned)((n8 + kT - 1) / kT), kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, ca,
-                                                                      cb, cc, scale, shift, (T*)dx, (T*)dres, n8, C, relu);
+int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, const float* stats, void* dx, void* dres,
+             void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats, int relu, float* ws,
+             cudaStream_t st) {
+  float* sums = nullptr;
+  if (batch_stats || dgamma) {   // frozen statistics without parameter gradients need no reduction at all
+    sums = ws;
+    OFA_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+    const Grid gs = grid_for(R, C, 2);
+    bn_bwd_stats_kernel<T><<<gs.g, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums);
+  }
+  const Grid ga = grid_for(R, C, 2);
+  bn_bwd_apply_kernel<T><<<ga.g, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, (const T*)gamma, stats, sums, (T*)dx,
+                                              (T*)dres, (T*)dgamma, (T*)dbeta, accumulate, R, C, ga.CS, batch_stats, relu);
   OFA_LAUNCH_CHECK("batchnorm backward");
   return 0;
 }
@@ -281,7 +354,7 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
 
 // scratch floats for either direction (partials + coefficients); `stats` of the forward is 4*C floats
 // (mean | rstd | scale | shift), of which mean and rstd are the backward's inputs
-extern "C" long long ofa_batchnorm_workspace_floats(int C) { return (long long)C * (3 + 2 * 592); }
+extern "C" long long ofa_batchnorm_workspace_floats(int C) { return 2LL * C; }
 
 extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                                  void* running_mean, void* running_var, long long R, int C, float eps, float momentum,
@@ -301,8 +374,7 @@ extern "C" int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, c
   OFA_CHECK(R > 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0, "ofa_batchnorm_bwd: C=%d must be a power of two in [8, 2048]", C);
   cudaStream_t st = (cudaStream_t)stream;
   OFA_CHECK(!relu || y || stats, "ofa_batchnorm_bwd: relu needs y or the forward stats");
-  const float *mean = stats, *rstd = stats + C, *scale = stats + 2 * C, *shift = stats + 3 * C;
-  if (dtype == OFA_BF16) return bwd_impl<__nv_bfloat16>(x, dy, y, gamma, mean, rstd, scale, shift, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
-  if (dtype == OFA_F32) return bwd_impl<float>(x, dy, y, gamma, mean, rstd, scale, shift, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
+  if (dtype == OFA_BF16) return bwd_impl<__nv_bfloat16>(x, dy, y, gamma, stats, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
+  if (dtype == OFA_F32) return bwd_impl<float>(x, dy, y, gamma, stats, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
   return ofa_set_error("ofa_batchnorm_bwd: bad dtype %d", dtype);
 }

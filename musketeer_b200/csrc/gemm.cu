@@ -13,8 +13,11 @@
 // so forward / dgrad / wgrad of every nn.Linear on the OFA path (models/ofa/unify_multihead_attention.py:213-232,399,
 // unify_transformer_layer.py:280-284,557-561, unify_transformer.py:739,906-911,1303-1316,1577-1583) run through this one
 // kernel without transposed copies.  fp32 "parity mode" feeds it 3-way bf16 splits concatenated along K (ops.py).
+#include <string.h>
+
 #include "common.cuh"
 
+static int g_ofa_gemm_tma_store = 1;      // bf16 epilogue through shared memory + TMA store (0: per-thread row stores)
 static int g_ofa_gemm_pair_enabled = 2;   // 0: single-CTA tiles, 1: pair with B multicast, 2: cta_group::2 MMA
 
 namespace {
@@ -36,6 +39,7 @@ struct GemmParams {
   int total;     // total work items
   float alpha;
   int act;  // 0 none, 1 gelu(erf)
+  int tma_store;  // bf16 output staged through shared memory and written with TMA (needs 16B-aligned D rows)
 };
 
 template <int BN>
@@ -48,6 +52,7 @@ struct Cfg {
 template <int BN>
 struct SmemLayout {
   uint8_t tiles[Cfg<BN>::kStages][Cfg<BN>::kStageBytes];  // 1024B aligned (SWIZZLE_128B)
+  uint8_t stage_out[4][2][4096];  // per epilogue warp: two 32-row x 64-column bf16 slabs (SWIZZLE_128B) for the TMA store
   uint64_t full[Cfg<BN>::kStages];
   uint64_t empty[Cfg<BN>::kStages];
   uint64_t tmem_full[2];
@@ -121,13 +126,88 @@ __device__ __forceinline__ void store_row32(OutT* dp, const float (&v)[32], int 
   }
 }
 
+
+// Epilogue of one 32-row slab (one warp) of a bf16 tile through shared memory + TMA store: every 64-column group is
+// packed into a 128B-swizzled [32][64] slab (lane = row, conflict-free 16-byte stores) and written with one
+// cp.async.bulk.tensor store, which also clips rows >= M and columns >= N.  Replaces 32 scattered 64-byte row segments
+// per warp instruction (2x the L2 write transactions) with full-line writes, and takes the stores off the LSU.
+__device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*stage)[4096], int& sbuf, uint32_t tmem_row,
+                                             int nch, int row, int n0, int bz, const GemmParams& p, int lane) {
+  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(p.bias);
+  const __nv_bfloat16* R =
+      p.resid ? reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)bz * p.batch_stride_r : nullptr;
+  const int row0 = row - lane;
+#pragma unroll 1
+  for (int c2 = 0; c2 < nch; c2 += 2) {
+    const int nb0 = n0 + c2 * 32;
+    if (nb0 >= p.N) break;
+    uint8_t* sb = stage[sbuf];
+    if (lane == 0) tma_store_wait_read<1>();   // the store issued two groups ago has finished reading this slab
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (c2 + half >= nch) break;
+      uint32_t r[32];
+      tmem_ld32(tmem_row + (c2 + half) * 32, r);
+      tmem_ld_wait();
+      const int nb = nb0 + half * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const int nvalid = min(32, p.N - nb);
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __bfloat162float(bias[nb + j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      }
+      if (R && row < p.M) {
+        const __nv_bfloat16* rr = R + (long long)row * p.ldr + nb;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint4 u = reinterpret_cast<const uint4*>(rr)[q4];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); v[q4 * 8 + 2 * k] += f.x; v[q4 * 8 + 2 * k + 1] += f.y; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __bfloat162float(rr[j]);
+        }
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int chunk = half * 4 + q4;   // 16-byte chunk inside the 128-byte slab row
+        *reinterpret_cast<uint4*>(sb + lane * 128 + ((chunk ^ (lane & 7)) << 4)) =
+            make_uint4(pack_bf16(v[8 * q4], v[8 * q4 + 1]), pack_bf16(v[8 * q4 + 2], v[8 * q4 + 3]),
+                       pack_bf16(v[8 * q4 + 4], v[8 * q4 + 5]), pack_bf16(v[8 * q4 + 6], v[8 * q4 + 7]));
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmD, sb, nb0, row0, bz);
+      tma_store_commit();
+    }
+    sbuf ^= 1;
+  }
+}
+
 // PAIR = 1: launched as clusters of two CTAs that own vertically adjacent 128-row tiles of the same column tile.  The B
 // (weight) stage is shared: each CTA fetches half of it and TMA-multicasts it into both CTAs' shared memory, which halves
 // the L2 -> SM traffic of the B operand (the 128 x 256 single-CTA kernel saturates the ~12 TB/s L2 fabric at ~750
 // TFLOP/s).  A stage may be refilled only after BOTH CTAs' MMAs have consumed it: tcgen05.commit multicasts the release.
 template <int A_MN, int B_MN, typename OutT, int BN, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmD, GemmParams p) {
   using C = Cfg<BN>;
   const int crank = PAIR ? (int)cluster_ctarank() : 0;
   const int wstart = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -230,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else {
     // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
-    int it = 0;
+    int it = 0, sbuf = 0;
     for (int w = wstart; w < total; w += wstep, ++it) {
       const Work wk = decode<BN, PAIR>(w, p, crank);
       const int m0 = wk.m0, n0 = wk.n0;
@@ -240,7 +320,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      if (p.splits > 1) {
+      if (sizeof(OutT) == 2 && p.tma_store) {
+        if (m0 + q * 32 < p.M) epilogue_tma(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, row, n0, wk.bz, p, lane);
+      } else if (p.splits > 1) {
         float* W = p.ws + ((size_t)(wk.sp * p.batch + wk.bz) * p.M) * p.N;
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
@@ -295,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);  // accumulator buffer may be overwritten
     }
+    if (lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last bulk stores
   }
   tc_fence_before();
   __syncthreads();
@@ -319,6 +402,7 @@ constexpr int kStageBytes2 = (BM * BK + 128 * BK) * 2;   // A rows of this CTA +
 
 struct SmemLayout2 {
   uint8_t tiles[kStages2][kStageBytes2];
+  uint8_t stage_out[4][2][4096];
   uint64_t full[kStages2];      // used on the leader: its arrive.expect_tx + the TMA bytes of both CTAs
   uint64_t empty[kStages2];     // per CTA, released by the leader's multicast commit
   uint64_t tmem_full[2];        // per CTA, multicast commit after the last k-block
@@ -348,7 +432,8 @@ __device__ __forceinline__ Work2 decode2(int w, const GemmParams& p) {
 
 template <int A_MN, int B_MN, typename OutT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmD, GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   SmemLayout2& sm = *reinterpret_cast<SmemLayout2*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -438,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
     __syncwarp();
   } else {
     const int q = warp & 3;
-    int it = 0;
+    int it = 0, sbuf = 0;
     OutT* D = reinterpret_cast<OutT*>(p.D);
     const OutT* R = reinterpret_cast<const OutT*>(p.resid);
     const OutT* bias = reinterpret_cast<const OutT*>(p.bias);
@@ -450,6 +535,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const int nch = wk.bn / 32;
+      if (sizeof(OutT) == 2 && p.tma_store) {
+        if (row - lane < p.M) epilogue_tma(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, row, wk.n0, 0, p, lane);
+      } else {
 #pragma unroll 1
       for (int c = 0; c < nch; ++c) {
         uint32_t r[32];
@@ -481,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
           store_row32<OutT>(D + (long long)row * p.ldd + nb, v, nvalid);
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -488,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
         else mbar_arrive_remote(&sm.tmem_empty[acc], 0);
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -499,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
 }
 
 template <int A_MN, int B_MN, typename OutT>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm_tc2_kernel<A_MN, B_MN, OutT>;
   static bool configured = false;
   const int smem = (int)sizeof(SmemLayout2) + 1024;
@@ -520,7 +610,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
   OFA_LAUNCH_CHECK("gemm_tc2_kernel");
   return 0;
 }
@@ -544,7 +634,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
 }
 
 template <int A_MN, int B_MN, typename OutT, int BN, int PAIR>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm_tc_kernel<A_MN, B_MN, OutT, BN, PAIR>;
   static bool configured = false;  // per template instantiation
   const int smem = (int)sizeof(SmemLayout<BN>) + 1024;
@@ -567,9 +657,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
   } else {
-    kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, p);
+    kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, td, p);
   }
   OFA_LAUNCH_CHECK("gemm_tc_kernel");
   if (p.splits > 1) {
@@ -581,9 +671,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 }
 
 template <int A_MN, int B_MN, typename OutT>
-int launch_bn(int bn, int pair, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  if (pair) return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 1>(ta, tb, p, st) : launch<A_MN, B_MN, OutT, 128, 1>(ta, tb, p, st);
-  return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 0>(ta, tb, p, st) : launch<A_MN, B_MN, OutT, 128, 0>(ta, tb, p, st);
+int launch_bn(int bn, int pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
+  if (pair) return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 1>(ta, tb, td, p, st) : launch<A_MN, B_MN, OutT, 128, 1>(ta, tb, td, p, st);
+  return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 0>(ta, tb, td, p, st) : launch<A_MN, B_MN, OutT, 128, 0>(ta, tb, td, p, st);
 }
 
 void plan(int M, int N, int K, int batch, int* bn, int* splits) {
@@ -605,6 +695,11 @@ void plan(int M, int N, int K, int batch, int* bn, int* splits) {
 }  // namespace
 
 // debugging / A-B switch for the CTA-pair (TMA multicast) variant; returns the previous setting
+extern "C" int ofa_gemm_set_tma_store(int enabled) {
+  const int old = g_ofa_gemm_tma_store;
+  g_ofa_gemm_tma_store = enabled;
+  return old;
+}
 extern "C" int ofa_gemm_set_pair_mode(int enabled) {
   const int old = g_ofa_gemm_pair_enabled;
   g_ofa_gemm_pair_enabled = enabled;
@@ -649,7 +744,23 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     strides[1] = (uint64_t)(batch > 1 ? stride_b : (long long)dims[1] * ldb) * 2;
     if (int e = ofa_make_tmap(&tb, B, 3, dims, strides, box, 1, 2)) return e;
   }
+  CUtensorMap td;
+  memset(&td, 0, sizeof(td));
+  const int nkb_plan = (K + BK - 1) / BK;
+  const int kbps = (nkb_plan + splits - 1) / splits;
+  const bool unsplit = (nkb_plan + kbps - 1) / kbps == 1;
+  int tma_store = 0;
+  if (g_ofa_gemm_tma_store && out_dtype == OFA_BF16 && unsplit && ldd % 8 == 0 && ((uintptr_t)D & 15) == 0 &&
+      (batch == 1 || stride_d % 8 == 0)) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch}, strides[2];
+    uint32_t box[3] = {64, 32, 1};
+    strides[0] = (uint64_t)ldd * 2;
+    strides[1] = (uint64_t)(batch > 1 ? stride_d : (long long)M * ldd) * 2;
+    if (int e = ofa_make_tmap(&td, D, 3, dims, strides, box, 1, 2)) return e;
+    tma_store = 1;
+  }
   GemmParams p;
+  p.tma_store = tma_store;
   p.D = D; p.bias = bias; p.resid = resid; p.ws = (float*)workspace; p.ldd = ldd; p.ldr = ldr;
   p.batch_stride_d = stride_d; p.batch_stride_r = stride_r;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
@@ -674,17 +785,17 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     const int sel2 = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
     if (out_dtype == OFA_BF16) {
       switch (sel2) {
-        case 0: return launch2<0, 0, __nv_bfloat16>(ta, tb, p, st2);
-        case 1: return launch2<0, 1, __nv_bfloat16>(ta, tb, p, st2);
-        case 2: return launch2<1, 0, __nv_bfloat16>(ta, tb, p, st2);
-        default: return launch2<1, 1, __nv_bfloat16>(ta, tb, p, st2);
+        case 0: return launch2<0, 0, __nv_bfloat16>(ta, tb, td, p, st2);
+        case 1: return launch2<0, 1, __nv_bfloat16>(ta, tb, td, p, st2);
+        case 2: return launch2<1, 0, __nv_bfloat16>(ta, tb, td, p, st2);
+        default: return launch2<1, 1, __nv_bfloat16>(ta, tb, td, p, st2);
       }
     } else if (out_dtype == OFA_F32) {
       switch (sel2) {
-        case 0: return launch2<0, 0, float>(ta, tb, p, st2);
-        case 1: return launch2<0, 1, float>(ta, tb, p, st2);
-        case 2: return launch2<1, 0, float>(ta, tb, p, st2);
-        default: return launch2<1, 1, float>(ta, tb, p, st2);
+        case 0: return launch2<0, 0, float>(ta, tb, td, p, st2);
+        case 1: return launch2<0, 1, float>(ta, tb, td, p, st2);
+        case 2: return launch2<1, 0, float>(ta, tb, td, p, st2);
+        default: return launch2<1, 1, float>(ta, tb, td, p, st2);
       }
     }
     return ofa_set_error("ofa_gemm_bf16: bad out_dtype %d", out_dtype);
@@ -710,17 +821,17 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   if (out_dtype == OFA_BF16) {
     switch (sel) {
-      case 0: return launch_bn<0, 0, __nv_bfloat16>(bn, pair, ta, tb, p, st);
-      case 1: return launch_bn<0, 1, __nv_bfloat16>(bn, pair, ta, tb, p, st);
-      case 2: return launch_bn<1, 0, __nv_bfloat16>(bn, pair, ta, tb, p, st);
-      default: return launch_bn<1, 1, __nv_bfloat16>(bn, pair, ta, tb, p, st);
+      case 0: return launch_bn<0, 0, __nv_bfloat16>(bn, pair, ta, tb, td, p, st);
+      case 1: return launch_bn<0, 1, __nv_bfloat16>(bn, pair, ta, tb, td, p, st);
+      case 2: return launch_bn<1, 0, __nv_bfloat16>(bn, pair, ta, tb, td, p, st);
+      default: return launch_bn<1, 1, __nv_bfloat16>(bn, pair, ta, tb, td, p, st);
     }
   } else if (out_dtype == OFA_F32) {
     switch (sel) {
-      case 0: return launch_bn<0, 0, float>(bn, pair, ta, tb, p, st);
-      case 1: return launch_bn<0, 1, float>(bn, pair, ta, tb, p, st);
-      case 2: return launch_bn<1, 0, float>(bn, pair, ta, tb, p, st);
-      default: return launch_bn<1, 1, float>(bn, pair, ta, tb, p, st);
+      case 0: return launch_bn<0, 0, float>(bn, pair, ta, tb, td, p, st);
+      case 1: return launch_bn<0, 1, float>(bn, pair, ta, tb, td, p, st);
+      case 2: return launch_bn<1, 0, float>(bn, pair, ta, tb, td, p, st);
+      default: return launch_bn<1, 1, float>(bn, pair, ta, tb, td, p, st);
     }
   }
   return ofa_set_error("ofa_gemm_bf16: bad out_dtype %d", out_dtype);

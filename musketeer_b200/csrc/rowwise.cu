@@ -116,60 +116,86 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, co
 // LayerNorm backward.  Persistent CTAs loop over rows; dgamma/dbeta partials stay in registers and are written as
 // [gridDim.x, C] fp32 partials that ln_bwd_reduce_kernel sums.   dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) [* gelu'(x)]
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(512) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename T, int GELU, int U>
+__global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                      const T* __restrict__ gamma, const float* __restrict__ mean_in,
                                                      const float* __restrict__ rstd_in, T* __restrict__ dx,
                                                      float* __restrict__ part_g, float* __restrict__ part_b, int rows,
-                                                     int C, int gelu_in) {
+                                                     int C) {
+  // U = rows per iteration: 2 for the plain variant up to 2048 columns (latency-bound), 1 otherwise (GELU is erf-bound)
   // blockDim.x = ceil(C/8) rounded up to a warp: thread t owns columns 8t..8t+7 of every row this CTA visits, so the
   // dgamma / dbeta partials need no cross-thread reduction; erf is evaluated once per element (GELU value and derivative).
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  __shared__ float red[2][2][16];
+  __shared__ float red[2][4][16];
   const int c = threadIdx.x * 8;
   const bool act = c < C;
   float ag[8], ab[8], gm[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; gm[j] = 0.f; }
   if (act) Vec8<T>::load(gamma + c, gm);
+  // two rows per iteration: both rows' loads are in flight together and one barrier serves both reductions
   int it = 0;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x, it ^= 1) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float d[8], xh[8], gp[8];
-    float s1 = 0.f, s2 = 0.f;
-    if (act) {
-      float raw[8];
-      Vec8<T>::load(dy + (size_t)row * C + c, d);
-      Vec8<T>::load(x + (size_t)row * C + c, raw);
+  for (int row = blockIdx.x; row < rows; row += U * gridDim.x, it ^= 1) {
+    const int row1 = row + gridDim.x;
+    const bool has1 = U == 2 && row1 < rows;
+    const int rr[2] = {row, has1 ? row1 : row};
+    float mean[U], rstd[U], d[U][8], xh[U][8], gp[U][8], s1[U], s2[U];
+    float raw[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float fx = raw[j];
-        gp[j] = 1.f;
-        if (gelu_in) {
-          const float cdf = 0.5f * (1.0f + erff(raw[j] * 0.70710678118654752440f));
-          fx = raw[j] * cdf;
-          gp[j] = cdf + raw[j] * 0.39894228040143267794f * __expf(-0.5f * raw[j] * raw[j]);
-        }
-        xh[j] = (fx - mean) * rstd;
-        const float g = d[j] * gm[j];
-        s1 += g;
-        s2 += g * xh[j];
-        ag[j] += d[j] * xh[j];
-        ab[j] += d[j];
+    for (int u = 0; u < U; ++u) {
+      mean[u] = mean_in[rr[u]]; rstd[u] = rstd_in[rr[u]];
+      if (act) {
+        Vec8<T>::load(dy + (size_t)rr[u] * C + c, d[u]);
+        Vec8<T>::load(x + (size_t)rr[u] * C + c, raw[u]);
       }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) { red[it][0][warp] = s1; red[it][1][warp] = s2; }
-    __syncthreads();
-    s1 = 0.f; s2 = 0.f;
-    for (int w = 0; w < nwarp; ++w) { s1 += red[it][0][w]; s2 += red[it][1][w]; }
-    s1 /= C; s2 /= C;
-    if (act) {
-      float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * gm[j] - s1 - xh[j] * s2) * gp[j];
-      Vec8<T>::store(dx + (size_t)row * C + c, o);
+    for (int u = 0; u < U; ++u) {
+      s1[u] = 0.f; s2[u] = 0.f;
+      if (act && (u == 0 || has1)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float fx = raw[u][j];
+          gp[u][j] = 1.f;
+          if (GELU) {
+            const float cdf = 0.5f * (1.0f + erff(raw[u][j] * 0.70710678118654752440f));
+            fx = raw[u][j] * cdf;
+            gp[u][j] = cdf + raw[u][j] * 0.39894228040143267794f * __expf(-0.5f * raw[u][j] * raw[u][j]);
+          }
+          xh[u][j] = (fx - mean[u]) * rstd[u];
+          const float g = d[u][j] * gm[j];
+          s1[u] += g;
+          s2[u] += g * xh[u][j];
+          ag[j] += d[u][j] * xh[u][j];
+          ab[j] += d[u][j];
+        }
+      }
+      s1[u] = warp_sum(s1[u]);
+      s2[u] = warp_sum(s2[u]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { red[it][2 * u][warp] = s1[u]; red[it][2 * u + 1][warp] = s2[u]; }
+    }
+    __syncthreads();
+    float t[2 * U];
+#pragma unroll
+    for (int k = 0; k < 2 * U; ++k) t[k] = 0.f;
+    for (int w = 0; w < nwarp; ++w) {
+#pragma unroll
+      for (int k = 0; k < 2 * U; ++k) t[k] += red[it][k][w];
+    }
+    if (act) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u == 0 || has1) {
+          const float m1 = t[2 * u] / C, m2 = t[2 * u + 1] / C;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rstd[u] * (d[u][j] * gm[j] - m1 - xh[u][j] * m2) * (GELU ? gp[u][j] : 1.f);
+          Vec8<T>::store(dx + (size_t)rr[u] * C + c, o);
+        }
+      }
     }
   }
   if (act) {
@@ -355,8 +381,12 @@ template <typename T>
 int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mean, const float* rstd, void* dx,
                   float* pg, float* pb, int nparts, int rows, int C, int gelu_in, cudaStream_t st) {
   const int threads = ((C / 8 + 31) / 32) * 32;
-  ln_bwd_kernel<T><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C,
-                                               gelu_in);
+  if (gelu_in)
+    ln_bwd_kernel<T, 1, 1><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C);
+  else if (threads <= 256)
+    ln_bwd_kernel<T, 0, 2><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C);
+  else
+    ln_bwd_kernel<T, 0, 1><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C);
   OFA_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
 }

@@ -157,6 +157,8 @@ class _Linear(torch.autograd.Function):
         x2 = x.reshape(-1, shp[-1])
         M, K = x2.shape
         N = w.shape[0]
+        ctx.w_param = w                       # leaf parameter (a 1x1 conv passes its [Cout, Cin, 1, 1] weight)
+        w = w.reshape(N, -1)
         r2 = resid.reshape(-1, N) if resid is not None else None
         ldd = _ceil8(N) if out_pad else N
         y = gemm(x2, w, M, N, K, bias=b, alpha=alpha, resid=r2, ldd=ldd)
@@ -181,12 +183,14 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
         if ctx.needs_input_grad[1]:
-            tgt, accum = _acc_target(w)
+            tgt, accum = _acc_target(ctx.w_param)
             if tgt is not None:
+                tgt = tgt.view(N, K)
                 gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt, out_dtype=w.dtype,
                      resid=tgt if accum else None)
             else:
                 dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out_dtype=w.dtype)
+                dw = dw.view(ctx.w_param.shape)
         if ctx.has_b and ctx.needs_input_grad[2]:
             tgt, accum = _acc_target(ctx.bias_param)
             if tgt is not None:
@@ -201,6 +205,19 @@ class _Linear(torch.autograd.Function):
 def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False):
     """(x W^T + b) * alpha + resid   (nn.Linear forward/backward through ofa_gemm_bf16)."""
     return _Linear.apply(x, w, b, alpha, resid, out_pad)
+
+
+def conv1x1(x, weight, stride=1):
+    """1x1 convolution (no bias) on a channels_last [N, C, H, W] tensor = the GEMM [N*H*W, Cin] x [Cout, Cin]^T on the
+    NHWC bytes (models/ofa/resnet.py:105-126: conv1 / conv3 / downsample of every bottleneck).  Returns a channels_last
+    [N, Cout, H', W'] tensor."""
+    _need_cuda(x)
+    if stride != 1:
+        x = x[:, :, ::stride, ::stride]
+    x = x.contiguous(memory_format=torch.channels_last)
+    N, Cin, H, W = x.shape
+    y = linear(x.permute(0, 2, 3, 1).reshape(N * H * W, Cin), weight)
+    return y.view(N, H, W, weight.shape[0]).permute(0, 3, 1, 2)
 
 
 def colsum(x2, alpha=1.0, out=None, accumulate=False):

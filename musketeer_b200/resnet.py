@@ -36,6 +36,8 @@ def _bn(mod, x, relu=False, residual=None):
 
 
 def _conv(mod, x):
+    if mod.kernel_size == (1, 1) and mod.stride[0] == mod.stride[1]:
+        return ops.conv1x1(x, mod.weight, mod.stride[0])          # tcgen05 GEMM on the NHWC bytes
     return F.conv2d(x, mod.weight, None, mod.stride, mod.padding)
 
 

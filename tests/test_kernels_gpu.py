@@ -308,3 +308,58 @@ def test_batchnorm_relu_residual(dtype, N, C, H, W, relu, res, training):
     if training:
         assert (rm.float() - rm2).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-2)
         assert (rv.float() - rv2).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,Cin,Cout,H,W,stride", [(2, 64, 64, 12, 12, 1), (3, 256, 64, 9, 7, 1), (2, 256, 512, 12, 12, 2),
+                                                   (2, 64, 256, 5, 5, 1)])
+def test_conv1x1_as_gemm(dtype, N, Cin, Cout, H, W, stride):
+    """1x1 convolution through the tcgen05 GEMM on NHWC bytes vs F.conv2d in fp32 (resnet.py:105-126): y, dx, dw."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) * Cin ** -0.5).cuda().to(dtype).requires_grad_()
+    y = ops.conv1x1(x, w, stride)
+    assert y.shape == (N, Cout, (H + stride - 1) // stride, (W + stride - 1) // stride)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(y.shape, generator=g).cuda().to(dtype)
+    y.backward(dy)
+    xf, wf = x.detach().double().cpu().requires_grad_(), w.detach().double().cpu().requires_grad_()   # no TF32 in the reference
+    yr = F.conv2d(xf, wf, None, stride)
+    yr.backward(dy.double().cpu())
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert (y.double().cpu() - yr).abs().max().item() < tol * max(1.0, yr.abs().max().item())
+    assert (x.grad.double().cpu() - xf.grad).abs().max().item() < tol * max(1.0, xf.grad.abs().max().item())
+    assert (w.grad.double().cpu() - wf.grad).abs().max().item() < tol * max(1.0, wf.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_adam_matches_fairseq_arithmetic(dtype):
+    """ofa_adam_step vs a plain fp32 restatement of trainer.py:863-898 + fairseq Adam / FP16Optimizer: three updates over
+    ragged parameter sizes (chunk boundaries, unaligned tails), gradient scaling, global-norm clipping, weight decay."""
+    from musketeer_b200.optim import FusedAdam
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shapes = [(70000,), (33, 7), (1,), (65536,), (257, 129)]
+    params = [torch.nn.Parameter((torch.randn(*s, generator=g) * 0.5).cuda().to(dtype)) for s in shapes]
+    opt = FusedAdam(params, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip_norm=0.1)
+    master = [p.detach().float().clone() for p in params]
+    m = [torch.zeros_like(x) for x in master]
+    v = [torch.zeros_like(x) for x in master]
+    for step in range(1, 4):
+        grads = [(torch.randn(*s, generator=g) * (0.3 if step != 2 else 1e-4)).cuda().to(dtype) for s in shapes]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        scale = 0.5
+        gn = opt.step(grad_scale=scale)
+        gf = [gr.float() * scale for gr in grads]
+        norm = torch.sqrt(sum((x.double() ** 2).sum() for x in gf)).item()
+        coef = min(1.0, 0.1 / (norm + 1e-6))
+        assert abs(gn.item() - norm) <= 1e-4 * norm
+        step_size = 1e-2 * (1 - 0.999 ** step) ** 0.5 / (1 - 0.9 ** step)
+        for i in range(len(params)):
+            gi = gf[i] * coef
+            m[i] = 0.9 * m[i] + 0.1 * gi
+            v[i] = 0.999 * v[i] + 0.001 * gi * gi
+            master[i] = master[i] - 0.01 * 1e-2 * master[i] - step_size * m[i] / (v[i].sqrt() + 1e-8)
+            assert (opt.master[opt.offsets[i]:opt.offsets[i] + master[i].numel()].view_as(master[i]) - master[i]).abs().max().item() < 2e-5
+            assert (params[i].detach().float() - master[i].to(dtype).float()).abs().max().item() <= (2e-5 if dtype == torch.float32 else 8e-3)

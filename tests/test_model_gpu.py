@@ -223,6 +223,9 @@ def test_fused_grad_accumulation_matches_autograd():
     for fused in (False, True):
         model, task = build_product(cfg, sd, dtype=torch.float32)
         model.train()
+        # batch statistics are summed with fp32 atomics (order varies in the last bit between runs, and ReLU masks next to
+        # zero amplify that through the stem): the two runs compare on running statistics, which are order-independent
+        model.encoder.embed_images.eval()
         crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0)
         inp = to_device(copy.deepcopy(samples), "cuda")
         if fused:

@@ -13,11 +13,21 @@ SHAPES = [  # (name, M, N, K, a_mn, b_mn)
     ("enc proj wgrad", 768, 768, 6680, 1, 1), ("dec small fwd", 96, 768, 768, 0, 0),
     ("logits fwd", 1856, 59457, 768, 0, 0), ("logits dgrad", 1856, 768, 59457, 0, 1),
     ("logits wgrad", 59457, 768, 1856, 1, 1),
+    # 1x1 convolutions of the ResNet-101 stem as GEMMs on NHWC bytes (64 images of 384x384)
+    ("l1 conv1 fwd", 589824, 64, 256, 0, 0), ("l1 conv3 fwd", 589824, 256, 64, 0, 0),
+    ("l1 conv3 dgrad", 589824, 64, 256, 0, 1), ("l1 conv3 wgrad", 256, 64, 589824, 1, 1),
+    ("l2 conv3 fwd", 147456, 512, 128, 0, 0), ("l3 conv1 fwd", 36864, 256, 1024, 0, 0),
+    ("l3 conv3 fwd", 36864, 1024, 256, 0, 0), ("l3 conv3 dgrad", 36864, 256, 1024, 0, 1),
+    ("l3 conv3 wgrad", 1024, 256, 36864, 1, 1), ("l3 conv1 wgrad", 256, 1024, 36864, 1, 1),
 ]
 from musketeer_b200 import _lib
 if "--one" in sys.argv:
     SHAPES = SHAPES[:2]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+if "--no-tma-store" in sys.argv:
+    _lib.load().ofa_gemm_set_tma_store(0)
+if "--conv" in sys.argv:
+    SHAPES = [s for s in SHAPES if "conv" in s[0]]
 for _m in (0, 1, 2):
     if "--mode%d" % _m in sys.argv:
         _lib.load().ofa_gemm_set_pair_mode(_m)

@@ -44,7 +44,7 @@ for ev in prof.events():
         agg[ev.name][1] += 1
 tot = sum(v[0] for v in agg.values())
 lines = ["one eager micro-step, per-task batch %d: %.2f ms device time in %d kernels" % (a.task_batch, tot / 1e3, sum(v[1] for v in agg.values()))]
-for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:160]:
     lines.append("%8.3f ms %5.1f%% %6d x %8.1f us  %s" % (t / 1e3, 100 * t / tot, n, t / n, name[:110]))
 os.makedirs(os.path.dirname(a.out), exist_ok=True)
 open(a.out, "w").write("\n".join(lines) + "\n")
