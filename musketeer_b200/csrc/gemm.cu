@@ -411,13 +411,17 @@ struct SmemLayout2 {
 };
 
 struct Work2 {
-  int m0, n0, bn;   // m0: first row of the PAIR tile (256 rows); bn: 256 or 128 (tail sub-tile)
+  int m0, n0, bn, sp;   // m0: first row of the PAIR tile (256 rows); bn: 256 or 128 (tail sub-tile); sp: K slice
 };
 __device__ __forceinline__ Work2 decode2(int w, const GemmParams& p) {
   Work2 r;
   int sub = 0;
   r.bn = 256;
-  if (w >= p.n_big) {
+  r.sp = 0;
+  if (p.splits > 1) {          // split-K: slices of one tile are adjacent work items (no tail sub-tiles)
+    r.sp = w % p.splits;
+    w /= p.splits;
+  } else if (w >= p.n_big) {
     const int u = w - p.n_big;
     sub = u & 1;
     w = p.n_big + (u >> 1);
@@ -471,7 +475,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
         const int m0 = wk.m0 + crank * 128;             // this CTA's A rows
         const int nh = wk.bn >> 1;                      // n-rows of B held by each CTA
         const int n0 = wk.n0 + crank * nh;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&sm.empty[s], ph ^ 1);
           uint8_t* sa = sm.tiles[s];
           uint8_t* sb = sa + BM * BK * 2;
@@ -503,7 +508,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
         mbar_wait(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&sm.full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(sm.tiles[s]);
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_2sm(tmem_d, da, db, idesc, (kb | k) != 0);
+            umma_f16_2sm(tmem_d, da, db, idesc, (kb != kb0) | (k != 0));
           }
           umma_commit_2sm_mc(&sm.empty[s], 3);
           if (++s == kStages2) { s = 0; ph ^= 1; }
@@ -535,7 +541,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const int nch = wk.bn / 32;
-      if (sizeof(OutT) == 2 && p.tma_store) {
+      if (p.splits > 1) {
+        float* W = p.ws + (size_t)wk.sp * p.M * p.N;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_d + c * 32, r);
+          tmem_ld_wait();
+          const int nb = wk.n0 + c * 32;
+          if (row < p.M && nb < p.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            store_row32<float>(W + (size_t)row * p.N + nb, v, min(32, p.N - nb));
+          }
+        }
+      } else if (sizeof(OutT) == 2 && p.tma_store) {
         if (row - lane < p.M) epilogue_tma(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, row, wk.n0, 0, p, lane);
       } else {
 #pragma unroll 1
@@ -588,6 +609,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
   }
 }
 
+// out[b][m][n] = epi(sum_sp ws[sp][b][m][n])
+template <typename OutT>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)p.M * p.N;
+  if (idx >= per * p.batch) return;
+  const int bz = (int)(idx / per);
+  const long long mn = idx % per;
+  const int m = (int)(mn / p.N), n = (int)(mn % p.N);
+  float v = 0.f;
+  for (int sp = 0; sp < p.splits; ++sp) v += p.ws[((size_t)(sp * p.batch + bz)) * per + mn];
+  if (p.bias) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.bias) + n);
+  v *= p.alpha;
+  if (p.act == 1) v = gelu_erf(v);
+  if (p.resid) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.resid) + (long long)bz * p.batch_stride_r + (long long)m * p.ldr + n);
+  reinterpret_cast<OutT*>(p.D)[(long long)bz * p.batch_stride_d + (long long)m * p.ldd + n] = (OutT)v;
+}
+
 template <int A_MN, int B_MN, typename OutT>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm_tc2_kernel<A_MN, B_MN, OutT>;
@@ -612,25 +651,12 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
   cfg.numAttrs = 1;
   OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
   OFA_LAUNCH_CHECK("gemm_tc2_kernel");
+  if (p.splits > 1) {
+    const long long n = (long long)p.M * p.N;
+    splitk_reduce_kernel<OutT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    OFA_LAUNCH_CHECK("splitk_reduce_kernel");
+  }
   return 0;
-}
-
-// out[b][m][n] = epi(sum_sp ws[sp][b][m][n])
-template <typename OutT>
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per = (long long)p.M * p.N;
-  if (idx >= per * p.batch) return;
-  const int bz = (int)(idx / per);
-  const long long mn = idx % per;
-  const int m = (int)(mn / p.N), n = (int)(mn % p.N);
-  float v = 0.f;
-  for (int sp = 0; sp < p.splits; ++sp) v += p.ws[((size_t)(sp * p.batch + bz)) * per + mn];
-  if (p.bias) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.bias) + n);
-  v *= p.alpha;
-  if (p.act == 1) v = gelu_erf(v);
-  if (p.resid) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.resid) + (long long)bz * p.batch_stride_r + (long long)m * p.ldr + n);
-  reinterpret_cast<OutT*>(p.D)[(long long)bz * p.batch_stride_d + (long long)m * p.ldd + n] = (OutT)v;
 }
 
 template <int A_MN, int B_MN, typename OutT, int BN, int PAIR>
@@ -676,6 +702,20 @@ int launch_bn(int bn, int pair, const CUtensorMap& ta, const CUtensorMap& tb, co
   return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 0>(ta, tb, td, p, st) : launch<A_MN, B_MN, OutT, 128, 0>(ta, tb, td, p, st);
 }
 
+// split-K plan of the cta_group::2 kernel for problems with fewer than one round of 256 x 256 pair tiles (weight gradients:
+// K = tokens): 0 = not applicable
+int plan2_splits(int M, int N, int K, int batch) {
+  if (batch != 1 || M < 256 || N < 256) return 0;
+  const int nkb = (K + BK - 1) / BK;
+  const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  const int workers = kNumSMs / 2;
+  if (t2 >= workers) return 0;
+  int s = (int)(workers / t2);
+  if (s > nkb / 64) s = nkb / 64;      // the pair pipeline needs a long main loop per slice to beat 128 x 128 tiles
+  if (s < 2 || t2 * s < (workers * 3) / 4) return 0;
+  return s;
+}
+
 void plan(int M, int N, int K, int batch, int* bn, int* splits) {
   const int tm = (M + BM - 1) / BM;
   const int nkb = (K + BK - 1) / BK;
@@ -710,6 +750,8 @@ extern "C" int ofa_gemm_set_pair_mode(int enabled) {
 extern "C" long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch) {
   int bn, splits;
   plan(M, N, K, batch, &bn, &splits);
+  const int s2 = plan2_splits(M, N, K, batch);
+  if (s2 > splits) splits = s2;
   return splits > 1 ? (long long)splits * batch * M * N * (long long)sizeof(float) : 0;
 }
 
@@ -750,8 +792,10 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   const int kbps = (nkb_plan + splits - 1) / splits;
   const bool unsplit = (nkb_plan + kbps - 1) / kbps == 1;
   int tma_store = 0;
+  // TMA stores clip at 16-byte granularity: with N % 8 != 0 the columns [N, ceil8(N)) of a row are written too (zeros), which
+  // is only acceptable when they are the row's own padding
   if (g_ofa_gemm_tma_store && out_dtype == OFA_BF16 && unsplit && ldd % 8 == 0 && ((uintptr_t)D & 15) == 0 &&
-      (batch == 1 || stride_d % 8 == 0)) {
+      (batch == 1 || stride_d % 8 == 0) && (N % 8 == 0 || ldd == (N + 7) / 8 * 8)) {
     uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch}, strides[2];
     uint32_t box[3] = {64, 32, 1};
     strides[0] = (uint64_t)ldd * 2;
@@ -768,16 +812,27 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   const int nkb = (K + BK - 1) / BK;
   p.kb_per_split = (nkb + splits - 1) / splits;
   p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty trailing slices
-  // cta_group::2 (mode 2): 256 x 256 pair tiles for plain problems with at least one full round of pair tiles
-  if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && p.splits == 1 && N >= 256 &&
-      (long long)((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2) {
+  // cta_group::2 (mode 2): 256 x 256 pair tiles for plain problems with at least one full round of pair tiles, or split
+  // along K when the output is small and the contraction long (weight gradients)
+  int s2 = g_ofa_gemm_pair_enabled == 2 ? plan2_splits(M, N, K, batch) : 0;
+  if (s2 > 1 && (workspace == nullptr || workspace_bytes < (long long)s2 * M * N * (long long)sizeof(float))) s2 = 0;
+  if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && N >= 256 &&
+      (s2 > 1 || (p.splits == 1 && (long long)((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2))) {
     p.tiles_m = (M + 255) / 256;
     p.tiles_n = (N + 255) / 256;
     const int tiles = p.tiles_m * p.tiles_n, workers = kNumSMs / 2;
     p.n_big = tiles;
     p.total = tiles;
+    p.splits = 1;
+    p.kb_per_split = nkb;
+    if (s2 > 1) {
+      p.kb_per_split = (nkb + s2 - 1) / s2;
+      p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;
+      p.total = tiles * p.splits;
+      p.tma_store = 0;
+    }
     const int rem = tiles % workers;
-    if (tiles > workers && rem > 0 && rem <= (workers * 3) / 4) {
+    if (p.splits == 1 && tiles > workers && rem > 0 && rem <= (workers * 3) / 4) {
       p.n_big = tiles - rem;
       p.total = p.n_big + rem * 2;
     }

@@ -363,3 +363,34 @@ def test_fused_adam_matches_fairseq_arithmetic(dtype):
             master[i] = master[i] - 0.01 * 1e-2 * master[i] - step_size * m[i] / (v[i].sqrt() + 1e-8)
             assert (opt.master[opt.offsets[i]:opt.offsets[i] + master[i].numel()].view_as(master[i]) - master[i]).abs().max().item() < 2e-5
             assert (params[i].detach().float() - master[i].to(dtype).float()).abs().max().item() <= (2e-5 if dtype == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize("tma_store", [1, 0])
+@pytest.mark.parametrize("M,N,K,act", [(300, 200, 136, 0), (4096, 3072, 768, 1), (2000, 4099, 256, 0), (8200, 768, 3072, 0),
+                                       (37, 64, 64, 0), (3072, 768, 6680, 0)])
+def test_gemm_bf16_output_epilogues(M, N, K, act, tma_store):
+    """bf16 output through both epilogues (shared-memory staging + TMA store vs per-thread row stores): bias, alpha, GELU,
+    residual, padded row stride, row / column tails -- against fp32 torch on the same bf16 operands."""
+    from musketeer_b200 import _lib
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    Kp, Np = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = torch.zeros(M, Kp).cuda().bfloat16()
+    B = torch.zeros(N, Kp).cuda().bfloat16()
+    A[:, :K] = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    B[:, :K] = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda().bfloat16()
+    resid = torch.randn(M, Np, generator=g).cuda().bfloat16()[:, :N]
+    out = torch.full((M, Np), 7.0, dtype=torch.bfloat16, device="cuda")
+    old = _lib.load().ofa_gemm_set_tma_store(tma_store)
+    try:
+        ops.gemm(A[:, :K], B[:, :K], M, N, K, out=out, bias=bias, alpha=0.5, act=act, resid=resid)
+    finally:
+        _lib.load().ofa_gemm_set_tma_store(old)
+    ref = (A[:, :K].float() @ B[:, :K].float().t() + bias.float()) * 0.5
+    if act:
+        ref = F.gelu(ref)
+    ref = ref + resid.float()
+    assert (out[:, :N].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    if Np > N:      # row padding: untouched by the row-store epilogue, zero-filled by the TMA store (16-byte clipping)
+        assert torch.all((out[:, N:] == 7.0) | (out[:, N:] == 0.0))
