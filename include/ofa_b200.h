@@ -75,6 +75,17 @@ int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* 
                       void* dres, void* dgamma, void* dbeta, int accumulate, long long R,
                       int C, int batch_stats, int relu, float* workspace, int dtype, void* stream);
 
+/* ---- 3x3 / stride 1 / padding 1 convolution as an implicit GEMM (models/ofa/resnet.py:107-108,119-121: conv2 of the
+ * stride-1 bottlenecks).  bf16 NHWC activations [N][H][W][C]; weight bytes [Cout][3][3][Cin] (a channels_last
+ * [Cout,Cin,3,3] tensor); Cin, Cout multiples of 64.  dgrad = 0: in = x (Cin channels) -> out = y (Cout channels);
+ * dgrad = 1: in = dy (Cout channels) -> out = dx (Cin channels).  The weight gradient is split along the pixel axis
+ * into an fp32 workspace and reduced; accumulate = 1 adds into dw (gradient accumulation across micro-batches).       */
+int ofa_conv3x3_bf16(const void* in, const void* weight, void* out, int NI, int H, int W, int Cin, int Cout, int dgrad,
+                     void* stream);
+long long ofa_conv3x3_wgrad_workspace_bytes(int NI, int H, int W, int Cin, int Cout);
+int ofa_conv3x3_wgrad_bf16(const void* x, const void* dy, void* dw, int NI, int H, int W, int Cin, int Cout,
+                           int accumulate, void* workspace, long long workspace_bytes, void* stream);
+
 /* ---- fused optimizer step (trainer.py:863-898 multiply_grads -> clip_grad_norm -> optimizer.step,
  * with the un-vendored fairseq Adam / FP16Optimizer arithmetic: fp32 master weights, decoupled weight decay
  * p -= wd*lr*p, bias-corrected step size, global-norm clipping with coefficient clip/(norm+1e-6)).

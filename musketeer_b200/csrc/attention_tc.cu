@@ -420,12 +420,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     mbar_wait(&sm.bar_sp, ph);
     tc_fence_after();
+    float dsv[32];
     {
       uint32_t rs[32], rp[32];
       tmem_ld32(tm + lane_off + COL_S + col0, rs);
       tmem_ld32(tm + lane_off + COL_DP + col0, rp);
       tmem_ld_wait();
-      float pv[32], dsv[32];
+      float pv[32];
       if (mode == 0) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
@@ -440,7 +441,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
-          if (has_tok) atomicAdd(&sm.hist_tok[tu - jj], ds);
         }
       } else if (mode == 2) {
 #pragma unroll
@@ -450,7 +450,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
-          if (has_img) atomicAdd(&sm.hist_img[idx], ds);
         }
       } else {
 #pragma unroll
@@ -470,10 +469,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
-          if (ds != 0.f) {
-            if (has_tok && tok_el) atomicAdd(&sm.hist_tok[tu - jj], ds);
-            if (has_img && img_idx >= 0) atomicAdd(&sm.hist_img[img_idx], ds);
-          }
         }
       }
 #pragma unroll
@@ -509,6 +504,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(&sm.bar_dq);
     }
     __syncwarp();
+    // relative-position table gradients: shared-memory histogram updates (fp32 shared atomics are CAS loops) run here,
+    // under the three tensor-core GEMMs just issued, instead of in front of them
+    if (mode == 1) {
+      if (has_tok) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) atomicAdd(&sm.hist_tok[tu - jj], dsv[jj]);
+      }
+    } else if (mode == 2) {
+      if (has_img) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) atomicAdd(&sm.hist_img[rowbase - (sm.kinfo[col0 + jj] & 0xffff)], dsv[jj]);
+      }
+    } else if (mode == 3 && (has_tok || has_img)) {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int jl = col0 + jj;
+        const int info = sm.kinfo[jl];
+        if (dsv[jj] != 0.f) {       // masked elements carry p = 0
+          if (has_tok && q_text && k0 + jl >= bz.k_text_off) atomicAdd(&sm.hist_tok[tu - jj], dsv[jj]);
+          if (has_img && q_img && (info & 0x40000000)) atomicAdd(&sm.hist_img[rowbase - (info & 0xffff)], dsv[jj]);
+        }
+      }
+    }
     mbar_wait(&sm.bar_dq, ph);
     tc_fence_after();
     if (t == 0 && qt + 1 < nq_tiles) {   // Q' / dO / P / dS buffers are free again

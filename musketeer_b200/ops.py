@@ -34,7 +34,7 @@ class _GradAccumulator:
             return None, False
         b = self.buf.get(k)
         if b is None or b.shape != param.shape or b.dtype != param.dtype or b.device != param.device:
-            b = self.buf[k] = torch.empty_like(param, memory_format=torch.contiguous_format)
+            b = self.buf[k] = torch.empty_like(param)      # same memory format as the parameter (channels_last conv weights)
         first = k not in self.written
         self.written.add(k)
         return b, not first
@@ -218,6 +218,54 @@ def conv1x1(x, weight, stride=1):
     N, Cin, H, W = x.shape
     y = linear(x.permute(0, 2, 3, 1).reshape(N * H * W, Cin), weight)
     return y.view(N, H, W, weight.shape[0]).permute(0, 3, 1, 2)
+
+
+class _Conv3x3(torch.autograd.Function):
+    """3x3 / stride 1 / padding 1 convolution as an implicit GEMM (csrc/conv.cu).  x: channels_last [N, Cin, H, W] bf16;
+    w: [Cout, Cin, 3, 3] stored channels_last, i.e. the bytes are [Cout][3][3][Cin]."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _need_cuda(x)
+        N, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        x = x.contiguous(memory_format=torch.channels_last)
+        wc = w.detach().contiguous(memory_format=torch.channels_last)
+        y = torch.empty((N, Cout, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        call("ofa_conv3x3_bf16", _p(x), _p(wc), _p(y), N, H, W, Cin, Cout, 0, _st(),
+             work=("flop", 2.0 * N * H * W * Cout * Cin * 9))
+        ctx.save_for_backward(x, wc)
+        ctx.w_param = w
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wc = ctx.saved_tensors
+        N, Cin, H, W = x.shape
+        Cout = wc.shape[0]
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x, memory_format=torch.channels_last)
+            call("ofa_conv3x3_bf16", _p(dy), _p(wc), _p(dx), N, H, W, Cin, Cout, 1, _st(),
+                 work=("flop", 2.0 * N * H * W * Cout * Cin * 9))
+        if ctx.needs_input_grad[1]:
+            tgt, accum = _acc_target(ctx.w_param)
+            if tgt is not None and not tgt.is_contiguous(memory_format=torch.channels_last):
+                tgt = None
+            out = tgt if tgt is not None else torch.empty_like(wc, memory_format=torch.channels_last)
+            wsb = _lib.load().ofa_conv3x3_wgrad_workspace_bytes(N, H, W, Cin, Cout)
+            ws = torch.empty(wsb // 4, dtype=torch.float32, device=x.device)
+            call("ofa_conv3x3_wgrad_bf16", _p(x), _p(dy), _p(out), N, H, W, Cin, Cout, int(tgt is not None and accum),
+                 _p(ws), wsb, _st(), work=("flop", 2.0 * N * H * W * Cout * Cin * 9))
+            if tgt is None:
+                dw = out
+        return dx, dw
+
+
+def conv3x3(x, weight):
+    """3x3, stride 1, padding 1, no bias, bf16 (models/ofa/resnet.py conv2 of the stride-1 bottlenecks)."""
+    return _Conv3x3.apply(x, weight)
 
 
 def colsum(x2, alpha=1.0, out=None, accumulate=False):

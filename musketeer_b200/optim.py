@@ -16,6 +16,15 @@ from .ops import _dt, _p, _st
 CHUNK = 65536
 
 
+def _dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _flat(t):
+    """1-D view of a dense tensor in storage order."""
+    return t.as_strided((t.numel(),), (1,))
+
+
 class FusedAdam:
     def __init__(self, params, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip_norm=0.1):
         seen, self.params = set(), []
@@ -28,8 +37,8 @@ class FusedAdam:
         p0 = self.params[0]
         if not p0.is_cuda:
             raise _lib.OfaKernelError("FusedAdam needs CUDA parameters (no CPU fallback exists)")
-        if any(p.dtype != p0.dtype or p.device != p0.device or not p.is_contiguous() for p in self.params):
-            raise ValueError("FusedAdam: parameters must share dtype and device and be contiguous")
+        if any(p.dtype != p0.dtype or p.device != p0.device or not _dense(p) for p in self.params):
+            raise ValueError("FusedAdam: parameters must share dtype and device and be dense in memory")
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.step_count = 0
         n = sum(p.numel() for p in self.params)
@@ -40,7 +49,7 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.offsets, off = [], 0
         for p in self.params:
-            self.master[off:off + p.numel()].copy_(p.detach().reshape(-1).float())
+            self.master[off:off + p.numel()].copy_(_flat(p.detach()).float())      # storage order (channels_last weights)
             self.offsets.append(off)
             off += p.numel()
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -57,8 +66,8 @@ class FusedAdam:
         n_chunks = 0
         for p, off in zip(self.params, self.offsets):
             g = p.grad
-            if g.dtype != p.dtype or not g.is_contiguous():
-                raise ValueError("FusedAdam: gradients must be contiguous and in the parameter dtype")
+            if g.dtype != p.dtype or g.stride() != p.stride():
+                raise ValueError("FusedAdam: gradients must have the parameter's dtype and memory layout")
             for c0 in range(0, p.numel(), CHUNK):
                 cn = min(CHUNK, p.numel() - c0)
                 recs += struct.pack("PPPPPq", p.data_ptr() + c0 * es, g.data_ptr() + c0 * es, mb + (off + c0) * 4,
@@ -76,6 +85,10 @@ class FusedAdam:
         for p in self.params:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
+            elif p.grad.stride() != p.stride():
+                g2 = torch.empty_like(p)          # the parameter's memory layout
+                g2.copy_(p.grad)
+                p.grad = g2
         self._build_table()
         self.step_count += 1
         _lib.call("ofa_adam_step", _p(self._table), self._n_chunks, _p(self._partial), _p(self.grad_norm), float(self.lr),

@@ -1,9 +1,10 @@
 """3-stage bottleneck ResNet patch embedder (models/ofa/resnet.py:86-225, frozen_bn.py:7-80), same parameter names.
 
-Round-1 status (DESIGN.md "ResNet stem"): BatchNorm (+ReLU, +residual add, running-stat update, frozen / eval mode) runs
-on this library's fused NHWC kernels (ops.batch_norm); the convolutions and the 3x3 max-pool still go through cuDNN /
-ATen library kernels (channels-last, model dtype) -- the implicit-GEMM tcgen05 convolution of SURVEY.md 8(a) row a3 is
-the next kernel to land.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
+BatchNorm (+ReLU, +residual add, running-stat update, frozen / eval mode) runs on this library's fused NHWC kernels
+(ops.batch_norm); every 1x1 convolution is a tcgen05 GEMM on the NHWC bytes (ops.conv1x1) and every stride-1 3x3
+convolution the implicit-GEMM kernel of csrc/conv.cu (ops.conv3x3), forward / dgrad / wgrad, in bf16.  Still on cuDNN / ATen
+library kernels: the 7x7 stem convolution, the two stride-2 3x3 convolutions, the 3x3 max-pool, and all convolutions of
+the fp32 parity mode.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -38,6 +39,15 @@ def _bn(mod, x, relu=False, residual=None):
 def _conv(mod, x):
     if mod.kernel_size == (1, 1) and mod.stride[0] == mod.stride[1]:
         return ops.conv1x1(x, mod.weight, mod.stride[0])          # tcgen05 GEMM on the NHWC bytes
+    if (mod.kernel_size == (3, 3) and mod.stride == (1, 1) and mod.padding == (1, 1) and x.dtype == torch.bfloat16
+            and mod.in_channels % 64 == 0 and mod.out_channels % 64 == 0):
+        w = mod.weight
+        if not w.is_contiguous(memory_format=torch.channels_last):     # once: [Cout][3][3][Cin] bytes, same shape / state dict
+            w.data = w.data.contiguous(memory_format=torch.channels_last)
+            if w.grad is not None:
+                w.grad = None
+        return ops.conv3x3(x, w)                                   # implicit-GEMM tcgen05 kernel (csrc/conv.cu)
+    # 7x7 stem, the two stride-2 3x3 convolutions and the fp32 parity mode: library convolution
     return F.conv2d(x, mod.weight, None, mod.stride, mod.padding)
 
 

@@ -394,3 +394,36 @@ def test_gemm_bf16_output_epilogues(M, N, K, act, tma_store):
     assert (out[:, :N].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
     if Np > N:      # row padding: untouched by the row-store epilogue, zero-filled by the TMA store (16-byte clipping)
         assert torch.all((out[:, N:] == 7.0) | (out[:, N:] == 0.0))
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 64, 64, 16, 16), (3, 128, 128, 8, 8), (2, 256, 256, 4, 4), (1, 64, 128, 13, 9),
+                                            (4, 256, 256, 24, 24)])
+def test_conv3x3_implicit_gemm(N, Cin, Cout, H, W):
+    """3x3 / stride 1 / pad 1 implicit-GEMM convolution (fprop, dgrad, wgrad with accumulation) vs F.conv2d in fp64 on the
+    same bf16 operands: partial spatial tiles (13 x 9, 4 x 4), odd image counts, Cout != Cin, all three tile widths."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(N * 100 + Cin + H)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).cuda().bfloat16()
+    w = w.contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = ops.conv3x3(x, w)
+    assert y.shape == (N, Cout, H, W) and y.is_contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(N, Cout, H, W, generator=g).cuda().bfloat16()
+    y.backward(dy)
+    xf, wf = x.detach().double().cpu().requires_grad_(), w.detach().double().cpu().requires_grad_()
+    yr = F.conv2d(xf, wf, None, 1, 1)
+    yr.backward(dy.double().cpu())
+    for got, ref, name in ((y, yr, "y"), (x.grad, xf.grad, "dx"), (w.grad, wf.grad, "dw")):
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert err < 2e-2 * max(1.0, ref.abs().max().item()), (name, err, ref.abs().max().item())
+    # gradient accumulation into an existing buffer (multi-task micro-step)
+    from musketeer_b200 import _lib
+    import ctypes as C
+    dw2 = w.grad.detach().clone(memory_format=torch.preserve_format)
+    wsb = _lib.load().ofa_conv3x3_wgrad_workspace_bytes(N, H, W, Cin, Cout)
+    ws = torch.empty(wsb // 4, dtype=torch.float32, device="cuda")
+    dyc = dy.contiguous(memory_format=torch.channels_last)
+    _lib.call("ofa_conv3x3_wgrad_bf16", C.c_void_p(x.data_ptr()), C.c_void_p(dyc.data_ptr()), C.c_void_p(dw2.data_ptr()), N, H, W,
+              Cin, Cout, 1, C.c_void_p(ws.data_ptr()), wsb, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    err = (dw2.double().cpu() - 2 * wf.grad).abs().max().item()
+    assert err < 3e-2 * max(1.0, 2 * wf.grad.abs().max().item()), err
