@@ -28,7 +28,7 @@ int ofa_set_error(const char* fmt, ...);
   } while (0)
 
 // dtype enum shared with include/ofa_b200.h
-enum { OFA_F32 = 0, OFA_BF16 = 1 };
+enum { OFA_F32 = 0, OFA_BF16 = 1, OFA_F32_ACC = 2 /* GEMM output only: D (fp32) += result */ };
 
 // host: encode a tiled tensor map (driver entry point resolved at runtime; no libcuda link dependency)
 int ofa_make_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -110,6 +110,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -372,7 +372,7 @@ void wgrad_plan(int NI, int H, int W, int Cin, int Cout, int* bn, int* splits, i
   *bn = Cin >= 256 ? 256 : (Cin >= 128 ? 128 : 64);
   const int tiles = 9 * ((Cout + BM - 1) / BM) * ((Cin + *bn - 1) / *bn);
   *kb_total = NI * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-  int s = (2 * kNumSMs + tiles - 1) / tiles;   // about two work items per SM
+  int s = (kNumSMs + tiles - 1) / tiles;       // about one work item per SM: the fp32 partials are the cost of a split
   if (s > *kb_total / 8) s = *kb_total / 8;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
@@ -392,8 +392,10 @@ extern "C" int ofa_conv3x3_bf16(const void* in, const void* weight, void* out, i
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.NI = NI; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dgrad = dgrad;
-  const int bn = c_out_act >= 256 ? 256 : (c_out_act >= 128 ? 128 : 64);
   p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_i = (NI + TN - 1) / TN;
+  // widest channel tile that still gives every SM a tile (small batches at 24 x 24 have only ~70 pixel tiles)
+  int bn = c_out_act >= 256 ? 256 : (c_out_act >= 128 ? 128 : 64);
+  while (bn > 64 && (long long)p.tiles_w * p.tiles_h * p.tiles_i * ((c_out_act + bn - 1) / bn) < kNumSMs) bn >>= 1;
   p.tiles_n = (c_out_act + bn - 1) / bn;
   p.total = p.tiles_w * p.tiles_h * p.tiles_i * p.tiles_n;
   CUtensorMap ta, tb, td;

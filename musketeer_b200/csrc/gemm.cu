@@ -39,6 +39,7 @@ struct GemmParams {
   int total;     // total work items
   float alpha;
   int act;  // 0 none, 1 gelu(erf)
+  int reduce_f32; // fp32 output ADDED into D by TMA reduce (gradient accumulation; K slices need no workspace)
   int tma_store;  // bf16 output staged through shared memory and written with TMA (needs 16B-aligned D rows)
 };
 
@@ -200,6 +201,38 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*s
   }
 }
 
+
+// fp32 accumulate epilogue of one 32-row slab: D[rows, 32-column group] += alpha * acc, by TMA reduce-add from a
+// 128B-swizzled [32][32] fp32 slab.  Used for weight gradients: every K slice and every task of a micro-step adds into
+// the same fp32 buffer, so split-K needs neither a partial workspace nor a reduce kernel.
+__device__ __forceinline__ void epilogue_reduce(const CUtensorMap* tmD, uint8_t (*stage)[4096], int& sbuf, uint32_t tmem_row,
+                                                int nch, int row0, int n0, int bz, const GemmParams& p, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    const int nb = n0 + c * 32;
+    if (nb >= p.N) break;
+    uint8_t* sb = stage[sbuf];
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint32_t r[32];
+    tmem_ld32(tmem_row + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      float4 v = make_float4(__uint_as_float(r[4 * q4]) * p.alpha, __uint_as_float(r[4 * q4 + 1]) * p.alpha,
+                             __uint_as_float(r[4 * q4 + 2]) * p.alpha, __uint_as_float(r[4 * q4 + 3]) * p.alpha);
+      *reinterpret_cast<float4*>(sb + lane * 128 + ((q4 ^ (lane & 7)) << 4)) = v;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_3d(tmD, sb, nb, row0, bz);
+      tma_store_commit();
+    }
+    sbuf ^= 1;
+  }
+}
+
 // PAIR = 1: launched as clusters of two CTAs that own vertically adjacent 128-row tiles of the same column tile.  The B
 // (weight) stage is shared: each CTA fetches half of it and TMA-multicasts it into both CTAs' shared memory, which halves
 // the L2 -> SM traffic of the B operand (the 128 x 256 single-CTA kernel saturates the ~12 TB/s L2 fabric at ~750
@@ -320,7 +353,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      if (sizeof(OutT) == 2 && p.tma_store) {
+      if (sizeof(OutT) == 4 && p.reduce_f32) {
+        if (m0 + q * 32 < p.M) epilogue_reduce(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, m0 + q * 32, n0, wk.bz, p, lane);
+      } else if (sizeof(OutT) == 2 && p.tma_store) {
         if (m0 + q * 32 < p.M) epilogue_tma(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, row, n0, wk.bz, p, lane);
       } else if (p.splits > 1) {
         float* W = p.ws + ((size_t)(wk.sp * p.batch + wk.bz) * p.M) * p.N;
@@ -541,7 +576,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const int nch = wk.bn / 32;
-      if (p.splits > 1) {
+      if (sizeof(OutT) == 4 && p.reduce_f32) {
+        if (row - lane < p.M) epilogue_reduce(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, row - lane, wk.n0, 0, p, lane);
+      } else if (p.splits > 1) {
         float* W = p.ws + (size_t)wk.sp * p.M * p.N;
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
@@ -651,7 +688,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
   cfg.numAttrs = 1;
   OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
   OFA_LAUNCH_CHECK("gemm_tc2_kernel");
-  if (p.splits > 1) {
+  if (p.splits > 1 && !p.reduce_f32) {
     const long long n = (long long)p.M * p.N;
     splitk_reduce_kernel<OutT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
     OFA_LAUNCH_CHECK("splitk_reduce_kernel");
@@ -688,7 +725,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, td, p);
   }
   OFA_LAUNCH_CHECK("gemm_tc_kernel");
-  if (p.splits > 1) {
+  if (p.splits > 1 && !p.reduce_f32) {
     const long long n = (long long)p.M * p.N * p.batch;
     splitk_reduce_kernel<OutT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
     OFA_LAUNCH_CHECK("splitk_reduce_kernel");
@@ -765,9 +802,17 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   OFA_CHECK(lda % 8 == 0 && ldb % 8 == 0, "ofa_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16B stride)");
   OFA_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "ofa_gemm_bf16: A/B must be 16B aligned");
   OFA_CHECK(stride_a % 8 == 0 && stride_b % 8 == 0, "ofa_gemm_bf16: batch strides must be multiples of 8 elements");
+  const int reduce_f32 = out_dtype == OFA_F32_ACC;
+  if (reduce_f32) {
+    OFA_CHECK(!bias && !resid && act == 0, "ofa_gemm_bf16: the fp32-accumulate output takes no bias / residual / activation");
+    OFA_CHECK(ldd % 4 == 0 && N % 4 == 0 && ((uintptr_t)D & 15) == 0 && stride_d % 4 == 0,
+              "ofa_gemm_bf16: fp32-accumulate output needs 16-byte aligned rows (N=%d ldd=%lld)", N, ldd);
+    out_dtype = OFA_F32;
+  }
   int bn, splits;
   plan(M, N, K, batch, &bn, &splits);
-  if (splits > 1 && (workspace == nullptr || workspace_bytes < (long long)splits * batch * M * N * (long long)sizeof(float)))
+  if (!reduce_f32 && splits > 1 &&
+      (workspace == nullptr || workspace_bytes < (long long)splits * batch * M * N * (long long)sizeof(float)))
     splits = 1;  // no workspace: run unsplit (still correct, just fewer CTAs)
   CUtensorMap ta, tb;
   {
@@ -803,7 +848,15 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     if (int e = ofa_make_tmap(&td, D, 3, dims, strides, box, 1, 2)) return e;
     tma_store = 1;
   }
+  if (reduce_f32) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch}, strides[2];
+    uint32_t box[3] = {32, 32, 1};
+    strides[0] = (uint64_t)ldd * 4;
+    strides[1] = (uint64_t)(batch > 1 ? stride_d : (long long)M * ldd) * 4;
+    if (int e = ofa_make_tmap(&td, D, 3, dims, strides, box, 1, 4)) return e;
+  }
   GemmParams p;
+  p.reduce_f32 = reduce_f32;
   p.tma_store = tma_store;
   p.D = D; p.bias = bias; p.resid = resid; p.ws = (float*)workspace; p.ldd = ldd; p.ldr = ldr;
   p.batch_stride_d = stride_d; p.batch_stride_r = stride_r;
@@ -815,7 +868,7 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   // cta_group::2 (mode 2): 256 x 256 pair tiles for plain problems with at least one full round of pair tiles, or split
   // along K when the output is small and the contraction long (weight gradients)
   int s2 = g_ofa_gemm_pair_enabled == 2 ? plan2_splits(M, N, K, batch) : 0;
-  if (s2 > 1 && (workspace == nullptr || workspace_bytes < (long long)s2 * M * N * (long long)sizeof(float))) s2 = 0;
+  if (!reduce_f32 && s2 > 1 && (workspace == nullptr || workspace_bytes < (long long)s2 * M * N * (long long)sizeof(float))) s2 = 0;
   if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && N >= 256 &&
       (s2 > 1 || (p.splits == 1 && (long long)((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2))) {
     p.tiles_m = (M + 255) / 256;

@@ -26,6 +26,31 @@ class _GradAccumulator:
         self.params = {id(p): p for p in model.parameters() if p.requires_grad}
         self.buf = {}
         self.written = set()
+        # weight gradients of the Linear / 1x1-conv GEMMs accumulate in fp32: every K slice, micro-batch and task adds into
+        # one arena by TMA reduce (ofa_gemm_bf16 out_dtype 2); `finish` casts the arena to the parameter dtype in one pass
+        self.arena32 = self.arena_out = None
+        self.region = {}           # id(param) -> (offset, numel)
+        self.arena_used = 0
+        self.written32 = set()
+
+    def target32(self, param):
+        """-> fp32 [N, K] accumulation view for a registered >= 2-D leaf parameter, else None."""
+        k = id(param)
+        if k not in self.params or param.dim() < 2 or not param.is_contiguous():
+            return None
+        if self.arena32 is None or self.arena32.device != param.device or self.arena_out.dtype != param.dtype:
+            total = sum(p.numel() for p in self.params.values() if p.dim() >= 2)
+            self.arena32 = torch.zeros(total, dtype=torch.float32, device=param.device)
+            self.arena_out = torch.empty(total, dtype=param.dtype, device=param.device)
+            self.region, self.arena_used = {}, 0
+        r = self.region.get(k)
+        if r is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("grad accumulation arena must be laid out by an eager warm-up step before graph capture")
+            r = self.region[k] = (self.arena_used, param.numel())
+            self.arena_used += (param.numel() + 63) // 64 * 64
+        self.written32.add(k)
+        return self.arena32[r[0]:r[0] + r[1]].view(param.shape[0], -1)
 
     def target(self, param):
         """-> (buffer, accumulate) for a registered leaf parameter, else (None, False)."""
@@ -39,11 +64,25 @@ class _GradAccumulator:
         self.written.add(k)
         return b, not first
 
+    def begin(self):
+        self.written, self.written32 = set(), set()
+        if self.arena32 is not None and self.arena_used:
+            self.arena32[:self.arena_used].zero_()
+
     def finish(self):
-        for k in self.written:
+        if self.written32:
+            self.arena_out[:self.arena_used].copy_(self.arena32[:self.arena_used])      # one cast for the whole model
+        for k in self.written32:
+            p = self.params[k]
+            off, n = self.region[k]
+            g = self.arena_out[off:off + n].view_as(p)
+            if k in self.written:            # e.g. the tied embedding: GEMM part + scatter-add part
+                g.add_(self.buf[k])
+            p.grad = g if p.grad is None else p.grad + g
+        for k in self.written - self.written32:
             p, b = self.params[k], self.buf[k]
             p.grad = b if p.grad is None else p.grad + b
-        self.written = set()
+        self.written, self.written32 = set(), set()
 
 
 _ACC = None
@@ -59,7 +98,7 @@ class grad_accumulation:
     def __enter__(self):
         global _ACC
         self.prev, _ACC = _ACC, self.acc
-        self.acc.written = set()
+        self.acc.begin()
         return self.acc
 
     def __exit__(self, et, ev, tb):
@@ -74,6 +113,12 @@ def _acc_target(param):
     if _ACC is None or param is None:
         return None, False
     return _ACC.target(param)
+
+
+def _acc_target32(param):
+    if _ACC is None or param is None:
+        return None
+    return _ACC.target32(param)
 
 
 def _dt(t):
@@ -120,7 +165,7 @@ def _split3(x2d, rows, cols, k_is_cols, pattern):
 
 
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, alpha=1.0, act=0, resid=None,
-         ldd=None):
+         ldd=None, acc32=False):
     """D[M,N] = act((A.B^T + bias) * alpha) + resid.   A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn);
     2-D tensors with unit inner stride.  fp32 operands take the split path."""
     _need_cuda(A)
@@ -138,11 +183,14 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
     else:
         lda, ldb = A.stride(0), B.stride(0)
     od = F32 if out_dtype == torch.float32 else BF16
+    if acc32:                   # out (fp32) += alpha * A.B^T   (TMA reduce-add; K slices need no workspace)
+        assert out is not None and out.dtype == torch.float32 and bias is None and resid is None and act == 0
+        od = 2
     if bias is not None:
         assert bias.dtype == out_dtype
     if resid is not None:
         assert resid.dtype == out_dtype and resid.stride(-1) == 1
-    wsb = _lib.load().ofa_gemm_workspace_bytes(M, N, Kk, 1)
+    wsb = 0 if acc32 else _lib.load().ofa_gemm_workspace_bytes(M, N, Kk, 1)
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=A.device) if wsb > 0 else None
     call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
          _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _p(ws), wsb, _st(),
@@ -183,8 +231,11 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
         if ctx.needs_input_grad[1]:
-            tgt, accum = _acc_target(ctx.w_param)
-            if tgt is not None:
+            tgt32 = _acc_target32(ctx.w_param) if K % 4 == 0 else None
+            tgt, accum = (None, False) if tgt32 is not None else _acc_target(ctx.w_param)
+            if tgt32 is not None:
+                gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt32, out_dtype=torch.float32, acc32=True)
+            elif tgt is not None:
                 tgt = tgt.view(N, K)
                 gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt, out_dtype=w.dtype,
                      resid=tgt if accum else None)
