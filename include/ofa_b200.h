@@ -81,7 +81,8 @@ int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* 
  * stride-1 bottlenecks).  bf16 NHWC activations [N][H][W][C]; weight bytes [Cout][3][3][Cin] (a channels_last
  * [Cout,Cin,3,3] tensor); Cin, Cout multiples of 64.  dgrad = 0: in = x (Cin channels) -> out = y (Cout channels);
  * dgrad = 1: in = dy (Cout channels) -> out = dx (Cin channels).  The weight gradient is split along the pixel axis
- * into an fp32 workspace and reduced; accumulate = 1 adds into dw (gradient accumulation across micro-batches).       */
+ * into an fp32 workspace and reduced; accumulate = 1 adds into dw (gradient accumulation across micro-batches);
+ * accumulate = 2: dw is an fp32 [Cout][3][3][Cin] buffer that every tile is reduce-added into (no workspace).       */
 int ofa_conv3x3_bf16(const void* in, const void* weight, void* out, int NI, int H, int W, int Cin, int Cout, int dgrad,
                      void* stream);
 long long ofa_conv3x3_wgrad_workspace_bytes(int NI, int H, int W, int Cin, int Cout);

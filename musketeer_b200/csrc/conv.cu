@@ -30,6 +30,7 @@ struct ConvParams {
   // wgrad
   float* ws;
   int kb_total, kb_per_split, splits, tiles_m;
+  int reduce_f32;          // wgrad: add the tile into an fp32 [Cout][9][Cin] buffer by TMA reduce instead of writing partials
 };
 
 template <int BN>
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
 // blocks of one image.  tmDY / tmX: {C, W, H, N} box {64, 8, 8, 1}.  Partials: ws[split][9][Cout][Cin] fp32.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
-                                                                    const __grid_constant__ CUtensorMap tmX, ConvParams p) {
+                                                                    const __grid_constant__ CUtensorMap tmX,
+                                                                    const __grid_constant__ CUtensorMap tmDW, ConvParams p) {
   using S = Smem<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_wgrad_kernel(const __grid
     __syncwarp();
   } else {
     const int q = warp & 3;
-    int it = 0;
+    int it = 0, sbuf = 0;
     for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
       int tap, m0, n0, sp;
       dec(w, tap, m0, n0, sp);
@@ -292,6 +294,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_wgrad_kernel(const __grid
       mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      if (p.reduce_f32) {
+        if (m0 + q * 32 < p.Cout) {
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            if (n0 + c * 32 >= p.Cin) break;
+            uint8_t* sb = sm.stage_out[q][sbuf];
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            uint32_t r[32];
+            tmem_ld32(tmem_row + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4)
+              *reinterpret_cast<uint4*>(sb + lane * 128 + ((q4 ^ (lane & 7)) << 4)) =
+                  make_uint4(r[4 * q4], r[4 * q4 + 1], r[4 * q4 + 2], r[4 * q4 + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_3d(&tmDW, sb, n0 + c * 32, tap, m0 + q * 32);
+              tma_store_commit();
+            }
+            sbuf ^= 1;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
+        continue;
+      }
       float* W = p.ws + (((size_t)sp * 9 + tap) * p.Cout + (row < p.Cout ? row : 0)) * p.Cin + n0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -310,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_wgrad_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.tmem_empty[acc]);
     }
+    if (lane == 0) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -355,7 +387,7 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 }
 
 template <int BN>
-int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const ConvParams& p, cudaStream_t st) {
+int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& tdw, const ConvParams& p, cudaStream_t st) {
   auto kern = conv3x3_wgrad_kernel<BN>;
   static bool configured = false;
   const int smem = (int)sizeof(Smem<BN>) + 1024;
@@ -363,16 +395,17 @@ int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const ConvParams
     OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<p.total < kNumSMs ? p.total : kNumSMs, kThreads, smem, st>>>(tdy, tx, p);
+  kern<<<p.total < kNumSMs ? p.total : kNumSMs, kThreads, smem, st>>>(tdy, tx, tdw, p);
   OFA_LAUNCH_CHECK("conv3x3_wgrad_kernel");
   return 0;
 }
 
-void wgrad_plan(int NI, int H, int W, int Cin, int Cout, int* bn, int* splits, int* kb_total) {
+void wgrad_plan(int NI, int H, int W, int Cin, int Cout, int* bn, int* splits, int* kb_total, int reduce = 0) {
   *bn = Cin >= 256 ? 256 : (Cin >= 128 ? 128 : 64);
   const int tiles = 9 * ((Cout + BM - 1) / BM) * ((Cin + *bn - 1) / *bn);
   *kb_total = NI * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-  int s = (kNumSMs + tiles - 1) / tiles;       // about one work item per SM: the fp32 partials are the cost of a split
+  // fp32 partials are the cost of a split: about one work item per SM; two when the tiles are reduce-added in place
+  int s = ((reduce ? 2 : 1) * kNumSMs + tiles - 1) / tiles;
   if (s > *kb_total / 8) s = *kb_total / 8;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
@@ -393,9 +426,7 @@ extern "C" int ofa_conv3x3_bf16(const void* in, const void* weight, void* out, i
   memset(&p, 0, sizeof(p));
   p.NI = NI; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dgrad = dgrad;
   p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH; p.tiles_i = (NI + TN - 1) / TN;
-  // widest channel tile that still gives every SM a tile (small batches at 24 x 24 have only ~70 pixel tiles)
-  int bn = c_out_act >= 256 ? 256 : (c_out_act >= 128 ? 128 : 64);
-  while (bn > 64 && (long long)p.tiles_w * p.tiles_h * p.tiles_i * ((c_out_act + bn - 1) / bn) < kNumSMs) bn >>= 1;
+  const int bn = c_out_act >= 256 ? 256 : (c_out_act >= 128 ? 128 : 64);   // measured: wider beats more, narrower tiles
   p.tiles_n = (c_out_act + bn - 1) / bn;
   p.total = p.tiles_w * p.tiles_h * p.tiles_i * p.tiles_n;
   CUtensorMap ta, tb, td;
@@ -432,10 +463,12 @@ extern "C" int ofa_conv3x3_wgrad_bf16(const void* x, const void* dy, void* dw, i
   memset(&p, 0, sizeof(p));
   p.NI = NI; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   int bn, splits, kbt;
-  wgrad_plan(NI, H, W, Cin, Cout, &bn, &splits, &kbt);
-  OFA_CHECK(workspace && workspace_bytes >= (long long)splits * 9 * Cout * Cin * (long long)sizeof(float),
+  const int reduce = accumulate == 2;   // dw is an fp32 [Cout][9][Cin] accumulation buffer
+  wgrad_plan(NI, H, W, Cin, Cout, &bn, &splits, &kbt, reduce);
+  OFA_CHECK(reduce || (workspace && workspace_bytes >= (long long)splits * 9 * Cout * Cin * (long long)sizeof(float)),
             "ofa_conv3x3_wgrad_bf16: workspace too small (see ofa_conv3x3_wgrad_workspace_bytes)");
   p.ws = (float*)workspace;
+  p.reduce_f32 = reduce;
   p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + TH - 1) / TH;
   p.kb_total = kbt;
   p.kb_per_split = (kbt + splits - 1) / splits;
@@ -443,15 +476,22 @@ extern "C" int ofa_conv3x3_wgrad_bf16(const void* x, const void* dy, void* dw, i
   p.tiles_m = (Cout + BM - 1) / BM;
   p.tiles_n = (Cin + bn - 1) / bn;
   p.total = 9 * p.tiles_m * p.tiles_n * p.splits;
-  CUtensorMap tdy, tx;
+  CUtensorMap tdy, tx, tdw;
+  memset(&tdw, 0, sizeof(tdw));
+  if (reduce) {
+    uint64_t dims[3] = {(uint64_t)Cin, 9, (uint64_t)Cout};
+    uint64_t strides[2] = {(uint64_t)Cin * 4, (uint64_t)9 * Cin * 4};
+    uint32_t box[3] = {32, 1, 32};
+    if (int e = ofa_make_tmap(&tdw, dw, 3, dims, strides, box, 1, 4)) return e;
+  }
   if (int e = act_tmap(&tdy, dy, Cout, W, H, NI, TW, TH, 1)) return e;
   if (int e = act_tmap(&tx, x, Cin, W, H, NI, TW, TH, 1)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (bn == 256) rc = launch_wgrad<256>(tdy, tx, p, st);
-  else if (bn == 128) rc = launch_wgrad<128>(tdy, tx, p, st);
-  else rc = launch_wgrad<64>(tdy, tx, p, st);
-  if (rc) return rc;
+  if (bn == 256) rc = launch_wgrad<256>(tdy, tx, tdw, p, st);
+  else if (bn == 128) rc = launch_wgrad<128>(tdy, tx, tdw, p, st);
+  else rc = launch_wgrad<64>(tdy, tx, tdw, p, st);
+  if (rc || reduce) return rc;
   const long long n = 9LL * Cout * Cin;
   conv_wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, (__nv_bfloat16*)dw, p.splits, Cout, Cin, accumulate);
   OFA_LAUNCH_CHECK("conv_wgrad_reduce_kernel");

@@ -36,7 +36,8 @@ class _GradAccumulator:
     def target32(self, param):
         """-> fp32 [N, K] accumulation view for a registered >= 2-D leaf parameter, else None."""
         k = id(param)
-        if k not in self.params or param.dim() < 2 or not param.is_contiguous():
+        dense = param.is_contiguous() or (param.dim() == 4 and param.is_contiguous(memory_format=torch.channels_last))
+        if k not in self.params or param.dim() < 2 or not dense:
             return None
         if self.arena32 is None or self.arena32.device != param.device or self.arena_out.dtype != param.dtype:
             total = sum(p.numel() for p in self.params.values() if p.dim() >= 2)
@@ -50,7 +51,7 @@ class _GradAccumulator:
             r = self.region[k] = (self.arena_used, param.numel())
             self.arena_used += (param.numel() + 63) // 64 * 64
         self.written32.add(k)
-        return self.arena32[r[0]:r[0] + r[1]].view(param.shape[0], -1)
+        return self.arena32[r[0]:r[0] + r[1]].view(param.shape[0], -1)      # storage order of the parameter
 
     def target(self, param):
         """-> (buffer, accumulate) for a registered leaf parameter, else (None, False)."""
@@ -75,7 +76,7 @@ class _GradAccumulator:
         for k in self.written32:
             p = self.params[k]
             off, n = self.region[k]
-            g = self.arena_out[off:off + n].view_as(p)
+            g = self.arena_out[off:off + n].as_strided(p.shape, p.stride())
             if k in self.written:            # e.g. the tied embedding: GEMM part + scatter-add part
                 g.add_(self.buf[k])
             p.grad = g if p.grad is None else p.grad + g
@@ -301,7 +302,13 @@ class _Conv3x3(torch.autograd.Function):
             call("ofa_conv3x3_bf16", _p(dy), _p(wc), _p(dx), N, H, W, Cin, Cout, 1, _st(),
                  work=("flop", 2.0 * N * H * W * Cout * Cin * 9))
         if ctx.needs_input_grad[1]:
-            tgt, accum = _acc_target(ctx.w_param)
+            w = ctx.w_param
+            tgt32 = _acc_target32(w) if w.is_contiguous(memory_format=torch.channels_last) else None
+            if tgt32 is not None:       # fp32 arena region in the weight's storage order [Cout][3][3][Cin]
+                call("ofa_conv3x3_wgrad_bf16", _p(x), _p(dy), _p(tgt32), N, H, W, Cin, Cout, 2, _p(None), 0, _st(),
+                     work=("flop", 2.0 * N * H * W * Cout * Cin * 9))
+                return dx, None
+            tgt, accum = _acc_target(w)
             if tgt is not None and not tgt.is_contiguous(memory_format=torch.channels_last):
                 tgt = None
             out = tgt if tgt is not None else torch.empty_like(wc, memory_format=torch.channels_last)

@@ -427,3 +427,10 @@ def test_conv3x3_implicit_gemm(N, Cin, Cout, H, W):
               Cin, Cout, 1, C.c_void_p(ws.data_ptr()), wsb, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     err = (dw2.double().cpu() - 2 * wf.grad).abs().max().item()
     assert err < 3e-2 * max(1.0, 2 * wf.grad.abs().max().item()), err
+    # fp32 accumulation buffer in weight storage order [Cout][3][3][Cin], tiles reduce-added in place (two calls)
+    acc = torch.zeros(Cout, 3, 3, Cin, dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        _lib.call("ofa_conv3x3_wgrad_bf16", C.c_void_p(x.data_ptr()), C.c_void_p(dyc.data_ptr()), C.c_void_p(acc.data_ptr()), N, H,
+                  W, Cin, Cout, 2, C.c_void_p(0), 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    err = (acc.permute(0, 3, 1, 2).double().cpu() - 2 * wf.grad).abs().max().item()
+    assert err < 1e-3 * max(1.0, 2 * wf.grad.abs().max().item()), err

@@ -215,22 +215,24 @@ def test_training_with_dropout_and_droppath_runs():
     assert abs(float(loss2.detach()) - float(loss.detach())) < 0.05 * abs(float(loss.detach()))   # same seed, BN stats moved
 
 
-def test_fused_grad_accumulation_matches_autograd():
-    """ops.grad_accumulation (producer kernels accumulate into one buffer per parameter) == plain autograd accumulation
-    on a three-task micro-step, fp32, to rounding."""
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_grad_accumulation_matches_autograd(dtype):
+    """ops.grad_accumulation (producer kernels accumulate into one buffer per parameter; GEMM / conv weight gradients into
+    the fp32 arena by TMA reduce) == plain autograd accumulation on a three-task micro-step: to rounding in fp32; in bf16
+    (the mode that runs the implicit-GEMM convolutions) to the bf16 rounding of the per-task partial gradients."""
     from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion, ops
     fx = load_golden("micro_multitask_rdrop")
     case = fx["case"]
     cfg, sd, samples = build_case(case)
     grads = []
     for fused in (False, True):
-        model, task = build_product(cfg, sd, dtype=torch.float32)
+        model, task = build_product(cfg, sd, dtype=dtype)
         model.train()
         # batch statistics are summed with fp32 atomics (order varies in the last bit between runs, and ReLU masks next to
         # zero amplify that through the stem): the two runs compare on running statistics, which are order-independent
         model.encoder.embed_images.eval()
         crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0)
-        inp = to_device(copy.deepcopy(samples), "cuda")
+        inp = to_device(copy.deepcopy(samples), "cuda", dtype)
         if fused:
             with ops.grad_accumulation(model):
                 loss, ss, _ = crit(model, inp)
@@ -243,4 +245,5 @@ def test_fused_grad_accumulation_matches_autograd():
         a, b = grads[0][n], grads[1][n]
         assert (a is None) == (b is None), n
         if a is not None:
-            assert (a - b).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item()), n
+            tol = 1e-5 if dtype == torch.float32 else 3e-2
+            assert (a.float() - b.float()).abs().max().item() <= tol * max(1.0, a.float().abs().max().item()), n
