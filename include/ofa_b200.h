@@ -89,6 +89,26 @@ long long ofa_conv3x3_wgrad_workspace_bytes(int NI, int H, int W, int Cin, int C
 int ofa_conv3x3_wgrad_bf16(const void* x, const void* dy, void* dw, int NI, int H, int W, int Cin, int Cout,
                            int accumulate, void* workspace, long long workspace_bytes, void* stream);
 
+/* ---- incremental decoding for beam search (models/sequence_generator.py:209-598; decoder layers with
+ * incremental_state, unify_transformer_layer.py:432-582; cache reorder unify_multihead_attention.py:458-480).
+ * ofa_attn_decode: one query token per row; G consecutive rows (the beams of a sentence) share cache row kv_row[group], so
+ * cross-attention K / V / pos_k live once per sentence.  scores = q.k + pos_q.pos_k (+ tok_lut[h][(q_pos - j) + tok_max - 1]),
+ * key padding kpm, fp32 softmax, out = P V * head_scale.  ofa_cache_gather: dst[p][r][:L] = src[p][order[r]][:L] over all
+ * (layer, k|v) planes p in one launch (beam reorder of the self-attention cache; only the L valid positions move).     */
+typedef struct OfaDecodeArgs {
+  const void* q; const void* pq; long long ldq, ldpq;
+  const void* k; const void* v; const void* pk;
+  long long ldk, bsk, ldv, bsv, ldpk, bspk;      /* element (row, j, h*64+d) at row*bs + j*ld + h*64 + d */
+  const int* kv_row; const int* pk_row;          /* [ceil(R/G)] cache rows (NULL: group index / kv_row) */
+  const unsigned char* kpm; long long kpm_stride;
+  void* o; long long ldo;
+  const float* head_scale; const float* tok_lut; int tok_max; int q_pos;
+  int R, G, H, S;
+} OfaDecodeArgs;
+int ofa_attn_decode(const OfaDecodeArgs* args, int dtype, void* stream);
+int ofa_cache_gather(const void* src, void* dst, const long long* order, int rows, int L, int D, long long row_stride,
+                     long long plane_stride, int planes, int dtype, void* stream);
+
 /* ---- fused optimizer step (trainer.py:863-898 multiply_grads -> clip_grad_norm -> optimizer.step,
  * with the un-vendored fairseq Adam / FP16Optimizer arithmetic: fp32 master weights, decoupled weight decay
  * p -= wd*lr*p, bias-corrected step size, global-norm clipping with coefficient clip/(norm+1e-6)).

@@ -32,6 +32,15 @@ class OfaAttnGrads(C.Structure):
                 ("dtok_lut", c_p), ("dimg_lut", c_p), ("delta", c_p), ("P", c_p), ("dS", c_p)]
 
 
+class OfaDecodeArgs(C.Structure):
+    _fields_ = [("q", c_p), ("pq", c_p), ("ldq", c_ll), ("ldpq", c_ll),
+                ("k", c_p), ("v", c_p), ("pk", c_p),
+                ("ldk", c_ll), ("bsk", c_ll), ("ldv", c_ll), ("bsv", c_ll), ("ldpk", c_ll), ("bspk", c_ll),
+                ("kv_row", c_p), ("pk_row", c_p), ("kpm", c_p), ("kpm_stride", c_ll),
+                ("o", c_p), ("ldo", c_ll), ("head_scale", c_p), ("tok_lut", c_p), ("tok_max", c_i), ("q_pos", c_i),
+                ("R", c_i), ("G", c_i), ("H", c_i), ("S", c_i)]
+
+
 # name -> argtypes, exactly the prototypes of include/ofa_b200.h
 SIGNATURES = {
     "ofa_abi_version": [],
@@ -59,6 +68,8 @@ SIGNATURES = {
     "ofa_conv3x3_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "ofa_conv3x3_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
     "ofa_conv3x3_wgrad_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p],
+    "ofa_attn_decode": [C.POINTER(OfaDecodeArgs), c_i, c_p],
+    "ofa_cache_gather": [c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_ll, c_i, c_i, c_p],
     "ofa_adam_step": [c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_p],
     "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p],
     "ofa_attn_fwd_simt": [C.POINTER(OfaAttnArgs), c_i, c_p],

@@ -124,6 +124,10 @@ class MultiheadAttention(nn.Module):
 
     def forward(self, query, k, v, pq, pk, tok_lut, img_lut, cfg):
         q = _lin(self.q_proj, query, alpha=self.scaling)
+        dec = cfg.get("decode")
+        if dec is not None:        # incremental decoding: one token per row against the KV cache (csrc/decode.cu)
+            return ops.attention_decode(q, pq, k, pk, v, dec["S"], self.num_heads, dec.get("G", 1), dec.get("kv_row"),
+                                        dec.get("pk_row"), dec.get("kpm"), self.c_attn, tok_lut, dec.get("q_pos", 0))
         cfg = dict(cfg)
         cfg["H"] = self.num_heads
         return ops.attention(q, pq, k, pk, v, tok_lut, img_lut, self.c_attn, cfg)
@@ -481,25 +485,54 @@ class TransformerDecoder(nn.Module):
             x = _ln(self.layernorm_embedding, x)
         x = ops.dropout_residual(x, None, self.dropout_p, 0.0, self.training)                  # :1495
         if incremental:
+            # KV cache of the incremental decoder.  Cross-attention K / V / pos_k are projected ONCE per SENTENCE: when the
+            # caller hands over the un-replicated encoder output (our SequenceGenerator), the G = rows / sentences beams of a
+            # sentence read the same cache row through `sent_row`; a caller that replicated encoder_out per beam (the
+            # reference generator) simply gets G = 1.  Self-attention K / V live in one preallocated ping-pong buffer
+            # [2][2*layers, rows, cap, d]; a beam reorder gathers only the valid prefix (reorder_incremental_state_scripting).
             st = incremental_state.setdefault("_ofa_b200", {})
-            if "cpk" not in st:       # first step: project the encoder side once (static_kv, :207-209,275-276)
+            if "cpk" not in st:
+                EB = enc.shape[0]
+                if B % EB != 0:
+                    raise ValueError("decoder rows (%d) must be a multiple of the encoder batch (%d)" % (B, EB))
+                st["G"] = B // EB
+                if st["G"] > 8:
+                    raise NotImplementedError("more than 8 beams per sentence share a cache row group")
+                st["sent_row"] = torch.arange(EB, device=dev, dtype=torch.int32)
                 st["cpk"] = _lin(self.cross_pos_k_linear, src_pos.contiguous())
                 st["cross"] = [layer.encoder_attn.project_kv(enc) for layer in self.layers]
-                st["self_k"] = [None] * self.num_layers
-                st["self_v"] = [None] * self.num_layers
-                st["spk"] = None
-            cpk = st["cpk"]
-            st["spk"] = spk_new if st["spk"] is None else torch.cat([st["spk"], spk_new], dim=1)
-            spk = st["spk"]
-            self_kpm = None
+                st["enc_pad"] = enc_pad.contiguous().view(torch.uint8)
+                st["cap"] = 32
+                st["kv"] = torch.zeros(2, 2 * self.num_layers, B, st["cap"], d, dtype=x.dtype, device=dev)
+                st["spk"] = torch.zeros(1, st["cap"], d, dtype=x.dtype, device=dev)
+                st["cur"], st["len"], st["rows"] = 0, 0, B
+                st["zero_row"] = torch.zeros(B, dtype=torch.int32, device=dev)
+            if t0 != st["len"]:
+                raise ValueError("incremental decoding expects one new token per call (cache holds %d, got position %d)"
+                                 % (st["len"], t0))
+            if t0 + 1 > st["cap"]:          # grow the caches (doubling)
+                cap = st["cap"] * 2
+                kv = torch.zeros(2, 2 * self.num_layers, st["kv"].shape[2], cap, d, dtype=x.dtype, device=dev)
+                kv[:, :, :, :st["cap"]] = st["kv"]
+                spk_new_buf = torch.zeros(1, cap, d, dtype=x.dtype, device=dev)
+                spk_new_buf[:, :st["cap"]] = st["spk"]
+                st["kv"], st["spk"], st["cap"] = kv, spk_new_buf, cap
+            st["spk"][0, t0] = spk_new[0, 0]            # pos_k depends on the position only: one shared row
+            cache = st["kv"][st["cur"]]
+            R = B
+            self_dec = {"S": t0 + 1, "G": 1, "pk_row": st["zero_row"][:R], "q_pos": t0}
+            cross_dec = {"S": enc.shape[1], "G": st["G"], "kv_row": st["sent_row"], "kpm": st["enc_pad"]}
+            self_cfg = {"decode": self_dec}
+            cross_cfg = {"decode": cross_dec}
+            cpk, spk = st["cpk"], st["spk"]
         else:
             cpk = _lin(self.cross_pos_k_linear, src_pos.contiguous())
             spk = spk_new
             self_kpm = prev_output_tokens.eq(self.padding_idx).contiguous().view(torch.uint8)
+            self_cfg = {"causal": True, "kpm": self_kpm, "q_pos_off": t0,
+                        "bias": {"q_text_off": 0, "k_text_off": 0}}
+            cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}}
         rel1d = self.rel_bucket_1d()
-        self_cfg = {"causal": True, "kpm": self_kpm, "q_pos_off": t0,
-                    "bias": {"q_text_off": 0, "k_text_off": 0}}
-        cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}}
         inner_states = [x.transpose(0, 1)]
         for i, layer in enumerate(self.layers):
             tok_lut = _tok_lut(self.token_rel_pos_table_list[i].weight, rel1d)
@@ -508,9 +541,10 @@ class TransformerDecoder(nn.Module):
                 k, v = attn.project_kv(h)
                 if incremental:
                     st = incremental_state["_ofa_b200"]
-                    st["self_k"][i] = k if st["self_k"][i] is None else torch.cat([st["self_k"][i], k], dim=1)
-                    st["self_v"][i] = v if st["self_v"][i] is None else torch.cat([st["self_v"][i], v], dim=1)
-                    return st["self_k"][i], st["self_v"][i]
+                    cache = st["kv"][st["cur"]]
+                    cache[2 * i, :B, t0] = k[:, 0]
+                    cache[2 * i + 1, :B, t0] = v[:, 0]
+                    return cache[2 * i], cache[2 * i + 1]
                 return k, v
 
             def cross_kv(attn, i=i):
@@ -520,6 +554,8 @@ class TransformerDecoder(nn.Module):
 
             x = layer(x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg)
             inner_states.append(x.transpose(0, 1))
+        if incremental:
+            incremental_state["_ofa_b200"]["len"] = t0 + 1
         x = _ln(self.layer_norm, x)
         return x, {"attn": [None], "inner_states": inner_states}
 
@@ -529,18 +565,19 @@ class TransformerDecoder(nn.Module):
         return ops.linear(features, self.output_projection.weight, None, 1.0, None, padded)
 
     def reorder_incremental_state_scripting(self, incremental_state, new_order):
+        """Beam reorder (models/sequence_generator.py:339-349): the self-attention cache is gathered row-wise over its valid
+        prefix into the other half of the ping-pong buffer (one launch for all layers); the per-sentence cross-attention
+        cache is never moved -- only the group -> sentence map follows the surviving sentences."""
         st = incremental_state.get("_ofa_b200")
         if not st:
             return
-        for i in range(self.num_layers):
-            if st["self_k"][i] is not None:
-                st["self_k"][i] = st["self_k"][i].index_select(0, new_order)
-                st["self_v"][i] = st["self_v"][i].index_select(0, new_order)
-        if st["spk"] is not None:
-            st["spk"] = st["spk"].index_select(0, new_order)
-        if st["cpk"].size(0) == new_order.size(0):
-            st["cpk"] = st["cpk"].index_select(0, new_order)
-            st["cross"] = [(k.index_select(0, new_order), v.index_select(0, new_order)) for k, v in st["cross"]]
+        rows = int(new_order.numel())
+        G = st["G"]
+        if st["len"] > 0:
+            ops.cache_gather(st["kv"][st["cur"]], st["kv"][1 - st["cur"]], new_order.contiguous(), rows, st["len"])
+            st["cur"] = 1 - st["cur"]
+        st["sent_row"] = st["sent_row"].index_select(0, torch.div(new_order[::G], G, rounding_mode="floor"))
+        st["rows"] = rows
 
     def get_normalized_probs(self, net_output, log_probs, sample=None):
         logits = net_output[0]

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import OfaAttnArgs, OfaAttnBias, OfaAttnGrads, call
+from ._lib import OfaAttnArgs, OfaAttnBias, OfaAttnGrads, OfaDecodeArgs, call
 
 F32, BF16 = 0, 1
 
@@ -669,6 +669,41 @@ def attention(q, pq, k, pk, v, tok_lut, img_lut, head_scale, cfg):
     """softmax(q k^T + pq pk^T + rel-pos LUT bias + masks) v * c_attn.   q/pq/k/pk/v: [B, L, H*64] (unit inner
     stride); tok_lut [H, 2047] / img_lut [H, n_rel] fp32 (differentiable); cfg: H, causal, kpm, q_pos_off, bias{...}."""
     return _Attention.apply(q, pq, k, pk, v, tok_lut, img_lut, head_scale, cfg)
+
+
+def attention_decode(q, pq, k, pk, v, S, H, G=1, kv_row=None, pk_row=None, kpm=None, head_scale=None, tok_lut=None,
+                     q_pos=0):
+    """Single-token attention over a KV cache (inference only; csrc/decode.cu).  q, pq: [R, 1, H*64] (pre-scaled);
+    k, v: caches [rows, cap, H*64] of which the first S positions are valid; pk likewise; G consecutive query rows share
+    cache row kv_row[group] (int32).  Returns [R, 1, H*64]."""
+    _need_cuda(q)
+    R, D = q.shape[0], q.shape[-1]
+    q2, pq2 = q.reshape(R, D), pq.reshape(R, D)
+    o = torch.empty(R, D, dtype=q.dtype, device=q.device)
+    a = OfaDecodeArgs()
+    a.q, a.pq, a.ldq, a.ldpq = q2.data_ptr(), pq2.data_ptr(), q2.stride(0), pq2.stride(0)
+    a.k, a.v, a.pk = k.data_ptr(), v.data_ptr(), pk.data_ptr()
+    a.ldk, a.bsk, a.ldv, a.bsv, a.ldpk, a.bspk = k.stride(1), k.stride(0), v.stride(1), v.stride(0), pk.stride(1), pk.stride(0)
+    a.kv_row = kv_row.data_ptr() if kv_row is not None else None
+    a.pk_row = pk_row.data_ptr() if pk_row is not None else None
+    a.kpm = kpm.data_ptr() if kpm is not None else None
+    a.kpm_stride = kpm.stride(0) if kpm is not None else 0
+    a.o, a.ldo = o.data_ptr(), D
+    hs = head_scale.float().contiguous() if head_scale is not None else None
+    a.head_scale = hs.data_ptr() if hs is not None else None
+    a.tok_lut = tok_lut.data_ptr() if tok_lut is not None else None
+    a.tok_max, a.q_pos = 1024, int(q_pos)
+    a.R, a.G, a.H, a.S = R, int(G), int(H), int(S)
+    call("ofa_attn_decode", C.byref(a), _dt(q), _st(),
+         work=("byte", (R // max(G, 1)) * S * D * 3.0 * q.element_size()))
+    return o.view(R, 1, D)
+
+
+def cache_gather(src, dst, order, rows, L):
+    """dst[p, r, :L] = src[p, order[r], :L] for caches [planes, cap_rows, cap_len, D] (beam reorder, valid prefix only)."""
+    planes, cap_rows, cap_len, D = src.shape
+    call("ofa_cache_gather", _p(src), _p(dst), _p(order), int(rows), int(L), D, cap_len * D, cap_rows * cap_len * D, planes,
+         _dt(src), _st())
 
 
 # ---------------------------------------------------------------------------------------------------------------------

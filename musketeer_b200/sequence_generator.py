@@ -75,9 +75,9 @@ class SequenceGenerator(torch.nn.Module):
         beam, V = self.beam_size, self.vocab_size
         max_len = int(self.max_len_a * src_len + self.max_len_b)
         assert self.min_len <= max_len, "min_len cannot be larger than max_len, please adjust these!"
+        # The encoder output is NOT replicated per beam (the reference does: sequence_generator.py:262-266): the decoder keeps
+        # the cross-attention K / V once per sentence and maps beam rows onto them (ofa.py incremental path)
         enc = model.encoder.forward_torchscript(net_input)
-        order = torch.arange(bsz, device=dev).view(-1, 1).repeat(1, beam).view(-1)
-        enc = model.encoder.reorder_encoder_out(enc, order)
         scores = torch.zeros(bsz * beam, max_len + 1, device=dev)
         tokens = torch.full((bsz * beam, max_len + 2), self.pad, dtype=torch.long, device=dev)
         tokens[:, 0] = self.bos
@@ -96,7 +96,6 @@ class SequenceGenerator(torch.nn.Module):
                     corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
                     reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
                 model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
-                enc = model.encoder.reorder_encoder_out(enc, reorder_state)
             logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
             logits = logits[:, -1, :].float() / self.temperature
             if self.constraint_start is not None:

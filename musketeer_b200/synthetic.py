@@ -99,7 +99,7 @@ def build_model(arch="ofa_base", device="cuda", dtype=torch.bfloat16, seed=0, vo
                            disable_entangle=True, layernorm_embedding=True, patch_layernorm_embedding=True,
                            code_layernorm_embedding=True, share_all_embeddings=True, encoder_normalize_before=True,
                            decoder_normalize_before=True, dropout=0.0, attention_dropout=0.0,
-                           patch_image_size=384, **over)
+                           **dict({"patch_image_size": 384}, **over))
     ARCHS[arch](args)
     torch.manual_seed(seed)
     task = Task(vocab)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--img", type=int, default=480)
     ap.add_argument("--beam", type=int, default=5)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--profile", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     model, task = build_model("ofa_base", dev, torch.bfloat16, seed=0, patch_image_size=a.img)
@@ -39,6 +40,21 @@ def main():
         torch.cuda.synchronize()
         if it:
             times.append(time.perf_counter() - t0)
+    if a.profile:
+        import collections
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            gen.generate([model], sample)
+            torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0.0, 0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                agg[ev.name][0] += ev.device_time
+                agg[ev.name][1] += 1
+        tot = sum(v[0] for v in agg.values())
+        print("device time %.2f ms in %d kernels" % (tot / 1e3, sum(v[1] for v in agg.values())))
+        for name, (t_, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+            print("%8.3f ms %5.1f%% %6d x %8.1f us  %s" % (t_ / 1e3, 100 * t_ / tot, n, t_ / n, name[:110]))
     t = sorted(times)[len(times) // 2]
     lens = [len(h[0]["tokens"]) for h in out]
     print(json.dumps({"metric": "beam-5 captions/s", "value": a.batch / t, "latency_ms": t * 1e3, "batch": a.batch,
