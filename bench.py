@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--profile-kernels", type=int, default=1)
     ap.add_argument("--graph", type=int, default=1, help="replay the micro-step as a CUDA graph (0: eager launches)")
+    ap.add_argument("--caption-bench", type=int, default=1, help="also time beam-5 captioning (BASELINE configs[4]) at N=1")
     return ap.parse_args()
 
 
@@ -94,19 +95,50 @@ def cpu_reference(steps, warmup, arch, img):
     sd["decoder.embed_tokens.weight"] = sd["encoder.embed_tokens.weight"]
     sd["decoder.output_projection.weight"] = sd["encoder.embed_tokens.weight"]
     times = []
+    # the update the trainer runs after the backward (trainer.py:863-898; fairseq Adam, train_musketeer.sh:136): global-norm
+    # clip 0.1 + Adam(lr 3e-5, betas (0.9, 0.999), eps 1e-8, decoupled weight decay 0.01) on the fp32 weights
+    leaves = [v for k, v in sd.items() if v.requires_grad and not k.startswith(("decoder.embed_tokens", "decoder.output_projection"))]
+    opt = torch.optim.AdamW(leaves, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
     for it in range(warmup + steps):
         group = make_tep_group(1, img=img, seed=it)
         t0 = time.perf_counter()
         loss, ss, _ = oo.criterion_forward(sd, cfg, group, epsilon=0.1)
         loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in leaves if p.grad is not None], 0.1)
+        opt.step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-        for v in sd.values():
-            if v.requires_grad:
-                v.grad = None
+        opt.zero_grad(set_to_none=True)
     t = sum(times) / len(times)
     return 5.0 / t, t, os.cpu_count()
+
+
+def caption_bench(dev, batch=64, img=480, beam=5, iters=2):
+    """BASELINE.json configs[4]: beam-5 captioning, OFA-base bf16, `batch` synthetic 480x480 images, prompt
+    of 8 source tokens, max_len_b 16 (random weights rarely emit EOS: the worst case of 17 decoder steps) -> captions/s."""
+    from musketeer_b200.sequence_generator import SequenceGenerator
+    from musketeer_b200.synthetic import build_model
+    model, task = build_model("ofa_base", dev, torch.bfloat16, seed=0, patch_image_size=img)
+    model.eval()
+    gen = SequenceGenerator([model], task.target_dictionary, beam_size=beam, max_len_a=0, max_len_b=16, min_len=1)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    src = torch.randint(4, 50265, (batch, 8), generator=g)
+    src[:, 0], src[:, -1] = 0, 2
+    sample = {"net_input": {"src_tokens": src.to(dev), "src_lengths": torch.full((batch,), 8).to(dev),
+                            "patch_images": torch.randn(batch, 3, img, img, generator=g).to(dev).bfloat16(),
+                            "patch_masks": torch.ones(batch, dtype=torch.bool, device=dev)}}
+    times = []
+    for it in range(iters + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = gen.generate([model], sample)
+        torch.cuda.synchronize()
+        if it:
+            times.append(time.perf_counter() - t0)
+    t = min(times)
+    return {"metric": "beam-5 captions/s (OFA-base, %d x %dx%d images, max_len 16)" % (batch, img, img), "value": batch / t,
+            "unit": "captions/s", "latency_ms": t * 1e3, "decoder_steps": max(len(h[0]["tokens"]) for h in out)}
 
 
 def main():
@@ -115,7 +147,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     workload = "OFA-base Musketeer TEP 5-task micro-step (caption S137/T12, VQA S230/T232, VG S259/T5, SNLI-VE " \
-               "S250/T250, gigaword S185/T12), %dx%d images, per-task batch %d, fwd+loss+bwd" % (a.img, a.img, a.task_batch)
+               "S250/T250, gigaword S185/T12), %dx%d images, per-task batch %d, fwd+loss+bwd+Adam update" % (a.img, a.img, a.task_batch)
 
     if a.impl == "reference":
         if rank != 0:
@@ -152,6 +184,8 @@ def main():
     resident = [to_device(h, dev, torch.bfloat16) for h in host]
     h2d = batch_bytes(host[0])
 
+    from musketeer_b200.optim import FusedAdam
+    optim = FusedAdam(model.parameters(), lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip_norm=0.1)
     graphed = None
     if a.graph:
         from musketeer_b200.graphed import GraphedTrainStep
@@ -177,6 +211,7 @@ def main():
             loss = eager_step(group)
         if reducer is not None:
             reducer.reduce_all() if graphed is not None and not eager else reducer.finish()
+        optim.step()        # update_freq = 1: every micro-step is followed by clip + Adam (trainer.py:863-898)
         if e2e:
             return float(loss)     # device -> host read of the step's result
         return loss
@@ -255,6 +290,11 @@ def main():
         g = tot.get("ofa_gemm_bf16")
         if g and top != "ofa_gemm_bf16":
             roof["gemm_tflops"] = g[1].get("flop", 0.0) / (g[0] / 1e3) / 1e12
+    caption = None
+    if a.caption_bench and world == 1:
+        del graphed, resident
+        torch.cuda.empty_cache()
+        caption = caption_bench(dev)
     cpu = None
     if a.cpu_baseline:
         v, t, cores = cpu_reference(1, 1, a.arch, a.img)
@@ -265,12 +305,13 @@ def main():
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "arch": a.arch, "l2": "activations and weights per step exceed the 126 MB L2",
-                   "optimizer_step": "not in the timed region (SURVEY.md 8f next row)", "dropout": 0.0,
+                   "optimizer_step": "fused clip + Adam (fp32 master weights) after every micro-step, inside the timed region",
+                   "dropout": 0.0,
                    "launch": "CUDA graph replay" if a.graph else "eager"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": samples * a.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
-        "roofline": roof, "cpu_baseline": cpu}))
+        "roofline": roof, "cpu_baseline": cpu, "caption_beam5": caption}))
     if world > 1:
         dist.destroy_process_group()
 
