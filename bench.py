@@ -210,7 +210,11 @@ def main():
                 group = to_device(group, dev, torch.bfloat16)
             loss = eager_step(group)
         if reducer is not None:
-            reducer.reduce_all() if graphed is not None and not eager else reducer.finish()
+            if graphed is not None and not eager:
+                if not reducer.reduce_flat(model):      # gradients live in the accumulator's flat arenas: in-place all-reduce
+                    reducer.reduce_all()
+            else:
+                reducer.finish()
         optim.step()        # update_freq = 1: every micro-step is followed by clip + Adam (trainer.py:863-898)
         if e2e:
             return float(loss)     # device -> host read of the step's result

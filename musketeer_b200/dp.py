@@ -103,6 +103,35 @@ class GradReducer:
                 off += n
         self._pending = None
 
+    def reduce_flat(self, model, chunk_bytes=64 << 20):
+        """After a micro-step run under ops.grad_accumulation (the CUDA-graph path), every gradient is a view into the two
+        flat arenas of the accumulator: average them in place with a few large NCCL all-reduces (ReduceOp.AVG) -- no
+        flatten / unflatten copies, no per-parameter kernels.  Returns False when the arenas do not cover the gradients."""
+        acc = getattr(model, "_ofa_grad_acc", None)
+        flats = acc.flat_grads() if acc is not None else []
+        if not flats:
+            return False
+        lo_hi = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in flats]
+        for p in self.params:
+            if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in lo_hi):
+                if getattr(p, "_ofa_zero_grad", False) or not bool(p.grad.any()):
+                    p._ofa_zero_grad = True       # unused parameter: zero on every rank (checked once)
+                    continue
+                return False
+        avg = dist.get_backend(self.pg) == "nccl"       # ReduceOp.AVG exists on NCCL only
+        works = []
+        for f in flats:
+            step = max(1, chunk_bytes // f.element_size())
+            for o in range(0, f.numel(), step):
+                works.append(dist.all_reduce(f[o:o + step], op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM,
+                                             group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+        if not avg:
+            for f in flats:
+                f.div_(self.world)
+        return True
+
     def reduce_all(self):
         """Reduce every bucket now (used after a CUDA-graph replay, where autograd hooks do not fire)."""
         self.prepare()

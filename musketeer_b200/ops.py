@@ -26,6 +26,11 @@ class _GradAccumulator:
         self.params = {id(p): p for p in model.parameters() if p.requires_grad}
         self.buf = {}
         self.written = set()
+        # the per-parameter buffers of the other producers (bias column sums, LayerNorm / BatchNorm reductions, embedding
+        # scatter-add) are carved out of one flat arena in the parameter dtype, so a data-parallel run all-reduces two
+        # flat tensors in place instead of ~1000 gradients (dp.GradReducer.reduce_flat)
+        self.arena_buf = None
+        self.buf_used = 0
         # weight gradients of the Linear / 1x1-conv GEMMs accumulate in fp32: every K slice, micro-batch and task adds into
         # one arena by TMA reduce (ofa_gemm_bf16 out_dtype 2); `finish` casts the arena to the parameter dtype in one pass
         self.arena32 = self.arena_out = None
@@ -60,7 +65,18 @@ class _GradAccumulator:
             return None, False
         b = self.buf.get(k)
         if b is None or b.shape != param.shape or b.dtype != param.dtype or b.device != param.device:
-            b = self.buf[k] = torch.empty_like(param)      # same memory format as the parameter (channels_last conv weights)
+            dense = param.is_contiguous() or (param.dim() == 4 and param.is_contiguous(memory_format=torch.channels_last))
+            if self.arena_buf is None or self.arena_buf.device != param.device or self.arena_buf.dtype != param.dtype:
+                self.arena_buf = torch.zeros(sum((p.numel() + 63) // 64 * 64 for p in self.params.values()),
+                                             dtype=param.dtype, device=param.device)
+                self.buf, self.buf_used = {}, 0
+            if dense and not torch.cuda.is_current_stream_capturing():
+                n = param.numel()       # same memory format as the parameter (channels_last conv weights)
+                b = self.arena_buf[self.buf_used:self.buf_used + n].as_strided(param.shape, param.stride())
+                self.buf_used += (n + 63) // 64 * 64
+            else:
+                b = torch.empty_like(param)
+            self.buf[k] = b
         first = k not in self.written
         self.written.add(k)
         return b, not first
@@ -84,6 +100,15 @@ class _GradAccumulator:
             p, b = self.params[k], self.buf[k]
             p.grad = b if p.grad is None else p.grad + b
         self.written, self.written32 = set(), set()
+
+    def flat_grads(self):
+        """The flat tensors every gradient produced inside the context lives in (valid after `finish`)."""
+        out = []
+        if self.arena_out is not None and self.arena_used:
+            out.append(self.arena_out[:self.arena_used])
+        if self.arena_buf is not None and self.buf_used:
+            out.append(self.arena_buf[:self.buf_used])
+        return out
 
 
 _ACC = None

@@ -63,7 +63,27 @@ def _worker(rank, world, port, outdir):
     model(x).backward()
     red.reduce_all()
     allred = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
-    torch.save((local, out, nosync, allred), os.path.join(outdir, "r%d.pt" % rank))
+    # reduce_flat: gradients are views into flat arenas (ops.grad_accumulation layout) -> in-place flat all-reduce
+    model.zero_grad(set_to_none=True)
+    model(x).backward()
+    named = [(n, p) for n, p in model.named_parameters() if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1) for _, p in named])
+    off = 0
+    for _, p in named:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+
+    class _Acc:
+        def flat_grads(self):
+            return [flat]
+    model._ofa_grad_acc = _Acc()
+    model.unused.grad = torch.zeros_like(model.unused)        # unused parameter: zeros outside the arenas are accepted
+    assert red.reduce_flat(model, chunk_bytes=512)
+    flatred = {n: p.grad.clone() for n, p in named}
+    model.unused.grad = torch.ones_like(model.unused)         # a real gradient outside the arenas -> refuse (caller falls back)
+    model.unused._ofa_zero_grad = False
+    assert not red.reduce_flat(model)
+    torch.save((local, out, nosync, allred, flatred), os.path.join(outdir, "r%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -83,6 +103,7 @@ def test_grad_reducer_world2(tmp_path):
         for r in range(2):
             assert torch.allclose(res[r][1][n], mean, atol=1e-6), n       # hook-driven bucketed reduce
             assert torch.allclose(res[r][3][n], mean, atol=1e-6), n       # reduce_all
+            assert torch.allclose(res[r][4][n], mean, atol=1e-6), n       # reduce_flat
             assert torch.allclose(res[r][2][n], res[r][0][n]), n          # no_sync: untouched local grads
     for r in range(2):
         assert res[r][1]["unused"] is not None and float(res[r][1]["unused"].abs().sum()) == 0.0
