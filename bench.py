@@ -142,6 +142,11 @@ def caption_bench(dev, batch=64, img=480, beam=5, iters=2):
 
 
 def main():
+    # the driver reads ONE JSON line from stdout: libraries that print there (NCCL's version banner) are sent to stderr by
+    # pointing fd 1 at fd 2 for the whole run; the JSON line goes to the saved descriptor at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     a = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -220,6 +225,24 @@ def main():
             return float(loss)     # device -> host read of the step's result
         return loss
 
+    def phases(nsteps):
+        """Device time of the three phases of a step (graph replay | gradient all-reduce | optimizer), events on this rank."""
+        acc = [0.0, 0.0, 0.0]
+        for i in range(nsteps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            graphed(resident[i % n_batches])
+            ev[1].record()
+            if reducer is not None and not reducer.reduce_flat(model):
+                reducer.reduce_all()
+            ev[2].record()
+            optim.step()
+            ev[3].record()
+            torch.cuda.synchronize()
+            for k in range(3):
+                acc[k] += ev[k].elapsed_time(ev[k + 1]) / nsteps
+        return {"replay_ms": acc[0], "allreduce_ms": acc[1], "optimizer_ms": acc[2]}
+
     def timed(nsteps, e2e):
         if world > 1:
             dist.barrier()
@@ -246,6 +269,7 @@ def main():
     ms = timed(a.steps, False)
     ms_e2e = timed(a.steps, True)
     clocks = sampler.stop() if sampler else None
+    ph = phases(a.steps) if graphed is not None else None
     # kernel launches of one step (counted on an eager step: a graph replay re-issues exactly these launches)
     l0 = _lib.LAUNCHES
     step(resident[0], eager=True)
@@ -312,7 +336,7 @@ def main():
                    "optimizer_step": "fused clip + Adam (fp32 master weights) after every micro-step, inside the timed region",
                    "dropout": 0.0,
                    "launch": "CUDA graph replay" if a.graph else "eager"},
-        "clocks": clocks, "gpu_launches": launches,
+        "clocks": clocks, "gpu_launches": launches, "phases": ph,
         "e2e": {"value": samples * a.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
         "roofline": roof, "cpu_baseline": cpu, "caption_beam5": caption}))

@@ -61,9 +61,7 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
         sample = sample[0] if isinstance(sample, list) else sample
         if self.use_rdrop:
             sample = construct_rdrop_sample(sample)
-        if self.drop_worst_ratio > 0 and update_num > self.drop_worst_after:
-            raise NotImplementedError("drop-worst (after update %d) is not wired into the fused loss yet"
-                                      % self.drop_worst_after)
+        drop = self.drop_worst_ratio if (self.drop_worst_ratio > 0 and update_num > self.drop_worst_after) else 0.0
         logits, _ = model(**sample["net_input"], padded_logits=True)
         target = sample["target"]
         if self.ignore_prefix_size > 0:                                                 # :239-243
@@ -73,8 +71,11 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
             target = target.masked_fill(target.eq(self.eos_idx), self.padding_idx)
         loss, nll_rows = ops.ls_cross_entropy(
             logits, target, self.eps, self.padding_idx, cmask=sample.get("constraint_masks"), conf=sample.get("conf"),
-            crange=self.constraint_range, rdrop=self.use_rdrop, reg_alpha=self.reg_alpha)
-        if self.ignore_prefix_size > 0 or self.ignore_eos or "ntokens" not in sample:
+            crange=self.constraint_range, rdrop=self.use_rdrop, reg_alpha=self.reg_alpha, drop_worst_ratio=drop)
+        if drop > 0:          # ntokens = rows kept (label_smoothed_cross_entropy.py:113)
+            n = int(target.ne(self.padding_idx).sum())
+            ntokens = 2 * int((n // 2) * (1 - drop)) if self.use_rdrop else int(n * (1 - drop))
+        elif self.ignore_prefix_size > 0 or self.ignore_eos or "ntokens" not in sample:
             ntokens = int(target.ne(self.padding_idx).sum())   # host sync, like the reference's boolean indexing (:258-260)
         else:
             ntokens = sample["ntokens"]    # the collater's count of non-pad target tokens: same number, no device sync

@@ -736,7 +736,7 @@ def cache_gather(src, dst, order, rows, L):
 # ---------------------------------------------------------------------------------------------------------------------
 class _LsCe(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, cmask, conf, eps, pad_idx, crange, rdrop, reg_alpha):
+    def forward(ctx, logits, target, cmask, conf, eps, pad_idx, crange, rdrop, reg_alpha, drop_ratio):
         """logits [B,T,V] (row stride may be padded) are CONSUMED: the kernel overwrites the buffer with
         d loss / d logits behind autograd's back (nothing upstream saves the logits; see decoder.output_layer)."""
         _need_cuda(logits)
@@ -754,6 +754,24 @@ class _LsCe(torch.autograd.Function):
              int(rdrop), reg_alpha, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st(),
              work=("byte", 2 * R * V * logits.element_size()))
         ctx.dlogits = logits.detach()
+        ctx.row_keep = None
+        if drop_ratio > 0:
+            # drop-worst (criterions/label_smoothed_cross_entropy.py:100-111): keep the int(n * (1 - ratio)) non-pad rows with
+            # the smallest loss (of the first R-Drop half; the second half keeps the same rows); dropped rows leave the
+            # loss, the KL term and -- through row_keep in the backward -- the gradient
+            valid = tgt.reshape(-1).ne(pad_idx)
+            half = R // 2 if rdrop else R
+            v1 = valid[:half]
+            k = int(int(v1.sum()) * (1 - drop_ratio))       # host sync, as the reference's boolean indexing + topk
+            idx = torch.topk(loss_rows[:half].masked_fill(~v1, float("inf")), k=k, largest=False).indices
+            keep1 = torch.zeros(half, dtype=torch.bool, device=logits.device)
+            keep1[idx] = True
+            keep = torch.cat([keep1, keep1]) if rdrop else keep1
+            loss_rows = loss_rows * keep
+            nll_rows = nll_rows * keep
+            if rdrop:
+                kl_rows = kl_rows * keep1
+            ctx.row_keep = keep.view(torch.uint8)
         ctx.mark_non_differentiable(nll_rows)
         loss = loss_rows.sum() + (reg_alpha * kl_rows.sum() if rdrop else 0.0)
         return loss, nll_rows
@@ -763,11 +781,13 @@ class _LsCe(torch.autograd.Function):
         dlogits = ctx.dlogits
         B, T, V = dlogits.shape
         scale = gloss.float().reshape(1).contiguous()
-        call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(None), _dt(dlogits), _st())
-        return dlogits, None, None, None, None, None, None, None, None
+        call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(ctx.row_keep), _dt(dlogits), _st())
+        return dlogits, None, None, None, None, None, None, None, None, None
 
 
-def ls_cross_entropy(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None, rdrop=False, reg_alpha=1.0):
-    """Sum over non-pad rows of the label-smoothed NLL (+ reg_alpha * symmetric KL between the two R-Drop halves).
-    Returns (loss, nll_rows).  `logits` is overwritten with its own gradient (one read + one write of M x V)."""
-    return _LsCe.apply(logits, target, cmask, conf, eps, pad_idx, crange, rdrop, reg_alpha)
+def ls_cross_entropy(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None, rdrop=False, reg_alpha=1.0,
+                     drop_worst_ratio=0.0):
+    """Sum over non-pad rows of the label-smoothed NLL (+ reg_alpha * symmetric KL between the two R-Drop halves),
+    optionally over the (1 - drop_worst_ratio) fraction of rows with the smallest loss.  Returns (loss, nll_rows; dropped
+    rows are 0).  `logits` is overwritten with its own gradient (one read + one write of M x V)."""
+    return _LsCe.apply(logits, target, cmask, conf, eps, pad_idx, crange, rdrop, reg_alpha, float(drop_worst_ratio))

@@ -247,3 +247,42 @@ def test_fused_grad_accumulation_matches_autograd(dtype):
         if a is not None:
             tol = 1e-5 if dtype == torch.float32 else 3e-2
             assert (a.float() - b.float()).abs().max().item() <= tol * max(1.0, a.float().abs().max().item()), n
+
+
+@pytest.mark.parametrize("name,rdrop", [("micro_pad", False), ("micro_rdrop_sample", True)])
+def test_drop_worst_matches_oracle(name, rdrop):
+    """drop-worst (--drop-worst-ratio 0.2 after 6000 updates in train_musketeer.sh:78,163-164;
+    label_smoothed_cross_entropy.py:100-113): kept-row loss, sample size and total gradient norm vs the oracle run on the
+    same weights / batch in fp32, with and without R-Drop."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg, sd, samples = build_case(case)
+    po = fx.get("patch_orders")
+    kw = dict(use_rdrop=rdrop, reg_alpha=1.0, drop_worst_ratio=0.3, drop_worst_after=5, update_num=10)
+    sdo = tie(sd)
+    s0 = copy.deepcopy(samples[0])
+    if case.get("sample_patch_num"):
+        s0["net_input"]["sample_patch_num"] = case["sample_patch_num"]
+    ref_loss, ref_ss, _ = oo.criterion_forward(sdo, cfg, s0, epsilon=0.1, patch_orders=po[0] if isinstance(po, list) else po, **kw)
+    (ref_loss / ref_ss).backward()
+    ref_gn = sum(float(v.grad.norm()) ** 2 for k, v in sdo.items() if v.requires_grad and v.grad is not None
+                 and not k.startswith(("decoder.embed_tokens", "decoder.output_projection"))) ** 0.5
+    model, task = build_product(cfg, sd, dtype=torch.float32)
+    model.train()
+    model.encoder.patch_orders_override = po[0] if isinstance(po, list) else po
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=rdrop, reg_alpha=1.0, drop_worst_ratio=0.3,
+                                                    drop_worst_after=5, sample_patch_num=0)
+    inp = to_device(copy.deepcopy(samples[0]), "cuda", torch.float32)
+    if case.get("sample_patch_num"):
+        inp["net_input"]["sample_patch_num"] = case["sample_patch_num"]
+    loss, ss, _ = crit(model, inp, update_num=10)
+    (loss / ss).backward()
+    gn = sum(float(p.grad.float().norm()) ** 2 for p in model.parameters() if p.grad is not None) ** 0.5
+    assert ss == ref_ss, (ss, ref_ss)
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-3 * abs(float(ref_loss.detach()))
+    assert abs(gn - ref_gn) <= 1e-3 * ref_gn, (gn, ref_gn)
+    # before the threshold update the criterion is unchanged
+    loss0, ss0, _ = crit(model, to_device(copy.deepcopy(samples[0]), "cuda", torch.float32) if not case.get("sample_patch_num")
+                         else inp, update_num=3)
+    assert ss0 > ss
