@@ -38,6 +38,8 @@ def test_sass_is_blackwell_native(lib_path):
     sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass      # tcgen05.mma
     assert "UTMALDG" in sass      # TMA tensor loads
+    assert "UTMASTG" in sass      # TMA tensor stores (GEMM / conv epilogues)
+    assert "UTMAREDG" in sass     # TMA reduce-add (fp32 gradient arenas, attention dQ)
     assert "LDTM" in sass         # tcgen05.ld
     assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
 
