@@ -42,6 +42,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// erf-GELU for the bf16 kernels: Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below bf16 resolution) costs one
+// MUFU.RCP, one MUFU.EX2 and seven FMAs and also yields exp(-x^2/2) for the derivative; the fp32 parity mode keeps erff.
+template <typename T>
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {   // cdf = Phi(x), pdf_x = x * phi(x)
+  if (sizeof(T) == 4) {
+    cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    pdf_x = x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+  } else {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float e = __expf(-z * z);                       // = exp(-x^2 / 2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_erfc = 0.5f * poly * t * e;          // 0.5 * (1 - erf(z))
+    cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+    pdf_x = x * 0.39894228040143267794f * e;
+  }
+}
 __device__ __forceinline__ float gelu_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
@@ -71,7 +91,11 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, co
       Vec8<T>::load(xr + c, v[i]);
       if (gelu_in) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = gelu_erf(v[i][j]);
+        for (int j = 0; j < 8; ++j) {
+          float cdf, pdfx;
+          gelu_parts<T>(v[i][j], cdf, pdfx);
+          v[i][j] *= cdf;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -158,9 +182,10 @@ __global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_ker
           float fx = raw[u][j];
           gp[u][j] = 1.f;
           if (GELU) {
-            const float cdf = 0.5f * (1.0f + erff(raw[u][j] * 0.70710678118654752440f));
+            float cdf, pdfx;
+            gelu_parts<T>(raw[u][j], cdf, pdfx);
             fx = raw[u][j] * cdf;
-            gp[u][j] = cdf + raw[u][j] * 0.39894228040143267794f * __expf(-0.5f * raw[u][j] * raw[u][j]);
+            gp[u][j] = cdf + pdfx;
           }
           xh[u][j] = (fx - mean[u]) * rstd[u];
           const float g = d[u][j] * gm[j];
@@ -432,13 +457,19 @@ extern "C" int ofa_layernorm_fwd(const void* x, const void* gamma, const void* b
 extern "C" int ofa_layernorm_bwd_nparts(int rows) {
   return rows < 1184 ? rows : 1184;  // 8 CTAs per SM on 148 SMs
 }
+// wide rows (C >= 2048: 256+ threads per CTA, at most 2-3 CTAs resident per SM) use fewer persistent CTAs, which also
+// quarters the [nparts, C] fp32 partials the reduce kernel has to re-read
+static int ln_bwd_nparts_for(int rows, int C) {
+  const int cap = C >= 2048 ? 296 : (C >= 1024 ? 592 : 1184);
+  return rows < cap ? rows : cap;
+}
 
 extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                                  const float* rstd, void* dx, void* dgamma, void* dbeta, float* workspace, int rows,
                                  int C, int gelu_in, int accumulate, int dtype, void* stream) {
   OFA_CHECK(rows > 0 && C > 0 && C % 8 == 0, "ofa_layernorm_bwd: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const int nparts = ofa_layernorm_bwd_nparts(rows);
+  const int nparts = ln_bwd_nparts_for(rows, C);   // <= ofa_layernorm_bwd_nparts(rows): the workspace bound
   float* pg = workspace;
   float* pb = workspace + (size_t)nparts * C;  // workspace: 2 * nparts * C floats
   OFA_CHECK(C <= 4096, "ofa_layernorm_bwd: C=%d too wide (max 4096)", C);

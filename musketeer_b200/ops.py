@@ -220,7 +220,7 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=A.device) if wsb > 0 else None
     call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
          _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _p(ws), wsb, _st(),
-         work=("flop", 2.0 * M * N * K))
+         work=("flop", 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), od)))
     return out
 
 

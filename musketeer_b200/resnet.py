@@ -26,12 +26,15 @@ class FrozenBatchNorm2d(nn.Module):
     momentum = 0.0
 
 
+_TRACK = []
+
+
 def _bn(mod, x, relu=False, residual=None):
     """nn.BatchNorm2d (batch statistics when the module is in training mode) or FrozenBatchNorm2d, as holders."""
     frozen = isinstance(mod, FrozenBatchNorm2d)
     training = mod.training and not frozen
     if training and mod.num_batches_tracked is not None:
-        mod.num_batches_tracked += 1
+        _TRACK.append(mod.num_batches_tracked)        # bumped once per stem forward with one fused add (ResNetStem.forward)
     return ops.batch_norm(x, mod.weight, mod.bias, mod.running_mean, mod.running_var, residual, relu, training,
                           0.1 if not frozen else 0.0, mod.eps)
 
@@ -112,6 +115,7 @@ class ResNetStem(nn.Module):
         tf32 = torch.backends.cudnn.allow_tf32
         if dt == torch.float32:
             torch.backends.cudnn.allow_tf32 = False      # fp32 parity mode must not silently drop to TF32
+        del _TRACK[:]
         try:
             x = x.to(dt).contiguous(memory_format=torch.channels_last)
             x = _bn(self.bn1, _conv(self.conv1, x), relu=True)
@@ -119,6 +123,9 @@ class ResNetStem(nn.Module):
             x = self.layer3(self.layer2(self.layer1(x)))
         finally:
             torch.backends.cudnn.allow_tf32 = tf32
+            if _TRACK:          # nn.BatchNorm2d bookkeeping: 94 counters, one multi-tensor kernel instead of 94 launches
+                torch._foreach_add_(list(_TRACK), 1)
+                del _TRACK[:]
         B, Cc, h, w = x.shape
         self.last_hw = (h, w)
         return x.permute(0, 2, 3, 1).reshape(B, h * w, Cc)
