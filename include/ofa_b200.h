@@ -20,7 +20,9 @@ int ofa_abi_version(void);
  * When D rows are padded to a multiple of 8 elements (ldd == ceil8(N)) the padding columns [N, ldd) may be overwritten.
  * a_mn_major=0: A stored row-major [M][K] (lda);  =1: stored [K][M].  Same for B with N.  out_dtype: D/bias/resid type;
  * out_dtype 2 = fp32 accumulate: D (fp32) += alpha * A.B^T by TMA reduce-add (weight-gradient accumulation across K
- * slices, micro-batches and tasks without a workspace; no bias / residual / activation).
+ * slices, micro-batches and tasks without a workspace; no residual / activation).  In this mode `bias`, if not NULL,
+ * names an fp32 [M] buffer that receives alpha * sum_k A(m,k): the bias gradient of a weight-gradient GEMM (A = dY^T),
+ * computed by one extra N = 16 tcgen05.mma per k-step against an all-ones tile.
  * replaces: unify_multihead_attention.py:213-232,399 (q/k/v/out proj), unify_transformer_layer.py:280-284,557-561
  * (fc1/fc2), unify_transformer.py:739 (image_proj), :906-911,1303-1316 (pos q/k), :1577-1583 (tied output proj)
  * and their autograd transposes.                                                                                    */

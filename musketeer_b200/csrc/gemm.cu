@@ -39,6 +39,7 @@ struct GemmParams {
   int total;     // total work items
   float alpha;
   int act;  // 0 none, 1 gelu(erf)
+  float* rowsum;  // fp32 [M]: rowsum[m] += alpha * sum_k A(m,k) (bias gradient of a weight-gradient GEMM) or null
   int reduce_f32; // fp32 output ADDED into D by TMA reduce (gradient accumulation; K slices need no workspace)
   int tma_store;  // bf16 output staged through shared memory and written with TMA (needs 16B-aligned D rows)
 };
@@ -54,6 +55,8 @@ template <int BN>
 struct SmemLayout {
   uint8_t tiles[Cfg<BN>::kStages][Cfg<BN>::kStageBytes];  // 1024B aligned (SWIZZLE_128B)
   uint8_t stage_out[4][2][4096];  // per epilogue warp: two 32-row x 64-column bf16 slabs (SWIZZLE_128B) for the TMA store
+  uint8_t ones[BN == 128 ? 1024 : 64];   // BN = 128 only (the 256-wide layout has no shared memory to spare): one 8-row
+                                         // swizzle atom of bf16 1.0 that both 8-row groups of the N = 16 operand alias (SBO = 0): B operand of the row-sum MMA (bias gradients inside the wgrad GEMM)
   uint64_t full[Cfg<BN>::kStages];
   uint64_t empty[Cfg<BN>::kStages];
   uint64_t tmem_full[2];
@@ -265,7 +268,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(&sm.tmem_addr);
+  // TMEM footprint matters beyond this kernel: a smaller allocation lets the next kernel's CTAs start while ours drain
+  // Row-sum calls (weight gradients: about one long tile per CTA, nothing for a second accumulator to overlap) run
+  // single-buffered -- 128 accumulator + 16 row-sum columns -- so that the allocation stays at 256 columns.
+  const bool rs_mode = BN == 128 && p.rowsum != nullptr;
+  const uint32_t tmem_cols = (uint32_t)C::kTmemCols;
+  if (warp == 2) tmem_alloc_n(&sm.tmem_addr, tmem_cols);
+  if (BN == 128 && p.rowsum) {
+    for (int e = threadIdx.x; e < 256; e += kThreads) reinterpret_cast<uint32_t*>(sm.ones)[e] = 0x3F803F80u;   // bf16 1.0 pairs
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
@@ -315,10 +327,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const Work wk = decode<BN, PAIR>(w, p, crank);
         const uint32_t idesc = umma_idesc_bf16(BM, wk.bn, A_MN, B_MN);
         const int kb0 = wk.sp * p.kb_per_split, kb1 = min(nkb_all, kb0 + p.kb_per_split);
-        const int acc = it & 1;
-        mbar_wait(&sm.tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        const int acc = rs_mode ? 0 : (it & 1);
+        mbar_wait(&sm.tmem_empty[acc], ((rs_mode ? it : (it >> 1)) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        const bool rs_tile = BN == 128 && p.rowsum && (wk.n0 % BN) == 0;
+        const int rs_nt = wk.n0 / BN;
+        uint32_t rs_acc = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&sm.full[s], ph);
           tc_fence_after();
@@ -331,6 +346,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
             umma_f16(tmem_d, da, db, idesc, (kb != kb0) | (k != 0));
+          }
+          // row sums of A on the tensor core: N = 16 MMAs against the all-ones tile.  They re-read the A stage (the 128 x 128
+          // kernel is shared-memory-bandwidth bound), so the k-blocks are dealt round-robin to the column tiles of a row block
+          if (rs_tile && kb % p.tiles_n == rs_nt) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+              umma_f16(tmem_base + BN, da, umma_smem_desc(smem_u32(sm.ones) + k * 32, 16, 0),
+                       umma_idesc_bf16(BM, 16, A_MN, 0), rs_acc | (k != 0));
+            }
+            rs_acc = 1;
           }
           if (PAIR) umma_commit_mc(&sm.empty[s], 3);  // both CTAs' producers write into this stage of both CTAs
           else umma_commit(&sm.empty[s]);             // frees the smem stage when these MMAs retire
@@ -348,13 +374,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const Work wk = decode<BN, PAIR>(w, p, crank);
       const int m0 = wk.m0, n0 = wk.n0;
       const int nch = wk.bn / 32;
-      const int acc = it & 1;
+      const int acc = rs_mode ? 0 : (it & 1);
       const int row = m0 + q * 32 + lane;
-      mbar_wait(&sm.tmem_full[acc], (it >> 1) & 1);
+      mbar_wait(&sm.tmem_full[acc], (rs_mode ? it : (it >> 1)) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       if (sizeof(OutT) == 4 && p.reduce_f32) {
         if (m0 + q * 32 < p.M) epilogue_reduce(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, m0 + q * 32, n0, wk.bz, p, lane);
+        const int rs_kb0 = wk.sp * p.kb_per_split, rs_tn = p.tiles_n;
+        const int rs_first = rs_kb0 + (((n0 / BN) - rs_kb0 % rs_tn) + rs_tn) % rs_tn;      // first k-block dealt to this tile
+        if (BN == 128 && p.rowsum && (n0 % BN) == 0 && rs_first < min(nkb_all, rs_kb0 + p.kb_per_split)) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + BN + ((uint32_t)(q * 32) << 16), r);
+          tmem_ld_wait();
+          if (row < p.M) atomicAdd(p.rowsum + row, __uint_as_float(r[0]) * p.alpha);
+        }
       } else if (sizeof(OutT) == 2 && p.tma_store) {
         if (m0 + q * 32 < p.M) epilogue_tma(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, row, n0, wk.bz, p, lane);
       } else if (p.splits > 1) {
@@ -419,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (PAIR) cluster_sync_all();   // neither CTA may retire while the peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    tmem_dealloc_n(tmem_base, tmem_cols);
   }
 }
 
@@ -803,14 +837,30 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   OFA_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "ofa_gemm_bf16: A/B must be 16B aligned");
   OFA_CHECK(stride_a % 8 == 0 && stride_b % 8 == 0, "ofa_gemm_bf16: batch strides must be multiples of 8 elements");
   const int reduce_f32 = out_dtype == OFA_F32_ACC;
+  float* rowsum = nullptr;
   if (reduce_f32) {
-    OFA_CHECK(!bias && !resid && act == 0, "ofa_gemm_bf16: the fp32-accumulate output takes no bias / residual / activation");
+    rowsum = (float*)bias;    // fp32-accumulate mode: `bias` names an fp32 [M] buffer that receives alpha * row sums of A
+    bias = nullptr;
+    OFA_CHECK(!resid && act == 0, "ofa_gemm_bf16: the fp32-accumulate output takes no residual / activation");
+    OFA_CHECK(!rowsum || batch == 1, "ofa_gemm_bf16: row sums need batch == 1");
     OFA_CHECK(ldd % 4 == 0 && N % 4 == 0 && ((uintptr_t)D & 15) == 0 && stride_d % 4 == 0,
               "ofa_gemm_bf16: fp32-accumulate output needs 16-byte aligned rows (N=%d ldd=%lld)", N, ldd);
     out_dtype = OFA_F32;
   }
   int bn, splits;
   plan(M, N, K, batch, &bn, &splits);
+  if (rowsum && bn != 128) {      // the row-sum columns live next to 2 x 128 accumulator columns
+    bn = 128;
+    splits = 1;
+    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + 127) / 128);
+    const int nkb_r = (K + BK - 1) / BK;
+    if (tiles * 2 <= kNumSMs && nkb_r >= 8) {
+      splits = (int)(kNumSMs / tiles);
+      if (splits > nkb_r / 4) splits = nkb_r / 4;
+      if (splits > 32) splits = 32;
+      if (splits < 1) splits = 1;
+    }
+  }
   if (!reduce_f32 && splits > 1 &&
       (workspace == nullptr || workspace_bytes < (long long)splits * batch * M * N * (long long)sizeof(float)))
     splits = 1;  // no workspace: run unsplit (still correct, just fewer CTAs)
@@ -856,6 +906,7 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     if (int e = ofa_make_tmap(&td, D, 3, dims, strides, box, 1, 4)) return e;
   }
   GemmParams p;
+  p.rowsum = rowsum;
   p.reduce_f32 = reduce_f32;
   p.tma_store = tma_store;
   p.D = D; p.bias = bias; p.resid = resid; p.ws = (float*)workspace; p.ldd = ldd; p.ldr = ldr;
@@ -867,9 +918,9 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // drop empty trailing slices
   // cta_group::2 (mode 2): 256 x 256 pair tiles for plain problems with at least one full round of pair tiles, or split
   // along K when the output is small and the contraction long (weight gradients)
-  int s2 = g_ofa_gemm_pair_enabled == 2 ? plan2_splits(M, N, K, batch) : 0;
+  int s2 = (g_ofa_gemm_pair_enabled == 2 && !rowsum) ? plan2_splits(M, N, K, batch) : 0;
   if (!reduce_f32 && s2 > 1 && (workspace == nullptr || workspace_bytes < (long long)s2 * M * N * (long long)sizeof(float))) s2 = 0;
-  if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && N >= 256 &&
+  if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && N >= 256 && !rowsum &&
       (s2 > 1 || (p.splits == 1 && (long long)((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2))) {
     p.tiles_m = (M + 255) / 256;
     p.tiles_n = (N + 255) / 256;

@@ -42,10 +42,10 @@ class _GradAccumulator:
         """-> fp32 [N, K] accumulation view for a registered >= 2-D leaf parameter, else None."""
         k = id(param)
         dense = param.is_contiguous() or (param.dim() == 4 and param.is_contiguous(memory_format=torch.channels_last))
-        if k not in self.params or param.dim() < 2 or not dense:
+        if k not in self.params or not dense:
             return None
         if self.arena32 is None or self.arena32.device != param.device or self.arena_out.dtype != param.dtype:
-            total = sum(p.numel() for p in self.params.values() if p.dim() >= 2)
+            total = sum((p.numel() + 63) // 64 * 64 for p in self.params.values())
             self.arena32 = torch.zeros(total, dtype=torch.float32, device=param.device)
             self.arena_out = torch.empty(total, dtype=param.dtype, device=param.device)
             self.region, self.arena_used = {}, 0
@@ -56,7 +56,8 @@ class _GradAccumulator:
             r = self.region[k] = (self.arena_used, param.numel())
             self.arena_used += (param.numel() + 63) // 64 * 64
         self.written32.add(k)
-        return self.arena32[r[0]:r[0] + r[1]].view(param.shape[0], -1)      # storage order of the parameter
+        v = self.arena32[r[0]:r[0] + r[1]]
+        return v.view(param.shape[0], -1) if param.dim() >= 2 else v      # storage order of the parameter
 
     def target(self, param):
         """-> (buffer, accumulate) for a registered leaf parameter, else (None, False)."""
@@ -191,7 +192,7 @@ def _split3(x2d, rows, cols, k_is_cols, pattern):
 
 
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, alpha=1.0, act=0, resid=None,
-         ldd=None, acc32=False):
+         ldd=None, acc32=False, rowsum=None):
     """D[M,N] = act((A.B^T + bias) * alpha) + resid.   A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn);
     2-D tensors with unit inner stride.  fp32 operands take the split path."""
     _need_cuda(A)
@@ -212,7 +213,10 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
     if acc32:                   # out (fp32) += alpha * A.B^T   (TMA reduce-add; K slices need no workspace)
         assert out is not None and out.dtype == torch.float32 and bias is None and resid is None and act == 0
         od = 2
-    if bias is not None:
+        if rowsum is not None:  # fp32 [M] += alpha * row sums of A (bias gradient), computed inside the same GEMM
+            assert rowsum.dtype == torch.float32 and rowsum.numel() == M and rowsum.is_contiguous()
+            bias = rowsum
+    elif bias is not None:
         assert bias.dtype == out_dtype
     if resid is not None:
         assert resid.dtype == out_dtype and resid.stride(-1) == 1
@@ -254,13 +258,19 @@ class _Linear(torch.autograd.Function):
             pad[:, :N].copy_(dy2)
             dy2 = pad[:, :N]
         dx = dw = db = dr = None
+        bias_done = False
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
         if ctx.needs_input_grad[1]:
             tgt32 = _acc_target32(ctx.w_param) if K % 4 == 0 else None
             tgt, accum = (None, False) if tgt32 is not None else _acc_target(ctx.w_param)
             if tgt32 is not None:
-                gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt32, out_dtype=torch.float32, acc32=True)
+                b32 = None
+                if ctx.has_b and ctx.needs_input_grad[2] and x2.dtype == torch.bfloat16:
+                    b32 = _acc_target32(ctx.bias_param)          # bias gradient = row sums of dY^T, from the same GEMM
+                gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt32, out_dtype=torch.float32, acc32=True,
+                     rowsum=b32)
+                bias_done = b32 is not None
             elif tgt is not None:
                 tgt = tgt.view(N, K)
                 gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out=tgt, out_dtype=w.dtype,
@@ -268,7 +278,7 @@ class _Linear(torch.autograd.Function):
             else:
                 dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True, alpha=ctx.alpha, out_dtype=w.dtype)
                 dw = dw.view(ctx.w_param.shape)
-        if ctx.has_b and ctx.needs_input_grad[2]:
+        if ctx.has_b and ctx.needs_input_grad[2] and not bias_done:
             tgt, accum = _acc_target(ctx.bias_param)
             if tgt is not None:
                 colsum(dy2, alpha=ctx.alpha, out=tgt, accumulate=accum)

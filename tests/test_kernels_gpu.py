@@ -434,3 +434,25 @@ def test_conv3x3_implicit_gemm(N, Cin, Cout, H, W):
                   W, Cin, Cout, 2, C.c_void_p(0), 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     err = (acc.permute(0, 3, 1, 2).double().cpu() - 2 * wf.grad).abs().max().item()
     assert err < 1e-3 * max(1.0, 2 * wf.grad.abs().max().item()), err
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 6680), (3072, 768, 1000), (200, 136, 333), (768, 3072, 13360), (64, 256, 9216)])
+def test_gemm_fp32_accumulate_with_rowsum(M, N, K):
+    """Weight-gradient mode: D (fp32) += alpha * A^T-major . B by TMA reduce-add over K slices, and the bias gradient
+    rowsum[m] += alpha * sum_k A(m, k) from the extra all-ones MMA; two calls accumulate."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = torch.zeros(K, Mp).cuda().bfloat16()     # dY [tokens, M]  (MN-major A)
+    B = torch.zeros(K, Np).cuda().bfloat16()     # X  [tokens, N]  (MN-major B)
+    A[:, :M] = torch.randn(K, M, generator=g).cuda().bfloat16()
+    B[:, :N] = torch.randn(K, N, generator=g).cuda().bfloat16()
+    out = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    rs = torch.zeros(M, dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        ops.gemm(A[:, :M], B[:, :N], M, N, K, a_mn=True, b_mn=True, alpha=0.5, out=out, out_dtype=torch.float32, acc32=True,
+                 rowsum=rs)
+    ref = A[:, :M].float().t() @ B[:, :N].float()
+    assert (out - ref).abs().max().item() < 2e-3 * math.sqrt(K)
+    rref = A[:, :M].float().sum(0)
+    assert (rs - rref).abs().max().item() < 1e-3 * math.sqrt(K), (rs - rref).abs().max().item()
