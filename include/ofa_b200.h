@@ -14,6 +14,9 @@ extern "C" {
 
 const char* ofa_last_error(void);
 int ofa_abi_version(void);
+/* programmatic dependent launch of the library's kernels (prologue overlap with the predecessor's tail): 1 = on (default);
+ * returns the previous setting */
+int ofa_set_pdl(int enabled);
 
 /* ---- GEMM: every nn.Linear on the path, forward / dgrad / wgrad --------------------------------------------------
  * D[b](m,n) = act((sum_k A[b](m,k) B[b](n,k) + bias[n]) * alpha) + resid[b](m,n);  A,B bf16, fp32 accumulate (tcgen05).

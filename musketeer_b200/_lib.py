@@ -44,6 +44,7 @@ class OfaDecodeArgs(C.Structure):
 # name -> argtypes, exactly the prototypes of include/ofa_b200.h
 SIGNATURES = {
     "ofa_abi_version": [],
+    "ofa_set_pdl": [c_i],
     "ofa_gemm_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_p, c_f,
                       c_i, c_p, c_ll, c_ll, c_p, c_ll, c_p],
     "ofa_gemm_workspace_bytes": [c_i, c_i, c_i, c_i],
@@ -100,6 +101,8 @@ def load(path=None):
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = c_ll if name.endswith(("_bytes", "_floats")) else c_i
+    if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch
+        lib.ofa_set_pdl(int(os.environ["OFA_PDL"]))
     _lib = lib
     return lib
 

@@ -62,6 +62,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<kTmemCols>(&sm.tmem_addr);
+  pdl_sync();   // everything above is on-chip set-up; the LUT staging below reads the predecessor's output
   // token LUT slice for this query tile
   const int S_t = a.S - bz.k_text_off;
   const int i_t0 = q0 + a.q_pos_off - bz.q_text_off;
@@ -321,6 +322,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&sm.tmem_addr);
+  pdl_sync();
   // tile classification: the keys are stationary per CTA
   const bool keys_all_img = bz.img_lut != nullptr && (k0 + BK2 <= bz.n_img_k);
   const bool keys_all_txt = bz.tok_lut != nullptr && (k0 >= bz.k_text_off) && (bz.img_lut == nullptr || k0 >= bz.n_img_k);
@@ -628,6 +630,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // delta[b,h,i] = sum_d dOut . Out   (one warp per (b, i, h))
 __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                       long long ldo, long long bso, int B, int T, int H, float* __restrict__ delta) {
+  pdl_sync();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= B * T * H) return;
   const int h = gw % H, i = (gw / H) % T, b = gw / (H * T);
@@ -644,6 +647,7 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, co
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
                                            __nv_bfloat16* __restrict__ dpq, long long lddq, long long bsdq,
                                            long long lddpq, long long bsdpq, int B, int T, int H) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 elements
   const long long total = (long long)B * T * H * 16;
   if (idx >= total) return;
@@ -684,7 +688,7 @@ extern "C" int ofa_attn_fwd_tc(const AttnArgs* a, void* stream) {
     configured = true;
   }
   dim3 grid((a->T + BQ - 1) / BQ, a->H, a->B);
-  attn_fwd_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tq, tpq, tk, tpk, tv, *a);
+  OFA_CUDA(ofa_launch_pdl(attn_fwd_tc_kernel, grid, kThreads, smem, (cudaStream_t)stream, tq, tpq, tk, tpk, tv, *a));
   OFA_LAUNCH_CHECK("attn_fwd_tc_kernel");
   return 0;
 }
@@ -720,14 +724,12 @@ extern "C" int ofa_attn_bwd_tc(const AttnArgs* a, const AttnGrads* g, float* dq_
   }
   const long long nrow = (long long)a->B * a->T * a->H;
   OFA_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)nrow * 128 * sizeof(float), st));
-  attn_bwd_delta_kernel<<<(unsigned)((nrow * 32 + 255) / 256), 256, 0, st>>>(
-      (const __nv_bfloat16*)g->dout, (const __nv_bfloat16*)a->o, a->ldo, a->bso, a->B, a->T, a->H, g->delta);
+  OFA_CUDA(ofa_launch_pdl(attn_bwd_delta_kernel, (unsigned)((nrow * 32 + 255) / 256), 256, 0, st, (const __nv_bfloat16*)g->dout, (const __nv_bfloat16*)a->o, a->ldo, a->bso, a->B, a->T, a->H, g->delta));
   OFA_LAUNCH_CHECK("attn_bwd_delta_kernel");
   dim3 grid((a->S + BK2 - 1) / BK2, a->H, a->B);
-  attn_bwd_tc_kernel<<<grid, kBwdThreads, smem, st>>>(tq, tpq, tk, tpk, tv, tdo, tdq, *a, *g);
+  OFA_CUDA(ofa_launch_pdl(attn_bwd_tc_kernel, grid, kBwdThreads, smem, st, tq, tpq, tk, tpk, tv, tdo, tdq, *a, *g));
   OFA_LAUNCH_CHECK("attn_bwd_tc_kernel");
-  attn_bwd_dq_convert_kernel<<<(unsigned)((nrow * 16 + 255) / 256), 256, 0, st>>>(
-      dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H);
+  OFA_CUDA(ofa_launch_pdl(attn_bwd_dq_convert_kernel, (unsigned)((nrow * 16 + 255) / 256), 256, 0, st, dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H));
   OFA_LAUNCH_CHECK("attn_bwd_dq_convert_kernel");
   return 0;
 }

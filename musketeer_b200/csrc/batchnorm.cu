@@ -96,6 +96,7 @@ constexpr int kUnroll = 4;
 template <typename T>
 __global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x, long long R, int C, int CS,
                                                       float* __restrict__ sums) {
+  pdl_sync();
   const Map m = make_map(CS);
   float a[8], b[8];
 #pragma unroll
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x
                                                       const float* __restrict__ sums, float* __restrict__ stats,
                                                       long long R, int C, int CS, float eps, float momentum, int training,
                                                       int relu) {
+  pdl_sync();
   const Map m = make_map(CS);
   float sc[8], sh[8];
   {
@@ -191,6 +193,7 @@ template <typename T>
 __global__ void __launch_bounds__(kT, 3) bn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                           const T* __restrict__ y, const float* __restrict__ stats,
                                                           long long R, int C, int CS, int relu, float* __restrict__ sums) {
+  pdl_sync();
   const Map m = make_map(CS);
   float a[8], b[8], sc[8], sh[8];   // b accumulates sum g*x; the xhat form follows from (b - mean*a) * rstd at the end
 #pragma unroll
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict
                                                           T* __restrict__ dx, T* __restrict__ dres, T* __restrict__ dgamma,
                                                           T* __restrict__ dbeta, int accumulate, long long R, int C, int CS,
                                                           int batch_stats, int relu) {
+  pdl_sync();
   const Map m = make_map(CS);
   float ca[8], cA[8], cB[8], sc[8], sh[8];
   {
@@ -323,11 +327,11 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
   if (training) {
     OFA_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
     const Grid gs = grid_for(R, C, kUnroll);
-    bn_stats_kernel<T><<<gs.g, kT, 0, st>>>((const T*)x, R, C, gs.CS, sums);
+    OFA_CUDA(ofa_launch_pdl(bn_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, R, C, gs.CS, sums));
   }
   const Grid ga = grid_for(R, C, kUnroll);
-  bn_apply_kernel<T><<<ga.g, kT, 0, st>>>((const T*)x, (const T*)res, (T*)y, (const T*)gamma, (const T*)beta, (T*)rm, (T*)rv,
-                                          sums, stats, R, C, ga.CS, eps, momentum, training, relu);
+  OFA_CUDA(ofa_launch_pdl(bn_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)res, (T*)y, (const T*)gamma, (const T*)beta, (T*)rm, (T*)rv,
+                                          sums, stats, R, C, ga.CS, eps, momentum, training, relu));
   OFA_LAUNCH_CHECK("batchnorm forward");
   return 0;
 }
@@ -341,11 +345,11 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
     sums = ws;
     OFA_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
     const Grid gs = grid_for(R, C, 2);
-    bn_bwd_stats_kernel<T><<<gs.g, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums);
+    OFA_CUDA(ofa_launch_pdl(bn_bwd_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums));
   }
   const Grid ga = grid_for(R, C, 2);
-  bn_bwd_apply_kernel<T><<<ga.g, kT, 0, st>>>((const T*)x, (const T*)dy, (const T*)y, (const T*)gamma, stats, sums, (T*)dx,
-                                              (T*)dres, (T*)dgamma, (T*)dbeta, accumulate, R, C, ga.CS, batch_stats, relu);
+  OFA_CUDA(ofa_launch_pdl(bn_bwd_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, (const T*)gamma, stats, sums, (T*)dx,
+                                              (T*)dres, (T*)dgamma, (T*)dbeta, accumulate, R, C, ga.CS, batch_stats, relu));
   OFA_LAUNCH_CHECK("batchnorm backward");
   return 0;
 }

@@ -30,6 +30,29 @@ int ofa_set_error(const char* fmt, ...);
 // dtype enum shared with include/ofa_b200.h
 enum { OFA_F32 = 0, OFA_BF16 = 1, OFA_F32_ACC = 2 /* GEMM output only: D (fp32) += result */ };
 
+// Programmatic dependent launch: kernels launched through ofa_launch_pdl may be scheduled while their predecessor in the
+// stream is still draining; they run their on-chip prologue (barrier init, TMEM allocation, descriptor prefetch) and then
+// block in pdl_sync() until the predecessor's memory is visible.  ONLY kernels that call pdl_sync() before their first
+// global-memory access may be launched this way.  g_ofa_pdl = 0 turns the attribute off (A/B switch).
+extern int g_ofa_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t ofa_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_ofa_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 // host: encode a tiled tensor map (driver entry point resolved at runtime; no libcuda link dependency)
 int ofa_make_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int swizzle128, int elem_bytes);

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // on-chip set-up done; from here on the kernel touches global memory
   const uint32_t tmem_base = sm.tmem_addr;
 
   if (warp == 0) {
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_wgrad_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();   // on-chip set-up done; from here on the kernel touches global memory
   const uint32_t tmem_base = sm.tmem_addr;
   const int per_img = p.tiles_w * p.tiles_h;
 
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_wgrad_kernel(const __grid
 // dW[co][tap][ci] (bf16, channels-last weight layout) = (accumulate ? dW : 0) + sum_sp ws[sp][tap][co][ci]
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ dw,
                                                                 int splits, int Cout, int Cin, int accumulate) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [tap][co][ci]
   const long long per = 9LL * Cout * Cin;
   if (idx >= per) return;
@@ -381,7 +384,7 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<p.total < kNumSMs ? p.total : kNumSMs, kThreads, smem, st>>>(ta, tb, td, p);
+  OFA_CUDA(ofa_launch_pdl(kern, p.total < kNumSMs ? p.total : kNumSMs, kThreads, smem, st, ta, tb, td, p));
   OFA_LAUNCH_CHECK("conv3x3_kernel");
   return 0;
 }
@@ -395,7 +398,7 @@ int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMa
     OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<p.total < kNumSMs ? p.total : kNumSMs, kThreads, smem, st>>>(tdy, tx, tdw, p);
+  OFA_CUDA(ofa_launch_pdl(kern, p.total < kNumSMs ? p.total : kNumSMs, kThreads, smem, st, tdy, tx, tdw, p));
   OFA_LAUNCH_CHECK("conv3x3_wgrad_kernel");
   return 0;
 }
@@ -493,7 +496,7 @@ extern "C" int ofa_conv3x3_wgrad_bf16(const void* x, const void* dy, void* dw, i
   else rc = launch_wgrad<64>(tdy, tx, tdw, p, st);
   if (rc || reduce) return rc;
   const long long n = 9LL * Cout * Cin;
-  conv_wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, (__nv_bfloat16*)dw, p.splits, Cout, Cin, accumulate);
+  OFA_CUDA(ofa_launch_pdl(conv_wgrad_reduce_kernel, (unsigned)((n + 255) / 256), 256, 0, st, p.ws, (__nv_bfloat16*)dw, p.splits, Cout, Cin, accumulate));
   OFA_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
   return 0;
 }

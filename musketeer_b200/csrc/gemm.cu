@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
+  pdl_sync();   // on-chip set-up done; from here on the kernel touches global memory
   const uint32_t tmem_base = sm.tmem_addr;
 
   if (warp == 0) {
@@ -534,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  pdl_sync();
   const uint32_t tmem_base = sm.tmem_addr;
 
   if (warp == 0) {
@@ -683,6 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
 // out[b][m][n] = epi(sum_sp ws[sp][b][m][n])
 template <typename OutT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (long long)p.M * p.N;
   if (idx >= per * p.batch) return;
@@ -713,18 +716,20 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_ofa_pdl ? 2 : 1;
   OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
   OFA_LAUNCH_CHECK("gemm_tc2_kernel");
   if (p.splits > 1 && !p.reduce_f32) {
     const long long n = (long long)p.M * p.N;
-    splitk_reduce_kernel<OutT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    OFA_CUDA(ofa_launch_pdl(splitk_reduce_kernel<OutT>, (unsigned)((n + 255) / 256), 256, 0, st, p));
     OFA_LAUNCH_CHECK("splitk_reduce_kernel");
   }
   return 0;
@@ -747,21 +752,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_ofa_pdl ? 2 : 1;
     OFA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
   } else {
-    kern<<<total < kNumSMs ? total : kNumSMs, kThreads, smem, st>>>(ta, tb, td, p);
+    OFA_CUDA(ofa_launch_pdl(kern, total < kNumSMs ? total : kNumSMs, kThreads, smem, st, ta, tb, td, p));
   }
   OFA_LAUNCH_CHECK("gemm_tc_kernel");
   if (p.splits > 1 && !p.reduce_f32) {
     const long long n = (long long)p.M * p.N * p.batch;
-    splitk_reduce_kernel<OutT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    OFA_CUDA(ofa_launch_pdl(splitk_reduce_kernel<OutT>, (unsigned)((n + 255) / 256), 256, 0, st, p));
     OFA_LAUNCH_CHECK("splitk_reduce_kernel");
   }
   return 0;

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, co
                                                      T* __restrict__ y, float* __restrict__ mean_out,
                                                      float* __restrict__ rstd_out, int rows, int C, float eps,
                                                      int gelu_in) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= rows) return;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_ker
   // U = rows per iteration: 2 for the plain variant up to 2048 columns (latency-bound), 1 otherwise (GELU is erf-bound)
   // blockDim.x = ceil(C/8) rounded up to a warp: thread t owns columns 8t..8t+7 of every row this CTA visits, so the
   // dgamma / dbeta partials need no cross-thread reduction; erf is evaluated once per element (GELU value and derivative).
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   __shared__ float red[2][4][16];
   const int c = threadIdx.x * 8;
@@ -236,6 +238,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b,
                                                             int nparts, int C, T* __restrict__ dgamma, T* __restrict__ dbeta,
                                                             int accumulate) {
+  pdl_sync();
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const float* src = blockIdx.y ? part_b : part_g;
@@ -397,8 +400,8 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
 template <typename T, int NV>
 int ln_fwd_launch(const void* x, const void* g, const void* b, const void* r, void* y, float* mean, float* rstd,
                   int rows, int C, float eps, int gelu_in, cudaStream_t st) {
-  ln_fwd_kernel<T, NV><<<(rows + 3) / 4, 128, 0, st>>>((const T*)x, (const T*)g, (const T*)b, (const T*)r, (T*)y, mean,
-                                                       rstd, rows, C, eps, gelu_in);
+  OFA_CUDA(ofa_launch_pdl(ln_fwd_kernel<T, NV>, (rows + 3) / 4, 128, 0, st, (const T*)x, (const T*)g, (const T*)b, (const T*)r, (T*)y, mean,
+                                                       rstd, rows, C, eps, gelu_in));
   OFA_LAUNCH_CHECK("ln_fwd_kernel");
   return 0;
 }
@@ -407,11 +410,11 @@ int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mea
                   float* pg, float* pb, int nparts, int rows, int C, int gelu_in, cudaStream_t st) {
   const int threads = ((C / 8 + 31) / 32) * 32;
   if (gelu_in)
-    ln_bwd_kernel<T, 1, 1><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C);
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 1, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
   else if (threads <= 256)
-    ln_bwd_kernel<T, 0, 2><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C);
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 0, 2>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
   else
-    ln_bwd_kernel<T, 0, 1><<<nparts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C);
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 0, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
   OFA_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
 }
@@ -477,11 +480,11 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   if (dtype == OFA_BF16) {
     rc = ln_bwd_launch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st);
     if (rc) return rc;
-    ln_bwd_reduce_kernel<__nv_bfloat16><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<__nv_bfloat16>, dim3((C + 31) / 32, 2), 256, 0, st, pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate));
   } else if (dtype == OFA_F32) {
     rc = ln_bwd_launch<float>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st);
     if (rc) return rc;
-    ln_bwd_reduce_kernel<float><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate);
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<float>, dim3((C + 31) / 32, 2), 256, 0, st, pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate));
   } else {
     return ofa_set_error("ofa_layernorm_bwd: bad dtype %d", dtype);
   }

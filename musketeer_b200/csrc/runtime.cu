@@ -18,6 +18,13 @@ extern "C" const char* ofa_last_error() { return g_ofa_err; }
 
 extern "C" int ofa_abi_version() { return 1; }
 
+int g_ofa_pdl = 1;
+extern "C" int ofa_set_pdl(int enabled) {
+  const int old = g_ofa_pdl;
+  g_ofa_pdl = enabled;
+  return old;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
