@@ -51,6 +51,7 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
 
 template <typename T>
 __global__ void __launch_bounds__(kT) attn_decode_kernel(OfaDecodeArgs a) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* qs = smem;                     // [G][128]  q | pos_q of the group's rows, this head
   float* ps = smem + a.G * 128;         // [G][S]    scores, then probabilities
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(kT) attn_decode_kernel(OfaDecodeArgs a) {
 template <typename T>
 __global__ void cache_gather_kernel(const T* __restrict__ src, T* __restrict__ dst, const long long* __restrict__ order,
                                     int rows, int L, int D, long long row_stride, long long plane_stride) {
+  pdl_sync();
   const int r = blockIdx.x, p = blockIdx.y;
   const long long so = (long long)p * plane_stride + order[r] * row_stride;
   const long long d_o = (long long)p * plane_stride + (long long)r * row_stride;
@@ -240,14 +242,14 @@ extern "C" int ofa_attn_decode(const OfaDecodeArgs* a, int dtype, void* stream) 
       OFA_CUDA(cudaFuncSetAttribute(attn_decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
     }
-    attn_decode_kernel<__nv_bfloat16><<<grid, kT, smem, st>>>(*a);
+    OFA_CUDA(ofa_launch_pdl(attn_decode_kernel<__nv_bfloat16>, grid, kT, smem, st, *a));
   } else if (dtype == OFA_F32) {
     static bool configured = false;
     if (!configured) {
       OFA_CUDA(cudaFuncSetAttribute(attn_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       configured = true;
     }
-    attn_decode_kernel<float><<<grid, kT, smem, st>>>(*a);
+    OFA_CUDA(ofa_launch_pdl(attn_decode_kernel<float>, grid, kT, smem, st, *a));
   } else {
     return ofa_set_error("ofa_attn_decode: bad dtype %d", dtype);
   }
@@ -264,10 +266,10 @@ extern "C" int ofa_cache_gather(const void* src, void* dst, const long long* ord
   dim3 grid(rows, planes);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == OFA_BF16)
-    cache_gather_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, order, rows, L, D,
-                                                             row_stride, plane_stride);
+    OFA_CUDA(ofa_launch_pdl(cache_gather_kernel<__nv_bfloat16>, grid, 128, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, order, rows, L, D,
+                                                             row_stride, plane_stride));
   else if (dtype == OFA_F32)
-    cache_gather_kernel<float><<<grid, 128, 0, st>>>((const float*)src, (float*)dst, order, rows, L, D, row_stride, plane_stride);
+    OFA_CUDA(ofa_launch_pdl(cache_gather_kernel<float>, grid, 128, 0, st, (const float*)src, (float*)dst, order, rows, L, D, row_stride, plane_stride));
   else
     return ofa_set_error("ofa_cache_gather: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("cache_gather_kernel");

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) dropout_residual_kernel(const T* __restri
                                                                T* __restrict__ y, long long n, int C, int rows_per_sample,
                                                                float p, const float* __restrict__ row_scale,
                                                                const unsigned long long* __restrict__ seed) {
+  pdl_sync();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
   const long long i0 = v * 4;
   if (i0 >= n) return;
@@ -57,9 +58,9 @@ extern "C" int ofa_dropout_residual(const void* x, const void* resid, void* y, l
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)(((n + 3) / 4 + 255) / 256);
   if (dtype == OFA_BF16)
-    dropout_residual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)resid, (__nv_bfloat16*)y, n, C, rows_per_sample, p, row_scale, seed);
+    OFA_CUDA(ofa_launch_pdl(dropout_residual_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)resid, (__nv_bfloat16*)y, n, C, rows_per_sample, p, row_scale, seed));
   else if (dtype == OFA_F32)
-    dropout_residual_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)resid, (float*)y, n, C, rows_per_sample, p, row_scale, seed);
+    OFA_CUDA(ofa_launch_pdl(dropout_residual_kernel<float>, grid, 256, 0, st, (const float*)x, (const float*)resid, (float*)y, n, C, rows_per_sample, p, row_scale, seed));
   else
     return ofa_set_error("ofa_dropout_residual: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("dropout_residual_kernel");

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
                                                          int cs, int ce, int rdrop, float reg_alpha,
                                                          float* __restrict__ loss_out, float* __restrict__ nll_out,
                                                          float* __restrict__ kl_out) {
+  pdl_sync();
   __shared__ float sh[kThreads / 32];
   const int half = rdrop ? R / 2 : R;
   const int r0 = blockIdx.x;  // < half
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
 template <typename T>
 __global__ void scale_rows_kernel(T* __restrict__ x, long long ld, int V, const float* __restrict__ scale,
                                   const unsigned char* __restrict__ row_keep) {
+  pdl_sync();
   const int r = blockIdx.x;
   const float s = (row_keep && !row_keep[r]) ? 0.f : *scale;
   T* xr = x + (size_t)r * ld;
@@ -186,9 +188,9 @@ extern "C" int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* ta
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = rdrop ? R / 2 : R;
   if (dtype == OFA_BF16)
-    ls_ce_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((__nv_bfloat16*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows);
+    OFA_CUDA(ofa_launch_pdl(ls_ce_kernel<__nv_bfloat16>, grid, kThreads, 0, st, (__nv_bfloat16*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows));
   else if (dtype == OFA_F32)
-    ls_ce_kernel<float><<<grid, kThreads, 0, st>>>((float*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows);
+    OFA_CUDA(ofa_launch_pdl(ls_ce_kernel<float>, grid, kThreads, 0, st, (float*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows));
   else
     return ofa_set_error("ofa_ls_ce_fwd_bwd: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("ls_ce_kernel");
@@ -200,8 +202,8 @@ extern "C" int ofa_scale_rows(void* x, long long ld, int R, int V, const float* 
                               int dtype, void* stream) {
   OFA_CHECK(R > 0 && V > 0, "ofa_scale_rows: R=%d V=%d", R, V);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == OFA_BF16) scale_rows_kernel<__nv_bfloat16><<<R, 512, 0, st>>>((__nv_bfloat16*)x, ld, V, scale, row_keep);
-  else if (dtype == OFA_F32) scale_rows_kernel<float><<<R, 512, 0, st>>>((float*)x, ld, V, scale, row_keep);
+  if (dtype == OFA_BF16) OFA_CUDA(ofa_launch_pdl(scale_rows_kernel<__nv_bfloat16>, R, 512, 0, st, (__nv_bfloat16*)x, ld, V, scale, row_keep));
+  else if (dtype == OFA_F32) OFA_CUDA(ofa_launch_pdl(scale_rows_kernel<float>, R, 512, 0, st, (float*)x, ld, V, scale, row_keep));
   else return ofa_set_error("ofa_scale_rows: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("scale_rows_kernel");
   return 0;

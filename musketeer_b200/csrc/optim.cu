@@ -43,6 +43,7 @@ __device__ __forceinline__ float block_sum(float v) {
 // partial[chunk] = sum g^2 (unscaled); deterministic: a fixed tree per chunk, the chunk sums are added in order later
 template <typename T>
 __global__ void __launch_bounds__(kT) sqnorm_kernel(const Chunk* __restrict__ table, float* __restrict__ partial) {
+  pdl_sync();
   const Chunk c = table[blockIdx.x];
   const T* g = reinterpret_cast<const T*>(c.grad);
   float s = 0.f;
@@ -71,6 +72,7 @@ struct AdamArgs {
 template <typename T>
 __global__ void __launch_bounds__(kT) adam_kernel(const Chunk* __restrict__ table, const float* __restrict__ partial,
                                                   float* __restrict__ grad_norm_out, AdamArgs a) {
+  pdl_sync();
   // every CTA re-derives the global norm from the per-chunk partials (a few thousand floats out of L2): same order in
   // every CTA and every run, no extra launch, no host round trip
   float s = 0.f;
@@ -111,11 +113,11 @@ extern "C" int ofa_adam_step(const void* chunk_table, int n_chunks, float* parti
   a.grad_scale = grad_scale; a.clip_norm = clip_norm; a.n_chunks = n_chunks;
   const Chunk* t = reinterpret_cast<const Chunk*>(chunk_table);
   if (param_dtype == OFA_BF16) {
-    sqnorm_kernel<__nv_bfloat16><<<n_chunks, kT, 0, st>>>(t, partial_sqnorm);
-    adam_kernel<__nv_bfloat16><<<n_chunks, kT, 0, st>>>(t, partial_sqnorm, grad_norm_out, a);
+    OFA_CUDA(ofa_launch_pdl(sqnorm_kernel<__nv_bfloat16>, n_chunks, kT, 0, st, t, partial_sqnorm));
+    OFA_CUDA(ofa_launch_pdl(adam_kernel<__nv_bfloat16>, n_chunks, kT, 0, st, t, partial_sqnorm, grad_norm_out, a));
   } else if (param_dtype == OFA_F32) {
-    sqnorm_kernel<float><<<n_chunks, kT, 0, st>>>(t, partial_sqnorm);
-    adam_kernel<float><<<n_chunks, kT, 0, st>>>(t, partial_sqnorm, grad_norm_out, a);
+    OFA_CUDA(ofa_launch_pdl(sqnorm_kernel<float>, n_chunks, kT, 0, st, t, partial_sqnorm));
+    OFA_CUDA(ofa_launch_pdl(adam_kernel<float>, n_chunks, kT, 0, st, t, partial_sqnorm, grad_norm_out, a));
   } else {
     return ofa_set_error("ofa_adam_step: bad dtype %d", param_dtype);
   }

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long ld, int rows, int C,
                                                              float* __restrict__ part, int vec_ok) {
+  pdl_sync();
   // block = 32 lanes (8 consecutive columns each -> 256 columns) x 8 row-lanes; grid.x = column tiles, grid.y = row slices
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + cx * 8;
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
 template <typename T>
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int C, T* __restrict__ out, float alpha,
                                     int accumulate) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
@@ -313,6 +315,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, 
 template <typename T>
 __global__ void embed_gather_kernel(const long long* __restrict__ idx, const T* __restrict__ table,
                                     const T* __restrict__ addvec, T* __restrict__ out, long long ldo, int rows, int C) {
+  pdl_sync();
   const int row = blockIdx.x;
   const T* src = table + (size_t)idx[row] * C;
   T* dst = out + (size_t)row * ldo;
@@ -335,6 +338,7 @@ __device__ __forceinline__ void atomic_add2(__nv_bfloat16* p, float a, float b) 
 template <typename T>
 __global__ void embed_scatter_add_kernel(const long long* __restrict__ idx, const T* __restrict__ dout, long long ldo,
                                          T* __restrict__ dtable, int rows, int C, long long skip_idx) {
+  pdl_sync();
   const int row = blockIdx.x;
   const long long id = idx[row];
   if (id == skip_idx) return;  // padding_idx rows receive no gradient (nn.Embedding semantics)
@@ -350,6 +354,7 @@ __global__ void embed_scatter_add_kernel(const long long* __restrict__ idx, cons
 // ------------------------------------------------------------------------------------------------
 __global__ void split3_kernel(const float* __restrict__ x, long long ldx, int rows, int C, __nv_bfloat16* __restrict__ out,
                               long long ldo, long long blk_stride, int pattern) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * C) return;
   const int r = (int)(i / C), c = (int)(i % C);
@@ -368,6 +373,7 @@ __global__ void split3_kernel(const float* __restrict__ x, long long ldx, int ro
 // out = a + b  |  out = a * rowmask (zero padded rows)  -- glue that has no natural producer to fuse into yet
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+  pdl_sync();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float x[8], y[8];
@@ -382,17 +388,20 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
 }
 template <typename T>
 __global__ void mask_rows_kernel(T* __restrict__ x, const unsigned char* __restrict__ rowmask, int rows, int C) {
+  pdl_sync();
   const int row = blockIdx.x;
   if (!rowmask[row]) return;
   for (int c = threadIdx.x; c < C; c += blockDim.x) x[(size_t)row * C + c] = (T)0.f;
 }
 template <typename T>
 __global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = (T)gelu_erf((float)x[i]);
 }
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dx[i] = (T)((float)dy[i] * gelu_grad((float)x[i]));
 }
@@ -502,11 +511,11 @@ extern "C" int ofa_colsum(const void* x, long long ld, int rows, int C, void* ou
   const int esz = dtype == OFA_BF16 ? 2 : 4;
   const int vec_ok = (((uintptr_t)x & 15) == 0) && ((ld * esz) % 16 == 0);
   if (dtype == OFA_BF16) {
-    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, workspace, vec_ok);
-    colsum_final_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (__nv_bfloat16*)out, alpha, accumulate);
+    OFA_CUDA(ofa_launch_pdl(colsum_partial_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, ld, rows, C, workspace, vec_ok));
+    OFA_CUDA(ofa_launch_pdl(colsum_final_kernel<__nv_bfloat16>, (C + 127) / 128, 128, 0, st, workspace, ny, C, (__nv_bfloat16*)out, alpha, accumulate));
   } else if (dtype == OFA_F32) {
-    colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, C, workspace, vec_ok && (ld * 4) % 32 == 0 && ((uintptr_t)x & 31) == 0);
-    colsum_final_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(workspace, ny, C, (float*)out, alpha, accumulate);
+    OFA_CUDA(ofa_launch_pdl(colsum_partial_kernel<float>, grid, 256, 0, st, (const float*)x, ld, rows, C, workspace, vec_ok && (ld * 4) % 32 == 0 && ((uintptr_t)x & 31) == 0));
+    OFA_CUDA(ofa_launch_pdl(colsum_final_kernel<float>, (C + 127) / 128, 128, 0, st, workspace, ny, C, (float*)out, alpha, accumulate));
   } else {
     return ofa_set_error("ofa_colsum: bad dtype %d", dtype);
   }
@@ -519,9 +528,9 @@ extern "C" int ofa_embed_gather(const long long* idx, const void* table, const v
   OFA_CHECK(rows > 0 && C % 8 == 0, "ofa_embed_gather: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == OFA_BF16)
-    embed_gather_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(idx, (const __nv_bfloat16*)table, (const __nv_bfloat16*)addvec, (__nv_bfloat16*)out, ldo, rows, C);
+    OFA_CUDA(ofa_launch_pdl(embed_gather_kernel<__nv_bfloat16>, rows, 128, 0, st, idx, (const __nv_bfloat16*)table, (const __nv_bfloat16*)addvec, (__nv_bfloat16*)out, ldo, rows, C));
   else if (dtype == OFA_F32)
-    embed_gather_kernel<float><<<rows, 128, 0, st>>>(idx, (const float*)table, (const float*)addvec, (float*)out, ldo, rows, C);
+    OFA_CUDA(ofa_launch_pdl(embed_gather_kernel<float>, rows, 128, 0, st, idx, (const float*)table, (const float*)addvec, (float*)out, ldo, rows, C));
   else
     return ofa_set_error("ofa_embed_gather: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("embed_gather_kernel");
@@ -533,9 +542,9 @@ extern "C" int ofa_embed_scatter_add(const long long* idx, const void* dout, lon
   OFA_CHECK(rows > 0 && C % 2 == 0, "ofa_embed_scatter_add: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == OFA_BF16)
-    embed_scatter_add_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(idx, (const __nv_bfloat16*)dout, ldo, (__nv_bfloat16*)dtable, rows, C, skip_idx);
+    OFA_CUDA(ofa_launch_pdl(embed_scatter_add_kernel<__nv_bfloat16>, rows, 128, 0, st, idx, (const __nv_bfloat16*)dout, ldo, (__nv_bfloat16*)dtable, rows, C, skip_idx));
   else if (dtype == OFA_F32)
-    embed_scatter_add_kernel<float><<<rows, 128, 0, st>>>(idx, (const float*)dout, ldo, (float*)dtable, rows, C, skip_idx);
+    OFA_CUDA(ofa_launch_pdl(embed_scatter_add_kernel<float>, rows, 128, 0, st, idx, (const float*)dout, ldo, (float*)dtable, rows, C, skip_idx));
   else
     return ofa_set_error("ofa_embed_scatter_add: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("embed_scatter_add_kernel");
@@ -546,7 +555,7 @@ extern "C" int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, v
                                long long blk_stride, int pattern, void* stream) {
   OFA_CHECK(rows > 0 && C > 0, "ofa_split3_bf16: rows=%d C=%d", rows, C);
   const long long n = (long long)rows * C;
-  split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, (__nv_bfloat16*)out, ldo, blk_stride, pattern);
+  OFA_CUDA(ofa_launch_pdl(split3_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, x, ldx, rows, C, (__nv_bfloat16*)out, ldo, blk_stride, pattern));
   OFA_LAUNCH_CHECK("split3_kernel");
   return 0;
 }
@@ -555,8 +564,8 @@ extern "C" int ofa_add(const void* a, const void* b, void* out, long long n, int
   OFA_CHECK(n > 0, "ofa_add: n=%lld", n);
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((n + 2047) / 2048);
-  if (dtype == OFA_BF16) add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
-  else if (dtype == OFA_F32) add_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n);
+  if (dtype == OFA_BF16) OFA_CUDA(ofa_launch_pdl(add_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n));
+  else if (dtype == OFA_F32) OFA_CUDA(ofa_launch_pdl(add_kernel<float>, grid, 256, 0, st, (const float*)a, (const float*)b, (float*)out, n));
   else return ofa_set_error("ofa_add: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("add_kernel");
   return 0;
@@ -565,8 +574,8 @@ extern "C" int ofa_add(const void* a, const void* b, void* out, long long n, int
 extern "C" int ofa_mask_rows(void* x, const unsigned char* rowmask, int rows, int C, int dtype, void* stream) {
   OFA_CHECK(rows > 0 && C > 0, "ofa_mask_rows: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == OFA_BF16) mask_rows_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>((__nv_bfloat16*)x, rowmask, rows, C);
-  else if (dtype == OFA_F32) mask_rows_kernel<float><<<rows, 128, 0, st>>>((float*)x, rowmask, rows, C);
+  if (dtype == OFA_BF16) OFA_CUDA(ofa_launch_pdl(mask_rows_kernel<__nv_bfloat16>, rows, 128, 0, st, (__nv_bfloat16*)x, rowmask, rows, C));
+  else if (dtype == OFA_F32) OFA_CUDA(ofa_launch_pdl(mask_rows_kernel<float>, rows, 128, 0, st, (float*)x, rowmask, rows, C));
   else return ofa_set_error("ofa_mask_rows: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("mask_rows_kernel");
   return 0;
@@ -577,11 +586,11 @@ extern "C" int ofa_gelu(const void* x, const void* dy, void* out, long long n, i
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (dtype == OFA_BF16) {
-    if (backward) gelu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)out, n);
-    else gelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n);
+    if (backward) OFA_CUDA(ofa_launch_pdl(gelu_bwd_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)out, n));
+    else OFA_CUDA(ofa_launch_pdl(gelu_fwd_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, n));
   } else if (dtype == OFA_F32) {
-    if (backward) gelu_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)dy, (float*)out, n);
-    else gelu_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, n);
+    if (backward) OFA_CUDA(ofa_launch_pdl(gelu_bwd_kernel<float>, grid, 256, 0, st, (const float*)x, (const float*)dy, (float*)out, n));
+    else OFA_CUDA(ofa_launch_pdl(gelu_fwd_kernel<float>, grid, 256, 0, st, (const float*)x, (float*)out, n));
   } else return ofa_set_error("ofa_gelu: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("gelu_kernel");
   return 0;
