@@ -72,7 +72,9 @@ int ofa_dropout_residual(const void* x, const void* resid, void* y, long long n,
 
 /* ---- BatchNorm2d (+ReLU, +residual) on NHWC activations viewed as [R = N*H*W, C]; training-mode batch statistics with
  * running-stat update (momentum, unbiased variance), or eval / frozen mode (models/ofa/resnet.py:113-133,211-220,
- * frozen_bn.py:36-57).  stats = 4*C floats (mean | rstd | scale | shift); mean and rstd feed the backward.            */
+ * frozen_bn.py:36-57).  stats = 4*C floats (mean | rstd | scale | shift); mean and rstd feed the backward.
+ * workspace: ofa_batchnorm_workspace_floats() floats that are ZERO ON ENTRY; the kernels leave them zero again, so one
+ * zero-initialised scratch per stream serves every call (no memset per layer).                                         */
 long long ofa_batchnorm_workspace_floats(int C);
 int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* running_mean,
                       void* running_var, long long R, int C, float eps, float momentum, int training, int relu,

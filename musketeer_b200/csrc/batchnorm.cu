@@ -90,6 +90,25 @@ __device__ __forceinline__ void block_accumulate(const Map& m, int C, int CS, co
   }
 }
 
+// The per-channel sums live in a caller-provided scratch that is ZERO ON ENTRY and LEFT ZERO ON EXIT: every CTA of the apply
+// kernel bumps a counter once it has read the sums, and the last one clears sums and counter for the next BatchNorm call in
+// the stream (no memset node per layer; 752 of them per training step before).  scratch = [2*C sums | ... | counter @ 2*kMaxC].
+constexpr int kMaxC = 2048;
+__device__ __forceinline__ void release_sums(float* __restrict__ sums, int C) {
+  __shared__ int last;
+  __syncthreads();                       // every thread of this CTA has read its sums
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* counter = reinterpret_cast<unsigned int*>(sums + 2 * kMaxC);
+    const unsigned int total = gridDim.x * gridDim.y;
+    last = atomicAdd(counter, 1u) == total - 1;
+    if (last) *counter = 0u;
+  }
+  __syncthreads();
+  if (last)
+    for (int c = threadIdx.x; c < 2 * C; c += kT) sums[c] = 0.f;
+}
+
 constexpr int kUnroll = 4;
 
 // forward statistics: sums[0][c] += sum x, sums[1][c] += sum x^2
@@ -160,6 +179,7 @@ __global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x
       }
     }
   }
+  if (training) release_sums(const_cast<float*>(sums), C);
   for (long long r = m.r0; r < R; r += kUnroll * m.stride) {
     typename V8<T>::Raw rx[kUnroll], rr[kUnroll];
 #pragma unroll
@@ -267,6 +287,7 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict
       }
     }
   }
+  if (sums) release_sums(const_cast<float*>(sums), C);
   constexpr int U = 2;
   for (long long r = m.r0; r < R; r += U * m.stride) {
     typename V8<T>::Raw rx[U], rg[U], ry_[U];
@@ -325,7 +346,6 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
              cudaStream_t st) {
   float* sums = ws;
   if (training) {
-    OFA_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
     const Grid gs = grid_for(R, C, kUnroll);
     OFA_CUDA(ofa_launch_pdl(bn_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, R, C, gs.CS, sums));
   }
@@ -343,7 +363,6 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
   float* sums = nullptr;
   if (batch_stats || dgamma) {   // frozen statistics without parameter gradients need no reduction at all
     sums = ws;
-    OFA_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
     const Grid gs = grid_for(R, C, 2);
     OFA_CUDA(ofa_launch_pdl(bn_bwd_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums));
   }
@@ -356,9 +375,10 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
 
 }  // namespace
 
-// scratch floats for either direction (partials + coefficients); `stats` of the forward is 4*C floats
+// scratch floats for either direction: ZERO ON ENTRY, left zero on exit (allocate once with zeros and reuse it for every
+// call in the stream); `stats` of the forward is 4*C floats
 // (mean | rstd | scale | shift), of which mean and rstd are the backward's inputs
-extern "C" long long ofa_batchnorm_workspace_floats(int C) { return 2LL * C; }
+extern "C" long long ofa_batchnorm_workspace_floats(int C) { (void)C; return 2LL * kMaxC + 32; }
 
 extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                                  void* running_mean, void* running_var, long long R, int C, float eps, float momentum,

@@ -518,6 +518,18 @@ def mask_rows(x, rowmask):
     return _MaskRows.apply(x, rowmask)
 
 
+_BN_SCRATCH = {}
+
+
+def _bn_scratch(device):
+    """The self-cleaning per-channel sum scratch of the BatchNorm kernels: zero on entry, left zero by the kernels."""
+    key = (device.type, device.index)
+    ws = _BN_SCRATCH.get(key)
+    if ws is None:
+        ws = _BN_SCRATCH[key] = torch.zeros(_lib.load().ofa_batchnorm_workspace_floats(0), dtype=torch.float32, device=device)
+    return ws
+
+
 class _BatchNorm(torch.autograd.Function):
     """x: conv output, logically [N,C,H,W] in channels_last memory format (== [N*H*W, C] row-major)."""
 
@@ -530,7 +542,7 @@ class _BatchNorm(torch.autograd.Function):
         y = torch.empty_like(x, memory_format=torch.channels_last)
         R = N * Hh * Ww
         stats = torch.empty(4 * Cc, dtype=torch.float32, device=x.device)
-        ws = torch.empty(_lib.load().ofa_batchnorm_workspace_floats(Cc), dtype=torch.float32, device=x.device)
+        ws = _bn_scratch(x.device)
         call("ofa_batchnorm_fwd", _p(x), _p(res), _p(y), _p(gamma), _p(beta), _p(running_mean), _p(running_var), R, Cc,
              float(eps), float(momentum), int(training), int(relu), _p(stats), _p(ws), _dt(x), _st(),
              work=("byte", (2 + training + (res is not None)) * R * Cc * x.element_size()))
@@ -556,7 +568,7 @@ class _BatchNorm(torch.autograd.Function):
             fused = tg is not None and tb is not None and ag == ab
             dg = tg if fused else torch.empty_like(gamma)
             db = tb if fused else torch.empty_like(gamma)
-        ws = torch.empty(_lib.load().ofa_batchnorm_workspace_floats(Cc), dtype=torch.float32, device=x.device)
+        ws = _bn_scratch(x.device)
         call("ofa_batchnorm_bwd", _p(x), _p(dy), _p(y), _p(gamma), _p(stats), _p(dx), _p(dres), _p(dg), _p(db),
              int(fused and ag), R, Cc, int(ctx.training), int(ctx.relu), _p(ws), _dt(x), _st(),
              work=("byte", (4 + 2 * ctx.relu + ctx.has_res) * R * Cc * x.element_size()))
