@@ -32,7 +32,8 @@ int ofa_set_pdl(int enabled);
 int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int batch, long long lda, long long ldb,
                   long long ldd, long long stride_a, long long stride_b, long long stride_d, int a_mn_major,
                   int b_mn_major, int out_dtype, const void* bias, float alpha, int act, const void* resid,
-                  long long ldr, long long stride_r, void* workspace, long long workspace_bytes, void* stream);
+                  long long ldr, long long stride_r, void* workspace, long long workspace_bytes, int alpha_cols,
+                  void* stream);   /* alpha_cols > 0: alpha scales output columns < alpha_cols only (fused q|k|v projection) */
 /* host helper: bytes of fp32 split-K scratch the call above wants for this problem (0 = none; passing less is legal) */
 long long ofa_gemm_workspace_bytes(int M, int N, int K, int batch);
 /* kernel variant switch (A/B testing): 0 single-CTA tiles, 1 CTA pair with TMA-multicast B, 2 cta_group::2 MMA on
@@ -175,6 +176,8 @@ typedef struct {
   float* delta;                     /* [B,H,T] workspace; sum over rows / c_attn[h] = d c_attn[h] */
   float* P;                         /* SIMT path: [B,H,T,S] fp32 workspace */
   float* dS;                        /* SIMT path: [B,H,T,S] fp32 workspace */
+  float dq_scale;                   /* tcgen05 path: dq (not dpq) is multiplied by this on its way out (the softmax scaling
+                                       of a q that came unscaled-in-weights from a fused q|k|v projection); 0 means 1 */
 } OfaAttnGrads;
 
 int ofa_attn_fwd_simt(const OfaAttnArgs* args, int dtype, void* stream);

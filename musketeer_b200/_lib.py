@@ -29,7 +29,7 @@ class OfaAttnGrads(C.Structure):
     _fields_ = [("dout", c_p), ("dq", c_p), ("dpq", c_p), ("dk", c_p), ("dpk", c_p), ("dv", c_p),
                 ("lddq", c_ll), ("lddpq", c_ll), ("lddk", c_ll), ("lddpk", c_ll), ("lddv", c_ll),
                 ("bsdq", c_ll), ("bsdpq", c_ll), ("bsdk", c_ll), ("bsdpk", c_ll), ("bsdv", c_ll),
-                ("dtok_lut", c_p), ("dimg_lut", c_p), ("delta", c_p), ("P", c_p), ("dS", c_p)]
+                ("dtok_lut", c_p), ("dimg_lut", c_p), ("delta", c_p), ("P", c_p), ("dS", c_p), ("dq_scale", c_f)]
 
 
 class OfaDecodeArgs(C.Structure):
@@ -46,7 +46,7 @@ SIGNATURES = {
     "ofa_abi_version": [],
     "ofa_set_pdl": [c_i],
     "ofa_gemm_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_p, c_f,
-                      c_i, c_p, c_ll, c_ll, c_p, c_ll, c_p],
+                      c_i, c_p, c_ll, c_ll, c_p, c_ll, c_i, c_p],
     "ofa_gemm_workspace_bytes": [c_i, c_i, c_i, c_i],
     "ofa_gemm_set_pair_mode": [c_i],
     "ofa_gemm_set_tma_store": [c_i],

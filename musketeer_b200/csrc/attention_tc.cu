@@ -646,13 +646,14 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, co
 // dq_acc [B,T,H,128] fp32 -> dq, dpq [B,T,H*64] bf16
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
                                            __nv_bfloat16* __restrict__ dpq, long long lddq, long long bsdq,
-                                           long long lddpq, long long bsdpq, int B, int T, int H) {
+                                           long long lddpq, long long bsdpq, int B, int T, int H, float dq_scale) {
   pdl_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 elements
   const long long total = (long long)B * T * H * 16;
   if (idx >= total) return;
   const int c8 = idx % 16, h = (idx / 16) % H, i = (idx / (16 * H)) % T, b = idx / (16LL * H * T);
-  const float4 x = reinterpret_cast<const float4*>(acc)[idx * 2], y = reinterpret_cast<const float4*>(acc)[idx * 2 + 1];
+  float4 x = reinterpret_cast<const float4*>(acc)[idx * 2], y = reinterpret_cast<const float4*>(acc)[idx * 2 + 1];
+  if (c8 < 8) { x.x *= dq_scale; x.y *= dq_scale; x.z *= dq_scale; x.w *= dq_scale; y.x *= dq_scale; y.y *= dq_scale; y.z *= dq_scale; y.w *= dq_scale; }
   const uint4 pk = make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
   if (c8 < 8) *reinterpret_cast<uint4*>(dq + (size_t)b * bsdq + (size_t)i * lddq + h * HD + c8 * 8) = pk;
   else *reinterpret_cast<uint4*>(dpq + (size_t)b * bsdpq + (size_t)i * lddpq + h * HD + (c8 - 8) * 8) = pk;
@@ -729,7 +730,7 @@ extern "C" int ofa_attn_bwd_tc(const AttnArgs* a, const AttnGrads* g, float* dq_
   dim3 grid((a->S + BK2 - 1) / BK2, a->H, a->B);
   OFA_CUDA(ofa_launch_pdl(attn_bwd_tc_kernel, grid, kBwdThreads, smem, st, tq, tpq, tk, tpk, tv, tdo, tdq, *a, *g));
   OFA_LAUNCH_CHECK("attn_bwd_tc_kernel");
-  OFA_CUDA(ofa_launch_pdl(attn_bwd_dq_convert_kernel, (unsigned)((nrow * 16 + 255) / 256), 256, 0, st, dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H));
+  OFA_CUDA(ofa_launch_pdl(attn_bwd_dq_convert_kernel, (unsigned)((nrow * 16 + 255) / 256), 256, 0, st, dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H, g->dq_scale == 0.f ? 1.f : g->dq_scale));
   OFA_LAUNCH_CHECK("attn_bwd_dq_convert_kernel");
   return 0;
 }

@@ -38,6 +38,7 @@ struct GemmParams {
   int n_big;     // work items [0, n_big) are full 128 x BN tiles; the rest are 128 x 64 sub-tiles of the last tiles
   int total;     // total work items
   float alpha;
+  int alpha_cols;  // alpha applies to output columns < alpha_cols only (fused q|k|v projection: q is pre-scaled); 0 = all
   int act;  // 0 none, 1 gelu(erf)
   float* rowsum;  // fp32 [M]: rowsum[m] += alpha * sum_k A(m,k) (bias gradient of a weight-gradient GEMM) or null
   int reduce_f32; // fp32 output ADDED into D by TMA reduce (gradient accumulation; K slices need no workspace)
@@ -164,8 +165,9 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*s
         for (int j = 0; j < 32; ++j)
           if (j < nvalid) v[j] += __bfloat162float(bias[nb + j]);
       }
+      const float al = (p.alpha_cols == 0 || nb < p.alpha_cols) ? p.alpha : 1.f;   // 32-column groups never straddle
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+      for (int j = 0; j < 32; ++j) v[j] *= al;
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -427,8 +429,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               for (int j = 0; j < 32; ++j)
                 if (j < nvalid) v[j] += ld_as_float<OutT>(bias + nb + j);
             }
+            const float al = (p.alpha_cols == 0 || nb < p.alpha_cols) ? p.alpha : 1.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+            for (int j = 0; j < 32; ++j) v[j] *= al;
             if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -648,8 +651,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
             for (int j = 0; j < 32; ++j)
               if (j < nvalid) v[j] += ld_as_float<OutT>(bias + nb + j);
           }
+          const float al = (p.alpha_cols == 0 || nb < p.alpha_cols) ? p.alpha : 1.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          for (int j = 0; j < 32; ++j) v[j] *= al;
           if (p.act == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmParams p) {
   float v = 0.f;
   for (int sp = 0; sp < p.splits; ++sp) v += p.ws[((size_t)(sp * p.batch + bz)) * per + mn];
   if (p.bias) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.bias) + n);
-  v *= p.alpha;
+  v *= (p.alpha_cols == 0 || n < p.alpha_cols) ? p.alpha : 1.f;
   if (p.act == 1) v = gelu_erf(v);
   if (p.resid) v += ld_as_float<OutT>(reinterpret_cast<const OutT*>(p.resid) + (long long)bz * p.batch_stride_r + (long long)m * p.ldr + n);
   reinterpret_cast<OutT*>(p.D)[(long long)bz * p.batch_stride_d + (long long)m * p.ldd + n] = (OutT)v;
@@ -838,7 +842,8 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
                              long long ldb, long long ldd, long long stride_a, long long stride_b, long long stride_d,
                              int a_mn_major, int b_mn_major, int out_dtype, const void* bias, float alpha, int act,
                              const void* resid, long long ldr, long long stride_r, void* workspace,
-                             long long workspace_bytes, void* stream) {
+                             long long workspace_bytes, int alpha_cols, void* stream) {
+  OFA_CHECK(alpha_cols >= 0 && alpha_cols % 32 == 0, "ofa_gemm_bf16: alpha_cols=%d must be a multiple of 32", alpha_cols);
   OFA_CHECK(M > 0 && N > 0 && K > 0 && batch > 0, "ofa_gemm_bf16: empty problem M=%d N=%d K=%d batch=%d", M, N, K, batch);
   OFA_CHECK(lda % 8 == 0 && ldb % 8 == 0, "ofa_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16B stride)");
   OFA_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "ofa_gemm_bf16: A/B must be 16B aligned");
@@ -918,7 +923,7 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   p.tma_store = tma_store;
   p.D = D; p.bias = bias; p.resid = resid; p.ws = (float*)workspace; p.ldd = ldd; p.ldr = ldr;
   p.batch_stride_d = stride_d; p.batch_stride_r = stride_r;
-  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.act = act;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.alpha_cols = alpha_cols; p.act = act;
   p.tiles_m = (M + BM - 1) / BM; p.tiles_n = (N + bn - 1) / bn; p.batch = batch; p.splits = splits;
   const int nkb = (K + BK - 1) / BK;
   p.kb_per_split = (nkb + splits - 1) / splits;

@@ -122,6 +122,14 @@ class MultiheadAttention(nn.Module):
     def project_kv(self, key):
         return _lin(self.k_proj, key), _lin(self.v_proj, key)
 
+    def forward_self(self, h, pq, pk, tok_lut, img_lut, cfg):
+        """Self-attention with the fused q|k|v projection (training / teacher-forced path)."""
+        q, k, v = ops.qkv_linear(h, self.q_proj, self.k_proj, self.v_proj, self.scaling)
+        cfg = dict(cfg)
+        # q leaves the GEMM as s * (x Wq^T + bq); the gradient handed back to the fused projection is d/d(x Wq^T + bq) = s * dq
+        cfg["H"], cfg["fused_qkv"], cfg["dq_scale"] = self.num_heads, True, self.scaling
+        return ops.attention(q, pq, k, pk, v, tok_lut, img_lut, self.c_attn, cfg)
+
     def forward(self, query, k, v, pq, pk, tok_lut, img_lut, cfg):
         q = _lin(self.q_proj, query, alpha=self.scaling)
         dec = cfg.get("decode")
@@ -179,8 +187,7 @@ class TransformerEncoderLayer(nn.Module, _FFNMixin):
 
     def forward(self, x, pq, pk, tok_lut, img_lut, cfg):
         h = _ln(self.self_attn_layer_norm, x)
-        k, v = self.self_attn.project_kv(h)
-        o = self.self_attn(h, k, v, pq, pk, tok_lut, img_lut, cfg)
+        o = self.self_attn.forward_self(h, pq, pk, tok_lut, img_lut, cfg)
         x = self._post_attn(self.self_attn, o, self.attn_ln, x)
         return self._ffn(x)
 
@@ -209,8 +216,11 @@ class TransformerDecoderLayer(nn.Module, _FFNMixin):
 
     def forward(self, x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg):
         h = _ln(self.self_attn_layer_norm, x)
-        k, v = self_kv(self.self_attn, h)
-        o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg)
+        if "decode" in self_cfg:                 # incremental decoding: K / V go through the cache
+            k, v = self_kv(self.self_attn, h)
+            o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg)
+        else:
+            o = self.self_attn.forward_self(h, spq, spk, tok_lut, None, self_cfg)
         x = self._post_attn(self.self_attn, o, self.self_attn_ln, x)
         h = _ln(self.encoder_attn_layer_norm, x)
         k, v = cross_kv(self.encoder_attn)

@@ -59,6 +59,27 @@ class _GradAccumulator:
         v = self.arena32[r[0]:r[0] + r[1]]
         return v.view(param.shape[0], -1) if param.dim() >= 2 else v      # storage order of the parameter
 
+    def group32(self, params):
+        """fp32 accumulation view spanning several parameters whose arena regions are adjacent (laid out together on first
+        use).  Returns None if they cannot be adjacent (already placed apart, sizes not multiples of 64)."""
+        if any(id(p) not in self.params or not p.is_contiguous() or p.numel() % 64 for p in params):
+            return None
+        placed = [id(p) in self.region for p in params]
+        if not all(placed):
+            if any(placed):
+                return None
+            for p in params:           # first use: consecutive offsets (target32 appends at the end of the arena)
+                if self.target32(p) is None:
+                    return None
+        offs = [self.region[id(p)][0] for p in params]
+        for p, o, o2 in zip(params, offs, offs[1:] + [None]):
+            if o2 is not None and o + p.numel() != o2:
+                return None
+        for p in params:
+            self.written32.add(id(p))
+        n = sum(p.numel() for p in params)
+        return self.arena32[offs[0]:offs[0] + n]
+
     def target(self, param):
         """-> (buffer, accumulate) for a registered leaf parameter, else (None, False)."""
         k = id(param)
@@ -148,6 +169,13 @@ def _acc_target32(param):
     return _ACC.target32(param)
 
 
+def _acc_group32(params):
+    """One contiguous fp32 arena region covering `params` back to back (fused q|k|v weight / bias gradients), or None."""
+    if _ACC is None:
+        return None
+    return _ACC.group32(params)
+
+
 def _dt(t):
     if t.dtype == torch.float32:
         return F32
@@ -192,7 +220,7 @@ def _split3(x2d, rows, cols, k_is_cols, pattern):
 
 
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, alpha=1.0, act=0, resid=None,
-         ldd=None, acc32=False, rowsum=None):
+         ldd=None, acc32=False, rowsum=None, alpha_cols=0):
     """D[M,N] = act((A.B^T + bias) * alpha) + resid.   A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn);
     2-D tensors with unit inner stride.  fp32 operands take the split path."""
     _need_cuda(A)
@@ -223,7 +251,8 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
     wsb = 0 if acc32 else _lib.load().ofa_gemm_workspace_bytes(M, N, Kk, 1)
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=A.device) if wsb > 0 else None
     call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
-         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _p(ws), wsb, _st(),
+         _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _p(ws), wsb,
+         int(alpha_cols), _st(),
          work=("flop", 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), od)))
     return out
 
@@ -287,6 +316,60 @@ class _Linear(torch.autograd.Function):
         if ctx.has_r and ctx.needs_input_grad[4]:
             dr = dy
         return dx, dw, db, None, dr, None
+
+
+class _QKVLinear(torch.autograd.Function):
+    """q|k|v projections of a self-attention as ONE GEMM over the concatenated weights ([3D, d]: three GEMM launches, three
+    dgrad launches + two adds and three wgrad launches become one each).  The softmax scaling multiplies the q columns in
+    the forward epilogue (alpha_cols) and dq on its way out of the attention backward (dq_scale), so the arithmetic per
+    element is that of q = (x Wq^T + bq) * s, k = x Wk^T + bk, v = x Wv^T + bv (unify_multihead_attention.py:213-232)."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, scaling):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        M, K = x2.shape
+        D = wq.shape[0]
+        w = torch.cat([wq, wk, wv], 0)
+        b = torch.cat([bq, bk, bv], 0)
+        y = gemm(x2, w, M, 3 * D, K, bias=b, alpha=scaling, alpha_cols=D)
+        ctx.save_for_backward(x2, w)
+        ctx.params = (wq, bq, wk, bk, wv, bv)
+        ctx.shp, ctx.D = shp, D
+        y = y.view(*shp[:-1], 3 * D)
+        return y[..., :D], y[..., D:2 * D], y[..., 2 * D:]
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        D = ctx.D
+        es = dq.element_size()
+        fused = (dq.dim() == 3 and dq.stride() == dk.stride() == dv.stride() and dq.stride(-1) == 1 and
+                 dq.stride(-2) == 3 * D and dk.data_ptr() == dq.data_ptr() + D * es and
+                 dv.data_ptr() == dq.data_ptr() + 2 * D * es and dq.stride(0) == dq.shape[1] * 3 * D)
+        if fused:       # written side by side by the attention backward
+            dy2 = dq.as_strided((M, 3 * D), (3 * D, 1))
+        else:
+            dy2 = torch.cat([dq.reshape(M, D), dk.reshape(M, D), dv.reshape(M, D)], 1)
+        dx = gemm(dy2, w, M, K, 3 * D, a_mn=False, b_mn=True).reshape(ctx.shp) if ctx.needs_input_grad[0] else None
+        wq, bq, wk, bk, wv, bv = ctx.params
+        grads = [None] * 6
+        t32 = _acc_group32([wq, wk, wv]) if x2.dtype == torch.bfloat16 else None
+        b32 = _acc_group32([bq, bk, bv]) if t32 is not None else None
+        if t32 is not None and b32 is not None:
+            gemm(dy2, x2, 3 * D, K, M, a_mn=True, b_mn=True, out=t32.view(3 * D, K), out_dtype=torch.float32, acc32=True,
+                 rowsum=b32)
+        else:
+            dw = gemm(dy2, x2, 3 * D, K, M, a_mn=True, b_mn=True, out_dtype=wq.dtype)
+            db = colsum(dy2)
+            grads = [dw[:D], db[:D], dw[D:2 * D], db[D:2 * D], dw[2 * D:], db[2 * D:]]
+        return (dx, *grads, None)
+
+
+def qkv_linear(x, q_proj, k_proj, v_proj, scaling):
+    """-> (q * scaling, k, v) as views of one [.., 3D] buffer (q_proj / k_proj / v_proj: nn.Linear parameter holders)."""
+    return _QKVLinear.apply(x, q_proj.weight, q_proj.bias, k_proj.weight, k_proj.bias, v_proj.weight, v_proj.bias, scaling)
 
 
 def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False):
@@ -685,8 +768,17 @@ class _Attention(torch.autograd.Function):
         a = _fill_args(q, pq, k, pk, v, o, lse, H, cfg["causal"], cfg.get("q_pos_off", 0), cfg.get("kpm"), hs,
                        ctx.bias, q.dtype == torch.bfloat16)
         g = OfaAttnGrads()
-        dq, dpq = torch.empty(B, T, D, dtype=q.dtype, device=q.device), torch.empty(B, T, D, dtype=q.dtype, device=q.device)
-        dk, dpk, dv = (torch.empty(B, S, D, dtype=q.dtype, device=q.device) for _ in range(3))
+        dpq = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+        dpk = torch.empty(B, S, D, dtype=q.dtype, device=q.device)
+        dq_scale = float(cfg.get("dq_scale", 1.0))
+        if cfg.get("fused_qkv") and T == S:
+            # self-attention fed by the fused q|k|v projection: the three gradients land side by side in one [B, L, 3D]
+            # buffer, which is the A operand of that projection's single dgrad / wgrad GEMM (no concatenation copy)
+            dqkv = torch.empty(B, T, 3 * D, dtype=q.dtype, device=q.device)
+            dq, dk, dv = dqkv[..., :D], dqkv[..., D:2 * D], dqkv[..., 2 * D:]
+        else:
+            dq = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+            dk, dv = (torch.empty(B, S, D, dtype=q.dtype, device=q.device) for _ in range(2))
         g.dout = do.data_ptr()
         for name, t in (("dq", dq), ("dpq", dpq), ("dk", dk), ("dpk", dpk), ("dv", dv)):
             setattr(g, name, t.data_ptr())
@@ -700,12 +792,15 @@ class _Attention(torch.autograd.Function):
         g.delta = delta.data_ptr()
         if q.dtype == torch.bfloat16 and cfg.get("use_tc", True):
             dq_acc = torch.empty(B * T * H * 128, dtype=torch.float32, device=q.device)
+            g.dq_scale = dq_scale
             call("ofa_attn_bwd_tc", C.byref(a), C.byref(g), _p(dq_acc), _st(), work=("flop", 2.0 * B * H * T * S * 512))
         else:
             P = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
             dS = torch.empty(B, H, T, S, dtype=torch.float32, device=q.device)
             g.P, g.dS = P.data_ptr(), dS.data_ptr()
             call("ofa_attn_bwd_simt", C.byref(a), C.byref(g), _dt(q), _st(), work=("flop", 2.0 * B * H * T * S * 512))
+            if dq_scale != 1.0:
+                dq.mul_(dq_scale)
         dhs = None
         if head_scale is not None:
             dhs = (delta.sum(dim=(0, 2)) / hs).to(head_scale.dtype)
