@@ -50,6 +50,7 @@ SIGNATURES = {
     "ofa_gemm_workspace_bytes": [c_i, c_i, c_i, c_i],
     "ofa_gemm_set_pair_mode": [c_i],
     "ofa_gemm_set_tma_store": [c_i],
+    "ofa_gemm_set_wgrad_bn256": [c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],
@@ -101,6 +102,8 @@ def load(path=None):
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = c_ll if name.endswith(("_bytes", "_floats")) else c_i
+    if os.environ.get("OFA_WGRAD_BN256") is not None:
+        lib.ofa_gemm_set_wgrad_bn256(int(os.environ["OFA_WGRAD_BN256"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch
         lib.ofa_set_pdl(int(os.environ["OFA_PDL"]))
     _lib = lib

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 
+static int g_ofa_gemm_wgrad_bn256 = 1;    // weight-gradient (fp32 accumulate) problems prefer 128 x 256 tiles
 static int g_ofa_gemm_tma_store = 1;      // bf16 epilogue through shared memory + TMA store (0: per-thread row stores)
 static int g_ofa_gemm_pair_enabled = 2;   // 0: single-CTA tiles, 1: pair with B multicast, 2: cta_group::2 MMA
 
@@ -56,8 +57,7 @@ template <int BN>
 struct SmemLayout {
   uint8_t tiles[Cfg<BN>::kStages][Cfg<BN>::kStageBytes];  // 1024B aligned (SWIZZLE_128B)
   uint8_t stage_out[4][2][4096];  // per epilogue warp: two 32-row x 64-column bf16 slabs (SWIZZLE_128B) for the TMA store
-  uint8_t ones[BN == 128 ? 1024 : 64];   // BN = 128 only (the 256-wide layout has no shared memory to spare): one 8-row
-                                         // swizzle atom of bf16 1.0 that both 8-row groups of the N = 16 operand alias (SBO = 0): B operand of the row-sum MMA (bias gradients inside the wgrad GEMM)
+  uint8_t ones[1024];             // one 8-row swizzle atom of bf16 1.0 that both 8-row groups of the N = 16 operand alias (SBO = 0): B operand of the row-sum MMA (bias gradients inside the wgrad GEMM)
   uint64_t full[Cfg<BN>::kStages];
   uint64_t empty[Cfg<BN>::kStages];
   uint64_t tmem_full[2];
@@ -273,10 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // TMEM footprint matters beyond this kernel: a smaller allocation lets the next kernel's CTAs start while ours drain
   // Row-sum calls (weight gradients: about one long tile per CTA, nothing for a second accumulator to overlap) run
   // single-buffered -- 128 accumulator + 16 row-sum columns -- so that the allocation stays at 256 columns.
-  const bool rs_mode = BN == 128 && p.rowsum != nullptr;
+  const bool rs_mode = p.rowsum != nullptr;
   const uint32_t tmem_cols = (uint32_t)C::kTmemCols;
   if (warp == 2) tmem_alloc_n(&sm.tmem_addr, tmem_cols);
-  if (BN == 128 && p.rowsum) {
+  if (p.rowsum) {
     for (int e = threadIdx.x; e < 256; e += kThreads) reinterpret_cast<uint32_t*>(sm.ones)[e] = 0x3F803F80u;   // bf16 1.0 pairs
     fence_proxy_async();
   }
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(&sm.tmem_empty[acc], ((rs_mode ? it : (it >> 1)) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        const bool rs_tile = BN == 128 && p.rowsum && (wk.n0 % BN) == 0;
+        const bool rs_tile = p.rowsum && (wk.n0 % BN) == 0;
         const int rs_nt = wk.n0 / BN;
         uint32_t rs_acc = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (m0 + q * 32 < p.M) epilogue_reduce(&tmD, sm.stage_out[q], sbuf, tmem_d, nch, m0 + q * 32, n0, wk.bz, p, lane);
         const int rs_kb0 = wk.sp * p.kb_per_split, rs_tn = p.tiles_n;
         const int rs_first = rs_kb0 + (((n0 / BN) - rs_kb0 % rs_tn) + rs_tn) % rs_tn;      // first k-block dealt to this tile
-        if (BN == 128 && p.rowsum && (n0 % BN) == 0 && rs_first < min(nkb_all, rs_kb0 + p.kb_per_split)) {
+        if (p.rowsum && (n0 % BN) == 0 && rs_first < min(nkb_all, rs_kb0 + p.kb_per_split)) {
           uint32_t r[16];
           tmem_ld16(tmem_base + BN + ((uint32_t)(q * 32) << 16), r);
           tmem_ld_wait();
@@ -817,6 +817,11 @@ void plan(int M, int N, int K, int batch, int* bn, int* splits) {
 }  // namespace
 
 // debugging / A-B switch for the CTA-pair (TMA multicast) variant; returns the previous setting
+extern "C" int ofa_gemm_set_wgrad_bn256(int enabled) {
+  const int old = g_ofa_gemm_wgrad_bn256;
+  g_ofa_gemm_wgrad_bn256 = enabled;
+  return old;
+}
 extern "C" int ofa_gemm_set_tma_store(int enabled) {
   const int old = g_ofa_gemm_tma_store;
   g_ofa_gemm_tma_store = enabled;
@@ -861,17 +866,19 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   }
   int bn, splits;
   plan(M, N, K, batch, &bn, &splits);
-  if (rowsum && bn != 128) {      // the row-sum columns live next to 2 x 128 accumulator columns
-    bn = 128;
-    splits = 1;
-    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + 127) / 128);
+  if (reduce_f32 && g_ofa_gemm_wgrad_bn256 && batch == 1 && N >= 256 && N % 256 == 0) {
+    // weight gradients (K slices reduce-add in place, about one long tile per CTA): 128 x 256 tiles halve the shared-memory
+    // traffic per MAC of the 128 x 128 tile that the occupancy heuristic of plan() would pick for so few tiles
+    const long long tiles = (long long)((M + BM - 1) / BM) * (N / 256);
     const int nkb_r = (K + BK - 1) / BK;
+    int s = 1;
     if (tiles * 2 <= kNumSMs && nkb_r >= 8) {
-      splits = (int)(kNumSMs / tiles);
-      if (splits > nkb_r / 4) splits = nkb_r / 4;
-      if (splits > 32) splits = 32;
-      if (splits < 1) splits = 1;
+      s = (int)(kNumSMs / tiles);
+      if (s > nkb_r / 4) s = nkb_r / 4;
+      if (s > 32) s = 32;
+      if (s < 1) s = 1;
     }
+    if (tiles * s >= kNumSMs / 2) { bn = 256; splits = s; }
   }
   if (!reduce_f32 && splits > 1 &&
       (workspace == nullptr || workspace_bytes < (long long)splits * batch * M * N * (long long)sizeof(float)))
