@@ -44,6 +44,8 @@ int ofa_gemm_set_pair_mode(int enabled);
 int ofa_gemm_set_tma_store(int enabled);
 /* weight-gradient tile-shape switch (A/B testing): 1 = 128 x 256 tiles for fp32-accumulate problems (default) */
 int ofa_gemm_set_wgrad_bn256(int enabled);
+/* smallest number of 256 x 256 pair tiles for which the cta_group::2 kernel is chosen (default 38; A/B testing) */
+int ofa_gemm_set_pair_min_tiles(int n);
 
 /* fp32 -> three bf16 terms laid out as six K-blocks (fp32 parity mode operands for ofa_gemm_bf16) */
 int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, long long ldo, long long blk_stride,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "ofa_gemm_set_pair_mode": [c_i],
     "ofa_gemm_set_tma_store": [c_i],
     "ofa_gemm_set_wgrad_bn256": [c_i],
+    "ofa_gemm_set_pair_min_tiles": [c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],
@@ -104,6 +105,8 @@ def load(path=None):
         fn.restype = c_ll if name.endswith(("_bytes", "_floats")) else c_i
     if os.environ.get("OFA_WGRAD_BN256") is not None:
         lib.ofa_gemm_set_wgrad_bn256(int(os.environ["OFA_WGRAD_BN256"]))
+    if os.environ.get("OFA_PAIR_MIN_TILES") is not None:
+        lib.ofa_gemm_set_pair_min_tiles(int(os.environ["OFA_PAIR_MIN_TILES"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch
         lib.ofa_set_pdl(int(os.environ["OFA_PDL"]))
     _lib = lib

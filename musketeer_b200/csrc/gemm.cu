@@ -17,6 +17,9 @@
 
 #include "common.cuh"
 
+// a 256 x 256 pair tile costs each SM about what one 128 x 128 tile costs (measured ~1.05 vs ~0.55 PFLOP/s): the pair kernel
+// wins as soon as the single-CTA kernel would need a second wave, i.e. from about a quarter of the machine's pairs
+static int g_ofa_gemm_pair_min_tiles = 38;
 static int g_ofa_gemm_wgrad_bn256 = 1;    // weight-gradient (fp32 accumulate) problems prefer 128 x 256 tiles
 static int g_ofa_gemm_tma_store = 1;      // bf16 epilogue through shared memory + TMA store (0: per-thread row stores)
 static int g_ofa_gemm_pair_enabled = 2;   // 0: single-CTA tiles, 1: pair with B multicast, 2: cta_group::2 MMA
@@ -801,8 +804,11 @@ int plan2_splits(int M, int N, int K, int batch) {
 void plan(int M, int N, int K, int batch, int* bn, int* splits) {
   const int tm = (M + BM - 1) / BM;
   const int nkb = (K + BK - 1) / BK;
-  // 128 x 256 tiles only when they still give every SM at least two tiles
-  *bn = (N >= 512 && (long long)tm * ((N + 255) / 256) * batch >= 2 * kNumSMs) ? 256 : 128;
+  // Tile width by a wave-count model: a 128 x 256 tile takes ~1.5x the time of a 128 x 128 tile (measured ~750 vs ~550
+  // TFLOP/s when the machine is full), so it wins whenever it saves enough waves
+  const long long t128 = (long long)tm * ((N + 127) / 128) * batch, t256 = (long long)tm * ((N + 255) / 256) * batch;
+  const long long w128 = (t128 + kNumSMs - 1) / kNumSMs, w256 = (t256 + kNumSMs - 1) / kNumSMs;
+  *bn = (N >= 256 && 3 * w256 < 2 * w128) ? 256 : 128;
   const long long tiles = (long long)tm * ((N + *bn - 1) / *bn) * batch;
   int s = 1;
   if (tiles * 2 <= kNumSMs && nkb >= 8) {
@@ -817,6 +823,11 @@ void plan(int M, int N, int K, int batch, int* bn, int* splits) {
 }  // namespace
 
 // debugging / A-B switch for the CTA-pair (TMA multicast) variant; returns the previous setting
+extern "C" int ofa_gemm_set_pair_min_tiles(int n) {
+  const int old = g_ofa_gemm_pair_min_tiles;
+  g_ofa_gemm_pair_min_tiles = n;
+  return old;
+}
 extern "C" int ofa_gemm_set_wgrad_bn256(int enabled) {
   const int old = g_ofa_gemm_wgrad_bn256;
   g_ofa_gemm_wgrad_bn256 = enabled;
@@ -940,7 +951,7 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
   int s2 = (g_ofa_gemm_pair_enabled == 2 && !rowsum) ? plan2_splits(M, N, K, batch) : 0;
   if (!reduce_f32 && s2 > 1 && (workspace == nullptr || workspace_bytes < (long long)s2 * M * N * (long long)sizeof(float))) s2 = 0;
   if (g_ofa_gemm_pair_enabled == 2 && batch == 1 && N >= 256 && !rowsum &&
-      (s2 > 1 || (p.splits == 1 && (long long)((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2))) {
+      (s2 > 1 || (p.splits == 1 && (long long)((M + 255) / 256) * ((N + 255) / 256) >= g_ofa_gemm_pair_min_tiles))) {
     p.tiles_m = (M + 255) / 256;
     p.tiles_n = (N + 255) / 256;
     const int tiles = p.tiles_m * p.tiles_n, workers = kNumSMs / 2;
