@@ -79,15 +79,18 @@ int ofa_dropout_residual(const void* x, const void* resid, void* y, long long n,
  * running-stat update (momentum, unbiased variance), or eval / frozen mode (models/ofa/resnet.py:113-133,211-220,
  * frozen_bn.py:36-57).  stats = 4*C floats (mean | rstd | scale | shift); mean and rstd feed the backward.
  * workspace: ofa_batchnorm_workspace_floats() floats that are ZERO ON ENTRY; the kernels leave them zero again, so one
- * zero-initialised scratch per stream serves every call (no memset per layer).                                         */
+ * zero-initialised scratch per stream serves every call (no memset per layer).
+ * groups > 1: the R rows are `groups` equal, consecutive groups (the images of several tasks batched through the stem);
+ * statistics / normalisation / backward are per group (stats = groups * 4*C floats), the running statistics are updated
+ * group after group and dgamma / dbeta are summed over the groups -- the arithmetic of `groups` separate calls.          */
 long long ofa_batchnorm_workspace_floats(int C);
 int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* running_mean,
                       void* running_var, long long R, int C, float eps, float momentum, int training, int relu,
-                      float* stats, float* workspace, int dtype, void* stream);
+                      float* stats, float* workspace, int groups, int dtype, void* stream);
 /* y may be NULL when relu && no residual: the mask is then recomputed from x with the forward's scale / shift */
 int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* stats, void* dx,
                       void* dres, void* dgamma, void* dbeta, int accumulate, long long R,
-                      int C, int batch_stats, int relu, float* workspace, int dtype, void* stream);
+                      int C, int batch_stats, int relu, float* workspace, int groups, int dtype, void* stream);
 
 /* ---- 3x3 / stride 1 / padding 1 convolution as an implicit GEMM (models/ofa/resnet.py:107-108,119-121: conv2 of the
  * stride-1 bottlenecks).  bf16 NHWC activations [N][H][W][C]; weight bytes [Cout][3][3][Cin] (a channels_last

@@ -26,8 +26,9 @@ def construct_rdrop_sample(x):
 class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
     def __init__(self, task, sentence_avg=False, label_smoothing=0.0, ignore_prefix_size=0, ignore_eos=False,
                  report_accuracy=False, drop_worst_ratio=0, drop_worst_after=0, use_rdrop=False, reg_alpha=1.0,
-                 sample_patch_num=196, constraint_range=None):
+                 sample_patch_num=196, constraint_range=None, batch_task_stems=True):
         super().__init__()
+        self.batch_task_stems = batch_task_stems
         self.task = task
         self.padding_idx = task.target_dictionary.pad()
         self.eos_idx = task.target_dictionary.eos()
@@ -43,12 +44,43 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
             cs, ce = constraint_range.split(",")
             self.constraint_range = (int(cs), int(ce))
 
-    def forward(self, model, sample, update_num=0, reduce=True):
+    def _batch_stems(self, model, sample):
+        """Multi-task micro-step: push the images of all image tasks through the ResNet stem in ONE grouped pass (BatchNorm
+        statistics stay per task, running statistics are updated in task order: musketeer_b200/resnet.py), and hand every
+        task its slice as `patch_features`.  Arithmetic per task is unchanged; every stem kernel runs once instead of
+        once per task.  Skipped when the tasks' image batches differ in shape, with R-Drop (the duplication happens inside
+        the per-task forward) or with ResNet drop-path."""
+        enc = getattr(model, "encoder", None)
+        stem = getattr(enc, "embed_images", None)
+        if stem is None or self.use_rdrop or not self.batch_task_stems:
+            return sample
+        idx = [i for i, s in enumerate(sample) if s["net_input"].get("patch_images") is not None
+               and s["net_input"].get("patch_features") is None]
+        if len(idx) < 2 or len(idx) > 8:
+            return sample
+        imgs = [sample[i]["net_input"]["patch_images"] for i in idx]
+        if any(im.shape != imgs[0].shape or im.dtype != imgs[0].dtype for im in imgs):
+            return sample
+        if getattr(stem, "drop_path_rate", 0.0) > 0.0 and stem.training:
+            return sample
+        feats = stem(torch.cat(imgs, 0), groups=len(idx)).split(imgs[0].shape[0], 0)     # split: one cat in the backward
+        hw = stem.last_hw
+        out = list(sample)
+        for k, i in enumerate(idx):
+            s = dict(sample[i])
+            s["net_input"] = dict(s["net_input"])
+            s["net_input"]["patch_features"] = (feats[k], hw)
+            out[i] = s
+        return out
+
+    def forward(self, model, sample, update_num=0, reduce=True, _top=True):
+        if isinstance(sample, list) and len(sample) > 1 and _top:
+            sample = self._batch_stems(model, sample)
         if isinstance(sample, list) and len(sample) > 1:                               # :175-202
             if self.sample_patch_num > 0:
                 sample[0]["net_input"]["sample_patch_num"] = self.sample_patch_num
-            loss_v1, ss1, log1 = self.forward(model, sample[0], update_num, reduce)
-            loss_v2, ss2, log2 = self.forward(model, sample[1:], update_num, reduce)
+            loss_v1, ss1, log1 = self.forward(model, sample[0], update_num, reduce, _top=False)
+            loss_v2, ss2, log2 = self.forward(model, sample[1:], update_num, reduce, _top=False)
             loss = loss_v1 / ss1 + loss_v2 / ss2
             logging_output = {
                 "loss": loss.data, "loss_v1": loss_v1.data, "loss_v2": loss_v2.data,

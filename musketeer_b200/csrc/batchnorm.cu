@@ -5,6 +5,9 @@
 //     forward : stats (1 read)              -> apply: y = relu(x*scale_c + shift_c + res)      (1-2 reads, 1 write)
 //     backward: reduce (dy, x, y -> s1, s2) -> apply: dx = a_c*(g - s1/n - xhat*s2/n), dres = g (g = dy masked by y > 0)
 // HBM-bound: every thread owns 8 consecutive channels (one 16-byte vector of bf16, two of fp32).
+// Groups: the R rows may be G equal groups (the images of G tasks of a Musketeer micro-step pushed through the stem as ONE
+// batch); statistics, normalisation and backward are per group (blockIdx.z), exactly as if each task had run alone, the
+// running statistics are updated group after group and dgamma / dbeta are summed over the groups.
 #include "common.cuh"
 
 namespace {
@@ -93,20 +96,20 @@ __device__ __forceinline__ void block_accumulate(const Map& m, int C, int CS, co
 // The per-channel sums live in a caller-provided scratch that is ZERO ON ENTRY and LEFT ZERO ON EXIT: every CTA of the apply
 // kernel bumps a counter once it has read the sums, and the last one clears sums and counter for the next BatchNorm call in
 // the stream (no memset node per layer; 752 of them per training step before).  scratch = [2*C sums | ... | counter @ 2*kMaxC].
-constexpr int kMaxC = 2048;
-__device__ __forceinline__ void release_sums(float* __restrict__ sums, int C) {
+constexpr int kMaxC = 2048, kMaxGroups = 8;
+__device__ __forceinline__ void release_sums(float* __restrict__ sums /* group 0 */, int C) {
   __shared__ int last;
   __syncthreads();                       // every thread of this CTA has read its sums
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned int* counter = reinterpret_cast<unsigned int*>(sums + 2 * kMaxC);
-    const unsigned int total = gridDim.x * gridDim.y;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(sums + 2 * kMaxC * kMaxGroups);
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
     last = atomicAdd(counter, 1u) == total - 1;
     if (last) *counter = 0u;
   }
   __syncthreads();
   if (last)
-    for (int c = threadIdx.x; c < 2 * C; c += kT) sums[c] = 0.f;
+    for (int c = threadIdx.x; c < 2 * C * (int)gridDim.z; c += kT) sums[c] = 0.f;
 }
 
 constexpr int kUnroll = 4;
@@ -117,6 +120,8 @@ __global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x
                                                       float* __restrict__ sums) {
   pdl_sync();
   const Map m = make_map(CS);
+  x += (long long)blockIdx.z * R * C;            // this group's rows
+  sums += (size_t)blockIdx.z * 2 * C;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
@@ -152,6 +157,14 @@ __global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x
                                                       int relu) {
   pdl_sync();
   const Map m = make_map(CS);
+  const float* sums0 = sums;                     // group 0 (running statistics, release)
+  {
+    const long long go = (long long)blockIdx.z * R * C;
+    x += go; y += go;
+    if (res) res += go;
+    if (sums) sums += (size_t)blockIdx.z * 2 * C;
+    stats += (size_t)blockIdx.z * 4 * C;
+  }
   float sc[8], sh[8];
   {
     const float n = (float)R;
@@ -172,14 +185,21 @@ __global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x
       sh[j] = (float)beta[c] - mean * sc[j];
       if (publish) {
         stats[c] = mean; stats[C + c] = rstd; stats[2 * C + c] = sc[j]; stats[3 * C + c] = sh[j];
-        if (training && running_mean) {
-          running_mean[c] = (T)((1.f - momentum) * (float)running_mean[c] + momentum * mean);
-          running_var[c] = (T)((1.f - momentum) * (float)running_var[c] + momentum * var * n / fmaxf(n - 1.f, 1.f));
+        if (training && running_mean && blockIdx.z == 0) {     // group after group, as sequential per-task forwards would
+          float rm = (float)running_mean[c], rvv = (float)running_var[c];
+          for (int g = 0; g < (int)gridDim.z; ++g) {
+            const float mg = sums0[(size_t)g * 2 * C + c] / n;
+            const float vg = fmaxf(sums0[(size_t)g * 2 * C + C + c] / n - mg * mg, 0.f);
+            rm = (float)(T)((1.f - momentum) * rm + momentum * mg);
+            rvv = (float)(T)((1.f - momentum) * rvv + momentum * vg * n / fmaxf(n - 1.f, 1.f));
+          }
+          running_mean[c] = (T)rm;
+          running_var[c] = (T)rvv;
         }
       }
     }
   }
-  if (training) release_sums(const_cast<float*>(sums), C);
+  if (training) release_sums(const_cast<float*>(sums0), C);
   for (long long r = m.r0; r < R; r += kUnroll * m.stride) {
     typename V8<T>::Raw rx[kUnroll], rr[kUnroll];
 #pragma unroll
@@ -215,6 +235,13 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_stats_kernel(const T* __restrict
                                                           long long R, int C, int CS, int relu, float* __restrict__ sums) {
   pdl_sync();
   const Map m = make_map(CS);
+  {
+    const long long go = (long long)blockIdx.z * R * C;
+    x += go; dy += go;
+    if (y) y += go;
+    stats += (size_t)blockIdx.z * 4 * C;
+    sums += (size_t)blockIdx.z * 2 * C;
+  }
   float a[8], b[8], sc[8], sh[8];   // b accumulates sum g*x; the xhat form follows from (b - mean*a) * rstd at the end
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -268,10 +295,19 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict
                                                           int batch_stats, int relu) {
   pdl_sync();
   const Map m = make_map(CS);
+  const float* sums0 = sums;
+  {
+    const long long go = (long long)blockIdx.z * R * C;
+    x += go; dy += go; dx += go;
+    if (y) y += go;
+    if (dres) dres += go;
+    stats += (size_t)blockIdx.z * 4 * C;
+    if (sums) sums += (size_t)blockIdx.z * 2 * C;
+  }
   float ca[8], cA[8], cB[8], sc[8], sh[8];
   {
     const float inv_n = 1.f / (float)R;
-    const bool publish = blockIdx.x == 0 && m.ry == 0 && dgamma != nullptr;
+    const bool publish = blockIdx.x == 0 && blockIdx.z == 0 && m.ry == 0 && dgamma != nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = m.c0 + j;
@@ -281,13 +317,15 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict
       ca[j] = (float)gamma[c] * rstd;
       cA[j] = batch_stats ? -ca[j] * rstd * s2 * inv_n : 0.f;
       cB[j] = batch_stats ? -ca[j] * s1 * inv_n - cA[j] * mean : 0.f;
-      if (publish) {
-        dgamma[c] = (T)(s2 + (accumulate ? (float)dgamma[c] : 0.f));
-        dbeta[c] = (T)(s1 + (accumulate ? (float)dbeta[c] : 0.f));
+      if (publish) {          // parameter gradients: summed over the groups
+        float t1 = 0.f, t2 = 0.f;
+        for (int g = 0; g < (int)gridDim.z; ++g) { t1 += sums0[(size_t)g * 2 * C + c]; t2 += sums0[(size_t)g * 2 * C + C + c]; }
+        dgamma[c] = (T)(t2 + (accumulate ? (float)dgamma[c] : 0.f));
+        dbeta[c] = (T)(t1 + (accumulate ? (float)dbeta[c] : 0.f));
       }
     }
   }
-  if (sums) release_sums(const_cast<float*>(sums), C);
+  if (sums) release_sums(const_cast<float*>(sums0), C);
   constexpr int U = 2;
   for (long long r = m.r0; r < R; r += U * m.stride) {
     typename V8<T>::Raw rx[U], rg[U], ry_[U];
@@ -327,29 +365,29 @@ struct Grid {
   int CS;
   dim3 g;
 };
-Grid grid_for(long long R, int C, int unroll) {
+Grid grid_for(long long R, int C, int unroll, int groups) {
   Grid r;
   r.CS = C < 256 ? C : 256;
   const int slabs = C / r.CS;
   const int rpi = kT / (r.CS / 8);
   long long gx = (R + (long long)rpi * unroll - 1) / ((long long)rpi * unroll);
-  const long long cap = (148 * 6 + slabs - 1) / slabs;   // ~6 CTAs of 256 threads per SM in total
+  const long long cap = (148 * 6 + slabs * groups - 1) / (slabs * groups);   // ~6 CTAs of 256 threads per SM in total
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  r.g = dim3((unsigned)gx, (unsigned)slabs);
+  r.g = dim3((unsigned)gx, (unsigned)slabs, (unsigned)groups);
   return r;
 }
 
 template <typename T>
 int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* rm, void* rv,
-             long long R, int C, float eps, float momentum, int training, int relu, float* stats, float* ws,
+             long long R, int C, float eps, float momentum, int training, int relu, float* stats, float* ws, int groups,
              cudaStream_t st) {
   float* sums = ws;
   if (training) {
-    const Grid gs = grid_for(R, C, kUnroll);
+    const Grid gs = grid_for(R, C, kUnroll, groups);
     OFA_CUDA(ofa_launch_pdl(bn_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, R, C, gs.CS, sums));
   }
-  const Grid ga = grid_for(R, C, kUnroll);
+  const Grid ga = grid_for(R, C, kUnroll, groups);
   OFA_CUDA(ofa_launch_pdl(bn_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)res, (T*)y, (const T*)gamma, (const T*)beta, (T*)rm, (T*)rv,
                                           sums, stats, R, C, ga.CS, eps, momentum, training, relu));
   OFA_LAUNCH_CHECK("batchnorm forward");
@@ -358,15 +396,15 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
 
 template <typename T>
 int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, const float* stats, void* dx, void* dres,
-             void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats, int relu, float* ws,
+             void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats, int relu, float* ws, int groups,
              cudaStream_t st) {
   float* sums = nullptr;
   if (batch_stats || dgamma) {   // frozen statistics without parameter gradients need no reduction at all
     sums = ws;
-    const Grid gs = grid_for(R, C, 2);
+    const Grid gs = grid_for(R, C, 2, groups);
     OFA_CUDA(ofa_launch_pdl(bn_bwd_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums));
   }
-  const Grid ga = grid_for(R, C, 2);
+  const Grid ga = grid_for(R, C, 2, groups);
   OFA_CUDA(ofa_launch_pdl(bn_bwd_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, (const T*)gamma, stats, sums, (T*)dx,
                                               (T*)dres, (T*)dgamma, (T*)dbeta, accumulate, R, C, ga.CS, batch_stats, relu));
   OFA_LAUNCH_CHECK("batchnorm backward");
@@ -378,27 +416,32 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
 // scratch floats for either direction: ZERO ON ENTRY, left zero on exit (allocate once with zeros and reuse it for every
 // call in the stream); `stats` of the forward is 4*C floats
 // (mean | rstd | scale | shift), of which mean and rstd are the backward's inputs
-extern "C" long long ofa_batchnorm_workspace_floats(int C) { (void)C; return 2LL * kMaxC + 32; }
+extern "C" long long ofa_batchnorm_workspace_floats(int C) { (void)C; return 2LL * kMaxC * kMaxGroups + 32; }
 
 extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                                  void* running_mean, void* running_var, long long R, int C, float eps, float momentum,
-                                 int training, int relu, float* stats, float* workspace, int dtype, void* stream) {
+                                 int training, int relu, float* stats, float* workspace, int groups, int dtype,
+                                 void* stream) {
+  OFA_CHECK(groups >= 1 && groups <= kMaxGroups && R % groups == 0, "ofa_batchnorm_fwd: groups=%d must divide R and be <= 8", groups);
+  R /= groups;
   OFA_CHECK(R > 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0, "ofa_batchnorm_fwd: C=%d must be a power of two in [8, 2048]", C);
   OFA_CHECK(training || (running_mean && running_var), "ofa_batchnorm_fwd: eval mode needs running statistics");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == OFA_BF16) return fwd_impl<__nv_bfloat16>(x, res, y, gamma, beta, running_mean, running_var, R, C, eps, momentum, training, relu, stats, workspace, st);
-  if (dtype == OFA_F32) return fwd_impl<float>(x, res, y, gamma, beta, running_mean, running_var, R, C, eps, momentum, training, relu, stats, workspace, st);
+  if (dtype == OFA_BF16) return fwd_impl<__nv_bfloat16>(x, res, y, gamma, beta, running_mean, running_var, R, C, eps, momentum, training, relu, stats, workspace, groups, st);
+  if (dtype == OFA_F32) return fwd_impl<float>(x, res, y, gamma, beta, running_mean, running_var, R, C, eps, momentum, training, relu, stats, workspace, groups, st);
   return ofa_set_error("ofa_batchnorm_fwd: bad dtype %d", dtype);
 }
 
 extern "C" int ofa_batchnorm_bwd(const void* x, const void* dy, const void* y, const void* gamma, const float* stats,
                                  void* dx, void* dres, void* dgamma, void* dbeta, int accumulate,
-                                 long long R, int C, int batch_stats, int relu, float* workspace, int dtype,
+                                 long long R, int C, int batch_stats, int relu, float* workspace, int groups, int dtype,
                                  void* stream) {
+  OFA_CHECK(groups >= 1 && groups <= kMaxGroups && R % groups == 0, "ofa_batchnorm_bwd: groups=%d must divide R and be <= 8", groups);
+  R /= groups;
   OFA_CHECK(R > 0 && C >= 8 && C <= 2048 && (C & (C - 1)) == 0, "ofa_batchnorm_bwd: C=%d must be a power of two in [8, 2048]", C);
   cudaStream_t st = (cudaStream_t)stream;
   OFA_CHECK(!relu || y || stats, "ofa_batchnorm_bwd: relu needs y or the forward stats");
-  if (dtype == OFA_BF16) return bwd_impl<__nv_bfloat16>(x, dy, y, gamma, stats, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
-  if (dtype == OFA_F32) return bwd_impl<float>(x, dy, y, gamma, stats, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, st);
+  if (dtype == OFA_BF16) return bwd_impl<__nv_bfloat16>(x, dy, y, gamma, stats, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, groups, st);
+  if (dtype == OFA_F32) return bwd_impl<float>(x, dy, y, gamma, stats, dx, dres, dgamma, dbeta, accumulate, R, C, batch_stats, relu, workspace, groups, st);
   return ofa_set_error("ofa_batchnorm_bwd: bad dtype %d", dtype);
 }

@@ -304,10 +304,13 @@ class TransformerEncoder(nn.Module):
             self._rel1d = _rel_bucket_1d(self.token_rp_bucket)
         return self._rel1d
 
-    def get_patch_images_info(self, patch_images, sample_patch_num, device):
-        feat = self.embed_images(patch_images)                        # [B, h*w, 1024] (NHWC-flattened)
-        B = patch_images.size(0)
-        h, w = self.embed_images.last_hw
+    def get_patch_images_info(self, patch_images, sample_patch_num, device, patch_features=None):
+        if patch_features is not None:            # stem output computed upstream (several tasks in one grouped pass)
+            feat, (h, w) = patch_features
+        else:
+            feat = self.embed_images(patch_images)                    # [B, h*w, 1024] (NHWC-flattened)
+            h, w = self.embed_images.last_hw
+        B = feat.size(0)
         P = h * w
         pid = (torch.arange(w, device=device).unsqueeze(0).expand(h, w) +
                torch.arange(h, device=device).unsqueeze(1) * self.args.image_bucket_size + 1).reshape(-1)
@@ -325,7 +328,8 @@ class TransformerEncoder(nn.Module):
         return feat.contiguous(), P, pad, pid.contiguous()
 
     def forward(self, src_tokens, src_lengths=None, patch_images=None, patch_images_2=None, patch_masks=None,
-                code_masks=None, return_all_hiddens=False, token_embeddings=None, sample_patch_num=None):
+                code_masks=None, return_all_hiddens=False, token_embeddings=None, sample_patch_num=None,
+                patch_features=None):
         if patch_images_2 is not None or token_embeddings is not None:
             raise NotImplementedError("patch_images_2 / token_embeddings are outside the hot-path scope")
         dev = src_tokens.device
@@ -342,8 +346,8 @@ class TransformerEncoder(nn.Module):
         x = ops.dropout_residual(x, None, self.dropout_p, 0.0, self.training)                # :733
         pos = ops.embedding(torch.arange(S, device=dev), self.embed_positions.weight)        # [S, d]   :885
         pos = _ln(self.pos_ln, pos).unsqueeze(0).expand(B, S, d)                             # :898
-        if patch_images is not None:
-            feat, P, img_pad, pid = self.get_patch_images_info(patch_images, sample_patch_num, dev)
+        if patch_images is not None or patch_features is not None:
+            feat, P, img_pad, pid = self.get_patch_images_info(patch_images, sample_patch_num, dev, patch_features)
             img_pad = img_pad | (~patch_masks)[:, None]                                      # :872
             bias = self.image_proj.bias + type_w[1] if type_w is not None else self.image_proj.bias
             xi = ops.linear(feat.to(w.dtype), self.image_proj.weight, bias)                  # :739-744
@@ -639,13 +643,13 @@ class OFAModel(nn.Module):
     def forward(self, src_tokens, src_lengths, prev_output_tokens, patch_images=None, patch_images_2=None,
                 patch_masks=None, code_masks=None, sample_patch_num=None, features_only=False,
                 classification_head_name=None, token_embeddings=None, return_all_hiddens=False, alignment_layer=None,
-                alignment_heads=None, task_name=None, padded_logits=False):
+                alignment_heads=None, task_name=None, padded_logits=False, patch_features=None):
         if classification_head_name is not None:
             raise NotImplementedError("classification heads are outside the hot-path scope (SURVEY.md 8)")
         encoder_out = self.encoder(src_tokens, src_lengths=src_lengths, patch_images=patch_images,
                                    patch_masks=patch_masks, patch_images_2=patch_images_2,
                                    token_embeddings=token_embeddings, return_all_hiddens=return_all_hiddens,
-                                   sample_patch_num=sample_patch_num)
+                                   sample_patch_num=sample_patch_num, patch_features=patch_features)
         self.enc_timer[1] += 1
         x, extra = self.decoder(prev_output_tokens, code_masks=code_masks, encoder_out=encoder_out,
                                 features_only=features_only, alignment_layer=alignment_layer,

@@ -617,22 +617,23 @@ class _BatchNorm(torch.autograd.Function):
     """x: conv output, logically [N,C,H,W] in channels_last memory format (== [N*H*W, C] row-major)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, training, momentum, eps):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, training, momentum, eps, groups):
         _need_cuda(x)
         N, Cc, Hh, Ww = x.shape
+        assert N % groups == 0
         x = x.contiguous(memory_format=torch.channels_last)
         res = residual.contiguous(memory_format=torch.channels_last) if residual is not None else None
         y = torch.empty_like(x, memory_format=torch.channels_last)
         R = N * Hh * Ww
-        stats = torch.empty(4 * Cc, dtype=torch.float32, device=x.device)
+        stats = torch.empty(groups * 4 * Cc, dtype=torch.float32, device=x.device)
         ws = _bn_scratch(x.device)
         call("ofa_batchnorm_fwd", _p(x), _p(res), _p(y), _p(gamma), _p(beta), _p(running_mean), _p(running_var), R, Cc,
-             float(eps), float(momentum), int(training), int(relu), _p(stats), _p(ws), _dt(x), _st(),
+             float(eps), float(momentum), int(training), int(relu), _p(stats), _p(ws), int(groups), _dt(x), _st(),
              work=("byte", (2 + training + (res is not None)) * R * Cc * x.element_size()))
         # with a residual the ReLU mask needs y; without one it is recomputed from x (saves a full read in the backward)
         ctx.save_for_backward(x, y if (relu and res is not None) else None, gamma, stats)
         ctx.beta_param = beta
-        ctx.relu, ctx.training, ctx.has_res = relu, training, residual is not None
+        ctx.relu, ctx.training, ctx.has_res, ctx.groups = relu, training, residual is not None, groups
         return y
 
     @staticmethod
@@ -653,18 +654,19 @@ class _BatchNorm(torch.autograd.Function):
             db = tb if fused else torch.empty_like(gamma)
         ws = _bn_scratch(x.device)
         call("ofa_batchnorm_bwd", _p(x), _p(dy), _p(y), _p(gamma), _p(stats), _p(dx), _p(dres), _p(dg), _p(db),
-             int(fused and ag), R, Cc, int(ctx.training), int(ctx.relu), _p(ws), _dt(x), _st(),
+             int(fused and ag), R, Cc, int(ctx.training), int(ctx.relu), _p(ws), int(ctx.groups), _dt(x), _st(),
              work=("byte", (4 + 2 * ctx.relu + ctx.has_res) * R * Cc * x.element_size()))
         if fused or not want_pg:
             dg = db = None
-        return dx, dg, db, None, None, dres, None, None, None, None
+        return dx, dg, db, None, None, dres, None, None, None, None, None
 
 
 def batch_norm(x, gamma, beta, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1,
-               eps=1e-5):
+               eps=1e-5, groups=1):
     """relu?(BN(x) + residual) on a channels_last [N,C,H,W] tensor; training=True uses batch statistics and updates the
-    running buffers in place (nn.BatchNorm2d semantics), False uses the running statistics (eval / FrozenBatchNorm2d)."""
-    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, residual, relu, training, momentum, eps)
+    running buffers in place (nn.BatchNorm2d semantics), False uses the running statistics (eval / FrozenBatchNorm2d).
+    groups > 1: the batch is `groups` equal consecutive groups normalised independently (several tasks in one stem pass)."""
+    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, residual, relu, training, momentum, eps, groups)
 
 
 class _DropoutResidual(torch.autograd.Function):

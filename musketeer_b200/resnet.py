@@ -27,6 +27,7 @@ class FrozenBatchNorm2d(nn.Module):
 
 
 _TRACK = []
+_GROUPS = [1]       # batch groups of the stem pass in flight (ResNetStem.forward(x, groups))
 
 
 def _bn(mod, x, relu=False, residual=None):
@@ -36,7 +37,7 @@ def _bn(mod, x, relu=False, residual=None):
     if training and mod.num_batches_tracked is not None:
         _TRACK.append(mod.num_batches_tracked)        # bumped once per stem forward with one fused add (ResNetStem.forward)
     return ops.batch_norm(x, mod.weight, mod.bias, mod.running_mean, mod.running_var, residual, relu, training,
-                          0.1 if not frozen else 0.0, mod.eps)
+                          0.1 if not frozen else 0.0, mod.eps, _GROUPS[0])
 
 
 def _conv(mod, x):
@@ -110,8 +111,14 @@ class ResNetStem(nn.Module):
             seq.append(Bottleneck(self.inplanes, planes, 1, None, norm, dpr[i]))
         return nn.Sequential(*seq)
 
-    def forward(self, x):
+    def forward(self, x, groups=1):
+        """groups > 1: x holds the images of `groups` tasks back to back (equal counts); every BatchNorm normalises each
+        group with its own batch statistics, so the result equals `groups` separate forwards while every convolution,
+        GEMM and normalisation kernel runs once on the whole batch."""
+        if groups > 1 and self.drop_path_rate > 0.0 and self.training:
+            raise ValueError("grouped stem passes are not combined with ResNet drop-path (per-call random streams)")
         dt = self.conv1.weight.dtype
+        _GROUPS[0] = groups
         tf32 = torch.backends.cudnn.allow_tf32
         if dt == torch.float32:
             torch.backends.cudnn.allow_tf32 = False      # fp32 parity mode must not silently drop to TF32
@@ -124,8 +131,9 @@ class ResNetStem(nn.Module):
         finally:
             torch.backends.cudnn.allow_tf32 = tf32
             if _TRACK:          # nn.BatchNorm2d bookkeeping: 94 counters, one multi-tensor kernel instead of 94 launches
-                torch._foreach_add_(list(_TRACK), 1)
+                torch._foreach_add_(list(_TRACK), groups)
                 del _TRACK[:]
+            _GROUPS[0] = 1
         B, Cc, h, w = x.shape
         self.last_hw = (h, w)
         return x.permute(0, 2, 3, 1).reshape(B, h * w, Cc)

@@ -286,3 +286,39 @@ def test_drop_worst_matches_oracle(name, rdrop):
     loss0, ss0, _ = crit(model, to_device(copy.deepcopy(samples[0]), "cuda", torch.float32) if not case.get("sample_patch_num")
                          else inp, update_num=3)
     assert ss0 > ss
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grouped_stem_pass_equals_per_task_stems(dtype):
+    """Multi-task micro-step with the images of all image tasks pushed through the ResNet stem in one grouped pass (per-task
+    BatchNorm statistics, running statistics updated in task order) vs one stem pass per task: loss, gradients, running
+    statistics and batch counters; and the grouped pass vs the oracle's sequential per-task forwards (fp32)."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    fx = load_golden("micro_multitask_rdrop")
+    case = fx["case"]
+    cfg, sd, samples = build_case(case)
+    res = []
+    for batched in (False, True):
+        model, task = build_product(cfg, sd, dtype=dtype)
+        model.train()
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0,
+                                                        batch_task_stems=batched)
+        loss, ss, _ = crit(model, to_device(copy.deepcopy(samples), "cuda", dtype))
+        loss.backward()
+        res.append((float(loss.detach()), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None},
+                    {n: b.float().clone() for n, b in model.named_buffers() if "running_" in n or "num_batches" in n}))
+    tol = 2e-4 if dtype == torch.float32 else 6e-2     # fp32: atomics order only; bf16: ReLU masks next to zero may flip
+    assert abs(res[0][0] - res[1][0]) <= (1e-5 if dtype == torch.float32 else 2e-2) * abs(res[0][0])
+    for n, b in res[0][2].items():
+        assert (b - res[1][2][n]).abs().max().item() <= (2e-4 if dtype == torch.float32 else 5e-2) * max(1.0, b.abs().max().item()), n
+    g0 = sum(float(v.norm()) ** 2 for v in res[0][1].values()) ** 0.5
+    g1 = sum(float(v.norm()) ** 2 for v in res[1][1].values()) ** 0.5
+    assert abs(g0 - g1) <= tol * g0, (g0, g1)
+    if dtype == torch.float32:
+        sdo = tie(sd)
+        ref_loss, _, _ = oo.criterion_forward(sdo, cfg, copy.deepcopy(samples), epsilon=0.1, use_rdrop=False, sample_patch_num=0)
+        ref_loss.backward()
+        ref_gn = sum(float(v.grad.norm()) ** 2 for k, v in sdo.items() if v.requires_grad and v.grad is not None
+                     and not k.startswith(("decoder.embed_tokens", "decoder.output_projection"))) ** 0.5
+        assert abs(res[1][0] - float(ref_loss.detach())) <= 1e-3 * abs(float(ref_loss.detach()))
+        assert abs(g1 - ref_gn) <= 1e-3 * ref_gn, (g1, ref_gn)
