@@ -26,9 +26,10 @@ def construct_rdrop_sample(x):
 class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
     def __init__(self, task, sentence_avg=False, label_smoothing=0.0, ignore_prefix_size=0, ignore_eos=False,
                  report_accuracy=False, drop_worst_ratio=0, drop_worst_after=0, use_rdrop=False, reg_alpha=1.0,
-                 sample_patch_num=196, constraint_range=None, batch_task_stems=True):
+                 sample_patch_num=196, constraint_range=None, batch_task_stems=True, batch_task_encoders=True):
         super().__init__()
         self.batch_task_stems = batch_task_stems
+        self.batch_task_encoders = batch_task_encoders and batch_task_stems
         self.task = task
         self.padding_idx = task.target_dictionary.pad()
         self.eos_idx = task.target_dictionary.eos()
@@ -63,9 +64,36 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
             return sample
         if getattr(stem, "drop_path_rate", 0.0) > 0.0 and stem.training:
             return sample
-        feats = stem(torch.cat(imgs, 0), groups=len(idx)).split(imgs[0].shape[0], 0)     # split: one cat in the backward
+        b = imgs[0].shape[0]
+        feats_all = stem(torch.cat(imgs, 0), groups=len(idx))
         hw = stem.last_hw
         out = list(sample)
+        nis = [sample[i]["net_input"] for i in idx]
+        merge = (self.batch_task_encoders and float(getattr(enc, "dropout_p", 0.0)) == 0.0 and
+                 all(ni.get("sample_patch_num") is None and ni.get("patch_images_2") is None for ni in nis) and
+                 not (self.sample_patch_num > 0 and 0 in idx))
+        if merge:
+            # ONE encoder pass for all image tasks: source tokens right-padded to the longest prompt (padded keys are masked
+            # and padded rows zeroed, so every real position computes what its own task's pass computes), then each task
+            # decodes against its slice of the encoder output.  Linear / LayerNorm / FFN kernels see 4x the rows.
+            pad = enc.padding_idx
+            S = max(ni["src_tokens"].shape[1] for ni in nis)
+            src = torch.cat([torch.nn.functional.pad(ni["src_tokens"], (0, S - ni["src_tokens"].shape[1]), value=pad)
+                             for ni in nis], 0)
+            masks = torch.cat([ni["patch_masks"] for ni in nis], 0)
+            eo = enc(src, src_lengths=None, patch_images=imgs[0], patch_masks=masks, patch_features=(feats_all, hw))
+            xs = eo["encoder_out"][0].transpose(0, 1).split(b, 0)              # [b, N, d] per task; split: one cat backward
+            pms = eo["encoder_padding_mask"][0].split(b, 0)
+            pos = eo["position_embeddings"][0].split(b, 0)
+            for k, i in enumerate(idx):
+                s = dict(sample[i])
+                s["net_input"] = dict(s["net_input"])
+                s["net_input"]["encoder_out"] = {"encoder_out": [xs[k].transpose(0, 1)], "encoder_padding_mask": [pms[k]],
+                                                 "position_embeddings": [pos[k]], "encoder_embedding": [],
+                                                 "encoder_states": [], "src_tokens": [], "src_lengths": []}
+                out[i] = s
+            return out
+        feats = feats_all.split(b, 0)                                           # split: one cat in the backward
         for k, i in enumerate(idx):
             s = dict(sample[i])
             s["net_input"] = dict(s["net_input"])

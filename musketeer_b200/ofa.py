@@ -643,13 +643,14 @@ class OFAModel(nn.Module):
     def forward(self, src_tokens, src_lengths, prev_output_tokens, patch_images=None, patch_images_2=None,
                 patch_masks=None, code_masks=None, sample_patch_num=None, features_only=False,
                 classification_head_name=None, token_embeddings=None, return_all_hiddens=False, alignment_layer=None,
-                alignment_heads=None, task_name=None, padded_logits=False, patch_features=None):
+                alignment_heads=None, task_name=None, padded_logits=False, patch_features=None, encoder_out=None):
         if classification_head_name is not None:
             raise NotImplementedError("classification heads are outside the hot-path scope (SURVEY.md 8)")
-        encoder_out = self.encoder(src_tokens, src_lengths=src_lengths, patch_images=patch_images,
-                                   patch_masks=patch_masks, patch_images_2=patch_images_2,
-                                   token_embeddings=token_embeddings, return_all_hiddens=return_all_hiddens,
-                                   sample_patch_num=sample_patch_num, patch_features=patch_features)
+        if encoder_out is None:       # (a multi-task criterion may hand over its slice of a merged encoder pass)
+            encoder_out = self.encoder(src_tokens, src_lengths=src_lengths, patch_images=patch_images,
+                                       patch_masks=patch_masks, patch_images_2=patch_images_2,
+                                       token_embeddings=token_embeddings, return_all_hiddens=return_all_hiddens,
+                                       sample_patch_num=sample_patch_num, patch_features=patch_features)
         self.enc_timer[1] += 1
         x, extra = self.decoder(prev_output_tokens, code_masks=code_masks, encoder_out=encoder_out,
                                 features_only=features_only, alignment_layer=alignment_layer,
