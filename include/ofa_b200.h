@@ -124,6 +124,11 @@ int ofa_attn_decode(const OfaDecodeArgs* args, int dtype, void* stream);
 int ofa_cache_gather(const void* src, void* dst, const long long* order, int rows, int L, int D, long long row_stride,
                      long long plane_stride, int planes, int dtype, void* stream);
 
+/* ---- 3x3 / stride 2 / padding 1 max-pool of the stem on bf16 NHWC activations (models/ofa/resnet.py:179,216).  idx: one
+ * byte per output element (window position of the first maximum); the backward gathers, no atomics.  C % 8 == 0.      */
+int ofa_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, int N, int H, int W, int C, void* stream);
+int ofa_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx, int N, int H, int W, int C, void* stream);
+
 /* ---- fused optimizer step (trainer.py:863-898 multiply_grads -> clip_grad_norm -> optimizer.step,
  * with the un-vendored fairseq Adam / FP16Optimizer arithmetic: fp32 master weights, decoupled weight decay
  * p -= wd*lr*p, bias-corrected step size, global-norm clipping with coefficient clip/(norm+1e-6)).

@@ -1,0 +1,117 @@
+// 3x3 / stride 2 / padding 1 max-pool of the ResNet stem on NHWC activations (models/ofa/resnet.py:179,216: nn.MaxPool2d),
+// forward and backward.  HBM-bound: one thread per output pixel and 8 channels (16-byte vectors); the forward stores the
+// window position of the maximum (first maximum in (kh, kw) scan order, like ATen) as one byte per element, the backward
+// GATHERS: every input pixel lies in at most four windows and sums the dy of those whose recorded maximum it is -- no
+// atomics, no zero-fill pass, deterministic.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          unsigned char* __restrict__ idx, int N, int H, int W, int C, int OH,
+                                                          int OW) {
+  pdl_sync();
+  const int c8 = C / 8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * OH * OW * c8) return;
+  const int cg = (int)(t % c8);
+  long long p = t / c8;
+  const int ow = (int)(p % OW); p /= OW;
+  const int oh = (int)(p % OH);
+  const int n = (int)(p / OH);
+  float best[8];
+  int bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { best[j] = -3.4e38f; bi[j] = 4; }   // the centre tap is always inside the image
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int h = oh * 2 - 1 + kh;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int w = ow * 2 - 1 + kw;
+      if (w < 0 || w >= W) continue;
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + cg * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > best[j]) { best[j] = v[j]; bi[j] = kh * 3 + kw; }
+    }
+  }
+  const long long o = (((long long)n * OH + oh) * OW + ow) * C + cg * 8;
+  *reinterpret_cast<uint4*>(y + o) = make_uint4(pack_bf16(best[0], best[1]), pack_bf16(best[2], best[3]),
+                                                pack_bf16(best[4], best[5]), pack_bf16(best[6], best[7]));
+  *reinterpret_cast<uint2*>(idx + o) = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24),
+                                                  bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const unsigned char* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
+                                                          int N, int H, int W, int C, int OH, int OW) {
+  pdl_sync();
+  const int c8 = C / 8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * H * W * c8) return;
+  const int cg = (int)(t % c8);
+  long long p = t / c8;
+  const int w = (int)(p % W); p /= W;
+  const int h = (int)(p % H);
+  const int n = (int)(p / H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  // windows covering input row h are oh = floor(h/2) (tap kh = h - 2*oh + 1) and, for odd h, oh = floor(h/2) + 1 (tap 0)
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    // candidate output rows: floor(h/2) and floor(h/2)+1 (the latter only covers h when h is odd)
+    const int oh = h / 2 + a;
+    const int kh = h - (oh * 2 - 1);
+    if (oh >= OH || kh < 0 || kh > 2) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ow = w / 2 + b;
+      const int kw = w - (ow * 2 - 1);
+      if (ow >= OW || kw < 0 || kw > 2) continue;
+      const long long o = (((long long)n * OH + oh) * OW + ow) * C + cg * 8;
+      const uint2 iv = *reinterpret_cast<const uint2*>(idx + o);
+      float g[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + o), g);
+      const int want = kh * 3 + kw;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int sel = ((j < 4 ? iv.x >> (8 * j) : iv.y >> (8 * (j - 4))) & 0xff);
+        if (sel == want) acc[j] += g[j];
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + (((long long)n * H + h) * W + w) * C + cg * 8) =
+      make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+}
+
+}  // namespace
+
+// see include/ofa_b200.h
+extern "C" int ofa_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, int N, int H, int W, int C, void* stream) {
+  OFA_CHECK(N > 0 && H > 0 && W > 0 && C % 8 == 0, "ofa_maxpool3x3s2_fwd: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long n = (long long)N * OH * OW * (C / 8);
+  OFA_CUDA(ofa_launch_pdl(maxpool_fwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
+                          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C, OH, OW));
+  return 0;
+}
+
+extern "C" int ofa_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx, int N, int H, int W, int C,
+                                    void* stream) {
+  OFA_CHECK(N > 0 && H > 0 && W > 0 && C % 8 == 0, "ofa_maxpool3x3s2_bwd: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long n = (long long)N * H * W * (C / 8);
+  OFA_CUDA(ofa_launch_pdl(maxpool_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
+                          (const __nv_bfloat16*)dy, idx, (__nv_bfloat16*)dx, N, H, W, C, OH, OW));
+  return 0;
+}

@@ -601,6 +601,35 @@ def mask_rows(x, rowmask):
     return _MaskRows.apply(x, rowmask)
 
 
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        N, Cc, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last)
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, Cc, OH, OW), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty(N * OH * OW * Cc, dtype=torch.uint8, device=x.device)
+        call("ofa_maxpool3x3s2_fwd", _p(x), _p(y), _p(idx), N, H, W, Cc, _st())
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, Cc, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        N, Cc, H, W = ctx.shape
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, Cc, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        call("ofa_maxpool3x3s2_bwd", _p(dy), _p(idx), _p(dx), N, H, W, Cc, _st())
+        return dx
+
+
+def max_pool3x3s2(x):
+    """nn.MaxPool2d(3, 2, 1) on a channels_last bf16 [N, C, H, W] tensor (C % 8 == 0)."""
+    return _MaxPool3x3s2.apply(x)
+
+
 _BN_SCRATCH = {}
 
 

@@ -3,8 +3,8 @@
 BatchNorm (+ReLU, +residual add, running-stat update, frozen / eval mode) runs on this library's fused NHWC kernels
 (ops.batch_norm); every 1x1 convolution is a tcgen05 GEMM on the NHWC bytes (ops.conv1x1) and every stride-1 3x3
 convolution the implicit-GEMM kernel of csrc/conv.cu (ops.conv3x3), forward / dgrad / wgrad, in bf16.  Still on cuDNN / ATen
-library kernels: the 7x7 stem convolution, the two stride-2 3x3 convolutions, the 3x3 max-pool, and all convolutions of
-the fp32 parity mode.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
+library kernels: the 7x7 stem convolution, the two stride-2 3x3 convolutions, and the convolutions / max-pool of the fp32
+parity mode (the bf16 max-pool is csrc/pool.cu).  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -126,7 +126,7 @@ class ResNetStem(nn.Module):
         try:
             x = x.to(dt).contiguous(memory_format=torch.channels_last)
             x = _bn(self.bn1, _conv(self.conv1, x), relu=True)
-            x = F.max_pool2d(x, 3, 2, 1)
+            x = ops.max_pool3x3s2(x) if x.dtype == torch.bfloat16 else F.max_pool2d(x, 3, 2, 1)
             x = self.layer3(self.layer2(self.layer1(x)))
         finally:
             torch.backends.cudnn.allow_tf32 = tf32

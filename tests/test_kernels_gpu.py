@@ -456,3 +456,22 @@ def test_gemm_fp32_accumulate_with_rowsum(M, N, K):
     assert (out - ref).abs().max().item() < 2e-3 * math.sqrt(K)
     rref = A[:, :M].float().sum(0)
     assert (rs - rref).abs().max().item() < 1e-3 * math.sqrt(K), (rs - rref).abs().max().item()
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 64, 32, 32), (3, 64, 17, 9), (1, 8, 5, 5), (2, 64, 192, 192)])
+def test_maxpool3x3s2(N, C, H, W):
+    """NHWC bf16 max-pool 3x3 / 2 / 1: forward bit-equal to F.max_pool2d; gather backward equal wherever the window maximum
+    is unique (bf16 ties inside a window may resolve to a different, equal-valued tap) and equal in total mass."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(H * W + C)
+    x = (torch.randn(N, C, H, W, generator=g) * 3).cuda().bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = ops.max_pool3x3s2(x)
+    xr = x.detach().float().requires_grad_()
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    assert y.shape == yr.shape and torch.equal(y.float(), yr)
+    dy = torch.randn(yr.shape, generator=g).cuda().bfloat16()
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert (x.grad.float().sum() - xr.grad.sum()).abs().item() <= 2e-2 * max(1.0, xr.grad.abs().sum().item() ** 0.5)
+    diff = (x.grad.float() - xr.grad).abs()
+    assert (diff > 3e-2).float().mean().item() < 0.02, (diff > 3e-2).float().mean().item()
