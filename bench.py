@@ -227,21 +227,24 @@ def main():
 
     def phases(nsteps):
         """Device time of the three phases of a step (graph replay | gradient all-reduce | optimizer), events on this rank."""
-        acc = [0.0, 0.0, 0.0]
+        acc = [0.0, 0.0, 0.0, 0.0]
         for i in range(nsteps):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record()
             graphed(resident[i % n_batches])
             ev[1].record()
+            if reducer is not None:
+                dist.barrier()            # separates waiting for the slowest rank from the collective itself
+            ev[2].record()
             if reducer is not None and not reducer.reduce_flat(model):
                 reducer.reduce_all()
-            ev[2].record()
-            optim.step()
             ev[3].record()
+            optim.step()
+            ev[4].record()
             torch.cuda.synchronize()
-            for k in range(3):
+            for k in range(4):
                 acc[k] += ev[k].elapsed_time(ev[k + 1]) / nsteps
-        return {"replay_ms": acc[0], "allreduce_ms": acc[1], "optimizer_ms": acc[2]}
+        return {"replay_ms": acc[0], "rank_skew_wait_ms": acc[1], "allreduce_ms": acc[2], "optimizer_ms": acc[3]}
 
     def timed(nsteps, e2e):
         if world > 1:

@@ -112,24 +112,36 @@ class GradReducer:
         if not flats:
             return False
         lo_hi = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in flats]
-        for p in self.params:
-            if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in lo_hi):
-                if getattr(p, "_ofa_zero_grad", False) or not bool(p.grad.any()):
-                    p._ofa_zero_grad = True       # unused parameter: zero on every rank (checked once)
-                    continue
-                return False
+        # gradients that autograd produced outside the arenas (library convolutions, c_attn, relative-position tables, ...):
+        # a few dozen small tensors, reduced through one temporary flat buffer
+        rest = [p for p in self.params
+                if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in lo_hi)]
         avg = dist.get_backend(self.pg) == "nccl"       # ReduceOp.AVG exists on NCCL only
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         works = []
         for f in flats:
             step = max(1, chunk_bytes // f.element_size())
             for o in range(0, f.numel(), step):
-                works.append(dist.all_reduce(f[o:o + step], op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM,
-                                             group=self.pg, async_op=True))
+                works.append(dist.all_reduce(f[o:o + step], op=op, group=self.pg, async_op=True))
+        tmp = None
+        if rest:
+            tmp = torch.cat([p.grad.reshape(-1) for p in rest])
+            works.append(dist.all_reduce(tmp, op=op, group=self.pg, async_op=True))
         for w in works:
             w.wait()
         if not avg:
             for f in flats:
                 f.div_(self.world)
+            if tmp is not None:
+                tmp.div_(self.world)
+        if tmp is not None:
+            off = 0
+            outs = []
+            for p in rest:
+                n = p.grad.numel()
+                outs.append(tmp[off:off + n].view_as(p.grad))
+                off += n
+            torch._foreach_copy_([p.grad for p in rest], outs)
         return True
 
     def reduce_all(self):

@@ -80,9 +80,12 @@ def _worker(rank, world, port, outdir):
     model.unused.grad = torch.zeros_like(model.unused)        # unused parameter: zeros outside the arenas are accepted
     assert red.reduce_flat(model, chunk_bytes=512)
     flatred = {n: p.grad.clone() for n, p in named}
-    model.unused.grad = torch.ones_like(model.unused)         # a real gradient outside the arenas -> refuse (caller falls back)
-    model.unused._ofa_zero_grad = False
-    assert not red.reduce_flat(model)
+    # a gradient outside the arenas is reduced through the temporary flat buffer
+    model.unused.grad = torch.full_like(model.unused, float(rank + 1))
+    assert red.reduce_flat(model, chunk_bytes=512)
+    assert torch.allclose(model.unused.grad, torch.full_like(model.unused, 1.5))
+    for n, p in named:          # (the arenas were averaged a second time: still the mean of equal values)
+        assert torch.allclose(p.grad, flatred[n], atol=1e-6), n
     torch.save((local, out, nosync, allred, flatred), os.path.join(outdir, "r%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
