@@ -119,7 +119,9 @@ class MultiheadAttention(nn.Module):
         self.q_proj = nn.Linear(embed_dim, embed_dim)
         self.out_proj = nn.Linear(embed_dim, embed_dim)
 
-    def project_kv(self, key):
+    def project_kv(self, key, fused=False):
+        if fused:       # one GEMM for k|v (training / teacher-forced cross-attention)
+            return ops.kv_linear(key, self.k_proj, self.v_proj)
         return _lin(self.k_proj, key), _lin(self.v_proj, key)
 
     def forward_self(self, h, pq, pk, tok_lut, img_lut, cfg):
@@ -545,7 +547,7 @@ class TransformerDecoder(nn.Module):
             self_kpm = prev_output_tokens.eq(self.padding_idx).contiguous().view(torch.uint8)
             self_cfg = {"causal": True, "kpm": self_kpm, "q_pos_off": t0,
                         "bias": {"q_text_off": 0, "k_text_off": 0}}
-            cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}}
+            cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}, "fused_kv": True}
         rel1d = self.rel_bucket_1d()
         inner_states = [x.transpose(0, 1)]
         for i, layer in enumerate(self.layers):
@@ -564,7 +566,7 @@ class TransformerDecoder(nn.Module):
             def cross_kv(attn, i=i):
                 if incremental:
                     return incremental_state["_ofa_b200"]["cross"][i]
-                return attn.project_kv(enc)
+                return attn.project_kv(enc, fused=True)
 
             x = layer(x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg)
             inner_states.append(x.transpose(0, 1))

@@ -318,58 +318,71 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None, dr, None
 
 
-class _QKVLinear(torch.autograd.Function):
-    """q|k|v projections of a self-attention as ONE GEMM over the concatenated weights ([3D, d]: three GEMM launches, three
-    dgrad launches + two adds and three wgrad launches become one each).  The softmax scaling multiplies the q columns in
-    the forward epilogue (alpha_cols) and dq on its way out of the attention backward (dq_scale), so the arithmetic per
-    element is that of q = (x Wq^T + bq) * s, k = x Wk^T + bk, v = x Wv^T + bv (unify_multihead_attention.py:213-232)."""
+class _FusedLinear(torch.autograd.Function):
+    """Several projections of the same input as ONE GEMM over the concatenated weights: q|k|v of a self-attention
+    ([3D, d]) or k|v of a cross-attention ([2D, d]); forward, dgrad and wgrad are one launch each instead of one per
+    projection (+ the adds of the separate input gradients).  With `scaling`, the first projection is the query: the
+    softmax scaling multiplies its columns in the forward epilogue (alpha_cols) and dq on its way out of the attention
+    backward (dq_scale), so the arithmetic per element is that of q = (x Wq^T + bq) * s, k = x Wk^T + bk, v = x Wv^T + bv
+    (unify_multihead_attention.py:213-232).  The gradients arrive side by side in one buffer when the attention backward
+    wrote them there (cfg fused_qkv / fused_kv); otherwise they are concatenated."""
 
     @staticmethod
-    def forward(ctx, x, wq, bq, wk, bk, wv, bv, scaling):
+    def forward(ctx, x, scaling, *params):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         M, K = x2.shape
-        D = wq.shape[0]
-        w = torch.cat([wq, wk, wv], 0)
-        b = torch.cat([bq, bk, bv], 0)
-        y = gemm(x2, w, M, 3 * D, K, bias=b, alpha=scaling, alpha_cols=D)
+        n = len(params) // 2
+        D = params[0].shape[0]
+        w = torch.cat(params[0::2], 0)
+        b = torch.cat(params[1::2], 0)
+        if scaling is not None:
+            y = gemm(x2, w, M, n * D, K, bias=b, alpha=scaling, alpha_cols=D)
+        else:
+            y = gemm(x2, w, M, n * D, K, bias=b)
         ctx.save_for_backward(x2, w)
-        ctx.params = (wq, bq, wk, bk, wv, bv)
-        ctx.shp, ctx.D = shp, D
-        y = y.view(*shp[:-1], 3 * D)
-        return y[..., :D], y[..., D:2 * D], y[..., 2 * D:]
+        ctx.params = params
+        ctx.shp, ctx.D, ctx.n = shp, D, n
+        y = y.view(*shp[:-1], n * D)
+        return tuple(y[..., i * D:(i + 1) * D] for i in range(n))
 
     @staticmethod
-    def backward(ctx, dq, dk, dv):
+    def backward(ctx, *dys):
         x2, w = ctx.saved_tensors
         M, K = x2.shape
-        D = ctx.D
-        es = dq.element_size()
-        fused = (dq.dim() == 3 and dq.stride() == dk.stride() == dv.stride() and dq.stride(-1) == 1 and
-                 dq.stride(-2) == 3 * D and dk.data_ptr() == dq.data_ptr() + D * es and
-                 dv.data_ptr() == dq.data_ptr() + 2 * D * es and dq.stride(0) == dq.shape[1] * 3 * D)
+        D, n = ctx.D, ctx.n
+        d0 = dys[0]
+        es = d0.element_size()
+        fused = (d0.dim() == 3 and d0.stride(-1) == 1 and d0.stride(-2) == n * D and d0.stride(0) == d0.shape[1] * n * D and
+                 all(d.stride() == d0.stride() and d.data_ptr() == d0.data_ptr() + i * D * es for i, d in enumerate(dys)))
         if fused:       # written side by side by the attention backward
-            dy2 = dq.as_strided((M, 3 * D), (3 * D, 1))
+            dy2 = d0.as_strided((M, n * D), (n * D, 1))
         else:
-            dy2 = torch.cat([dq.reshape(M, D), dk.reshape(M, D), dv.reshape(M, D)], 1)
-        dx = gemm(dy2, w, M, K, 3 * D, a_mn=False, b_mn=True).reshape(ctx.shp) if ctx.needs_input_grad[0] else None
-        wq, bq, wk, bk, wv, bv = ctx.params
-        grads = [None] * 6
-        t32 = _acc_group32([wq, wk, wv]) if x2.dtype == torch.bfloat16 else None
-        b32 = _acc_group32([bq, bk, bv]) if t32 is not None else None
+            dy2 = torch.cat([d.reshape(M, D) for d in dys], 1)
+        dx = gemm(dy2, w, M, K, n * D, a_mn=False, b_mn=True).reshape(ctx.shp) if ctx.needs_input_grad[0] else None
+        params = ctx.params
+        grads = [None] * (2 * n)
+        t32 = _acc_group32(list(params[0::2])) if x2.dtype == torch.bfloat16 else None
+        b32 = _acc_group32(list(params[1::2])) if t32 is not None else None
         if t32 is not None and b32 is not None:
-            gemm(dy2, x2, 3 * D, K, M, a_mn=True, b_mn=True, out=t32.view(3 * D, K), out_dtype=torch.float32, acc32=True,
+            gemm(dy2, x2, n * D, K, M, a_mn=True, b_mn=True, out=t32.view(n * D, K), out_dtype=torch.float32, acc32=True,
                  rowsum=b32)
         else:
-            dw = gemm(dy2, x2, 3 * D, K, M, a_mn=True, b_mn=True, out_dtype=wq.dtype)
+            dw = gemm(dy2, x2, n * D, K, M, a_mn=True, b_mn=True, out_dtype=params[0].dtype)
             db = colsum(dy2)
-            grads = [dw[:D], db[:D], dw[D:2 * D], db[D:2 * D], dw[2 * D:], db[2 * D:]]
-        return (dx, *grads, None)
+            for i in range(n):
+                grads[2 * i], grads[2 * i + 1] = dw[i * D:(i + 1) * D], db[i * D:(i + 1) * D]
+        return (dx, None, *grads)
 
 
 def qkv_linear(x, q_proj, k_proj, v_proj, scaling):
     """-> (q * scaling, k, v) as views of one [.., 3D] buffer (q_proj / k_proj / v_proj: nn.Linear parameter holders)."""
-    return _QKVLinear.apply(x, q_proj.weight, q_proj.bias, k_proj.weight, k_proj.bias, v_proj.weight, v_proj.bias, scaling)
+    return _FusedLinear.apply(x, scaling, q_proj.weight, q_proj.bias, k_proj.weight, k_proj.bias, v_proj.weight, v_proj.bias)
+
+
+def kv_linear(x, k_proj, v_proj):
+    """-> (k, v) as views of one [.., 2D] buffer (cross-attention keys / values of the encoder output)."""
+    return _FusedLinear.apply(x, None, k_proj.weight, k_proj.bias, v_proj.weight, v_proj.bias)
 
 
 def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False):
@@ -802,7 +815,12 @@ class _Attention(torch.autograd.Function):
         dpq = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
         dpk = torch.empty(B, S, D, dtype=q.dtype, device=q.device)
         dq_scale = float(cfg.get("dq_scale", 1.0))
-        if cfg.get("fused_qkv") and T == S:
+        if cfg.get("fused_kv"):
+            # cross-attention fed by the fused k|v projection: dk and dv side by side
+            dq = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+            dkv = torch.empty(B, S, 2 * D, dtype=q.dtype, device=q.device)
+            dk, dv = dkv[..., :D], dkv[..., D:]
+        elif cfg.get("fused_qkv") and T == S:
             # self-attention fed by the fused q|k|v projection: the three gradients land side by side in one [B, L, 3D]
             # buffer, which is the A operand of that projection's single dgrad / wgrad GEMM (no concatenation copy)
             dqkv = torch.empty(B, T, 3 * D, dtype=q.dtype, device=q.device)
