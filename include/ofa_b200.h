@@ -129,6 +129,11 @@ int ofa_cache_gather(const void* src, void* dst, const long long* order, int row
 int ofa_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, int N, int H, int W, int C, void* stream);
 int ofa_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx, int N, int H, int W, int C, void* stream);
 
+/* ---- patch matrix of the 7x7 / stride 2 / padding 3 stem convolution (models/ofa/resnet.py:176,214): x bf16 NHWC with
+ * C = 3 -> col bf16 [N*OH*OW][152], columns (c, kh, kw) as in weight.view(64, 147), 5 zero columns of row padding; the
+ * convolution and its weight gradient are ofa_gemm_bf16 calls on col.                                                   */
+int ofa_stem_patches(const void* x, void* col, int N, int H, int W, void* stream);
+
 /* ---- fused optimizer step (trainer.py:863-898 multiply_grads -> clip_grad_norm -> optimizer.step,
  * with the un-vendored fairseq Adam / FP16Optimizer arithmetic: fp32 master weights, decoupled weight decay
  * p -= wd*lr*p, bias-corrected step size, global-norm clipping with coefficient clip/(norm+1e-6)).

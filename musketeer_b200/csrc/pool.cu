@@ -115,3 +115,50 @@ extern "C" int ofa_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, vo
                           (const __nv_bfloat16*)dy, idx, (__nv_bfloat16*)dx, N, H, W, C, OH, OW));
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 7x7 / stride 2 / padding 3 stem convolution (models/ofa/resnet.py:176,214: conv1, 3 -> 64 channels) as patch matrix +
+// GEMM: with 3 input channels there is no 64-channel K block for the implicit-GEMM kernel, so the patches are written out
+// once, bf16 [N*OH*OW][152] (147 = 3*7*7 taps in (c, kh, kw) order -- the order of weight.view(64, 147) -- zero-padded to a
+// 16-byte row), and both the forward and the weight gradient are plain ofa_gemm_bf16 calls on it.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kStemK = 147, kStemKp = 152;
+__global__ void __launch_bounds__(256) stem_patches_kernel(const __nv_bfloat16* __restrict__ x /* NHWC, C = 3 */,
+                                                           __nv_bfloat16* __restrict__ col, int N, int H, int W, int OH, int OW) {
+  pdl_sync();
+  // one thread per (output pixel, tap row kh): 7 taps x 3 channels = 21 contiguous-ish input elements
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * OH * OW * 8) return;
+  const int kh = (int)(t & 7);
+  long long p = t >> 3;
+  const int ow = (int)(p % OW);
+  const int oh = (int)((p / OW) % OH);
+  const int n = (int)(p / ((long long)OW * OH));
+  __nv_bfloat16* dst = col + p * kStemKp;
+  if (kh == 7) {                      // the padding columns 147..151
+#pragma unroll
+    for (int j = kStemK; j < kStemKp; ++j) dst[j] = __float2bfloat16(0.f);
+    return;
+  }
+  const int h = oh * 2 - 3 + kh;
+  const bool hin = h >= 0 && h < H;
+#pragma unroll
+  for (int kw = 0; kw < 7; ++kw) {
+    const int w = ow * 2 - 3 + kw;
+    const bool in = hin && w >= 0 && w < W;
+    const __nv_bfloat16* src = x + (((long long)n * H + (hin ? h : 0)) * W + (in ? w : 0)) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[c * 49 + kh * 7 + kw] = in ? src[c] : __float2bfloat16(0.f);
+  }
+}
+}  // namespace
+
+extern "C" int ofa_stem_patches(const void* x, void* col, int N, int H, int W, void* stream) {
+  OFA_CHECK(N > 0 && H > 0 && W > 0, "ofa_stem_patches: bad shape");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long n = (long long)N * OH * OW * 8;
+  OFA_CUDA(ofa_launch_pdl(stem_patches_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
+                          (const __nv_bfloat16*)x, (__nv_bfloat16*)col, N, H, W, OH, OW));
+  return 0;
+}

@@ -614,6 +614,44 @@ def mask_rows(x, rowmask):
     return _MaskRows.apply(x, rowmask)
 
 
+class _StemConv7x7(torch.autograd.Function):
+    """conv1 of the ResNet stem (7x7, stride 2, padding 3, 3 -> Cout channels, no bias) as patch matrix + tcgen05 GEMM.
+    x: channels_last [N, 3, H, W] bf16 (no gradient: it is the image); w: [Cout, 3, 7, 7]."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        _need_cuda(x)
+        N, Cin, H, W = x.shape
+        assert Cin == 3 and tuple(w.shape[1:]) == (3, 7, 7)
+        x = x.contiguous(memory_format=torch.channels_last)
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        M, Cout = N * OH * OW, w.shape[0]
+        col = torch.empty(M, 152, dtype=x.dtype, device=x.device)
+        call("ofa_stem_patches", _p(x), _p(col), N, H, W, _st())
+        wp = torch.zeros(Cout, 152, dtype=w.dtype, device=w.device)
+        wp[:, :147] = w.detach().reshape(Cout, 147)
+        y = gemm(col[:, :147], wp[:, :147], M, Cout, 147)
+        ctx.save_for_backward(col)
+        ctx.w_param, ctx.dims = w, (N, Cout, OH, OW)
+        return y.view(N, OH, OW, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (col,) = ctx.saved_tensors
+        N, Cout, OH, OW = ctx.dims
+        M = N * OH * OW
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dy2 = dy.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(M, Cout)
+            dwp = gemm(dy2, col[:, :147], Cout, 147, M, a_mn=True, b_mn=True, out_dtype=dy.dtype, ldd=152)
+            dw = dwp[:, :147].reshape(ctx.w_param.shape)
+        return None, dw
+
+
+def stem_conv7x7(x, weight):
+    return _StemConv7x7.apply(x, weight)
+
+
 class _MaxPool3x3s2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

@@ -3,8 +3,8 @@
 BatchNorm (+ReLU, +residual add, running-stat update, frozen / eval mode) runs on this library's fused NHWC kernels
 (ops.batch_norm); every 1x1 convolution is a tcgen05 GEMM on the NHWC bytes (ops.conv1x1) and every stride-1 3x3
 convolution the implicit-GEMM kernel of csrc/conv.cu (ops.conv3x3), forward / dgrad / wgrad, in bf16.  Still on cuDNN / ATen
-library kernels: the 7x7 stem convolution, the two stride-2 3x3 convolutions, and the convolutions / max-pool of the fp32
-parity mode (the bf16 max-pool is csrc/pool.cu).  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
+library kernels: the two stride-2 3x3 convolutions, and the convolutions / max-pool of the fp32 parity mode (the bf16 7x7
+stem convolution = patch matrix + GEMM and the bf16 max-pool are csrc/pool.cu).  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -51,7 +51,10 @@ def _conv(mod, x):
             if w.grad is not None:
                 w.grad = None
         return ops.conv3x3(x, w)                                   # implicit-GEMM tcgen05 kernel (csrc/conv.cu)
-    # 7x7 stem, the two stride-2 3x3 convolutions and the fp32 parity mode: library convolution
+    if (mod.kernel_size == (7, 7) and mod.stride == (2, 2) and mod.padding == (3, 3) and mod.in_channels == 3
+            and x.dtype == torch.bfloat16):
+        return ops.stem_conv7x7(x, mod.weight)                     # patch matrix + tcgen05 GEMM (csrc/pool.cu)
+    # the two stride-2 3x3 convolutions and the fp32 parity mode: library convolution
     return F.conv2d(x, mod.weight, None, mod.stride, mod.padding)
 
 

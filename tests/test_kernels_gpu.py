@@ -475,3 +475,21 @@ def test_maxpool3x3s2(N, C, H, W):
     assert (x.grad.float().sum() - xr.grad.sum()).abs().item() <= 2e-2 * max(1.0, xr.grad.abs().sum().item() ** 0.5)
     diff = (x.grad.float() - xr.grad).abs()
     assert (diff > 3e-2).float().mean().item() < 0.02, (diff > 3e-2).float().mean().item()
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 64), (1, 37, 29), (3, 96, 96)])
+def test_stem_conv7x7_patches_gemm(N, H, W):
+    """7x7 / 2 / 3 stem convolution as patch matrix + GEMM vs F.conv2d in fp64 on the same bf16 operands: y and dw."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(H + W)
+    x = torch.randn(N, 3, H, W, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 147 ** -0.5).cuda().bfloat16().requires_grad_()
+    y = ops.stem_conv7x7(x, w)
+    dy = torch.randn(y.shape, generator=g).cuda().bfloat16()
+    y.backward(dy)
+    wf = w.detach().double().cpu().requires_grad_()
+    yr = F.conv2d(x.double().cpu(), wf, None, 2, 3)
+    yr.backward(dy.double().cpu())
+    assert y.shape == yr.shape
+    assert (y.double().cpu() - yr).abs().max().item() < 2e-2 * max(1.0, yr.abs().max().item())
+    assert (w.grad.double().cpu() - wf.grad).abs().max().item() < 2e-2 * max(1.0, wf.grad.abs().max().item())
