@@ -17,7 +17,7 @@ class SequenceGenerator(torch.nn.Module):
                  normalize_scores=True, len_penalty=1.0, unk_penalty=0.0, temperature=1.0, match_source_len=False,
                  no_repeat_ngram_size=0, search_strategy=None, eos=None, symbols_to_strip_from_output=None,
                  lm_model=None, lm_weight=1.0, constraint_trie=None, constraint_range=None, gen_code=False,
-                 gen_box=False, ignore_eos=False, zero_shot=False):
+                 gen_box=False, ignore_eos=False, zero_shot=False, cuda_graphs=True):
         super().__init__()
         models = list(models) if isinstance(models, (list, tuple)) else [models]
         if len(models) != 1 or lm_model is not None:
@@ -43,6 +43,11 @@ class SequenceGenerator(torch.nn.Module):
             self.constraint_start, self.constraint_end = int(cs), int(ce)
         assert temperature > 0, "--temperature must be greater than 0"
         self.model.eval()
+        # Decoder steps >= 1 are captured as CUDA graphs per (rows, source length, step) on the second call with a given shape
+        # and replayed afterwards while no sentence has finished (the batch shrinks then and the search continues eagerly):
+        # a step is ~300 small launches, so the beam search is host-bound without it.
+        self.cuda_graphs = cuda_graphs
+        self._static = {}
 
     @torch.no_grad()
     def forward(self, sample, prefix_tokens=None, bos_token=None):
@@ -79,8 +84,23 @@ class SequenceGenerator(torch.nn.Module):
         # the cross-attention K / V once per sentence and maps beam rows onto them (ofa.py incremental path)
         enc = model.encoder.forward_torchscript(net_input)
         scores = torch.zeros(bsz * beam, max_len + 1, device=dev)
-        tokens = torch.full((bsz * beam, max_len + 2), self.pad, dtype=torch.long, device=dev)
+        static = None
+        if self.cuda_graphs and dev.type == "cuda":
+            sig = (bsz, beam, max_len, enc["encoder_out"][0].shape[0], str(enc["encoder_out"][0].dtype))
+            static = self._static.get(sig)
+            if static is None:
+                static = self._static[sig] = {
+                    "tokens": torch.empty((bsz * beam, max_len + 2), dtype=torch.long, device=dev),
+                    "order": torch.zeros(bsz * beam, dtype=torch.long, device=dev),
+                    "inc": {"_ofa_b200": {"reuse": True}}, "graphs": {}, "calls": 0, "pool": None}
+            static["calls"] += 1
+        if static is not None:
+            tokens = static["tokens"]
+            tokens.fill_(self.pad)
+        else:
+            tokens = torch.full((bsz * beam, max_len + 2), self.pad, dtype=torch.long, device=dev)
         tokens[:, 0] = self.bos
+        bsz0 = bsz
         cands_to_ignore = torch.zeros(bsz, beam, dtype=torch.bool, device=dev)
         finalized: List[List[Dict]] = [[] for _ in range(bsz)]
         finished = [False] * bsz
@@ -88,15 +108,20 @@ class SequenceGenerator(torch.nn.Module):
         cand_size = 2 * beam
         bbsz_offsets = (torch.arange(bsz, device=dev) * beam).unsqueeze(1)
         cand_offsets = torch.arange(cand_size, device=dev)
-        inc = {}
+        inc = static["inc"] if static is not None else {}
         reorder_state = batch_idxs = None
         for step in range(max_len + 1):
-            if reorder_state is not None:
-                if batch_idxs is not None:
-                    corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
-                    reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
-                model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
-            logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
+            if reorder_state is not None and batch_idxs is not None:
+                corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
+                reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
+            graphable = (static is not None and step >= 1 and bsz == bsz0 and batch_idxs is None and static["calls"] >= 2
+                         and tokens is static["tokens"])
+            if graphable:
+                logits = self._graphed_step(model, static, step, tokens, enc, inc, reorder_state)
+            else:
+                if reorder_state is not None:
+                    model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
+                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
             logits = logits[:, -1, :].float() / self.temperature
             if self.constraint_start is not None:
                 logits[:, 4:self.constraint_start] = -math.inf
@@ -169,6 +194,28 @@ class SequenceGenerator(torch.nn.Module):
             _, o = torch.sort(sc, descending=True)
             finalized[s] = [finalized[s][i] for i in o]
         return finalized
+
+    def _graphed_step(self, model, static, step, tokens, enc, inc, reorder_state):
+        """Beam reorder + one decoder step as a CUDA graph.  The graph holds pointers into the persistent token buffer, the
+        reorder-index buffer and the decoder's KV-cache state; the Python side of that state (ping-pong index, length, the
+        group -> sentence map tensor) is restored to its post-step value after every replay."""
+        st = inc["_ofa_b200"]
+        static["order"].copy_(reorder_state)
+        key = (step, st.get("layout", 0))
+        g = static["graphs"].get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=static["pool"]):
+                model.decoder.reorder_incremental_state_scripting(inc, static["order"])
+                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
+            if static["pool"] is None:
+                static["pool"] = graph.pool()
+            g = static["graphs"][key] = {"graph": graph, "logits": logits,
+                                         "post": (st["cur"], st["len"], st["sent_row"], st["rows"])}
+        g["graph"].replay()
+        st["cur"], st["len"], st["sent_row"], st["rows"] = g["post"]
+        return g["logits"]
 
     def _finalize(self, step, bbsz_idx, eos_scores, tokens, scores, finalized, finished, beam, max_len):
         tokens_clone = tokens.index_select(0, bbsz_idx)[:, 1:step + 2].clone()

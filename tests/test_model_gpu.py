@@ -152,13 +152,28 @@ def test_beam_search_tokens_bit_exact_fp32(name):
     model.eval()
     sample = to_device(synth.make_batch(**case["batch"]), "cuda")
     gen = SequenceGenerator([model], task.target_dictionary, **case["gen"])
-    hyp = gen.generate([model], sample)
-    assert len(hyp) == len(fx["tokens"])
-    for s in range(len(hyp)):
-        assert len(hyp[s]) == len(fx["tokens"][s])
-        for h, t, sc in zip(hyp[s], fx["tokens"][s], fx["scores"][s]):
-            assert torch.equal(h["tokens"].cpu(), t), (s, h["tokens"].tolist(), t.tolist())
-            assert abs(float(h["score"]) - sc) < 1e-4
+    # call 1 runs every decoder step eagerly, call 2 captures the steps as CUDA graphs (and replays them), call 3 replays:
+    # all three must reproduce the reference's tokens
+    for call in range(3):
+        hyp = gen.generate([model], sample)
+        assert len(hyp) == len(fx["tokens"])
+        for s in range(len(hyp)):
+            assert len(hyp[s]) == len(fx["tokens"][s])
+            for h, t, sc in zip(hyp[s], fx["tokens"][s], fx["scores"][s]):
+                assert torch.equal(h["tokens"].cpu(), t), (call, s, h["tokens"].tolist(), t.tolist())
+                assert abs(float(h["score"]) - sc) < 1e-4
+    if name == "gen_micro":
+        # replayed steps hold pointers into persistent buffers: a different batch of the same shape must give what a
+        # graph-free generator gives
+        b2 = dict(case["batch"], seed=case["batch"].get("seed", 0) + 17)
+        sample2 = to_device(synth.make_batch(**b2), "cuda")
+        ref = SequenceGenerator([model], task.target_dictionary, cuda_graphs=False, **case["gen"]).generate([model], sample2)
+        got = gen.generate([model], sample2)
+        assert any(len(g["graphs"]) for g in gen._static.values())
+        for hs, rs in zip(got, ref):
+            assert len(hs) == len(rs)
+            for h, r in zip(hs, rs):
+                assert torch.equal(h["tokens"], r["tokens"]) and abs(float(h["score"]) - float(r["score"])) < 1e-5
 
 
 def test_incremental_decoder_matches_teacher_forcing():
