@@ -171,22 +171,37 @@ __global__ void __launch_bounds__(kT) attn_decode_kernel(OfaDecodeArgs a) {
   float o0[GMAX], o1[GMAX];
 #pragma unroll
   for (int g = 0; g < GMAX; ++g) { o0[g] = 0.f; o1[g] = 0.f; }
-  for (int j = warp; j < S; j += kT / 32) {
-    float v0, v1;
-    if (sizeof(T) == 2) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
-          reinterpret_cast<const __nv_bfloat16*>(V) + (size_t)j * a.ldv + lane * 2));
-      v0 = f.x; v1 = f.y;
-    } else {
-      const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(V) + (size_t)j * a.ldv + lane * 2);
-      v0 = f.x; v1 = f.y;
+  // eight keys per iteration: the eight V loads are issued together (the loop is L2-latency-bound otherwise)
+  constexpr int U = 8, NW = kT / 32;
+  for (int j0 = warp; j0 < S; j0 += U * NW) {
+    float v0[U], v1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * NW;
+      v0[u] = 0.f; v1[u] = 0.f;
+      if (j < S) {
+        if (sizeof(T) == 2) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+              reinterpret_cast<const __nv_bfloat16*>(V) + (size_t)j * a.ldv + lane * 2));
+          v0[u] = f.x; v1[u] = f.y;
+        } else {
+          const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(V) + (size_t)j * a.ldv + lane * 2);
+          v0[u] = f.x; v1[u] = f.y;
+        }
+      }
     }
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) {
-      if (g < G) {
-        const float p = ps[g * S + j];
-        o0[g] = fmaf(p, v0, o0[g]);
-        o1[g] = fmaf(p, v1, o1[g]);
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * NW;
+      if (j < S) {
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g) {
+          if (g < G) {
+            const float p = ps[g * S + j];
+            o0[g] = fmaf(p, v0[u], o0[g]);
+            o1[g] = fmaf(p, v1[u], o1[g]);
+          }
+        }
       }
     }
   }
