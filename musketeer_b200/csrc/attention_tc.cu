@@ -274,6 +274,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //   buffers) and added into an fp32 accumulator by TMA reduce (cp.reduce.async.bulk.tensor .add: four 16 KB bulk
 //   operations per tile pair instead of 4096 red.global.add.v4 per CTA, which saturated the L2 atomic units);
 //   relative-position table gradients are privatised in shared-memory histograms.
+// -DOFA_ATTN_DEBUG: clock64() stamps of thread 0 of one CTA around every phase of the backward main loop, per query tile
+// (tools/attn_phase_debug.py reads them through ofa_attn_debug_read).  Not compiled into the shipped library.
+#ifdef OFA_ATTN_DEBUG
+__device__ long long g_attn_dbg[128];
+#define DBG_T(i) if (dbg && t == 0) { const long long now_ = clock64(); g_attn_dbg[(it & 7) * 12 + (i)] += now_ - dbg_last; dbg_last = now_; }
+#else
+#define DBG_T(i)
+#endif
 constexpr int BK2 = 128;
 constexpr int kBwdThreads = 512;   // 4 threads per query row, 32 key columns each
 constexpr int kTokHist = 1024 + 128;
@@ -373,10 +381,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t id_dq = umma_idesc_bf16(128, 128, 0, 1);   // dQ' = dS K'
   const int col0 = qd * 32;
 
+#ifdef OFA_ATTN_DEBUG
+  const bool dbg = blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == 1;
+  long long dbg_last = clock64();
+#endif
   int it = 0;
   for (int qt = qt0; qt < nq_tiles; ++qt, ++it) {
     const uint32_t ph = it & 1;
     const int q0 = qt * BQ;
+    DBG_T(0)
     if (t == 0) {
       if (it == 0) mbar_wait(&sm.bar_kv, 0);
       mbar_wait(&sm.bar_q, ph);
@@ -420,8 +433,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       else if ((keys_all_txt && !q_text) || (keys_all_img && !q_img) || (!bz.tok_lut && !bz.img_lut)) mode = 0;
     }
 
+    DBG_T(1)
     mbar_wait(&sm.bar_sp, ph);
     tc_fence_after();
+    DBG_T(2)
     float dsv[32];
     {
       uint32_t rs[32], rp[32];
@@ -485,9 +500,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                        pack_bf16(dsv[c16 * 8 + 4], dsv[c16 * 8 + 5]), pack_bf16(dsv[c16 * 8 + 6], dsv[c16 * 8 + 7]));
       }
     }
+    DBG_T(3)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    DBG_T(4)
     if (t == 0) {
       tc_fence_after();
       const uint32_t acc = it != 0;
@@ -506,6 +523,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(&sm.bar_dq);
     }
     __syncwarp();
+    DBG_T(9)
     // relative-position table gradients: shared-memory histogram updates (fp32 shared atomics are CAS loops) run here,
     // under the three tensor-core GEMMs just issued, instead of in front of them
     if (mode == 1) {
@@ -529,8 +547,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    DBG_T(5)
     mbar_wait(&sm.bar_dq, ph);
     tc_fence_after();
+    DBG_T(6)
     if (t == 0 && qt + 1 < nq_tiles) {   // Q' / dO / P / dS buffers are free again
       mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
       tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, q0 + BQ, b);
@@ -549,9 +569,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         *reinterpret_cast<uint4*>(slab + r * 128 + ((v4 ^ (r & 7)) << 4)) =
             make_uint4(rq[v4 * 4], rq[v4 * 4 + 1], rq[v4 * 4 + 2], rq[v4 * 4 + 3]);
     }
+    DBG_T(7)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    DBG_T(8)
     if (t == 0) {
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) tma_reduce_add_4d(&tmDQ, sm.p[0] + s4 * (BQ * 128), s4 * 32, h, q0, b);
@@ -669,6 +691,14 @@ int make_qkv_tmap(CUtensorMap* tm, const void* p, int L, int H, int B, long long
 
 }  // namespace
 
+#ifdef OFA_ATTN_DEBUG
+extern "C" int ofa_attn_debug_read(long long* out) {
+  cudaMemcpyFromSymbol(out, g_attn_dbg, sizeof(long long) * 128);
+  long long z[128] = {0};
+  cudaMemcpyToSymbol(g_attn_dbg, z, sizeof(z));
+  return 0;
+}
+#endif
 extern "C" int ofa_attn_fwd_tc(const AttnArgs* a, void* stream) {
   OFA_CHECK(a->T > 0 && a->S > 0 && a->B > 0 && a->H > 0, "ofa_attn_fwd_tc: empty problem");
   OFA_CHECK(a->pq && a->pk, "ofa_attn_fwd_tc: the absolute-position operands pq/pk are required");
