@@ -151,8 +151,8 @@ int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* target, const
                       const float* conf, int rows_per_sample, int R, int V, long long pad_idx, float eps, int cs,
                       int ce, int rdrop, float reg_alpha, float* loss_rows, float* nll_rows, float* kl_rows, int dtype,
                       void* stream);
-int ofa_scale_rows(void* x, long long ld, int R, int V, const float* scale, const unsigned char* row_keep, int dtype,
-                   void* stream);
+int ofa_scale_rows(void* x, long long ld, int R, int V, const float* scale, const unsigned char* row_keep,
+                   int scale_per_row, int dtype, void* stream); /* scale: device scalar, or one factor per row */
 
 /* ---- attention with OFA position biases (unify_multihead_attention.py:345-398; bias assembly of
  * unify_transformer.py:640-658,906-933,1282-1318,1519-1529 computed in-kernel) ------------------------------------- */

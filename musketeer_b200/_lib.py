@@ -77,7 +77,7 @@ SIGNATURES = {
     "ofa_maxpool3x3s2_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "ofa_stem_patches": [c_p, c_p, c_i, c_i, c_i, c_p],
     "ofa_adam_step": [c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_p],
-    "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p],
+    "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
     "ofa_attn_fwd_simt": [C.POINTER(OfaAttnArgs), c_i, c_p],
     "ofa_attn_bwd_simt": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_i, c_p],
     "ofa_attn_fwd_tc": [C.POINTER(OfaAttnArgs), c_p],

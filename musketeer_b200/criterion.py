@@ -26,10 +26,12 @@ def construct_rdrop_sample(x):
 class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
     def __init__(self, task, sentence_avg=False, label_smoothing=0.0, ignore_prefix_size=0, ignore_eos=False,
                  report_accuracy=False, drop_worst_ratio=0, drop_worst_after=0, use_rdrop=False, reg_alpha=1.0,
-                 sample_patch_num=196, constraint_range=None, batch_task_stems=True, batch_task_encoders=True):
+                 sample_patch_num=196, constraint_range=None, batch_task_stems=True, batch_task_encoders=True,
+                 batch_task_decoders=True):
         super().__init__()
         self.batch_task_stems = batch_task_stems
         self.batch_task_encoders = batch_task_encoders and batch_task_stems
+        self.batch_task_decoders = batch_task_decoders and self.batch_task_encoders
         self.task = task
         self.padding_idx = task.target_dictionary.pad()
         self.eos_idx = task.target_dictionary.eos()
@@ -92,6 +94,8 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
                                                  "position_embeddings": [pos[k]], "encoder_embedding": [],
                                                  "encoder_states": [], "src_tokens": [], "src_lengths": []}
                 out[i] = s
+            if self.batch_task_decoders:
+                self._batch_decoders(model, out, idx, xs, pms, pos, b)
             return out
         feats = feats_all.split(b, 0)                                           # split: one cat in the backward
         for k, i in enumerate(idx):
@@ -100,6 +104,51 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
             s["net_input"]["patch_features"] = (feats[k], hw)
             out[i] = s
         return out
+
+    def _batch_decoders(self, model, out, idx, xs, pms, pos, b):
+        """Tasks of the merged encoder pass whose targets have similar lengths share ONE decoder pass + ONE loss launch
+        (targets right-padded to the longest: padded positions are masked keys and pad targets).  The per-row losses come
+        back as a vector, so every task still gets the sum over its own rows and its own sample size.  Tasks with
+        constraint masks / confidences keep their own pass."""
+        pad = self.padding_idx
+        cand = [(k, i) for k, i in enumerate(idx) if out[i].get("constraint_masks") is None and out[i].get("conf") is None]
+        cand.sort(key=lambda ki: out[ki[1]]["net_input"]["prev_output_tokens"].shape[1])
+        groups, cur = [], []
+        for k, i in cand:
+            T = out[i]["net_input"]["prev_output_tokens"].shape[1]
+            if cur:
+                T0 = out[cur[0][1]]["net_input"]["prev_output_tokens"].shape[1]      # shortest of the group
+                if not (T <= 32 or T0 >= 0.8 * T):
+                    groups.append(cur)
+                    cur = []
+            cur.append((k, i))
+        if cur:
+            groups.append(cur)
+        for grp in groups:
+            if len(grp) < 2:
+                continue
+            Tm = max(out[i]["net_input"]["prev_output_tokens"].shape[1] for _, i in grp)
+            prevs, tgts = [], []
+            for _, i in grp:
+                prev, tgt = out[i]["net_input"]["prev_output_tokens"], out[i]["target"]
+                if self.ignore_prefix_size > 0:
+                    tgt = tgt.clone()
+                    tgt[:, :self.ignore_prefix_size] = pad
+                if self.ignore_eos:
+                    tgt = tgt.masked_fill(tgt.eq(self.eos_idx), pad)
+                prevs.append(torch.nn.functional.pad(prev, (0, Tm - prev.shape[1]), value=pad))
+                tgts.append(torch.nn.functional.pad(tgt, (0, Tm - tgt.shape[1]), value=pad))
+            eo = {"encoder_out": [torch.cat([xs[k] for k, _ in grp], 0).transpose(0, 1)],
+                  "encoder_padding_mask": [torch.cat([pms[k] for k, _ in grp], 0)],
+                  "position_embeddings": [torch.cat([pos[k] for k, _ in grp], 0)]}
+            logits, _ = model.decoder(torch.cat(prevs, 0), encoder_out=eo, padded_logits=True)
+            if hasattr(model, "dec_timer"):
+                model.dec_timer[1] += 1
+            loss_rows, nll_rows = ops.ls_cross_entropy_rows(logits, torch.cat(tgts, 0), self.eps, pad,
+                                                            crange=self.constraint_range)
+            n = b * Tm
+            for g, (_, i) in enumerate(grp):
+                out[i]["_precomputed"] = (loss_rows[g * n:(g + 1) * n].sum(), nll_rows[g * n:(g + 1) * n].sum())
 
     def forward(self, model, sample, update_num=0, reduce=True, _top=True):
         if isinstance(sample, list) and len(sample) > 1 and _top:
@@ -122,16 +171,21 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
         if self.use_rdrop:
             sample = construct_rdrop_sample(sample)
         drop = self.drop_worst_ratio if (self.drop_worst_ratio > 0 and update_num > self.drop_worst_after) else 0.0
-        logits, _ = model(**sample["net_input"], padded_logits=True)
+        pre = sample.get("_precomputed") if drop == 0 else None      # this task's rows of a merged decoder pass
+        if pre is None:
+            logits, _ = model(**sample["net_input"], padded_logits=True)
         target = sample["target"]
         if self.ignore_prefix_size > 0:                                                 # :239-243
             target = target.clone()
             target[:, :self.ignore_prefix_size] = self.padding_idx
         if self.ignore_eos:                                                             # :244-250
             target = target.masked_fill(target.eq(self.eos_idx), self.padding_idx)
-        loss, nll_rows = ops.ls_cross_entropy(
-            logits, target, self.eps, self.padding_idx, cmask=sample.get("constraint_masks"), conf=sample.get("conf"),
-            crange=self.constraint_range, rdrop=self.use_rdrop, reg_alpha=self.reg_alpha, drop_worst_ratio=drop)
+        if pre is not None:
+            loss, nll_rows = pre
+        else:
+            loss, nll_rows = ops.ls_cross_entropy(
+                logits, target, self.eps, self.padding_idx, cmask=sample.get("constraint_masks"), conf=sample.get("conf"),
+                crange=self.constraint_range, rdrop=self.use_rdrop, reg_alpha=self.reg_alpha, drop_worst_ratio=drop)
         if drop > 0:          # ntokens = rows kept (label_smoothed_cross_entropy.py:113)
             n = int(target.ne(self.padding_idx).sum())
             ntokens = 2 * int((n // 2) * (1 - drop)) if self.use_rdrop else int(n * (1 - drop))

@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
 
 template <typename T>
 __global__ void scale_rows_kernel(T* __restrict__ x, long long ld, int V, const float* __restrict__ scale,
-                                  const unsigned char* __restrict__ row_keep) {
+                                  const unsigned char* __restrict__ row_keep, int per_row) {
   pdl_sync();
   const int r = blockIdx.x;
-  const float s = (row_keep && !row_keep[r]) ? 0.f : *scale;
+  const float s = (row_keep && !row_keep[r]) ? 0.f : scale[per_row ? r : 0];
   T* xr = x + (size_t)r * ld;
   for (int v = threadIdx.x; v < V; v += blockDim.x) xr[v] = (T)((float)xr[v] * s);
 }
@@ -197,13 +197,14 @@ extern "C" int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* ta
   return 0;
 }
 
-// dlogits[r, :] *= *scale (device scalar: upstream grad), rows with row_keep==0 zeroed (drop-worst, :100-111)
+// dlogits[r, :] *= scale (device scalar, or scale[r] with scale_per_row: the upstream gradient of every row's loss -- rows of
+// several tasks normalised by their own sample sizes), rows with row_keep==0 zeroed (drop-worst, :100-111)
 extern "C" int ofa_scale_rows(void* x, long long ld, int R, int V, const float* scale, const unsigned char* row_keep,
-                              int dtype, void* stream) {
+                              int scale_per_row, int dtype, void* stream) {
   OFA_CHECK(R > 0 && V > 0, "ofa_scale_rows: R=%d V=%d", R, V);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == OFA_BF16) OFA_CUDA(ofa_launch_pdl(scale_rows_kernel<__nv_bfloat16>, R, 512, 0, st, (__nv_bfloat16*)x, ld, V, scale, row_keep));
-  else if (dtype == OFA_F32) OFA_CUDA(ofa_launch_pdl(scale_rows_kernel<float>, R, 512, 0, st, (float*)x, ld, V, scale, row_keep));
+  if (dtype == OFA_BF16) OFA_CUDA(ofa_launch_pdl(scale_rows_kernel<__nv_bfloat16>, R, 512, 0, st, (__nv_bfloat16*)x, ld, V, scale, row_keep, scale_per_row));
+  else if (dtype == OFA_F32) OFA_CUDA(ofa_launch_pdl(scale_rows_kernel<float>, R, 512, 0, st, (float*)x, ld, V, scale, row_keep, scale_per_row));
   else return ofa_set_error("ofa_scale_rows: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("scale_rows_kernel");
   return 0;

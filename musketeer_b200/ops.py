@@ -985,8 +985,47 @@ class _LsCe(torch.autograd.Function):
         dlogits = ctx.dlogits
         B, T, V = dlogits.shape
         scale = gloss.float().reshape(1).contiguous()
-        call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(ctx.row_keep), _dt(dlogits), _st())
+        call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(ctx.row_keep), 0, _dt(dlogits), _st())
         return dlogits, None, None, None, None, None, None, None, None, None
+
+
+class _LsCeRows(torch.autograd.Function):
+    """Per-row variant (no R-Drop / drop-worst): returns the differentiable vector of row losses, so that rows of several
+    tasks decoded in one batch can be summed and normalised per task; the backward scales every row of the in-place
+    d(logits) by its own upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, target, cmask, conf, eps, pad_idx, crange):
+        _need_cuda(logits)
+        B, T, V = logits.shape
+        assert logits.stride(2) == 1 and logits.stride(0) == T * logits.stride(1)
+        R = B * T
+        tgt = target.contiguous()
+        loss_rows = torch.empty(R, dtype=torch.float32, device=logits.device)
+        nll_rows = torch.empty(R, dtype=torch.float32, device=logits.device)
+        kl_rows = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        cm = cmask.contiguous().view(torch.uint8) if cmask is not None else None
+        cf = conf.float().contiguous() if conf is not None else None
+        cs, ce = crange if crange is not None else (-1, -1)
+        call("ofa_ls_ce_fwd_bwd", _p(logits), logits.stride(1), _p(tgt), _p(cm), _p(cf), T, R, V, pad_idx, eps, cs, ce,
+             0, 1.0, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st(),
+             work=("byte", 2 * R * V * logits.element_size()))
+        ctx.dlogits = logits.detach()
+        ctx.mark_non_differentiable(nll_rows)
+        return loss_rows, nll_rows
+
+    @staticmethod
+    def backward(ctx, g_rows, gnll):
+        dlogits = ctx.dlogits
+        B, T, V = dlogits.shape
+        scale = g_rows.float().contiguous()
+        call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(None), 1, _dt(dlogits), _st())
+        return dlogits, None, None, None, None, None, None
+
+
+def ls_cross_entropy_rows(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None):
+    """-> (loss_rows [B*T], nll_rows [B*T]); pad rows are 0.  `logits` is overwritten with its own gradient."""
+    return _LsCeRows.apply(logits, target, cmask, conf, eps, pad_idx, crange)
 
 
 def ls_cross_entropy(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None, rdrop=False, reg_alpha=1.0,

@@ -313,11 +313,12 @@ def test_grouped_stem_pass_equals_per_task_stems(dtype):
     case = fx["case"]
     cfg, sd, samples = build_case(case)
     res = []
-    for batched, merged in ((False, False), (True, False), (True, True)):
+    for batched, merged, mdec in ((False, False, False), (True, False, False), (True, True, False), (True, True, True)):
         model, task = build_product(cfg, sd, dtype=dtype)
         model.train()
         crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0,
-                                                        batch_task_stems=batched, batch_task_encoders=merged)
+                                                        batch_task_stems=batched, batch_task_encoders=merged,
+                                                        batch_task_decoders=mdec)
         loss, ss, _ = crit(model, to_device(copy.deepcopy(samples), "cuda", dtype))
         loss.backward()
         res.append((float(loss.detach()), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None},
@@ -342,5 +343,47 @@ def test_grouped_stem_pass_equals_per_task_stems(dtype):
         ref_loss.backward()
         ref_gn = sum(float(v.grad.norm()) ** 2 for k, v in sdo.items() if v.requires_grad and v.grad is not None
                      and not k.startswith(("decoder.embed_tokens", "decoder.output_projection"))) ** 0.5
-        assert abs(res[2][0] - float(ref_loss.detach())) <= 1e-3 * abs(float(ref_loss.detach()))
+        assert abs(res[3][0] - float(ref_loss.detach())) <= 1e-3 * abs(float(ref_loss.detach()))
         assert abs(g1 - ref_gn) <= 1e-3 * ref_gn, (g1, ref_gn)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_merged_decoder_passes_equal_per_task_passes(dtype):
+    """Five-task micro-step whose image tasks group into two merged decoder passes (targets 7|9 and 40|44, right-padded to the
+    longest of the group) vs every task decoding on its own, and vs the oracle's sequential forwards (fp32)."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    cfg = synth.make_cfg("ofa_micro", vocab_size=4099)
+    sd = synth.synth_state_dict(cfg, seed=0)
+    spec = [(19, 7, True), (30, 9, True), (22, 40, True), (17, 44, True), (25, 6, False)]
+    samples = [synth.make_batch(2, s, t, img=96, seed=40 + i, vocab=4099, with_image=im) for i, (s, t, im) in enumerate(spec)]
+    res = []
+    for mdec in (False, True):
+        model, task = build_product(cfg, sd, dtype=dtype)
+        model.train()
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0,
+                                                        batch_task_decoders=mdec)
+        calls = {"n": 0}
+        orig = model.decoder.forward
+
+        def counted(*a, _o=orig, **k):
+            calls["n"] += 1
+            return _o(*a, **k)
+
+        model.decoder.forward = counted
+        loss, ss, log = crit(model, to_device(copy.deepcopy(samples), "cuda", dtype))
+        loss.backward()
+        assert calls["n"] == (3 if mdec else 5)          # two merged groups + the text-only task
+        res.append((float(loss.detach()), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None},
+                    log))
+    assert abs(res[0][0] - res[1][0]) <= (1e-5 if dtype == torch.float32 else 2e-2) * abs(res[0][0])
+    for key in ("ntokens", "nsentences", "sample_size", "sample_size_v1", "sample_size_v2"):
+        assert res[0][2][key] == res[1][2][key], key
+    g0 = sum(float(v.norm()) ** 2 for v in res[0][1].values()) ** 0.5
+    g1 = sum(float(v.norm()) ** 2 for v in res[1][1].values()) ** 0.5
+    assert abs(g0 - g1) <= (1e-3 if dtype == torch.float32 else 6e-2) * g0, (g0, g1)
+    if dtype == torch.float32:
+        for n, v in res[0][1].items():
+            if "embed_images" not in n:
+                assert (v - res[1][1][n]).abs().max().item() <= 5e-3 * max(1.0, v.abs().max().item()), n
+        ref_loss, _, _ = oo.criterion_forward(tie(sd), cfg, copy.deepcopy(samples), epsilon=0.1, use_rdrop=False, sample_patch_num=0)
+        assert abs(res[1][0] - float(ref_loss.detach())) <= 1e-3 * abs(float(ref_loss.detach()))
