@@ -95,7 +95,29 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
                                                  "encoder_states": [], "src_tokens": [], "src_lengths": []}
                 out[i] = s
             if self.batch_task_decoders:
-                self._batch_decoders(model, out, idx, xs, pms, pos, b)
+                xs, pms, pos, idx2 = list(xs), list(pms), list(pos), list(idx)
+                # text-only tasks with the same batch size join the decoder groups: their own encoder pass, right-padded
+                # (masked) to the merged pass's source length
+                N = xs[0].shape[1]
+                for i, smp in enumerate(sample):
+                    ni = smp["net_input"]
+                    if (i in idx or ni.get("patch_images") is not None or ni.get("encoder_out") is not None
+                            or ni["src_tokens"].shape[0] != b or ni["src_tokens"].shape[1] > N):
+                        continue
+                    e1 = enc(ni["src_tokens"], src_lengths=ni.get("src_lengths"))
+                    x1, pm1, ps1 = e1["encoder_out"][0].transpose(0, 1), e1["encoder_padding_mask"][0], e1["position_embeddings"][0]
+                    padn = N - x1.shape[1]
+                    xs.append(torch.nn.functional.pad(x1, (0, 0, 0, padn)))
+                    pms.append(torch.nn.functional.pad(pm1, (0, padn), value=True))
+                    pos.append(torch.nn.functional.pad(ps1, (0, 0, 0, padn)))
+                    s1 = dict(smp)
+                    s1["net_input"] = dict(ni)
+                    s1["net_input"]["encoder_out"] = {"encoder_out": [xs[-1].transpose(0, 1)], "encoder_padding_mask": [pms[-1]],
+                                                      "position_embeddings": [pos[-1]], "encoder_embedding": [],
+                                                      "encoder_states": [], "src_tokens": [], "src_lengths": []}
+                    out[i] = s1
+                    idx2.append(i)
+                self._batch_decoders(model, out, idx2, xs, pms, pos, b)
             return out
         feats = feats_all.split(b, 0)                                           # split: one cat in the backward
         for k, i in enumerate(idx):

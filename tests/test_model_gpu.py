@@ -372,7 +372,7 @@ def test_merged_decoder_passes_equal_per_task_passes(dtype):
         model.decoder.forward = counted
         loss, ss, log = crit(model, to_device(copy.deepcopy(samples), "cuda", dtype))
         loss.backward()
-        assert calls["n"] == (3 if mdec else 5)          # two merged groups + the text-only task
+        assert calls["n"] == (2 if mdec else 5)          # two merged groups (the text-only task joins the short one)
         res.append((float(loss.detach()), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None},
                     log))
     assert abs(res[0][0] - res[1][0]) <= (1e-5 if dtype == torch.float32 else 2e-2) * abs(res[0][0])
