@@ -127,37 +127,34 @@ constexpr int kStemK = 147, kStemKp = 152;
 __global__ void __launch_bounds__(256) stem_patches_kernel(const __nv_bfloat16* __restrict__ x /* NHWC, C = 3 */,
                                                            __nv_bfloat16* __restrict__ col, int N, int H, int W, int OH, int OW) {
   pdl_sync();
-  // one thread per (output pixel, tap row kh): 7 taps x 3 channels = 21 contiguous-ish input elements
+  // one thread per (output pixel, 8 consecutive columns): 19 threads write a 304-byte patch row with 16-byte stores; the
+  // 8 taps are scalar reads of a 7 x 21-element window that stays in L1
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)N * OH * OW * 8) return;
-  const int kh = (int)(t & 7);
-  long long p = t >> 3;
+  if (t >= (long long)N * OH * OW * 19) return;
+  const int cg = (int)(t % 19);
+  const long long p = t / 19;
   const int ow = (int)(p % OW);
   const int oh = (int)((p / OW) % OH);
   const int n = (int)(p / ((long long)OW * OH));
-  __nv_bfloat16* dst = col + p * kStemKp;
-  if (kh == 7) {                      // the padding columns 147..151
+  const __nv_bfloat16* img = x + (long long)n * H * W * 3;
+  unsigned short v[8];
 #pragma unroll
-    for (int j = kStemK; j < kStemKp; ++j) dst[j] = __float2bfloat16(0.f);
-    return;
+  for (int e = 0; e < 8; ++e) {
+    const int j = cg * 8 + e;            // column (c, kh, kw); 147..151 are padding
+    const int c = j / 49, rem = j - c * 49, kh = rem / 7, kw = rem - kh * 7;
+    const int h = oh * 2 - 3 + kh, w = ow * 2 - 3 + kw;
+    const bool in = j < kStemK && h >= 0 && h < H && w >= 0 && w < W;
+    v[e] = in ? reinterpret_cast<const unsigned short*>(img)[((long long)h * W + w) * 3 + c] : (unsigned short)0;
   }
-  const int h = oh * 2 - 3 + kh;
-  const bool hin = h >= 0 && h < H;
-#pragma unroll
-  for (int kw = 0; kw < 7; ++kw) {
-    const int w = ow * 2 - 3 + kw;
-    const bool in = hin && w >= 0 && w < W;
-    const __nv_bfloat16* src = x + (((long long)n * H + (hin ? h : 0)) * W + (in ? w : 0)) * 3;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) dst[c * 49 + kh * 7 + kw] = in ? src[c] : __float2bfloat16(0.f);
-  }
+  *reinterpret_cast<uint4*>(col + p * kStemKp + cg * 8) =
+      make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
 }
 }  // namespace
 
 extern "C" int ofa_stem_patches(const void* x, void* col, int N, int H, int W, void* stream) {
   OFA_CHECK(N > 0 && H > 0 && W > 0, "ofa_stem_patches: bad shape");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  const long long n = (long long)N * OH * OW * 8;
+  const long long n = (long long)N * OH * OW * 19;
   OFA_CUDA(ofa_launch_pdl(stem_patches_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream,
                           (const __nv_bfloat16*)x, (__nv_bfloat16*)col, N, H, W, OH, OW));
   return 0;
