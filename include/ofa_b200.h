@@ -56,6 +56,9 @@ int ofa_split3_bf16(const float* x, long long ldx, int rows, int C, void* out, l
 int ofa_layernorm_fwd(const void* x, const void* gamma, const void* beta, const void* resid, void* y, float* mean,
                       float* rstd, int rows, int C, float eps, int gelu_in, int dtype, void* stream);
 int ofa_layernorm_bwd_nparts(int rows); /* host helper: workspace = 2 * nparts * C floats */
+/* A/B switch: wide rows (> 2048 columns) of the backward stream through a shared-memory ring filled by bulk copies
+   (default 1); returns the previous setting */
+int ofa_layernorm_set_staged(int enabled);
 int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
                       void* dgamma, void* dbeta, float* workspace, int rows, int C, int gelu_in, int accumulate,
                       int dtype, void* stream); /* accumulate=1: dgamma/dbeta += (gradient accumulation across micro-batches) */
@@ -84,6 +87,9 @@ int ofa_dropout_residual(const void* x, const void* resid, void* y, long long n,
  * statistics / normalisation / backward are per group (stats = groups * 4*C floats), the running statistics are updated
  * group after group and dgamma / dbeta are summed over the groups -- the arithmetic of `groups` separate calls.          */
 long long ofa_batchnorm_workspace_floats(int C);
+/* tuning switches: resident-CTA waves per launch (0 = automatic, the default) and rows in flight per thread of the
+   backward kernels (2, 4 or 6; default 4); values outside the accepted set leave the setting unchanged */
+int ofa_batchnorm_set_tuning(int waves, int bwd_unroll);
 int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* running_mean,
                       void* running_var, long long R, int C, float eps, float momentum, int training, int relu,
                       float* stats, float* workspace, int groups, int dtype, void* stream);

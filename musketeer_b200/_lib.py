@@ -55,6 +55,7 @@ SIGNATURES = {
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],
+    "ofa_layernorm_set_staged": [c_i],
     "ofa_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "ofa_colsum": [c_p, c_ll, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_p],
     "ofa_embed_gather": [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p],
@@ -64,6 +65,7 @@ SIGNATURES = {
     "ofa_gelu": [c_p, c_p, c_p, c_ll, c_i, c_i, c_p],
     "ofa_dropout_residual": [c_p, c_p, c_p, c_ll, c_i, c_i, c_f, c_p, c_p, c_i, c_p],
     "ofa_batchnorm_workspace_floats": [c_i],
+    "ofa_batchnorm_set_tuning": [c_i, c_i],
     "ofa_batchnorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
     "ofa_batchnorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
     "ofa_ls_ce_fwd_bwd": [c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_i,
@@ -110,6 +112,11 @@ def load(path=None):
         lib.ofa_gemm_set_wgrad_bn256(int(os.environ["OFA_WGRAD_BN256"]))
     if os.environ.get("OFA_PAIR_MIN_TILES") is not None:
         lib.ofa_gemm_set_pair_min_tiles(int(os.environ["OFA_PAIR_MIN_TILES"]))
+    if os.environ.get("OFA_BN_TUNING") is not None:      # "waves,bwd_unroll"
+        w, u = os.environ["OFA_BN_TUNING"].split(",")
+        lib.ofa_batchnorm_set_tuning(int(w), int(u))
+    if os.environ.get("OFA_LN_STAGED") is not None:
+        lib.ofa_layernorm_set_staged(int(os.environ["OFA_LN_STAGED"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch
         lib.ofa_set_pdl(int(os.environ["OFA_PDL"]))
     _lib = lib

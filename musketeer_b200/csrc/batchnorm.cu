@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x
       }
     }
   }
-  if (training) release_sums(const_cast<float*>(sums0), C);
   for (long long r = m.r0; r < R; r += kUnroll * m.stride) {
     typename V8<T>::Raw rx[kUnroll], rr[kUnroll];
 #pragma unroll
@@ -225,12 +224,13 @@ __global__ void __launch_bounds__(kT, 3) bn_apply_kernel(const T* __restrict__ x
       }
     }
   }
+  if (training) release_sums(const_cast<float*>(sums0), C);   // after the stream: nothing waits on it
 }
 
 // backward statistics: sums[0][c] += sum g, sums[1][c] += sum g * xhat, g = dy * (relu ? y > 0 : 1).  Without a residual
 // the ReLU mask is recomputed from x with the forward's scale / shift (saves the read of y).
-template <typename T>
-__global__ void __launch_bounds__(kT, 3) bn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+template <typename T, int U>
+__global__ void __launch_bounds__(kT, U == 2 ? 3 : 2) bn_bwd_stats_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                           const T* __restrict__ y, const float* __restrict__ stats,
                                                           long long R, int C, int CS, int relu, float* __restrict__ sums) {
   pdl_sync();
@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_stats_kernel(const T* __restrict
     a[j] = 0.f; b[j] = 0.f;
     sc[j] = stats[2 * C + c]; sh[j] = stats[3 * C + c];
   }
-  constexpr int U = 2;
   for (long long r = m.r0; r < R; r += U * m.stride) {
     typename V8<T>::Raw rx[U], rg[U], ry_[U];
 #pragma unroll
@@ -286,8 +285,8 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_stats_kernel(const T* __restrict
 
 // backward apply: dx = ca*(g - s1/n - xhat*s2/n) = ca*g + A*x + B  with  ca = gamma*rstd, A = -ca*rstd*s2/n,
 // B = -ca*s1/n - A*mean  (eval / frozen statistics: A = B = 0);  dres = g.  CTA column 0 writes dgamma = s2, dbeta = s1.
-template <typename T>
-__global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+template <typename T, int U>
+__global__ void __launch_bounds__(kT, U == 2 ? 3 : 2) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                           const T* __restrict__ y, const T* __restrict__ gamma,
                                                           const float* __restrict__ stats, const float* __restrict__ sums,
                                                           T* __restrict__ dx, T* __restrict__ dres, T* __restrict__ dgamma,
@@ -325,8 +324,6 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict
       }
     }
   }
-  if (sums) release_sums(const_cast<float*>(sums0), C);
-  constexpr int U = 2;
   for (long long r = m.r0; r < R; r += U * m.stride) {
     typename V8<T>::Raw rx[U], rg[U], ry_[U];
 #pragma unroll
@@ -359,19 +356,27 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const T* __restrict
       }
     }
   }
+  if (sums) release_sums(const_cast<float*>(sums0), C);   // after the stream: nothing waits on it
 }
 
 struct Grid {
   int CS;
   dim3 g;
 };
-Grid grid_for(long long R, int C, int unroll, int groups) {
+// tuning switches (ofa_batchnorm_set_tuning): resident-CTA waves of the grid-stride kernels and rows in flight per thread
+// of the backward kernels
+int g_bn_waves = 0 /* auto */, g_bn_bwd_unroll = 4;
+
+Grid grid_for(long long R, int C, int unroll, int groups, int ctas_per_sm) {
   Grid r;
   r.CS = C < 256 ? C : 256;
   const int slabs = C / r.CS;
   const int rpi = kT / (r.CS / 8);
   long long gx = (R + (long long)rpi * unroll - 1) / ((long long)rpi * unroll);
-  const long long cap = (148 * 6 + slabs * groups - 1) / (slabs * groups);   // ~6 CTAs of 256 threads per SM in total
+  // measured (tools/rowwise_bench.py): one resident wave is best for single-slab tensors, two waves for C > 256
+  const int waves = g_bn_waves > 0 ? g_bn_waves : (slabs > 1 ? 2 : 1);
+  const int total = 148 * ctas_per_sm * waves;
+  const long long cap = (total + slabs * groups - 1) / (slabs * groups);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   r.g = dim3((unsigned)gx, (unsigned)slabs, (unsigned)groups);
@@ -384,10 +389,10 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
              cudaStream_t st) {
   float* sums = ws;
   if (training) {
-    const Grid gs = grid_for(R, C, kUnroll, groups);
+    const Grid gs = grid_for(R, C, kUnroll, groups, 4);
     OFA_CUDA(ofa_launch_pdl(bn_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, R, C, gs.CS, sums));
   }
-  const Grid ga = grid_for(R, C, kUnroll, groups);
+  const Grid ga = grid_for(R, C, kUnroll, groups, 3);
   OFA_CUDA(ofa_launch_pdl(bn_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)res, (T*)y, (const T*)gamma, (const T*)beta, (T*)rm, (T*)rv,
                                           sums, stats, R, C, ga.CS, eps, momentum, training, relu));
   OFA_LAUNCH_CHECK("batchnorm forward");
@@ -399,14 +404,17 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
              void* dgamma, void* dbeta, int accumulate, long long R, int C, int batch_stats, int relu, float* ws, int groups,
              cudaStream_t st) {
   float* sums = nullptr;
+  const int U = g_bn_bwd_unroll, occ = U == 2 ? 3 : 2;
   if (batch_stats || dgamma) {   // frozen statistics without parameter gradients need no reduction at all
     sums = ws;
-    const Grid gs = grid_for(R, C, 2, groups);
-    OFA_CUDA(ofa_launch_pdl(bn_bwd_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums));
+    const Grid gs = grid_for(R, C, U, groups, occ);
+    auto kern = U == 2 ? bn_bwd_stats_kernel<T, 2> : U == 4 ? bn_bwd_stats_kernel<T, 4> : bn_bwd_stats_kernel<T, 6>;
+    OFA_CUDA(ofa_launch_pdl(kern, gs.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, stats, R, C, gs.CS, relu, sums));
   }
-  const Grid ga = grid_for(R, C, 2, groups);
-  OFA_CUDA(ofa_launch_pdl(bn_bwd_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, (const T*)gamma, stats, sums, (T*)dx,
-                                              (T*)dres, (T*)dgamma, (T*)dbeta, accumulate, R, C, ga.CS, batch_stats, relu));
+  const Grid ga = grid_for(R, C, U, groups, occ);
+  auto kern = U == 2 ? bn_bwd_apply_kernel<T, 2> : U == 4 ? bn_bwd_apply_kernel<T, 4> : bn_bwd_apply_kernel<T, 6>;
+  OFA_CUDA(ofa_launch_pdl(kern, ga.g, kT, 0, st, (const T*)x, (const T*)dy, (const T*)y, (const T*)gamma, stats, sums, (T*)dx,
+                          (T*)dres, (T*)dgamma, (T*)dbeta, accumulate, R, C, ga.CS, batch_stats, relu));
   OFA_LAUNCH_CHECK("batchnorm backward");
   return 0;
 }
@@ -416,6 +424,12 @@ int bwd_impl(const void* x, const void* dy, const void* y, const void* gamma, co
 // scratch floats for either direction: ZERO ON ENTRY, left zero on exit (allocate once with zeros and reuse it for every
 // call in the stream); `stats` of the forward is 4*C floats
 // (mean | rstd | scale | shift), of which mean and rstd are the backward's inputs
+extern "C" int ofa_batchnorm_set_tuning(int waves, int bwd_unroll) {
+  if (waves >= 0 && waves <= 8) g_bn_waves = waves;   // 0 = automatic
+  if (bwd_unroll == 2 || bwd_unroll == 4 || bwd_unroll == 6) g_bn_bwd_unroll = bwd_unroll;
+  return 0;
+}
+
 extern "C" long long ofa_batchnorm_workspace_floats(int C) { (void)C; return 2LL * kMaxC * kMaxGroups + 32; }
 
 extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,

@@ -11,6 +11,19 @@ template <typename T>
 struct Vec8 {};  // 8 elements per thread-vector
 template <>
 struct Vec8<float> {
+  struct Raw { float4 a, b; };
+  __device__ static Raw ldraw(const float* p) { Raw r; r.a = reinterpret_cast<const float4*>(p)[0]; r.b = reinterpret_cast<const float4*>(p)[1]; return r; }
+  __device__ static void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
+  __device__ static void unpack2(const Raw& r, float2 (&v)[4]) {
+    v[0] = make_float2(r.a.x, r.a.y); v[1] = make_float2(r.a.z, r.a.w);
+    v[2] = make_float2(r.b.x, r.b.y); v[3] = make_float2(r.b.z, r.b.w);
+  }
+  __device__ static void store2(float* p, const float2 (&v)[4]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+  }
   __device__ static void load(const float* p, float (&v)[8]) {
     float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -22,6 +35,22 @@ struct Vec8<float> {
 };
 template <>
 struct Vec8<__nv_bfloat16> {
+  struct Raw { uint4 u; };
+  __device__ static Raw ldraw(const __nv_bfloat16* p) { Raw r; r.u = *reinterpret_cast<const uint4*>(p); return r; }
+  __device__ static void unpack(const Raw& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ static void unpack2(const Raw& r, float2 (&v)[4]) {     // one shift / one mask per element
+    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+  }
+  __device__ static void store2(__nv_bfloat16* p, const float2 (&v)[4]) {
+    *reinterpret_cast<uint4*>(p) =
+        make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y), pack_bf16(v[3].x, v[3].y));
+  }
   __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -37,28 +66,82 @@ struct Vec8<__nv_bfloat16> {
   }
 };
 
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot per TWO IEEE fp32 operations, bit-identical to
+// the scalar forms.  The wide LayerNorm(+GELU) kernels are issue-bound (ncu: 31 instructions per element, 67% issue
+// utilisation at 2.9 TB/s), so halving the FP32 instruction count is what moves them towards the HBM roofline.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)),
+      "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 k2(float c) { return make_float2(c, c); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// erf-GELU for the bf16 kernels: Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below bf16 resolution) costs one
-// MUFU.RCP, one MUFU.EX2 and seven FMAs and also yields exp(-x^2/2) for the derivative; the fp32 parity mode keeps erff.
+// erf-GELU for the bf16 kernels: Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below bf16 resolution) with
+// approximate MUFU.RCP / MUFU.EX2 (no IEEE fix-up paths): h = Phi(-|x|) = 0.5*erfc(|x|/sqrt2) costs 2 MUFU + 8 FP32
+// instructions and also yields exp(-x^2/2) for the derivative; the fp32 parity mode keeps erff.
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float half_erfc_abs(float x, float& e) {    // e = exp(-x^2 / 2)
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  e = fast_ex2(x * x * (-0.5f * 1.44269504088896340736f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  return poly * t * e;
+}
+template <typename T>
+__device__ __forceinline__ float gelu_value(float x) {
+  if (sizeof(T) == 4) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float e;
+  const float h = half_erfc_abs(x, e);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));                // x >= 0: x - x*h;  x < 0: x*h
+}
+// two elements at once; nh = -Phi(-|x|) comes out of the (negated) polynomial, e = exp(-x^2/2), ax = |x|
+__device__ __forceinline__ float2 neg_half_erfc_abs2(float2 x, float2& ax, float2& e) {
+  ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 u = ffma2(ax, k2(0.3275911f * 0.70710678118654752440f), k2(1.0f));
+  const float2 t = make_float2(fast_rcp(u.x), fast_rcp(u.y));
+  const float2 w = fmul2(fmul2(x, x), k2(-0.5f * 1.44269504088896340736f));
+  e = make_float2(fast_ex2(w.x), fast_ex2(w.y));
+  float2 poly = ffma2(k2(-0.5f * 1.061405429f), t, k2(0.5f * 1.453152027f));
+  poly = ffma2(poly, t, k2(-0.5f * 1.421413741f));
+  poly = ffma2(poly, t, k2(0.5f * 0.284496736f));
+  poly = ffma2(poly, t, k2(-0.5f * 0.254829592f));
+  return fmul2(fmul2(poly, t), e);
+}
+template <typename T>
+__device__ __forceinline__ float2 gelu_value2(float2 x) {
+  if (sizeof(T) == 4) return make_float2(gelu_value<T>(x.x), gelu_value<T>(x.y));
+  float2 ax, e;
+  const float2 nh = neg_half_erfc_abs2(x, ax, e);
+  return ffma2(ax, nh, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));       // x >= 0: x - x*h;  x < 0: x*h
+}
 template <typename T>
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {   // cdf = Phi(x), pdf_x = x * phi(x)
   if (sizeof(T) == 4) {
     cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     pdf_x = x * 0.39894228040143267794f * __expf(-0.5f * x * x);
   } else {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    const float e = __expf(-z * z);                       // = exp(-x^2 / 2)
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float half_erfc = 0.5f * poly * t * e;          // 0.5 * (1 - erf(z))
-    cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+    float e;
+    const float h = half_erfc_abs(x, e);
+    cdf = x >= 0.f ? 1.0f - h : h;
     pdf_x = x * 0.39894228040143267794f * e;
   }
 }
@@ -72,31 +155,33 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // LayerNorm forward.  One warp per row, row cached in registers (NV vectors of 8 per lane), two-pass variance.
 //   y = LN(f(x)) * gamma + beta (+ resid),  f = identity | gelu
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NV>
+template <typename T, int NV, int GELU>
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
                                                      const T* __restrict__ beta, const T* __restrict__ resid,
                                                      T* __restrict__ y, float* __restrict__ mean_out,
-                                                     float* __restrict__ rstd_out, int rows, int C, float eps,
-                                                     int gelu_in) {
+                                                     float* __restrict__ rstd_out, int rows, int C, float eps) {
   pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= rows) return;
   const T* xr = x + (size_t)row * C;
+  // the whole row is requested before any arithmetic (NV independent 16-byte loads per lane in flight)
+  typename Vec8<T>::Raw raw[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    raw[i] = Vec8<T>::ldraw(xr + (c < C ? c : 0));
+  }
   float v[NV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
+    Vec8<T>::unpack(raw[i], v[i]);
     if (c < C) {
-      Vec8<T>::load(xr + c, v[i]);
-      if (gelu_in) {
+      if (GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float cdf, pdfx;
-          gelu_parts<T>(v[i][j], cdf, pdfx);
-          v[i][j] *= cdf;
-        }
+        for (int j = 0; j < 8; ++j) v[i][j] = gelu_value<T>(v[i][j]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -112,11 +197,22 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, co
     const int c = (i * 32 + lane) * 8;
     if (c < C) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q = fmaf(d, d, q); }
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  const float nmr = -mean * rstd;
+  // narrow rows: the residual row is requested up front as well (it is the only other HBM stream)
+  constexpr bool kHoistResid = NV <= 4;
+  typename Vec8<T>::Raw rres[kHoistResid ? NV : 1];
+  if (kHoistResid && resid) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      rres[i] = Vec8<T>::ldraw(resid + (size_t)row * C + (c < C ? c : 0));
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
@@ -125,14 +221,112 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, co
       Vec8<T>::load(gamma + c, g);
       Vec8<T>::load(beta + c, b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[i][j], rstd, nmr), g[j], b[j]);
       if (resid) {
         float r[8];
-        Vec8<T>::load(resid + (size_t)row * C + c, r);
+        if (kHoistResid) Vec8<T>::unpack(rres[i], r);
+        else Vec8<T>::load(resid + (size_t)row * C + c, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += r[j];
       }
       Vec8<T>::store(y + (size_t)row * C + c, o);
+    }
+  }
+}
+
+// Wide rows (C > 1536, the FFN's LN(GELU(fc1))): a warp per row needs ~100 live registers per lane, which leaves 3-4
+// warps per scheduler and the row loads exposed (ncu: long-scoreboard stalls dominate, 2.9 TB/s).  Here a 128-thread CTA
+// owns a row (VPT 16-byte vectors per thread, ~64 registers, 7-8 CTAs per SM), loops over rows persistently with the
+// NEXT row's loads already in flight, keeps gamma / beta as fp32 in shared memory, and does the arithmetic two elements
+// per instruction (FFMA2).
+template <typename T, int VPT, int GELU>
+__global__ void __launch_bounds__(128, 7) ln_fwd_wide_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                             const T* __restrict__ beta, const T* __restrict__ resid,
+                                                             T* __restrict__ y, float* __restrict__ mean_out,
+                                                             float* __restrict__ rstd_out, int rows, int C, float eps) {
+  extern __shared__ __align__(16) float ln_gb[];     // gamma[C] | beta[C] in fp32, converted once per CTA
+  __shared__ float red_s[2][4], red_q[2][4];
+  pdl_sync();
+  for (int c = threadIdx.x * 8; c < C; c += 128 * 8) {
+    float g[8], b[8];
+    Vec8<T>::load(gamma + c, g);
+    Vec8<T>::load(beta + c, b);
+    Vec8<float>::store(ln_gb + c, g);
+    Vec8<float>::store(ln_gb + C + c, b);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_c = 1.f / (float)C;
+  int cs[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) cs[i] = (i * 128 + threadIdx.x) * 8;
+  typename Vec8<T>::Raw nxt[VPT];
+  int row = blockIdx.x;
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) nxt[i] = Vec8<T>::ldraw(x + (size_t)row * C + (cs[i] < C ? cs[i] : 0));
+  }
+  for (int it = 0; row < rows; row += gridDim.x, it ^= 1) {
+    float2 v[VPT][4];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) Vec8<T>::unpack2(nxt[i], v[i]);
+    const int row_n = row + gridDim.x;
+    if (row_n < rows) {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) nxt[i] = Vec8<T>::ldraw(x + (size_t)row_n * C + (cs[i] < C ? cs[i] : 0));
+    }
+    float2 s2 = k2(0.f);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      if (cs[i] < C) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (GELU) v[i][j] = gelu_value2<T>(v[i][j]);
+          s2 = fadd2(s2, v[i][j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] = k2(0.f);
+      }
+    }
+    const float sw = warp_sum(s2.x + s2.y);
+    if (lane == 0) red_s[it][warp] = sw;
+    __syncthreads();
+    const float mean = ((red_s[it][0] + red_s[it][1]) + (red_s[it][2] + red_s[it][3])) * inv_c;
+    const float2 nm2 = k2(-mean);
+    float2 q2 = k2(0.f);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      if (cs[i] < C) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 d = fadd2(v[i][j], nm2); q2 = ffma2(d, d, q2); }
+      }
+    }
+    const float qw = warp_sum(q2.x + q2.y);
+    if (lane == 0) red_q[it][warp] = qw;
+    __syncthreads();
+    const float rstd = rsqrtf(((red_q[it][0] + red_q[it][1]) + (red_q[it][2] + red_q[it][3])) * inv_c + eps);
+    if (threadIdx.x == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    const float2 rs2 = k2(rstd), nmr2 = k2(-mean * rstd);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = cs[i];
+      if (c < C) {
+        const float4 g0 = *reinterpret_cast<const float4*>(ln_gb + c), g1 = *reinterpret_cast<const float4*>(ln_gb + c + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(ln_gb + C + c), b1 = *reinterpret_cast<const float4*>(ln_gb + C + c + 4);
+        const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+        const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        float2 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = ffma2(ffma2(v[i][j], rs2, nmr2), g[j], b[j]);
+        if (resid) {
+          float2 r[4];
+          Vec8<T>::unpack2(Vec8<T>::ldraw(resid + (size_t)row * C + c), r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fadd2(o[j], r[j]);
+        }
+        Vec8<T>::store2(y + (size_t)row * C + c, o);
+      }
     }
   }
 }
@@ -224,6 +418,109 @@ __global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_ker
         }
       }
     }
+  }
+  if (act) {
+    float* pg = part_g + (size_t)blockIdx.x * C + c;
+    float* pb = part_b + (size_t)blockIdx.x * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pg[j] = ag[j]; pb[j] = ab[j]; }
+  }
+}
+
+// Wide rows (the FFN's LN(GELU(fc1)) over 3072 columns): a CTA spans a whole row, so only 2 CTAs fit an SM and loads held
+// in registers keep too few bytes in flight (one row per CTA: latency-bound at ~40% of HBM).  Here the rows stream through
+// a shared-memory ring filled by 1-D bulk copies (TMA, mbarrier completion) kStages rows ahead of the math; registers
+// only hold the row being processed.  Same thread mapping, reductions and partials as ln_bwd_kernel.
+template <typename T, int GELU, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2) ln_bwd_staged_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                const T* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                                const float* __restrict__ rstd_in, T* __restrict__ dx,
+                                                                float* __restrict__ part_g, float* __restrict__ part_b,
+                                                                int rows, int C, int stages) {
+  extern __shared__ __align__(128) unsigned char ln_ring[];     // stages x (dy row | x row)
+  __shared__ __align__(8) uint64_t full[8];
+  __shared__ __align__(16) float red[2][2][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)C * sizeof(T);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_sync();
+  const int n_my = (rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // rows blockIdx.x + i * gridDim.x
+  auto fill = [&](int i, int s) {
+    const size_t row = (size_t)blockIdx.x + (size_t)i * gridDim.x;
+    unsigned char* dst = ln_ring + (size_t)s * 2 * row_bytes;
+    mbar_expect_tx(&full[s], 2 * row_bytes);
+    bulk_load_1d(dst, dy + row * C, row_bytes, &full[s]);
+    bulk_load_1d(dst + row_bytes, x + row * C, row_bytes, &full[s]);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < stages && i < n_my; ++i) fill(i, i);
+  const int c = threadIdx.x * 8;
+  const bool act = c < C;
+  const float inv_c = 1.f / (float)C;
+  float ag[8], ab[8], gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; gm[j] = 0.f; }
+  if (act) Vec8<T>::load(gamma + c, gm);
+  float mean_n = n_my > 0 ? mean_in[blockIdx.x] : 0.f, rstd_n = n_my > 0 ? rstd_in[blockIdx.x] : 0.f;
+  if (threadIdx.x < 64) (&red[0][0][0])[threadIdx.x] = 0.f;      // warps beyond nwarp contribute zeros to the fixed-size sums
+  __syncthreads();
+  int s = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < n_my; ++i) {
+    const int it = i & 1;
+    const size_t row = (size_t)blockIdx.x + (size_t)i * gridDim.x;
+    const float rstd = rstd_n, nmr = -mean_n * rstd_n;
+    if (i + 1 < n_my) { mean_n = mean_in[row + gridDim.x]; rstd_n = rstd_in[row + gridDim.x]; }
+    mbar_wait(&full[s], phase);
+    float d[8], xh[8], gp[8], s1 = 0.f, s2 = 0.f;
+    if (act) {
+      const T* srow = reinterpret_cast<const T*>(ln_ring + (size_t)s * 2 * row_bytes);
+      float raw[8];
+      Vec8<T>::load(srow + c, d);
+      Vec8<T>::load(srow + C + c, raw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float fx = raw[j];
+        gp[j] = 1.f;
+        if (GELU) {
+          float cdf, pdfx;
+          gelu_parts<T>(raw[j], cdf, pdfx);
+          fx = raw[j] * cdf;
+          gp[j] = cdf + pdfx;
+        }
+        xh[j] = fmaf(fx, rstd, nmr);
+        const float g = d[j] * gm[j];
+        s1 += g;
+        s2 = fmaf(g, xh[j], s2);
+        ag[j] = fmaf(d[j], xh[j], ag[j]);
+        ab[j] += d[j];
+        d[j] = g;
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[it][0][warp] = s1; red[it][1][warp] = s2; }
+    __syncthreads();                      // every thread has its slice of the stage in registers: the slot can be refilled
+    if (threadIdx.x == 0 && i + stages < n_my) fill(i + stages, s);
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float4 p1 = reinterpret_cast<const float4*>(red[it][0])[w], p2 = reinterpret_cast<const float4*>(red[it][1])[w];
+      t1 += (p1.x + p1.y) + (p1.z + p1.w);
+      t2 += (p2.x + p2.y) + (p2.z + p2.w);
+    }
+    if (act) {
+      const float m1r = -t1 * inv_c * rstd, m2r = -t2 * inv_c * rstd;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(xh[j], m2r, fmaf(d[j], rstd, m1r)) * (GELU ? gp[j] : 1.f);
+      Vec8<T>::store(dx + row * C + c, o);
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; }
   }
   if (act) {
     float* pg = part_g + (size_t)blockIdx.x * C + c;
@@ -406,11 +703,22 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
   if (i < n) dx[i] = (T)((float)dy[i] * gelu_grad((float)x[i]));
 }
 
+int g_ln_bwd_staged = 1;   // A/B switch (ofa_layernorm_set_staged)
+
 template <typename T, int NV>
 int ln_fwd_launch(const void* x, const void* g, const void* b, const void* r, void* y, float* mean, float* rstd,
                   int rows, int C, float eps, int gelu_in, cudaStream_t st) {
-  OFA_CUDA(ofa_launch_pdl(ln_fwd_kernel<T, NV>, (rows + 3) / 4, 128, 0, st, (const T*)x, (const T*)g, (const T*)b, (const T*)r, (T*)y, mean,
-                                                       rstd, rows, C, eps, gelu_in));
+  if (NV >= 8) {      // wide rows: one CTA per row, persistent
+    constexpr int VPT = NV >= 8 ? NV / 4 : 1;
+    auto kern = gelu_in ? ln_fwd_wide_kernel<T, VPT, 1> : ln_fwd_wide_kernel<T, VPT, 0>;
+    const int cap = 148 * 7;
+    OFA_CUDA(ofa_launch_pdl(kern, rows < cap ? rows : cap, 128, 2 * (size_t)C * sizeof(float), st, (const T*)x, (const T*)g,
+                            (const T*)b, (const T*)r, (T*)y, mean, rstd, rows, C, eps));
+  } else {
+    auto kern = gelu_in ? ln_fwd_kernel<T, NV, 1> : ln_fwd_kernel<T, NV, 0>;
+    OFA_CUDA(ofa_launch_pdl(kern, (rows + 3) / 4, 128, 0, st, (const T*)x, (const T*)g, (const T*)b, (const T*)r, (T*)y, mean,
+                            rstd, rows, C, eps));
+  }
   OFA_LAUNCH_CHECK("ln_fwd_kernel");
   return 0;
 }
@@ -418,6 +726,24 @@ template <typename T>
 int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mean, const float* rstd, void* dx,
                   float* pg, float* pb, int nparts, int rows, int C, int gelu_in, cudaStream_t st) {
   const int threads = ((C / 8 + 31) / 32) * 32;
+  // wide rows: shared-memory ring (2 CTAs per SM, up to ~100 KB each)
+  const size_t row_pair = 2 * (size_t)C * sizeof(T);
+  int stages = (int)((100 * 1024) / row_pair);
+  if (stages > 6) stages = 6;
+  if (g_ln_bwd_staged && threads > 256 && stages >= 2 && (row_pair % 32) == 0) {
+    const size_t smem = stages * row_pair;
+    const int v = (gelu_in ? 1 : 0) + (threads <= 384 ? 2 : 0);
+    auto kern = v == 3 ? ln_bwd_staged_kernel<T, 1, 384> : v == 2 ? ln_bwd_staged_kernel<T, 0, 384>
+              : v == 1 ? ln_bwd_staged_kernel<T, 1, 512> : ln_bwd_staged_kernel<T, 0, 512>;
+    static bool attr_done[4] = {false, false, false, false};
+    if (!attr_done[v]) {
+      OFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      attr_done[v] = true;
+    }
+    OFA_CUDA(ofa_launch_pdl(kern, nparts, threads, smem, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C, stages));
+    OFA_LAUNCH_CHECK("ln_bwd_staged_kernel");
+    return 0;
+  }
   if (gelu_in)
     OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 1, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
   else if (threads <= 256)
@@ -464,6 +790,12 @@ extern "C" int ofa_layernorm_fwd(const void* x, const void* gamma, const void* b
     DISPATCH_NV(nv, (ln_fwd_launch<float, NV>(x, gamma, beta, resid, y, mean, rstd, rows, C, eps, gelu_in, st)))
   }
   return ofa_set_error("ofa_layernorm_fwd: bad dtype %d", dtype);
+}
+
+extern "C" int ofa_layernorm_set_staged(int enabled) {
+  const int old = g_ln_bwd_staged;
+  g_ln_bwd_staged = enabled;
+  return old;
 }
 
 extern "C" int ofa_layernorm_bwd_nparts(int rows) {

@@ -69,7 +69,9 @@ def test_linear_fp32_split_fwd_bwd(M, N, K):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,C,gelu", [(37, 128, False), (713, 768, False), (100, 3072, True), (9, 1024, True),
-                                         (50, 256, False)])
+                                         (50, 256, False),
+                                         # wide rows: the backward's shared-memory ring wraps (296 CTAs, > 6 rows each)
+                                         (2000, 3072, True), (1500, 4096, False)])
 def test_layernorm(dtype, rows, C, gelu):
     ops = _ops()
     g = torch.Generator(device="cpu").manual_seed(rows + C)
