@@ -281,12 +281,18 @@ def main():
     # events cannot bracket nodes inside a graph replay); used for the roofline object only, never for `value`
     prof = None
     if a.profile_kernels:
+        # an eager step is host-bound: without a backlog every start event would also time the wait for the next launch.
+        # A spin kernel lets the host queue the whole step ahead of the GPU, so the pairs bracket kernel time only; it is
+        # sized from the measured host time of one instrumented eager step (host speed differs from box to box).
         _lib.PROFILE = {}
         torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(resident[0], eager=True)
+        host_s = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        _lib.PROFILE = {}
         for i in range(a.steps):
-            # an eager step is host-bound: without a backlog every start event would also time the wait for the next launch.
-            # A spin kernel lets the host queue the whole step ahead of the GPU, so the pairs bracket kernel time only.
-            torch.cuda._sleep(int(0.45 * 1.9e9))
+            torch.cuda._sleep(int(1.3 * host_s * 1.965e9))
             step(resident[i % n_batches], eager=True)
             torch.cuda.synchronize()
         torch.cuda.synchronize()

@@ -59,9 +59,12 @@ int ofa_layernorm_bwd_nparts(int rows); /* host helper: workspace = 2 * nparts *
 /* A/B switch: wide rows (> 2048 columns) of the backward stream through a shared-memory ring filled by bulk copies
    (default 1); returns the previous setting */
 int ofa_layernorm_set_staged(int enabled);
+/* accumulate=1: dgamma/dbeta += (gradient accumulation across micro-batches).  dskip (optional, [rows, C]): the gradient
+   that reached x through the residual branch that forks off before the LayerNorm (unify_transformer_layer.py:259-262:
+   residual = x; x = self_attn_layer_norm(x)); it is added into dx in the same pass instead of by a separate kernel. */
 int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
                       void* dgamma, void* dbeta, float* workspace, int rows, int C, int gelu_in, int accumulate,
-                      int dtype, void* stream); /* accumulate=1: dgamma/dbeta += (gradient accumulation across micro-batches) */
+                      const void* dskip, int dtype, void* stream);
 
 /* ---- glue -------------------------------------------------------------------------------------------------------- */
 int ofa_colsum(const void* x, long long ld, int rows, int C, void* out, float* workspace /* 64*C floats */, float alpha,

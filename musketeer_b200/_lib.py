@@ -56,7 +56,7 @@ SIGNATURES = {
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
     "ofa_layernorm_bwd_nparts": [c_i],
     "ofa_layernorm_set_staged": [c_i],
-    "ofa_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "ofa_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p],
     "ofa_colsum": [c_p, c_ll, c_i, c_i, c_p, c_p, c_f, c_i, c_i, c_p],
     "ofa_embed_gather": [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p],
     "ofa_embed_scatter_add": [c_p, c_p, c_ll, c_p, c_i, c_i, c_ll, c_i, c_p],

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_ker
                                                      const T* __restrict__ gamma, const float* __restrict__ mean_in,
                                                      const float* __restrict__ rstd_in, T* __restrict__ dx,
                                                      float* __restrict__ part_g, float* __restrict__ part_b, int rows,
-                                                     int C) {
+                                                     int C, const T* __restrict__ dskip) {
   // U = rows per iteration: 2 for the plain variant up to 2048 columns (latency-bound), 1 otherwise (GELU is erf-bound)
   // blockDim.x = ceil(C/8) rounded up to a warp: thread t owns columns 8t..8t+7 of every row this CTA visits, so the
   // dgamma / dbeta partials need no cross-thread reduction; erf is evaluated once per element (GELU value and derivative).
@@ -359,36 +359,40 @@ __global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_ker
     const int row1 = row + gridDim.x;
     const bool has1 = U == 2 && row1 < rows;
     const int rr[2] = {row, has1 ? row1 : row};
-    float mean[U], rstd[U], d[U][8], xh[U][8], gp[U][8], s1[U], s2[U];
-    float raw[U][8];
+    float mean[U], rstd[U], xh[U][8], gp[U][8], s1[U], s2[U];
+    typename Vec8<T>::Raw rd[U], rs[U], rx[U];     // dy and the skip-branch gradient stay packed until they are used
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       mean[u] = mean_in[rr[u]]; rstd[u] = rstd_in[rr[u]];
       if (act) {
-        Vec8<T>::load(dy + (size_t)rr[u] * C + c, d[u]);
-        Vec8<T>::load(x + (size_t)rr[u] * C + c, raw[u]);
+        rd[u] = Vec8<T>::ldraw(dy + (size_t)rr[u] * C + c);
+        rx[u] = Vec8<T>::ldraw(x + (size_t)rr[u] * C + c);
+        if (dskip) rs[u] = Vec8<T>::ldraw(dskip + (size_t)rr[u] * C + c);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       s1[u] = 0.f; s2[u] = 0.f;
       if (act && (u == 0 || has1)) {
+        float d[8], raw[8];
+        Vec8<T>::unpack(rd[u], d);
+        Vec8<T>::unpack(rx[u], raw);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float fx = raw[u][j];
+          float fx = raw[j];
           gp[u][j] = 1.f;
           if (GELU) {
             float cdf, pdfx;
-            gelu_parts<T>(raw[u][j], cdf, pdfx);
-            fx = raw[u][j] * cdf;
+            gelu_parts<T>(raw[j], cdf, pdfx);
+            fx = raw[j] * cdf;
             gp[u][j] = cdf + pdfx;
           }
           xh[u][j] = (fx - mean[u]) * rstd[u];
-          const float g = d[u][j] * gm[j];
+          const float g = d[j] * gm[j];
           s1[u] += g;
           s2[u] += g * xh[u][j];
-          ag[j] += d[u][j] * xh[u][j];
-          ab[j] += d[u][j];
+          ag[j] += d[j] * xh[u][j];
+          ab[j] += d[j];
         }
       }
       s1[u] = warp_sum(s1[u]);
@@ -411,9 +415,16 @@ __global__ void __launch_bounds__(U == 2 ? 256 : 512, U == 2 ? 3 : 2) ln_bwd_ker
       for (int u = 0; u < U; ++u) {
         if (u == 0 || has1) {
           const float m1 = t[2 * u] / C, m2 = t[2 * u + 1] / C;
-          float o[8];
+          float o[8], d[8];
+          Vec8<T>::unpack(rd[u], d);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rstd[u] * (d[u][j] * gm[j] - m1 - xh[u][j] * m2) * (GELU ? gp[u][j] : 1.f);
+          for (int j = 0; j < 8; ++j) o[j] = rstd[u] * (d[j] * gm[j] - m1 - xh[u][j] * m2) * (GELU ? gp[u][j] : 1.f);
+          if (dskip) {
+            float sk[8];
+            Vec8<T>::unpack(rs[u], sk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += sk[j];
+          }
           Vec8<T>::store(dx + (size_t)rr[u] * C + c, o);
         }
       }
@@ -724,13 +735,13 @@ int ln_fwd_launch(const void* x, const void* g, const void* b, const void* r, vo
 }
 template <typename T>
 int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mean, const float* rstd, void* dx,
-                  float* pg, float* pb, int nparts, int rows, int C, int gelu_in, cudaStream_t st) {
+                  float* pg, float* pb, int nparts, int rows, int C, int gelu_in, const void* dskip, cudaStream_t st) {
   const int threads = ((C / 8 + 31) / 32) * 32;
   // wide rows: shared-memory ring (2 CTAs per SM, up to ~100 KB each)
   const size_t row_pair = 2 * (size_t)C * sizeof(T);
   int stages = (int)((100 * 1024) / row_pair);
   if (stages > 6) stages = 6;
-  if (g_ln_bwd_staged && threads > 256 && stages >= 2 && (row_pair % 32) == 0) {
+  if (g_ln_bwd_staged && threads > 256 && stages >= 2 && (row_pair % 32) == 0 && !dskip) {
     const size_t smem = stages * row_pair;
     const int v = (gelu_in ? 1 : 0) + (threads <= 384 ? 2 : 0);
     auto kern = v == 3 ? ln_bwd_staged_kernel<T, 1, 384> : v == 2 ? ln_bwd_staged_kernel<T, 0, 384>
@@ -745,11 +756,11 @@ int ln_bwd_launch(const void* dy, const void* x, const void* g, const float* mea
     return 0;
   }
   if (gelu_in)
-    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 1, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 1, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C, (const T*)dskip));
   else if (threads <= 256)
-    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 0, 2>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 0, 2>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C, (const T*)dskip));
   else
-    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 0, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C));
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_kernel<T, 0, 1>, nparts, threads, 0, st, (const T*)dy, (const T*)x, (const T*)g, mean, rstd, (T*)dx, pg, pb, rows, C, (const T*)dskip));
   OFA_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
 }
@@ -810,7 +821,7 @@ static int ln_bwd_nparts_for(int rows, int C) {
 
 extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                                  const float* rstd, void* dx, void* dgamma, void* dbeta, float* workspace, int rows,
-                                 int C, int gelu_in, int accumulate, int dtype, void* stream) {
+                                 int C, int gelu_in, int accumulate, const void* dskip, int dtype, void* stream) {
   OFA_CHECK(rows > 0 && C > 0 && C % 8 == 0, "ofa_layernorm_bwd: rows=%d C=%d", rows, C);
   cudaStream_t st = (cudaStream_t)stream;
   const int nparts = ln_bwd_nparts_for(rows, C);   // <= ofa_layernorm_bwd_nparts(rows): the workspace bound
@@ -819,11 +830,11 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   OFA_CHECK(C <= 4096, "ofa_layernorm_bwd: C=%d too wide (max 4096)", C);
   int rc = 1;
   if (dtype == OFA_BF16) {
-    rc = ln_bwd_launch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st);
+    rc = ln_bwd_launch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, dskip, st);
     if (rc) return rc;
     OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<__nv_bfloat16>, dim3((C + 31) / 32, 2), 256, 0, st, pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate));
   } else if (dtype == OFA_F32) {
-    rc = ln_bwd_launch<float>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, st);
+    rc = ln_bwd_launch<float>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, dskip, st);
     if (rc) return rc;
     OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<float>, dim3((C + 31) / 32, 2), 256, 0, st, pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate));
   } else {

@@ -90,8 +90,10 @@ def _lin(mod, x, alpha=1.0, resid=None):
     return ops.linear(x, mod.weight, mod.bias, alpha, resid)
 
 
-def _ln(mod, x, resid=None, gelu_in=False):
-    return ops.layer_norm(x, mod.weight, mod.bias, resid, gelu_in, mod.eps)
+def _ln(mod, x, resid=None, gelu_in=False, fork=False):
+    """fork=True: returns (LN(x), x); taking the residual connection from the second value adds its gradient inside the
+    LayerNorm backward kernel (ops._LayerNorm) instead of in a separate pass."""
+    return ops.layer_norm(x, mod.weight, mod.bias, resid, gelu_in, mod.eps, fork)
 
 
 def _unsupported(args, names):
@@ -159,8 +161,8 @@ class _FFNMixin:
         return _lin(attn.out_proj, o, resid=x)                   # residual fused into the GEMM epilogue
 
     def _ffn(self, x):
-        r = x
-        u = _lin(self.fc1, _ln(self.final_layer_norm, x))
+        h, r = _ln(self.final_layer_norm, x, fork=True)
+        u = _lin(self.fc1, h)
         if self.ffn_layernorm is not None:
             g = _ln(self.ffn_layernorm, u, gelu_in=True)   # GELU fused into the LN prologue
         else:
@@ -188,7 +190,7 @@ class TransformerEncoderLayer(nn.Module, _FFNMixin):
         self.dropout_p = float(args.dropout)
 
     def forward(self, x, pq, pk, tok_lut, img_lut, cfg):
-        h = _ln(self.self_attn_layer_norm, x)
+        h, x = _ln(self.self_attn_layer_norm, x, fork=True)
         o = self.self_attn.forward_self(h, pq, pk, tok_lut, img_lut, cfg)
         x = self._post_attn(self.self_attn, o, self.attn_ln, x)
         return self._ffn(x)
@@ -217,14 +219,14 @@ class TransformerDecoderLayer(nn.Module, _FFNMixin):
         self.dropout_p = float(args.dropout)
 
     def forward(self, x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg):
-        h = _ln(self.self_attn_layer_norm, x)
+        h, x = _ln(self.self_attn_layer_norm, x, fork=True)
         if "decode" in self_cfg:                 # incremental decoding: K / V go through the cache
             k, v = self_kv(self.self_attn, h)
             o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg)
         else:
             o = self.self_attn.forward_self(h, spq, spk, tok_lut, None, self_cfg)
         x = self._post_attn(self.self_attn, o, self.self_attn_ln, x)
-        h = _ln(self.encoder_attn_layer_norm, x)
+        h, x = _ln(self.encoder_attn_layer_norm, x, fork=True)
         k, v = cross_kv(self.encoder_attn)
         o = self.encoder_attn(h, k, v, cpq, cpk, None, None, cross_cfg)
         x = self._post_attn(self.encoder_attn, o, self.cross_attn_ln, x)

@@ -259,7 +259,7 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, alpha, resid, out_pad):
+    def forward(ctx, x, w, b, alpha, resid, out_pad, fork=False):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         M, K = x2.shape
@@ -274,13 +274,18 @@ class _Linear(torch.autograd.Function):
         ctx.alpha, ctx.has_b, ctx.has_r, ctx.shp = alpha, b is not None, resid is not None, shp
         if ldd != N:
             y = y[:, :N]
+        ctx.set_materialize_grads(False)
+        if fork:        # second output = x: the branch that bypasses this projection; its gradient is added in the dgrad epilogue
+            return y.reshape(*shp[:-1], N), x
         return y.reshape(*shp[:-1], N)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x2, w = ctx.saved_tensors
         M, K = x2.shape
         N = w.shape[0]
+        if dy is None:
+            return dskip, None, None, None, None, None, None
         dy2 = dy.reshape(-1, N)
         if dy2.stride(-1) != 1 or (dy2.stride(0) % 8 != 0 and dy2.dtype == torch.bfloat16):
             pad = torch.zeros(M, _ceil8(N), dtype=dy2.dtype, device=dy2.device)
@@ -289,7 +294,14 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = dr = None
         bias_done = False
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha).reshape(ctx.shp)
+            sk2 = None
+            if dskip is not None:
+                sk2 = dskip.reshape(-1, K)
+                if sk2.stride(-1) != 1 or (sk2.stride(0) % 8 != 0 and sk2.dtype == torch.bfloat16):
+                    sk2 = sk2.contiguous()
+            dx = gemm(dy2, w, M, K, N, a_mn=False, b_mn=True, alpha=ctx.alpha, resid=sk2).reshape(ctx.shp)
+        elif dskip is not None:
+            dx = dskip
         if ctx.needs_input_grad[1]:
             tgt32 = _acc_target32(ctx.w_param) if K % 4 == 0 else None
             tgt, accum = (None, False) if tgt32 is not None else _acc_target(ctx.w_param)
@@ -315,7 +327,7 @@ class _Linear(torch.autograd.Function):
                 db = colsum(dy2, alpha=ctx.alpha)
         if ctx.has_r and ctx.needs_input_grad[4]:
             dr = dy
-        return dx, dw, db, None, dr, None
+        return dx, dw, db, None, dr, None, None
 
 
 class _FusedLinear(torch.autograd.Function):
@@ -385,21 +397,28 @@ def kv_linear(x, k_proj, v_proj):
     return _FusedLinear.apply(x, None, k_proj.weight, k_proj.bias, v_proj.weight, v_proj.bias)
 
 
-def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False):
-    """(x W^T + b) * alpha + resid   (nn.Linear forward/backward through ofa_gemm_bf16)."""
-    return _Linear.apply(x, w, b, alpha, resid, out_pad)
+def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False, fork=False):
+    """(x W^T + b) * alpha + resid   (nn.Linear forward/backward through ofa_gemm_bf16).  fork=True returns (y, x): use
+    the second value for a branch that bypasses the projection, its gradient is then added in the dgrad GEMM epilogue."""
+    return _Linear.apply(x, w, b, alpha, resid, out_pad, fork)
 
 
-def conv1x1(x, weight, stride=1):
+def conv1x1(x, weight, stride=1, fork=False):
     """1x1 convolution (no bias) on a channels_last [N, C, H, W] tensor = the GEMM [N*H*W, Cin] x [Cout, Cin]^T on the
     NHWC bytes (models/ofa/resnet.py:105-126: conv1 / conv3 / downsample of every bottleneck).  Returns a channels_last
-    [N, Cout, H', W'] tensor."""
+    [N, Cout, H', W'] tensor; with fork=True (stride 1) also the input again, for the identity / downsample branch of the
+    bottleneck: that branch's gradient is added in the epilogue of this convolution's dgrad GEMM."""
     _need_cuda(x)
     if stride != 1:
+        assert not fork
         x = x[:, :, ::stride, ::stride]
     x = x.contiguous(memory_format=torch.channels_last)
     N, Cin, H, W = x.shape
-    y = linear(x.permute(0, 2, 3, 1).reshape(N * H * W, Cin), weight)
+    x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, Cin)
+    if fork:
+        y, xs = linear(x2, weight, fork=True)
+        return y.view(N, H, W, weight.shape[0]).permute(0, 3, 1, 2), xs.view(N, H, W, Cin).permute(0, 3, 1, 2)
+    y = linear(x2, weight)
     return y.view(N, H, W, weight.shape[0]).permute(0, 3, 1, 2)
 
 
@@ -470,8 +489,12 @@ def colsum(x2, alpha=1.0, out=None, accumulate=False):
 # LayerNorm (+ fused GELU prologue / residual epilogue)
 # ---------------------------------------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
+    """fork=True also returns x itself (second output): the residual branch that leaves before the LayerNorm
+    (unify_transformer_layer.py:259-262).  Its gradient comes back into THIS node and is added inside the backward kernel
+    (dskip) instead of by autograd's separate accumulation pass over the activations."""
+
     @staticmethod
-    def forward(ctx, x, gamma, beta, resid, gelu_in, eps):
+    def forward(ctx, x, gamma, beta, resid, gelu_in, eps, fork):
         _need_cuda(x)
         shp = x.shape
         Cc = shp[-1]
@@ -485,14 +508,20 @@ class _LayerNorm(torch.autograd.Function):
              int(gelu_in), _dt(x2), _st(), work=("byte", (2 + (resid is not None)) * rows * Cc * x2.element_size()))
         ctx.save_for_backward(x2, gamma, mean, rstd)
         ctx.beta_param = beta
-        ctx.gelu_in, ctx.shp, ctx.has_r = gelu_in, shp, resid is not None
+        ctx.gelu_in, ctx.shp, ctx.has_r, ctx.fork = gelu_in, shp, resid is not None, fork
+        ctx.set_materialize_grads(False)
+        if fork:
+            return y.reshape(shp), x
         return y.reshape(shp)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x2, gamma, mean, rstd = ctx.saved_tensors
         rows, Cc = x2.shape
+        if dy is None:                      # only the skip branch was used
+            return dskip, None, None, None, None, None, None
         dy2 = dy.reshape(-1, Cc).contiguous()
+        sk2 = dskip.reshape(-1, Cc).contiguous() if dskip is not None else None
         dx = torch.empty_like(x2)
         (tg, ag), (tb, ab) = _acc_target(gamma), _acc_target(ctx.beta_param)
         fused = tg is not None and tb is not None and ag == ab
@@ -502,13 +531,16 @@ class _LayerNorm(torch.autograd.Function):
         nparts = _lib.load().ofa_layernorm_bwd_nparts(rows)
         ws = torch.empty(2 * nparts * Cc, dtype=torch.float32, device=x2.device)
         call("ofa_layernorm_bwd", _p(dy2), _p(x2), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db), _p(ws), rows,
-             Cc, int(ctx.gelu_in), int(acc), _dt(x2), _st(), work=("byte", 3 * rows * Cc * x2.element_size()))
-        return dx.reshape(ctx.shp), (None if fused else dg), (None if fused else db), (dy if ctx.has_r else None), None, None
+             Cc, int(ctx.gelu_in), int(acc), _p(sk2), _dt(x2), _st(),
+             work=("byte", (3 + (sk2 is not None)) * rows * Cc * x2.element_size()))
+        return (dx.reshape(ctx.shp), (None if fused else dg), (None if fused else db), (dy if ctx.has_r else None), None,
+                None, None)
 
 
-def layer_norm(x, gamma, beta, resid=None, gelu_in=False, eps=1e-5):
-    """LN(f(x)) * gamma + beta (+ resid), f = gelu if gelu_in."""
-    return _LayerNorm.apply(x, gamma, beta, resid, gelu_in, eps)
+def layer_norm(x, gamma, beta, resid=None, gelu_in=False, eps=1e-5, fork=False):
+    """LN(f(x)) * gamma + beta (+ resid), f = gelu if gelu_in.  fork=True returns (LN(x), x): use the second value for the
+    residual connection so that its gradient is added inside the LayerNorm backward kernel."""
+    return _LayerNorm.apply(x, gamma, beta, resid, gelu_in, eps, fork)
 
 
 class _Gelu(torch.autograd.Function):

@@ -73,11 +73,13 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        idn = x
-        out = _bn(self.bn1, _conv(self.conv1, x), relu=True)
+        # conv1 hands x back for the identity / downsample branch: that branch's gradient is then added in the epilogue of
+        # conv1's dgrad GEMM instead of by a separate pass over the activation
+        out, idn = ops.conv1x1(x, self.conv1.weight, fork=True)
+        out = _bn(self.bn1, out, relu=True)
         out = _bn(self.bn2, _conv(self.conv2, out), relu=True)
         if self.downsample is not None:
-            idn = _bn(self.downsample[1], _conv(self.downsample[0], x))
+            idn = _bn(self.downsample[1], _conv(self.downsample[0], idn))
         if self.drop_path_rate > 0.0 and self.training:        # resnet.py:5-20,130 (per-sample Bernoulli keep)
             out = _bn(self.bn3, _conv(self.conv3, out))
             keep = 1.0 - self.drop_path_rate

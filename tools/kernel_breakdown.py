@@ -15,6 +15,7 @@ from musketeer_b200.synthetic import build_model, make_tep_group, to_device
 ap = argparse.ArgumentParser()
 ap.add_argument("--task-batch", type=int, default=8)
 ap.add_argument("--out", default="gpurun_out/breakdown.txt")
+ap.add_argument("--ops", action="store_true", help="also list ATen operators by input shape and Python call site")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 model, task = build_model("ofa_base", dev, torch.bfloat16)
@@ -49,3 +50,19 @@ for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:160]:
 os.makedirs(os.path.dirname(a.out), exist_ok=True)
 open(a.out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
+
+if a.ops:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof2:
+        step()
+        torch.cuda.synchronize()
+    rows = []
+    for ev in prof2.key_averages(group_by_input_shape=True, group_by_stack_n=6):
+        if ev.self_device_time_total > 0:
+            stack = [f for f in ev.stack if "musketeer_b200" in f or "bench" in f or "tools" in f][:2]
+            rows.append((ev.self_device_time_total, ev.count, ev.key, str(ev.input_shapes)[:70], " <- ".join(x.split("/")[-1][:60] for x in stack)))
+    rows.sort(reverse=True)
+    out = ["", "ATen / autograd operators with device time (self), by input shape and call site:"]
+    for t, n, k, shp, st in rows[:70]:
+        out.append("%8.3f ms %5d x  %-34s %-70s %s" % (t / 1e3, n, k[:34], shp, st))
+    open(a.out, "a").write("\n".join(out) + "\n")
+    print("\n".join(out))
