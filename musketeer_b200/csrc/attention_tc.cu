@@ -294,11 +294,15 @@ struct BwdSmem {
   uint8_t dout[BQ * 128];    // [128 rows][64 x bf16]
   uint8_t p[2][BQ * 128];    // [64-key half][128 rows][128 B]
   uint8_t ds[2][BQ * 128];
-  float hist_tok[kTokHist];  // d tok_lut, indexed (i_t - jl) + 127
+  // relative-position table gradients as FIXED-POINT sums: value * 2^(kq - E) in int32, E = the CTA's running block
+  // exponent.  Shared-memory float atomics are compare-and-swap loops on sm_100 (5.5 us per 128x128 tile, measured:
+  // tools/scratch/atom_probe.cu); int32 adds are native ATOMS.ADD (0.9 us) and order-independent.
+  int hist_tok[kTokHist];    // d tok_lut, indexed (i_t - jl) + 127
   float tok_s[kTokHist];     // tok_lut staged with the same indexing (valid when all keys of the tile are text)
-  float hist_img[kImgHistMax + 1];
+  int hist_img[kImgHistMax + 1];
+  alignas(16) uint32_t wmax[16];   // per-warp max |dS| of the current tile (float bits)
   int kinfo[BK2];            // bit31 masked | bit30 image key | [0,16) kr*(2*ibs-1)+kc
-  uint64_t bar_kv, bar_q, bar_sp, bar_dq;
+  uint64_t bar_kv, bar_q, bar_sp, bar_dq, bar_qf;
   uint32_t tmem_addr;
 };
 
@@ -326,7 +330,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (t == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmPQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmPK);
     tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
-    mbar_init(&sm.bar_kv, 1); mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_sp, 1); mbar_init(&sm.bar_dq, 1);
+    mbar_init(&sm.bar_kv, 1); mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_sp, 1); mbar_init(&sm.bar_dq, 1); mbar_init(&sm.bar_qf, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&sm.tmem_addr);
@@ -336,7 +340,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const bool keys_all_txt = bz.tok_lut != nullptr && (k0 >= bz.k_text_off) && (bz.img_lut == nullptr || k0 >= bz.n_img_k);
   const int tok_base = k0 - bz.k_text_off + 127;   // (i_t - j_t) = u - tok_base with u = i_t - jl + 127
   for (int e = t; e < kTokHist; e += kBwdThreads) {
-    sm.hist_tok[e] = 0.f;
+    sm.hist_tok[e] = 0;
     float lv = 0.f;
     if (bz.tok_lut) {
       const int rel = e - tok_base + bz.tok_max - 1;
@@ -344,7 +348,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     sm.tok_s[e] = lv;
   }
-  for (int e = t; e < kImgHistMax + 1; e += kBwdThreads) sm.hist_img[e] = 0.f;
+  for (int e = t; e < kImgHistMax + 1; e += kBwdThreads) sm.hist_img[e] = 0;
   int my_masked = 0;
   if (t < BK2) {
     const int j = k0 + t;
@@ -362,6 +366,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tm = sm.tmem_addr;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 384;
+  // masked keys (padding / beyond S) of this thread's 32 columns: the keys are stationary, so one bit mask serves every
+  // query tile and the fast softmax paths stay usable on tiles that contain padded keys
+  uint32_t colmask = 0;
+  if (keys_any_masked) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) colmask |= (sm.kinfo[qd * 32 + jj] < 0 ? 1u : 0u) << jj;
+  }
 
   if (qt0 < nq_tiles && t == 0) {
     mbar_expect_tx(&sm.bar_kv, 3 * BK2 * 128);
@@ -385,6 +396,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const bool dbg = blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == 1;
   long long dbg_last = clock64();
 #endif
+  // fixed-point histograms: kq fractional bits below the block exponent; a bin receives at most 128 values of magnitude
+  // <= 2^kq per tile, so 2^(kq + 7) * tiles stays below 2^30
+  const bool has_hist = has_tok || has_img;
+  int kq = 23;
+  for (int n = 1; n < nq_tiles - qt0; n <<= 1) --kq;
+  int e_cur = 0;                                   // biased exponent E + 126 of the current scale; 0 = tables still empty
   int it = 0;
   for (int qt = qt0; qt < nq_tiles; ++qt, ++it) {
     const uint32_t ph = it & 1;
@@ -393,6 +410,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (t == 0) {
       if (it == 0) mbar_wait(&sm.bar_kv, 0);
       mbar_wait(&sm.bar_q, ph);
+      DBG_T(10)
       tc_fence_after();
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb)
@@ -404,6 +422,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int ks = 0; ks < 4; ++ks)
         umma_f16(tm + COL_DP, umma_smem_desc(smem_u32(sm.dout) + ks * 32, 16, 1024),
                  umma_smem_desc(smem_u32(sm.v) + ks * 32, 16, 1024), id_s, ks != 0);
+      DBG_T(11)
       tma_store_wait_read<0>();   // the previous tile's dQ' reduce has finished reading the P / dS buffers (see below)
       umma_commit(&sm.bar_sp);
     }
@@ -425,8 +444,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int i_t = iabs - bz.q_text_off;
     const int tu = i_t + 127 - col0;   // tok_s / hist_tok index of column col0 for this row; column jj -> tu - jj
     // fast paths need: no masked key in the tile, a valid row, and no causal cut inside this thread's 32 columns
-    const bool plain = !keys_any_masked && row_ok && !(a.causal && k0 + col0 + 31 > iabs);
-    int mode = 3;                                       // 3 = generic per-element path
+    const bool plain = row_ok && !(a.causal && k0 + col0 + 31 > iabs);
+    int mode = row_ok ? 3 : 4;                          // 3 = generic per-element path, 4 = row beyond T: all zero
     if (plain) {
       if (q_text && keys_all_txt) mode = 1;             // text x text: token LUT from shared memory
       else if (q_img && keys_all_img) mode = 2;         // image x image: image LUT gather
@@ -447,14 +466,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (mode == 0) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const float p = __expf(__uint_as_float(rs[jj]) - lse);
+          float p = __expf(__uint_as_float(rs[jj]) - lse);
+          if (colmask & (1u << jj)) p = 0.f;
           pv[jj] = p;
           dsv[jj] = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
         }
+      } else if (mode == 4) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) { pv[jj] = 0.f; dsv[jj] = 0.f; }
       } else if (mode == 1) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const float p = __expf(__uint_as_float(rs[jj]) + sm.tok_s[tu - jj] - lse);
+          float p = __expf(__uint_as_float(rs[jj]) + sm.tok_s[tu - jj] - lse);
+          if (colmask & (1u << jj)) p = 0.f;
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
@@ -463,7 +487,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const int idx = rowbase - (sm.kinfo[col0 + jj] & 0xffff);
-          const float p = __expf(__uint_as_float(rs[jj]) + __ldg(img_lut + idx) - lse);
+          float p = __expf(__uint_as_float(rs[jj]) + __ldg(img_lut + idx) - lse);
+          if (colmask & (1u << jj)) p = 0.f;
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
@@ -500,6 +525,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                        pack_bf16(dsv[c16 * 8 + 4], dsv[c16 * 8 + 5]), pack_bf16(dsv[c16 * 8 + 6], dsv[c16 * 8 + 7]));
       }
     }
+    if (has_hist) {
+      float m = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) m = fmaxf(m, fabsf(dsv[jj]));
+      uint32_t mb = __float_as_uint(m);
+      if (mb >= 0x7f800000u) mb = 0x7f7fffffu;      // inf / nan: saturate the scale, the conversion below saturates too
+      const uint32_t wm = __reduce_max_sync(0xffffffffu, mb);   // non-negative floats order like their bit patterns
+      if ((t & 31) == 0) sm.wmax[warp] = wm;
+    }
     DBG_T(3)
     fence_proxy_async();
     tc_fence_before();
@@ -516,34 +550,73 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int ks = 0; ks < 8; ++ks)   // dK'[keys, 128] += dS^T Q'
         umma_f16(tm + COL_DK, umma_smem_desc(smem_u32(sm.ds[0]) + ks * 2048, BQ * 128, 1024),
                  umma_smem_desc(smem_u32(sm.q[0]) + ks * 2048, BQ * 128, 1024), id_dk, acc | (ks != 0));
+      umma_commit(&sm.bar_qf);         // dV and dK' retired = Q' and dO are no longer read
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)   // dQ'[rows, 128] = dS K'      (contraction over the 128 keys)
         umma_f16(tm + COL_S, umma_smem_desc(smem_u32(sm.ds[ks >> 2]) + (ks & 3) * 32, 16, 1024),
                  umma_smem_desc(smem_u32(sm.k[0]) + ks * 2048, BK2 * 128, 1024), id_dq, ks != 0);
       umma_commit(&sm.bar_dq);
+      if (qt + 1 < nq_tiles) {
+        // reload Q' / dO for the next query tile as soon as dV / dK' are done: the TMA latency (~2 us) then runs under the
+        // dQ' GEMM and the histogram phase instead of in front of the next tile's first GEMM
+        mbar_wait(&sm.bar_qf, ph);
+        tc_fence_after();
+        mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
+        tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, q0 + BQ, b);
+        tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, q0 + BQ, b);
+        tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, q0 + BQ, b);
+      }
     }
     __syncwarp();
     DBG_T(9)
-    // relative-position table gradients: shared-memory histogram updates (fp32 shared atomics are CAS loops) run here,
-    // under the three tensor-core GEMMs just issued, instead of in front of them
+    // relative-position table gradients: shared-memory histogram updates run here, under the three tensor-core GEMMs just
+    // issued.  Block exponent: every thread derives the tile's max |dS| from the 16 warp maxima; when it outgrows the
+    // current scale the tables are shifted down first (rare: the scale only ever grows, by at least 2 bits a time).
+    float qscale = 0.f;
+    if (has_hist) {
+      uint32_t mb = 0;
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) {
+        const uint4 u = reinterpret_cast<const uint4*>(sm.wmax)[w4];
+        mb = max(max(mb, u.x), max(max(u.y, u.z), u.w));
+      }
+      int e_t = (int)(mb >> 23);                    // |dS| < 2^(e_t - 126) for every element of the tile
+      if (e_t < 40) e_t = 40;                       // all-zero / denormal-scale tiles: any scale will do
+      if (e_t > e_cur) {
+        const int e_new = e_t + 1;
+        if (e_cur != 0) {                           // CTA-uniform branch
+          const int sh = e_new - e_cur;
+          for (int e = t; e < kTokHist + kImgHistMax + 1; e += kBwdThreads) {
+            int* bin = e < kTokHist ? &sm.hist_tok[e] : &sm.hist_img[e - kTokHist];
+            const int v = *bin;
+            if (v != 0) *bin = sh >= 31 ? 0 : (v + (1 << (sh - 1))) >> sh;
+          }
+          __syncthreads();
+        }
+        e_cur = e_new;
+      }
+      qscale = __uint_as_float((uint32_t)(253 + kq - e_cur) << 23);      // 2^(kq - (e_cur - 126))
+    }
     if (mode == 1) {
       if (has_tok) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) atomicAdd(&sm.hist_tok[tu - jj], dsv[jj]);
+        for (int jj = 0; jj < 32; ++jj) atomicAdd(&sm.hist_tok[tu - jj], __float2int_rn(dsv[jj] * qscale));
       }
     } else if (mode == 2) {
       if (has_img) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) atomicAdd(&sm.hist_img[rowbase - (sm.kinfo[col0 + jj] & 0xffff)], dsv[jj]);
+        for (int jj = 0; jj < 32; ++jj)
+          atomicAdd(&sm.hist_img[rowbase - (sm.kinfo[col0 + jj] & 0xffff)], __float2int_rn(dsv[jj] * qscale));
       }
-    } else if (mode == 3 && (has_tok || has_img)) {
+    } else if (mode == 3 && has_hist) {
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {
         const int jl = col0 + jj;
         const int info = sm.kinfo[jl];
         if (dsv[jj] != 0.f) {       // masked elements carry p = 0
-          if (has_tok && q_text && k0 + jl >= bz.k_text_off) atomicAdd(&sm.hist_tok[tu - jj], dsv[jj]);
-          if (has_img && q_img && (info & 0x40000000)) atomicAdd(&sm.hist_img[rowbase - (info & 0xffff)], dsv[jj]);
+          const int qv = __float2int_rn(dsv[jj] * qscale);
+          if (has_tok && q_text && k0 + jl >= bz.k_text_off) atomicAdd(&sm.hist_tok[tu - jj], qv);
+          if (has_img && q_img && (info & 0x40000000)) atomicAdd(&sm.hist_img[rowbase - (info & 0xffff)], qv);
         }
       }
     }
@@ -551,12 +624,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(&sm.bar_dq, ph);
     tc_fence_after();
     DBG_T(6)
-    if (t == 0 && qt + 1 < nq_tiles) {   // Q' / dO / P / dS buffers are free again
-      mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
-      tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, q0 + BQ, b);
-      tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, q0 + BQ, b);
-      tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, q0 + BQ, b);
-    }
     {
       // dQ' partial [128 rows][32 columns of this quarter] -> fp32 slab qd (128B-swizzled rows) in the P / dS buffers, which
       // are idle until the next tile's softmax phase; one TMA reduce per slab adds it into dq_acc (rows >= T are clipped)
@@ -626,19 +693,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int v4 = 0; v4 < 2; ++v4) reinterpret_cast<uint4*>(d1)[v4] = z;
   }
   __syncthreads();
+  const float unq = e_cur != 0 ? __uint_as_float((uint32_t)(e_cur + 1 - kq) << 23) : 0.f;      // 2^((e_cur - 126) - kq)
   if (has_tok) {
     float* gt = g.dtok_lut + (size_t)h * (2 * bz.tok_max - 1);
     for (int e = t; e < kTokHist; e += kBwdThreads) {
-      const float v = sm.hist_tok[e];
+      const int v = sm.hist_tok[e];
       const int rel = e - tok_base + bz.tok_max - 1;
-      if (v != 0.f && rel >= 0 && rel < 2 * bz.tok_max - 1) atomicAdd(gt + rel, v);
+      if (v != 0 && rel >= 0 && rel < 2 * bz.tok_max - 1) atomicAdd(gt + rel, (float)v * unq);
     }
   }
   if (has_img) {
     float* gi = g.dimg_lut + (size_t)h * bz.n_img_rel;
     for (int e = t; e < bz.n_img_rel && e < kImgHistMax; e += kBwdThreads) {
-      const float v = sm.hist_img[e];
-      if (v != 0.f) atomicAdd(gi + e, v);
+      const int v = sm.hist_img[e];
+      if (v != 0) atomicAdd(gi + e, (float)v * unq);
     }
   }
   tc_fence_before();

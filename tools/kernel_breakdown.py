@@ -57,8 +57,8 @@ if a.ops:
         torch.cuda.synchronize()
     rows = []
     for ev in prof2.key_averages(group_by_input_shape=True, group_by_stack_n=6):
-        if ev.self_device_time_total > 0:
-            stack = [f for f in ev.stack if "musketeer_b200" in f or "bench" in f or "tools" in f][:2]
+        if ev.self_device_time_total > 0 and ev.key.startswith("aten::"):
+            stack = [f for f in ev.stack if "musketeer_b200/" in f or "bench" in f][:3]
             rows.append((ev.self_device_time_total, ev.count, ev.key, str(ev.input_shapes)[:70], " <- ".join(x.split("/")[-1][:60] for x in stack)))
     rows.sort(reverse=True)
     out = ["", "ATen / autograd operators with device time (self), by input shape and call site:"]
