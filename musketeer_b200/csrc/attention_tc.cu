@@ -445,7 +445,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int tu = i_t + 127 - col0;   // tok_s / hist_tok index of column col0 for this row; column jj -> tu - jj
     // fast paths need: no masked key in the tile, a valid row, and no causal cut inside this thread's 32 columns
     const bool plain = row_ok && !(a.causal && k0 + col0 + 31 > iabs);
-    int mode = row_ok ? 3 : 4;                          // 3 = generic per-element path, 4 = row beyond T: all zero
+    const uint32_t cm = row_ok ? colmask : 0xffffffffu; // rows beyond T: the plain path with every column masked
+    int mode = row_ok ? 3 : 0;                          // 3 = generic per-element path
     if (plain) {
       if (q_text && keys_all_txt) mode = 1;             // text x text: token LUT from shared memory
       else if (q_img && keys_all_img) mode = 2;         // image x image: image LUT gather
@@ -467,18 +468,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           float p = __expf(__uint_as_float(rs[jj]) - lse);
-          if (colmask & (1u << jj)) p = 0.f;
+          if (cm & (1u << jj)) p = 0.f;
           pv[jj] = p;
           dsv[jj] = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
         }
-      } else if (mode == 4) {
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) { pv[jj] = 0.f; dsv[jj] = 0.f; }
       } else if (mode == 1) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           float p = __expf(__uint_as_float(rs[jj]) + sm.tok_s[tu - jj] - lse);
-          if (colmask & (1u << jj)) p = 0.f;
+          if (cm & (1u << jj)) p = 0.f;
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
@@ -488,7 +486,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int jj = 0; jj < 32; ++jj) {
           const int idx = rowbase - (sm.kinfo[col0 + jj] & 0xffff);
           float p = __expf(__uint_as_float(rs[jj]) + __ldg(img_lut + idx) - lse);
-          if (colmask & (1u << jj)) p = 0.f;
+          if (cm & (1u << jj)) p = 0.f;
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
           dsv[jj] = ds;
