@@ -139,16 +139,39 @@ __device__ __forceinline__ void store_row32(OutT* dp, const float (&v)[32], int 
 // packed into a 128B-swizzled [32][64] slab (lane = row, conflict-free 16-byte stores) and written with one
 // cp.async.bulk.tensor store, which also clips rows >= M and columns >= N.  Replaces 32 scattered 64-byte row segments
 // per warp instruction (2x the L2 write transactions) with full-line writes, and takes the stores off the LSU.
-__device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*stage)[4096], int& sbuf, uint32_t tmem_row,
+template <bool RESID>
+__device__ __forceinline__ void epilogue_tma_impl(const CUtensorMap* tmD, uint8_t (*stage)[4096], int& sbuf, uint32_t tmem_row,
                                              int nch, int row, int n0, int bz, const GemmParams& p, int lane) {
   const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(p.bias);
   const __nv_bfloat16* R =
-      p.resid ? reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)bz * p.batch_stride_r : nullptr;
+      RESID && p.resid ? reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)bz * p.batch_stride_r : nullptr;
   const int row0 = row - lane;
+  // residual rows are fetched one 64-column step ahead: each lane reads its own row (32 different lines per load
+  // instruction), so an inline load would expose a full memory latency per step and the epilogue of short-K GEMMs
+  // (the 1x1-convolution dgrads with the identity-branch gradient as residual) would be bound by it
+  const bool rfast = RESID && R != nullptr && row < p.M && ((reinterpret_cast<uintptr_t>(R) & 15) == 0) && (p.ldr % 8 == 0) && (n0 % 8 == 0);
+  uint4 rn[8];
+  auto fetch = [&](int c2n) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int nb = n0 + (c2n + half) * 32;
+      const bool ok = c2n + half < nch && nb + 32 <= p.N;
+      const uint4* src = reinterpret_cast<const uint4*>(R + (long long)row * p.ldr + (ok ? nb : 0));
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) rn[half * 4 + q4] = ok ? src[q4] : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  if (rfast) fetch(0);
 #pragma unroll 1
   for (int c2 = 0; c2 < nch; c2 += 2) {
     const int nb0 = n0 + c2 * 32;
     if (nb0 >= p.N) break;
+    uint4 rc[8];
+    if (RESID) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rc[q] = rn[q];
+      if (rfast && c2 + 2 < nch) fetch(c2 + 2);
+    }
     uint8_t* sb = stage[sbuf];
     if (lane == 0) tma_store_wait_read<1>();   // the store issued two groups ago has finished reading this slab
     __syncwarp();
@@ -175,7 +198,14 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*s
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       }
-      if (R && row < p.M) {
+      if (RESID && rfast && nvalid == 32) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rc[half * 4 + q4]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); v[q4 * 8 + 2 * k] += f.x; v[q4 * 8 + 2 * k + 1] += f.y; }
+        }
+      } else if (RESID && R && row < p.M) {
         const __nv_bfloat16* rr = R + (long long)row * p.ldr + nb;
         if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
 #pragma unroll
@@ -207,6 +237,13 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*s
     }
     sbuf ^= 1;
   }
+}
+
+// the residual-free instantiation carries none of the residual prefetch state (most GEMMs of the step)
+__device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, uint8_t (*stage)[4096], int& sbuf, uint32_t tmem_row,
+                                             int nch, int row, int n0, int bz, const GemmParams& p, int lane) {
+  if (p.resid) epilogue_tma_impl<true>(tmD, stage, sbuf, tmem_row, nch, row, n0, bz, p, lane);
+  else epilogue_tma_impl<false>(tmD, stage, sbuf, tmem_row, nch, row, n0, bz, p, lane);
 }
 
 
