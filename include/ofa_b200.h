@@ -143,6 +143,12 @@ int ofa_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx, int
  * convolution and its weight gradient are ofa_gemm_bf16 calls on col.                                                   */
 int ofa_stem_patches(const void* x, void* col, int N, int H, int W, void* stream);
 
+/* ---- stride-2 pixel subsampling of an NHWC activation = the input side of the stride-2 1x1 downsample convolutions
+ * (models/ofa/resnet.py:196-203), and its adjoint (zero fill + scatter in one pass).  [N, H, W, C] are the dimensions of
+ * the FULL-resolution tensor; the subsampled one is [N, (H+1)/2, (W+1)/2, C].  esize = bytes per element (2 | 4),
+ * C * esize % 16 == 0.  backward = 0: dst = src[:, ::2, ::2, :];  backward = 1: dst (full) = adjoint of src (subsampled) */
+int ofa_subsample2(const void* src, void* dst, int N, int H, int W, int C, int esize, int backward, void* stream);
+
 /* ---- fused optimizer step (trainer.py:863-898 multiply_grads -> clip_grad_norm -> optimizer.step,
  * with the un-vendored fairseq Adam / FP16Optimizer arithmetic: fp32 master weights, decoupled weight decay
  * p -= wd*lr*p, bias-corrected step size, global-norm clipping with coefficient clip/(norm+1e-6)).

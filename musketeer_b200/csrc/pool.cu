@@ -159,3 +159,51 @@ extern "C" int ofa_stem_patches(const void* x, void* col, int N, int H, int W, v
                           (const __nv_bfloat16*)x, (__nv_bfloat16*)col, N, H, W, OH, OW));
   return 0;
 }
+
+// ---- stride-2 pixel subsampling of an NHWC activation (the input side of the stride-2 1x1 downsample convolutions,
+// models/ofa/resnet.py:196-203: conv1x1(inplanes, planes * 4, stride)) and its adjoint.  16-byte vectors; esize = bytes per
+// element, C * esize % 16 == 0.   fwd: y[n, h, w, :] = x[n, 2h, 2w, :]     bwd: dx = 0 except dx[n, 2h, 2w, :] = dy[n, h, w, :]
+namespace {
+__global__ void __launch_bounds__(256) subsample2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H,
+                                                             int W, int Ho, int Wo, int CV) {
+  pdl_sync();
+  const long long total = (long long)N * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long pix = i / CV;
+    const int wo = (int)(pix % Wo); pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    y[i] = x[(((long long)n * H + 2 * ho) * W + 2 * wo) * CV + cv];
+  }
+}
+__global__ void __launch_bounds__(256) subsample2_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H,
+                                                             int W, int Ho, int Wo, int CV) {
+  pdl_sync();
+  const long long total = (long long)N * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long pix = i / CV;
+    const int w = (int)(pix % W); pix /= W;
+    const int h = (int)(pix % H);
+    const int n = (int)(pix / H);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (((h | w) & 1) == 0) v = dy[(((long long)n * Ho + (h >> 1)) * Wo + (w >> 1)) * CV + cv];
+    dx[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int ofa_subsample2(const void* src, void* dst, int N, int H, int W, int C, int esize, int backward, void* stream) {
+  OFA_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && (esize == 2 || esize == 4) && (C * esize) % 16 == 0,
+            "ofa_subsample2: N=%d H=%d W=%d C=%d esize=%d (C * esize must be a multiple of 16)", N, H, W, C, esize);
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C * esize / 16;
+  const long long total = (long long)N * (backward ? (long long)H * W : (long long)Ho * Wo) * CV;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backward) OFA_CUDA(ofa_launch_pdl(subsample2_bwd_kernel, (unsigned)blocks, 256, 0, st, (const uint4*)src, (uint4*)dst, N, H, W, Ho, Wo, CV));
+  else OFA_CUDA(ofa_launch_pdl(subsample2_fwd_kernel, (unsigned)blocks, 256, 0, st, (const uint4*)src, (uint4*)dst, N, H, W, Ho, Wo, CV));
+  OFA_LAUNCH_CHECK("subsample2_kernel");
+  return 0;
+}

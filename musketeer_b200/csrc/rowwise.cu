@@ -541,25 +541,29 @@ __global__ void __launch_bounds__(MAXT, 2) ln_bwd_staged_kernel(const T* __restr
   }
 }
 
-// sums the [nparts, C] fp32 partials: block = 32 columns x 8 partial-lanes, coalesced along columns
+// sums the [nparts, C] fp32 partials: block = 8 columns x 32 partial-lanes (one 32-byte sector per row and lane group);
+// C/8 x 2 CTAs, so that the few hundred KB .. MB of partials are read by ~200 CTAs instead of ~50
 template <typename T>
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b,
                                                             int nparts, int C, T* __restrict__ dgamma, T* __restrict__ dbeta,
                                                             int accumulate) {
   pdl_sync();
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  const int cx = threadIdx.x & 7, py = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cx;
   const float* src = blockIdx.y ? part_b : part_g;
-  float s = 0.f;
-  if (c < C)
-    for (int p = py; p < nparts; p += 8) s += src[(size_t)p * C + c];
-  __shared__ float red[8][33];
-  red[py][cx] = s;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    int p = py;
+    for (; p + 32 < nparts; p += 64) { s0 += src[(size_t)p * C + c]; s1 += src[(size_t)(p + 32) * C + c]; }
+    if (p < nparts) s0 += src[(size_t)p * C + c];
+  }
+  __shared__ float red[32][9];
+  red[py][cx] = s0 + s1;
   __syncthreads();
   if (py == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    for (int i = 0; i < 32; ++i) t += red[i][cx];
     T* dst = (blockIdx.y ? dbeta : dgamma) + c;
     if (accumulate) t += (float)*dst;
     *dst = (T)t;
@@ -832,11 +836,11 @@ extern "C" int ofa_layernorm_bwd(const void* dy, const void* x, const void* gamm
   if (dtype == OFA_BF16) {
     rc = ln_bwd_launch<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, dskip, st);
     if (rc) return rc;
-    OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<__nv_bfloat16>, dim3((C + 31) / 32, 2), 256, 0, st, pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate));
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<__nv_bfloat16>, dim3((C + 7) / 8, 2), 256, 0, st, pg, pb, nparts, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate));
   } else if (dtype == OFA_F32) {
     rc = ln_bwd_launch<float>(dy, x, gamma, mean, rstd, dx, pg, pb, nparts, rows, C, gelu_in, dskip, st);
     if (rc) return rc;
-    OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<float>, dim3((C + 31) / 32, 2), 256, 0, st, pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate));
+    OFA_CUDA(ofa_launch_pdl(ln_bwd_reduce_kernel<float>, dim3((C + 7) / 8, 2), 256, 0, st, pg, pb, nparts, C, (float*)dgamma, (float*)dbeta, accumulate));
   } else {
     return ofa_set_error("ofa_layernorm_bwd: bad dtype %d", dtype);
   }

@@ -403,6 +403,28 @@ def linear(x, w, b=None, alpha=1.0, resid=None, out_pad=False, fork=False):
     return _Linear.apply(x, w, b, alpha, resid, out_pad, fork)
 
 
+class _Subsample2(torch.autograd.Function):
+    """x[:, :, ::2, ::2] of a channels_last tensor as one gather pass; the backward writes zeros and the scattered gradient in
+    one pass (csrc/pool.cu) instead of autograd's fill + strided copy."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, Cc, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = torch.empty((N, Cc, (H + 1) // 2, (W + 1) // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        call("ofa_subsample2", _p(x), _p(y), N, H, W, Cc, x.element_size(), 0, _st(), work=("byte", 2 * y.numel() * x.element_size()))
+        ctx.shape = (N, Cc, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, Cc, H, W = ctx.shape
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, Cc, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        call("ofa_subsample2", _p(dy), _p(dx), N, H, W, Cc, dy.element_size(), 1, _st(), work=("byte", dx.numel() * dy.element_size()))
+        return dx
+
+
 def conv1x1(x, weight, stride=1, fork=False):
     """1x1 convolution (no bias) on a channels_last [N, C, H, W] tensor = the GEMM [N*H*W, Cin] x [Cout, Cin]^T on the
     NHWC bytes (models/ofa/resnet.py:105-126: conv1 / conv3 / downsample of every bottleneck).  Returns a channels_last
@@ -411,7 +433,10 @@ def conv1x1(x, weight, stride=1, fork=False):
     _need_cuda(x)
     if stride != 1:
         assert not fork
-        x = x[:, :, ::stride, ::stride]
+        if stride == 2 and (x.shape[1] * x.element_size()) % 16 == 0:
+            x = _Subsample2.apply(x)
+        else:
+            x = x[:, :, ::stride, ::stride]
     x = x.contiguous(memory_format=torch.channels_last)
     N, Cin, H, W = x.shape
     x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, Cin)

@@ -128,6 +128,29 @@ def test_layernorm_fork_adds_skip_gradient(dtype, rows, C):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W", [(12, 12), (9, 7)])
+def test_conv1x1_stride2_subsample(dtype, H, W):
+    """stride-2 1x1 convolution: gather kernel in front of the GEMM, zero-fill + scatter adjoint behind its dgrad (bit-exact
+    data movement; the products are compared against fp64)."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(H * 31 + W)
+    x = torch.randn(3, 64, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = (0.1 * torch.randn(32, 64, 1, 1, generator=g)).cuda().to(dtype).requires_grad_()
+    y = ops.conv1x1(x, w, stride=2)
+    a = torch.randn(y.shape, generator=g).cuda().to(dtype)
+    (y * a).sum().backward()
+    xf, wf = x.detach().double().cpu().requires_grad_(), w.detach().double().cpu().requires_grad_()
+    yr = F.conv2d(xf, wf, stride=2)
+    assert y.shape == yr.shape
+    (yr * a.double().cpu()).sum().backward()
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert (y.double().cpu() - yr).abs().max().item() < tol
+    assert (x.grad.double().cpu() - xf.grad).abs().max().item() < tol * 4
+    assert torch.equal(x.grad[:, :, 1::2, :], torch.zeros_like(x.grad[:, :, 1::2, :]))
+    assert (w.grad.double().cpu() - wf.grad).abs().max().item() < tol * 20
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv1x1_fork_adds_identity_gradient(dtype):
     """conv1x1(fork=True): the identity branch's gradient joins dx in the dgrad GEMM epilogue."""
     ops = _ops()

@@ -66,3 +66,17 @@ if a.ops:
         out.append("%8.3f ms %5d x  %-34s %-70s %s" % (t / 1e3, n, k[:34], shp, st))
     open(a.out, "a").write("\n".join(out) + "\n")
     print("\n".join(out))
+
+    # who launches the big elementwise kernels?  (CPU op -> parents)
+    out = ["", "large ATen elementwise / copy kernels and the operators that launched them:"]
+    for ev in prof2.events():
+        ks = getattr(ev, "kernels", None) or []
+        for k in ks:
+            if k.duration > 150 and ("elementwise" in k.name or "copy" in k.name.lower() or "Fill" in k.name):
+                chain, e = [], ev
+                while e is not None and len(chain) < 6:
+                    chain.append("%s%s" % (e.name[:40], str(e.input_shapes)[:60] if e.input_shapes else ""))
+                    e = e.cpu_parent
+                out.append("%8.1f us  %s  <=  %s" % (k.duration, k.name[:60], "  <-  ".join(chain)))
+    open(a.out, "a").write("\n".join(out) + "\n")
+    print("\n".join(out))
