@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/scratch/atom_probe tools/scratch/atom_probe.cu
 // probe: shared-memory histogram update cost, float CAS-loop atomics vs native int32 atomics, attention-bwd access pattern
 #include <cstdio>
 #include <cuda_runtime.h>
