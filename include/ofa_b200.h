@@ -162,12 +162,15 @@ int ofa_adam_step(const void* chunk_table, int n_chunks, float* partial_sqnorm, 
 
 /* ---- label-smoothed CE (+R-Drop KL): loss rows and d(logits) in one kernel, gradient written in place --------------
  * replaces criterions/label_smoothed_cross_entropy.py:81-126,228-260.                                                */
+/* grad_row_scale (optional, [R]): the gradient rows are written multiplied by it -- the caller's promise of each row's
+ * upstream gradient (e.g. 1 / sample_size of the row's task), so that the later ofa_scale_rows pass over the logits-sized
+ * gradient degenerates to skipped rows (scale exactly 1); loss_rows / nll_rows stay unscaled.                          */
 int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* target, const unsigned char* cmask,
                       const float* conf, int rows_per_sample, int R, int V, long long pad_idx, float eps, int cs,
-                      int ce, int rdrop, float reg_alpha, float* loss_rows, float* nll_rows, float* kl_rows, int dtype,
-                      void* stream);
+                      int ce, int rdrop, float reg_alpha, float* loss_rows, float* nll_rows, float* kl_rows,
+                      const float* grad_row_scale, int dtype, void* stream);
 int ofa_scale_rows(void* x, long long ld, int R, int V, const float* scale, const unsigned char* row_keep,
-                   int scale_per_row, int dtype, void* stream); /* scale: device scalar, or one factor per row */
+                   int scale_per_row, int dtype, void* stream); /* scale: device scalar, or one factor per row; rows with factor 1 are skipped */
 
 /* ---- attention with OFA position biases (unify_multihead_attention.py:345-398; bias assembly of
  * unify_transformer.py:640-658,906-933,1282-1318,1519-1529 computed in-kernel) ------------------------------------- */

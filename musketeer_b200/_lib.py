@@ -68,8 +68,8 @@ SIGNATURES = {
     "ofa_batchnorm_set_tuning": [c_i, c_i],
     "ofa_batchnorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
     "ofa_batchnorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
-    "ofa_ls_ce_fwd_bwd": [c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_i,
-                          c_p],
+    "ofa_ls_ce_fwd_bwd": [c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p,
+                          c_i, c_p],
     "ofa_conv3x3_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "ofa_conv3x3_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
     "ofa_conv3x3_wgrad_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p],

@@ -166,9 +166,16 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
             logits, _ = model.decoder(torch.cat(prevs, 0), encoder_out=eo, padded_logits=True)
             if hasattr(model, "dec_timer"):
                 model.dec_timer[1] += 1
-            loss_rows, nll_rows = ops.ls_cross_entropy_rows(logits, torch.cat(tgts, 0), self.eps, pad,
-                                                            crange=self.constraint_range)
             n = b * Tm
+            # every row's loss will be divided by its task's sample size (forward(): loss_v1 / ss1 + ...): promise that
+            # upstream gradient to the loss kernel, so the logits-sized gradient is written once, already scaled
+            expected = None
+            if self.ignore_prefix_size == 0 and not self.ignore_eos and all("ntokens" in out[i] for _, i in grp):
+                ones = torch.ones(n, dtype=torch.float32, device=logits.device)
+                expected = torch.cat([ones / (out[i]["target"].size(0) if self.sentence_avg else out[i]["ntokens"])
+                                      for _, i in grp])
+            loss_rows, nll_rows = ops.ls_cross_entropy_rows(logits, torch.cat(tgts, 0), self.eps, pad,
+                                                            crange=self.constraint_range, expected_grad=expected)
             for g, (_, i) in enumerate(grp):
                 out[i]["_precomputed"] = (loss_rows[g * n:(g + 1) * n].sum(), nll_rows[g * n:(g + 1) * n].sum())
 

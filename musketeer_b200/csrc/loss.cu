@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
                                                          int rows_per_sample, int R, int V, long long pad_idx, float eps,
                                                          int cs, int ce, int rdrop, float reg_alpha,
                                                          float* __restrict__ loss_out, float* __restrict__ nll_out,
-                                                         float* __restrict__ kl_out) {
+                                                         float* __restrict__ kl_out, const float* __restrict__ grad_row_scale) {
   pdl_sync();
   __shared__ float sh[kThreads / 32];
   const int half = rdrop ? R / 2 : R;
@@ -139,8 +139,10 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
   }
   __syncthreads();  // all reads of x[target] above happen before the in-place overwrite below
   // gradient sweep (in place).  d/dx_u = c(1-eps-eps_i)(P_u - [u=y]) + c eps_i (n P_u - 1) + alpha (g_u - P_u sum_v g_v)
-  float sg[2];
+  float sg[2], gs[2] = {1.f, 1.f};
   for (int k = 0; k < nrow; ++k) sg[k] = 0.5f * (-c[k] * c[k] * A[k] - c[k] * (Z[1 - k] - Z[k]));
+  if (grad_row_scale)       // the caller's promise of the upstream gradient of this row's loss (the loss value stays unscaled)
+    for (int k = 0; k < nrow; ++k) gs[k] = grad_row_scale[r0 + k * half];
   for (int v = threadIdx.x; v < V; v += kThreads) {
     const bool ok = rc[0].allowed(v);
     float x0 = 0.f, x1 = 0.f;
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(kThreads) ls_ce_kernel(T* __restrict__ logits,
         g1 += reg_alpha * (gq - Q * sg[1]);
       }
     }
-    xr[0][v] = (T)g0;
-    if (rdrop) xr[1][v] = (T)g1;
+    xr[0][v] = (T)(g0 * gs[0]);
+    if (rdrop) xr[1][v] = (T)(g1 * gs[1]);
   }
 }
 
@@ -172,8 +174,22 @@ __global__ void scale_rows_kernel(T* __restrict__ x, long long ld, int V, const 
   pdl_sync();
   const int r = blockIdx.x;
   const float s = (row_keep && !row_keep[r]) ? 0.f : scale[per_row ? r : 0];
+  if (s == 1.0f) return;       // exact no-op: the row is neither read nor written
   T* xr = x + (size_t)r * ld;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) xr[v] = (T)((float)xr[v] * s);
+  int v0 = 0;
+  if (sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {       // 16-byte vectors over the aligned body
+    const int nv = V / 8;
+    uint4* x4 = reinterpret_cast<uint4*>(xr);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      uint4 u = x4[i];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); h[k] = __floats2bfloat162_rn(f.x * s, f.y * s); }
+      x4[i] = u;
+    }
+    v0 = nv * 8;
+  }
+  for (int v = v0 + threadIdx.x; v < V; v += blockDim.x) xr[v] = (T)((float)xr[v] * s);
 }
 
 }  // namespace
@@ -181,16 +197,16 @@ __global__ void scale_rows_kernel(T* __restrict__ x, long long ld, int V, const 
 extern "C" int ofa_ls_ce_fwd_bwd(void* logits, long long ld, const long long* target, const unsigned char* cmask,
                                  const float* conf, int rows_per_sample, int R, int V, long long pad_idx, float eps,
                                  int cs, int ce, int rdrop, float reg_alpha, float* loss_rows, float* nll_rows,
-                                 float* kl_rows, int dtype, void* stream) {
+                                 float* kl_rows, const float* grad_row_scale, int dtype, void* stream) {
   OFA_CHECK(R > 0 && V > 1, "ofa_ls_ce_fwd_bwd: R=%d V=%d", R, V);
   OFA_CHECK(!rdrop || (R % 2 == 0 && kl_rows), "ofa_ls_ce_fwd_bwd: R-Drop needs an even row count and kl_rows");
   OFA_CHECK(!(cmask && cs >= 0), "ofa_ls_ce_fwd_bwd: constraint mask and constraint range are exclusive");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = rdrop ? R / 2 : R;
   if (dtype == OFA_BF16)
-    OFA_CUDA(ofa_launch_pdl(ls_ce_kernel<__nv_bfloat16>, grid, kThreads, 0, st, (__nv_bfloat16*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows));
+    OFA_CUDA(ofa_launch_pdl(ls_ce_kernel<__nv_bfloat16>, grid, kThreads, 0, st, (__nv_bfloat16*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows, grad_row_scale));
   else if (dtype == OFA_F32)
-    OFA_CUDA(ofa_launch_pdl(ls_ce_kernel<float>, grid, kThreads, 0, st, (float*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows));
+    OFA_CUDA(ofa_launch_pdl(ls_ce_kernel<float>, grid, kThreads, 0, st, (float*)logits, ld, target, cmask, conf, rows_per_sample, R, V, pad_idx, eps, cs, ce, rdrop, reg_alpha, loss_rows, nll_rows, kl_rows, grad_row_scale));
   else
     return ofa_set_error("ofa_ls_ce_fwd_bwd: bad dtype %d", dtype);
   OFA_LAUNCH_CHECK("ls_ce_kernel");

@@ -1012,7 +1012,7 @@ class _LsCe(torch.autograd.Function):
         cf = conf.float().contiguous() if conf is not None else None
         cs, ce = crange if crange is not None else (-1, -1)
         call("ofa_ls_ce_fwd_bwd", _p(logits), logits.stride(1), _p(tgt), _p(cm), _p(cf), T, R, V, pad_idx, eps, cs, ce,
-             int(rdrop), reg_alpha, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st(),
+             int(rdrop), reg_alpha, _p(loss_rows), _p(nll_rows), _p(kl_rows), _p(None), _dt(logits), _st(),
              work=("byte", 2 * R * V * logits.element_size()))
         ctx.dlogits = logits.detach()
         ctx.row_keep = None
@@ -1052,12 +1052,16 @@ class _LsCeRows(torch.autograd.Function):
     d(logits) by its own upstream gradient."""
 
     @staticmethod
-    def forward(ctx, logits, target, cmask, conf, eps, pad_idx, crange):
+    def forward(ctx, logits, target, cmask, conf, eps, pad_idx, crange, expected_grad):
         _need_cuda(logits)
         B, T, V = logits.shape
         assert logits.stride(2) == 1 and logits.stride(0) == T * logits.stride(1)
         R = B * T
         tgt = target.contiguous()
+        # expected_grad [R] fp32: the caller's promise of d(total loss) / d(loss_rows); the gradient rows are written already
+        # multiplied by it, and the backward only rescales the rows whose actual upstream gradient differs (none, normally)
+        gsc = expected_grad.float().contiguous() if expected_grad is not None else None
+        ctx.gsc = gsc
         loss_rows = torch.empty(R, dtype=torch.float32, device=logits.device)
         nll_rows = torch.empty(R, dtype=torch.float32, device=logits.device)
         kl_rows = torch.zeros(1, dtype=torch.float32, device=logits.device)
@@ -1065,7 +1069,7 @@ class _LsCeRows(torch.autograd.Function):
         cf = conf.float().contiguous() if conf is not None else None
         cs, ce = crange if crange is not None else (-1, -1)
         call("ofa_ls_ce_fwd_bwd", _p(logits), logits.stride(1), _p(tgt), _p(cm), _p(cf), T, R, V, pad_idx, eps, cs, ce,
-             0, 1.0, _p(loss_rows), _p(nll_rows), _p(kl_rows), _dt(logits), _st(),
+             0, 1.0, _p(loss_rows), _p(nll_rows), _p(kl_rows), _p(gsc), _dt(logits), _st(),
              work=("byte", 2 * R * V * logits.element_size()))
         ctx.dlogits = logits.detach()
         ctx.mark_non_differentiable(nll_rows)
@@ -1076,13 +1080,17 @@ class _LsCeRows(torch.autograd.Function):
         dlogits = ctx.dlogits
         B, T, V = dlogits.shape
         scale = g_rows.float().contiguous()
+        if ctx.gsc is not None:     # exactly 1 where the promise held (same fp32 value), 0 / 0 -> rows that carry no gradient
+            scale = torch.where(ctx.gsc != 0, scale / ctx.gsc, torch.ones_like(scale))
         call("ofa_scale_rows", _p(dlogits), dlogits.stride(1), B * T, V, _p(scale), _p(None), 1, _dt(dlogits), _st())
-        return dlogits, None, None, None, None, None, None
+        return dlogits, None, None, None, None, None, None, None
 
 
-def ls_cross_entropy_rows(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None):
-    """-> (loss_rows [B*T], nll_rows [B*T]); pad rows are 0.  `logits` is overwritten with its own gradient."""
-    return _LsCeRows.apply(logits, target, cmask, conf, eps, pad_idx, crange)
+def ls_cross_entropy_rows(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None, expected_grad=None):
+    """-> (loss_rows [B*T], nll_rows [B*T]); pad rows are 0.  `logits` is overwritten with its own gradient.
+    expected_grad [B*T]: what the caller will multiply every row's loss by (1 / sample_size of its task); when the backward
+    then receives exactly that, the logits-sized gradient needs no second pass."""
+    return _LsCeRows.apply(logits, target, cmask, conf, eps, pad_idx, crange, expected_grad)
 
 
 def ls_cross_entropy(logits, target, eps, pad_idx, cmask=None, conf=None, crange=None, rdrop=False, reg_alpha=1.0,

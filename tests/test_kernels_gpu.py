@@ -96,6 +96,37 @@ def test_layernorm(dtype, rows, C, gelu):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kept", [True, False])
+def test_ls_cross_entropy_rows_expected_grad(dtype, kept):
+    """The per-row loss writes d(logits) pre-multiplied by the promised upstream gradient; whether the promise holds
+    (rows skipped in the backward) or not (rows rescaled), the gradient equals the unpromised path's."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, T, V = 6, 5, 1003
+    Vp = (V + 7) // 8 * 8
+    logits = torch.randn(B, T, V, generator=g) * 2
+    target = torch.randint(4, V, (B, T), generator=g)
+    target[2, 3:] = 1
+    w = torch.cat([torch.ones(15) / 13, torch.ones(15) / 7]).cuda()         # two "tasks" with sample sizes 13 and 7
+    up = w if kept else w * torch.linspace(0.5, 2.0, 30).cuda()             # actual upstream gradient of the rows
+
+    def run(expected):
+        buf = torch.zeros(B, T, Vp, dtype=dtype, device="cuda")
+        buf[:, :, :V] = logits.to(dtype).cuda()
+        view = buf[:, :, :V].requires_grad_()
+        loss_rows, _ = ops.ls_cross_entropy_rows(view, target.cuda(), 0.1, 1, expected_grad=expected)
+        (loss_rows * up).sum().backward()
+        return loss_rows.detach(), view.grad.float()
+
+    l0, g0 = run(None)
+    l1, g1 = run(w)
+    assert torch.equal(l0, l1)                                              # loss values are never scaled
+    tol = 1e-7 if dtype == torch.float32 else 2e-3
+    assert (g0 - g1).abs().max().item() <= tol * max(1.0, g0.abs().max().item())
+    assert g0.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,C", [(333, 768), (64, 3072)])
 def test_layernorm_fork_adds_skip_gradient(dtype, rows, C):
     """layer_norm(fork=True) hands x back for the residual branch; the branch's gradient is added inside the backward
