@@ -141,7 +141,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool keys_any_masked = __syncthreads_or(my_masked) != 0;   // kinfo visible; also reconverges warp 0
     const bool keys_all_img = bz.img_lut != nullptr && (k0 + BKV <= bz.n_img_k);
     const bool keys_all_txt = bz.tok_lut != nullptr && (k0 >= bz.k_text_off) && (bz.img_lut == nullptr || k0 >= bz.n_img_k);
-    const bool plain = !keys_any_masked && !(a.causal && k0 + col0 + 31 > iabs);
+    // padded / masked keys inside this thread's 32 columns as a bit mask: the fast paths stay usable on such tiles
+    uint32_t cm = 0;
+    if (keys_any_masked) {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) cm |= (sm.kinfo[col0 + jj] < 0 ? 1u : 0u) << jj;
+    }
+    const bool plain = !(a.causal && k0 + col0 + 31 > iabs);
     int mode = 3;
     if (plain) {
       if (q_text && keys_all_txt) mode = 1;
@@ -163,14 +169,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_wait();
       if (mode == 0) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(rr[jj]);
+        for (int jj = 0; jj < 32; ++jj) s[jj] = (cm >> jj) & 1u ? -CUDART_INF_F : __uint_as_float(rr[jj]);
       } else if (mode == 1) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(rr[jj]) + sm.tok_s[tb - jj];
+        for (int jj = 0; jj < 32; ++jj) s[jj] = (cm >> jj) & 1u ? -CUDART_INF_F : __uint_as_float(rr[jj]) + sm.tok_s[tb - jj];
       } else if (mode == 2) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
-          s[jj] = __uint_as_float(rr[jj]) + __ldg(img_lut + rowbase - (sm.kinfo[col0 + jj] & 0xffff));
+          s[jj] = (cm >> jj) & 1u ? -CUDART_INF_F
+                                  : __uint_as_float(rr[jj]) + __ldg(img_lut + rowbase - (sm.kinfo[col0 + jj] & 0xffff));
       } else {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
