@@ -221,8 +221,6 @@ def main():
             else:
                 reducer.finish()
         optim.step()        # update_freq = 1: every micro-step is followed by clip + Adam (trainer.py:863-898)
-        if e2e:
-            return float(loss)     # device -> host read of the step's result
         return loss
 
     def phases(nsteps):
@@ -246,14 +244,34 @@ def main():
                 acc[k] += ev[k].elapsed_time(ev[k + 1]) / nsteps
         return {"replay_ms": acc[0], "rank_skew_wait_ms": acc[1], "allreduce_ms": acc[2], "optimizer_ms": acc[3]}
 
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    losses_read = []
+
     def timed(nsteps, e2e):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        pending = None
         for i in range(nsteps):
-            step((host if e2e else resident)[i % n_batches], e2e)
+            loss = step((host if e2e else resident)[i % n_batches], e2e)
+            if e2e and graphed is not None and i + 1 < nsteps:
+                graphed.prefetch(host[(i + 1) % n_batches])     # next step's H2D copy runs under this step's compute
+            if e2e:
+                # device -> host read of every step's result, one step behind (asynchronous logging, as a trainer does): the
+                # copy into pinned memory is queued behind the step, the host reads step i-1's value while step i runs
+                buf = loss_host[i % 2]
+                buf.copy_(loss.detach().reshape(1).float(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    losses_read.append(float(pending[0][0]))
+                pending = (buf, ev)
+        if pending is not None:
+            pending[1].synchronize()
+            losses_read.append(float(pending[0][0]))
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -351,7 +369,10 @@ def main():
                    "launch": "CUDA graph replay" if a.graph else "eager"},
         "clocks": clocks, "gpu_launches": launches, "phases": ph,
         "e2e": {"value": samples * a.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps,
+                "readback": "loss of every step copied to pinned memory and read by the host one step behind",
+                "h2d": "every step's batches copied from pinned host memory inside the timed region; the copy of step i+1 is issued on a copy stream while step i computes (the first step's copy is exposed)",
+                "last_loss": losses_read[-1] if losses_read else None},
         "roofline": roof, "cpu_baseline": cpu, "caption_beam5": caption}))
     if world > 1:
         dist.destroy_process_group()

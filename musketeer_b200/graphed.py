@@ -69,6 +69,26 @@ class GraphedTrainStep:
             loss, ss = self._run(static)
         return {"graph": graph, "static": static, "loss": loss.detach(), "sample_size": ss}
 
+    def prefetch(self, samples):
+        """Start the host -> device copy of the NEXT micro-step's batches on a copy stream, into a staging set next to the
+        graph's static inputs, while the current step computes (the data loader's job in a trainer).  The following
+        __call__ with the same `samples` object then only does device-to-device copies.  No-op before the first capture."""
+        e = self.cache.get(_signature(samples))
+        if e is None:
+            return
+        if "staging" not in e:
+            e["staging"] = map_tensors(e["static"], lambda t: torch.empty_like(t))
+            e["copy_stream"] = torch.cuda.Stream()
+            e["staged_ev"] = torch.cuda.Event()
+            e["consumed_ev"] = None
+        cs = e["copy_stream"]
+        if e["consumed_ev"] is not None:
+            cs.wait_event(e["consumed_ev"])          # the previous step's device-to-device copy has drained the staging set
+        with torch.cuda.stream(cs):
+            _copy_into(e["staging"], samples)
+            e["staged_ev"].record(cs)
+        e["staged_for"] = id(samples)
+
     def __call__(self, samples):
         """samples: host (ideally pinned) or device tensors in the reference `sample` layout.  Returns (loss tensor, sample_size);
         parameter .grad fields hold the gradients of this micro-step after the call."""
@@ -76,6 +96,13 @@ class GraphedTrainStep:
         e = self.cache.get(sig)
         if e is None:
             e = self.cache[sig] = self._capture(samples)
+        elif e.get("staged_for") == id(samples):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(e["staged_ev"])
+            _copy_into(e["static"], e["staging"])
+            e["consumed_ev"] = torch.cuda.Event()
+            e["consumed_ev"].record(cur)
+            e["staged_for"] = None
         else:
             _copy_into(e["static"], samples)
         e["graph"].replay()
