@@ -42,6 +42,12 @@ def test_sass_is_blackwell_native(lib_path):
     assert "UTMAREDG" in sass     # TMA reduce-add (fp32 gradient arenas, attention dQ)
     assert "LDTM" in sass         # tcgen05.ld
     assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+    assert "UBLKCP" in sass       # 1-D bulk copies (the LayerNorm backward's shared-memory row ring)
+    assert "FFMA2" in sass        # packed fp32x2 arithmetic (wide-row LayerNorm / GELU forward)
+    # relative-position table gradients of the attention backward: native int32 shared atomics, no float CAS loops
+    bwd = sass[sass.index("attn_bwd_tc_kernel"):]
+    bwd = bwd[:bwd.index("Function :", 10)] if "Function :" in bwd[10:] else bwd
+    assert "ATOMS.ADD" in bwd and "ATOMS.CAST" not in bwd
 
 
 @pytest.mark.parametrize("arch", ["ofa_tiny", "ofa_base"])
