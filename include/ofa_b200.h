@@ -219,6 +219,9 @@ int ofa_attn_fwd_simt(const OfaAttnArgs* args, int dtype, void* stream);
 int ofa_attn_bwd_simt(const OfaAttnArgs* args, const OfaAttnGrads* grads, int dtype, void* stream);
 /* bf16, TMA + tcgen05/TMEM flash attention */
 int ofa_attn_fwd_tc(const OfaAttnArgs* args, void* stream);
+/* A/B switch: 1 = warp-specialised forward (TMA producer warp, tcgen05 issuer warp, two softmax warpgroups; default),
+ * 0 = the single-role kernel of round 1; returns the previous setting */
+int ofa_attn_set_fwd_ws(int enabled);
 /* backward: fills grads->delta, dq/dpq/dk/dpk/dv and accumulates dtok_lut / dimg_lut; dq_acc = B*T*H*128 floats scratch */
 int ofa_attn_bwd_tc(const OfaAttnArgs* args, const OfaAttnGrads* grads, float* dq_acc, void* stream);
 

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofa_b200.so")
+LIB_PATH = os.environ.get("OFA_B200_LIB") or os.path.join(_HERE, "libofa_b200.so")    # override: kernel experiments
 
 _lib = None
 
@@ -84,6 +84,7 @@ SIGNATURES = {
     "ofa_attn_fwd_simt": [C.POINTER(OfaAttnArgs), c_i, c_p],
     "ofa_attn_bwd_simt": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_i, c_p],
     "ofa_attn_fwd_tc": [C.POINTER(OfaAttnArgs), c_p],
+    "ofa_attn_set_fwd_ws": [c_i],
     "ofa_attn_bwd_tc": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_p, c_p],
 }
 
@@ -118,6 +119,8 @@ def load(path=None):
         lib.ofa_batchnorm_set_tuning(int(w), int(u))
     if os.environ.get("OFA_LN_STAGED") is not None:
         lib.ofa_layernorm_set_staged(int(os.environ["OFA_LN_STAGED"]))
+    if os.environ.get("OFA_ATTN_FWD_WS") is not None:   # A/B switch: warp-specialised attention forward (default on)
+        lib.ofa_attn_set_fwd_ws(int(os.environ["OFA_ATTN_FWD_WS"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch
         lib.ofa_set_pdl(int(os.environ["OFA_PDL"]))
     _lib = lib

@@ -13,6 +13,8 @@ def construct_rdrop_sample(x):
     if isinstance(x, dict):
         return {k: construct_rdrop_sample(v) for k, v in x.items()}
     if isinstance(x, torch.Tensor):
+        if x.dim() == 0:            # a collater count living on the device (CUDA-graph path): doubled like the ints below
+            return x * 2
         return x.repeat(2, *([1] * (x.dim() - 1)))
     if isinstance(x, bool) or x is None:
         return x
@@ -73,7 +75,9 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
         nis = [sample[i]["net_input"] for i in idx]
         merge = (self.batch_task_encoders and float(getattr(enc, "dropout_p", 0.0)) == 0.0 and
                  all(ni.get("sample_patch_num") is None and ni.get("patch_images_2") is None for ni in nis) and
-                 not (self.sample_patch_num > 0 and 0 in idx))
+                 # the recursion below sets sample_patch_num on every task but the LAST of the list (:175-178): any image task
+                 # that would receive it keeps its own, patch-sampling, encoder pass
+                 not (self.sample_patch_num > 0 and any(i < len(sample) - 1 for i in idx)))
         if merge:
             # ONE encoder pass for all image tasks: source tokens right-padded to the longest prompt (padded keys are masked
             # and padded rows zeroed, so every real position computes what its own task's pass computes), then each task

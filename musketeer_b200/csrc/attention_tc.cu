@@ -271,6 +271,434 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// forward, warp-specialised (the default): one CTA = one (batch, head) and TWO 128-row query tiles sweeping 64-key tiles.
+//   warps 0-7 / 8-15 : softmax of query tile 0 / 1 -- two threads per query row (TMEM lane), 32 scores each per key tile in
+//                      registers (warp w: columns 0-31, warp w+4: columns 32-63 of the same rows; the row maximum is
+//                      exchanged through shared memory behind a 256-thread named barrier), online softmax, P (bf16) to
+//                      swizzled shared memory, O folded from the per-tile P.V partial (32 output columns per thread)
+//   warp 16          : TMA producer -- Q' once, K'/V through a 3-stage ring; starts before the LUT staging of the others
+//   warps 17, 18     : tcgen05 issuers, one per query tile -- S(j+1) is issued BEFORE P.V(j), so the tensor pipe computes the
+//                      next scores while the softmax warps work on the current ones; every hand-over is an mbarrier
+//                      (tcgen05.commit -> s_full / o_full / kv_empty; softmax arrivals -> s_free / p_full), no __syncthreads
+//                      in the main loop.
+// The tensor cores read an operand that lives in shared memory at ~64 B/clk (measured: a 128x64x16 MMA with both operands
+// in shared memory takes ~100 cycles instead of 32, ncu r02_attn_fwd_ws_v0), so with kTS both A operands are moved to tensor
+// memory: Q' is copied there once per CTA (bf16 pairs, 64 columns), P is written there by the softmax threads (tcgen05.st)
+// instead of to swizzled shared memory; only K' and V are then read from shared memory.  The per-head image LUT (27.6 KB), the token LUT slice
+// of the 256 query rows and the per-key metadata of ALL keys are staged in shared memory once per CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+// -DOFA_WS_DEBUG: clock64() phase accounting of one softmax warp and of the issuer thread of one CTA (tools/attn_ws_phases.py
+// reads it through ofa_attn_ws_debug_read).  Not compiled into the shipped library.
+#ifdef OFA_WS_DEBUG
+__device__ long long g_ws_dbg[64];
+#define WSD_DECL(cond) const bool wsd = (cond); long long wsd_last = clock64();
+#define WSD(i) if (wsd) { const long long now_ = clock64(); g_ws_dbg[i] += now_ - wsd_last; wsd_last = now_; }
+#else
+#define WSD_DECL(cond)
+#define WSD(i)
+#endif
+constexpr int kImgLutMax = 83 * 83 + 3 + 1;
+constexpr int WS_QT = 2, WS_ST = 3, WS_SOFTMAX = 512, WS_THREADS = WS_SOFTMAX + 32 * (1 + WS_QT), WS_MAXK = 2048;
+// TMEM columns per query tile: S [0,64) | O partial [64,128) | (kTS) Q' as bf16 A operand [128,192) | P as bf16 A operand [192,224)
+constexpr int WS_TILE_COLS = 256, WS_COL_S = 0, WS_COL_O = 64, WS_COL_Q = 128, WS_COL_P = 192;
+constexpr int WS_TOK = 1024 + WS_QT * BQ;
+
+struct WsSmem {
+  uint8_t q[WS_QT][2][BQ * 128];    // [tile][q | pos_q][128 rows][128 B]
+  uint8_t k[WS_ST][2][BKV * 128];   // [stage][k | pos_k][64 keys][128 B]
+  uint8_t v[WS_ST][BKV * 128];      // [stage][64 keys][64 x bf16]
+  uint8_t p[WS_QT][BQ * 128];       // [tile][128 rows][64 keys x bf16]
+  float img_s[kImgLutMax];          // image rel-pos LUT of this head
+  float tok_s[WS_TOK];              // token rel-pos LUT slice: index (row in CTA) + S_t - 1 - j_t
+  alignas(16) int koff[WS_MAXK];    // image keys: 4 * (kr*(2*ibs-1)+kc) (a byte offset into img_s), else 0
+  uint32_t kmask[WS_MAXK / 32];     // bit set = key masked (padding, beyond S)
+  float rowmax[WS_QT][2][2][BQ];    // [tile][iteration parity][column half][row]: row-maximum exchange of the two half-row threads
+  float rowsum[WS_QT][2][BQ];       // final exchange of the partial row sums
+  uint64_t q_full, k_full[WS_ST], kv_empty[WS_ST], s_full[WS_QT], s_free[WS_QT], p_full[WS_QT], o_full[WS_QT], qt_full[WS_QT];
+  uint32_t tmem_addr;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool kTS>   // kTS: the A operands of both GEMMs (Q', P) live in tensor memory instead of shared memory
+__global__ void __launch_bounds__(WS_THREADS, 1)
+attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmPQ,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmPK,
+                   const __grid_constant__ CUtensorMap tmV, AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+#ifdef OFA_WS_DEBUG
+  if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5 && t == 0) g_ws_dbg[39] += clock64();
+#endif
+  constexpr int kProducer = WS_SOFTMAX / 32, kIssuer = kProducer + 1;
+  const int q0 = blockIdx.x * (WS_QT * BQ), h = blockIdx.y, b = blockIdx.z;
+  const AttnBias& bz = a.bias;
+  const int ntiles_all = (a.S + BKV - 1) / BKV;
+  int nt[WS_QT];
+#pragma unroll
+  for (int tile = 0; tile < WS_QT; ++tile) {
+    const int q0t = q0 + tile * BQ;
+    int n = q0t < a.T ? ntiles_all : 0;
+    if (a.causal && n) n = min(n, (q0t + BQ - 1 + a.q_pos_off) / BKV + 1);   // key tiles above the diagonal are skipped
+    nt[tile] = n;
+  }
+  const int nmax = max(nt[0], nt[1]);
+  const int w83 = 2 * bz.ibs - 1;
+#ifdef OFA_WS_DEBUG
+  const bool wsd_cta = blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5;
+#endif
+
+  if (warp == kProducer) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmPQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmPK);
+      tma_prefetch_desc(&tmV);
+      mbar_init(&sm.q_full, 1);
+      for (int s = 0; s < WS_ST; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.kv_empty[s], (nt[0] > 0) + (nt[1] > 0)); }
+      for (int q = 0; q < WS_QT; ++q) {
+        mbar_init(&sm.s_full[q], 1); mbar_init(&sm.s_free[q], 2 * BQ); mbar_init(&sm.p_full[q], 2 * BQ);
+        mbar_init(&sm.o_full[q], 1); mbar_init(&sm.qt_full[q], 2 * BQ);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<WS_QT * WS_TILE_COLS>(&sm.tmem_addr);
+  }
+  pdl_sync();   // everything above is on-chip set-up; what follows reads the predecessor's output
+  if (warp == kProducer && lane == 0) {
+    // Q' and the first K'/V stages are requested before the LUT staging below, so their latency runs under it
+    uint32_t qbytes = 0;
+#pragma unroll
+    for (int tile = 0; tile < WS_QT; ++tile) qbytes += nt[tile] ? 2 * BQ * 128 : 0;
+    mbar_expect_tx(&sm.q_full, qbytes);
+#pragma unroll
+    for (int tile = 0; tile < WS_QT; ++tile)
+      if (nt[tile]) {
+        tma_load_4d(sm.q[tile][0], &tmQ, &sm.q_full, 0, h, q0 + tile * BQ, b);
+        tma_load_4d(sm.q[tile][1], &tmPQ, &sm.q_full, 0, h, q0 + tile * BQ, b);
+      }
+    for (int j = 0; j < min(nmax, WS_ST); ++j) {
+      mbar_expect_tx(&sm.k_full[j], 3 * BKV * 128);
+      tma_load_4d(sm.k[j][0], &tmK, &sm.k_full[j], 0, h, j * BKV, b);
+      tma_load_4d(sm.k[j][1], &tmPK, &sm.k_full[j], 0, h, j * BKV, b);
+      tma_load_4d(sm.v[j], &tmV, &sm.k_full[j], 0, h, j * BKV, b);
+    }
+  }
+  const int S_t = a.S - bz.k_text_off;
+  {
+    const int Spad = ntiles_all * BKV;
+    for (int j0 = 0; j0 < Spad; j0 += WS_THREADS) {
+      if (j0 + warp * 32 < Spad) {   // warp-uniform
+        const int j = j0 + t;
+        const bool masked = j >= a.S || (a.kpm && a.kpm[(size_t)b * a.S + j]);
+        int off = 0;
+        if (bz.img_lut && j < bz.n_img_k) {
+          const int pid = bz.k_pid[(size_t)b * bz.n_img_k + j] - 1;
+          off = 4 * ((pid / bz.ibs) * w83 + (pid % bz.ibs));
+        }
+        sm.koff[j] = off;
+        const uint32_t bal = __ballot_sync(0xffffffffu, masked);
+        if (lane == 0) sm.kmask[j >> 5] = bal;
+      }
+    }
+    if (bz.tok_lut) {
+      const int i_t0 = q0 + a.q_pos_off - bz.q_text_off;
+      const float* lut = bz.tok_lut + (size_t)h * (2 * bz.tok_max - 1);
+      for (int e = t; e < WS_TOK; e += WS_THREADS) {
+        const int rel = i_t0 + e - (S_t - 1) + bz.tok_max - 1;
+        sm.tok_s[e] = (rel >= 0 && rel < 2 * bz.tok_max - 1) ? lut[rel] : 0.f;
+      }
+    }
+    if (bz.img_lut) {
+      const float4* lut4 = reinterpret_cast<const float4*>(bz.img_lut + (size_t)h * bz.n_img_rel);
+      if ((((size_t)h * bz.n_img_rel) & 3) == 0 && (reinterpret_cast<uintptr_t>(bz.img_lut) & 15) == 0) {
+        for (int e = t; e < (bz.n_img_rel >> 2); e += WS_THREADS) reinterpret_cast<float4*>(sm.img_s)[e] = lut4[e];
+        for (int e = (bz.n_img_rel & ~3) + t; e < bz.n_img_rel; e += WS_THREADS)
+          sm.img_s[e] = bz.img_lut[(size_t)h * bz.n_img_rel + e];
+      } else {
+        for (int e = t; e < bz.n_img_rel; e += WS_THREADS) sm.img_s[e] = bz.img_lut[(size_t)h * bz.n_img_rel + e];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = sm.tmem_addr;
+#ifdef OFA_WS_DEBUG
+  if (wsd_cta && t == 0) g_ws_dbg[40] += clock64();      // (start stamps are subtracted on the host side: single CTA)
+#endif
+
+  if (warp == kProducer) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      for (int j = WS_ST; j < nmax; ++j) {
+        const int st = j % WS_ST;
+        mbar_wait(&sm.kv_empty[st], ((j / WS_ST) - 1) & 1);
+        mbar_expect_tx(&sm.k_full[st], 3 * BKV * 128);
+        tma_load_4d(sm.k[st][0], &tmK, &sm.k_full[st], 0, h, j * BKV, b);
+        tma_load_4d(sm.k[st][1], &tmPK, &sm.k_full[st], 0, h, j * BKV, b);
+        tma_load_4d(sm.v[st], &tmV, &sm.k_full[st], 0, h, j * BKV, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kIssuer) {
+    // ---------------------------------------------------------------------------------------------- tcgen05 issuers
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);
+      auto issue_s = [&](int tile, int st) {
+        const uint32_t tb = tm + tile * WS_TILE_COLS;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t db = umma_smem_desc(smem_u32(sm.k[st][kb]) + ks * 32, 16, 1024);
+            if (kTS) umma_f16_ts(tb + WS_COL_S, tb + WS_COL_Q + kb * 32 + ks * 8, db, idesc_s, (kb | ks) != 0);
+            else umma_f16(tb + WS_COL_S, umma_smem_desc(smem_u32(sm.q[tile][kb]) + ks * 32, 16, 1024), db, idesc_s, (kb | ks) != 0);
+          }
+        umma_commit(&sm.s_full[tile]);
+      };
+      auto issue_pv = [&](int tile, int st) {
+        const uint32_t tb = tm + tile * WS_TILE_COLS;
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint64_t db = umma_smem_desc(smem_u32(sm.v[st]) + ks * 2048, 1024, 1024);
+          if (kTS) umma_f16_ts(tb + WS_COL_O, tb + WS_COL_P + ks * 8, db, idesc_o, ks != 0);
+          else umma_f16(tb + WS_COL_O, umma_smem_desc(smem_u32(sm.p[tile]) + ks * 32, 16, 1024), db, idesc_o, ks != 0);
+        }
+        umma_commit(&sm.o_full[tile]);
+      };
+      // one issuer thread per query tile (two warps): a tcgen05.mma costs its issuing thread ~80-110 cycles whatever its
+      // size (phase timing, tools/attn_ws_phases.py), so the two tiles' instruction streams are issued concurrently
+      const int tile = warp - kIssuer;
+      const int n = nt[tile];
+      WSD_DECL(wsd_cta && tile == 0)
+      if (n > 0) {
+        if (kTS) mbar_wait(&sm.qt_full[tile], 0);      // Q' of the tile has been copied into tensor memory
+        else mbar_wait(&sm.q_full, 0);
+        mbar_wait(&sm.k_full[0], 0);
+        tc_fence_after();
+        WSD(20)
+        issue_s(tile, 0);
+        WSD(21)
+      }
+      for (int j = 0; n > 0 && j < nmax; ++j) {
+        const int st = j % WS_ST;
+        // a tile with fewer key tiles than its neighbour (causal) keeps releasing the stages, in step with the producer
+        if (j >= n) mbar_wait(&sm.k_full[st], (j / WS_ST) & 1);
+        if (j + 1 < n) {
+          const int st1 = (j + 1) % WS_ST;
+          mbar_wait(&sm.k_full[st1], ((j + 1) / WS_ST) & 1);
+          WSD(22)
+          mbar_wait(&sm.s_free[tile], j & 1);      // the softmax warps hold S(j) in registers
+          tc_fence_after();
+          WSD(23)
+          issue_s(tile, st1);
+          WSD(24)
+        }
+        if (j < n) {
+          mbar_wait(&sm.p_full[tile], j & 1);
+          tc_fence_after();
+          WSD(27)
+          issue_pv(tile, st);
+          WSD(28)
+        }
+        umma_commit(&sm.kv_empty[st]);             // (both issuers: the stage is free when both tiles' MMAs have retired)
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- softmax warps (warp < kProducer)
+    const int tile = warp >> 3;
+    const int hf = (warp >> 2) & 1;         // column half of the key tile: 32 scores / 32 output columns per thread
+    const int n = nt[tile];
+    const int r = (warp & 3) * 32 + lane;   // row inside the tile = TMEM lane
+    const int rc = tile * BQ + r;           // row inside the CTA (token-LUT indexing)
+    const int i = q0 + rc, iabs = i + a.q_pos_off;
+    const bool row_ok = i < a.T;
+    const bool q_text = bz.tok_lut && iabs >= bz.q_text_off;
+    const bool q_img = bz.img_lut && iabs < bz.n_img_q && row_ok;
+    const char* img_row = reinterpret_cast<const char*>(sm.img_s);
+    if (q_img) {
+      const int pid = bz.q_pid[(size_t)b * bz.n_img_q + iabs] - 1;
+      img_row += 4 * ((pid / bz.ibs + bz.ibs - 1) * w83 + (pid % bz.ibs + bz.ibs - 1));
+    }
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tmem_t = tm + lane_off + tile * WS_TILE_COLS;
+    const uint32_t tmem_s = tmem_t + WS_COL_S + hf * 32, tmem_o = tmem_t + WS_COL_O + hf * 32, tmem_p = tmem_t + WS_COL_P + hf * 16;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m = -CUDART_INF_F, l = 0.f, alpha_prev = 1.f;
+    float o[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    uint8_t* prow = sm.p[tile] + r * 128;
+    const int sw = r & 7;
+    if (kTS && n > 0) {
+      // Q' -> tensor memory, once: this thread moves the 64 bf16 of its row's q (hf = 0) or pos_q (hf = 1) block (8 swizzled
+      // 16-byte chunks of the TMA tile) into 32 columns of the A-operand region
+      mbar_wait(&sm.q_full, 0);
+      uint32_t qa[32];
+      const uint8_t* qrow = sm.q[tile][hf] + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(qrow + ((c ^ sw) << 4));
+        qa[4 * c] = u.x; qa[4 * c + 1] = u.y; qa[4 * c + 2] = u.z; qa[4 * c + 3] = u.w;
+      }
+      tmem_st32(tmem_t + WS_COL_Q + hf * 32, qa);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sm.qt_full[tile]);
+    }
+    // bias class of a 32-column key block: fully image keys -> image LUT gather (image query rows) or no bias; fully text
+    // keys -> token LUT (text query rows) or no bias; blocks that straddle the image / text boundary and blocks cut by the
+    // causal diagonal take the generic per-element path (mode 3)
+    const bool no_bias = !bz.tok_lut && !bz.img_lut;
+    const int blk_img_end = no_bias ? (1 << 30) : (bz.img_lut ? bz.n_img_k / 32 : 0);
+    const int blk_txt_beg = bz.tok_lut ? (max(bz.k_text_off, bz.img_lut ? bz.n_img_k : 0) + 31) / 32 : (1 << 30);
+    const int mode_img = (q_img && !no_bias) ? 2 : 0, mode_txt = q_text ? 1 : 0;
+    auto fold = [&](float al) {             // o = o * al + (P.V partial of the previous key tile)
+      uint32_t ro[32];
+      tmem_ld32(tmem_o, ro);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) o[jj] = fmaf(o[jj], al, __uint_as_float(ro[jj]));
+    };
+    WSD_DECL(wsd_cta && warp == 0 && lane == 0)
+    for (int j = 0; j < n; ++j) {
+      const int kc0 = j * BKV + hf * 32;    // first key column of this thread
+      float s[32];
+      WSD(0)
+      mbar_wait(&sm.s_full[tile], j & 1);
+      tc_fence_after();
+      WSD(1)
+      {
+        uint32_t rr[32];
+        tmem_ld32(tmem_s, rr);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&sm.s_free[tile]);      // S(j) is in registers: the issuer may overwrite it with S(j+1)
+        WSD(2)
+        const uint32_t cm = sm.kmask[kc0 >> 5];
+        const int blk = 2 * j + hf;         // 32-column block index on the key axis
+        int mode = blk < blk_img_end ? mode_img : (blk >= blk_txt_beg ? mode_txt : 3);
+        if (a.causal && kc0 + 31 > iabs) mode = 3;
+        const int tb = rc + S_t - 1 - (kc0 - bz.k_text_off);   // tok_s index of column kc0; column jj -> tb - jj
+        if (mode == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(rr[jj]);
+        } else if (mode == 1) {
+          const float* ts = sm.tok_s + tb;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(rr[jj]) + ts[-jj];
+        } else if (mode == 2) {
+          const int4* ko = reinterpret_cast<const int4*>(sm.koff + kc0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int4 kk = ko[j4];
+            s[j4 * 4 + 0] = __uint_as_float(rr[j4 * 4 + 0]) + *reinterpret_cast<const float*>(img_row - kk.x);
+            s[j4 * 4 + 1] = __uint_as_float(rr[j4 * 4 + 1]) + *reinterpret_cast<const float*>(img_row - kk.y);
+            s[j4 * 4 + 2] = __uint_as_float(rr[j4 * 4 + 2]) + *reinterpret_cast<const float*>(img_row - kk.z);
+            s[j4 * 4 + 3] = __uint_as_float(rr[j4 * 4 + 3]) + *reinterpret_cast<const float*>(img_row - kk.w);
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int jg = kc0 + jj;
+            float x = __uint_as_float(rr[jj]);
+            if (q_text && jg >= bz.k_text_off) x += sm.tok_s[tb - jj];
+            if (q_img && jg < bz.n_img_k) x += *reinterpret_cast<const float*>(img_row - sm.koff[jg]);
+            if (a.causal && jg > iabs) x = -CUDART_INF_F;
+            s[jj] = x;
+          }
+        }
+        if (cm != 0) {                      // padded keys in these 32 columns (warp-uniform: the mask is per key)
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj)
+            if ((cm >> jj) & 1u) s[jj] = -CUDART_INF_F;
+        }
+      }
+      float mx4[4] = {s[0], s[1], s[2], s[3]};   // four independent chains: the row maximum is on the critical path
+#pragma unroll
+      for (int jj = 4; jj < 32; ++jj) mx4[jj & 3] = fmaxf(mx4[jj & 3], s[jj]);
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      sm.rowmax[tile][j & 1][hf][r] = mx;
+      WSD(3)
+      named_bar_sync(1 + tile, 2 * BQ);
+      mx = fmaxf(mx, sm.rowmax[tile][j & 1][hf ^ 1][r]);
+      WSD(4)
+      const float mn = fmaxf(m, mx);
+      const float mu = (mn == -CUDART_INF_F) ? 0.f : mn;
+      const float alpha = ex2((m - mu) * kLog2e);
+      m = mn;
+      const float mneg = -mu * kLog2e;
+      uint32_t pk[16];
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float p0 = ex2(fmaf(s[2 * jj], kLog2e, mneg)), p1 = ex2(fmaf(s[2 * jj + 1], kLog2e, mneg));
+        rs4[jj & 3] += p0 + p1;
+        pk[jj] = pack_bf16(p0, p1);
+      }
+      l = l * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      WSD(5)
+      if (j > 0) {                          // P.V(j-1) has retired: its partial is ready and the P buffer is free
+        mbar_wait(&sm.o_full[tile], (j - 1) & 1);
+        tc_fence_after();
+        WSD(6)
+        fold(alpha_prev);
+        WSD(7)
+      }
+      alpha_prev = alpha;
+      if (kTS) {
+        tmem_st16(tmem_p, pk);
+        tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async();
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.p_full[tile]);
+      WSD(8)
+    }
+#ifdef OFA_WS_DEBUG
+    if (wsd) g_ws_dbg[41] += clock64();
+#endif
+    if (n > 0) {
+      mbar_wait(&sm.o_full[tile], (n - 1) & 1);
+      tc_fence_after();
+      fold(alpha_prev);
+      // total row sum = the two half-row partial sums (same running maximum on both sides)
+      sm.rowsum[tile][hf][r] = l;
+      named_bar_sync(1 + tile, 2 * BQ);
+      l += sm.rowsum[tile][hf ^ 1][r];
+    }
+    if (row_ok) {
+      const float inv = (l > 0.f ? 1.f / l : 0.f) * (a.head_scale ? a.head_scale[h] : 1.f);
+      __nv_bfloat16* O = (__nv_bfloat16*)a.o + (size_t)b * a.bso + (size_t)i * a.ldo + h * HD + hf * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        reinterpret_cast<uint4*>(O)[c] =
+            make_uint4(pack_bf16(o[8 * c] * inv, o[8 * c + 1] * inv), pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
+                       pack_bf16(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_bf16(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+      if (hf == 0) a.lse[((size_t)b * a.H + h) * a.T + i] = (m == -CUDART_INF_F ? 0.f : m) + logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+#ifdef OFA_WS_DEBUG
+  if (wsd_cta && t == 0) g_ws_dbg[42] += clock64();
+#endif
+  if (warp == kProducer) {
+    tc_fence_after();
+    tmem_dealloc<WS_QT * WS_TILE_COLS>(tm);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------------
 // One CTA = one (batch, head, 128-key tile); K', V stay in shared memory, dK' and dV accumulate in TMEM over the sweep of
@@ -309,6 +737,8 @@ struct BwdSmem {
   int hist_img[kImgHistMax + 1];
   alignas(16) uint32_t wmax[16];   // per-warp max |dS| of the current tile (float bits)
   int kinfo[BK2];            // bit31 masked | bit30 image key | [0,16) kr*(2*ibs-1)+kc
+  float img_s[kImgHistMax + 1];   // image rel-pos LUT of this head (the per-element gather went to L1 / L2 before: long-scoreboard
+                                  // stalls were the top stall reason of the round-1 capture)
   uint64_t bar_kv, bar_q, bar_sp, bar_dq, bar_qf;
   uint32_t tmem_addr;
 };
@@ -356,6 +786,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     sm.tok_s[e] = lv;
   }
   for (int e = t; e < kImgHistMax + 1; e += kBwdThreads) sm.hist_img[e] = 0;
+  if (bz.img_lut) {
+    const float* lut = bz.img_lut + (size_t)h * bz.n_img_rel;
+    for (int e = t; e < bz.n_img_rel; e += kBwdThreads) sm.img_s[e] = lut[e];
+  }
   int my_masked = 0;
   if (t < BK2) {
     const int j = k0 + t;
@@ -392,7 +826,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, qt0 * BQ, b);
   }
   const float cs = a.head_scale ? a.head_scale[h] : 1.f;
-  const float* img_lut = bz.img_lut ? bz.img_lut + (size_t)h * bz.n_img_rel : nullptr;
+  const float* img_lut = sm.img_s;
   constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);    // S, dP
   constexpr uint32_t id_dv = umma_idesc_bf16(128, 64, 1, 1);    // dV  = P^T dO
   constexpr uint32_t id_dk = umma_idesc_bf16(128, 128, 1, 1);   // dK' = dS^T Q'
@@ -492,7 +926,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const int idx = rowbase - (sm.kinfo[col0 + jj] & 0xffff);
-          float p = __expf(__uint_as_float(rs[jj]) + __ldg(img_lut + idx) - lse);
+          float p = __expf(__uint_as_float(rs[jj]) + img_lut[idx] - lse);
           if (cm & (1u << jj)) p = 0.f;
           const float ds = p * fmaf(__uint_as_float(rp[jj]), cs, -delta);
           pv[jj] = p;
@@ -509,7 +943,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (tok_el) x += sm.tok_s[tu - jj];
           if (q_img && (info & 0x40000000)) {
             img_idx = rowbase - (info & 0xffff);
-            x += __ldg(img_lut + img_idx);
+            x += img_lut[img_idx];
           }
           const bool masked = info < 0 || (a.causal && j > iabs) || !row_ok;
           const float p = masked ? 0.f : __expf(x - lse);
@@ -764,6 +1198,22 @@ int make_qkv_tmap(CUtensorMap* tm, const void* p, int L, int H, int B, long long
 
 }  // namespace
 
+static int g_attn_fwd_ws = 1;
+/* A/B switch: 1 = warp-specialised forward with the A operands in tensor memory (default), 2 = warp-specialised with every
+ * operand in shared memory, 0 = the single-role round-1 kernel; returns the previous setting */
+extern "C" int ofa_attn_set_fwd_ws(int enabled) {
+  const int old = g_attn_fwd_ws;
+  g_attn_fwd_ws = enabled;
+  return old;
+}
+#ifdef OFA_WS_DEBUG
+extern "C" int ofa_attn_ws_debug_read(long long* out) {
+  cudaMemcpyFromSymbol(out, g_ws_dbg, sizeof(long long) * 64);
+  long long z[64] = {0};
+  cudaMemcpyToSymbol(g_ws_dbg, z, sizeof(z));
+  return 0;
+}
+#endif
 #ifdef OFA_ATTN_DEBUG
 extern "C" int ofa_attn_debug_read(long long* out) {
   cudaMemcpyFromSymbol(out, g_attn_dbg, sizeof(long long) * 128);
@@ -785,6 +1235,22 @@ extern "C" int ofa_attn_fwd_tc(const AttnArgs* a, void* stream) {
   if (int e = make_qkv_tmap(&tk, a->k, a->S, a->H, a->B, a->ldk, a->bsk, BKV)) return e;
   if (int e = make_qkv_tmap(&tpk, a->pk, a->S, a->H, a->B, a->ldpk, a->bspk, BKV)) return e;
   if (int e = make_qkv_tmap(&tv, a->v, a->S, a->H, a->B, a->ldv, a->bsv, BKV)) return e;
+  if (g_attn_fwd_ws && a->S <= WS_MAXK && a->bias.n_img_rel <= kImgLutMax && a->S - a->bias.k_text_off <= 1024) {
+    static bool configured_ws = false;
+    const int smem_ws = (int)sizeof(WsSmem) + 1024;
+    if (!configured_ws) {
+      OFA_CUDA(cudaFuncSetAttribute(attn_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ws));
+      OFA_CUDA(cudaFuncSetAttribute(attn_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ws));
+      configured_ws = true;
+    }
+    dim3 grid_ws((a->T + WS_QT * BQ - 1) / (WS_QT * BQ), a->H, a->B);
+    if (g_attn_fwd_ws == 2)
+      OFA_CUDA(ofa_launch_pdl(attn_fwd_ws_kernel<false>, grid_ws, WS_THREADS, smem_ws, (cudaStream_t)stream, tq, tpq, tk, tpk, tv, *a));
+    else
+      OFA_CUDA(ofa_launch_pdl(attn_fwd_ws_kernel<true>, grid_ws, WS_THREADS, smem_ws, (cudaStream_t)stream, tq, tpq, tk, tpk, tv, *a));
+    OFA_LAUNCH_CHECK("attn_fwd_ws_kernel");
+    return 0;
+  }
   static bool configured = false;
   const int smem = (int)sizeof(TcSmem) + 1024;  // 1 KB slack for the 1024B align-up
   if (!configured) {

@@ -49,8 +49,8 @@ class GradReducer:
 
     def prepare(self):
         """Call before the backward whose gradients must be reduced.  (Hook-driven overlap needs every accumulation to
-        go through autograd: set musketeer_b200.ops.FUSE_GRAD_ACCUM = False for eager multi-task steps; the CUDA-graph
-        path uses reduce_all() after the replay and keeps the fusion.)"""
+        go through autograd, i.e. the backward must run OUTSIDE `ops.grad_accumulation(model)`; the CUDA-graph path
+        keeps the fused accumulation and uses reduce_flat() after the replay.)"""
         self._pending = [len(b) for b in self.buckets]
         self._flat = [None] * len(self.buckets)
         self._works = []
@@ -114,8 +114,10 @@ class GradReducer:
         lo_hi = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in flats]
         # gradients that autograd produced outside the arenas (library convolutions, c_attn, relative-position tables, ...):
         # a few dozen small tensors, reduced through one temporary flat buffer
+        # every rank must issue identically sized collectives: ALL parameters outside the arenas take part, those without a
+        # gradient on this rank (a parameter unused by this rank's batch) as zeros
         rest = [p for p in self.params
-                if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in lo_hi)]
+                if p.grad is None or not any(lo <= p.grad.data_ptr() < hi for lo, hi in lo_hi)]
         avg = dist.get_backend(self.pg) == "nccl"       # ReduceOp.AVG exists on NCCL only
         op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         works = []
@@ -125,6 +127,9 @@ class GradReducer:
                 works.append(dist.all_reduce(f[o:o + step], op=op, group=self.pg, async_op=True))
         tmp = None
         if rest:
+            for p in rest:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
             tmp = torch.cat([p.grad.reshape(-1) for p in rest])
             works.append(dist.all_reduce(tmp, op=op, group=self.pg, async_op=True))
         for w in works:

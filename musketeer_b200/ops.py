@@ -21,6 +21,10 @@ F32, BF16 = 0, 1
 # LayerNorm reduce, embedding scatter-add) write / accumulate straight into one persistent buffer per parameter and hand
 # autograd `None`; on exit the buffers become `param.grad`.  Outside the context everything goes through autograd as usual
 # (required when gradient hooks must observe each accumulation, e.g. the eager DDP overlap path).
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class _GradAccumulator:
     def __init__(self, model):
         self.params = {id(p): p for p in model.parameters() if p.requires_grad}
@@ -37,6 +41,8 @@ class _GradAccumulator:
         self.region = {}           # id(param) -> (offset, numel)
         self.arena_used = 0
         self.written32 = set()
+        self.continuing = set()    # parameters whose .grad aliases the arenas at `begin` (gradient accumulation over micro-steps)
+        self._buf_live = {}        # id(param) -> the bf16 buffer holds a contribution that belongs to the current .grad
 
     def target32(self, param):
         """-> fp32 [N, K] accumulation view for a registered >= 2-D leaf parameter, else None."""
@@ -51,7 +57,7 @@ class _GradAccumulator:
             self.region, self.arena_used = {}, 0
         r = self.region.get(k)
         if r is None:
-            if torch.cuda.is_current_stream_capturing():
+            if _capturing():
                 raise RuntimeError("grad accumulation arena must be laid out by an eager warm-up step before graph capture")
             r = self.region[k] = (self.arena_used, param.numel())
             self.arena_used += (param.numel() + 63) // 64 * 64
@@ -92,7 +98,7 @@ class _GradAccumulator:
                 self.arena_buf = torch.zeros(sum((p.numel() + 63) // 64 * 64 for p in self.params.values()),
                                              dtype=param.dtype, device=param.device)
                 self.buf, self.buf_used = {}, 0
-            if dense and not torch.cuda.is_current_stream_capturing():
+            if dense and not _capturing():
                 n = param.numel()       # same memory format as the parameter (channels_last conv weights)
                 b = self.arena_buf[self.buf_used:self.buf_used + n].as_strided(param.shape, param.stride())
                 self.buf_used += (n + 63) // 64 * 64
@@ -101,26 +107,58 @@ class _GradAccumulator:
             self.buf[k] = b
         first = k not in self.written
         self.written.add(k)
+        if first and k in self.continuing and self._buf_live.get(k):
+            first = False                   # the buffer holds the sum of earlier micro-steps: keep adding
+        elif first:
+            self._buf_live[k] = False       # about to be overwritten by this step's first contribution
         return b, not first
+
+    def _aliases(self, k, p):
+        """True when p.grad IS this accumulator's view of parameter k (left there by a previous `finish`): the caller kept
+        the gradients of an earlier micro-step (update_freq > 1, trainer.py:752-773) and this step must ADD to them."""
+        g = p.grad
+        if g is None:
+            return False
+        r = self.region.get(k)
+        if r is not None and self.arena_out is not None and g.dtype == self.arena_out.dtype and \
+                g.data_ptr() == self.arena_out.data_ptr() + r[0] * self.arena_out.element_size():
+            return True
+        b = self.buf.get(k)
+        return b is not None and g.data_ptr() == b.data_ptr()
 
     def begin(self):
         self.written, self.written32 = set(), set()
+        # Parameters whose .grad still aliases the arenas carry the running sum of earlier micro-steps: their fp32 regions are
+        # NOT zeroed (the arena keeps the running fp32 sum, `finish` re-casts it) and their bf16 buffers are accumulated into
+        # from the first write on.  Everything else starts from zero.  (Under CUDA-graph capture gradients are None.)
+        self.continuing = set()
+        if not _capturing():
+            self.continuing = {k for k, p in self.params.items() if p.grad is not None and self._aliases(k, p)}
+        self._buf_live = {k: True for k in self.continuing if self._buf_live.get(k)}
         if self.arena32 is not None and self.arena_used:
-            self.arena32[:self.arena_used].zero_()
+            if not self.continuing:
+                self.arena32[:self.arena_used].zero_()
+            else:
+                for k, (off, n) in self.region.items():
+                    if k not in self.continuing:
+                        self.arena32[off:off + n].zero_()
 
     def finish(self):
-        if self.written32:
+        if self.written32 or (self.continuing and self.arena_used):
             self.arena_out[:self.arena_used].copy_(self.arena32[:self.arena_used])      # one cast for the whole model
-        for k in self.written32:
+        cont = self.continuing
+        for k in self.written32 | {k for k in cont if k in self.region}:
             p = self.params[k]
             off, n = self.region[k]
             g = self.arena_out[off:off + n].as_strided(p.shape, p.stride())
-            if k in self.written:            # e.g. the tied embedding: GEMM part + scatter-add part
-                g.add_(self.buf[k])
-            p.grad = g if p.grad is None else p.grad + g
-        for k in self.written - self.written32:
+            if k in self.written or (k in cont and k in self.buf and self._buf_live.get(k)):
+                g.add_(self.buf[k])          # e.g. the tied embedding: GEMM part + scatter-add part
+            p.grad = g if (p.grad is None or k in cont) else p.grad + g
+        for k in self.written - self.written32 - {k for k in cont if k in self.region}:
             p, b = self.params[k], self.buf[k]
-            p.grad = b if p.grad is None else p.grad + b
+            p.grad = b if (p.grad is None or k in cont) else p.grad + b
+        for k in self.written:
+            self._buf_live[k] = True
         self.written, self.written32 = set(), set()
 
     def flat_grads(self):

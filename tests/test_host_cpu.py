@@ -112,3 +112,41 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_grad_accumulator_keeps_running_sum_over_micro_steps():
+    """update_freq > 1 (trainer.py:752-773): a second micro-step that runs without clearing .grad must ADD to the first one's
+    gradients although .grad aliases the accumulator's arenas (the arenas were overwritten and .grad doubled).
+    The producers are emulated on the CPU by writing into the accumulator's targets the way the kernels do."""
+    import torch
+    from musketeer_b200 import ops
+    lin = torch.nn.Linear(64, 64)            # weight -> fp32 arena (GEMM reduce-add); bias -> bf16/param-dtype buffer
+    emb = torch.nn.Embedding(16, 64)         # both: GEMM part (tied projection) + scatter-add part
+    model = torch.nn.ModuleList([lin, emb])
+
+    def micro_step(c):
+        with ops.grad_accumulation(model) as acc:
+            acc.target32(lin.weight).add_(c)                         # TMA reduce-add of a wgrad GEMM
+            b, accum = acc.target(lin.bias)                          # colsum kernel: overwrite or accumulate
+            b.copy_(b + 2 * c if accum else torch.full_like(b, 2 * c))
+            acc.target32(emb.weight).add_(3 * c)
+            e, accum = acc.target(emb.weight)
+            if not accum:
+                e.zero_()
+            e.add_(4 * c)
+
+    micro_step(1.0)
+    assert float(lin.weight.grad[0, 0]) == 1 and float(lin.bias.grad[0]) == 2 and float(emb.weight.grad[0, 0]) == 7
+    micro_step(3.0)                                                  # no zero_grad in between
+    assert float(lin.weight.grad[0, 0]) == 4, float(lin.weight.grad[0, 0])
+    assert float(lin.bias.grad[0]) == 8 and float(emb.weight.grad[0, 0]) == 28
+    with ops.grad_accumulation(model) as acc:                        # a step that touches only one parameter keeps the others
+        acc.target32(lin.weight).add_(1.0)
+    assert float(lin.weight.grad[0, 0]) == 5 and float(lin.bias.grad[0]) == 8 and float(emb.weight.grad[0, 0]) == 28
+    for p in model.parameters():
+        p.grad = None
+    micro_step(2.0)                                                  # cleared gradients start from zero again
+    assert float(lin.weight.grad[0, 0]) == 2 and float(lin.bias.grad[0]) == 4 and float(emb.weight.grad[0, 0]) == 14
+    lin.weight.grad = torch.ones_like(lin.weight)                    # a foreign gradient tensor is added to, not replaced
+    micro_step(1.0)
+    assert float(lin.weight.grad[0, 0]) == 2

@@ -387,3 +387,108 @@ def test_merged_decoder_passes_equal_per_task_passes(dtype):
                 assert (v - res[1][1][n]).abs().max().item() <= 5e-3 * max(1.0, v.abs().max().item()), n
         ref_loss, _, _ = oo.criterion_forward(tie(sd), cfg, copy.deepcopy(samples), epsilon=0.1, use_rdrop=False, sample_patch_num=0)
         assert abs(res[1][0] - float(ref_loss.detach())) <= 1e-3 * abs(float(ref_loss.detach()))
+
+
+def _multitask_case():
+    fx = load_golden("micro_multitask_rdrop")
+    return build_case(fx["case"])
+
+
+def test_grad_accumulation_over_two_micro_steps_without_zero_grad():
+    """update_freq = 2 (trainer.py:752-773; the Musketeer script uses 16): the second micro-step runs under
+    ops.grad_accumulation without clearing .grad -- whose tensors alias the accumulator's arenas -- and must ADD to the first
+    (the arenas were overwritten and the sum came out as 2 x the second step)."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion, ops
+    cfg, sd, samples = _multitask_case()
+    batches = [to_device(copy.deepcopy(samples), "cuda", torch.float32),
+               to_device(copy.deepcopy(samples[::-1]), "cuda", torch.float32)]
+    model, task = build_product(cfg, sd, dtype=torch.float32)
+    model.train()
+    model.encoder.embed_images.eval()          # running statistics: the three passes below see the same stem
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0)
+
+    def run(batch):
+        with ops.grad_accumulation(model):
+            loss, _, _ = crit(model, copy.deepcopy(batch))
+            loss.backward()
+
+    singles = []
+    for b in batches:
+        for p in model.parameters():
+            p.grad = None
+        run(b)
+        singles.append({n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    for p in model.parameters():
+        p.grad = None
+    run(batches[0])
+    run(batches[1])                             # no zero_grad in between
+    for n, p in model.named_parameters():
+        if n not in singles[0]:
+            continue
+        want = singles[0][n] + singles[1][n]
+        err = (p.grad.float() - want).abs().max().item()
+        assert err <= 2e-4 * max(1.0, want.abs().max().item()), (n, err)
+
+
+def test_graphed_step_equals_eager_and_is_keyed_on_shapes_only():
+    """GraphedTrainStep: (1) loss / gradients of a replay equal the eager step; (2) two batches of the same shapes but different
+    `ntokens` share ONE capture (the collater counts are device scalars, not cache keys -- ADVICE r1); (3) BatchNorm running
+    statistics after the first graphed call equal those after ONE eager step (the warm-up passes are undone); (4) first= / last=
+    sum the gradients of the micro-steps of one update."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion, ops
+    from musketeer_b200.graphed import GraphedTrainStep
+    cfg, sd, samples = _multitask_case()
+    b0 = copy.deepcopy(samples)
+    b1 = copy.deepcopy(samples)
+    for s in b1:                                 # same shapes, fewer target tokens
+        s["target"][:, -2:] = 1
+        s["ntokens"] = int(s["target"].ne(1).sum())
+    assert any(x["ntokens"] != y["ntokens"] for x, y in zip(b0, b1))
+    dt = torch.float32
+
+    def eager(model, crit, batch):
+        for p in model.parameters():
+            p.grad = None
+        with ops.grad_accumulation(model):
+            loss, _, _ = crit(model, to_device(copy.deepcopy(batch), "cuda", dt))
+            loss.backward()
+        return float(loss.detach()), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    m_e, task = build_product(cfg, sd, dtype=dt)
+    m_g, _ = build_product(cfg, sd, dtype=dt)
+    m_e.train(), m_g.train()
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0)
+    graphed = GraphedTrainStep(m_g, crit, torch.device("cuda"), dt)
+    stats = lambda m: {n: b.float().clone() for n, b in m.named_buffers() if "running_" in n or "num_batches" in n}
+    ref = [eager(m_e, crit, b0)]
+    st_e = stats(m_e)
+    loss, _ = graphed(b0)
+    st_g = stats(m_g)
+    got = [(float(loss), {n: p.grad.float().clone() for n, p in m_g.named_parameters() if p.grad is not None})]
+    for n in st_e:
+        assert (st_e[n] - st_g[n]).abs().max().item() <= 2e-4 * max(1.0, st_e[n].abs().max().item()), n
+    ref.append(eager(m_e, crit, b1))
+    loss, _ = graphed(b1)
+    got.append((float(loss), {n: p.grad.float().clone() for n, p in m_g.named_parameters() if p.grad is not None}))
+    assert len(graphed.cache) == 1
+    for (lr, gr), (lg, gg) in zip(ref, got):
+        assert abs(lr - lg) <= 1e-4 * abs(lr), (lr, lg)
+        n0 = sum(float(v.norm()) ** 2 for v in gr.values()) ** 0.5
+        n1 = sum(float(v.norm()) ** 2 for v in gg.values()) ** 0.5
+        assert abs(n0 - n1) <= 2e-3 * n0, (n0, n1)
+        for n, v in gr.items():
+            if "embed_images" not in n:          # the stem sits behind 90+ BatchNorm backward passes on 2-image batches
+                assert (v - gg[n]).abs().max().item() <= 5e-3 * max(1.0, v.abs().max().item()), n
+    # update_freq = 2 through the graph: gradients of both micro-steps summed
+    m_g.encoder.embed_images.eval()
+    g2 = GraphedTrainStep(m_g, crit, torch.device("cuda"), dt)
+    g2(b0)
+    a = {n: p.grad.float().clone() for n, p in m_g.named_parameters() if p.grad is not None}
+    g2(b1)
+    b = {n: p.grad.float().clone() for n, p in m_g.named_parameters() if p.grad is not None}
+    g2(b0, first=True, last=False)
+    g2(b1, first=False, last=True)
+    for n, p in m_g.named_parameters():
+        if n in a:
+            want = a[n] + b[n]
+            assert (p.grad.float() - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item()), n
