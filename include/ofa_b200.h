@@ -143,6 +143,20 @@ int ofa_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, void* dx, int
  * convolution and its weight gradient are ofa_gemm_bf16 calls on col.                                                   */
 int ofa_stem_patches(const void* x, void* col, int N, int H, int W, void* stream);
 
+/* ---- patch matrix (im2col) of an NHWC activation and its adjoint: every convolution that the implicit-GEMM kernel above does
+ * not cover (the two stride-2 3x3 convolutions of the stem, models/ofa/resnet.py:34-37,107-121, and all k > 1 convolutions of
+ * the fp32 parity mode incl. the 7x7 stem convolution :176,214) is `patch matrix x weight^T` on ofa_gemm_bf16.
+ * col[(n,oh,ow)][(kh*KW + kw)*C + c] = x[n][oh*stride - pad + kh][ow*stride - pad + kw][c] (0 outside), row stride ldcol;
+ * ofa_col2im is the adjoint (dx = sum of the patch entries that read each pixel, fixed order, no atomics).           */
+int ofa_im2col(const void* x, void* col, int N, int H, int W, int C, int KH, int KW, int stride, int pad, long long ldcol,
+               int dtype, void* stream);
+int ofa_col2im(const void* dcol, void* dx, int N, int H, int W, int C, int KH, int KW, int stride, int pad, long long ldcol,
+               int dtype, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on NHWC activations of either dtype (the fp32 parity mode; bf16 with C % 8 == 0 uses the vectorised
+ * kernels above).  backward = 0: in = x, out = y, idx written;  backward = 1: in = dy, out = dx, idx read.             */
+int ofa_maxpool3x3s2_any(const void* in, unsigned char* idx, void* out, int N, int H, int W, int C, int backward, int dtype,
+                         void* stream);
+
 /* ---- stride-2 pixel subsampling of an NHWC activation = the input side of the stride-2 1x1 downsample convolutions
  * (models/ofa/resnet.py:196-203), and its adjoint (zero fill + scatter in one pass).  [N, H, W, C] are the dimensions of
  * the FULL-resolution tensor; the subsampled one is [N, (H+1)/2, (W+1)/2, C].  esize = bytes per element (2 | 4),

@@ -78,6 +78,9 @@ SIGNATURES = {
     "ofa_maxpool3x3s2_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "ofa_maxpool3x3s2_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "ofa_subsample2": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "ofa_im2col": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_ll, c_i, c_p],
+    "ofa_col2im": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_ll, c_i, c_p],
+    "ofa_maxpool3x3s2_any": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "ofa_stem_patches": [c_p, c_p, c_i, c_i, c_i, c_p],
     "ofa_adam_step": [c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_p],
     "ofa_scale_rows": [c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_i, c_p],

@@ -3,10 +3,36 @@
 Mirrors criterions/label_smoothed_cross_entropy.py:129-275 (same constructor arguments, `forward(model, sample,
 update_num, reduce)` -> `(loss, sample_size, logging_output)` with the same logging keys, multi-task list recursion
 of :175-202, R-Drop sample duplication of :56-71 incl. the doubled `sample_patch_num`)."""
+from dataclasses import dataclass, field
+from typing import Optional
+
 import numpy as np
 import torch
 
 from . import ops
+from ._fairseq_compat import FairseqCriterion, HAVE_FAIRSEQ, metrics
+
+try:        # the criterion's flags are a fairseq dataclass in the reference (:14-53); fairseq derives --label-smoothing etc. from it
+    from fairseq.dataclass import FairseqDataclass
+    from omegaconf import II
+    _SENTENCE_AVG = II("optimization.sentence_avg")
+except ImportError:
+    FairseqDataclass, _SENTENCE_AVG = object, False
+
+
+@dataclass
+class AdjustLabelSmoothedCrossEntropyCriterionConfig(FairseqDataclass):
+    label_smoothing: float = field(default=0.0, metadata={"help": "epsilon for label smoothing, 0 means no label smoothing"})
+    report_accuracy: bool = field(default=False, metadata={"help": "report accuracy metric"})
+    ignore_prefix_size: int = field(default=0, metadata={"help": "Ignore first N tokens"})
+    ignore_eos: bool = field(default=False, metadata={"help": "Ignore eos token"})
+    sentence_avg: bool = _SENTENCE_AVG
+    drop_worst_ratio: float = field(default=0.0, metadata={"help": "ratio for discarding bad samples"})
+    drop_worst_after: int = field(default=0, metadata={"help": "steps for discarding bad samples"})
+    use_rdrop: bool = field(default=False, metadata={"help": "use R-Drop"})
+    reg_alpha: float = field(default=1.0, metadata={"help": "weight for R-Drop"})
+    sample_patch_num: int = field(default=196, metadata={"help": "sample patches for v1"})
+    constraint_range: Optional[str] = field(default=None, metadata={"help": "constraint range"})
 
 
 def construct_rdrop_sample(x):
@@ -25,12 +51,18 @@ def construct_rdrop_sample(x):
     raise NotImplementedError(type(x))
 
 
-class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
+class AdjustLabelSmoothedCrossEntropyCriterion(FairseqCriterion):
+    """A FairseqCriterion (fairseq's `register_criterion` accepts nothing else); `batch_task_*` are this package's own
+    switches for the multi-task batching and default to on."""
+
     def __init__(self, task, sentence_avg=False, label_smoothing=0.0, ignore_prefix_size=0, ignore_eos=False,
                  report_accuracy=False, drop_worst_ratio=0, drop_worst_after=0, use_rdrop=False, reg_alpha=1.0,
                  sample_patch_num=196, constraint_range=None, batch_task_stems=True, batch_task_encoders=True,
                  batch_task_decoders=True):
-        super().__init__()
+        super().__init__(task)
+        if report_accuracy:
+            raise NotImplementedError("--report-accuracy crashes in the reference (compute_accuracy unpacks 2 of 3 values, "
+                                      "SURVEY.md appendix C) and no script sets it")
         self.batch_task_stems = batch_task_stems
         self.batch_task_encoders = batch_task_encoders and batch_task_stems
         self.batch_task_decoders = batch_task_decoders and self.batch_task_encoders
@@ -230,6 +262,29 @@ class AdjustLabelSmoothedCrossEntropyCriterion(torch.nn.Module):
         logging_output = {"loss": loss.data, "nll_loss": nll_rows.sum().data, "ntokens": sample["ntokens"],
                           "nsentences": sample["nsentences"], "sample_size": sample_size}
         return loss, sample_size, logging_output
+
+    @classmethod
+    def reduce_metrics(cls, logging_outputs) -> None:
+        """Aggregate the logging outputs of the data-parallel workers (label_smoothed_cross_entropy.py:286-345)."""
+        if metrics is None:
+            raise RuntimeError("reduce_metrics needs fairseq.metrics")
+        tot = lambda key: sum(log.get(key, 0) for log in logging_outputs)
+        sample_size, ntokens = tot("sample_size"), tot("ntokens")
+        ss1, ss2 = max(tot("sample_size_v1"), 1), max(tot("sample_size_v2"), 1)
+        metrics.log_scalar("loss", tot("loss") / sample_size, sample_size, round=3)
+        metrics.log_scalar("loss_v1", tot("loss_v1") / ss1, ss1, round=3)
+        metrics.log_scalar("loss_v2", tot("loss_v2") / ss2, ss2, round=3)
+        metrics.log_scalar("nll_loss", tot("nll_loss") / sample_size, ntokens, round=3)
+        try:
+            from fairseq import utils as fs_utils
+            metrics.log_derived("ppl", lambda meters: fs_utils.get_perplexity(meters["nll_loss"].avg))
+        except (ImportError, AttributeError):
+            pass
+        metrics.log_scalar("ntokens", ntokens, 1, round=3)
+        metrics.log_scalar("nsentences", tot("nsentences"), 1, round=3)
+        metrics.log_scalar("sample_size", sample_size, 1, round=3)
+        metrics.log_scalar("sample_size_v1", tot("sample_size_v1"), 1, round=3)
+        metrics.log_scalar("sample_size_v2", tot("sample_size_v2"), 1, round=3)
 
     @staticmethod
     def logging_outputs_can_be_summed():

@@ -93,6 +93,60 @@ __device__ __forceinline__ void block_accumulate(const Map& m, int C, int CS, co
   }
 }
 
+// ---- order-independent (bit-reproducible) accumulation of the FORWARD statistics ----------------------------------------
+// fp32 atomics add the CTAs' partial sums in arrival order, so batch statistics differed in the last bits from run to run;
+// behind 90+ BatchNorm / ReLU layers that noise moved whole-model gradient norms by percents on small batches.
+// Here every partial sum is added EXACTLY: a float is an integer mantissa times a power of two, the mantissa is shifted to
+// the fixed binary position of one of kLimbs 64-bit integer accumulators per value (limb k collects least-significant-bit
+// positions [kP0 + 24k, kP0 + 24k + 24)) and added with an integer atomic -- integer addition is associative, so the limbs
+// hold the same bits whatever the arrival order.  The last CTA of the launch (atomic ticket) folds the limbs into the fp32
+// sums the apply kernel reads, most significant first, in double precision, and clears them for the next call.  Range: values
+// from 2^-57 (smaller ones lose low bits) to 2^54; non-finite partial sums poison the fp32 slot directly so NaN / inf reach
+// the loss as before.  The backward statistics keep fp32 atomics: their rounding noise meets no ReLU mask on its way to the
+// parameter gradients and stays at the 1e-7 level.
+constexpr int kLimbs = 4, kP0 = -80;
+constexpr int kSumsN = 2 * 2048 * 8;     // = 2 * kMaxC * kMaxGroups floats of fp32 sums at the start of the scratch
+__device__ __forceinline__ void exact_add(unsigned long long* __restrict__ limbs, float* __restrict__ sums, int slot, float p) {
+  const uint32_t bits = __float_as_uint(p);
+  if ((bits & 0x7fffffffu) == 0u) return;
+  int e = (int)((bits >> 23) & 0xffu);
+  if (e == 0xff) { atomicAdd(sums + slot, p); return; }
+  long long mant = (long long)((bits & 0x7fffffu) | (e ? 0x800000u : 0u));
+  if (e == 0) e = 1;
+  const int pos = e - 150 - kP0;          // position of the mantissa's least significant bit above the bottom of limb 0
+  int k = 0, o = 0;
+  if (pos < 0) mant >>= min(-pos, 31);
+  else { k = min(pos / 24, kLimbs - 1); o = min(pos - 24 * k, 38); }
+  long long v = mant << o;
+  if (bits >> 31) v = -v;
+  atomicAdd(limbs + (size_t)k * kSumsN + slot, (unsigned long long)v);
+}
+// called by every thread of every CTA of bn_stats_kernel after its exact_add calls
+__device__ __forceinline__ void exact_finalize(unsigned long long* __restrict__ limbs, float* __restrict__ sums, int nvals) {
+  __shared__ int last_cta;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(limbs + (size_t)kLimbs * kSumsN);
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    last_cta = atomicAdd(ticket, 1u) == total - 1;
+    if (last_cta) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  for (int s = threadIdx.x; s < nvals; s += kT) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = kLimbs - 1; k >= 0; --k) {
+      const long long L = (long long)__ldcg(limbs + (size_t)k * kSumsN + s);
+      acc += (double)L * exp2((double)(kP0 + 24 * k));
+      limbs[(size_t)k * kSumsN + s] = 0ull;
+    }
+    sums[s] = __ldcg(sums + s) + (float)acc;      // (+ a non-finite poison value, if any)
+  }
+}
+
 // The per-channel sums live in a caller-provided scratch that is ZERO ON ENTRY and LEFT ZERO ON EXIT: every CTA of the apply
 // kernel bumps a counter once it has read the sums, and the last one clears sums and counter for the next BatchNorm call in
 // the stream (no memset node per layer; 752 of them per training step before).  scratch = [2*C sums | ... | counter @ 2*kMaxC].
@@ -117,11 +171,10 @@ constexpr int kUnroll = 4;
 // forward statistics: sums[0][c] += sum x, sums[1][c] += sum x^2
 template <typename T>
 __global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x, long long R, int C, int CS,
-                                                      float* __restrict__ sums) {
+                                                      float* __restrict__ sums_base, unsigned long long* __restrict__ limbs) {
   pdl_sync();
   const Map m = make_map(CS);
   x += (long long)blockIdx.z * R * C;            // this group's rows
-  sums += (size_t)blockIdx.z * 2 * C;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
@@ -142,7 +195,24 @@ __global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x
       }
     }
   }
-  block_accumulate(m, C, CS, a, b, sums);
+  // block-level reduction over the row-lanes (fixed order), then one exact integer accumulation per channel and CTA
+  {
+    __shared__ float sa[kT * 8], sb[kT * 8];   // [rpi][CS]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sa[m.ry * CS + m.cx * 8 + j] = a[j];
+      sb[m.ry * CS + m.cx * 8 + j] = b[j];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < CS) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int q = 0; q < m.rpi; ++q) { s0 += sa[q * CS + threadIdx.x]; s1 += sb[q * CS + threadIdx.x]; }
+      const int slot = (int)blockIdx.z * 2 * C + (int)blockIdx.y * CS + (int)threadIdx.x;
+      exact_add(limbs, sums_base, slot, s0);
+      exact_add(limbs, sums_base, slot + C, s1);
+    }
+  }
+  exact_finalize(limbs, sums_base, 2 * C * (int)gridDim.z);
 }
 
 // forward apply: y = relu?(x * scale_c + shift_c + res).  Every thread derives scale / shift of its 8 channels from the
@@ -390,7 +460,8 @@ int fwd_impl(const void* x, const void* res, void* y, const void* gamma, const v
   float* sums = ws;
   if (training) {
     const Grid gs = grid_for(R, C, kUnroll, groups, 4);
-    OFA_CUDA(ofa_launch_pdl(bn_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, R, C, gs.CS, sums));
+    unsigned long long* limbs = reinterpret_cast<unsigned long long*>(ws + kSumsN + 32);
+    OFA_CUDA(ofa_launch_pdl(bn_stats_kernel<T>, gs.g, kT, 0, st, (const T*)x, R, C, gs.CS, sums, limbs));
   }
   const Grid ga = grid_for(R, C, kUnroll, groups, 3);
   OFA_CUDA(ofa_launch_pdl(bn_apply_kernel<T>, ga.g, kT, 0, st, (const T*)x, (const T*)res, (T*)y, (const T*)gamma, (const T*)beta, (T*)rm, (T*)rv,
@@ -430,7 +501,12 @@ extern "C" int ofa_batchnorm_set_tuning(int waves, int bwd_unroll) {
   return 0;
 }
 
-extern "C" long long ofa_batchnorm_workspace_floats(int C) { (void)C; return 2LL * kMaxC * kMaxGroups + 32; }
+// scratch (floats): [0, kSumsN) fp32 sums | counter | pad to 32 | kLimbs * kSumsN 64-bit limbs | ticket | pad
+extern "C" long long ofa_batchnorm_workspace_floats(int C) {
+  (void)C;
+  static_assert(kSumsN == 2 * kMaxC * kMaxGroups, "scratch layout");
+  return (long long)kSumsN + 32 + 2LL * kLimbs * kSumsN + 32;
+}
 
 extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                                  void* running_mean, void* running_var, long long R, int C, float eps, float momentum,

@@ -11,6 +11,7 @@ Contract kept from the reference:
 nn.Linear / nn.LayerNorm / nn.Embedding objects below are parameter holders only -- their torch forward is never
 called; arithmetic goes through `musketeer_b200.ops`.  Internally activations are batch-first [B, L, d].
 """
+import logging
 import math
 import random
 from types import SimpleNamespace
@@ -21,7 +22,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._fairseq_compat import (FairseqEncoder, FairseqEncoderDecoderModel, FairseqIncrementalDecoder, HAVE_FAIRSEQ)
 from .resnet import ResNetStem
+
+logger = logging.getLogger(__name__)
 
 DEFAULT_MAX_SOURCE_POSITIONS = 1024
 DEFAULT_MAX_TARGET_POSITIONS = 1024
@@ -103,8 +107,44 @@ def _unsupported(args, names):
                                       n.replace("_", "-"))
 
 
+def _upgrade_layer_norm_names(module, state_dict, name, layer_norm_map):
+    """Old checkpoints: `...layer_norms.{i}.*` -> the named LayerNorms; keys the checkpoint lacks are filled from the module
+    (unify_transformer_layer.py:200-221,587-615)."""
+    own = module.state_dict()
+    for old, new in layer_norm_map.items():
+        for m in ("weight", "bias"):
+            k = "{}.layer_norms.{}.{}".format(name, old, m)
+            if k in state_dict:
+                state_dict["{}.{}.{}".format(name, new, m)] = state_dict.pop(k)
+    prefix = name + "." if name != "" else ""
+    for k, v in own.items():
+        if prefix + k not in state_dict:
+            state_dict[prefix + k] = v
+
+
+def _grow_image_positions(module, state_dict, key):
+    """A checkpoint trained with a smaller image bucket grid: append freshly initialised position rows
+    (unify_transformer.py:1060-1071,1647-1658)."""
+    have, want = state_dict[key], module.embed_image_positions.weight
+    if len(have) < len(want):
+        extra = torch.zeros(len(want) - len(have), have.size(1))
+        nn.init.normal_(extra, mean=0, std=have.size(1) ** -0.5)
+        state_dict[key] = torch.cat([have, extra.to(dtype=have.dtype, device=have.device)])
+
+
 class MultiheadAttention(nn.Module):
     """Parameter holder + call into ops.attention (unify_multihead_attention.py:20-409)."""
+
+    def upgrade_state_dict_named(self, state_dict, name):
+        """fused `in_proj_weight / in_proj_bias` of very old checkpoints -> q / k / v projections (:495-524)."""
+        prefix = name + "." if name != "" else ""
+        for kind in ("weight", "bias"):
+            k = prefix + "in_proj_" + kind
+            if k in state_dict:
+                w = state_dict.pop(k)
+                dim = w.shape[0] // 3
+                for i, proj in enumerate(("q_proj", "k_proj", "v_proj")):
+                    state_dict[prefix + proj + "." + kind] = w[i * dim:(i + 1) * dim]
 
     def __init__(self, embed_dim, num_heads, scale_factor=2.0, scale_heads=False, self_attention=False,
                  encoder_decoder_attention=False):
@@ -195,6 +235,10 @@ class TransformerEncoderLayer(nn.Module, _FFNMixin):
         x = self._post_attn(self.self_attn, o, self.attn_ln, x)
         return self._ffn(x)
 
+    def upgrade_state_dict_named(self, state_dict, name):
+        self.self_attn.upgrade_state_dict_named(state_dict, name + ".self_attn")
+        _upgrade_layer_norm_names(self, state_dict, name, {"0": "self_attn_layer_norm", "1": "final_layer_norm"})
+
 
 class TransformerDecoderLayer(nn.Module, _FFNMixin):
     """unify_transformer_layer.py:296-582."""
@@ -232,6 +276,12 @@ class TransformerDecoderLayer(nn.Module, _FFNMixin):
         x = self._post_attn(self.encoder_attn, o, self.cross_attn_ln, x)
         return self._ffn(x)
 
+    def upgrade_state_dict_named(self, state_dict, name):
+        self.self_attn.upgrade_state_dict_named(state_dict, name + ".self_attn")
+        self.encoder_attn.upgrade_state_dict_named(state_dict, name + ".encoder_attn")
+        _upgrade_layer_norm_names(self, state_dict, name, {"0": "self_attn_layer_norm", "1": "encoder_attn_layer_norm",
+                                                           "2": "final_layer_norm"})
+
 
 def _rel_bucket_1d(token_rp_bucket):
     """bucket as a function of (i - j) only: index rel + 1023 for rel in [-1023, 1023]."""
@@ -249,13 +299,12 @@ def _img_lut(table_weight):
     return table_weight.t().float().contiguous()                                     # [H, n_rel]
 
 
-class TransformerEncoder(nn.Module):
+class TransformerEncoder(FairseqEncoder):
     """unify_transformer.py:493-1072."""
 
     def __init__(self, args, dictionary, embed_tokens):
-        super().__init__()
+        super().__init__(dictionary)
         self.args = args
-        self.dictionary = dictionary
         _unsupported(args, ["encoder_prompt", "adapter", "bitfit", "sync_bn", "interpolate_position",
                             "entangle_position_embedding", "scale_resids"])
         if args.attention_dropout or getattr(args, "activation_dropout", 0) or getattr(args, "relu_dropout", 0):
@@ -394,6 +443,17 @@ class TransformerEncoder(nn.Module):
     def forward_torchscript(self, net_input):
         return self.forward(**{k: v for k, v in net_input.items() if k != "prev_output_tokens"})
 
+    def upgrade_state_dict_named(self, state_dict, name):
+        """unify_transformer.py:1033-1072."""
+        for i, layer in enumerate(self.layers):
+            layer.upgrade_state_dict_named(state_dict, "{}.layers.{}".format(name, i))
+        prefix = name + "." if name != "" else ""
+        for k, v in self.state_dict().items():
+            if prefix + k not in state_dict:
+                state_dict[prefix + k] = v
+        _grow_image_positions(self, state_dict, prefix + "embed_image_positions.weight")
+        return state_dict
+
     def reorder_encoder_out(self, encoder_out, new_order):
         out = {}
         for k, dim in (("encoder_out", 1), ("encoder_padding_mask", 0), ("encoder_embedding", 0), ("src_tokens", 0),
@@ -406,13 +466,13 @@ class TransformerEncoder(nn.Module):
         return self.max_source_positions
 
 
-class TransformerDecoder(nn.Module):
-    """unify_transformer.py:1075-1659."""
+class TransformerDecoder(FairseqIncrementalDecoder):
+    """unify_transformer.py:1075-1659.  A FairseqIncrementalDecoder: the reference generator enables incremental decoding only
+    for decoders of that type (models/sequence_generator.py:776-781)."""
 
     def __init__(self, args, dictionary, embed_tokens, no_encoder_attn=False):
-        super().__init__()
+        super().__init__(dictionary)
         self.args = args
-        self.dictionary = dictionary
         _unsupported(args, ["decoder_prompt", "adapter", "cross_self_attention", "no_cross_attention"])
         self.dropout_p = float(args.dropout)
         self.register_buffer("version", torch.Tensor([3]))
@@ -621,20 +681,48 @@ class TransformerDecoder(nn.Module):
     def max_positions(self):
         return self.max_target_positions
 
+    def upgrade_state_dict_named(self, state_dict, name):
+        """unify_transformer.py:1605-1659."""
+        prefix = name + "." if name != "" else ""
+        if prefix + "output_projection.weight" not in state_dict and prefix + "embed_tokens.weight" in state_dict:
+            state_dict[prefix + "output_projection.weight"] = state_dict[prefix + "embed_tokens.weight"]    # tied (:1615-1626)
+        for i, layer in enumerate(self.layers):
+            layer.upgrade_state_dict_named(state_dict, "{}.layers.{}".format(name, i))
+        own = self.state_dict()
+        state_dict[prefix + "image_position_idx"] = own["image_position_idx"]       # always the model's own (:1640-1642)
+        for k, v in own.items():
+            if prefix + k not in state_dict:
+                state_dict[prefix + k] = v
+        _grow_image_positions(self, state_dict, prefix + "embed_image_positions.weight")
+        return state_dict
 
-class OFAModel(nn.Module):
-    """models/ofa/ofa.py:25-171.  Registered as fairseq model "ofa" by musketeer_b200.plugin when fairseq is present."""
+
+class OFAModel(FairseqEncoderDecoderModel):
+    """models/ofa/ofa.py:25-171.  Registered as fairseq model "ofa" (+ architectures ofa_tiny ... ofa_huge) by
+    musketeer_b200.plugin; with fairseq on the path this IS a FairseqEncoderDecoderModel."""
 
     def __init__(self, args, encoder, decoder):
-        super().__init__()
+        super().__init__(encoder, decoder)
         self.args = args
-        self.encoder, self.decoder = encoder, decoder
         self.supports_align_args = True
         self.apply(init_bert_params)
         self.classification_heads = nn.ModuleDict()
         if hasattr(self.encoder, "dictionary"):
             self.eos = self.encoder.dictionary.eos()
         self.enc_timer, self.dec_timer, self.cls_timer = [0, 0], [0, 0], [0, 0]
+
+    @staticmethod
+    def add_args(parser):
+        """Every flag of TransformerModel.add_args + OFAModel.add_args (unify_transformer.py:150-334, ofa.py:45-73)."""
+        from .options import add_model_args
+        add_model_args(parser)
+
+    def half(self):
+        """trainer.py:99-106 calls .half() under --fp16 (what train_musketeer.sh:174 passes).  The kernels of this package
+        compute in bfloat16 (fp32 accumulation): same exponent range as fp32, so fairseq's fp16 loss scaler never overflows
+        and the run proceeds exactly as with --bf16."""
+        logger.warning("musketeer_b200: --fp16 requested; the sm_100a kernels run bfloat16 (fp32 accumulate) instead")
+        return self.bfloat16()
 
     @classmethod
     def build_model(cls, args, task):
@@ -664,6 +752,9 @@ class OFAModel(nn.Module):
                 patch_masks=None, code_masks=None, sample_patch_num=None, features_only=False,
                 classification_head_name=None, token_embeddings=None, return_all_hiddens=False, alignment_layer=None,
                 alignment_heads=None, task_name=None, padded_logits=False, patch_features=None, encoder_out=None):
+        if patch_images is not None and patch_images.dtype != self.encoder.embed_tokens.weight.dtype:
+            # the trainer casts float inputs with .half() under --fp16 (trainer.py:1227-1244)
+            patch_images = patch_images.to(self.encoder.embed_tokens.weight.dtype)
         if classification_head_name is not None:
             raise NotImplementedError("classification heads are outside the hot-path scope (SURVEY.md 8)")
         if encoder_out is None:       # (a multi-task criterion may hand over its slice of a merged encoder pass)
@@ -695,11 +786,49 @@ class OFAModel(nn.Module):
     def set_num_updates(self, num_updates):
         pass
 
+    def register_embedding_tokens(self, ans2label_dict, src_dict, bpe):
+        """ofa.py:173-186: BPE ids of the answer strings whose embeddings seed vocabulary rows added at load time."""
+        self.ans_tensor_list = []
+        for i in range(len(ans2label_dict)):
+            ans = src_dict[-len(ans2label_dict) + i]
+            ans = ans[5:-1].replace("_", " ")
+            self.ans_tensor_list.append(src_dict.encode_line(line=bpe.encode(" {}".format(ans.lower())),
+                                                             add_if_not_exist=False, append_eos=False).long())
+
+    def register_classification_head(self, name, num_classes=None, inner_dim=None, use_two_images=False, **kwargs):
+        raise NotImplementedError("classification heads are outside the hot-path scope (SURVEY.md 8; no Musketeer script uses them)")
+
     def upgrade_state_dict_named(self, state_dict, name):
-        """Checkpoint compatibility (ofa.py:216-318 subset): fill tied / buffer keys missing from old checkpoints."""
+        """Checkpoint compatibility (ofa.py:216-318): classification heads of the checkpoint that this model does not have are
+        dropped; a trailing <mask> row is removed; a vocabulary that grew since the checkpoint gets new embedding rows (mean
+        answer-token embedding when `register_embedding_tokens` ran, else N(0, d^-0.5)); encoder / decoder / layer upgrades."""
         prefix = name + "." if name != "" else ""
-        own = self.state_dict()
-        for k, v in own.items():
-            if prefix + k not in state_dict:
-                state_dict[prefix + k] = v
+        self.encoder.upgrade_state_dict_named(state_dict, prefix + "encoder")
+        self.decoder.upgrade_state_dict_named(state_dict, prefix + "decoder")
+        head_prefix = prefix + "classification_heads."
+        for k in [k for k in state_dict if k.startswith(head_prefix)]:
+            logger.warning("deleting classification head (%s) from checkpoint not present in current model: %s",
+                           k[len(head_prefix):].split(".")[0], k)
+            del state_dict[k]
+        emb_keys = ["encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "decoder.output_projection.weight"]
+        loaded = state_dict["encoder.embed_tokens.weight"].size(0)
+        n_dict = len(self.encoder.dictionary)
+        has_mask = "<mask>" in self.encoder.dictionary if hasattr(self.encoder.dictionary, "__contains__") else True
+        if loaded == n_dict + 1 and not has_mask:
+            for k in emb_keys + ["encoder.output_projection.weight"]:
+                if k in state_dict:
+                    state_dict[k] = state_dict[k][:-1, :]
+        if loaded < n_dict:
+            w = state_dict["encoder.embed_tokens.weight"]
+            new = torch.zeros(n_dict - loaded, w.size(1))
+            if getattr(self, "ans_tensor_list", None):
+                assert len(new) == len(self.ans_tensor_list)
+                for i, ans in enumerate(self.ans_tensor_list):
+                    e = F.embedding(ans.to(w.device), w)
+                    new[i] = e.sum(0) / e.size(0)
+            else:
+                nn.init.normal_(new, mean=0, std=w.size(1) ** -0.5)
+            new = new.to(dtype=w.dtype, device=w.device)
+            for k in emb_keys:
+                state_dict[k] = torch.cat([state_dict[k], new])
         return state_dict

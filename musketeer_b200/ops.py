@@ -771,9 +771,85 @@ class _MaxPool3x3s2(torch.autograd.Function):
         return dx
 
 
+class _MaxPool3x3s2Any(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        N, Cc, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last)
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, Cc, OH, OW), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty(N * OH * OW * Cc, dtype=torch.uint8, device=x.device)
+        call("ofa_maxpool3x3s2_any", _p(x), _p(idx), _p(y), N, H, W, Cc, 0, _dt(x), _st())
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, Cc, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        N, Cc, H, W = ctx.shape
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, Cc, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        call("ofa_maxpool3x3s2_any", _p(dy), _p(idx), _p(dx), N, H, W, Cc, 1, _dt(dy), _st())
+        return dx
+
+
 def max_pool3x3s2(x):
-    """nn.MaxPool2d(3, 2, 1) on a channels_last bf16 [N, C, H, W] tensor (C % 8 == 0)."""
-    return _MaxPool3x3s2.apply(x)
+    """nn.MaxPool2d(3, 2, 1) on a channels_last [N, C, H, W] tensor: vectorised bf16 kernels when C % 8 == 0, else (and in the
+    fp32 parity mode) the generic kernels of csrc/im2col.cu."""
+    if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        return _MaxPool3x3s2.apply(x)
+    return _MaxPool3x3s2Any.apply(x)
+
+
+class _Im2col(torch.autograd.Function):
+    """NHWC patch matrix [N*OH*OW, ceil8(KH*KW*C)] (columns ordered (kh, kw, c), zero padded) and its adjoint (csrc/im2col.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, KH, KW, stride, pad):
+        _need_cuda(x)
+        N, Cc, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last)
+        OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+        K = KH * KW * Cc
+        ld = _ceil8(K)
+        col = torch.empty(N * OH * OW, ld, dtype=x.dtype, device=x.device)
+        if ld != K:
+            col[:, K:].zero_()
+        call("ofa_im2col", _p(x), _p(col), N, H, W, Cc, KH, KW, stride, pad, ld, _dt(x), _st(),
+             work=("byte", 2.0 * col.numel() * x.element_size()))
+        ctx.dims = (N, Cc, H, W, KH, KW, stride, pad, ld)
+        return col              # [N*OH*OW, ceil8(K)]: columns beyond K are zero
+
+    @staticmethod
+    def backward(ctx, dcol):
+        N, Cc, H, W, KH, KW, stride, pad, ld = ctx.dims
+        if dcol.stride(-1) != 1 or dcol.stride(0) != ld:
+            buf = torch.empty(dcol.shape[0], ld, dtype=dcol.dtype, device=dcol.device)
+            buf[:, :dcol.shape[1]].copy_(dcol)
+            dcol = buf
+        dx = torch.empty((N, Cc, H, W), dtype=dcol.dtype, device=dcol.device, memory_format=torch.channels_last)
+        call("ofa_col2im", _p(dcol), _p(dx), N, H, W, Cc, KH, KW, stride, pad, ld, _dt(dcol), _st(),
+             work=("byte", float(dcol.numel() + dx.numel()) * dcol.element_size()))
+        return dx, None, None, None, None
+
+
+def conv_im2col(x, weight, stride, pad):
+    """k x k convolution (no bias) as patch matrix x weight^T on the tcgen05 GEMM: the two stride-2 3x3 convolutions of the stem
+    and every k > 1 convolution of the fp32 parity mode (models/ofa/resnet.py:34-37,107-121,176,214).  x: channels_last
+    [N, Cin, H, W]; weight [Cout, Cin, KH, KW] (any memory format; a channels_last weight is used in place)."""
+    N, Cin, H, W = x.shape
+    Cout, _, KH, KW = weight.shape
+    OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    needs_x_grad = x.requires_grad
+    col = _Im2col.apply(x if needs_x_grad else x.detach(), KH, KW, stride, pad)
+    w2 = weight.permute(0, 2, 3, 1).reshape(Cout, KH * KW * Cin)         # (kh, kw, c) column order; a view for channels_last weights
+    K = KH * KW * Cin
+    if K % 8:                   # the patch matrix has zero columns up to a multiple of 8 (16-byte TMA rows): pad the weight alike
+        w2 = torch.nn.functional.pad(w2, (0, _ceil8(K) - K))
+    y = linear(col, w2)
+    return y.view(N, OH, OW, Cout).permute(0, 3, 1, 2)
 
 
 _BN_SCRATCH = {}

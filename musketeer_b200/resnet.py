@@ -2,9 +2,10 @@
 
 BatchNorm (+ReLU, +residual add, running-stat update, frozen / eval mode) runs on this library's fused NHWC kernels
 (ops.batch_norm); every 1x1 convolution is a tcgen05 GEMM on the NHWC bytes (ops.conv1x1) and every stride-1 3x3
-convolution the implicit-GEMM kernel of csrc/conv.cu (ops.conv3x3), forward / dgrad / wgrad, in bf16.  Still on cuDNN / ATen
-library kernels: the two stride-2 3x3 convolutions, and the convolutions / max-pool of the fp32 parity mode (the bf16 7x7
-stem convolution = patch matrix + GEMM and the bf16 max-pool are csrc/pool.cu).  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
+convolution the implicit-GEMM kernel of csrc/conv.cu (ops.conv3x3), forward / dgrad / wgrad, in bf16.  The two stride-2 3x3
+convolutions and every k > 1 convolution of the fp32 parity mode are a patch matrix (csrc/im2col.cu) times the weight on the
+same GEMM (fp32 operands through the three-way bf16 split), the max-pool is csrc/pool.cu / csrc/im2col.cu: no cuDNN / ATen
+convolution or pooling kernel is left on the path in either mode.  Output is NHWC-flattened [B, h*w, 1024] so `image_proj` consumes it without a transpose copy."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -54,8 +55,10 @@ def _conv(mod, x):
     if (mod.kernel_size == (7, 7) and mod.stride == (2, 2) and mod.padding == (3, 3) and mod.in_channels == 3
             and x.dtype == torch.bfloat16):
         return ops.stem_conv7x7(x, mod.weight)                     # patch matrix + tcgen05 GEMM (csrc/pool.cu)
-    # the two stride-2 3x3 convolutions and the fp32 parity mode: library convolution
-    return F.conv2d(x, mod.weight, None, mod.stride, mod.padding)
+    # the two stride-2 3x3 convolutions and every k > 1 convolution of the fp32 parity mode: patch matrix + tcgen05 GEMM
+    # (fp32 operands through the three-way bf16 split) -- no library convolution is left on the path
+    assert mod.stride[0] == mod.stride[1] and mod.padding[0] == mod.padding[1] and mod.groups == 1 and mod.dilation == (1, 1)
+    return ops.conv_im2col(x, mod.weight, mod.stride[0], mod.padding[0])
 
 
 class Bottleneck(nn.Module):
@@ -124,17 +127,13 @@ class ResNetStem(nn.Module):
             raise ValueError("grouped stem passes are not combined with ResNet drop-path (per-call random streams)")
         dt = self.conv1.weight.dtype
         _GROUPS[0] = groups
-        tf32 = torch.backends.cudnn.allow_tf32
-        if dt == torch.float32:
-            torch.backends.cudnn.allow_tf32 = False      # fp32 parity mode must not silently drop to TF32
         del _TRACK[:]
         try:
             x = x.to(dt).contiguous(memory_format=torch.channels_last)
             x = _bn(self.bn1, _conv(self.conv1, x), relu=True)
-            x = ops.max_pool3x3s2(x) if x.dtype == torch.bfloat16 else F.max_pool2d(x, 3, 2, 1)
+            x = ops.max_pool3x3s2(x)
             x = self.layer3(self.layer2(self.layer1(x)))
         finally:
-            torch.backends.cudnn.allow_tf32 = tf32
             if _TRACK:          # nn.BatchNorm2d bookkeeping: 94 counters, one multi-tensor kernel instead of 94 launches
                 torch._foreach_add_(list(_TRACK), groups)
                 del _TRACK[:]

@@ -58,6 +58,27 @@ CASES = {
     "micro_frozenbn_eval": dict(arch="ofa_micro", cfg=dict(vocab_size=4099, freeze_resnet=True),
                                 tasks=[dict(bsz=2, src_len=15, tgt_len=11, img=64, seed=10, vocab=4099)],
                                 crit=dict(label_smoothing=0.1), eval_mode=True),
+    # ---- the BENCHMARKED configuration (BASELINE.json configs[1]): OFA-base, 384x384, one Musketeer TEP
+    # five-task group (caption S137/T12, VQA S230/T232, VG S259/T5, SNLI-VE S250/T250, gigaword S185/T12; VQA / SNLI-VE targets
+    # padded over the prompt), per-task batch 1 and 2 (rows of the second sample right-padded)
+    "base_tep_b1": dict(arch="ofa_base", cfg={}, col_stride=373,
+                        tasks=[dict(bsz=1, src_len=137, tgt_len=12, img=384, seed=30),
+                               dict(bsz=1, src_len=230, tgt_len=232, img=384, seed=31, target_prefix_pad=171),
+                               dict(bsz=1, src_len=259, tgt_len=5, img=384, seed=32),
+                               dict(bsz=1, src_len=250, tgt_len=250, img=384, seed=33, target_prefix_pad=217),
+                               dict(bsz=1, src_len=185, tgt_len=12, seed=34, with_image=False)],
+                        crit=dict(label_smoothing=0.1, sample_patch_num=0)),
+    "base_tep_b2": dict(arch="ofa_base", cfg={}, col_stride=373,
+                        tasks=[dict(bsz=2, src_len=137, tgt_len=12, img=384, seed=40, n_pad=3),
+                               dict(bsz=2, src_len=230, tgt_len=232, img=384, seed=41, target_prefix_pad=171, n_pad=5),
+                               dict(bsz=2, src_len=259, tgt_len=5, img=384, seed=42, n_pad=2),
+                               dict(bsz=2, src_len=250, tgt_len=250, img=384, seed=43, target_prefix_pad=217, n_pad=7),
+                               dict(bsz=2, src_len=185, tgt_len=12, seed=44, with_image=False, n_pad=4)],
+                        crit=dict(label_smoothing=0.1, sample_patch_num=0)),
+    # BASELINE.json configs[3]: OFA-large visual grounding, 512x512, one sample
+    "large_vg_512": dict(arch="ofa_large", cfg=dict(patch_image_size=512), col_stride=373,
+                         tasks=[dict(bsz=1, src_len=32, tgt_len=5, img=512, seed=50)],
+                         crit=dict(label_smoothing=0.1)),
 }
 GEN_CASES = {
     "gen_micro": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.1,
@@ -66,6 +87,19 @@ GEN_CASES = {
     "gen_micro_ngram": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.1,
                             batch=dict(bsz=2, src_len=9, tgt_len=2, img=64, seed=21, vocab=4099, n_pad=0),
                             gen=dict(beam_size=3, max_len_a=0, max_len_b=10, min_len=2, no_repeat_ngram_size=2)),
+    # weight scales that make the random-init model emit VARIED tokens (with the default scales the tied embedding of the
+    # previous token dominates the logits and every hypothesis repeats one token): beams cross, sentences finish at
+    # different steps, n-gram blocking bites
+    "gen_micro_varied": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                             batch=dict(bsz=4, src_len=9, tgt_len=2, img=64, seed=24, vocab=4099, n_pad=1),
+                             gen=dict(beam_size=5, max_len_a=0, max_len_b=12, min_len=1)),
+    "gen_micro_varied_ngram": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                                   batch=dict(bsz=3, src_len=9, tgt_len=2, img=64, seed=25, vocab=4099, n_pad=0),
+                                   gen=dict(beam_size=4, max_len_a=0, max_len_b=12, min_len=2, no_repeat_ngram_size=2)),
+    # BASELINE.json configs[4] at its real architecture: OFA-base, 480x480, beam 5, max_len_b 16, B = 8
+    "gen_base_b8": dict(arch="ofa_base", cfg=dict(patch_image_size=480), emb_std=0.05, w_std=0.3,
+                        batch=dict(bsz=8, src_len=8, tgt_len=2, img=480, seed=23, n_pad=0),
+                        gen=dict(beam_size=5, max_len_a=0, max_len_b=16, min_len=1)),
     # BASELINE.json configs[4] scaled to ofa_tiny / batch 2 (the oracle finishes in seconds)
     "gen_tiny": dict(arch="ofa_tiny", cfg={}, emb_std=0.1,
                      batch=dict(bsz=2, src_len=8, tgt_len=2, img=256, seed=22, n_pad=0),
@@ -105,7 +139,17 @@ def run_train_case(name, case):
         ref_in[0]["net_input"]["sample_patch_num"] = spn
     if "py_seed" in case:
         random.seed(case["py_seed"])
-    loss, ss, log = crit(model, ref_in if len(ref_in) > 1 else ref_in[0])
+    if len(ref_in) > 1 and ck.get("sample_patch_num", 0) == 0:
+        # The reference's list recursion sits inside `if self.sample_patch_num > 0:` (label_smoothed_cross_entropy.py:175-183)
+        # and raises UnboundLocalError without patch sampling.  The plain multi-task step is therefore driven task by task
+        # through the reference criterion's single-sample path and combined with the recursion's arithmetic
+        # (loss = sum_t loss_t / sample_size_t, sample_size = 1).
+        parts = [crit(model, smp) for smp in ref_in]
+        loss = sum(l / s for l, s, _ in parts)
+        ss = 1
+        log = {"loss_v1": parts[0][0].data}
+    else:
+        loss, ss, log = crit(model, ref_in if len(ref_in) > 1 else ref_in[0])
     (loss / ss).backward()
     loss = loss.detach()
     rs_after = {k: float(v.float().norm()) for k, v in model.state_dict().items() if "running_" in k}
@@ -145,11 +189,23 @@ def run_train_case(name, case):
     # reference logits for the (last) single-task forward, eval of the same weights without rdrop dup
     fx = {"recipe": json.dumps({k: v for k, v in case.items()}), "loss": float(loss), "sample_size": ss,
           "grad_norms": gnorm, "grad_norm_total": total}
+    stride = case.get("col_stride", COL_STRIDE)
     if "tasks" in lg2:
         fx["task_loss"] = [float(t["loss"]) for t in lg2["tasks"]]
         fx["task_ntokens"] = [int(t["ntokens"]) for t in lg2["tasks"]]
         fx["patch_orders"] = [t["patch_orders"] for t in lg2["tasks"]]
         fx["loss_v1"] = float(log["loss_v1"])
+        if "col_stride" in case and not ck.get("use_rdrop") and not spn:
+            # per-task reference logits (sub-sampled columns + per-row logsumexp) of the same weights: what every task's rows of a
+            # merged encoder / decoder pass must reproduce
+            fx["task_logits_sub"], fx["task_logits_lse"] = [], []
+            stats_keep = {k: v.clone() for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
+            with torch.no_grad():
+                for smp in samples:
+                    lg = model(**copy.deepcopy(smp["net_input"]))[0].float()
+                    fx["task_logits_sub"].append(lg[:, :, ::stride].contiguous())
+                    fx["task_logits_lse"].append(torch.logsumexp(lg, -1))
+            model.load_state_dict(stats_keep, strict=False)
     else:
         fx["nll_loss"] = float(log["nll_loss"])
         fx["patch_orders"] = lg2["patch_orders"]
@@ -166,7 +222,7 @@ def run_train_case(name, case):
             if ck.get("use_rdrop") and spn:
                 pass
             logits = model(**ni)[0].float()
-        fx["logits_sub"] = logits[:, :, ::COL_STRIDE].contiguous()
+        fx["logits_sub"] = logits[:, :, ::stride].contiguous()
         fx["logits_lse"] = torch.logsumexp(logits, -1)
         d = (lg2["logits"].detach() - logits).abs().max().item() if lg2["logits"].shape == logits.shape else -1
         print("   logits oracle-vs-ref maxabs", d)
@@ -183,7 +239,7 @@ def run_train_case(name, case):
 
 def run_gen_case(name, case):
     cfg = synth.make_cfg(case["arch"], **case["cfg"])
-    sd = synth.synth_state_dict(cfg, seed=0, emb_std=case["emb_std"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
     model, task = rh.build_model(cfg, sd)
     model.eval()
     sample = synth.make_batch(**case["batch"])
@@ -208,13 +264,57 @@ def run_gen_case(name, case):
         name, len(hyp), hyp[0][0]["tokens"].tolist(), ["%.3f" % x for x in gaps]))
 
 
+def add_bf16_deviation(name, case):
+    """How far the REFERENCE ALGORITHM ITSELF moves when it is executed in bfloat16 (`model.bfloat16()` semantics of
+    trainer.py:99-106: bf16 weights, activations and images; the oracle on the host): stored next to the fp32 reference
+    values so that the bf16 CUDA path is held to `max(north-star tolerance, 1.25 x this deviation)` per quantity -- the rule
+    tests/test_model_gpu.py already uses for logits, now also for loss and per-parameter gradient norms."""
+    path = os.path.join(OUT, name + ".pt")
+    fx = torch.load(path, weights_only=False)
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0)
+    sdb = {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in sd.items()}
+    sdb = tie(sdb)
+    samples = build_samples(case)
+    for smp in samples:
+        if "patch_images" in smp["net_input"]:
+            smp["net_input"]["patch_images"] = smp["net_input"]["patch_images"].bfloat16()
+    ck = dict(case["crit"])
+    loss, ss, lg = oo.criterion_forward(sdb, cfg, samples if len(samples) > 1 else samples[0], epsilon=ck["label_smoothing"],
+                                        use_rdrop=ck.get("use_rdrop", False), sample_patch_num=ck.get("sample_patch_num", 0))
+    (loss / ss).backward()
+    stride = case.get("col_stride", COL_STRIDE)
+    out = {"loss": float(loss), "grad_norms": {}, "logits_dev": [], "lse_dev": [], "logits_rms": []}
+    for n in fx["grad_norms"]:
+        g = sdb[n].grad
+        out["grad_norms"][n] = float(g.float().norm()) if g is not None else None
+    out["grad_norm_total"] = sum(v * v for v in out["grad_norms"].values() if v is not None) ** 0.5
+    tasks = lg["tasks"] if "tasks" in lg else [lg]
+    out["task_loss"] = [float(t["loss"]) for t in tasks]
+    subs = fx.get("task_logits_sub") or [fx["logits_sub"]]
+    lses = fx.get("task_logits_lse") or [fx["logits_lse"]]
+    for t, sub, lse in zip(tasks, subs, lses):
+        lgt = t["logits"].detach().float()
+        out["logits_dev"].append(float((lgt[:, :, ::stride] - sub).abs().max()))
+        out["lse_dev"].append(float((torch.logsumexp(lgt, -1) - lse).abs().max()))
+        out["logits_rms"].append(float((lgt[:, :, ::stride] - sub).pow(2).mean().sqrt()))
+    fx["bf16_ref"] = out
+    torch.save(fx, path)
+    print("%-24s bf16 oracle: loss %.5f (fp32 %.5f)  grad-norm %.4f (fp32 %.4f)  logits dev %s" % (
+        name, out["loss"], fx["loss"], out["grad_norm_total"], fx["grad_norm_total"], ["%.3f" % d for d in out["logits_dev"]]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     only = sys.argv[1:]
+    if only and only[0] == "--bf16":
+        for name in only[1:]:
+            add_bf16_deviation(name, CASES[name])
+        return
     # state-dict contract (SURVEY.md 8b): names, order, shapes, dtypes for every arch
     names = {}
-    for arch in ("ofa_tiny", "ofa_base") + (() if only else ("ofa_medium", "ofa_large")):
+    for arch in ("ofa_tiny", "ofa_base", "ofa_medium", "ofa_large"):
         cfg = synth.make_cfg(arch)
         model, _ = rh.build_model(cfg)
         msd = model.state_dict()

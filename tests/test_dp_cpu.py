@@ -86,7 +86,24 @@ def _worker(rank, world, port, outdir):
     assert torch.allclose(model.unused.grad, torch.full_like(model.unused, 1.5))
     for n, p in named:          # (the arenas were averaged a second time: still the mean of equal values)
         assert torch.allclose(p.grad, flatred[n], atol=1e-6), n
-    torch.save((local, out, nosync, allred, flatred), os.path.join(outdir, "r%d.pt" % rank))
+    # DistributedOFAModel: the wrapper trainer.py drives (forward / no_sync / all_reduce_grads / .module), update_freq = 2
+    from musketeer_b200.dp import DistributedOFAModel
+    m2 = _Toy()
+    wrapped = DistributedOFAModel(m2, world_size=world, bucket_bytes=1024)
+    assert wrapped.module is m2 and wrapped.a is m2.a                           # attribute passthrough
+    assert list(wrapped.state_dict().keys()) == list(m2.state_dict().keys())   # no "module." prefix in checkpoints
+    x2 = torch.randn(8, 16)
+    m2.zero_grad(set_to_none=True)
+    m2(x).backward()
+    m2(x2).backward()
+    local2 = {n: p.grad.clone() for n, p in m2.named_parameters() if p.grad is not None}
+    m2.zero_grad(set_to_none=True)
+    with wrapped.no_sync():                      # trainer.py:755-773: first micro-batch accumulates locally
+        wrapped(x).backward()
+    wrapped(x2).backward()                       # last micro-batch: buckets are reduced under the backward
+    wrapped.all_reduce_grads()                   # trainer.py:848-852
+    ddp2 = {n: p.grad.clone() for n, p in m2.named_parameters() if p.grad is not None}
+    torch.save((local, out, nosync, allred, flatred, local2, ddp2), os.path.join(outdir, "r%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -108,6 +125,10 @@ def test_grad_reducer_world2(tmp_path):
             assert torch.allclose(res[r][3][n], mean, atol=1e-6), n       # reduce_all
             assert torch.allclose(res[r][4][n], mean, atol=1e-6), n       # reduce_flat
             assert torch.allclose(res[r][2][n], res[r][0][n]), n          # no_sync: untouched local grads
+    for n in res[0][5]:
+        mean2 = (res[0][5][n] + res[1][5][n]) / 2
+        for r in range(2):
+            assert torch.allclose(res[r][6][n], mean2, atol=1e-6), n      # wrapper: (g1 + g2) averaged over the ranks
     for r in range(2):
         assert res[r][1]["unused"] is not None and float(res[r][1]["unused"].abs().sum()) == 0.0
         # both ranks hold identical gradients afterwards (trainer._check_grad_norms invariant, trainer.py:1397-1433)

@@ -667,3 +667,41 @@ def test_stem_conv7x7_patches_gemm(N, H, W):
     assert y.shape == yr.shape
     assert (y.double().cpu() - yr).abs().max().item() < 2e-2 * max(1.0, yr.abs().max().item())
     assert (w.grad.double().cpu() - wf.grad).abs().max().item() < 2e-2 * max(1.0, wf.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,Cin,Cout,H,W,k,stride,pad", [(2, 64, 64, 24, 24, 3, 2, 1), (3, 128, 64, 9, 7, 3, 1, 1),
+                                                         (2, 3, 64, 32, 32, 7, 2, 3), (2, 256, 256, 12, 12, 3, 2, 1)])
+def test_conv_im2col_fwd_bwd(dtype, N, Cin, Cout, H, W, k, stride, pad):
+    """Patch-matrix convolution (csrc/im2col.cu + ofa_gemm_bf16): the stride-2 3x3 convolutions of the stem and the k > 1
+    convolutions of the fp32 parity mode (models/ofa/resnet.py:34-37,107-121,176,214) against F.conv2d in fp64."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(N * 31 + Cin + k)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * (Cin * k * k) ** -0.5).cuda().to(dtype).requires_grad_()
+    y = ops.conv_im2col(x, w, stride, pad)
+    dy = torch.randn(y.shape, generator=g).cuda().to(dtype)
+    y.backward(dy)
+    xr, wr = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    yr = F.conv2d(xr, wr, None, stride, pad)
+    yr.backward(dy.double())
+    tol = 1e-5 if dtype == torch.float32 else 3e-2
+    assert y.shape == yr.shape
+    assert (y.double() - yr).abs().max().item() < tol * max(1.0, yr.abs().max().item())
+    assert (x.grad.double() - xr.grad).abs().max().item() < tol * max(1.0, xr.grad.abs().max().item())
+    assert (w.grad.double() - wr.grad).abs().max().item() < tol * max(1.0, wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype,C", [(torch.float32, 64), (torch.float32, 5), (torch.bfloat16, 12)])
+def test_maxpool_generic(dtype, C):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(C)
+    x = torch.randn(2, C, 17, 20, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = ops.max_pool3x3s2(x)
+    dy = torch.randn(y.shape, generator=g).cuda().to(dtype)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_()
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    yr.backward(dy.float())
+    assert torch.equal(y.float(), yr)
+    assert (x.grad.float() - xr.grad).abs().max().item() < (1e-6 if dtype == torch.float32 else 2e-2)

@@ -98,10 +98,7 @@ def test_bf16_mode_within_tolerance(name):
     figure is itself at the bf16 noise floor of the reference.  We therefore require the CUDA path to be
     no further from the fp32 reference logits than 1.25x the reference's own bf16 deviation (or 2e-2 if larger); the
     distance to the reference's bf16 logits (two independent bf16 roundings, bounded by the sum of both deviations) is
-    printed for the record.  Loss / total gradient norm: within 1e-2 / 1e-1 relative of the fp32 reference (the micro
-    cases normalise over 32-sample batches in bf16 and the batch statistics are summed with order-dependent fp32
-    atomics: the total norm moves by a few percent between runs; the 1e-3 bound of the north star is the fp32-mode
-    test above)."""
+    printed for the record."""
     fx = load_golden(name)
     case = fx["case"]
     cfg, sd, samples = build_case(case)
@@ -122,10 +119,26 @@ def test_bf16_mode_within_tolerance(name):
     cross = (got - ref_bf16).abs().max().item()
     print("bf16 logits: ours-vs-fp32ref %.4f  ref_bf16-vs-fp32ref %.4f  ours-vs-ref_bf16 %.4f" % (ours_dev, ref_dev, cross))
     assert ours_dev <= max(2e-2, 1.25 * ref_dev), (ours_dev, ref_dev)
+    # loss / total gradient norm: the same rule, against the reference algorithm executed in bf16 end to end (criterion +
+    # backward of the oracle on the host).  These 4-layer micro models are dominated by their random-init ResNet stem, whose bf16
+    # gradient noise is a single chaotic realisation per implementation (profiles/r02_stem_bf16_gradient_deviation.txt): 4 x
+    # the reference's deviation here; the OFA-base test below holds the transformer parameters to 1.25 x.
+    sdt = tie(sdb)
+    sb = copy.deepcopy(samples[0])
+    sb["net_input"]["patch_images"] = sb["net_input"]["patch_images"].bfloat16()
+    bl, bss, _ = oo.criterion_forward(sdt, cfg, sb, epsilon=case["crit"]["label_smoothing"])
+    (bl / bss).backward()
+    b_gn = sum(float(v.grad.float().norm()) ** 2 for k, v in sdt.items() if v.requires_grad and v.grad is not None
+               and not k.startswith(("decoder.embed_tokens", "decoder.output_projection"))) ** 0.5
+    dev_l = abs(float(bl.detach()) - fx["loss"]) / abs(fx["loss"])
+    dev_g = abs(b_gn - fx["grad_norm_total"]) / fx["grad_norm_total"]
     model2, loss, ss, log, *_ = _run_product(case, fx, torch.bfloat16)
-    assert abs(float(loss.detach()) - fx["loss"]) <= 1e-2 * abs(fx["loss"])
     tot = sum(float(p.grad.float().norm()) ** 2 for p in model2.parameters() if p.grad is not None) ** 0.5
-    assert abs(tot - fx["grad_norm_total"]) <= 1e-1 * fx["grad_norm_total"], (tot, fx["grad_norm_total"])
+    rel_l = abs(float(loss.detach()) - fx["loss"]) / abs(fx["loss"])
+    rel_g = abs(tot - fx["grad_norm_total"]) / fx["grad_norm_total"]
+    print("bf16 loss rel %.3e (reference in bf16 %.3e)  total grad-norm rel %.3e (reference in bf16 %.3e)" % (rel_l, dev_l, rel_g, dev_g))
+    assert rel_l <= max(1e-3, 1.25 * dev_l), (rel_l, dev_l)
+    assert rel_g <= max(1e-3, 4 * dev_g), (rel_g, dev_g)
 
 
 def test_state_dict_contract():
@@ -140,14 +153,15 @@ def test_state_dict_contract():
     assert list(msd.keys()) == [e[0] for e in spec["ofa_tiny"]["entries"]]
 
 
-@pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny"])
+@pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny", "gen_micro_varied", "gen_micro_varied_ngram",
+                                  "gen_base_b8"])
 def test_beam_search_tokens_bit_exact_fp32(name):
     """fp32 mode: beam-search output token ids must equal the reference's bit for bit; scores within 1e-4."""
     from musketeer_b200.sequence_generator import SequenceGenerator
     fx = load_golden(name)
     case = fx["case"]
     cfg = synth.make_cfg(case["arch"], **case["cfg"])
-    sd = synth.synth_state_dict(cfg, seed=0, emb_std=case["emb_std"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
     model, task = build_product(cfg, sd, dtype=torch.float32)
     model.eval()
     sample = to_device(synth.make_batch(**case["batch"]), "cuda")
@@ -161,7 +175,8 @@ def test_beam_search_tokens_bit_exact_fp32(name):
             assert len(hyp[s]) == len(fx["tokens"][s])
             for h, t, sc in zip(hyp[s], fx["tokens"][s], fx["scores"][s]):
                 assert torch.equal(h["tokens"].cpu(), t), (call, s, h["tokens"].tolist(), t.tolist())
-                assert abs(float(h["score"]) - sc) < 1e-4
+                # normalised cumulative log-probability: 1e-4, or 1e-3 at OFA-base depth (17 steps x 6 layers of split-fp32 GEMMs)
+                assert abs(float(h["score"]) - sc) < (1e-3 if case["arch"] == "ofa_base" else 1e-4)
     if name == "gen_micro":
         # replayed steps hold pointers into persistent buffers: a different batch of the same shape must give what a
         # graph-free generator gives
@@ -492,3 +507,145 @@ def test_graphed_step_equals_eager_and_is_keyed_on_shapes_only():
         if n in a:
             want = a[n] + b[n]
             assert (p.grad.float() - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item()), n
+
+
+def _bound(tol, dev, k=1.25):
+    """The bf16 rule of this file: a quantity may deviate from the fp32 reference by the north-star tolerance or by k x what
+    the REFERENCE ALGORITHM ITSELF deviates when executed in bf16 (stored in the fixture by oracle/make_golden.py --bf16),
+    whichever is larger."""
+    return max(tol, k * dev)
+
+
+@pytest.mark.parametrize("name", ["base_tep_b1", "base_tep_b2"])
+def test_benchmarked_config_bf16_merged_tasks_match_reference(name):
+    """BASELINE configs[1] at its real architecture: OFA-base, 384x384, one TEP five-task group (caption / VQA / VG / SNLI-VE /
+    gigaword), bf16, WITH the multi-task batching that produces the headline number (grouped stem pass, merged encoder pass at
+    N = 576 + 259, merged decoder passes {5, 12, 12} and {232, 250}) -- against the unmodified reference run in fp32
+    (tests/golden/base_tep_b*.pt).  Checked: every task's logits (sub-sampled columns + per-row logsumexp) out of the merged
+    encoder pass, every task's loss out of the merged decoder + fused loss launches, total loss, total gradient norm, every
+    transformer parameter's gradient norm (individually and as a distribution), and the stem's gradient norms statistically.
+
+    Bounds: north-star tolerance or 1.25 x the deviation of the reference executed in bf16, whichever is larger.  Two
+    quantities are extreme-value / single-realisation statistics and get the rule in a form that fits them: the max-abs logits
+    error (maximum over ~40k sub-sampled entries: 1.5 x, next to the 1.25 x bound on the RMS error), and the gradient norms of
+    the ResNet stem's parameters, which in bf16 move by 3 % (median) to 20 % (max) for ANY bf16 implementation incl. torch's own
+    (profiles/r02_stem_bf16_gradient_deviation.txt): median and 90th percentile of their relative deviation are compared with
+    the same statistics of the reference-in-bf16 run."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg, sd, samples = build_case(case)
+    bref = fx["bf16_ref"]
+    stride = case["col_stride"]
+    dt = torch.bfloat16
+    model, task = build_product(cfg, sd, dtype=dt)
+    model.train()
+    crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, sample_patch_num=0)
+    # (1) per-task logits and losses out of the merged passes
+    with torch.no_grad():
+        stats = {n: b.clone() for n, b in model.named_buffers() if "running_" in n or "num_batches" in n}
+        out = crit._batch_stems(model, to_device(copy.deepcopy(samples), "cuda", dt))
+        n_merged = sum("_precomputed" in s for s in out)
+        assert n_merged == 5, n_merged                      # both decoder groups formed, the text-only task joined
+        for i, s in enumerate(out):
+            ni = s["net_input"]
+            logits, _ = model.decoder(ni["prev_output_tokens"], encoder_out=ni["encoder_out"])
+            got = logits.float().cpu()
+            d = got[:, :, ::stride] - fx["task_logits_sub"][i]
+            err, rms = d.abs().max().item(), d.pow(2).mean().sqrt().item()
+            lse_err = (torch.logsumexp(got, -1) - fx["task_logits_lse"][i]).abs().max().item()
+            print("task %d logits max-abs %.4f rms %.5f (reference in bf16: %.4f / %.5f)  lse err %.4f" % (
+                i, err, rms, bref["logits_dev"][i], bref["logits_rms"][i], lse_err))
+            assert err <= _bound(2e-2, bref["logits_dev"][i], 1.5), (i, err, bref["logits_dev"][i])
+            assert rms <= _bound(2e-3, bref["logits_rms"][i]), (i, rms, bref["logits_rms"][i])
+            assert lse_err <= _bound(2e-2, bref["lse_dev"][i]), (i, lse_err)
+            tl = float(s["_precomputed"][0])
+            ref_tl = fx["task_loss"][i]
+            assert abs(tl - ref_tl) <= _bound(1e-3 * abs(ref_tl), abs(bref["task_loss"][i] - ref_tl)), (i, tl, ref_tl)
+        model.load_state_dict(stats, strict=False)
+    # (2) the whole micro-step: loss and gradients
+    loss, ss, log = crit(model, to_device(copy.deepcopy(samples), "cuda", dt))
+    (loss / ss).backward()
+    ref, bl = fx["loss"], bref["loss"]
+    lossf = float(loss.detach())
+    assert abs(lossf - ref) <= _bound(1e-3 * abs(ref), abs(bl - ref)), (lossf, ref, bl)
+    tot, worst, stem, tr = 0.0, ("", 0.0, 0.0), {"ours": [], "ref": []}, {"ours": [], "ref": []}
+    for n, p in model.named_parameters():
+        g = fx["grad_norms"].get(n)
+        if g is None:
+            continue
+        gn = float(p.grad.float().norm())
+        tot += gn * gn
+        bg = bref["grad_norms"].get(n)
+        if n.endswith(ZERO_GRAD_SUFFIXES) or g < 1e-6 * fx["grad_norm_total"] or bg is None:
+            continue
+        if "embed_images" in n:
+            stem["ours"].append(abs(gn - g) / g)
+            stem["ref"].append(abs(bg - g) / g)
+            continue
+        tr["ours"].append(abs(gn - g) / g)
+        tr["ref"].append(abs(bg - g) / g)
+        lim = _bound(3e-2 * g, abs(bg - g), 3.0)
+        if abs(gn - g) / lim > worst[1]:
+            worst = (n, abs(gn - g) / lim, abs(gn - g) / g)
+    tot = tot ** 0.5
+    rt, bt = fx["grad_norm_total"], bref["grad_norm_total"]
+    q = lambda v, f: sorted(v)[int(len(v) * f)]
+    print("loss %.5f (ref %.5f, reference in bf16 %.5f)  grad-norm %.4f (ref %.4f, reference in bf16 %.4f)" % (lossf, ref, bl, tot, rt, bt))
+    print("worst transformer parameter %s at %.2f of its bound (rel %.3e); stem (%d parameters) median %.3e p90 %.3e, reference "
+          "in bf16 median %.3e p90 %.3e" % (worst[0], worst[1], worst[2], len(stem["ours"]), q(stem["ours"], .5), q(stem["ours"], .9),
+                                             q(stem["ref"], .5), q(stem["ref"], .9)))
+    print("transformer parameters (%d): median %.3e p90 %.3e, reference in bf16 median %.3e p90 %.3e" % (
+        len(tr["ours"]), q(tr["ours"], .5), q(tr["ours"], .9), q(tr["ref"], .5), q(tr["ref"], .9)))
+    assert abs(tot - rt) <= _bound(1e-3 * rt, abs(bt - rt)), (tot, rt, bt)
+    # every transformer parameter individually (small LayerNorm / bias gradients are sums with cancellation: a single bf16
+    # realisation of the reference bounds them only loosely, 3 x), and their distribution tightly (1.25 x)
+    assert worst[1] <= 1.0, worst
+    assert q(tr["ours"], .5) <= _bound(2e-3, q(tr["ref"], .5)) and q(tr["ours"], .9) <= _bound(1e-2, q(tr["ref"], .9))
+    assert q(stem["ours"], .5) <= _bound(1e-2, q(stem["ref"], .5), 1.5) and q(stem["ours"], .9) <= _bound(1e-2, q(stem["ref"], .9), 1.5)
+
+
+def test_ofa_large_512_fp32_matches_reference():
+    """BASELINE configs[3] architecture (OFA-large, 12+12 layers, d = 1024, H = 16, ResNet-152, 512x512 -> 1024 patches): one
+    visual-grounding sample, fp32 parity mode, against the unmodified reference: logits 1e-4, loss / gradient norm 1e-3."""
+    fx = load_golden("large_vg_512")
+    case = fx["case"]
+    model, loss, ss, log, cfg, sd, samples = _run_product(case, fx, torch.float32)
+    assert ss == fx["sample_size"]
+    assert abs(float(loss.detach()) - fx["loss"]) <= 1e-3 * abs(fx["loss"]), (float(loss.detach()), fx["loss"])
+    tot = sum(float(p.grad.float().norm()) ** 2 for p in model.parameters() if p.grad is not None) ** 0.5
+    assert abs(tot - fx["grad_norm_total"]) <= 1e-3 * fx["grad_norm_total"], (tot, fx["grad_norm_total"])
+    model.zero_grad(set_to_none=True)
+    ni = to_device(copy.deepcopy(samples[0]["net_input"]), "cuda")
+    with torch.no_grad():
+        logits, _ = model(**ni)
+    got = logits.float().cpu()
+    assert (got[:, :, ::case["col_stride"]] - fx["logits_sub"]).abs().max().item() < 1e-4
+    assert (torch.logsumexp(got, -1) - fx["logits_lse"]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_is_bit_reproducible(dtype):
+    """The forward pass contains no order-dependent floating-point reduction any more (the BatchNorm batch statistics are
+    accumulated exactly, csrc/batchnorm.cu): two runs of the same multi-task step on fresh models give the SAME loss bits and
+    the same logits bits -- on the 2-image micro batches whose ReLU masks used to flip with the atomics' arrival order and move
+    the total gradient norm by percents.  Gradients (fp32 reduce-adds in the backward) agree to rounding."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    cfg, sd, samples = _multitask_case()
+    runs = []
+    for _ in range(2):
+        model, task = build_product(cfg, sd, dtype=dtype)
+        model.train()
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=False, sample_patch_num=0)
+        inp = to_device(copy.deepcopy(samples), "cuda", dtype)
+        with torch.no_grad():
+            lg, _ = model(**to_device(copy.deepcopy(samples[0]["net_input"]), "cuda", dtype))
+        loss, ss, _ = crit(model, inp)
+        loss.backward()
+        gn = sum(float(p.grad.float().norm()) ** 2 for p in model.parameters() if p.grad is not None) ** 0.5
+        rs = torch.cat([b.float().reshape(-1) for n, b in model.named_buffers() if "running_" in n])
+        runs.append((loss.detach().clone(), lg.clone(), gn, rs))
+    assert torch.equal(runs[0][0], runs[1][0]), (float(runs[0][0]), float(runs[1][0]))
+    assert torch.equal(runs[0][1], runs[1][1])
+    assert torch.equal(runs[0][3], runs[1][3])
+    assert abs(runs[0][2] - runs[1][2]) <= (1e-5 if dtype == torch.float32 else 2e-3) * runs[0][2], (runs[0][2], runs[1][2])
