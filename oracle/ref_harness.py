@@ -1,7 +1,9 @@
-"""Runs the UNMODIFIED reference hot-path files from /root/reference through `oracle/ref_shim`.
+"""Runs the UNMODIFIED reference hot-path files through `oracle/ref_shim`.
 
-TEST INFRASTRUCTURE ONLY; usable only where the reference tree is present (this container).
-It is what pins the oracle restatement (`oracle/ofa_oracle.py`) and produces `tests/golden/`.
+TEST INFRASTRUCTURE ONLY.  The reference tree is looked up in $MUSKETEER_REF, /root/reference (the build container) and
+baseline/_ref (a byte-for-byte copy of the files this path needs, made by tools/install_reference.py; git-ignored, it
+travels to the GPU box with the snapshot).  It is what pins the oracle restatement (`oracle/ofa_oracle.py`), produces
+`tests/golden/`, and is timed as the reference arm of bench.py.
 """
 import importlib
 import importlib.util
@@ -11,8 +13,18 @@ import types
 
 import torch
 
-REF = os.environ.get("MUSKETEER_REF", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "ref_shim")
+
+
+def _find_ref():
+    for c in (os.environ.get("MUSKETEER_REF"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "models", "ofa")):
+            return c
+    return os.environ.get("MUSKETEER_REF", "/root/reference")
+
+
+REF = _find_ref()
 
 
 def available():
