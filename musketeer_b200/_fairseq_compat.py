@@ -1,6 +1,6 @@
 """The fairseq base classes and registries the OFA plugin binds to.
 
-With fairseq importable (a real training environment, or the test shim under oracle/ref_shim on sys.path) the names below
+With fairseq importable (a real training environment, or the stand-in package the tests put on sys.path) the names below
 ARE fairseq's: `OFAModel` is then a `FairseqEncoderDecoderModel`, its decoder a `FairseqIncrementalDecoder` (the reference
 generator gates incremental decoding on that: models/sequence_generator.py:776-781), the criterion a `FairseqCriterion`
 (real `register_criterion` rejects anything else), and `register_model("ofa")` / `register_model_architecture` /

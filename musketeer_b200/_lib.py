@@ -135,10 +135,40 @@ LAUNCHES = 0          # number of C-ABI kernel entry calls (each launches >= 1 k
 PROFILE = None        # when a dict: name -> list of (start_event, end_event, work) recorded on the launching stream
 
 
+# NVTX ranges around every C-ABI launch (the reference wraps its step in record_function / emit_nvtx scopes: ofa_task.py:337-346,
+# train.py:537-540): on when OFA_NVTX=1, after set_nvtx(True), or whenever a torch profiler / emit_nvtx context is active.
+NVTX = bool(int(os.environ.get("OFA_NVTX", "0")))
+
+
+def set_nvtx(enabled):
+    global NVTX
+    NVTX = bool(enabled)
+
+
+def _nvtx_on():
+    if NVTX:
+        return True
+    try:
+        import torch
+        return torch.autograd._profiler_enabled()
+    except Exception:
+        return False
+
+
 def call(name, *args, work=None):
     global LAUNCHES
     lib = load()
     LAUNCHES += 1
+    if _nvtx_on():
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(lib, name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        if rc != 0:
+            raise OfaKernelError("%s: %s" % (name, lib.ofa_last_error().decode()))
+        return
     if PROFILE is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -306,16 +306,20 @@ class _Linear(torch.autograd.Function):
         w = w.reshape(N, -1)
         r2 = resid.reshape(-1, N) if resid is not None else None
         ldd = _ceil8(N) if out_pad else N
-        y = gemm(x2, w, M, N, K, bias=b, alpha=alpha, resid=r2, ldd=ldd)
+        if ldd == N:
+            # the result is allocated in its final shape and handed out as is (not as a view made inside this Function): callers
+            # may modify it in place -- the reference criterion masks the logits it gets back (label_smoothed_cross_entropy.py:233-236)
+            yn = torch.empty(*shp[:-1], N, dtype=x2.dtype, device=x2.device)
+            gemm(x2, w, M, N, K, bias=b, alpha=alpha, resid=r2, out=yn.view(M, N))
+        else:
+            yn = gemm(x2, w, M, N, K, bias=b, alpha=alpha, resid=r2, ldd=ldd)[:, :N].reshape(*shp[:-1], N)
         ctx.save_for_backward(x2, w)
         ctx.bias_param = b
         ctx.alpha, ctx.has_b, ctx.has_r, ctx.shp = alpha, b is not None, resid is not None, shp
-        if ldd != N:
-            y = y[:, :N]
         ctx.set_materialize_grads(False)
         if fork:        # second output = x: the branch that bypasses this projection; its gradient is added in the dgrad epilogue
-            return y.reshape(*shp[:-1], N), x
-        return y.reshape(*shp[:-1], N)
+            return yn, x
+        return yn
 
     @staticmethod
     def backward(ctx, dy, dskip=None):
