@@ -120,18 +120,57 @@ int ofa_conv3x3_wgrad_bf16(const void* x, const void* dy, void* dw, int NI, int 
  * key padding kpm, fp32 softmax, out = P V * head_scale.  ofa_cache_gather: dst[p][r][:L] = src[p][order[r]][:L] over all
  * (layer, k|v) planes p in one launch (beam reorder of the self-attention cache; only the L valid positions move).     */
 typedef struct OfaDecodeArgs {
-  const void* q; const void* pq; long long ldq, ldpq;
+  const void* q; const void* pq; long long ldq, ldpq;   /* pq / pk NULL (together): no absolute-position term in this launch */
   const void* k; const void* v; const void* pk;
   long long ldk, bsk, ldv, bsv, ldpk, bspk;      /* element (row, j, h*64+d) at row*bs + j*ld + h*64 + d */
   const int* kv_row; const int* pk_row;          /* [ceil(R/G)] cache rows (NULL: group index / kv_row) */
   const unsigned char* kpm; long long kpm_stride;
-  void* o; long long ldo;
-  const float* head_scale; const float* tok_lut; int tok_max; int q_pos;
+  void* o; long long ldo; const float* head_scale; const float* tok_lut; int tok_max; int q_pos;
   int R, G, H, S;
+  /* a score term shared by all layers (the cross-attention pos_q.pos_k^T: unify_transformer.py:1461-1466) is computed once per
+   * step by a launch with score_out set (raw scores, no softmax, v / o unused) and added by the layers' launches as bias_in;
+   * both [R][H][bias_ld] fp32 */
+  const float* bias_in; float* score_out; long long bias_ld;
+  /* paged K / V: key j of cache row r lives in page page_table[r*max_pages + j/page_len] at (j % page_len)*ld; page p starts
+   * at p*page_stride elements from k / v (NULL: contiguous rows) */
+  const int* page_table; int page_len, max_pages; long long page_stride;
 } OfaDecodeArgs;
 int ofa_attn_decode(const OfaDecodeArgs* args, int dtype, void* stream);
 int ofa_cache_gather(const void* src, void* dst, const long long* order, int rows, int L, int D, long long row_stride,
                      long long plane_stride, int planes, int dtype, void* stream);
+/* paged self-attention cache of the incremental decoder: pool [slot][plane = 2*layer + (k|v)][page_len][D].  A beam reorder
+ * (models/sequence_generator.py:337-350; the reference index_selects every K / V tensor, unify_multihead_attention.py:455-473)
+ * copies TABLE ENTRIES of the full, immutable pages and copies only the `off` valid positions of the partial last page into the
+ * row's own slot (r*max_pages + page)*2 + parity; ofa_page_write appends one layer's new K / V token of every row.           */
+int ofa_page_reorder(void* pool, const int* table_src, int* table_dst, const long long* order, int rows, int max_pages, int page,
+                     int off, int parity, int page_len, int D, int planes, int dtype, void* stream);
+int ofa_page_write(void* pool, const int* table, const void* k, const void* v, long long ldk, long long ldv, int rows,
+                   int max_pages, int page, int off, int page_len, int D, int planes, int plane_k, int dtype, void* stream);
+
+/* ---- one beam-search step after the decoder (models/sequence_generator.py:352-437,852-889; models/search.py:119-144):
+ * logits -> temperature -> constraint masks -> fp32 log-softmax -> min-len / max-len / pad / unk / n-gram / zero-shot masks ->
+ * + previous beam scores -> the K = 2*beam best (score, beam*V + token) per sentence, sorted.  Constraint trie as CSR
+ * (children of node n: trie_tok[trie_ptr[n] .. trie_ptr[n+1])) with the per-row node in `node` (-1: the prefix left the trie,
+ * only eos is allowed, utils/trie.py:23-30); ofa_trie_advance moves the nodes along the chosen tokens after a reorder.
+ * row_val / row_idx: workspace [R][ofa_beam_topk_width(K)].                                                                  */
+typedef struct OfaBeamArgs {
+  const void* logits; long long ld; int dtype;
+  int R, beam, V, K;
+  float temperature;
+  const float* prev_scores;            /* [R] or NULL */
+  int step0;                           /* 1: only the first beam of every sentence takes part */
+  int eos, pad, unk; float unk_penalty;
+  int block_eos, force_eos, eos_one;   /* step < min_len | step >= max_len | with force_eos: lprobs[eos] = 1 (ignore_eos) */
+  int range_lo, range_hi, range_post;  /* constraint range: keep tokens < 4 and [lo, hi); lo < 0: none; post: after the softmax */
+  const int* trie_ptr; const int* trie_tok; const int* node; int trie_post;
+  const long long* tokens; long long ldtok; int step; int ngram;   /* n-gram blocking over tokens[r][0..step]; ngram 0: off */
+  float* row_val; int* row_idx;
+  float* cand_scores; long long* cand_index;   /* [R/beam][K] */
+} OfaBeamArgs;
+int ofa_beam_topk(const OfaBeamArgs* args, void* stream);
+int ofa_beam_topk_width(int K);
+int ofa_trie_advance(const int* trie_ptr, const int* trie_tok, const int* trie_child, const int* node_in, const long long* parent,
+                     const long long* tok, long long tok_stride, int* node_out, int R, void* stream);
 
 /* ---- 3x3 / stride 2 / padding 1 max-pool of the stem on bf16 NHWC activations (models/ofa/resnet.py:179,216).  idx: one
  * byte per output element (window position of the first maximum); the backward gathers, no atomics.  C % 8 == 0.      */

@@ -38,7 +38,19 @@ class OfaDecodeArgs(C.Structure):
                 ("ldk", c_ll), ("bsk", c_ll), ("ldv", c_ll), ("bsv", c_ll), ("ldpk", c_ll), ("bspk", c_ll),
                 ("kv_row", c_p), ("pk_row", c_p), ("kpm", c_p), ("kpm_stride", c_ll),
                 ("o", c_p), ("ldo", c_ll), ("head_scale", c_p), ("tok_lut", c_p), ("tok_max", c_i), ("q_pos", c_i),
-                ("R", c_i), ("G", c_i), ("H", c_i), ("S", c_i)]
+                ("R", c_i), ("G", c_i), ("H", c_i), ("S", c_i),
+                ("bias_in", c_p), ("score_out", c_p), ("bias_ld", c_ll),
+                ("page_table", c_p), ("page_len", c_i), ("max_pages", c_i), ("page_stride", c_ll)]
+
+
+class OfaBeamArgs(C.Structure):
+    _fields_ = [("logits", c_p), ("ld", c_ll), ("dtype", c_i), ("R", c_i), ("beam", c_i), ("V", c_i), ("K", c_i),
+                ("temperature", c_f), ("prev_scores", c_p), ("step0", c_i), ("eos", c_i), ("pad", c_i), ("unk", c_i),
+                ("unk_penalty", c_f), ("block_eos", c_i), ("force_eos", c_i), ("eos_one", c_i),
+                ("range_lo", c_i), ("range_hi", c_i), ("range_post", c_i),
+                ("trie_ptr", c_p), ("trie_tok", c_p), ("node", c_p), ("trie_post", c_i),
+                ("tokens", c_p), ("ldtok", c_ll), ("step", c_i), ("ngram", c_i),
+                ("row_val", c_p), ("row_idx", c_p), ("cand_scores", c_p), ("cand_index", c_p)]
 
 
 # name -> argtypes, exactly the prototypes of include/ofa_b200.h
@@ -75,6 +87,11 @@ SIGNATURES = {
     "ofa_conv3x3_wgrad_bf16": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p],
     "ofa_attn_decode": [C.POINTER(OfaDecodeArgs), c_i, c_p],
     "ofa_cache_gather": [c_p, c_p, c_p, c_i, c_i, c_i, c_ll, c_ll, c_i, c_i, c_p],
+    "ofa_page_reorder": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "ofa_page_write": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "ofa_beam_topk": [C.POINTER(OfaBeamArgs), c_p],
+    "ofa_beam_topk_width": [c_i],
+    "ofa_trie_advance": [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_i, c_p],
     "ofa_maxpool3x3s2_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "ofa_maxpool3x3s2_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "ofa_subsample2": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -1,0 +1,303 @@
+// One beam-search step after the decoder: last-token logits -> (temperature, constraint masks) -> fp32 log-softmax ->
+// (min-len / max-len / pad / unk / n-gram / zero-shot masks) -> + cumulative beam scores -> top 2*beam candidates per sentence.
+// Replaces, per step, the ~15 ATen kernels of models/sequence_generator.py:352-437 (`forward_decoder` tail :852-889 incl. the
+// per-row Python trie walk `constraint_trie.get_next_layer(tokens.tolist())`, the masks :381-404, NGramRepeatBlock :425-426 --
+// a host loop over `tokens.cpu()` in fairseq -- and `BeamSearch.step` = models/search.py:119-144: topk over beam*V) by two
+// launches that read the logits once:
+//   beam_row_kernel   : one CTA per beam row.  Pass A: max / sum-exp over the softmax domain (whole vocabulary, a constraint
+//                       range, or the children of the row's trie node).  Pass B: every thread keeps its K best
+//                       (log-prob + previous score) in registers; banned tokens (pad, blocked eos, repeated n-grams, post-softmax
+//                       constraints) are a bit mask over the vocabulary in shared memory; K rounds of block arg-max emit the
+//                       row's K best, sorted.
+//   beam_merge_kernel : one warp per sentence merges beam x K candidates into the K best (value descending, flat index
+//                       ascending among equals), as int64 flat indices beam * V + token like torch.topk over [bsz, beam * V].
+//   trie_advance_kernel: per-row trie node after the beam reorder (node of the parent beam advanced by the chosen token).
+// HBM/L2-bound: R * V logits read twice from L2 (they were just written by the output GEMM).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+struct OfaBeamArgs {   // mirrored by musketeer_b200/_lib.py and include/ofa_b200.h
+  const void* logits; long long ld; int dtype;
+  int R, beam, V, K;
+  float temperature;
+  const float* prev_scores;
+  int step0;
+  int eos, pad, unk; float unk_penalty;
+  int block_eos, force_eos, eos_one;
+  int range_lo, range_hi, range_post;
+  const int* trie_ptr; const int* trie_tok; const int* node; int trie_post;
+  const long long* tokens; long long ldtok; int step; int ngram;
+  float* row_val; int* row_idx;
+  float* cand_scores; long long* cand_index;
+};
+
+namespace {
+
+constexpr int kT = 256;
+constexpr int KMAX = 16;
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p, long long i) { return (float)p[i]; }
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+// insert (v, i) into a descending sorted list of K entries held in registers
+template <int K>
+__device__ __forceinline__ void insert(float (&val)[K], int (&idx)[K], float v, int i) {
+  if (!better(v, i, val[K - 1], idx[K - 1])) return;
+  val[K - 1] = v; idx[K - 1] = i;
+#pragma unroll
+  for (int k = K - 1; k > 0; --k) {
+    if (better(val[k], idx[k], val[k - 1], idx[k - 1])) {
+      const float tv = val[k]; val[k] = val[k - 1]; val[k - 1] = tv;
+      const int ti = idx[k]; idx[k] = idx[k - 1]; idx[k - 1] = ti;
+    }
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
+  pdl_sync();
+  extern __shared__ uint32_t ban[];                 // bit per vocabulary entry: excluded from the candidates
+  __shared__ float red[kT / 32];
+  __shared__ float cv[kT / 32][K];
+  __shared__ int ci[kT / 32][K];
+  __shared__ float bcast;
+  const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int V = a.V;
+  float* out_v = a.row_val + (size_t)r * K;
+  int* out_i = a.row_idx + (size_t)r * K;
+  if (a.step0 && (r % a.beam) != 0) {               // step 0: every beam of a sentence is the same hypothesis (search.py:128-131)
+    if (t < K) { out_v[t] = -CUDART_INF_F; out_i[t] = 0x7fffffff; }
+    return;
+  }
+  const T* x = reinterpret_cast<const T*>(a.logits) + (size_t)r * a.ld;
+  const float inv_t = 1.f / a.temperature;
+  const int nw = (V + 31) / 32;
+  // allowed list of the trie node (-1 = dead prefix -> [eos]; utils/trie.py:23-30)
+  const int* al = nullptr;
+  int nal = -1;
+  int eos_only = 0;
+  if (a.node) {
+    const int nd = a.node[r];
+    if (nd < 0) eos_only = 1, nal = 1;
+    else { al = a.trie_tok + a.trie_ptr[nd]; nal = a.trie_ptr[nd + 1] - a.trie_ptr[nd]; }
+  }
+  const bool pre_list = nal >= 0 && !a.trie_post;
+  const bool pre_range = a.range_lo >= 0 && !a.range_post;
+  // ---- ban mask -----------------------------------------------------------------------------------------------------
+  const bool post_list = nal >= 0 && a.trie_post;
+  for (int w = t; w < nw; w += kT) ban[w] = post_list ? 0xffffffffu : 0u;
+  __syncthreads();
+  if (post_list) {
+    for (int e = t; e < nal; e += kT) { const int tok = eos_only ? a.eos : al[e]; atomicAnd(&ban[tok >> 5], ~(1u << (tok & 31))); }
+    __syncthreads();
+  }
+  if (a.range_lo >= 0 && a.range_post) {
+    for (int v = 4 + t; v < V; v += kT) if (v < a.range_lo || v >= a.range_hi) atomicOr(&ban[v >> 5], 1u << (v & 31));
+  }
+  if (t == 0) {
+    atomicOr(&ban[a.pad >> 5], 1u << (a.pad & 31));
+    if (a.block_eos) atomicOr(&ban[a.eos >> 5], 1u << (a.eos & 31));
+  }
+  if (a.ngram > 0 && a.step + 2 - a.ngram >= 0) {
+    // generated so far: tokens[r][0 .. step]; the last n-1 of them are the key, every earlier occurrence bans its successor
+    const long long* tk = a.tokens + (size_t)r * a.ldtok;
+    const int n = a.ngram, key0 = a.step + 2 - n;
+    for (int i = t; i + n - 1 <= a.step; i += kT) {
+      bool same = true;
+      for (int e = 0; e < n - 1; ++e) same = same && tk[i + e] == tk[key0 + e];
+      if (same) { const int tok = (int)tk[i + n - 1]; if (tok >= 0 && tok < V) atomicOr(&ban[tok >> 5], 1u << (tok & 31)); }
+    }
+  }
+  __syncthreads();
+  // ---- pass A: log-sum-exp over the softmax domain ---------------------------------------------------------------------
+  auto in_domain = [&](int v) { return !pre_range || v < 4 || (v >= a.range_lo && v < a.range_hi); };
+  float mx = -CUDART_INF_F;
+  if (pre_list) {
+    for (int e = t; e < nal; e += kT) { const float s = ldf(x, eos_only ? a.eos : al[e]) * inv_t; if (s == s) mx = fmaxf(mx, s); }
+  } else {
+    for (int v = t; v < V; v += kT) if (in_domain(v)) { const float s = ldf(x, v) * inv_t; if (s == s) mx = fmaxf(mx, s); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (t == 0) { float m = red[0]; for (int w = 1; w < kT / 32; ++w) m = fmaxf(m, red[w]); bcast = m; }
+  __syncthreads();
+  mx = bcast;
+  const float mu = mx == -CUDART_INF_F ? 0.f : mx;
+  float sum = 0.f;
+  if (pre_list) {
+    for (int e = t; e < nal; e += kT) { const float s = ldf(x, eos_only ? a.eos : al[e]) * inv_t; if (s == s) sum += __expf(s - mu); }
+  } else {
+    for (int v = t; v < V; v += kT) if (in_domain(v)) { const float s = ldf(x, v) * inv_t; if (s == s) sum += __expf(s - mu); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (t == 0) { float s = 0.f; for (int w = 0; w < kT / 32; ++w) s += red[w]; bcast = s; }
+  __syncthreads();
+  const float lse = mu + logf(bcast);              // all domain entries -inf / NaN: lse = -inf + ... -> every log-prob NaN -> -inf below
+  const float prev = a.prev_scores ? a.prev_scores[r] : 0.f;
+  // ---- pass B: per-thread K best --------------------------------------------------------------------------------------
+  float val[K]; int idx[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { val[k] = -CUDART_INF_F; idx[k] = 0x7fffffff; }
+  auto consider = [&](int v) {
+    float lp = ldf(x, v) * inv_t - lse;
+    if (lp != lp) lp = -CUDART_INF_F;                                   // sequence_generator.py:386
+    if ((ban[v >> 5] >> (v & 31)) & 1u) lp = -CUDART_INF_F;
+    if (v == a.unk) lp -= a.unk_penalty;
+    if (a.force_eos) lp = v == a.eos ? (a.eos_one ? 1.f : lp) : -CUDART_INF_F;   // :399-404
+    insert<K>(val, idx, lp + prev, v);
+  };
+  if (pre_list) {
+    for (int e = t; e < nal; e += kT) consider(eos_only ? a.eos : al[e]);
+  } else if (a.force_eos) {
+    if (t == 0 && in_domain(a.eos)) consider(a.eos);
+  } else {
+    for (int v = t; v < V; v += kT) if (in_domain(v)) consider(v);
+  }
+  // ---- K rounds of block arg-max -------------------------------------------------------------------------------------------
+  // warp level first: each warp reduces to its K best (K rounds of shuffles), then warp 0 merges the 8 lists
+  int head = 0;        // next unconsumed entry of this thread's sorted list
+  for (int k = 0; k < K; ++k) {
+    float bv = head < K ? val[0] : -CUDART_INF_F;
+    int bi = head < K ? idx[0] : 0x7fffffff;
+    int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (better(ov, oi, bv, bi) || (ov == bv && oi == bi && ol < bl)) { bv = ov; bi = oi; bl = ol; }
+    }
+    if (lane == 0) { cv[warp][k] = bv; ci[warp][k] = bi; }
+    if (lane == bl && head < K) {      // pop: shift the list (registers, static indexing)
+#pragma unroll
+      for (int q = 0; q < K - 1; ++q) { val[q] = val[q + 1]; idx[q] = idx[q + 1]; }
+      val[K - 1] = -CUDART_INF_F; idx[K - 1] = 0x7fffffff;
+      ++head;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // merge the per-warp sorted lists: lane w < 8 walks list w
+    int pos = 0;
+    for (int k = 0; k < K; ++k) {
+      float bv = (lane < kT / 32 && pos < K) ? cv[lane][pos] : -CUDART_INF_F;
+      int bi = (lane < kT / 32 && pos < K) ? ci[lane][pos] : 0x7fffffff;
+      int bl = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (better(ov, oi, bv, bi) || (ov == bv && oi == bi && ol < bl)) { bv = ov; bi = oi; bl = ol; }
+      }
+      if (lane == 0) { out_v[k] = bv; out_i[k] = bi; }
+      if (lane == bl) ++pos;
+    }
+  }
+}
+
+template <int KT>      // KT: width of the per-row lists in the workspace; a.K candidates are emitted
+__global__ void beam_merge_kernel(OfaBeamArgs a) {
+  pdl_sync();
+  const int s = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s * a.beam >= a.R) return;
+  // lane b < beam walks the sorted list of beam row b
+  int pos = 0;
+  const float* rv = a.row_val + ((size_t)s * a.beam + (lane < a.beam ? lane : 0)) * KT;
+  const int* ri = a.row_idx + ((size_t)s * a.beam + (lane < a.beam ? lane : 0)) * KT;
+  for (int k = 0; k < a.K; ++k) {
+    const bool have = lane < a.beam && pos < KT && ri[pos] != 0x7fffffff;
+    float bv = have ? rv[pos] : -CUDART_INF_F;
+    long long bi = have ? (long long)lane * a.V + ri[pos] : 0x7fffffffffffffffLL;
+    int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bl = ol; }
+    }
+    if (lane == 0) {
+      a.cand_scores[(size_t)s * a.K + k] = bv;
+      // fewer than K candidates exist (tiny constraint sets): fillers with score -inf, as torch.topk returns
+      a.cand_index[(size_t)s * a.K + k] = bi == 0x7fffffffffffffffLL ? (long long)(a.V - 1 - k) : bi;
+    }
+    if (lane == bl) ++pos;
+  }
+}
+
+// node_out[r] = child of node_in[parent[r]] along token tok[r]; -1 when the prefix has left the trie
+__global__ void trie_advance_kernel(const int* __restrict__ trie_ptr, const int* __restrict__ trie_tok, const int* __restrict__ trie_child,
+                                    const int* __restrict__ node_in, const long long* __restrict__ parent,
+                                    const long long* __restrict__ tok, long long tok_stride, int* __restrict__ node_out, int R) {
+  pdl_sync();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int nd = node_in[parent ? parent[r] : r];
+  int out = -1;
+  if (nd >= 0) {
+    const long long tk = tok[(size_t)r * tok_stride];
+    for (int e = trie_ptr[nd]; e < trie_ptr[nd + 1]; ++e)
+      if (trie_tok[e] == tk) { out = trie_child[e]; break; }
+  }
+  node_out[r] = out;
+}
+
+template <typename T>
+int launch_rows(const OfaBeamArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)((a.V + 31) / 32) * 4;
+  if (a.K <= 4) return (int)ofa_launch_pdl(beam_row_kernel<T, 4>, dim3(a.R), kT, smem, st, a);
+  if (a.K <= 8) return (int)ofa_launch_pdl(beam_row_kernel<T, 8>, dim3(a.R), kT, smem, st, a);
+  if (a.K <= 10) return (int)ofa_launch_pdl(beam_row_kernel<T, 10>, dim3(a.R), kT, smem, st, a);
+  return (int)ofa_launch_pdl(beam_row_kernel<T, 16>, dim3(a.R), kT, smem, st, a);
+}
+
+}  // namespace
+
+extern "C" int ofa_beam_topk(const OfaBeamArgs* a, void* stream) {
+  OFA_CHECK(a->R > 0 && a->beam > 0 && a->R % a->beam == 0 && a->V > 4 && a->K >= 1 && a->K <= KMAX && a->beam <= 32,
+            "ofa_beam_topk: bad sizes R=%d beam=%d V=%d K=%d", a->R, a->beam, a->V, a->K);
+  OFA_CHECK(a->logits && a->row_val && a->row_idx && a->cand_scores && a->cand_index, "ofa_beam_topk: null operand");
+  OFA_CHECK(a->temperature > 0.f, "ofa_beam_topk: temperature must be > 0");
+  OFA_CHECK(!a->node || (a->trie_ptr && a->trie_tok), "ofa_beam_topk: trie arrays missing");
+  OFA_CHECK(a->ngram <= 0 || a->tokens, "ofa_beam_topk: n-gram blocking needs the token buffer");
+  OFA_CHECK((size_t)((a->V + 31) / 32) * 4 <= 48 * 1024, "ofa_beam_topk: vocabulary too large for the shared-memory mask");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the row kernel writes K' >= K entries per row (template sizes 4 / 8 / 10 / 16): the workspace rows are K' wide
+  OfaBeamArgs b = *a;
+  const int Kt = a->K <= 4 ? 4 : a->K <= 8 ? 8 : a->K <= 10 ? 10 : 16;
+  b.K = Kt;
+  int rc = a->dtype == OFA_BF16 ? launch_rows<__nv_bfloat16>(b, st) : launch_rows<float>(b, st);
+  if (rc != 0) return ofa_set_error("ofa_beam_topk: launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  OFA_LAUNCH_CHECK("beam_row_kernel");
+  const int bsz = a->R / a->beam;
+  b.K = a->K;
+  // (merge reads rows of width Kt, emits K)
+  if (Kt == 4) OFA_CUDA(ofa_launch_pdl(beam_merge_kernel<4>, dim3((bsz + 3) / 4), 128, 0, st, b));
+  else if (Kt == 8) OFA_CUDA(ofa_launch_pdl(beam_merge_kernel<8>, dim3((bsz + 3) / 4), 128, 0, st, b));
+  else if (Kt == 10) OFA_CUDA(ofa_launch_pdl(beam_merge_kernel<10>, dim3((bsz + 3) / 4), 128, 0, st, b));
+  else OFA_CUDA(ofa_launch_pdl(beam_merge_kernel<16>, dim3((bsz + 3) / 4), 128, 0, st, b));
+  OFA_LAUNCH_CHECK("beam_merge_kernel");
+  return 0;
+}
+
+extern "C" int ofa_beam_topk_width(int K) { return K <= 4 ? 4 : K <= 8 ? 8 : K <= 10 ? 10 : 16; }
+
+extern "C" int ofa_trie_advance(const int* trie_ptr, const int* trie_tok, const int* trie_child, const int* node_in,
+                                const long long* parent, const long long* tok, long long tok_stride, int* node_out, int R,
+                                void* stream) {
+  OFA_CHECK(R > 0 && trie_ptr && trie_tok && trie_child && node_in && tok && node_out, "ofa_trie_advance: null operand");
+  OFA_CUDA(ofa_launch_pdl(trie_advance_kernel, dim3((R + 127) / 128), 128, 0, (cudaStream_t)stream, trie_ptr, trie_tok, trie_child,
+                          node_in, parent, tok, tok_stride, node_out, R));
+  OFA_LAUNCH_CHECK("trie_advance_kernel");
+  return 0;
+}

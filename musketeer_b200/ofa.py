@@ -174,12 +174,29 @@ class MultiheadAttention(nn.Module):
         cfg["H"], cfg["fused_qkv"], cfg["dq_scale"] = self.num_heads, True, self.scaling
         return ops.attention(q, pq, k, pk, v, tok_lut, img_lut, self.c_attn, cfg)
 
-    def forward(self, query, k, v, pq, pk, tok_lut, img_lut, cfg):
-        q = _lin(self.q_proj, query, alpha=self.scaling)
+    def qkv_eval(self, h):
+        """Inference: q * scaling | k | v of one GEMM over the concatenated projection weights, which are built once and cached
+        (keyed on the parameters' version counters) instead of being concatenated at every decoder step."""
+        ps = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.q_proj.bias, self.k_proj.bias, self.v_proj.bias)
+        key = tuple(p._version for p in ps) + (ps[0].data_ptr(), ps[0].dtype)
+        c = getattr(self, "_qkv_cache", None)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                c = self._qkv_cache = (key, torch.cat(ps[:3], 0), torch.cat(ps[3:], 0))
+        shp = h.shape
+        D = self.embed_dim
+        y = ops.gemm(h.reshape(-1, shp[-1]), c[1], h.numel() // shp[-1], 3 * D, shp[-1], bias=c[2], alpha=self.scaling, alpha_cols=D)
+        y = y.view(*shp[:-1], 3 * D)
+        return y[..., :D], y[..., D:2 * D], y[..., 2 * D:]
+
+    def forward(self, query, k, v, pq, pk, tok_lut, img_lut, cfg, q_pre=None):
+        q = q_pre if q_pre is not None else _lin(self.q_proj, query, alpha=self.scaling)
         dec = cfg.get("decode")
         if dec is not None:        # incremental decoding: one token per row against the KV cache (csrc/decode.cu)
-            return ops.attention_decode(q, pq, k, pk, v, dec["S"], self.num_heads, dec.get("G", 1), dec.get("kv_row"),
-                                        dec.get("pk_row"), dec.get("kpm"), self.c_attn, tok_lut, dec.get("q_pos", 0))
+            bias = dec.get("bias")         # the position term of this attention, computed once per step for all layers
+            return ops.attention_decode(q, None if bias is not None else pq, k, None if bias is not None else pk, v, dec["S"],
+                                        self.num_heads, dec.get("G", 1), dec.get("kv_row"), dec.get("pk_row"), dec.get("kpm"),
+                                        self.c_attn, tok_lut, dec.get("q_pos", 0), bias_in=bias, page=dec.get("page"))
         cfg = dict(cfg)
         cfg["H"] = self.num_heads
         return ops.attention(q, pq, k, pk, v, tok_lut, img_lut, self.c_attn, cfg)
@@ -264,9 +281,9 @@ class TransformerDecoderLayer(nn.Module, _FFNMixin):
 
     def forward(self, x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg):
         h, x = _ln(self.self_attn_layer_norm, x, fork=True)
-        if "decode" in self_cfg:                 # incremental decoding: K / V go through the cache
-            k, v = self_kv(self.self_attn, h)
-            o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg)
+        if "decode" in self_cfg:                 # incremental decoding: K / V go through the (paged) cache
+            q, k, v = self_kv(self.self_attn, h)
+            o = self.self_attn(h, k, v, spq, spk, tok_lut, None, self_cfg, q_pre=q)
         else:
             o = self.self_attn.forward_self(h, spq, spk, tok_lut, None, self_cfg)
         x = self._post_attn(self.self_attn, o, self.self_attn_ln, x)
@@ -566,9 +583,12 @@ class TransformerDecoder(FairseqIncrementalDecoder):
             # KV cache of the incremental decoder.  Cross-attention K / V / pos_k are projected ONCE per SENTENCE: when the
             # caller hands over the un-replicated encoder output (our SequenceGenerator), the G = rows / sentences beams of a
             # sentence read the same cache row through `sent_row`; a caller that replicated encoder_out per beam (the
-            # reference generator) simply gets G = 1.  Self-attention K / V live in one preallocated ping-pong buffer
-            # [2][2*layers, rows, cap, d]; a beam reorder gathers only the valid prefix (reorder_incremental_state_scripting).
+            # reference generator) simply gets G = 1.  Self-attention K / V live in a PAGED pool: [slot][2*layers][page_len][d]
+            # with a block table per row; a beam reorder copies table entries of the full pages and only the partial last page
+            # (reorder_incremental_state_scripting).  The cross-attention position term cross_pos_q . cross_pos_k^T is the same
+            # for every layer (unify_transformer.py:1461-1466): one launch per step writes it, the six layers add it.
             st = incremental_state.setdefault("_ofa_b200", {})
+            PL = 16
             if "cpk" not in st or (t0 == 0 and st.get("reuse")):
                 EB = enc.shape[0]
                 if B % EB != 0:
@@ -580,7 +600,7 @@ class TransformerDecoder(FairseqIncrementalDecoder):
                 cross = [layer.encoder_attn.project_kv(enc) for layer in self.layers]
                 pad8 = enc_pad.contiguous().view(torch.uint8)
                 same = ("cpk" in st and st["G"] == G and st["cpk"].shape == cpk.shape and st["cpk"].dtype == cpk.dtype
-                        and st["kv"].shape[2] == B)
+                        and st["table"][0].shape[0] == B)
                 if same:
                     # persistent state (the generator replays captured decoder steps that hold these pointers): refresh the
                     # contents in place
@@ -594,28 +614,46 @@ class TransformerDecoder(FairseqIncrementalDecoder):
                     st["G"] = G
                     st["sent_row0"] = st["sent_row"] = torch.arange(EB, device=dev, dtype=torch.int32)
                     st["cpk"], st["cross"], st["enc_pad"] = cpk, cross, pad8.clone()
-                    st["cap"] = 32
-                    st["kv"] = torch.zeros(2, 2 * self.num_layers, B, st["cap"], d, dtype=x.dtype, device=dev)
-                    st["spk"] = torch.zeros(1, st["cap"], d, dtype=x.dtype, device=dev)
+                    st["max_pages"] = 2
+                    st["pool"] = torch.zeros(B * st["max_pages"] * 2, 2 * self.num_layers, PL, d, dtype=x.dtype, device=dev)
+                    st["table"] = [torch.full((B, st["max_pages"]), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+                    st["spk"] = torch.zeros(1, st["max_pages"] * PL, d, dtype=x.dtype, device=dev)
                     st["zero_row"] = torch.zeros(B, dtype=torch.int32, device=dev)
+                    st["bias"] = torch.empty(B, H, (enc.shape[1] + 3) // 4 * 4, dtype=torch.float32, device=dev)
+                    st["home"] = torch.arange(B, device=dev, dtype=torch.int32)
                     st["layout"] = st.get("layout", 0) + 1          # captured steps of an older layout are stale
-                st["cur"], st["len"], st["rows"] = 0, 0, B
+                st["tcur"], st["ppar"], st["len"], st["rows"], st["reordered_at"] = 0, 0, 0, B, -1
             if t0 != st["len"]:
                 raise ValueError("incremental decoding expects one new token per call (cache holds %d, got position %d)"
                                  % (st["len"], t0))
-            if t0 + 1 > st["cap"]:          # grow the caches (doubling)
-                cap = st["cap"] * 2
-                kv = torch.zeros(2, 2 * self.num_layers, st["kv"].shape[2], cap, d, dtype=x.dtype, device=dev)
-                kv[:, :, :, :st["cap"]] = st["kv"]
+            if t0 + 1 > st["max_pages"] * PL:          # grow (doubling): slots are (row * max_pages + page) * 2 + parity
+                mp, mp2 = st["max_pages"], st["max_pages"] * 2
+                B0 = st["table"][0].shape[0]
+                pool = torch.zeros(B0 * mp2 * 2, 2 * self.num_layers, PL, d, dtype=x.dtype, device=dev)
+                pool.view(B0, mp2, 2, -1)[:, :mp] = st["pool"].view(B0, mp, 2, -1)
+                tabs = []
+                for tb in st["table"]:
+                    slot = tb.long()
+                    new = ((slot // 2) // mp) * (mp2 * 2) + ((slot // 2) % mp) * 2 + slot % 2
+                    t2 = torch.full((B0, mp2), -1, dtype=torch.int32, device=dev)
+                    t2[:, :mp] = torch.where(tb >= 0, new.int(), tb)
+                    tabs.append(t2)
+                spk2 = torch.zeros(1, mp2 * PL, d, dtype=x.dtype, device=dev)
+                spk2[:, :mp * PL] = st["spk"]
+                st["pool"], st["table"], st["spk"], st["max_pages"] = pool, tabs, spk2, mp2
                 st["layout"] = st.get("layout", 0) + 1
-                spk_new_buf = torch.zeros(1, cap, d, dtype=x.dtype, device=dev)
-                spk_new_buf[:, :st["cap"]] = st["spk"]
-                st["kv"], st["spk"], st["cap"] = kv, spk_new_buf, cap
+            page, off = t0 // PL, t0 % PL
+            table = st["table"][st["tcur"]]
+            if off == 0 and st["reordered_at"] != t0:       # a new page starts: every row's own slot
+                st["ppar"] = 1 - st["ppar"]
+                table[:B, page] = (st["home"][:B] * st["max_pages"] + page) * 2 + st["ppar"]
             st["spk"][0, t0] = spk_new[0, 0]            # pos_k depends on the position only: one shared row
-            cache = st["kv"][st["cur"]]
-            R = B
-            self_dec = {"S": t0 + 1, "G": 1, "pk_row": st["zero_row"][:R], "q_pos": t0}
-            cross_dec = {"S": enc.shape[1], "G": st["G"], "kv_row": st["sent_row"], "kpm": st["enc_pad"]}
+            pstride = 2 * self.num_layers * PL * d
+            self_dec = {"S": t0 + 1, "G": 1, "pk_row": st["zero_row"][:B], "q_pos": t0, "page": (table, PL, pstride)}
+            bias = st["bias"]
+            ops.attention_decode(cpq, None, st["cpk"], None, None, enc.shape[1], H, st["G"], st["sent_row"], None, st["enc_pad"],
+                                 score_out=bias)
+            cross_dec = {"S": enc.shape[1], "G": st["G"], "kv_row": st["sent_row"], "kpm": st["enc_pad"], "bias": bias}
             self_cfg = {"decode": self_dec}
             cross_cfg = {"decode": cross_dec}
             cpk, spk = st["cpk"], st["spk"]
@@ -632,14 +670,11 @@ class TransformerDecoder(FairseqIncrementalDecoder):
             tok_lut = _tok_lut(self.token_rel_pos_table_list[i].weight, rel1d)
 
             def self_kv(attn, h, i=i):
-                k, v = attn.project_kv(h)
-                if incremental:
-                    st = incremental_state["_ofa_b200"]
-                    cache = st["kv"][st["cur"]]
-                    cache[2 * i, :B, t0] = k[:, 0]
-                    cache[2 * i + 1, :B, t0] = v[:, 0]
-                    return cache[2 * i], cache[2 * i + 1]
-                return k, v
+                q, k, v = attn.qkv_eval(h)
+                st = incremental_state["_ofa_b200"]
+                pool, tb = st["pool"], st["table"][st["tcur"]]
+                ops.page_write(pool, tb[:B], k, v, i, t0 // 16, t0 % 16, 16)
+                return q, pool[0, 2 * i], pool[0, 2 * i + 1]       # base of this layer's k / v planes inside page 0
 
             def cross_kv(attn, i=i):
                 if incremental:
@@ -659,17 +694,28 @@ class TransformerDecoder(FairseqIncrementalDecoder):
         return ops.linear(features, self.output_projection.weight, None, 1.0, None, padded)
 
     def reorder_incremental_state_scripting(self, incremental_state, new_order):
-        """Beam reorder (models/sequence_generator.py:339-349): the self-attention cache is gathered row-wise over its valid
-        prefix into the other half of the ping-pong buffer (one launch for all layers); the per-sentence cross-attention
-        cache is never moved -- only the group -> sentence map follows the surviving sentences."""
+        """Beam reorder (models/sequence_generator.py:339-349).  The self-attention cache is paged: the new rows' block tables
+        take the parents' entries for every full page (no data moves), and only the valid prefix of the partial last page is
+        copied into the row's own slot (one launch for all layers); the per-sentence cross-attention cache is never moved --
+        only the group -> sentence map follows the surviving sentences."""
         st = incremental_state.get("_ofa_b200")
         if not st:
             return
         rows = int(new_order.numel())
         G = st["G"]
-        if st["len"] > 0:
-            ops.cache_gather(st["kv"][st["cur"]], st["kv"][1 - st["cur"]], new_order.contiguous(), rows, st["len"])
-            st["cur"] = 1 - st["cur"]
+        t0 = st["len"]                       # the position the next decoder call writes
+        if t0 > 0:
+            page, off = t0 // 16, t0 % 16
+            if off == 0 and page >= st["max_pages"]:
+                pass                         # the pool grows in the next decoder call; full pages only: plain table copy below
+            src, dst = st["table"][st["tcur"]], st["table"][1 - st["tcur"]]
+            st["ppar"] = 1 - st["ppar"]
+            if page < st["max_pages"]:
+                ops.page_reorder(st["pool"], src, dst, new_order.contiguous(), rows, page, off, st["ppar"], 16)
+                st["reordered_at"] = t0
+            else:
+                dst[:rows] = src.index_select(0, new_order)
+            st["tcur"] = 1 - st["tcur"]
         st["sent_row"] = st["sent_row"].index_select(0, torch.div(new_order[::G], G, rounding_mode="floor"))
         st["rows"] = rows
 

@@ -1076,31 +1076,114 @@ def attention(q, pq, k, pk, v, tok_lut, img_lut, head_scale, cfg):
 
 
 def attention_decode(q, pq, k, pk, v, S, H, G=1, kv_row=None, pk_row=None, kpm=None, head_scale=None, tok_lut=None,
-                     q_pos=0):
+                     q_pos=0, bias_in=None, score_out=None, page=None):
     """Single-token attention over a KV cache (inference only; csrc/decode.cu).  q, pq: [R, 1, H*64] (pre-scaled);
     k, v: caches [rows, cap, H*64] of which the first S positions are valid; pk likewise; G consecutive query rows share
-    cache row kv_row[group] (int32).  Returns [R, 1, H*64]."""
+    cache row kv_row[group] (int32).  pq / pk None: no absolute-position term.  bias_in [R, H, ld] fp32 is added to the
+    scores; with score_out [R, H, ld] the launch only writes its raw scores (the shared cross-attention position term,
+    computed once per step).  page = (table int32 [rows, max_pages], page_len, page_stride): k / v are page pools.
+    Returns [R, 1, H*64] (None in score_out mode)."""
     _need_cuda(q)
     R, D = q.shape[0], q.shape[-1]
-    q2, pq2 = q.reshape(R, D), pq.reshape(R, D)
-    o = torch.empty(R, D, dtype=q.dtype, device=q.device)
+    q2 = q.reshape(R, D)
     a = OfaDecodeArgs()
-    a.q, a.pq, a.ldq, a.ldpq = q2.data_ptr(), pq2.data_ptr(), q2.stride(0), pq2.stride(0)
-    a.k, a.v, a.pk = k.data_ptr(), v.data_ptr(), pk.data_ptr()
-    a.ldk, a.bsk, a.ldv, a.bsv, a.ldpk, a.bspk = k.stride(1), k.stride(0), v.stride(1), v.stride(0), pk.stride(1), pk.stride(0)
+    a.q, a.ldq = q2.data_ptr(), q2.stride(0)
+    if pq is not None:
+        pq2 = pq.reshape(R, D)
+        a.pq, a.ldpq = pq2.data_ptr(), pq2.stride(0)
+        a.pk, a.ldpk, a.bspk = pk.data_ptr(), pk.stride(1), pk.stride(0)
+    a.k = k.data_ptr()
+    if page is not None:
+        table, page_len, page_stride = page
+        a.page_table, a.page_len, a.max_pages, a.page_stride = table.data_ptr(), int(page_len), table.shape[1], int(page_stride)
+        a.ldk = a.ldv = D
+        a.bsk = a.bsv = 0
+    else:
+        a.ldk, a.bsk = k.stride(1), k.stride(0)
+    o = None
+    if score_out is None:
+        a.v = v.data_ptr()
+        if page is None:
+            a.ldv, a.bsv = v.stride(1), v.stride(0)
+        o = torch.empty(R, D, dtype=q.dtype, device=q.device)
+        a.o, a.ldo = o.data_ptr(), D
+    else:
+        a.score_out, a.bias_ld = score_out.data_ptr(), score_out.stride(1)
+    if bias_in is not None:
+        a.bias_in, a.bias_ld = bias_in.data_ptr(), bias_in.stride(1)
     a.kv_row = kv_row.data_ptr() if kv_row is not None else None
     a.pk_row = pk_row.data_ptr() if pk_row is not None else None
     a.kpm = kpm.data_ptr() if kpm is not None else None
     a.kpm_stride = kpm.stride(0) if kpm is not None else 0
-    a.o, a.ldo = o.data_ptr(), D
     hs = head_scale.float().contiguous() if head_scale is not None else None
     a.head_scale = hs.data_ptr() if hs is not None else None
     a.tok_lut = tok_lut.data_ptr() if tok_lut is not None else None
     a.tok_max, a.q_pos = 1024, int(q_pos)
     a.R, a.G, a.H, a.S = R, int(G), int(H), int(S)
+    nb = (2 if score_out is not None or pq is None else 3) - (1 if score_out is not None else 0)
     call("ofa_attn_decode", C.byref(a), _dt(q), _st(),
-         work=("byte", (R // max(G, 1)) * S * D * 3.0 * q.element_size()))
-    return o.view(R, 1, D)
+         work=("byte", (R // max(G, 1)) * S * D * float(nb) * q.element_size()))
+    return o.view(R, 1, D) if o is not None else None
+
+
+def page_reorder(pool, table_src, table_dst, order, rows, page, off, parity, page_len):
+    """Beam reorder of the paged self-attention cache: table entries of the full pages are copied, the partial last page is
+    copied on write into the row's own slot (csrc/decode.cu)."""
+    n_slots, planes, pl, D = pool.shape
+    max_pages = table_src.shape[1]
+    call("ofa_page_reorder", _p(pool), _p(table_src), _p(table_dst), _p(order), rows, max_pages, int(page), int(off), int(parity),
+         int(page_len), D, planes, _dt(pool), _st())
+
+
+def page_write(pool, table, k, v, layer, page, off, page_len):
+    """Append one layer's new K / V token of every row at position `off` of page `page`."""
+    n_slots, planes, pl, D = pool.shape
+    rows, max_pages = table.shape
+    k2, v2 = k.reshape(rows, D), v.reshape(rows, D)
+    call("ofa_page_write", _p(pool), _p(table), _p(k2), _p(v2), k2.stride(0), v2.stride(0), rows, max_pages, int(page), int(off),
+         int(page_len), D, planes, 2 * layer, _dt(pool), _st())
+
+
+def beam_topk(logits, beam, K, temperature=1.0, prev_scores=None, step0=False, eos=2, pad=1, unk=3, unk_penalty=0.0,
+              block_eos=False, force_eos=False, eos_one=False, crange=None, range_post=False, trie=None, node=None,
+              trie_post=False, tokens=None, step=0, ngram=0, ws=None):
+    """Fused tail of a beam-search step (csrc/beam.cu): logits [R, V] -> (cand_scores [R/beam, K] fp32, cand_index int64).
+    trie = (ptr, tok, child) int32 CSR tensors; node int32 [R]; tokens int64 [R, L] for n-gram blocking."""
+    from ._lib import OfaBeamArgs
+    _need_cuda(logits)
+    R, V = logits.shape
+    assert logits.stride(1) == 1
+    a = OfaBeamArgs()
+    a.logits, a.ld, a.dtype = logits.data_ptr(), logits.stride(0), _dt(logits)
+    a.R, a.beam, a.V, a.K = R, int(beam), V, int(K)
+    a.temperature = float(temperature)
+    a.prev_scores = prev_scores.data_ptr() if prev_scores is not None else None
+    a.step0 = int(step0)
+    a.eos, a.pad, a.unk, a.unk_penalty = int(eos), int(pad), int(unk), float(unk_penalty)
+    a.block_eos, a.force_eos, a.eos_one = int(block_eos), int(force_eos), int(eos_one)
+    a.range_lo, a.range_hi = (int(crange[0]), int(crange[1])) if crange is not None else (-1, -1)
+    a.range_post = int(range_post)
+    if trie is not None:
+        a.trie_ptr, a.trie_tok, a.node, a.trie_post = trie[0].data_ptr(), trie[1].data_ptr(), node.data_ptr(), int(trie_post)
+    if ngram > 0:
+        a.tokens, a.ldtok, a.step, a.ngram = tokens.data_ptr(), tokens.stride(0), int(step), int(ngram)
+    kw = _lib.load().ofa_beam_topk_width(int(K))
+    if ws is None or ws[0].numel() < R * kw:
+        ws = (torch.empty(R * kw, dtype=torch.float32, device=logits.device),
+              torch.empty(R * kw, dtype=torch.int32, device=logits.device))
+    cs = torch.empty(R // beam, K, dtype=torch.float32, device=logits.device)
+    ci = torch.empty(R // beam, K, dtype=torch.int64, device=logits.device)
+    a.row_val, a.row_idx, a.cand_scores, a.cand_index = ws[0].data_ptr(), ws[1].data_ptr(), cs.data_ptr(), ci.data_ptr()
+    call("ofa_beam_topk", C.byref(a), _st(), work=("byte", 2.0 * R * V * logits.element_size()))
+    return cs, ci, ws
+
+
+def trie_advance(trie, node_in, parent, tok):
+    """node_out[r] = child of node_in[parent[r]] along tok[r] (-1 when the prefix leaves the trie)."""
+    out = torch.empty_like(node_in)
+    call("ofa_trie_advance", _p(trie[0]), _p(trie[1]), _p(trie[2]), _p(node_in), _p(parent), _p(tok), tok.stride(0), _p(out),
+         node_in.numel(), _st())
+    return out
 
 
 def cache_gather(src, dst, order, rows, L):

@@ -1,15 +1,37 @@
 """Beam search over the incremental OFA decoder (models/sequence_generator.py:19-764 + fairseq BeamSearch.step as
 spelled out in models/search.py:109-144).  Same constructor arguments, `generate(models, sample, **kw)` signature and
 result layout (list over sentences of hypothesis dicts sorted by score: tokens / score / attention / alignment /
-positional_scores).  The per-step decoder work (one token per beam, KV appended to the cache, cross-attention K/V
-projected once) runs on the kernels of libofa_b200.so; the beam bookkeeping stays in torch index ops on the device.
+positional_scores).  Per step, on the kernels of libofa_b200.so: one token per beam through the decoder (paged self-attention
+KV cache, cross-attention K / V projected once per sentence, csrc/decode.cu), then ONE fused launch pair for the tail --
+temperature, constraint range / constraint trie, fp32 log-softmax, min-len / max-len / pad / unk masks, n-gram blocking,
+previous beam scores and the top 2*beam selection (csrc/beam.cu).  The constraint trie (utils/trie.py; built by the tasks,
+tasks/mm_tasks/vqa_gen.py:158-167) is flattened to CSR once and walked on the device; the beam bookkeeping stays in torch
+index ops on the device.
 
-Out of scope here (raises): constraint tries, prefix tokens, image-code / box generation, LM fusion, ensembles > 1."""
+Out of scope here (raises): prefix tokens, image-code / box generation, LM fusion, ensembles > 1."""
 import math
 from typing import Dict, List, Optional
 
 import torch
-import torch.nn.functional as F
+
+from . import ops
+
+
+def flatten_trie(trie, device):
+    """utils/trie.py Trie -> CSR tensors (ptr [n+1], tok [e], child [e]); the root is node 0.  Children are stored in
+    insertion order, like `list(node.child.keys())`.  Nodes are TreeNode objects (`.child` dict) or plain nested dicts."""
+    nodes, ptr, tok, child = [trie.root], [0], [], []
+    i = 0
+    while i < len(nodes):
+        kids = nodes[i].child if hasattr(nodes[i], "child") else nodes[i]
+        for t, c in kids.items():
+            tok.append(int(t))
+            child.append(len(nodes))
+            nodes.append(c)
+        ptr.append(len(tok))
+        i += 1
+    mk = lambda v: torch.tensor(v if v else [0], dtype=torch.int32, device=device)
+    return mk(ptr), mk(tok), mk(child)
 
 
 class SequenceGenerator(torch.nn.Module):
@@ -22,9 +44,10 @@ class SequenceGenerator(torch.nn.Module):
         models = list(models) if isinstance(models, (list, tuple)) else [models]
         if len(models) != 1 or lm_model is not None:
             raise NotImplementedError("ensembles / LM fusion are outside the hot-path scope")
-        if constraint_trie is not None or gen_code or gen_box or search_strategy is not None or match_source_len:
-            raise NotImplementedError("constraint tries, code/box generation and custom search strategies are outside "
-                                      "the hot-path scope (SURVEY.md 8f)")
+        if gen_code or gen_box or search_strategy is not None or match_source_len:
+            raise NotImplementedError("code/box generation and custom search strategies are outside the hot-path scope")
+        if beam_size > 8:
+            raise NotImplementedError("beam sizes above 8 (the beams of a sentence share one cross-attention cache row group)")
         self.model = models[0]
         self.tgt_dict = tgt_dict
         self.pad, self.unk, self.bos = tgt_dict.pad(), tgt_dict.unk(), tgt_dict.bos()
@@ -37,6 +60,9 @@ class SequenceGenerator(torch.nn.Module):
         self.temperature = temperature
         self.no_repeat_ngram_size = no_repeat_ngram_size
         self.ignore_eos = ignore_eos
+        self.zero_shot = zero_shot            # constraints are applied AFTER the softmax (sequence_generator.py:878-889)
+        self.constraint_trie = constraint_trie
+        self._trie_csr = None
         self.constraint_start = self.constraint_end = None
         if constraint_range is not None:
             cs, ce = constraint_range.split(",")
@@ -56,18 +82,6 @@ class SequenceGenerator(torch.nn.Module):
     @torch.no_grad()
     def generate(self, models, sample, **kwargs):
         return self._generate(models, sample, **kwargs)
-
-    def _ngram_block(self, tokens, lprobs, step):
-        n = self.no_repeat_ngram_size
-        if step + 2 - n < 0:
-            return lprobs
-        toks = tokens[:, :step + 1].tolist()
-        for r, gen in enumerate(toks):
-            key = gen[step + 2 - n: step + 1]
-            banned = [gen[i + n - 1] for i in range(len(gen) - n + 1) if gen[i:i + n - 1] == key]
-            if banned:
-                lprobs[r, banned] = -math.inf
-        return lprobs
 
     def _generate(self, models, sample, prefix_tokens=None, constraints=None, bos_token=None):
         if prefix_tokens is not None or constraints is not None:
@@ -110,6 +124,18 @@ class SequenceGenerator(torch.nn.Module):
         cand_offsets = torch.arange(cand_size, device=dev)
         inc = static["inc"] if static is not None else {}
         reorder_state = batch_idxs = None
+        topk_ws = None
+        trie = node = None
+        if self.constraint_trie is not None:
+            # CSR trie on the device; every row starts at the node reached by bos (the reference walks [0] + tokens[1:] from the
+            # root at every step: sequence_generator.py:861-866)
+            if self._trie_csr is None or self._trie_csr[0].device != dev:
+                self._trie_csr = flatten_trie(self.constraint_trie, dev)
+            trie = self._trie_csr
+            root = torch.zeros(bsz * beam, dtype=torch.int32, device=dev)
+            node = ops.trie_advance(trie, root, None, torch.zeros(bsz * beam, dtype=torch.long, device=dev))
+        if self.constraint_start is not None and trie is not None:
+            raise ValueError("constraint_trie and constraint_range are mutually exclusive (sequence_generator.py:858,871)")
         for step in range(max_len + 1):
             if reorder_state is not None and batch_idxs is not None:
                 corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
@@ -122,30 +148,15 @@ class SequenceGenerator(torch.nn.Module):
                 if reorder_state is not None:
                     model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
                 logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
-            logits = logits[:, -1, :].float() / self.temperature
-            if self.constraint_start is not None:
-                logits[:, 4:self.constraint_start] = -math.inf
-                logits[:, self.constraint_end:] = -math.inf
-            lprobs = F.log_softmax(logits, dim=-1)
-            if step < self.min_len:
-                lprobs[:, self.eos] = -math.inf
-            lprobs[lprobs != lprobs] = -math.inf
-            lprobs[:, self.pad] = -math.inf
-            lprobs[:, self.unk] -= self.unk_penalty
-            if step >= max_len:
-                lprobs[:, :self.eos] = -math.inf
-                lprobs[:, self.eos + 1:] = -math.inf
-                if self.ignore_eos:
-                    lprobs[:, self.eos] = 1
-            if self.no_repeat_ngram_size > 0:
-                lprobs = self._ngram_block(tokens, lprobs, step)
-            lp3 = lprobs.view(bsz, -1, V)
-            if step == 0:
-                lp3 = lp3[:, ::beam, :].contiguous()
-            else:
-                lp3 = lp3 + scores.view(bsz, beam, -1)[:, :, step - 1].unsqueeze(-1)
-            flat = lp3.view(bsz, -1)
-            cand_scores, idx = torch.topk(flat, k=min(cand_size, flat.size(1) - 1))
+            # fused tail: temperature, constraints, log-softmax, masks, n-gram blocking, + beam scores, top 2*beam (csrc/beam.cu)
+            lg = logits[:, -1, :]
+            prev = scores.view(bsz, beam, -1)[:, :, step - 1].reshape(-1).contiguous() if step > 0 else None
+            cand_scores, idx, topk_ws = ops.beam_topk(
+                lg, beam, min(cand_size, beam * V - 1), self.temperature, prev, step0=(step == 0), eos=self.eos, pad=self.pad,
+                unk=self.unk, unk_penalty=self.unk_penalty, block_eos=step < self.min_len, force_eos=step >= max_len,
+                eos_one=self.ignore_eos, crange=(self.constraint_start, self.constraint_end) if self.constraint_start is not None else None,
+                range_post=self.zero_shot, trie=trie, node=node, trie_post=self.zero_shot, tokens=tokens, step=step,
+                ngram=self.no_repeat_ngram_size, ws=topk_ws)
             cand_beams = idx // V
             cand_indices = idx.fmod(V)
             cand_bbsz_idx = cand_beams + bbsz_offsets
@@ -173,6 +184,8 @@ class SequenceGenerator(torch.nn.Module):
                 cand_scores = cand_scores[batch_idxs]
                 cand_indices = cand_indices[batch_idxs]
                 cands_to_ignore = cands_to_ignore[batch_idxs]
+                if node is not None:
+                    node = node.view(bsz, beam)[batch_idxs].reshape(-1).contiguous()
                 scores = scores.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
                 tokens = tokens.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
                 bsz = new_bsz
@@ -188,6 +201,8 @@ class SequenceGenerator(torch.nn.Module):
             if step > 0:
                 scores[:, :step] = torch.index_select(scores[:, :step], 0, active_bbsz_idx)
             scores.view(bsz, beam, -1)[:, :, step] = torch.gather(cand_scores, 1, active_hypos)
+            if node is not None:       # trie node of every surviving hypothesis: its parent's node advanced by the chosen token
+                node = ops.trie_advance(trie, node, active_bbsz_idx.contiguous(), tokens[:, step + 1])
             reorder_state = active_bbsz_idx
         for s in range(len(finalized)):
             sc = torch.tensor([float(h["score"]) for h in finalized[s]])
@@ -201,7 +216,7 @@ class SequenceGenerator(torch.nn.Module):
         group -> sentence map tensor) is restored to its post-step value after every replay."""
         st = inc["_ofa_b200"]
         static["order"].copy_(reorder_state)
-        key = (step, st.get("layout", 0))
+        key = (step, st.get("layout", 0), st["tcur"], st["ppar"])
         g = static["graphs"].get(key)
         if g is None:
             torch.cuda.synchronize()
@@ -211,11 +226,12 @@ class SequenceGenerator(torch.nn.Module):
                 logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
             if static["pool"] is None:
                 static["pool"] = graph.pool()
-            g = static["graphs"][key] = {"graph": graph, "logits": logits,
-                                         "post": (st["cur"], st["len"], st["sent_row"], st["rows"])}
+            g = static["graphs"][key] = {"graph": graph, "logits": logits, "post": {k: st[k] for k in self._STATE_KEYS}}
         g["graph"].replay()
-        st["cur"], st["len"], st["sent_row"], st["rows"] = g["post"]
+        st.update(g["post"])
         return g["logits"]
+
+    _STATE_KEYS = ("tcur", "ppar", "len", "sent_row", "rows", "reordered_at")
 
     def _finalize(self, step, bbsz_idx, eos_scores, tokens, scores, finalized, finished, beam, max_len):
         tokens_clone = tokens.index_select(0, bbsz_idx)[:, 1:step + 2].clone()

@@ -100,6 +100,22 @@ GEN_CASES = {
     "gen_base_b8": dict(arch="ofa_base", cfg=dict(patch_image_size=480), emb_std=0.05, w_std=0.3,
                         batch=dict(bsz=8, src_len=8, tgt_len=2, img=480, seed=23, n_pad=0),
                         gen=dict(beam_size=5, max_len_a=0, max_len_b=16, min_len=1)),
+    # constrained decoding: answer trie (tasks/mm_tasks/vqa_gen.py:158-167 inserts [bos] + answer + [eos]) before
+    # and after the softmax (zero_shot), and a constraint range (tasks/mm_tasks/refcoco.py style "lo,hi") in both modes
+    "gen_micro_trie": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                           batch=dict(bsz=4, src_len=9, tgt_len=2, img=64, seed=26, vocab=4099, n_pad=1),
+                           gen=dict(beam_size=5, max_len_a=0, max_len_b=8, min_len=1), trie=dict(n=40, max_len=4, seed=3)),
+    "gen_micro_trie_zeroshot": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                                    batch=dict(bsz=3, src_len=9, tgt_len=2, img=64, seed=27, vocab=4099, n_pad=0),
+                                    gen=dict(beam_size=4, max_len_a=0, max_len_b=8, min_len=1, zero_shot=True),
+                                    trie=dict(n=25, max_len=3, seed=4)),
+    "gen_micro_range": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                            batch=dict(bsz=3, src_len=9, tgt_len=2, img=64, seed=28, vocab=4099, n_pad=1),
+                            gen=dict(beam_size=5, max_len_a=0, max_len_b=6, min_len=4, constraint_range="3000,4000")),
+    "gen_micro_range_zeroshot": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                                     batch=dict(bsz=2, src_len=9, tgt_len=2, img=64, seed=29, vocab=4099, n_pad=0),
+                                     gen=dict(beam_size=3, max_len_a=0, max_len_b=6, min_len=2, constraint_range="100,900",
+                                              zero_shot=True, temperature=0.8, unk_penalty=0.5)),
     # BASELINE.json configs[4] scaled to ofa_tiny / batch 2 (the oracle finishes in seconds)
     "gen_tiny": dict(arch="ofa_tiny", cfg={}, emb_std=0.1,
                      batch=dict(bsz=2, src_len=8, tgt_len=2, img=256, seed=22, n_pad=0),
@@ -243,12 +259,21 @@ def run_gen_case(name, case):
     model, task = rh.build_model(cfg, sd)
     model.eval()
     sample = synth.make_batch(**case["batch"])
-    gen = rh.build_generator(model, task, **case["gen"])
+    ref_trie = our_trie = None
+    if "trie" in case:
+        from utils.trie import Trie as RefTrie          # the reference's own class (utils/trie.py)
+        ref_trie, our_trie = RefTrie(2), oo.Trie(2)
+        for w in synth.trie_words(vocab=cfg.vocab_size, **case["trie"]):
+            ref_trie.insert(w)
+            our_trie.insert(w)
+    gen = rh.build_generator(model, task, constraint_trie=ref_trie, **case["gen"])
     hyp = gen.generate([model], copy.deepcopy(sample))
     g = dict(case["gen"])
     ours = oo.generate(sd, cfg, sample["net_input"], beam=g["beam_size"], max_len_a=g["max_len_a"],
                        max_len_b=g["max_len_b"], min_len=g["min_len"],
-                       no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0))
+                       no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0), temperature=g.get("temperature", 1.0),
+                       unk_penalty=g.get("unk_penalty", 0.0), constraint_trie=our_trie,
+                       constraint_range=g.get("constraint_range"), zero_shot=g.get("zero_shot", False))
     fx = {"recipe": json.dumps(case), "tokens": [], "scores": [], "pos_scores": []}
     for s in range(len(hyp)):
         assert len(hyp[s]) == len(ours[s])

@@ -415,8 +415,31 @@ def criterion_forward(sd, cfg, sample, epsilon=0.1, use_rdrop=False, reg_alpha=1
 # beam search     models/sequence_generator.py:209-598,637-746 ; models/search.py:109-144
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
+class Trie:
+    # utils/trie.py:9-30 restated with plain dicts: insert a token list; next layer of a prefix ([eos] once the prefix left the trie)
+    def __init__(self, eos):
+        self.root, self.eos = {}, eos
+
+    def insert(self, word):
+        cur = self.root
+        for c in word:
+            cur = cur.setdefault(c, {})
+
+    def get_next_layer(self, word):
+        cur = self.root
+        for c in word:
+            cur = cur.get(c)
+            if cur is None:
+                return [self.eos]
+        return list(cur.keys())
+
+
 def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, len_penalty=1.0,
-             temperature=1.0, no_repeat_ngram_size=0, unk_penalty=0.0):
+             temperature=1.0, no_repeat_ngram_size=0, unk_penalty=0.0, constraint_trie=None, constraint_range=None,
+             zero_shot=False):
+    cstart = cend = None
+    if constraint_range is not None:                                                            # :82-86
+        cstart, cend = (int(v) for v in constraint_range.split(","))
     src = net_input["src_tokens"]
     bsz, src_len = src.shape
     V = cfg.vocab_size
@@ -449,7 +472,25 @@ def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, l
             enc = {k: (v.index_select(0, reorder_state) if isinstance(v, torch.Tensor) else v)
                    for k, v in enc.items()}
         logits = decoder_forward(sd, cfg, tokens[:, :step + 1], enc, incremental_state=inc)
-        lprobs = F.log_softmax(logits[:, -1, :] / temperature, dim=-1, dtype=torch.float32)   # :852,875
+        lg = logits[:, -1, :] / temperature                                                    # :852
+        allowed = None
+        if constraint_trie is not None:                                                         # :857-868, :878-885
+            allowed = torch.zeros(lg.shape, dtype=torch.bool)
+            for r, pref in enumerate(tokens[:, :step + 1].tolist()):
+                allowed[r, constraint_trie.get_next_layer([0] + pref[1:])] = True
+        if not zero_shot:
+            if allowed is not None:
+                lg = lg.masked_fill(~allowed, -math.inf)
+            if cstart is not None:                                                              # :869-872
+                lg[:, 4:cstart] = -math.inf
+                lg[:, cend:] = -math.inf
+        lprobs = F.log_softmax(lg, dim=-1, dtype=torch.float32)                                # :875
+        if zero_shot:
+            if allowed is not None:
+                lprobs = lprobs.masked_fill(~allowed, -math.inf)
+            if cstart is not None:                                                              # :886-889
+                lprobs[:, 4:cstart] = -math.inf
+                lprobs[:, cend:] = -math.inf
         if step < min_len:
             lprobs[:, EOS] = -math.inf                                                          # :381-383
         lprobs[lprobs != lprobs] = -math.inf

@@ -313,6 +313,20 @@ def synth_state_dict(cfg, seed=0, emb_std=0.02, w_std=0.02, rel_std=0.2):
     return sd
 
 
+def trie_words(n, max_len, seed, vocab=VOCAB, alphabet=12):
+    """Answer candidates for a constraint trie, as the tasks insert them ([bos] + answer + [eos], tasks/mm_tasks/vqa_gen.py:
+    158-167): n answers of 1..max_len tokens over a small random alphabet, so prefixes are shared and some answers are
+    prefixes of others."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(5000 + seed)
+    alpha = (torch.randperm(min(50265, vocab) - 4, generator=g)[:alphabet] + 4).tolist()
+    words = []
+    for _ in range(n):
+        L = int(torch.randint(1, max_len + 1, (1,), generator=g))
+        words.append([BOS] + [alpha[int(i)] for i in torch.randint(0, alphabet, (L,), generator=g)] + [EOS])
+    return words
+
+
 # ----------------------------------------------------------------------------------------------
 # synthetic batches (reference `sample` layout: data/mm_data/*_dataset.py collaters)
 # ----------------------------------------------------------------------------------------------

@@ -705,3 +705,109 @@ def test_maxpool_generic(dtype, C):
     yr.backward(dy.float())
     assert torch.equal(y.float(), yr)
     assert (x.grad.float() - xr.grad).abs().max().item() < (1e-6 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("step,ngram,crange,post", [(0, 0, None, False), (3, 0, None, False), (4, 2, None, False),
+                                                    (2, 0, (50, 400), False), (2, 0, (50, 400), True), (9, 3, None, False)])
+def test_beam_topk_matches_torch(dtype, step, ngram, crange, post):
+    """Fused beam-search tail (csrc/beam.cu) against the torch restatement of models/sequence_generator.py:352-437,852-889 +
+    models/search.py:119-144: candidate scores (1e-5) and flat indices (exact)."""
+    ops = _ops()
+    bsz, beam, V, min_len, max_len = 5, 4, 4099, 3, 9
+    g = torch.Generator(device="cpu").manual_seed(step * 7 + ngram)
+    logits = (torch.randn(bsz * beam, V, generator=g) * 3).cuda().to(dtype)
+    prev = torch.randn(bsz * beam, generator=g).cuda()
+    tokens = torch.randint(4, 12, (bsz * beam, max_len + 2), generator=g).cuda()      # small alphabet: repeated n-grams
+    tokens[:, 0] = 0
+    temperature, unk_pen = 0.7, 0.3
+    cs, ci, _ = ops.beam_topk(logits, beam, 2 * beam, temperature, prev if step > 0 else None, step0=(step == 0), eos=2, pad=1,
+                              unk=3, unk_penalty=unk_pen, block_eos=step < min_len, force_eos=step >= max_len, crange=crange,
+                              range_post=post, tokens=tokens, step=step, ngram=ngram)
+    x = logits.float() / temperature
+    if crange is not None and not post:
+        x[:, 4:crange[0]] = -math.inf
+        x[:, crange[1]:] = -math.inf
+    lp = torch.log_softmax(x, -1)
+    if crange is not None and post:
+        lp[:, 4:crange[0]] = -math.inf
+        lp[:, crange[1]:] = -math.inf
+    if step < min_len:
+        lp[:, 2] = -math.inf
+    lp[lp != lp] = -math.inf
+    lp[:, 1] = -math.inf
+    lp[:, 3] -= unk_pen
+    if step >= max_len:
+        lp[:, :2] = -math.inf
+        lp[:, 3:] = -math.inf
+    if ngram > 0 and step + 2 - ngram >= 0:
+        toks = tokens[:, :step + 1].tolist()
+        for r, gen in enumerate(toks):
+            key = gen[step + 2 - ngram: step + 1]
+            banned = [gen[i + ngram - 1] for i in range(len(gen) - ngram + 1) if gen[i:i + ngram - 1] == key]
+            if banned:
+                lp[r, banned] = -math.inf
+    l3 = lp.view(bsz, beam, V)
+    l3 = l3[:, ::beam, :].contiguous() if step == 0 else l3 + prev.view(bsz, beam, 1)
+    rs, ri = torch.topk(l3.view(bsz, -1), k=2 * beam)
+    finite = torch.isfinite(rs)
+    assert torch.equal(torch.isfinite(cs), finite)
+    assert (cs[finite] - rs[finite]).abs().max().item() < (1e-5 if dtype == torch.float32 else 1e-4)
+    # equal scores (common with bf16 logits): torch.topk's order among ties is unspecified; ours is flat index ascending
+    tol = 1e-5 if dtype == torch.float32 else 1e-4
+    flat = l3.view(bsz, -1)
+    assert (flat.gather(1, ci)[finite] - rs[finite]).abs().max().item() < tol        # every index holds the reference score of its rank
+    for b in range(bsz):
+        n = int(finite[b].sum())
+        assert len(set(ci[b, :n].tolist())) == n
+        clear = rs[b, :n] > rs[b, n - 1] + tol                                       # strictly inside the top k: must be selected
+        assert set(ri[b, :n][clear].tolist()) <= set(ci[b, :n].tolist())
+        tie = cs[b, 1:n] == cs[b, :n - 1]
+        assert bool((ci[b, 1:n][tie] > ci[b, :n - 1][tie]).all())
+
+
+def test_attention_decode_paged_and_bias_hoist():
+    """Decode attention (csrc/decode.cu): (a) K / V read through a page table == the same keys stored contiguously; (b) the
+    position term written once by a score_out launch and added as bias_in == the fused q.k + pos_q.pos_k launch."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    H, D, R, G, S, PL = 4, 256, 10, 5, 37, 16
+    mk = lambda *s: torch.randn(*s, generator=g).cuda().bfloat16()
+    q, pq = mk(R, 1, D) * 0.3, mk(R, 1, D) * 0.3
+    k, v, pk = mk(R // G, 48, D), mk(R // G, 48, D), mk(R // G, 48, D)
+    kpm = torch.zeros(R // G, 48, dtype=torch.uint8).cuda()
+    kpm[1, S - 5:] = 1
+    rows = torch.arange(R // G, dtype=torch.int32).cuda()
+    hs = (1 + 0.1 * torch.randn(H, generator=g)).cuda()
+    ref = ops.attention_decode(q, pq, k, pk, v, S, H, G, rows, None, kpm, hs)
+    bias = torch.empty(R, H, 40, dtype=torch.float32).cuda()
+    ops.attention_decode(pq, None, pk, None, None, S, H, G, rows, None, kpm, score_out=bias)
+    got = ops.attention_decode(q, None, k, None, v, S, H, G, rows, None, kpm, hs, bias_in=bias)
+    assert (got.float() - ref.float()).abs().max().item() < 2e-2
+    # fp64 restatement
+    f = lambda t_, L: t_.double().view(-1, L, H, 64)
+    sc = torch.einsum("rhd,rjhd->rhj", (q.double().view(R, H, 64)), f(k, 48).repeat_interleave(G, 0)[:, :S]) + \
+        torch.einsum("rhd,rjhd->rhj", (pq.double().view(R, H, 64)), f(pk, 48).repeat_interleave(G, 0)[:, :S])
+    sc = sc.masked_fill(kpm.bool().repeat_interleave(G, 0)[:, None, :S], -math.inf)
+    o = torch.einsum("rhj,rjhd->rhd", torch.softmax(sc, -1), f(v, 48).repeat_interleave(G, 0)[:, :S]) * hs.double().view(1, H, 1)
+    assert (ref.double().view(R, H, 64) - o).abs().max().item() < 2e-2
+    # paged self-attention layout: G = 1, keys of row r scattered over pages in a shuffled pool
+    R2, S2, L = 6, 21, 1
+    k2, v2 = mk(R2, 32, D), mk(R2, 32, D)
+    q2, pq2 = mk(R2, 1, D) * 0.3, mk(R2, 1, D) * 0.3
+    spk = mk(1, 32, D)
+    zero = torch.zeros(R2, dtype=torch.int32).cuda()
+    ref2 = ops.attention_decode(q2, pq2, k2, spk, v2, S2, H, 1, None, zero)
+    max_pages = 2
+    perm = torch.randperm(R2 * max_pages, generator=g)
+    pool = torch.zeros(R2 * max_pages, 2 * L, PL, D).cuda().bfloat16()
+    table = torch.empty(R2, max_pages, dtype=torch.int32)
+    for r in range(R2):
+        for p_ in range(max_pages):
+            slot = int(perm[r * max_pages + p_])
+            table[r, p_] = slot
+            pool[slot, 0] = k2[r, p_ * PL:(p_ + 1) * PL]
+            pool[slot, 1] = v2[r, p_ * PL:(p_ + 1) * PL]
+    got2 = ops.attention_decode(q2, pq2, pool[0, 0], spk, pool[0, 1], S2, H, 1, None, zero,
+                                page=(table.cuda(), PL, 2 * L * PL * D))
+    assert torch.equal(got2, ref2)

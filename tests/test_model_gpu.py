@@ -154,7 +154,8 @@ def test_state_dict_contract():
 
 
 @pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny", "gen_micro_varied", "gen_micro_varied_ngram",
-                                  "gen_base_b8"])
+                                  "gen_base_b8", "gen_micro_trie", "gen_micro_trie_zeroshot", "gen_micro_range",
+                                  "gen_micro_range_zeroshot"])
 def test_beam_search_tokens_bit_exact_fp32(name):
     """fp32 mode: beam-search output token ids must equal the reference's bit for bit; scores within 1e-4."""
     from musketeer_b200.sequence_generator import SequenceGenerator
@@ -165,7 +166,12 @@ def test_beam_search_tokens_bit_exact_fp32(name):
     model, task = build_product(cfg, sd, dtype=torch.float32)
     model.eval()
     sample = to_device(synth.make_batch(**case["batch"]), "cuda")
-    gen = SequenceGenerator([model], task.target_dictionary, **case["gen"])
+    gkw = dict(case["gen"])
+    if "trie" in case:          # constraint trie (utils/trie.py layout: nested children keyed by token), walked on the device
+        gkw["constraint_trie"] = oo.Trie(2)
+        for w in synth.trie_words(vocab=cfg.vocab_size, **case["trie"]):
+            gkw["constraint_trie"].insert(w)
+    gen = SequenceGenerator([model], task.target_dictionary, **gkw)
     # call 1 runs every decoder step eagerly, call 2 captures the steps as CUDA graphs (and replays them), call 3 replays:
     # all three must reproduce the reference's tokens
     for call in range(3):

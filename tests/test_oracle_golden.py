@@ -61,17 +61,25 @@ def test_train_case(name):
             assert abs(float(v.norm()) - fx["bn_running_norms"][k]) <= 1e-4 * fx["bn_running_norms"][k], k
 
 
-@pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny"])
+@pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny", "gen_micro_trie", "gen_micro_trie_zeroshot",
+                                  "gen_micro_range", "gen_micro_range_zeroshot"])
 def test_beam_search(name):
     fx = load_golden(name)
     case = fx["case"]
     cfg = synth.make_cfg(case["arch"], **case["cfg"])
-    sd = synth.synth_state_dict(cfg, seed=0, emb_std=case["emb_std"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
     sample = synth.make_batch(**case["batch"])
     g = case["gen"]
+    trie = None
+    if "trie" in case:
+        trie = oo.Trie(2)
+        for w in synth.trie_words(vocab=cfg.vocab_size, **case["trie"]):
+            trie.insert(w)
     hyp = oo.generate(sd, cfg, sample["net_input"], beam=g["beam_size"], max_len_a=g["max_len_a"],
                       max_len_b=g["max_len_b"], min_len=g["min_len"],
-                      no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0))
+                      no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0), temperature=g.get("temperature", 1.0),
+                      unk_penalty=g.get("unk_penalty", 0.0), constraint_trie=trie,
+                      constraint_range=g.get("constraint_range"), zero_shot=g.get("zero_shot", False))
     assert len(hyp) == len(fx["tokens"])
     for s in range(len(hyp)):
         assert len(hyp[s]) == len(fx["tokens"][s])
