@@ -214,9 +214,391 @@ __global__ void __launch_bounds__(kT) attn_decode_kernel(OfaDecodeArgs a) {
   }
 }
 
+// ---- long-key decode attention (cross-attention over the encoder output: S ~ 900, G beams per sentence) ----------------
+// One CTA = one (group, head), 128 threads.  K and V rows of this head (64 elements every ld elements) are streamed through a
+// ring of cp.async stages in shared memory (TK keys per stage, rows padded by 16 bytes so that 16-byte shared loads of
+// neighbouring keys fall into different banks): the copies of NST-1 stages are in flight while a stage is consumed, so the
+// DRAM latency is paid once per launch instead of once per tile (the register-only kernel above keeps one tile per warp in
+// flight and its online softmax serialises the tiles).  Two streamed passes over a score buffer in shared memory:
+//   pass 1  K tiles -> scores[g][j] = q_g . k_j (+ bias_in, key padding)          thread = (key, quarter of the 64 dims)
+//   softmax per query over the score buffer (one warp per query, fp32)            V tiles are already being fetched
+//   pass 2  V tiles -> out_g += p[g][j] * v_j                                      thread = (two output dims, quarter of the keys)
+// Algorithmic bytes per launch: groups * S * 64 * H * 2 tensors * sizeof(T).
+constexpr int TK = 32;       // keys per stage
+constexpr int NST = 3;       // stages of the ring (bf16, G = 5, S = 908: 33 KB per CTA -> 6 CTAs per SM, 768 CTAs in one wave)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kT) attn_decode_long_kernel(OfaDecodeArgs a) {
+  constexpr int ROWB = HD * (int)sizeof(T);            // bytes of one key row of this head
+  constexpr int PITCH = ROWB + 16;
+  constexpr int CH = ROWB / 16;                        // 16-byte chunks per row
+  constexpr int STAGE = TK * PITCH;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned char* ring = dsm;                           // [NST][TK][PITCH]
+  const int S = a.S, Sp = (S + TK - 1) / TK * TK;
+  float* sc = reinterpret_cast<float*>(dsm + NST * STAGE);   // [G][Sp]: bias / key-padding mask, then scores, then probabilities
+  __shared__ __align__(16) float qs[G][HD];
+  __shared__ float inv_l[G];
+  float (*wo)[G][HD] = reinterpret_cast<float(*)[G][HD]>(ring);      // [4][G][HD] partial outputs, over the drained ring
+  static_assert(sizeof(float) * (kT / 32) * G * HD <= (size_t)NST * STAGE, "partial outputs must fit the ring");
+  const int grp = blockIdx.x, h = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int row0 = grp * G;
+  pdl_sync();
+  const int krow = a.kv_row ? a.kv_row[grp] : grp;
+  for (int e = t; e < G * HD; e += kT) {
+    const int g = e / HD, d = e % HD;
+    qs[g][d] = row0 + g < a.R ? (float)reinterpret_cast<const T*>(a.q)[(size_t)(row0 + g) * a.ldq + h * HD + d] : 0.f;
+  }
+  const unsigned char* Kb = reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(a.k) + (size_t)krow * a.bsk + h * HD);
+  const unsigned char* Vb = a.v ? reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(a.v) + (size_t)krow * a.bsv + h * HD) : nullptr;
+  const size_t ldk_b = (size_t)a.ldk * sizeof(T), ldv_b = (size_t)a.ldv * sizeof(T);
+  const unsigned char* kpm = a.kpm ? a.kpm + (size_t)krow * a.kpm_stride : nullptr;
+  const int ntile = (S + TK - 1) / TK;
+  const uint32_t ring_u = smem_u32(ring);
+  // copy of tile `tile` of K (which = 0) or V (which = 1) into ring stage `st`; keys beyond S are zero-filled
+  auto issue = [&](int which, int tile, int st) {
+    const unsigned char* base = which ? Vb : Kb;
+    const size_t ld_b = which ? ldv_b : ldk_b;
+    for (int e = t; e < TK * CH; e += kT) {
+      const int key = e / CH, c = e % CH;
+      const int j = tile * TK + key;
+      const int ok = j < S;
+      cp_async16(ring_u + st * STAGE + key * PITCH + c * 16, base + (size_t)(ok ? j : 0) * ld_b + c * 16, ok ? 16 : 0);
+    }
+  };
+  const int total = Vb && !a.score_out ? 2 * ntile : ntile;     // unified tile stream: K tiles then V tiles
+  auto issue_seq = [&](int n) {
+    if (n < total) issue(n >= ntile, n >= ntile ? n - ntile : n, n % NST);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int n = 0; n < NST - 1; ++n) issue_seq(n);
+  // score buffer <- bias_in (0 without), -inf on padded keys and beyond S: coalesced loads while the first tiles are in flight
+  for (int e = t; e < G * Sp; e += kT) {
+    const int g = e / Sp, j = e - g * Sp;
+    float b = -CUDART_INF_F;
+    if (j < S && !(kpm && kpm[j]))
+      b = a.bias_in && row0 + g < a.R ? a.bias_in[((size_t)(row0 + g) * a.H + h) * a.bias_ld + j] : 0.f;
+    sc[e] = b;
+  }
+  // ---- pass 1: scores ---------------------------------------------------------------------------------------------------
+  const int key = t >> 2, part = t & 3;                // 16 of the 64 dims per thread
+  for (int n = 0; n < ntile; ++n) {
+    cp_async_wait<NST - 2>();
+    __syncthreads();                                   // stage n landed for everybody; stage (n-1) % NST is free again
+    issue_seq(n + NST - 1);
+    const unsigned char* row = ring + (n % NST) * STAGE + key * PITCH + part * (ROWB / 4);
+    float kf[16];
+    if constexpr (sizeof(T) == 2) {
+      load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(row), *reinterpret_cast<float(*)[8]>(&kf[0]));
+      load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(row) + 8, *reinterpret_cast<float(*)[8]>(&kf[8]));
+    } else {
+      load8<float>(reinterpret_cast<const float*>(row), *reinterpret_cast<float(*)[8]>(&kf[0]));
+      load8<float>(reinterpret_cast<const float*>(row) + 8, *reinterpret_cast<float(*)[8]>(&kf[8]));
+    }
+    const int j = n * TK + key;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&qs[g][part * 16 + c4 * 4]);
+        s = fmaf(q4.x, kf[c4 * 4], s); s = fmaf(q4.y, kf[c4 * 4 + 1], s);
+        s = fmaf(q4.z, kf[c4 * 4 + 2], s); s = fmaf(q4.w, kf[c4 * 4 + 3], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == g % 4) {                             // (zero-filled keys beyond S: -inf + 0)
+        const float b = sc[g * Sp + j];
+        if (a.score_out) {
+          if (j < S && row0 + g < a.R) a.score_out[((size_t)(row0 + g) * a.H + h) * a.bias_ld + j] = b == -CUDART_INF_F ? 0.f : b + s;
+        } else {
+          sc[g * Sp + j] = b + s;
+        }
+      }
+    }
+  }
+  if (a.score_out) { cp_async_wait<0>(); return; }
+  __syncthreads();
+  // ---- softmax over the score buffer: warp w takes queries w, w + 4 ---------------------------------------------------------
+  for (int g = warp; g < G; g += kT / 32) {
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < Sp; j += 32) mx = fmaxf(mx, sc[g * Sp + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float mu = mx == -CUDART_INF_F ? 0.f : mx;
+    float sum = 0.f;
+    for (int j = lane; j < Sp; j += 32) { const float p = __expf(sc[g * Sp + j] - mu); sc[g * Sp + j] = p; sum += p; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) inv_l[g] = sum > 0.f ? 1.f / sum : 0.f;
+  }
+  // ---- pass 2: out += p v ------------------------------------------------------------------------------------------------
+  float o0[G], o1[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { o0[g] = 0.f; o1[g] = 0.f; }
+  for (int n = ntile; n < 2 * ntile; ++n) {
+    cp_async_wait<NST - 2>();
+    __syncthreads();                                   // (the first one also publishes the softmax results)
+    issue_seq(n + NST - 1);
+    const unsigned char* tile = ring + (n % NST) * STAGE;
+    const int j0 = (n - ntile) * TK + warp * (TK / 4);       // this warp's 8 keys of the tile (p = 0 and v = 0 beyond S)
+#pragma unroll
+    for (int u4 = 0; u4 < TK / 4; u4 += 4) {
+      float2 v2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v2[u] = load2<T>(reinterpret_cast<const T*>(tile + (warp * (TK / 4) + u4 + u) * PITCH) + lane * 2);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&sc[g * Sp + j0 + u4]);
+        o0[g] = fmaf(p4.x, v2[0].x, o0[g]); o1[g] = fmaf(p4.x, v2[0].y, o1[g]);
+        o0[g] = fmaf(p4.y, v2[1].x, o0[g]); o1[g] = fmaf(p4.y, v2[1].y, o1[g]);
+        o0[g] = fmaf(p4.z, v2[2].x, o0[g]); o1[g] = fmaf(p4.z, v2[2].y, o1[g]);
+        o0[g] = fmaf(p4.w, v2[3].x, o0[g]); o1[g] = fmaf(p4.w, v2[3].y, o1[g]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                     // everybody is done reading the ring
+#pragma unroll
+  for (int g = 0; g < G; ++g) { wo[warp][g][lane * 2] = o0[g]; wo[warp][g][lane * 2 + 1] = o1[g]; }
+  __syncthreads();
+  const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  for (int e = t; e < G * HD; e += kT) {
+    const int g = e / HD, d = e % HD;
+    if (row0 + g >= a.R) continue;
+    const float oo = (wo[0][g][d] + wo[1][g][d]) + (wo[2][g][d] + wo[3][g][d]);
+    reinterpret_cast<T*>(a.o)[(size_t)(row0 + g) * a.ldo + h * HD + d] = (T)(oo * inv_l[g] * cs);
+  }
+}
+
+// ---- bf16 long-key decode attention on warp-level tensor-core tiles ----------------------------------------------------------
+// Same two streamed passes as attn_decode_long_kernel, but the arithmetic of a 16-key tile is 4 (q.k) + 8 (p.v) mma.sync
+// m16n8k16 instructions instead of ~1400 scalar ones (the SIMT kernel above spends 81 k warp instructions per CTA and is
+// issue-bound at 1.3 TB/s), and the four warps stream their own key tiles (tile i -> warp i % 4) through private two-stage
+// cp.async rings: no CTA barrier inside the passes.  The queries (G <= 8 rows) are the N = 8 side of q.k and rows 0..G-1 of the
+// M = 16 side of p.v; probabilities go to the tensor core in bf16 (un-normalised exp(s - max) in [0, 1], normalised in fp32).
+// One query token per row has nothing for tcgen05 (M = 128 tiles): the kernel is a DRAM stream, the MMAs only get the issue
+// slots out of its way.
+constexpr int TKW = 16;      // keys per warp tile
+constexpr int WPITCH = HD * 2 + 16;
+constexpr int WSTAGE = TKW * WPITCH;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kT) attn_decode_mma_kernel(OfaDecodeArgs a) {
+  using T = __nv_bfloat16;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned char* ring = dsm;                           // [4 warps][2 stages][TKW][WPITCH]
+  const int S = a.S, Sp = (S + TKW - 1) / TKW * TKW;
+  float* sc = reinterpret_cast<float*>(dsm + (kT / 32) * 2 * WSTAGE);   // [G][Sp]
+  float (*qs)[HD] = reinterpret_cast<float(*)[HD]>(ring + WSTAGE);   // [G][HD] q in fp32: warp 0's second stage, until pass 1 starts
+  static_assert(sizeof(float) * G * HD <= (size_t)WSTAGE, "q must fit one stage");
+  __shared__ float inv_l[G];
+  float (*wo)[G][HD] = reinterpret_cast<float(*)[G][HD]>(ring);
+  static_assert(sizeof(float) * (kT / 32) * G * HD <= (size_t)(kT / 32) * 2 * WSTAGE, "partial outputs must fit the ring");
+  const int grp = blockIdx.x, h = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int row0 = grp * G;
+  pdl_sync();
+  const int krow = a.kv_row ? a.kv_row[grp] : grp;
+  for (int e = t; e < G * HD; e += kT) {
+    const int g = e / HD, d = e % HD;
+    qs[g][d] = row0 + g < a.R ? (float)reinterpret_cast<const T*>(a.q)[(size_t)(row0 + g) * a.ldq + h * HD + d] : 0.f;
+  }
+  const unsigned char* Kb = reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(a.k) + (size_t)krow * a.bsk + h * HD);
+  const unsigned char* Vb = a.v ? reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(a.v) + (size_t)krow * a.bsv + h * HD) : nullptr;
+  const size_t ldk_b = (size_t)a.ldk * sizeof(T), ldv_b = (size_t)a.ldv * sizeof(T);
+  const unsigned char* kpm = a.kpm ? a.kpm + (size_t)krow * a.kpm_stride : nullptr;
+  const int ntile = Sp / TKW;
+  const int nw = ntile > warp ? (ntile - warp + 3) / 4 : 0;            // tiles of this warp: warp, warp + 4, ...
+  const bool two = Vb && !a.score_out;
+  const int total = two ? 2 * nw : nw;
+  const uint32_t wring = smem_u32(ring) + warp * 2 * WSTAGE;
+  // this lane copies half a row (4 x 16 bytes) of key lane / 2 of the tile
+  const int ckey = lane >> 1, cch = (lane & 1) * 4;
+  auto issue = [&](int n) {
+    if (n < total) {
+      const bool isv = n >= nw;
+      const int j = (warp + 4 * (isv ? n - nw : n)) * TKW + ckey;
+      const int ok = j < S ? 16 : 0;
+      const unsigned char* src = (isv ? Vb : Kb) + (size_t)(ok ? j : 0) * (isv ? ldv_b : ldk_b) + cch * 16;
+      const uint32_t dst = wring + (n & 1) * WSTAGE + ckey * WPITCH + cch * 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cp_async16(dst + c * 16, src + c * 16, ok);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int e = t; e < G * Sp; e += kT) {             // score buffer <- bias_in (0 without), -inf on padded keys and beyond S
+    const int g = e / Sp, j = e - g * Sp;
+    float b = -CUDART_INF_F;
+    if (j < S && !(kpm && kpm[j]))
+      b = a.bias_in && row0 + g < a.R ? a.bias_in[((size_t)(row0 + g) * a.H + h) * a.bias_ld + j] : 0.f;
+    sc[e] = b;
+  }
+  __syncthreads();
+  // B fragments of q (dims x queries): query lane / 4, dims ks * 16 + 2 * (lane % 4) + {0, 1} and + 8
+  const int fr = lane >> 2, fc = (lane & 3) * 2;
+  uint32_t bq[4][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const float* qr = &qs[fr < G ? fr : 0][ks * 16 + fc];
+    bq[ks][0] = fr < G ? pack_bf16(qr[0], qr[1]) : 0u;
+    bq[ks][1] = fr < G ? pack_bf16(qr[8], qr[9]) : 0u;
+  }
+  __syncthreads();                                     // q is in registers: its stage may be filled
+  // ldmatrix lane address inside a tile: row (l & 7) + 8 * ((l >> 3) & 1), column block (l >> 4) * 8 elements
+  const uint32_t lm_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * WPITCH + (lane >> 4) * 16);
+  // ---- pass 1: scores ---------------------------------------------------------------------------------------------------
+  for (int n = 0; n < nw; ++n) {
+    __syncwarp();
+    issue(n + 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t st = wring + (n & 1) * WSTAGE + lm_off;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[4];
+      ldmatrix_x4(af, st + ks * 32);
+      mma_bf16_16816(c, af, bq[ks][0], bq[ks][1]);
+    }
+    const int j = (warp + 4 * n) * TKW + fr;           // c[0], c[1]: key j, queries fc, fc + 1;  c[2], c[3]: key j + 8
+    if (fc < G) { sc[fc * Sp + j] += c[0]; sc[fc * Sp + j + 8] += c[2]; }
+    if (fc + 1 < G) { sc[(fc + 1) * Sp + j] += c[1]; sc[(fc + 1) * Sp + j + 8] += c[3]; }
+  }
+  __syncthreads();
+  if (a.score_out) {
+    cp_async_wait<0>();
+    for (int e = t; e < G * Sp; e += kT) {
+      const int g = e / Sp, j = e - g * Sp;
+      if (j < S && row0 + g < a.R) a.score_out[((size_t)(row0 + g) * a.H + h) * a.bias_ld + j] = sc[e] == -CUDART_INF_F ? 0.f : sc[e];
+    }
+    return;
+  }
+  // ---- softmax over the score buffer: warp w takes queries w, w + 4 ---------------------------------------------------------
+  for (int g = warp; g < G; g += kT / 32) {
+    float mx = -CUDART_INF_F;
+    for (int j = lane; j < Sp; j += 32) mx = fmaxf(mx, sc[g * Sp + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float mu = mx == -CUDART_INF_F ? 0.f : mx;
+    float sum = 0.f;
+    for (int j = lane; j < Sp; j += 32) { const float p = __expf(sc[g * Sp + j] - mu); sc[g * Sp + j] = p; sum += p; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) inv_l[g] = sum > 0.f ? 1.f / sum : 0.f;
+  }
+  __syncthreads();
+  // ---- pass 2: out += p v  (A = probabilities: rows = queries, B = V tile through ldmatrix.trans) --------------------------------
+  float o[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) { o[nb][0] = 0.f; o[nb][1] = 0.f; o[nb][2] = 0.f; o[nb][3] = 0.f; }
+  for (int n = nw; n < 2 * nw; ++n) {
+    __syncwarp();
+    issue(n + 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const int j0 = (warp + 4 * (n - nw)) * TKW;
+    uint32_t pa[4] = {0u, 0u, 0u, 0u};
+    if (fr < G) {
+      const float2 p0 = *reinterpret_cast<const float2*>(&sc[fr * Sp + j0 + fc]);
+      const float2 p1 = *reinterpret_cast<const float2*>(&sc[fr * Sp + j0 + fc + 8]);
+      pa[0] = pack_bf16(p0.x, p0.y);
+      pa[2] = pack_bf16(p1.x, p1.y);
+    }
+    const uint32_t st = wring + (n & 1) * WSTAGE + lm_off;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {                   // dims nb * 16 .. + 16: two n-blocks of 8
+      uint32_t bf[4];
+      ldmatrix_x4_trans(bf, st + nb * 32);
+      mma_bf16_16816(o[2 * nb], pa, bf[0], bf[1]);
+      mma_bf16_16816(o[2 * nb + 1], pa, bf[2], bf[3]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                     // everybody is done with the rings
+  if (fr < G) {
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { wo[warp][fr][nb * 8 + fc] = o[nb][0]; wo[warp][fr][nb * 8 + fc + 1] = o[nb][1]; }
+  }
+  __syncthreads();
+  const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  for (int e = t; e < G * HD; e += kT) {
+    const int g = e / HD, d = e % HD;
+    if (row0 + g >= a.R) continue;
+    const float oo = (wo[0][g][d] + wo[1][g][d]) + (wo[2][g][d] + wo[3][g][d]);
+    reinterpret_cast<T*>(a.o)[(size_t)(row0 + g) * a.ldo + h * HD + d] = (T)(oo * inv_l[g] * cs);
+  }
+}
+
+template <int G>
+int launch_decode_mma(const OfaDecodeArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)(kT / 32) * 2 * WSTAGE + (size_t)G * ((a.S + TKW - 1) / TKW * TKW) * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  static bool configured = false;
+  if (smem > 48 * 1024 && !configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_decode_mma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid((a.R + G - 1) / G, a.H);
+  return (int)ofa_launch_pdl(attn_decode_mma_kernel<G>, grid, kT, smem, st, a);
+}
+
+template <typename T, int G>
+int launch_decode_long(const OfaDecodeArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)NST * TK * (HD * sizeof(T) + 16) + (size_t)G * ((a.S + TK - 1) / TK * TK) * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_decode_long_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = 200 * 1024;
+  }
+  dim3 grid((a.R + G - 1) / G, a.H);
+  return (int)ofa_launch_pdl(attn_decode_long_kernel<T, G>, grid, kT, smem, st, a);
+}
+
 template <typename T>
 int launch_decode(const OfaDecodeArgs& a, cudaStream_t st) {
   dim3 grid((a.R + a.G - 1) / a.G, a.H);
+  // long key ranges without the self-attention extras (position keys, rel-pos LUT, pages): the staged two-pass kernel
+  if (a.S >= 64 && !a.pk && !a.tok_lut && !a.page_table) {
+    int rc = -1;
+    switch (a.G) {
+#define OFA_DEC_CASE(g) case g: \
+        if constexpr (sizeof(T) == 2) rc = launch_decode_mma<g>(a, st); else rc = launch_decode_long<T, g>(a, st); \
+        break;
+      OFA_DEC_CASE(1) OFA_DEC_CASE(2) OFA_DEC_CASE(3) OFA_DEC_CASE(4) OFA_DEC_CASE(5) OFA_DEC_CASE(6) OFA_DEC_CASE(7) OFA_DEC_CASE(8)
+#undef OFA_DEC_CASE
+    }
+    if (rc >= 0) return rc;      // -1: score buffer too large for shared memory -> the register kernel below
+  }
   switch (a.G) {
 #define OFA_DEC_CASE(g) case g: return (int)ofa_launch_pdl(attn_decode_kernel<T, g>, grid, kT, 0, st, a);
     OFA_DEC_CASE(1) OFA_DEC_CASE(2) OFA_DEC_CASE(3) OFA_DEC_CASE(4) OFA_DEC_CASE(5) OFA_DEC_CASE(6) OFA_DEC_CASE(7) OFA_DEC_CASE(8)

@@ -147,7 +147,7 @@ class SequenceGenerator(torch.nn.Module):
             else:
                 if reorder_state is not None:
                     model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
-                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
+                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc, padded_logits=True)
             # fused tail: temperature, constraints, log-softmax, masks, n-gram blocking, + beam scores, top 2*beam (csrc/beam.cu)
             lg = logits[:, -1, :]
             prev = scores.view(bsz, beam, -1)[:, :, step - 1].reshape(-1).contiguous() if step > 0 else None
@@ -223,7 +223,7 @@ class SequenceGenerator(torch.nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, pool=static["pool"]):
                 model.decoder.reorder_incremental_state_scripting(inc, static["order"])
-                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc)
+                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc, padded_logits=True)
             if static["pool"] is None:
                 static["pool"] = graph.pool()
             g = static["graphs"][key] = {"graph": graph, "logits": logits, "post": {k: st[k] for k in self._STATE_KEYS}}

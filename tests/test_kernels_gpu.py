@@ -709,7 +709,8 @@ def test_maxpool_generic(dtype, C):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("step,ngram,crange,post", [(0, 0, None, False), (3, 0, None, False), (4, 2, None, False),
-                                                    (2, 0, (50, 400), False), (2, 0, (50, 400), True), (9, 3, None, False)])
+                                                    (2, 0, (50, 400), False), (2, 0, (50, 400), True), (9, 3, None, False),
+                                                    (5, 0, "flat", False)])
 def test_beam_topk_matches_torch(dtype, step, ngram, crange, post):
     """Fused beam-search tail (csrc/beam.cu) against the torch restatement of models/sequence_generator.py:352-437,852-889 +
     models/search.py:119-144: candidate scores (1e-5) and flat indices (exact)."""
@@ -717,6 +718,9 @@ def test_beam_topk_matches_torch(dtype, step, ngram, crange, post):
     bsz, beam, V, min_len, max_len = 5, 4, 4099, 3, 9
     g = torch.Generator(device="cpu").manual_seed(step * 7 + ngram)
     logits = (torch.randn(bsz * beam, V, generator=g) * 3).cuda().to(dtype)
+    if crange == "flat":       # rows of equal logits: every entry ties (the candidate list of the threshold path overflows)
+        logits[::2] = 0.25
+        crange = None
     prev = torch.randn(bsz * beam, generator=g).cuda()
     tokens = torch.randint(4, 12, (bsz * beam, max_len + 2), generator=g).cuda()      # small alphabet: repeated n-grams
     tokens[:, 0] = 0

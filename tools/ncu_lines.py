@@ -28,13 +28,21 @@ def sass_lines(cubin, kernel):
 def main():
     rep, cubin, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    import os, shlex
+    # NCU_ARGS='--kernel-name regex:foo --launch-count 1' selects one launch of a multi-kernel report
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + shlex.split(os.environ.get("NCU_ARGS", "")),
+                         capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
     hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    data = []
+    for r in rows[hi + 1:]:            # the first launch only (a report may hold several)
+        if r and r[0] in ("Kernel Name", "Address"):
+            break
+        if len(r) == len(hdr):
+            data.append(r)
     lines = sass_lines(cubin, kernel)
     if len(lines) != len(data):
         print("warning: %d SASS instructions in the cubin vs %d in the report" % (len(lines), len(data)))
