@@ -172,6 +172,14 @@ int ofa_beam_topk_width(int K);
 int ofa_trie_advance(const int* trie_ptr, const int* trie_tok, const int* trie_child, const int* node_in, const long long* parent,
                      const long long* tok, long long tok_stride, int* node_out, int R, void* stream);
 
+/* ---- all-candidate scoring (utils/eval_utils.py:203-209; tasks/mm_tasks/vqa_gen.py:296-304, snli_ve.py:203-210): out[r] = sum
+ * over the positions p in [seg_off[r], seg_off[r+1]) of log_softmax(logits[p] restricted to the next layer of trie node
+ * node[p])[target[p]].  node[p] = -1: whole vocabulary, -2: position not counted; target == pad and empty layers count 0; a
+ * target outside its layer gives -inf.  logits [positions][ld], fp32 arithmetic, fixed summation order.                  */
+int ofa_trie_score(const void* logits, long long ld, int dtype, int V, const int* seg_off, const int* node,
+                   const long long* target, const int* trie_ptr, const int* trie_tok, int pad, float* out, int rows,
+                   void* stream);
+
 /* ---- 3x3 / stride 2 / padding 1 max-pool of the stem on bf16 NHWC activations (models/ofa/resnet.py:179,216).  idx: one
  * byte per output element (window position of the first maximum); the backward gathers, no atomics.  C % 8 == 0.      */
 int ofa_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, int N, int H, int W, int C, void* stream);

@@ -338,6 +338,58 @@ __global__ void trie_advance_kernel(const int* __restrict__ trie_ptr, const int*
   node_out[r] = out;
 }
 
+// All-candidate scoring (utils/eval_utils.py:203-209, tasks/mm_tasks/vqa_gen.py:296-304): for every candidate row the sum over
+// its counted positions of log_softmax(logits restricted to the trie's next layer)[target].  The reference builds a dense bool
+// mask [rows, T, V] on the host per chunk, masked_fills the logits, takes a full-vocabulary log-softmax and gathers; here a
+// position only reads the logits of its node's children.  One CTA per row, positions in order (a fixed summation order).
+//   node[p] >= 0: children of that trie node;  -1: the whole vocabulary;  -2: position does not count (prompt / padding).
+template <typename T>
+__global__ void __launch_bounds__(128) trie_score_kernel(const T* __restrict__ logits, long long ld, int V, const int* __restrict__ seg_off,
+                                                         const int* __restrict__ node, const long long* __restrict__ target,
+                                                         const int* __restrict__ trie_ptr, const int* __restrict__ trie_tok, int pad,
+                                                         float* __restrict__ out) {
+  pdl_sync();
+  __shared__ float red[4];
+  __shared__ int found_s;
+  const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  float total = 0.f;
+  for (int p = seg_off[r]; p < seg_off[r + 1]; ++p) {
+    const int nd = node[p];
+    const long long tgt = target[p];
+    if (nd == -2 || tgt == pad) continue;
+    const int* al = nd >= 0 ? trie_tok + trie_ptr[nd] : nullptr;
+    const int n = nd >= 0 ? trie_ptr[nd + 1] - trie_ptr[nd] : V;
+    if (n == 0) continue;                             // empty next layer: the mask row is all False (eval_utils.py:208)
+    const T* x = logits + (size_t)p * ld;
+    if (t == 0) found_s = 0;
+    float mx = -CUDART_INF_F;
+    bool found = false;
+    for (int e = t; e < n; e += 128) {
+      const int v = al ? al[e] : e;
+      found = found || v == tgt;
+      mx = fmaxf(mx, (float)x[v]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = mx;
+    if (found) found_s = 1;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    const bool hit = found_s != 0;
+    float sum = 0.f;
+    for (int e = t; e < n; e += 128) sum += expf((float)x[al ? al[e] : e] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = (red[0] + red[1]) + (red[2] + red[3]);
+    total += hit ? ((float)x[tgt] - mx) - logf(sum) : -CUDART_INF_F;
+  }
+  if (t == 0) out[r] = total;
+}
+
 template <typename T>
 int launch_rows(const OfaBeamArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)((a.V + 31) / 32) * 4;
@@ -385,5 +437,20 @@ extern "C" int ofa_trie_advance(const int* trie_ptr, const int* trie_tok, const 
   OFA_CUDA(ofa_launch_pdl(trie_advance_kernel, dim3((R + 127) / 128), 128, 0, (cudaStream_t)stream, trie_ptr, trie_tok, trie_child,
                           node_in, parent, tok, tok_stride, node_out, R));
   OFA_LAUNCH_CHECK("trie_advance_kernel");
+  return 0;
+}
+
+extern "C" int ofa_trie_score(const void* logits, long long ld, int dtype, int V, const int* seg_off, const int* node,
+                              const long long* target, const int* trie_ptr, const int* trie_tok, int pad, float* out, int rows,
+                              void* stream) {
+  OFA_CHECK(rows > 0 && V > 0 && logits && seg_off && node && target && out, "ofa_trie_score: null operand or empty problem");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == OFA_BF16)
+    OFA_CUDA(ofa_launch_pdl(trie_score_kernel<__nv_bfloat16>, dim3(rows), 128, 0, st, (const __nv_bfloat16*)logits, ld, V, seg_off, node, target, trie_ptr, trie_tok, pad, out));
+  else if (dtype == OFA_F32)
+    OFA_CUDA(ofa_launch_pdl(trie_score_kernel<float>, dim3(rows), 128, 0, st, (const float*)logits, ld, V, seg_off, node, target, trie_ptr, trie_tok, pad, out));
+  else
+    return ofa_set_error("ofa_trie_score: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("trie_score_kernel");
   return 0;
 }

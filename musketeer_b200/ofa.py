@@ -289,7 +289,16 @@ class TransformerDecoderLayer(nn.Module, _FFNMixin):
         x = self._post_attn(self.self_attn, o, self.self_attn_ln, x)
         h, x = _ln(self.encoder_attn_layer_norm, x, fork=True)
         k, v = cross_kv(self.encoder_attn)
-        o = self.encoder_attn(h, k, v, cpq, cpk, None, None, cross_cfg)
+        G = cross_cfg.get("rows_per_sentence", 1)
+        if G > 1:
+            # G consecutive decoder rows (the candidates / hypotheses of one sentence) attend to ONE encoder row: cross-attention
+            # is independent per query position, so the rows of a sentence are folded into the query-length axis (a view)
+            # instead of replicating the encoder output G times (utils/eval_utils.py:192-201 repeat_interleaves it)
+            B, T, d = h.shape
+            o = self.encoder_attn(h.reshape(B // G, G * T, d), k, v, cpq.reshape(B // G, G * T, d), cpk, None, None, cross_cfg)
+            o = o.reshape(B, T, d)
+        else:
+            o = self.encoder_attn(h, k, v, cpq, cpk, None, None, cross_cfg)
         x = self._post_attn(self.encoder_attn, o, self.cross_attn_ln, x)
         return self._ffn(x)
 
@@ -664,6 +673,10 @@ class TransformerDecoder(FairseqIncrementalDecoder):
             self_cfg = {"causal": True, "kpm": self_kpm, "q_pos_off": t0,
                         "bias": {"q_text_off": 0, "k_text_off": 0}}
             cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}, "fused_kv": True}
+            if enc.shape[0] != B:           # un-replicated encoder output: rows b*G .. b*G + G - 1 belong to sentence b
+                if B % enc.shape[0] != 0:
+                    raise ValueError("decoder rows (%d) must be a multiple of the encoder batch (%d)" % (B, enc.shape[0]))
+                cross_cfg["rows_per_sentence"] = B // enc.shape[0]
         rel1d = self.rel_bucket_1d()
         inner_states = [x.transpose(0, 1)]
         for i, layer in enumerate(self.layers):
@@ -679,6 +692,11 @@ class TransformerDecoder(FairseqIncrementalDecoder):
             def cross_kv(attn, i=i):
                 if incremental:
                     return incremental_state["_ofa_b200"]["cross"][i]
+                memo = encoder_out.get("_cross_kv_memo") if not self.training else None
+                if memo is not None:        # repeated teacher-forced passes over one encoder output (all-candidate scoring)
+                    if i not in memo:
+                        memo[i] = attn.project_kv(enc, fused=True)
+                    return memo[i]
                 return attn.project_kv(enc, fused=True)
 
             x = layer(x, self_kv, cross_kv, spq, spk, cpq, cpk, tok_lut, self_cfg, cross_cfg)

@@ -1186,6 +1186,19 @@ def trie_advance(trie, node_in, parent, tok):
     return out
 
 
+def trie_score(logits, seg_off, node, target, trie, pad):
+    """All-candidate scores (csrc/beam.cu trie_score_kernel): logits [P, V] of the counted positions, seg_off int32 [rows + 1],
+    node int32 [P], target int64 [P]; trie = (ptr, tok, child) CSR or None when every node is -1 / -2.  Returns fp32 [rows]."""
+    _need_cuda(logits)
+    P, V = logits.shape
+    assert logits.stride(1) == 1 and node.numel() == P and target.numel() == P
+    rows = seg_off.numel() - 1
+    out = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    call("ofa_trie_score", _p(logits), logits.stride(0), _dt(logits), V, _p(seg_off), _p(node), _p(target),
+         _p(trie[0]) if trie is not None else None, _p(trie[1]) if trie is not None else None, int(pad), _p(out), rows, _st())
+    return out
+
+
 def cache_gather(src, dst, order, rows, L):
     """dst[p, r, :L] = src[p, order[r], :L] for caches [planes, cap_rows, cap_len, D] (beam reorder, valid prefix only)."""
     planes, cap_rows, cap_len, D = src.shape

@@ -17,9 +17,10 @@ import torch
 from . import ops
 
 
-def flatten_trie(trie, device):
+def flatten_trie(trie, device, return_index=False):
     """utils/trie.py Trie -> CSR tensors (ptr [n+1], tok [e], child [e]); the root is node 0.  Children are stored in
-    insertion order, like `list(node.child.keys())`.  Nodes are TreeNode objects (`.child` dict) or plain nested dicts."""
+    insertion order, like `list(node.child.keys())`.  Nodes are TreeNode objects (`.child` dict) or plain nested dicts.
+    return_index=True also returns {id(node object): CSR node index}."""
     nodes, ptr, tok, child = [trie.root], [0], [], []
     i = 0
     while i < len(nodes):
@@ -31,7 +32,10 @@ def flatten_trie(trie, device):
         ptr.append(len(tok))
         i += 1
     mk = lambda v: torch.tensor(v if v else [0], dtype=torch.int32, device=device)
-    return mk(ptr), mk(tok), mk(child)
+    csr = (mk(ptr), mk(tok), mk(child))
+    if return_index:
+        return csr, {id(n): k for k, n in enumerate(nodes)}
+    return csr
 
 
 class SequenceGenerator(torch.nn.Module):

@@ -289,6 +289,87 @@ def run_gen_case(name, case):
         name, len(hyp), hyp[0][0]["tokens"].tolist(), ["%.3f" % x for x in gaps]))
 
 
+ALLCAND_CASES = {
+    # all-candidate scoring: utils/eval_utils.py:161-214 with a VQA-style answer trie, prompts of different
+    # lengths (prompt_type 'prev_output' puts the question in the decoder prompt), two chunks of candidates
+    "allcand_micro": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                          batch=dict(bsz=3, src_len=11, tgt_len=2, img=64, seed=60, vocab=4099, n_pad=2),
+                          answers=dict(n=14, max_len=3, seed=7), valid_batch_size=8, prompt_lens=[1, 3, 2]),
+    "allcand_tiny": dict(arch="ofa_tiny", cfg={}, emb_std=0.05, w_std=0.3,
+                         batch=dict(bsz=2, src_len=12, tgt_len=2, img=256, seed=61, n_pad=3),
+                         answers=dict(n=9, max_len=4, seed=8), valid_batch_size=5, prompt_lens=[1, 1]),
+}
+
+
+def allcand_prompts(case, vocab):
+    g = torch.Generator(device="cpu").manual_seed(900 + case["batch"]["seed"])
+    return [[0] + torch.randint(4, vocab, (n - 1,), generator=g).tolist() for n in case["prompt_lens"]]
+
+
+def run_allcand_case(name, case):
+    """The reference's own eval_vqa_gen (its function text is compiled from utils/eval_utils.py where it lies; the module's
+    import of every task is not needed for it) on the unmodified reference model, against the oracle's restatement."""
+    import ast
+    import importlib
+    import math
+    from utils.trie import Trie as RefTrie
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
+    model, task = rh.build_model(cfg, sd)
+    model.eval()
+    sample = synth.make_batch(**case["batch"])
+    answers = synth.candidate_answers(vocab=cfg.vocab_size, **case["answers"])
+    ref_trie, our_trie = RefTrie(2), oo.Trie(2)
+    for a in answers:
+        ref_trie.insert([0] + a.tolist() + [2])
+        our_trie.insert([0] + a.tolist() + [2])
+    # tasks/mm_tasks/vqa_gen.py:168-183 (build_model): per-answer constraint masks, chunked by valid_batch_size
+    masks = []
+    for a in answers:
+        m = torch.zeros((len(a) + 1, cfg.vocab_size)).bool()
+        for i in range(len(a) + 1):
+            m[i][ref_trie.get_next_layer([0] + a[:i].tolist())] = True
+        masks.append(m)
+    vb = case["valid_batch_size"]
+    task.valid_answers_list = [answers[i:i + vb] for i in range(0, len(answers), vb)]
+    task.valid_constraint_masks_list = [masks[i:i + vb] for i in range(0, len(answers), vb)]
+    task.index2ans = {i: i for i in range(len(answers))}
+    task.src_dict = task.tgt_dict = task.target_dictionary
+    sample = dict(sample, decoder_prompts=allcand_prompts(case, cfg.vocab_size), id=torch.arange(case["batch"]["bsz"]),
+                  ref_dict=[{} for _ in range(case["batch"]["bsz"])])
+    src = open(os.path.join(rh.REF, "utils", "eval_utils.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "eval_vqa_gen"][0]
+    ns = {"torch": torch, "math": math, "data_utils": importlib.import_module("data.data_utils")}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "utils/eval_utils.py", "exec"), ns)
+    # the function returns only the argmax; capture the score matrix it builds through torch.cat of its valid_result list
+    captured = {}
+    real_cat = torch.cat
+
+    def spy_cat(ts, dim=0, **kw):
+        out = real_cat(ts, dim=dim, **kw)
+        if dim == -1 and out.dim() == 2 and out.shape == (case["batch"]["bsz"], len(answers)):
+            captured["scores"] = out.clone()
+        return out
+    # torch >= 1.13 promotes cat([tensor([]) (float32, an empty prompt tail), int64, int64]) to float; the torch 1.8 the reference
+    # pins skipped empty operands.  Same stand-in policy as ref_harness' kl_div: the empty list becomes an empty int64 tensor.
+    def compat_tensor(x, **kw):
+        return torch.tensor(x, dtype=torch.long) if isinstance(x, list) and len(x) == 0 and not kw else torch.tensor(x, **kw)
+    over = {"cat": spy_cat, "tensor": compat_tensor}
+    ns["torch"] = type("T", (), {"__getattr__": lambda self, k: over[k] if k in over else getattr(torch, k)})()
+    with torch.no_grad():
+        results, _ = ns["eval_vqa_gen"](task, None, [model], sample, beam_search_vqa_eval=False)
+    ref_scores = captured["scores"]
+    ours = oo.score_all_candidates(sd, cfg, sample["net_input"], sample["decoder_prompts"], answers, our_trie, vb)
+    err = float((ours - ref_scores).abs().max())
+    assert err < 1e-4, err
+    assert ours.argmax(1).tolist() == [r["answer"] for r in results]
+    top2 = ref_scores.topk(2, dim=1).values
+    fx = {"recipe": json.dumps(case), "scores": ref_scores, "predicts": [r["answer"] for r in results]}
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print("%-24s scores %s predicts %s oracle-vs-ref maxabs %.1e top-2 gaps %s" % (
+        name, tuple(ref_scores.shape), fx["predicts"], err, ["%.3f" % float(x) for x in (top2[:, 0] - top2[:, 1])]))
+
+
 def add_bf16_deviation(name, case):
     """How far the REFERENCE ALGORITHM ITSELF moves when it is executed in bfloat16 (`model.bfloat16()` semantics of
     trainer.py:99-106: bf16 weights, activations and images; the oracle on the host): stored next to the fp32 reference
@@ -356,6 +437,9 @@ def main():
     for name, case in CASES.items():
         if not only or name in only:
             run_train_case(name, case)
+    for name, case in ALLCAND_CASES.items():
+        if not only or name in only:
+            run_allcand_case(name, case)
     for name, case in GEN_CASES.items():
         if not only or name in only:
             run_gen_case(name, case)

@@ -559,6 +559,57 @@ def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, l
     return finalized
 
 
+def _collate(items, pad):
+    # data/data_utils.py collate_tokens, left_pad=False: right-padded stack (1-D token lists or 2-D bool mask rows)
+    n = max(v.size(0) for v in items)
+    out = items[0].new_full((len(items), n) + tuple(items[0].shape[1:]), pad)
+    for i, v in enumerate(items):
+        out[i, :v.size(0)] = v
+    return out
+
+
+def candidate_masks(answers, trie, vocab):
+    # tasks/mm_tasks/vqa_gen.py:170-176: mask row i of an answer = next layer of the trie after [bos] + answer[:i]
+    masks = []
+    for ans in answers:
+        m = torch.zeros(len(ans) + 1, vocab, dtype=torch.bool)
+        for i in range(len(ans) + 1):
+            m[i, trie.get_next_layer([BOS] + ans[:i].tolist())] = True
+        masks.append(m)
+    return masks
+
+
+@torch.no_grad()
+def score_all_candidates(sd, cfg, net_input, decoder_prompts, answers, trie, valid_batch_size):
+    """All-candidate inference: utils/eval_utils.py:161-214 (= tasks/mm_tasks/vqa_gen.py:257-306, snli_ve.py:171-215).
+    Encoder once; per chunk of `valid_batch_size` answers the decoder scores prompt + answer + eos teacher-forced for every
+    (sentence, answer) pair with the encoder output replicated per answer; logits outside the trie's next layer are -inf before
+    the log-softmax; the score is the sum of the target log-probabilities over the answer positions.  Returns [B, n_answers]."""
+    V = cfg.vocab_size
+    enc = encoder_forward(sd, cfg, net_input["src_tokens"], net_input.get("patch_images"), net_input.get("patch_masks"),
+                          training=False)
+    masks = candidate_masks(answers, trie, V)
+    eos = torch.tensor([EOS])
+    result = []
+    for c0 in range(0, len(answers), valid_batch_size):                                         # vqa_gen.py:181-183
+        ans, msk = answers[c0:c0 + valid_batch_size], masks[c0:c0 + valid_batch_size]
+        C = len(ans)
+        tgt = _collate([torch.cat([torch.tensor(dp[1:], dtype=torch.long), a, eos]) for dp in decoder_prompts for a in ans], PAD)
+        prev = _collate([torch.cat([torch.tensor(dp, dtype=torch.long), a]) for dp in decoder_prompts for a in ans], PAD)
+        cm = _collate([torch.cat([torch.zeros(len(dp) - 1, V, dtype=torch.bool), m]) for dp in decoder_prompts for m in msk], False)
+        rep = {"encoder_out": enc["encoder_out"].repeat_interleave(C, 0),                      # :192-201
+               "encoder_padding_mask": enc["encoder_padding_mask"].repeat_interleave(C, 0),
+               "position_embeddings": enc["position_embeddings"].repeat_interleave(C, 0)}
+        logits = decoder_forward(sd, cfg, prev, rep)
+        logits = logits.masked_fill(~cm, -math.inf)                                             # :204
+        lprobs = F.log_softmax(logits.float(), dim=-1)
+        sc = lprobs.gather(-1, tgt.unsqueeze(-1)).squeeze(-1)
+        sc = sc.masked_fill(tgt.eq(PAD), 0)                                                     # :207
+        sc = sc.masked_fill((~cm).all(2), 0)                                                    # :208
+        result.append(sc.sum(1).view(-1, C))
+    return torch.cat(result, dim=-1)
+
+
 def _finalize(step, bbsz_idx, eos_scores, tokens, scores, finalized, finished, beam, max_len, lenpen):
     # finalize_hypos  models/sequence_generator.py:637-746
     tokens_clone = tokens.index_select(0, bbsz_idx)[:, 1:step + 2].clone()

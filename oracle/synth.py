@@ -327,6 +327,19 @@ def trie_words(n, max_len, seed, vocab=VOCAB, alphabet=12):
     return words
 
 
+def candidate_answers(n, max_len, seed, vocab=VOCAB, alphabet=12):
+    """n DISTINCT answers (token tensors without bos / eos) over a small alphabet, as ans2label_dict's keys would encode."""
+    seen, out = set(), []
+    for w in trie_words(4 * n, max_len, seed, vocab, alphabet):
+        a = tuple(w[1:-1])
+        if a not in seen:
+            seen.add(a)
+            out.append(torch.tensor(a, dtype=torch.long))
+        if len(out) == n:
+            break
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # synthetic batches (reference `sample` layout: data/mm_data/*_dataset.py collaters)
 # ----------------------------------------------------------------------------------------------

@@ -197,6 +197,70 @@ def test_beam_search_tokens_bit_exact_fp32(name):
                 assert torch.equal(h["tokens"], r["tokens"]) and abs(float(h["score"]) - float(r["score"])) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["allcand_micro", "allcand_tiny"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_all_candidate_scorer_matches_reference(name, dtype):
+    """AllCandidateScorer (un-replicated encoder output, cross K / V projected once, vocabulary projection on the
+    counted positions only, trie-restricted log-softmax on the device) against the scores of the reference's eval_vqa_gen
+    (utils/eval_utils.py:161-214, golden): fp32 1e-4 + same answers; bf16 within the gap the ranking tolerates."""
+    from musketeer_b200.scorers import AllCandidateScorer
+    from oracle.make_golden import allcand_prompts
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
+    model, task = build_product(cfg, sd, dtype=dtype)
+    model.eval()
+    answers = synth.candidate_answers(vocab=cfg.vocab_size, **case["answers"])
+    trie = oo.Trie(2)
+    for a in answers:
+        trie.insert([0] + a.tolist() + [2])
+    sample = to_device(synth.make_batch(**case["batch"]), "cuda")
+    if dtype == torch.bfloat16:
+        sample["net_input"]["patch_images"] = sample["net_input"]["patch_images"].bfloat16()
+    sample["decoder_prompts"] = allcand_prompts(case, cfg.vocab_size)
+    scorer = AllCandidateScorer(model, answers, trie, case["valid_batch_size"])
+    sc = scorer.score(sample).cpu()
+    ref = fx["scores"]
+    assert sc.shape == ref.shape
+    err = (sc - ref).abs().max().item()
+    print("all-candidate scores max-abs error %.2e (%s)" % (err, dtype))
+    if dtype == torch.float32:
+        assert err < 1e-4
+        assert sc.argmax(1).tolist() == fx["predicts"]
+        # chunking must not matter: one chunk for all answers
+        one = AllCandidateScorer(model, answers, trie, len(answers)).score(sample).cpu()
+        assert (one - ref).abs().max().item() < 1e-4
+    else:
+        # bound = max(0.05, 1.25 x how far the reference algorithm itself moves in bf16 (the oracle on the host, bf16 weights / images))
+        sdb = tie({k: (v.bfloat16() if v.is_floating_point() else v) for k, v in sd.items()})
+        nib = dict(synth.make_batch(**case["batch"])["net_input"])
+        nib["patch_images"] = nib["patch_images"].bfloat16()
+        dev_bf16 = (oo.score_all_candidates(sdb, cfg, nib, sample["decoder_prompts"], answers, trie, case["valid_batch_size"]).float()
+                    - ref).abs().max().item()
+        print("reference algorithm in bf16 deviates by %.2e" % dev_bf16)
+        assert err <= max(0.05, 1.25 * dev_bf16), (err, dev_bf16)
+        top2 = ref.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 2 * err
+        assert [p for p, c in zip(sc.argmax(1).tolist(), clear) if c] == [p for p, c in zip(fx["predicts"], clear) if c]
+    # unconstrained scoring = plain log-softmax of the teacher-forced decoder (fp32 check against torch on the product's logits)
+    if dtype == torch.float32:
+        plain = AllCandidateScorer(model, answers[:3], None, 3).score(sample).cpu()
+        ni = sample["net_input"]
+        enc = model.encoder(ni["src_tokens"], src_lengths=ni["src_lengths"], patch_images=ni["patch_images"],
+                            patch_masks=ni["patch_masks"])
+        for b, pr in enumerate(sample["decoder_prompts"]):
+            for c, a in enumerate(answers[:3]):
+                prev = torch.tensor([pr + a.tolist()], device="cuda")
+                e1 = {k: ([v[0][:, b:b + 1] if k == "encoder_out" else v[0][b:b + 1]] if isinstance(v, list) and v else v)
+                      for k, v in enc.items()}
+                lg, _ = model.decoder(prev, encoder_out=e1)
+                lp = torch.log_softmax(lg[0].float(), -1)
+                tg = a.tolist() + [2]
+                want = sum(float(lp[len(pr) - 1 + i, tg[i]]) for i in range(len(tg)))
+                assert abs(float(plain[b, c]) - want) < 2e-4, (b, c, float(plain[b, c]), want)
+
+
 def test_incremental_decoder_matches_teacher_forcing():
     """Incremental decoding (KV cache) must reproduce the teacher-forced logits position by position (fp32, 1e-4)."""
     fx = load_golden("micro_text_only")

@@ -88,6 +88,25 @@ def test_beam_search(name):
             assert abs(float(h["score"]) - sc) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["allcand_micro", "allcand_tiny"])
+def test_all_candidate_scores(name):
+    """Oracle restatement of utils/eval_utils.py:161-214 against the scores of the reference's own eval_vqa_gen (golden)."""
+    from oracle.make_golden import allcand_prompts
+    fx = load_golden(name)
+    case = fx["case"]
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
+    sample = synth.make_batch(**case["batch"])
+    answers = synth.candidate_answers(vocab=cfg.vocab_size, **case["answers"])
+    trie = oo.Trie(2)
+    for a in answers:
+        trie.insert([0] + a.tolist() + [2])
+    sc = oo.score_all_candidates(sd, cfg, sample["net_input"], allcand_prompts(case, cfg.vocab_size), answers, trie,
+                                 case["valid_batch_size"])
+    assert (sc - fx["scores"]).abs().max().item() < 1e-4
+    assert sc.argmax(1).tolist() == fx["predicts"]
+
+
 def test_bucket_tables_bit_exact():
     """Integer tables must be bit-exact (north_star); closed forms vs the reference builders' output."""
     import json, os
