@@ -172,6 +172,11 @@ int ofa_beam_topk_width(int K);
 int ofa_trie_advance(const int* trie_ptr, const int* trie_tok, const int* trie_child, const int* node_in, const long long* parent,
                      const long long* tok, long long tok_stride, int* node_out, int R, void* stream);
 
+/* ---- input hand-off: decoded uint8 HWC pixels [N][H][W][3] -> normalised [N][3][H][W] activations (bf16 or fp32) with the
+ * host transforms of data/mm_data/*_dataset.py (ToTensor: x / 255; Normalize: (x - mean) / std; IEEE fp32, same order), so the
+ * loader ships 1 byte per value instead of 4 (trainer.py:1246-1284 moves the fp32 tensor, then casts).  mean3 / std3: HOST floats. */
+int ofa_normalize_u8(const void* x, void* y, int N, int H, int W, const float* mean3, const float* std3, int dtype, void* stream);
+
 /* ---- all-candidate scoring (utils/eval_utils.py:203-209; tasks/mm_tasks/vqa_gen.py:296-304, snli_ve.py:203-210): out[r] = sum
  * over the positions p in [seg_off[r], seg_off[r+1]) of log_softmax(logits[p] restricted to the next layer of trie node
  * node[p])[target[p]].  node[p] = -1: whole vocabulary, -2: position not counted; target == pad and empty layers count 0; a

@@ -207,3 +207,79 @@ extern "C" int ofa_subsample2(const void* src, void* dst, int N, int H, int W, i
   OFA_LAUNCH_CHECK("subsample2_kernel");
   return 0;
 }
+
+// ---- input hand-off: uint8 HWC images -> normalised NCHW activations on the device --------------------------
+// The reference normalises on the host (data/mm_data/*_dataset.py: transforms.ToTensor() = x / 255, then
+// transforms.Normalize(mean, std) = (x - mean) / std, all fp32) and ships 4 bytes per sample value through PCIe
+// (trainer.py:1246-1284 move_to_cuda, then apply_bfloat16).  Here the loader ships the decoded uint8 pixels (1 byte) and this
+// kernel applies the same three IEEE fp32 operations in the same order (bit-equal to the host result before the final cast).
+// HBM-bound: 3 bytes read, 3 * sizeof(T) written per pixel; four pixels per thread (three 32-bit loads, 8-byte plane stores).
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const unsigned char* __restrict__ x, T* __restrict__ y, long long npix,
+                                                           long long plane, float m0, float m1, float m2, float s0, float s1,
+                                                           float s2) {
+  pdl_sync();
+  // npix = N * H * W pixels in all; plane = H * W; pixel p of image n -> y[(n * 3 + c) * plane + p]
+  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q >= npix) return;
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  unsigned char b[12];
+  const bool full = q + 4 <= npix && (plane & 3) == 0;      // four pixels of one image, 12 bytes at a 4-byte aligned address
+  if (full) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(x + q * 3);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { b[i] = (w0 >> (8 * i)) & 255; b[4 + i] = (w1 >> (8 * i)) & 255; b[8 + i] = (w2 >> (8 * i)) & 255; }
+  } else {
+    for (int i = 0; i < 12; ++i) b[i] = q * 3 + i < npix * 3 ? x[q * 3 + i] : 0;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    T o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[i] = cvt_out<T>(__fdiv_rn(__fsub_rn(__fdiv_rn((float)b[i * 3 + c], 255.f), mean[c]), sd[c]));
+    if (full) {
+      const long long n = q / plane, p = q - n * plane;
+      T* dst = y + (n * 3 + c) * plane + p;
+      if constexpr (sizeof(T) == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);
+      else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+    } else {
+      for (int i = 0; i < 4 && q + i < npix; ++i) {
+        const long long n = (q + i) / plane, p = (q + i) - n * plane;
+        y[(n * 3 + c) * plane + p] = o[i];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ofa_normalize_u8(const void* x, void* y, int N, int H, int W, const float* mean3, const float* std3, int dtype,
+                                void* stream) {
+  OFA_CHECK(N > 0 && H > 0 && W > 0 && x && y && mean3 && std3, "ofa_normalize_u8: null operand or empty problem");
+  OFA_CHECK(((uintptr_t)x & 3) == 0 && ((uintptr_t)y & 15) == 0, "ofa_normalize_u8: unaligned buffers");
+  const long long plane = (long long)H * W, npix = plane * N;
+  const long long threads = (npix + 3) / 4;
+  dim3 grid((unsigned)((threads + 255) / 256));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == OFA_BF16)
+    OFA_CUDA(ofa_launch_pdl(normalize_u8_kernel<__nv_bfloat16>, grid, 256, 0, st, (const unsigned char*)x, (__nv_bfloat16*)y, npix, plane,
+                            mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]));
+  else if (dtype == OFA_F32)
+    OFA_CUDA(ofa_launch_pdl(normalize_u8_kernel<float>, grid, 256, 0, st, (const unsigned char*)x, (float*)y, npix, plane,
+                            mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]));
+  else
+    return ofa_set_error("ofa_normalize_u8: bad dtype %d", dtype);
+  OFA_LAUNCH_CHECK("normalize_u8_kernel");
+  return 0;
+}

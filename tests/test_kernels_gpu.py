@@ -815,3 +815,41 @@ def test_attention_decode_paged_and_bias_hoist():
     got2 = ops.attention_decode(q2, pq2, pool[0, 0], spk, pool[0, 1], S2, H, 1, None, zero,
                                 page=(table.cuda(), PL, 2 * L * PL * D))
     assert torch.equal(got2, ref2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 64, 64), (2, 17, 23), (1, 384, 384)])
+def test_device_normalise_matches_host_transforms(dtype, shape):
+    """uint8 HWC pixels normalised on the device == ToTensor + Normalize on the host (data/mm_data/
+    caption_dataset.py:71-74: x / 255, then (x - mean) / std in fp32), bit for bit in fp32 and after the bf16 cast."""
+    from musketeer_b200.input_pipeline import normalize_images, IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+    B, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(H)
+    u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    for mean, std in (((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD)):
+        ref = u8.permute(0, 3, 1, 2).to(torch.float32).div(255)                                   # ToTensor
+        ref = ref.sub(torch.tensor(mean).view(1, 3, 1, 1)).div(torch.tensor(std).view(1, 3, 1, 1))  # Normalize
+        got = normalize_images(u8.cuda(), mean, std, dtype)
+        assert got.shape == (B, 3, H, W) and got.dtype == dtype
+        assert torch.equal(got.cpu(), ref.to(dtype))
+
+
+def test_prefetcher_hands_over_normalised_batches():
+    """DevicePrefetcher: pinned uint8 batches copied and normalised on a side stream arrive equal to the host pipeline's."""
+    from musketeer_b200.input_pipeline import DevicePrefetcher, pin
+    g = torch.Generator(device="cpu").manual_seed(5)
+    host = []
+    for i in range(4):
+        host.append(pin({"id": torch.arange(2) + i, "net_input": {"src_tokens": torch.randint(4, 100, (2, 7), generator=g),
+                                                               "patch_images_u8": torch.randint(0, 256, (2, 32, 32, 3), generator=g, dtype=torch.uint8),
+                                                               "patch_masks": torch.ones(2, dtype=torch.bool)}}))
+    seen = 0
+    for i, dev in enumerate(DevicePrefetcher(host, torch.device("cuda", 0), torch.bfloat16)):
+        u8 = host[i]["net_input"]["patch_images_u8"]
+        ref = u8.permute(0, 3, 1, 2).float().div(255).sub(0.5).div(0.5).bfloat16()
+        assert "patch_images_u8" not in dev["net_input"]
+        assert torch.equal(dev["net_input"]["patch_images"].cpu(), ref)
+        assert torch.equal(dev["net_input"]["src_tokens"].cpu(), host[i]["net_input"]["src_tokens"])
+        assert dev["net_input"]["src_tokens"].dtype == torch.long and dev["net_input"]["patch_masks"].dtype == torch.bool
+        seen += 1
+    assert seen == 4
