@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--profile-kernels", type=int, default=1)
     ap.add_argument("--graph", type=int, default=1, help="replay the micro-step as a CUDA graph (0: eager launches)")
     ap.add_argument("--caption-bench", type=int, default=1, help="also time beam-5 captioning (BASELINE configs[4]) at N=1")
+    ap.add_argument("--script-flags", type=int, default=1,
+                    help="also time the micro-step under the flags of run_scripts/musketeer/train_musketeer.sh:56-71,164 at N=1")
     return ap.parse_args()
 
 
@@ -156,6 +158,47 @@ def caption_bench(dev, batch=64, img=480, beam=5, iters=2):
     t = min(times)
     return {"metric": "beam-5 captions/s (OFA-base, %d x %dx%d images, max_len 16)" % (batch, img, img), "value": batch / t,
             "unit": "captions/s", "latency_ms": t * 1e3, "decoder_steps": max(len(h[0]["tokens"]) for h in out)}
+
+
+def script_flags_bench(dev, arch, img, steps, warmup):
+    """The same 5-task micro-step under the flags run_scripts/musketeer/train_musketeer.sh actually passes (:56-71,164):
+    dropout 0.1, encoder / decoder drop-path 0.1, --use-rdrop (every task's batch duplicated, KL term between the halves),
+    sample_patch_num 196 (every image task but the last keeps a random patch subset of its 576 patches: 392 of them, because
+    construct_rdrop_sample doubles every int of the sample, label_smoothed_cross_entropy.py:61-62), at the headline's per-task batch 16
+    and at the script's own batch 2.  samples/s counts the un-duplicated samples.  Device-resident inputs, CUDA-graph replay +
+    fused Adam inside the timed region."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion, _lib
+    from musketeer_b200.graphed import GraphedTrainStep
+    from musketeer_b200.optim import FusedAdam
+    from musketeer_b200.synthetic import build_model, make_tep_group, to_device
+    out = {"flags": "dropout 0.1, encoder/decoder drop-path 0.1, use_rdrop (reg_alpha 1.0), sample_patch_num 196 (392 kept under R-Drop, as in the reference), label smoothing 0.1"}
+    for tb in (16, 2):
+        model, task = build_model(arch, dev, torch.bfloat16, seed=0, dropout=0.1, encoder_drop_path_rate=0.1,
+                                  decoder_drop_path_rate=0.1)
+        model.train()
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=True, reg_alpha=1.0, sample_patch_num=196)
+        optim = FusedAdam(model.parameters(), lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip_norm=0.1)
+        graphed = GraphedTrainStep(model, crit, dev, torch.bfloat16)
+        groups = [to_device(make_tep_group(tb, img=img, seed=500 + i), dev, torch.bfloat16) for i in range(2)]
+        loss = None
+        for i in range(warmup):
+            loss, _ = graphed(groups[i % 2])
+            optim.step()
+        torch.cuda.synchronize()
+        l0 = _lib.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss, _ = graphed(groups[i % 2])
+            optim.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["task_batch_%d" % tb] = {"value": 5 * tb / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms,
+                                     "loss": float(loss), "rows_per_task_with_rdrop": 2 * tb}
+        del graphed, model, optim, groups
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -371,10 +414,13 @@ def main():
         g = tot.get("ofa_gemm_bf16")
         if g and top != "ofa_gemm_bf16":
             roof["gemm_tflops"] = g[1].get("flop", 0.0) / (g[0] / 1e3) / 1e12
-    caption = None
-    if a.caption_bench and world == 1:
+    caption = script = None
+    if world == 1 and (a.caption_bench or a.script_flags):
         del graphed, resident
         torch.cuda.empty_cache()
+    if a.script_flags and world == 1:
+        script = script_flags_bench(dev, a.arch, a.img, a.steps, a.warmup)
+    if a.caption_bench and world == 1:
         caption = caption_bench(dev)
     cpu = None
     if a.cpu_baseline:
@@ -396,7 +442,7 @@ def main():
                 "readback": "loss of every step copied to pinned memory and read by the host one step behind",
                 "h2d": "every step's batches copied from pinned host memory inside the timed region; the copy of step i+1 is issued on a copy stream while step i computes (the first step's copy is exposed)",
                 "last_loss": losses_read[-1] if losses_read else None},
-        "roofline": roof, "cpu_baseline": cpu, "caption_beam5": caption}))
+        "roofline": roof, "cpu_baseline": cpu, "caption_beam5": caption, "script_flags": script}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -85,11 +85,17 @@ class AdjustLabelSmoothedCrossEntropyCriterion(FairseqCriterion):
         """Multi-task micro-step: push the images of all image tasks through the ResNet stem in ONE grouped pass (BatchNorm
         statistics stay per task, running statistics are updated in task order: musketeer_b200/resnet.py), and hand every
         task its slice as `patch_features`.  Arithmetic per task is unchanged; every stem kernel runs once instead of
-        once per task.  Skipped when the tasks' image batches differ in shape, with R-Drop (the duplication happens inside
-        the per-task forward) or with ResNet drop-path."""
+        once per task.  Skipped when the tasks' image batches differ in shape or with ResNet drop-path.
+
+        The flags of run_scripts/musketeer/train_musketeer.sh keep the merged passes: with R-Drop every image task's sample is
+        duplicated HERE (construct_rdrop_sample, label_smoothed_cross_entropy.py:56-71,204-207) before the grouped stem, so a
+        task's group is what its own forward would have pushed through the stem; dropout / drop-path draw independent
+        per-element / per-row masks, which is what the per-task passes do too (other random numbers, the same distribution);
+        patch sampling (`sample_patch_num`, :175-178: every task but the last of the list) is applied inside the merged pass,
+        the per-row patch subsets drawn in task order like the per-task passes draw them."""
         enc = getattr(model, "encoder", None)
         stem = getattr(enc, "embed_images", None)
-        if stem is None or self.use_rdrop or not self.batch_task_stems:
+        if stem is None or not self.batch_task_stems:
             return sample
         idx = [i for i, s in enumerate(sample) if s["net_input"].get("patch_images") is not None
                and s["net_input"].get("patch_features") is None]
@@ -100,16 +106,22 @@ class AdjustLabelSmoothedCrossEntropyCriterion(FairseqCriterion):
             return sample
         if getattr(stem, "drop_path_rate", 0.0) > 0.0 and stem.training:
             return sample
+        if self.use_rdrop:
+            sample = list(sample)
+            for i in idx:
+                sample[i] = dict(construct_rdrop_sample(sample[i]), _rdrop_done=True)
+            imgs = [sample[i]["net_input"]["patch_images"] for i in idx]
         b = imgs[0].shape[0]
         feats_all = stem(torch.cat(imgs, 0), groups=len(idx))
         hw = stem.last_hw
         out = list(sample)
         nis = [sample[i]["net_input"] for i in idx]
-        merge = (self.batch_task_encoders and float(getattr(enc, "dropout_p", 0.0)) == 0.0 and
+        sampled = self.sample_patch_num > 0
+        merge = (self.batch_task_encoders and
                  all(ni.get("sample_patch_num") is None and ni.get("patch_images_2") is None for ni in nis) and
-                 # the recursion below sets sample_patch_num on every task but the LAST of the list (:175-178): any image task
-                 # that would receive it keeps its own, patch-sampling, encoder pass
-                 not (self.sample_patch_num > 0 and any(i < len(sample) - 1 for i in idx)))
+                 # the recursion below sets sample_patch_num on every task but the LAST of the list (:175-178): the merged pass
+                 # samples patches for all of its tasks or for none
+                 (not sampled or all(i < len(sample) - 1 for i in idx)))
         if merge:
             # ONE encoder pass for all image tasks: source tokens right-padded to the longest prompt (padded keys are masked
             # and padded rows zeroed, so every real position computes what its own task's pass computes), then each task
@@ -119,7 +131,11 @@ class AdjustLabelSmoothedCrossEntropyCriterion(FairseqCriterion):
             src = torch.cat([torch.nn.functional.pad(ni["src_tokens"], (0, S - ni["src_tokens"].shape[1]), value=pad)
                              for ni in nis], 0)
             masks = torch.cat([ni["patch_masks"] for ni in nis], 0)
-            eo = enc(src, src_lengths=None, patch_images=imgs[0], patch_masks=masks, patch_features=(feats_all, hw))
+            eo = enc(src, src_lengths=None, patch_images=imgs[0], patch_masks=masks, patch_features=(feats_all, hw),
+                     # (construct_rdrop_sample doubles every int of the sample, sample_patch_num included -- the per-task
+                     # path and the reference, label_smoothed_cross_entropy.py:61-62, keep 2 x sample_patch_num patches
+                     # under R-Drop; so does the merged pass)
+                     sample_patch_num=self.sample_patch_num * (2 if self.use_rdrop else 1) if sampled else None)
             xs = eo["encoder_out"][0].transpose(0, 1).split(b, 0)              # [b, N, d] per task; split: one cat backward
             pms = eo["encoder_padding_mask"][0].split(b, 0)
             pos = eo["position_embeddings"][0].split(b, 0)
@@ -130,7 +146,7 @@ class AdjustLabelSmoothedCrossEntropyCriterion(FairseqCriterion):
                                                  "position_embeddings": [pos[k]], "encoder_embedding": [],
                                                  "encoder_states": [], "src_tokens": [], "src_lengths": []}
                 out[i] = s
-            if self.batch_task_decoders:
+            if self.batch_task_decoders and not self.use_rdrop:      # (the R-Drop KL term pairs the two halves of ONE task's logits)
                 xs, pms, pos, idx2 = list(xs), list(pms), list(pos), list(idx)
                 # text-only tasks with the same batch size join the decoder groups: their own encoder pass, right-padded
                 # (masked) to the merged pass's source length
@@ -233,7 +249,7 @@ class AdjustLabelSmoothedCrossEntropyCriterion(FairseqCriterion):
             }
             return loss, 1, logging_output
         sample = sample[0] if isinstance(sample, list) else sample
-        if self.use_rdrop:
+        if self.use_rdrop and not sample.get("_rdrop_done"):
             sample = construct_rdrop_sample(sample)
         drop = self.drop_worst_ratio if (self.drop_worst_ratio > 0 and update_num > self.drop_worst_after) else 0.0
         pre = sample.get("_precomputed") if drop == 0 else None      # this task's rows of a merged decoder pass

@@ -56,6 +56,45 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ dcol,
   }
 }
 
+// bf16, C % 8 == 0: eight channels per thread (16-byte loads of the <= 4 taps that reach an input pixel at stride 2, fp32 sums,
+// one 16-byte store): the scalar kernel above spent 975 us on the 96x96x128 gradient of layer2.0.conv2 (per-element index
+// arithmetic and 2-byte accesses), this one is bound by the 2.3 x |dx| bytes it moves.
+__global__ void __launch_bounds__(256) col2im_vec8_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx,
+                                                          int N, int H, int W, int C, int KH, int KW, int S, int P, int OH, int OW,
+                                                          long long ldcol) {
+  pdl_sync();
+  const int c8 = C / 8;
+  const long long total = (long long)N * H * W * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int hh = h + P - kh;
+      if (hh < 0 || hh % S != 0 || hh / S >= OH) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ww = w + P - kw;
+        if (ww < 0 || ww % S != 0 || ww / S >= OW) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(
+            dcol + (((long long)n * OH + hh / S) * OW + ww / S) * ldcol + (long long)(kh * KW + kw) * C + c);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+    *reinterpret_cast<uint4*>(dx + i * 8) = o;
+  }
+}
+
 // generic max-pool 3x3 / stride 2 / padding 1 (nn.MaxPool2d(3, 2, 1): first maximum in window order wins, as ATen)
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_any_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
@@ -146,6 +185,8 @@ extern "C" int ofa_col2im(const void* dcol, void* dx, int N, int H, int W, int C
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == OFA_F32)
     OFA_CUDA(ofa_launch_pdl(col2im_kernel<float>, grid_for(total), 256, 0, st, (const float*)dcol, (float*)dx, N, H, W, C, KH, KW, stride, pad, OH, OW, ldcol));
+  else if (C % 8 == 0 && ldcol % 8 == 0 && (((uintptr_t)dcol | (uintptr_t)dx) & 15) == 0)
+    OFA_CUDA(ofa_launch_pdl(col2im_vec8_kernel, grid_for(total / 8), 256, 0, st, (const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, N, H, W, C, KH, KW, stride, pad, OH, OW, ldcol));
   else
     OFA_CUDA(ofa_launch_pdl(col2im_kernel<__nv_bfloat16>, grid_for(total), 256, 0, st, (const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, N, H, W, C, KH, KW, stride, pad, OH, OW, ldcol));
   OFA_LAUNCH_CHECK("col2im_kernel");

@@ -396,8 +396,16 @@ class TransformerEncoder(FairseqEncoder):
         pid = pid[None, :].expand(B, P)
         pad = torch.zeros(B, P, dtype=torch.bool, device=device)
         if sample_patch_num is not None:                              # unify_transformer.py:671-682
+            if sample_patch_num > P:
+                raise ValueError("Sample larger than population or is negative")     # what random.sample raises in the reference
             if self.patch_orders_override is not None:
                 orders = self.patch_orders_override.to(device)
+                if orders.shape[0] == 1:                                  # one subset for every row (tests)
+                    orders = orders.expand(B, -1)
+            elif feat.is_cuda:
+                # a uniformly random ordered k-subset per row, like random.sample, drawn from the device generator: no host
+                # loop, no host -> device copy, and capturable in the step's CUDA graph (fresh numbers on every replay)
+                orders = torch.rand(B, P, device=device).argsort(dim=1)[:, :sample_patch_num]
             else:
                 orders = torch.LongTensor([random.sample(range(P), k=sample_patch_num) for _ in range(B)]).to(device)
             feat = feat.gather(1, orders.unsqueeze(2).expand(-1, -1, feat.size(2)))

@@ -95,11 +95,12 @@ def build_model(arch="ofa_base", device="cuda", dtype=torch.bfloat16, seed=0, vo
     """Random-init OFA with the Musketeer flag set (run_scripts/musketeer/train_musketeer.sh:124-176), dropout 0."""
     from types import SimpleNamespace
     from . import ARCHS, OFAModel
-    args = SimpleNamespace(scale_attn=True, scale_fc=True, scale_heads=True, add_type_embedding=True,
-                           disable_entangle=True, layernorm_embedding=True, patch_layernorm_embedding=True,
-                           code_layernorm_embedding=True, share_all_embeddings=True, encoder_normalize_before=True,
-                           decoder_normalize_before=True, dropout=0.0, attention_dropout=0.0,
-                           **dict({"patch_image_size": 384}, **over))
+    kw = dict(scale_attn=True, scale_fc=True, scale_heads=True, add_type_embedding=True,
+              disable_entangle=True, layernorm_embedding=True, patch_layernorm_embedding=True,
+              code_layernorm_embedding=True, share_all_embeddings=True, encoder_normalize_before=True,
+              decoder_normalize_before=True, dropout=0.0, attention_dropout=0.0, patch_image_size=384)
+    kw.update(over)             # e.g. dropout=0.1, encoder_drop_path_rate=0.1, decoder_drop_path_rate=0.1 (the script's values)
+    args = SimpleNamespace(**kw)
     ARCHS[arch](args)
     torch.manual_seed(seed)
     task = Task(vocab)

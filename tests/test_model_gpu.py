@@ -432,6 +432,65 @@ def test_grouped_stem_pass_equals_per_task_stems(dtype):
         assert abs(g1 - ref_gn) <= 1e-3 * ref_gn, (g1, ref_gn)
 
 
+def test_merged_passes_survive_the_script_flags():
+    """R-Drop + patch sampling (run_scripts/musketeer/train_musketeer.sh:66-71,164) keep the grouped stem and the merged encoder
+    pass: with dropout 0 and one fixed patch subset the merged micro-step equals the per-task passes (fp32: loss 1e-5, gradient
+    norm 1e-3) and the oracle's criterion (label_smoothed_cross_entropy.py:56-71,175-211); with dropout / drop-path on, the
+    merged and per-task steps are two draws of the same estimator (loss within a few percent, finite gradients)."""
+    from musketeer_b200 import AdjustLabelSmoothedCrossEntropyCriterion
+    cfg = synth.make_cfg("ofa_micro", vocab_size=4099)
+    sd = synth.synth_state_dict(cfg, seed=0)
+    spec = [(19, 7, True), (30, 9, True), (22, 12, True), (25, 6, False)]
+    samples = [synth.make_batch(2, s, t, img=96, seed=70 + i, vocab=4099, with_image=im) for i, (s, t, im) in enumerate(spec)]
+    k = 9                  # of 36 patches; R-Drop doubles the ints of the sample, sample_patch_num included (:61-62): 18 are kept
+    orders = torch.randperm(36, generator=torch.Generator().manual_seed(3))[:2 * k].unsqueeze(0)
+    res = []
+    for merged in (False, True):
+        model, task = build_product(cfg, sd, dtype=torch.float32)
+        model.train()
+        model.encoder.patch_orders_override = orders
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=True, reg_alpha=1.0, sample_patch_num=k,
+                                                        batch_task_stems=merged)
+        calls = {"n": 0}
+        orig = model.encoder.forward
+
+        def counted(*a, _o=orig, **kw):
+            calls["n"] += 1
+            return _o(*a, **kw)
+
+        model.encoder.forward = counted
+        loss, ss, log = crit(model, to_device(copy.deepcopy(samples), "cuda"))
+        loss.backward()
+        assert calls["n"] == (2 if merged else 4)      # merged: one pass for the three image tasks + the text task's own
+        res.append((float(loss.detach()), sum(float(p.grad.norm()) ** 2 for p in model.parameters() if p.grad is not None) ** 0.5, log))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[0][0]), (res[0][0], res[1][0])
+    assert abs(res[0][1] - res[1][1]) <= 1e-3 * res[0][1], (res[0][1], res[1][1])
+    for key in ("ntokens", "nsentences", "sample_size_v1", "sample_size_v2"):
+        assert res[0][2][key] == res[1][2][key], key
+    sdo = tie(sd)
+    ref_loss, _, _ = oo.criterion_forward(sdo, cfg, copy.deepcopy(samples), epsilon=0.1, use_rdrop=True, sample_patch_num=k,
+                                          patch_orders=[orders.expand(4, -1)] * 4)
+    assert abs(res[1][0] - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)), (res[1][0], float(ref_loss))
+    # dropout / drop-path on: same estimator, other random numbers
+    losses = {False: [], True: []}
+    for merged in (False, True):
+        model, task = build_product(synth.make_cfg("ofa_micro", vocab_size=4099, dropout=0.1, encoder_drop_path_rate=0.1,
+                                                   decoder_drop_path_rate=0.1), sd, dtype=torch.bfloat16)
+        model.train()
+        crit = AdjustLabelSmoothedCrossEntropyCriterion(task, False, 0.1, use_rdrop=True, reg_alpha=1.0, sample_patch_num=k,
+                                                        batch_task_stems=merged)
+        for rep in range(6):
+            torch.manual_seed(100 + rep)
+            for p in model.parameters():
+                p.grad = None
+            loss, _, _ = crit(model, to_device(copy.deepcopy(samples), "cuda", torch.bfloat16))
+            loss.backward()
+            assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.grad is not None)
+            losses[merged].append(float(loss.detach()))
+    m0, m1 = sum(losses[False]) / 6, sum(losses[True]) / 6
+    assert abs(m0 - m1) <= 0.05 * abs(m0), (losses[False], losses[True])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_merged_decoder_passes_equal_per_task_passes(dtype):
     """Five-task micro-step whose image tasks group into two merged decoder passes (targets 7|9 and 40|44, right-padded to the
