@@ -718,7 +718,9 @@ __device__ long long g_attn_dbg[128];
 #define DBG_T(i)
 #endif
 constexpr int BK2 = 128;
-constexpr int kBwdThreads = 512;   // 4 threads per query row, 32 key columns each
+constexpr int kBwdSoft = 512;      // softmax / histogram / drain threads: 4 per query row, 32 key columns each
+constexpr int kBwdThreads = kBwdSoft + 128;  // + one more warpgroup: its first warp (16) is the TMA producer and tcgen05 issuer
+                                             // (one elected lane); a whole warpgroup because setmaxnreg works per warpgroup
 constexpr int kTokHist = 1024 + 128;
 constexpr int kImgHistMax = 83 * 83 + 3;
 
@@ -740,6 +742,9 @@ struct BwdSmem {
   float img_s[kImgHistMax + 1];   // image rel-pos LUT of this head (the per-element gather went to L1 / L2 before: long-scoreboard
                                   // stalls were the top stall reason of the round-1 capture)
   uint64_t bar_kv, bar_q, bar_sp, bar_dq, bar_qf;
+  uint64_t bar_pds;      // P / dS of the tile are in shared memory (softmax threads -> issuer)
+  uint64_t bar_drain;    // dQ' of the tile has left tensor memory (softmax threads -> issuer: dP of the next tile may land there)
+  uint64_t bar_slab;     // the dQ' reduce has finished reading the staging slabs (thread 0 -> softmax threads: P / dS may be written)
   uint32_t tmem_addr;
 };
 
@@ -768,6 +773,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmPQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmPK);
     tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
     mbar_init(&sm.bar_kv, 1); mbar_init(&sm.bar_q, 1); mbar_init(&sm.bar_sp, 1); mbar_init(&sm.bar_dq, 1); mbar_init(&sm.bar_qf, 1);
+    mbar_init(&sm.bar_pds, 1); mbar_init(&sm.bar_drain, 1); mbar_init(&sm.bar_slab, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&sm.tmem_addr);
@@ -810,12 +816,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // masked keys (padding / beyond S) of this thread's 32 columns: the keys are stationary, so one bit mask serves every
   // query tile and the fast softmax paths stay usable on tiles that contain padded keys
   uint32_t colmask = 0;
-  if (keys_any_masked) {
+  if (keys_any_masked && t < kBwdSoft) {
 #pragma unroll
     for (int jj = 0; jj < 32; ++jj) colmask |= (sm.kinfo[qd * 32 + jj] < 0 ? 1u : 0u) << jj;
   }
 
-  if (qt0 < nq_tiles && t == 0) {
+  if (qt0 < nq_tiles && t == kBwdSoft) {
     mbar_expect_tx(&sm.bar_kv, 3 * BK2 * 128);
     tma_load_4d(sm.k[0], &tmK, &sm.bar_kv, 0, h, k0, b);
     tma_load_4d(sm.k[1], &tmPK, &sm.bar_kv, 0, h, k0, b);
@@ -844,30 +850,73 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   for (int n = 1; n < nq_tiles - qt0; n <<= 1) --kq;
   int e_cur = 0;                                   // biased exponent E + 126 of the current scale; 0 = tables still empty
   int it = 0;
+  // register budget: 640 threads launch with 96 registers each; the issuer warpgroup hands most of its share to the four
+  // softmax warpgroups (the pool is what the CTA launched with: 640 x 96 = 4 x 128 x 112 + 128 x 32)
+  if (t >= kBwdSoft) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp != kBwdSoft / 32) return;
+    // ---- warp 16: TMA producer + tcgen05 issuer.  Runs ahead of the 16 softmax warps: S of the next query tile is issued as
+    // soon as its Q' has landed (under the histogram / dQ' drain of the current one), MMA issue no longer delays warp 0's share
+    // of the softmax and histogram work, every hand-over is an mbarrier.  dQ' accumulates in the dP columns (dP is consumed
+    // by then), so S never waits for the drain.
+    if ((t & 31) == 0) {
+      for (int qt = qt0; qt < nq_tiles; ++qt, ++it) {
+        const uint32_t ph = it & 1;
+        const int q0 = qt * BQ;
+        if (it == 0) mbar_wait(&sm.bar_kv, 0);
+        mbar_wait(&sm.bar_q, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tm + COL_S, umma_smem_desc(smem_u32(sm.q[kb]) + ks * 32, 16, 1024),
+                     umma_smem_desc(smem_u32(sm.k[kb]) + ks * 32, 16, 1024), id_s, (kb | ks) != 0);
+        if (it > 0) {                      // dQ' of the previous tile has been read out of the dP columns
+          mbar_wait(&sm.bar_drain, (it - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tm + COL_DP, umma_smem_desc(smem_u32(sm.dout) + ks * 32, 16, 1024),
+                   umma_smem_desc(smem_u32(sm.v) + ks * 32, 16, 1024), id_s, ks != 0);
+        umma_commit(&sm.bar_sp);
+        mbar_wait(&sm.bar_pds, ph);        // P / dS staged by the softmax threads
+        tc_fence_after();
+        const uint32_t acc = it != 0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dV[keys, hd] += P^T dO   (contraction over the 128 query rows, 16 per MMA)
+          umma_f16(tm + COL_DV, umma_smem_desc(smem_u32(sm.p[0]) + ks * 2048, BQ * 128, 1024),
+                   umma_smem_desc(smem_u32(sm.dout) + ks * 2048, 1024, 1024), id_dv, acc | (ks != 0));
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dK'[keys, 128] += dS^T Q'
+          umma_f16(tm + COL_DK, umma_smem_desc(smem_u32(sm.ds[0]) + ks * 2048, BQ * 128, 1024),
+                   umma_smem_desc(smem_u32(sm.q[0]) + ks * 2048, BQ * 128, 1024), id_dk, acc | (ks != 0));
+        umma_commit(&sm.bar_qf);         // dV and dK' retired = Q' and dO are no longer read
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dQ'[rows, 128] = dS K'      (contraction over the 128 keys)
+          umma_f16(tm + COL_DP, umma_smem_desc(smem_u32(sm.ds[ks >> 2]) + (ks & 3) * 32, 16, 1024),
+                   umma_smem_desc(smem_u32(sm.k[0]) + ks * 2048, BK2 * 128, 1024), id_dq, ks != 0);
+        umma_commit(&sm.bar_dq);
+        if (qt + 1 < nq_tiles) {
+          // reload Q' / dO for the next query tile as soon as dV / dK' are done: the TMA latency (~2 us) runs under the dQ'
+          // GEMM, the histogram phase and the drain
+          mbar_wait(&sm.bar_qf, ph);
+          tc_fence_after();
+          mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
+          tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, q0 + BQ, b);
+          tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, q0 + BQ, b);
+          tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, q0 + BQ, b);
+        }
+      }
+    }
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
   for (int qt = qt0; qt < nq_tiles; ++qt, ++it) {
     const uint32_t ph = it & 1;
     const int q0 = qt * BQ;
     DBG_T(0)
-    if (t == 0) {
-      if (it == 0) mbar_wait(&sm.bar_kv, 0);
-      mbar_wait(&sm.bar_q, ph);
-      DBG_T(10)
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tm + COL_S, umma_smem_desc(smem_u32(sm.q[kb]) + ks * 32, 16, 1024),
-                   umma_smem_desc(smem_u32(sm.k[kb]) + ks * 32, 16, 1024), id_s, (kb | ks) != 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_f16(tm + COL_DP, umma_smem_desc(smem_u32(sm.dout) + ks * 32, 16, 1024),
-                 umma_smem_desc(smem_u32(sm.v) + ks * 32, 16, 1024), id_s, ks != 0);
-      DBG_T(11)
-      tma_store_wait_read<0>();   // the previous tile's dQ' reduce has finished reading the P / dS buffers (see below)
-      umma_commit(&sm.bar_sp);
-    }
-    __syncwarp();
     // per-row metadata
     const int i = q0 + r;
     const int iabs = i + a.q_pos_off;
@@ -952,6 +1001,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           dsv[jj] = ds;
         }
       }
+      if (it > 0) {       // the previous tile's dQ' reduce must have finished READING the P / dS buffers (its staging slabs)
+        if (t == 0) { tma_store_wait_read<0>(); mbar_arrive(&sm.bar_slab); }
+        mbar_wait(&sm.bar_slab, (it - 1) & 1);
+      }
 #pragma unroll
       for (int c16 = 0; c16 < 4; ++c16) {
         const int chunk = ch * 4 + c16;   // 16-byte chunk inside the 128-byte row of this half
@@ -976,37 +1029,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     DBG_T(3)
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    named_bar_sync(1, kBwdSoft);
     DBG_T(4)
-    if (t == 0) {
-      tc_fence_after();
-      const uint32_t acc = it != 0;
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks)   // dV[keys, hd] += P^T dO   (contraction over the 128 query rows, 16 per MMA)
-        umma_f16(tm + COL_DV, umma_smem_desc(smem_u32(sm.p[0]) + ks * 2048, BQ * 128, 1024),
-                 umma_smem_desc(smem_u32(sm.dout) + ks * 2048, 1024, 1024), id_dv, acc | (ks != 0));
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks)   // dK'[keys, 128] += dS^T Q'
-        umma_f16(tm + COL_DK, umma_smem_desc(smem_u32(sm.ds[0]) + ks * 2048, BQ * 128, 1024),
-                 umma_smem_desc(smem_u32(sm.q[0]) + ks * 2048, BQ * 128, 1024), id_dk, acc | (ks != 0));
-      umma_commit(&sm.bar_qf);         // dV and dK' retired = Q' and dO are no longer read
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks)   // dQ'[rows, 128] = dS K'      (contraction over the 128 keys)
-        umma_f16(tm + COL_S, umma_smem_desc(smem_u32(sm.ds[ks >> 2]) + (ks & 3) * 32, 16, 1024),
-                 umma_smem_desc(smem_u32(sm.k[0]) + ks * 2048, BK2 * 128, 1024), id_dq, ks != 0);
-      umma_commit(&sm.bar_dq);
-      if (qt + 1 < nq_tiles) {
-        // reload Q' / dO for the next query tile as soon as dV / dK' are done: the TMA latency (~2 us) then runs under the
-        // dQ' GEMM and the histogram phase instead of in front of the next tile's first GEMM
-        mbar_wait(&sm.bar_qf, ph);
-        tc_fence_after();
-        mbar_expect_tx(&sm.bar_q, 3 * BQ * 128);
-        tma_load_4d(sm.q[0], &tmQ, &sm.bar_q, 0, h, q0 + BQ, b);
-        tma_load_4d(sm.q[1], &tmPQ, &sm.bar_q, 0, h, q0 + BQ, b);
-        tma_load_4d(sm.dout, &tmDO, &sm.bar_q, 0, h, q0 + BQ, b);
-      }
-    }
-    __syncwarp();
+    if (t == 0) mbar_arrive(&sm.bar_pds);      // warp 16 issues dV / dK' / dQ' while the histogram below runs
     DBG_T(9)
     // relative-position table gradients: shared-memory histogram updates run here, under the three tensor-core GEMMs just
     // issued.  Block exponent: every thread derives the tile's max |dS| from the 16 warp maxima; when it outgrows the
@@ -1025,12 +1050,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int e_new = e_t + 1;
         if (e_cur != 0) {                           // CTA-uniform branch
           const int sh = e_new - e_cur;
-          for (int e = t; e < kTokHist + kImgHistMax + 1; e += kBwdThreads) {
+          for (int e = t; e < kTokHist + kImgHistMax + 1; e += kBwdSoft) {
             int* bin = e < kTokHist ? &sm.hist_tok[e] : &sm.hist_img[e - kTokHist];
             const int v = *bin;
             if (v != 0) *bin = sh >= 31 ? 0 : (v + (1 << (sh - 1))) >> sh;
           }
-          __syncthreads();
+          named_bar_sync(1, kBwdSoft);
         }
         e_cur = e_new;
       }
@@ -1067,7 +1092,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // dQ' partial [128 rows][32 columns of this quarter] -> fp32 slab qd (128B-swizzled rows) in the P / dS buffers, which
       // are idle until the next tile's softmax phase; one TMA reduce per slab adds it into dq_acc (rows >= T are clipped)
       uint32_t rq[32];
-      tmem_ld32(tm + lane_off + COL_S + col0, rq);
+      tmem_ld32(tm + lane_off + COL_DP + col0, rq);
       tmem_ld_wait();
       uint8_t* slab = sm.p[0] + qd * (BQ * 128);
 #pragma unroll
@@ -1078,9 +1103,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     DBG_T(7)
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    named_bar_sync(1, kBwdSoft);
     DBG_T(8)
     if (t == 0) {
+      mbar_arrive(&sm.bar_drain);
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) tma_reduce_add_4d(&tmDQ, sm.p[0] + s4 * (BQ * 128), s4 * 32, h, q0, b);
       tma_store_commit();
@@ -1131,11 +1157,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __nv_bfloat16* d1 = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + qd * 16;
     for (int v4 = 0; v4 < 2; ++v4) reinterpret_cast<uint4*>(d1)[v4] = z;
   }
-  __syncthreads();
+  named_bar_sync(1, kBwdSoft);
   const float unq = e_cur != 0 ? __uint_as_float((uint32_t)(e_cur + 1 - kq) << 23) : 0.f;      // 2^((e_cur - 126) - kq)
   if (has_tok) {
     float* gt = g.dtok_lut + (size_t)h * (2 * bz.tok_max - 1);
-    for (int e = t; e < kTokHist; e += kBwdThreads) {
+    for (int e = t; e < kTokHist; e += kBwdSoft) {
       const int v = sm.hist_tok[e];
       const int rel = e - tok_base + bz.tok_max - 1;
       if (v != 0 && rel >= 0 && rel < 2 * bz.tok_max - 1) atomicAdd(gt + rel, (float)v * unq);
@@ -1143,13 +1169,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (has_img) {
     float* gi = g.dimg_lut + (size_t)h * bz.n_img_rel;
-    for (int e = t; e < bz.n_img_rel && e < kImgHistMax; e += kBwdThreads) {
+    for (int e = t; e < bz.n_img_rel && e < kImgHistMax; e += kBwdSoft) {
       const int v = sm.hist_img[e];
       if (v != 0) atomicAdd(gi + e, (float)v * unq);
     }
   }
   tc_fence_before();
-  __syncthreads();
+  named_bar_sync(1, kBwdSoft);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<512>(tm);
