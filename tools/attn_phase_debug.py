@@ -24,11 +24,11 @@ for it in range(3):
     o.backward(do)
     torch.cuda.synchronize()
     lib.ofa_attn_debug_read(buf)
-names = ["loop top", "wait dQ' reduce read + commit", "wait S/dP", "softmax math + smem", "sync", "hist atomics", "wait MMA2", "dQ stage", "sync",
-         "issue MMA2 (+reload)", "wait Q'/dO", "issue MMA1"]
+names = ["loop top + row metadata", "wait S/dP (issuer: Q' landed, S, drain, dP)", "tmem ld issue", "softmax math + slab wait + smem", "named barrier", "hist atomics", "wait dQ' MMA", "dQ drain", "named barrier",
+         "arrive bar_pds", "-", "-"]
 print("CTA (key tile 2: image keys), thread 0, microseconds per phase and query tile (1.9 GHz):")
 print("%-24s" % "phase" + "".join("%8d" % i for i in range(7)))
-order = [0, 10, 11, 1, 2, 3, 4, 9, 5, 6, 7, 8]
+order = [0, 1, 2, 3, 4, 9, 5, 6, 7, 8]
 for ph in order:
     print("%-24s" % names[ph] + "".join("%8.2f" % (buf[i * 12 + ph] / 1900.0) for i in range(7)))
 print("%-24s" % "total" + "".join("%8.2f" % (sum(buf[i * 12 + ph] for ph in range(12)) / 1900.0) for i in range(7)))
