@@ -32,3 +32,5 @@ order = [0, 1, 2, 3, 4, 9, 5, 6, 7, 8]
 for ph in order:
     print("%-24s" % names[ph] + "".join("%8.2f" % (buf[i * 12 + ph] / 1900.0) for i in range(7)))
 print("%-24s" % "total" + "".join("%8.2f" % (sum(buf[i * 12 + ph] for ph in range(12)) / 1900.0) for i in range(7)))
+print("prologue %.2f us | prologue + main loop %.2f us | epilogue %.2f us   (accumulated over %d backward calls: divide by 1)" % (
+    buf[96] / 1900.0, buf[97] / 1900.0, buf[98] / 1900.0, 1))
