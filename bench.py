@@ -397,6 +397,9 @@ def main():
             for r in recs:
                 if r[2]:
                     w[r[2][0]] = w.get(r[2][0], 0.0) + r[2][1]
+                    if len(r[2]) > 2 and len(r[2][2]) >= 6:        # GEMM: operands + result bytes, (M, N, K, a_mn, b_mn, out dtype)
+                        M_, N_, K_, od = r[2][2][0], r[2][2][1], r[2][2][2], r[2][2][5]
+                        w["byte_alg"] = w.get("byte_alg", 0.0) + 2.0 * (M_ * K_ + N_ * K_) + (2.0 if od == 1 else 4.0) * M_ * N_
             tot[name] = (t, w, len(recs))
         top = max(tot, key=lambda k: tot[k][0])
         t, w, n = tot[top]
@@ -411,6 +414,13 @@ def main():
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind, "launches": n,
                     "avg_launch_us": t * 1e3 / n, "share_of_library_kernel_time": share}
+        if top == "ofa_gemm_bf16" and a.task_batch == 16 and a.arch == "ofa_base" and a.img == 384:
+            # DRAM bytes per launch of the same kernel family in the same step, from the committed ncu pass (cannot be read
+            # live): profiles/r02_ncu_launch_list_b16_step.txt, 638 gemm_tc* launches, cold-cache and serialised under ncu
+            roof["traffic"] = 89.45e6 + 20.83e6
+            roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's 638 GEMM launches)"
+            roof["traffic_source"] = "profiles/r02_ncu_launch_list_b16_step.txt"
+            roof["algorithmic_bytes_per_launch"] = w["byte_alg"] / n if w.get("byte_alg") else None
         g = tot.get("ofa_gemm_bf16")
         if g and top != "ofa_gemm_bf16":
             roof["gemm_tflops"] = g[1].get("flop", 0.0) / (g[0] / 1e3) / 1e12
