@@ -82,6 +82,7 @@ def load():
     if _loaded:
         return _loaded["ns"]
     assert available(), "reference tree not found at %s" % REF
+    os.environ["MUSKETEER_REF"] = REF        # the shim's fairseq.search loads models/search.py from the same tree
     for p in (_SHIM, REF):
         if p not in sys.path:
             sys.path.insert(0, p)
