@@ -161,8 +161,22 @@ def caption_bench(dev, batch=64, img=480, beam=5, iters=2):
         if it:
             times.append(time.perf_counter() - t0)
     t = min(times)
+    steps = max(len(h[0]["tokens"]) for h in out)
+    # HBM roofline of the decode phase (one token per beam: every step streams the per-sentence cross-attention K / V of the
+    # six layers, the shared position keys once, the decoder weights incl. the tied vocabulary projection, and writes + reads
+    # the logits), against the WHOLE generate latency -- the encoder pass (tensor-bound) is inside the denominator, so the
+    # fraction is a lower bound for the decode kernels
+    d, S, R = 768, (img // 16) ** 2 + 8, batch * beam
+    V = model.decoder.output_projection.weight.shape[0]
+    dec_w = sum(p.numel() for p in model.decoder.parameters()) * 2
+    step_bytes = 6 * batch * S * d * 2 * 2 + batch * S * d * 2 + dec_w + 2 * R * V * 2
+    pk, _ = peaks()
+    ach = steps * step_bytes / t / 1e9
     return {"metric": "beam-5 captions/s (OFA-base, %d x %dx%d images, max_len 16)" % (batch, img, img), "value": batch / t,
-            "unit": "captions/s", "latency_ms": t * 1e3, "decoder_steps": max(len(h[0]["tokens"]) for h in out)}
+            "unit": "captions/s", "latency_ms": t * 1e3, "decoder_steps": steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                         "bytes_per_decoder_step": step_bytes,
+                         "note": "decode-phase algorithmic bytes / whole generate latency (encoder pass included): lower bound"}}
 
 
 def script_flags_bench(dev, arch, img, steps, warmup):
