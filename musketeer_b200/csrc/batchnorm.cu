@@ -121,26 +121,30 @@ __device__ __forceinline__ void exact_add(unsigned long long* __restrict__ limbs
   if (bits >> 31) v = -v;
   atomicAdd(limbs + (size_t)k * kSumsN + slot, (unsigned long long)v);
 }
-// called by every thread of every CTA of bn_stats_kernel after its exact_add calls
-__device__ __forceinline__ void exact_finalize(unsigned long long* __restrict__ limbs, float* __restrict__ sums, int nvals) {
+// called by every thread of every CTA of bn_stats_kernel after its exact_add calls.  One ticket per (channel slab, group): the
+// CTAs that share blockIdx.y / blockIdx.z are exactly the contributors of that slab's 2 * CS slots, and the last of them folds
+// just those (two values per thread) -- a single last CTA folding all 2 * C * groups values (first version) walked 8192 values
+// alone behind everybody else: 14 -> 28 us per launch.
+constexpr int kMaxTickets = 64;
+__device__ __forceinline__ void exact_finalize(unsigned long long* __restrict__ limbs, float* __restrict__ sums, int C, int CS) {
   __shared__ int last_cta;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(limbs + (size_t)kLimbs * kSumsN);
-    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    last_cta = atomicAdd(ticket, 1u) == total - 1;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(limbs + (size_t)kLimbs * kSumsN) + (blockIdx.z * gridDim.y + blockIdx.y);
+    last_cta = atomicAdd(ticket, 1u) == gridDim.x - 1;
     if (last_cta) *ticket = 0u;
   }
   __syncthreads();
   if (!last_cta) return;
   __threadfence();
-  for (int s = threadIdx.x; s < nvals; s += kT) {
+  for (int e = threadIdx.x; e < 2 * CS; e += kT) {
+    const int s = (int)blockIdx.z * 2 * C + (e < CS ? 0 : C) + (int)blockIdx.y * CS + (e < CS ? e : e - CS);
     double acc = 0.0;
 #pragma unroll
     for (int k = kLimbs - 1; k >= 0; --k) {
       const long long L = (long long)__ldcg(limbs + (size_t)k * kSumsN + s);
-      acc += (double)L * exp2((double)(kP0 + 24 * k));
+      acc += (double)L * __longlong_as_double((long long)(1023 + kP0 + 24 * k) << 52);      // 2^(kP0 + 24 k), exact
       limbs[(size_t)k * kSumsN + s] = 0ull;
     }
     sums[s] = __ldcg(sums + s) + (float)acc;      // (+ a non-finite poison value, if any)
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(kT, 4) bn_stats_kernel(const T* __restrict__ x
       exact_add(limbs, sums_base, slot + C, s1);
     }
   }
-  exact_finalize(limbs, sums_base, 2 * C * (int)gridDim.z);
+  exact_finalize(limbs, sums_base, C, CS);
 }
 
 // forward apply: y = relu?(x * scale_c + shift_c + res).  Every thread derives scale / shift of its 8 channels from the
@@ -501,11 +505,11 @@ extern "C" int ofa_batchnorm_set_tuning(int waves, int bwd_unroll) {
   return 0;
 }
 
-// scratch (floats): [0, kSumsN) fp32 sums | counter | pad to 32 | kLimbs * kSumsN 64-bit limbs | ticket | pad
+// scratch (floats): [0, kSumsN) fp32 sums | counter | pad to 32 | kLimbs * kSumsN 64-bit limbs | kMaxTickets tickets
 extern "C" long long ofa_batchnorm_workspace_floats(int C) {
   (void)C;
   static_assert(kSumsN == 2 * kMaxC * kMaxGroups, "scratch layout");
-  return (long long)kSumsN + 32 + 2LL * kLimbs * kSumsN + 32;
+  return (long long)kSumsN + 32 + 2LL * kLimbs * kSumsN + kMaxTickets;     // one ticket per (channel slab, group)
 }
 
 extern "C" int ofa_batchnorm_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,

@@ -7,6 +7,7 @@ Two numeric modes, selected by the activation dtype:
                as six K-blocks on the same tcgen05 kernel; attention runs on the exact SIMT kernels.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -257,6 +258,9 @@ def _split3(x2d, rows, cols, k_is_cols, pattern):
     return out, c8, 6 * kp
 
 
+_NO_SPLITK = bool(int(os.environ.get("OFA_GEMM_NO_SPLITK", "0")))     # A/B switch: no split-K workspace -> small GEMMs run unsplit
+
+
 def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, alpha=1.0, act=0, resid=None,
          ldd=None, acc32=False, rowsum=None, alpha_cols=0):
     """D[M,N] = act((A.B^T + bias) * alpha) + resid.   A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn);
@@ -286,7 +290,7 @@ def gemm(A, B, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=N
         assert bias.dtype == out_dtype
     if resid is not None:
         assert resid.dtype == out_dtype and resid.stride(-1) == 1
-    wsb = 0 if acc32 else _lib.load().ofa_gemm_workspace_bytes(M, N, Kk, 1)
+    wsb = 0 if (acc32 or _NO_SPLITK) else _lib.load().ofa_gemm_workspace_bytes(M, N, Kk, 1)
     ws = torch.empty(wsb // 4, dtype=torch.float32, device=A.device) if wsb > 0 else None
     call("ofa_gemm_bf16", _p(A), _p(B), _p(out), M, N, Kk, 1, lda, ldb, ldd, 0, 0, 0, int(a_mn), int(b_mn), od,
          _p(bias), float(alpha), int(act), _p(resid), resid.stride(0) if resid is not None else 0, 0, _p(ws), wsb,
