@@ -44,6 +44,9 @@ int ofa_gemm_set_pair_mode(int enabled);
 int ofa_gemm_set_tma_store(int enabled);
 /* weight-gradient tile-shape switch (A/B testing): 1 = 128 x 256 tiles for fp32-accumulate problems (default) */
 int ofa_gemm_set_wgrad_bn256(int enabled);
+/* small-M tile-shape switch (A/B testing): 1 = 128 x 64 tiles, unsplit up to K = 1984, for bf16 forward / dgrad problems with
+ * fewer 128-wide tiles than half the SMs (default) */
+int ofa_gemm_set_small64(int enabled);
 /* smallest number of 256 x 256 pair tiles for which the cta_group::2 kernel is chosen (default 38; A/B testing) */
 int ofa_gemm_set_pair_min_tiles(int n);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ofa_gemm_set_pair_mode": [c_i],
     "ofa_gemm_set_tma_store": [c_i],
     "ofa_gemm_set_wgrad_bn256": [c_i],
+    "ofa_gemm_set_small64": [c_i],
     "ofa_gemm_set_pair_min_tiles": [c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
@@ -143,6 +144,8 @@ def load(path=None):
         lib.ofa_layernorm_set_staged(int(os.environ["OFA_LN_STAGED"]))
     if os.environ.get("OFA_ATTN_FWD_WS") is not None:   # A/B switch: warp-specialised attention forward (default on)
         lib.ofa_attn_set_fwd_ws(int(os.environ["OFA_ATTN_FWD_WS"]))
+    if os.environ.get("OFA_GEMM_SMALL64") is not None:      # A/B switch: 128 x 64 tiles for small-M GEMMs
+        lib.ofa_gemm_set_small64(int(os.environ["OFA_GEMM_SMALL64"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch
         lib.ofa_set_pdl(int(os.environ["OFA_PDL"]))
     _lib = lib

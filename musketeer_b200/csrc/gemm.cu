@@ -20,6 +20,7 @@
 // a 256 x 256 pair tile costs each SM about what one 128 x 128 tile costs (measured ~1.05 vs ~0.55 PFLOP/s): the pair kernel
 // wins as soon as the single-CTA kernel would need a second wave, i.e. from about a quarter of the machine's pairs
 static int g_ofa_gemm_pair_min_tiles = 38;
+static int g_ofa_gemm_small64 = 1;        // 128 x 64 tiles for small-M forward / dgrad problems (A/B switch)
 static int g_ofa_gemm_wgrad_bn256 = 1;    // weight-gradient (fp32 accumulate) problems prefer 128 x 256 tiles
 static int g_ofa_gemm_tma_store = 1;      // bf16 epilogue through shared memory + TMA store (0: per-thread row stores)
 static int g_ofa_gemm_pair_enabled = 2;   // 0: single-CTA tiles, 1: pair with B multicast, 2: cta_group::2 MMA
@@ -821,6 +822,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
 template <int A_MN, int B_MN, typename OutT>
 int launch_bn(int bn, int pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
   if (pair) return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 1>(ta, tb, td, p, st) : launch<A_MN, B_MN, OutT, 128, 1>(ta, tb, td, p, st);
+  if constexpr (A_MN == 0 && sizeof(OutT) == 2) {      // 128 x 64 tiles: forward / dgrad of the small-M problems (decoder steps)
+    if (bn == 64) return launch<A_MN, B_MN, OutT, 64, 0>(ta, tb, td, p, st);
+  }
   return bn == 256 ? launch<A_MN, B_MN, OutT, 256, 0>(ta, tb, td, p, st) : launch<A_MN, B_MN, OutT, 128, 0>(ta, tb, td, p, st);
 }
 
@@ -863,6 +867,11 @@ void plan(int M, int N, int K, int batch, int* bn, int* splits) {
 extern "C" int ofa_gemm_set_pair_min_tiles(int n) {
   const int old = g_ofa_gemm_pair_min_tiles;
   g_ofa_gemm_pair_min_tiles = n;
+  return old;
+}
+extern "C" int ofa_gemm_set_small64(int enabled) {
+  const int old = g_ofa_gemm_small64;
+  g_ofa_gemm_small64 = enabled;
   return old;
 }
 extern "C" int ofa_gemm_set_wgrad_bn256(int enabled) {
@@ -927,6 +936,22 @@ extern "C" int ofa_gemm_bf16(const void* A, const void* B, void* D, int M, int N
       if (s < 1) s = 1;
     }
     if (tiles * s >= kNumSMs / 2) { bn = 256; splits = s; }
+  }
+  if (!reduce_f32 && g_ofa_gemm_small64 && batch == 1 && !a_mn_major && out_dtype == OFA_BF16 && N % 64 == 0) {
+    // small-M problems (one decoder step: M = beams; the 12-token decoder groups of a training step): fewer 128-wide tiles than
+    // half the machine.  128 x 64 tiles double the CTA count, and K up to 1984 then runs unsplit -- the fp32 partials and the
+    // reduce pass of split-K cost more than the second half of the k-loop (M = 576, N = K = 768: 19.3 us split vs cuBLAS 9.1)
+    const int tm = (M + BM - 1) / BM, nkb64 = (K + BK - 1) / BK;
+    if ((long long)tm * ((N + 127) / 128) * 2 <= kNumSMs) {
+      const int tiles = tm * (N / 64);
+      int s = 1;
+      if (tiles * 2 <= kNumSMs && nkb64 >= 32) {
+        s = kNumSMs / tiles;
+        if (s > nkb64 / 8) s = nkb64 / 8;
+        if (s < 1) s = 1;
+      }
+      if (s <= splits || splits == 1) { bn = 64; splits = s; }
+    }
   }
   if (!reduce_f32 && splits > 1 &&
       (workspace == nullptr || workspace_bytes < (long long)splits * batch * M * N * (long long)sizeof(float)))

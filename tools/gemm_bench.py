@@ -26,6 +26,16 @@ if "--one" in sys.argv:
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 if "--no-tma-store" in sys.argv:
     _lib.load().ofa_gemm_set_tma_store(0)
+if "--dec" in sys.argv:      # decoder groups of the merged task passes (32 x 250 and 48 x 12 target positions) and the encoder pass
+    SHAPES = [("dec8000 qkv fwd", 8000, 2304, 768, 0, 0), ("dec8000 proj fwd", 8000, 768, 768, 0, 0),
+              ("dec8000 proj dgrad", 8000, 768, 768, 0, 1), ("dec8000 fc1 fwd", 8000, 3072, 768, 0, 0),
+              ("dec8000 fc2 fwd", 8000, 768, 3072, 0, 0), ("dec576 proj fwd", 576, 768, 768, 0, 0),
+              ("dec320 proj fwd", 320, 768, 768, 0, 0), ("dec320 qkv fwd", 320, 2304, 768, 0, 0),
+              ("dec320 fc1 fwd", 320, 3072, 768, 0, 0), ("dec320 fc2 fwd", 320, 768, 3072, 0, 0),
+              ("dec576 fc2 fwd", 576, 768, 3072, 0, 0), ("dec576 fc1 dgrad", 576, 768, 3072, 0, 1),
+              ("dec576 proj dgrad", 576, 768, 768, 0, 1), ("enc53440 qkv fwd", 53440, 2304, 768, 0, 0),
+              ("enc53440 proj fwd", 53440, 768, 768, 0, 0), ("l3 conv1 dgrad", 36864, 1024, 256, 0, 1),
+              ("l3 conv3 fwd", 36864, 1024, 256, 0, 0)]
 if "--conv" in sys.argv:
     SHAPES = [s for s in SHAPES if "conv" in s[0]]
 for _m in (0, 1, 2):
