@@ -462,7 +462,7 @@ def main():
             traceback.print_exc(file=sys.stderr)
             caption = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     cpu = None
-    if a.cpu_baseline:
+    if a.cpu_baseline and world == 1:       # (rank 0 at N = 1 only: the other N reuse that figure)
         try:
             v, t, cores, kind = cpu_reference(1, 1, a.arch, a.img, a.ref_task_batch)
             cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
