@@ -180,6 +180,16 @@ int ofa_trie_advance(const int* trie_ptr, const int* trie_tok, const int* trie_c
  * loader ships 1 byte per value instead of 4 (trainer.py:1246-1284 moves the fp32 tensor, then casts).  mean3 / std3: HOST floats. */
 int ofa_normalize_u8(const void* x, void* y, int N, int H, int W, const float* mean3, const float* std3, int dtype, void* stream);
 
+/* ---- beam bookkeeping of one step without finalisation (models/sequence_generator.py:438-586): eos_n[s] = eos candidates among
+ * the first `beam` of sentence s (the caller takes the reference's finalisation path when any is non-zero); otherwise the first
+ * `beam` non-eos / non-ignored candidates become the new hypotheses: parents' token / score prefixes gathered into the OUTPUT
+ * buffers, chosen token (column step + 1) and cumulative score (column step) appended, ignore flags and the reorder index
+ * (active_bbsz, int64 [bsz*beam]) written.  cand_index = beam * V + token as produced by ofa_beam_topk; C2 = 2 * beam.      */
+int ofa_beam_advance(const float* cand_scores, const long long* cand_index, int C2, const unsigned char* ignore_in,
+                     const long long* tok_in, long long ldtok, const float* sc_in, long long ldsc, long long* tok_out,
+                     float* sc_out, unsigned char* ignore_out, long long* active_bbsz, int* eos_n, int bsz, int beam, int V,
+                     int eos, int step, void* stream);
+
 /* ---- all-candidate scoring (utils/eval_utils.py:203-209; tasks/mm_tasks/vqa_gen.py:296-304, snli_ve.py:203-210): out[r] = sum
  * over the positions p in [seg_off[r], seg_off[r+1]) of log_softmax(logits[p] restricted to the next layer of trie node
  * node[p])[target[p]].  node[p] = -1: whole vocabulary, -2: position not counted; target == pad and empty layers count 0; a

@@ -94,6 +94,7 @@ SIGNATURES = {
     "ofa_beam_topk_width": [c_i],
     "ofa_trie_advance": [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_i, c_p],
     "ofa_normalize_u8": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_p],
+    "ofa_beam_advance": [c_p, c_p, c_i, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "ofa_trie_score": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p],
     "ofa_maxpool3x3s2_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "ofa_maxpool3x3s2_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],

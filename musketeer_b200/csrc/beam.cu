@@ -454,3 +454,75 @@ extern "C" int ofa_trie_score(const void* logits, long long ld, int dtype, int V
   OFA_LAUNCH_CHECK("trie_score_kernel");
   return 0;
 }
+
+// ---- beam bookkeeping of one step (models/sequence_generator.py:438-586 when no hypothesis finishes) -------------------------
+// From the top 2*beam candidates of every sentence: eos candidates among the first `beam` (not ignored, finite) are COUNTED
+// (eos_n[s]; the host takes the reference's finalisation path for the whole step when any count is non-zero), and -- the
+// common case, valid when all counts are zero -- the `beam` first non-eos / non-ignored candidates become the new hypotheses
+// (:528-560: active_mask = eos_mask * cand_size + arange, topk(smallest)): their parents' token / score prefixes are gathered
+// into the OTHER token / score buffers and the chosen token / cumulative score appended (:562-586).  Replaces ~20 index kernels
+// (eq, ne, and, masked_select, add, topk, ge, gather x3, index_select x2, copies) by one launch; one CTA per sentence.
+namespace {
+__global__ void __launch_bounds__(32) beam_advance_kernel(const float* __restrict__ cand_scores, const long long* __restrict__ cand_index,
+                                                          int C2, const unsigned char* __restrict__ ignore_in,
+                                                          const long long* __restrict__ tok_in, long long ldtok,
+                                                          const float* __restrict__ sc_in, long long ldsc,
+                                                          long long* __restrict__ tok_out, float* __restrict__ sc_out,
+                                                          unsigned char* __restrict__ ignore_out, long long* __restrict__ active_bbsz,
+                                                          int* __restrict__ eos_n, int beam, int V, int eos, int step) {
+  pdl_sync();
+  __shared__ long long sel_row[16], sel_tok[16];
+  __shared__ float sel_score[16];
+  const int s = blockIdx.x, lane = threadIdx.x;
+  if (lane == 0) {
+    unsigned mask = 0;      // bit c: candidate c is an eos candidate or (c < beam) ignored
+    int n = 0;
+    for (int c = 0; c < C2; ++c) {
+      const long long idx = cand_index[(size_t)s * C2 + c];
+      const float sc = cand_scores[(size_t)s * C2 + c];
+      bool e = (idx % V) == eos && sc != -CUDART_INF_F;                      // :444
+      const bool ign = c < beam && ignore_in[(size_t)s * beam + c] != 0;
+      if (ign) e = false;                                                      // :446
+      if (c < beam && e) ++n;
+      if (e || ign) mask |= 1u << c;                                           // :528
+    }
+    eos_n[s] = n;
+    int k = 0;
+    for (int pass = 0; pass < 2 && k < beam; ++pass)                           // smallest active_mask first: unmasked in candidate order,
+      for (int c = 0; c < C2 && k < beam; ++c)                                 // then masked ones (:533-539)
+        if (((mask >> c) & 1u) == (unsigned)pass) {
+          const long long idx = cand_index[(size_t)s * C2 + c];
+          sel_row[k] = idx / V + (long long)s * beam;                          // cand_bbsz_idx (:440)
+          sel_tok[k] = idx % V;
+          sel_score[k] = cand_scores[(size_t)s * C2 + c];
+          ignore_out[(size_t)s * beam + k] = pass ? 1 : 0;                     // :544
+          active_bbsz[(size_t)s * beam + k] = sel_row[k];
+          ++k;
+        }
+  }
+  __syncwarp();
+  for (int k = 0; k < beam; ++k) {
+    const long long src = sel_row[k], dst = (long long)s * beam + k;
+    for (int c = lane; c <= step; c += 32) tok_out[dst * ldtok + c] = tok_in[src * ldtok + c];          // :563-565
+    for (int c = lane; c < step; c += 32) sc_out[dst * ldsc + c] = sc_in[src * ldsc + c];              // :571-574
+    if (lane == 0) {
+      tok_out[dst * ldtok + step + 1] = sel_tok[k];                                                     // :567-569
+      sc_out[dst * ldsc + step] = sel_score[k];                                                         // :575-577
+    }
+  }
+}
+}  // namespace
+
+extern "C" int ofa_beam_advance(const float* cand_scores, const long long* cand_index, int C2, const unsigned char* ignore_in,
+                                const long long* tok_in, long long ldtok, const float* sc_in, long long ldsc, long long* tok_out,
+                                float* sc_out, unsigned char* ignore_out, long long* active_bbsz, int* eos_n, int bsz, int beam,
+                                int V, int eos, int step, void* stream) {
+  OFA_CHECK(bsz > 0 && beam > 0 && beam <= 16 && C2 >= beam && C2 <= 32 && V > 0 && step >= 0, "ofa_beam_advance: bad sizes");
+  OFA_CHECK(cand_scores && cand_index && ignore_in && tok_in && sc_in && tok_out && sc_out && ignore_out && active_bbsz && eos_n,
+            "ofa_beam_advance: null operand");
+  OFA_CHECK(tok_in != tok_out && sc_in != sc_out, "ofa_beam_advance: the gather needs separate output buffers");
+  OFA_CUDA(ofa_launch_pdl(beam_advance_kernel, dim3(bsz), 32, 0, (cudaStream_t)stream, cand_scores, cand_index, C2, ignore_in, tok_in,
+                          ldtok, sc_in, ldsc, tok_out, sc_out, ignore_out, active_bbsz, eos_n, beam, V, eos, step));
+  OFA_LAUNCH_CHECK("beam_advance_kernel");
+  return 0;
+}

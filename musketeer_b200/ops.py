@@ -1182,6 +1182,18 @@ def beam_topk(logits, beam, K, temperature=1.0, prev_scores=None, step0=False, e
     return cs, ci, ws
 
 
+def beam_advance(cand_scores, cand_index, ignore_in, tok_in, sc_in, tok_out, sc_out, ignore_out, active_bbsz, eos_n, beam, V,
+                 eos, step):
+    """Beam bookkeeping of one step without finalisation (csrc/beam.cu beam_advance_kernel); all buffers preallocated."""
+    _need_cuda(cand_scores)
+    bsz, C2 = cand_scores.shape
+    assert ignore_in.dtype == torch.bool and ignore_out.dtype == torch.bool and eos_n.dtype == torch.int32
+    assert tok_in.stride(1) == 1 and tok_out.stride(0) == tok_in.stride(0) and sc_out.stride(0) == sc_in.stride(0)
+    call("ofa_beam_advance", _p(cand_scores), _p(cand_index), C2, _p(ignore_in), _p(tok_in), tok_in.stride(0), _p(sc_in),
+         sc_in.stride(0), _p(tok_out), _p(sc_out), _p(ignore_out), _p(active_bbsz), _p(eos_n), bsz, int(beam), int(V), int(eos),
+         int(step), _st())
+
+
 def trie_advance(trie, node_in, parent, tok):
     """node_out[r] = child of node_in[parent[r]] along tok[r] (-1 when the prefix leaves the trie)."""
     out = torch.empty_like(node_in)

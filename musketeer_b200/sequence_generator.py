@@ -108,18 +108,31 @@ class SequenceGenerator(torch.nn.Module):
             static = self._static.get(sig)
             if static is None:
                 static = self._static[sig] = {
-                    "tokens": torch.empty((bsz * beam, max_len + 2), dtype=torch.long, device=dev),
+                    # two token buffers: a step's bookkeeping gathers the surviving hypotheses from one into the other
+                    "tokens": [torch.empty((bsz * beam, max_len + 2), dtype=torch.long, device=dev) for _ in range(2)],
                     "order": torch.zeros(bsz * beam, dtype=torch.long, device=dev),
                     "inc": {"_ofa_b200": {"reuse": True}}, "graphs": {}, "calls": 0, "pool": None}
             static["calls"] += 1
         if static is not None:
-            tokens = static["tokens"]
-            tokens.fill_(self.pad)
+            tok_bufs = static["tokens"]
+            for t_ in tok_bufs:
+                t_.fill_(self.pad)
         else:
-            tokens = torch.full((bsz * beam, max_len + 2), self.pad, dtype=torch.long, device=dev)
-        tokens[:, 0] = self.bos
+            tok_bufs = [torch.full((bsz * beam, max_len + 2), self.pad, dtype=torch.long, device=dev) for _ in range(2)]
+        for t_ in tok_bufs:
+            t_[:, 0] = self.bos
+        tokens, alt_tokens = tok_bufs
+        alt_scores = torch.zeros_like(scores)
         bsz0 = bsz
         cands_to_ignore = torch.zeros(bsz, beam, dtype=torch.bool, device=dev)
+        alt_ignore = torch.zeros_like(cands_to_ignore)
+        fused = dev.type == "cuda"                      # one-launch bookkeeping (csrc/beam.cu beam_advance_kernel)
+        if fused:
+            active_buf = [torch.empty(bsz * beam, dtype=torch.long, device=dev) for _ in range(2)]
+            eos_n = torch.zeros(bsz, dtype=torch.int32, device=dev)
+            if getattr(self, "_eos_host", None) is None or self._eos_host.numel() < bsz:
+                self._eos_host = torch.zeros(max(bsz, 64), dtype=torch.int32).pin_memory()      # (page-locking is slow: once)
+            eos_host = self._eos_host
         finalized: List[List[Dict]] = [[] for _ in range(bsz)]
         finished = [False] * bsz
         num_remaining = bsz
@@ -145,7 +158,7 @@ class SequenceGenerator(torch.nn.Module):
                 corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
                 reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
             graphable = (static is not None and step >= 1 and bsz == bsz0 and batch_idxs is None and static["calls"] >= 2
-                         and tokens is static["tokens"])
+                         and (tokens is static["tokens"][0] or tokens is static["tokens"][1]))
             if graphable:
                 logits = self._graphed_step(model, static, step, tokens, enc, inc, reorder_state)
             else:
@@ -161,6 +174,27 @@ class SequenceGenerator(torch.nn.Module):
                 eos_one=self.ignore_eos, crange=(self.constraint_start, self.constraint_end) if self.constraint_start is not None else None,
                 range_post=self.zero_shot, trie=trie, node=node, trie_post=self.zero_shot, tokens=tokens, step=step,
                 ngram=self.no_repeat_ngram_size, ws=topk_ws)
+            if fused and step < max_len:
+                # the common step -- no hypothesis ends: one launch gathers the surviving hypotheses into the other buffers and
+                # counts the eos candidates; the count is the one host synchronisation of the step (the reference synchronises in
+                # masked_select, :447-450).  Any eos candidate -> the reference's own sequence of operations below, on the
+                # untouched inputs.
+                if alt_tokens.shape != tokens.shape:
+                    alt_tokens = torch.full_like(tokens, self.pad)
+                    alt_scores, alt_ignore = torch.zeros_like(scores), torch.zeros_like(cands_to_ignore)
+                act = active_buf[step & 1][:bsz * beam]
+                ops.beam_advance(cand_scores, idx, cands_to_ignore.contiguous(), tokens, scores, alt_tokens, alt_scores, alt_ignore,
+                                 act, eos_n[:bsz], beam, V, self.eos, step)
+                eos_host[:bsz].copy_(eos_n[:bsz], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if int(eos_host[:bsz].sum()) == 0:
+                    tokens, alt_tokens = alt_tokens, tokens
+                    scores, alt_scores = alt_scores, scores
+                    cands_to_ignore, alt_ignore = alt_ignore, cands_to_ignore
+                    if node is not None:
+                        node = ops.trie_advance(trie, node, act, tokens[:, step + 1])
+                    reorder_state, batch_idxs = act, None
+                    continue
             cand_beams = idx // V
             cand_indices = idx.fmod(V)
             cand_bbsz_idx = cand_beams + bbsz_offsets
@@ -220,7 +254,7 @@ class SequenceGenerator(torch.nn.Module):
         group -> sentence map tensor) is restored to its post-step value after every replay."""
         st = inc["_ofa_b200"]
         static["order"].copy_(reorder_state)
-        key = (step, st.get("layout", 0), st["tcur"], st["ppar"])
+        key = (step, st.get("layout", 0), st["tcur"], st["ppar"], 0 if tokens is static["tokens"][0] else 1)
         g = static["graphs"].get(key)
         if g is None:
             torch.cuda.synchronize()
