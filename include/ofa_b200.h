@@ -301,6 +301,9 @@ int ofa_attn_fwd_tc(const OfaAttnArgs* args, void* stream);
 /* A/B switch: 1 = warp-specialised forward (TMA producer warp, tcgen05 issuer warp, two softmax warpgroups; default),
  * 0 = the single-role kernel of round 1; returns the previous setting */
 int ofa_attn_set_fwd_ws(int enabled);
+/* A/B switch: 1 = attention backward with T <= 16 query rows and no relative-position bias (short-target cross-attention) runs on
+ * the warp-level kernel of csrc/attention_small.cu (default), 0 = always the 128-row tcgen05 kernel; returns the previous setting */
+int ofa_attn_set_bwd_small(int enabled);
 /* backward: fills grads->delta, dq/dpq/dk/dpk/dv and accumulates dtok_lut / dimg_lut; dq_acc = B*T*H*128 floats scratch */
 int ofa_attn_bwd_tc(const OfaAttnArgs* args, const OfaAttnGrads* grads, float* dq_acc, void* stream);
 

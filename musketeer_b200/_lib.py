@@ -109,6 +109,7 @@ SIGNATURES = {
     "ofa_attn_bwd_simt": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_i, c_p],
     "ofa_attn_fwd_tc": [C.POINTER(OfaAttnArgs), c_p],
     "ofa_attn_set_fwd_ws": [c_i],
+    "ofa_attn_set_bwd_small": [c_i],
     "ofa_attn_bwd_tc": [C.POINTER(OfaAttnArgs), C.POINTER(OfaAttnGrads), c_p, c_p],
 }
 
@@ -145,6 +146,8 @@ def load(path=None):
         lib.ofa_layernorm_set_staged(int(os.environ["OFA_LN_STAGED"]))
     if os.environ.get("OFA_ATTN_FWD_WS") is not None:   # A/B switch: warp-specialised attention forward (default on)
         lib.ofa_attn_set_fwd_ws(int(os.environ["OFA_ATTN_FWD_WS"]))
+    if os.environ.get("OFA_ATTN_BWD_SMALL") is not None:     # A/B switch: short-query attention backward kernel
+        lib.ofa_attn_set_bwd_small(int(os.environ["OFA_ATTN_BWD_SMALL"]))
     if os.environ.get("OFA_GEMM_SMALL64") is not None:      # A/B switch: 128 x 64 tiles for small-M GEMMs
         lib.ofa_gemm_set_small64(int(os.environ["OFA_GEMM_SMALL64"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch

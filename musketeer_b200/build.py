@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofa_b200.so")
-SOURCES = ["runtime.cu", "gemm.cu", "rowwise.cu", "loss.cu", "attention_simt.cu", "attention_tc.cu", "dropout.cu", "batchnorm.cu", "optim.cu", "conv.cu", "decode.cu", "pool.cu", "im2col.cu", "beam.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "rowwise.cu", "loss.cu", "attention_simt.cu", "attention_tc.cu", "attention_small.cu", "dropout.cu", "batchnorm.cu", "optim.cu", "conv.cu", "decode.cu", "pool.cu", "im2col.cu", "beam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

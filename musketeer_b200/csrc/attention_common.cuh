@@ -7,6 +7,10 @@ typedef OfaAttnArgs AttnArgs;
 typedef OfaAttnBias AttnBias;
 typedef OfaAttnGrads AttnGrads;
 
+// csrc/attention_small.cu: bf16 backward for T <= 16 query rows without relative-position bias (short-target cross-attention)
+bool ofa_attn_bwd_small_applicable(const AttnArgs* a, const AttnGrads* g);
+int ofa_attn_bwd_small_launch(const AttnArgs* a, const AttnGrads* g, cudaStream_t st);
+
 #ifdef __CUDACC__
 // index into the per-head image LUT for position ids (1-based, row-major over an ibs x ibs grid):
 // closed form of make_image_bucket_position (models/ofa/unify_transformer.py:66-81) for ids >= 1

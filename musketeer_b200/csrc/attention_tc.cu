@@ -1276,6 +1276,12 @@ int make_qkv_tmap(CUtensorMap* tm, const void* p, int L, int H, int B, long long
 
 }  // namespace
 
+static int g_attn_bwd_small = 1;      // A/B switch: short-query backward kernel (ofa_attn_set_bwd_small)
+extern "C" int ofa_attn_set_bwd_small(int enabled) {
+  const int old = g_attn_bwd_small;
+  g_attn_bwd_small = enabled;
+  return old;
+}
 static int g_attn_fwd_ws = 1;
 /* A/B switch: 1 = warp-specialised forward with the A operands in tensor memory (default), 2 = warp-specialised with every
  * operand in shared memory, 0 = the single-role round-1 kernel; returns the previous setting */
@@ -1371,6 +1377,13 @@ extern "C" int ofa_attn_bwd_tc(const AttnArgs* a, const AttnGrads* g, float* dq_
     configured = true;
   }
   const long long nrow = (long long)a->B * a->T * a->H;
+  if (g_attn_bwd_small && ofa_attn_bwd_small_applicable(a, g)) {
+    // short targets against a long source (decoder cross-attention of the 5 / 12-token tasks): one 128-thread CTA per (batch,
+    // head) on warp-level MMA tiles, dQ' in registers -- no accumulator memset, no convert pass (csrc/attention_small.cu)
+    OFA_CUDA(ofa_launch_pdl(attn_bwd_delta_kernel, (unsigned)((nrow * 8 + 255) / 256), 256, 0, st, (const __nv_bfloat16*)g->dout, (const __nv_bfloat16*)a->o, a->ldo, a->bso, a->B, a->T, a->H, g->delta));
+    OFA_LAUNCH_CHECK("attn_bwd_delta_kernel");
+    return ofa_attn_bwd_small_launch(a, g, st);
+  }
   OFA_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)nrow * 128 * sizeof(float), st));
   OFA_CUDA(ofa_launch_pdl(attn_bwd_delta_kernel, (unsigned)((nrow * 8 + 255) / 256), 256, 0, st, (const __nv_bfloat16*)g->dout, (const __nv_bfloat16*)a->o, a->ldo, a->bso, a->B, a->T, a->H, g->delta));
   OFA_LAUNCH_CHECK("attn_bwd_delta_kernel");

@@ -326,7 +326,10 @@ def _attn_inputs(B, T, S, H, P, dtype, seed, causal=False):
 @pytest.mark.parametrize("dtype,use_tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)])
 @pytest.mark.parametrize("B,T,S,H,P,causal", [(2, 40, 40, 2, 16, False), (2, 33, 33, 4, 0, True),
                                               (1, 200, 200, 2, 150, False), (2, 5, 77, 2, 0, False),
-                                              (1, 130, 130, 1, 0, True)])
+                                              (1, 130, 130, 1, 0, True),
+                                              # short targets x long source (csrc/attention_small.cu): the 12-token decoder group
+                                              # of the bench step, and the 16-row limit with a ragged last key tile
+                                              (3, 12, 835, 12, 0, False), (2, 16, 100, 4, 0, False)])
 def test_attention_fwd_bwd(dtype, use_tc, B, T, S, H, P, causal):
     ops = _ops()
     cross = T != S
