@@ -138,7 +138,7 @@ def cpu_reference(steps, warmup, arch, img, task_batch=2):
     return 5.0 * task_batch / t, t, os.cpu_count(), kind
 
 
-def caption_bench(dev, batch=64, img=480, beam=5, iters=2):
+def caption_bench(dev, batch=64, img=480, beam=5, iters=6):
     """BASELINE.json configs[4]: beam-5 captioning, OFA-base bf16, `batch` synthetic 480x480 images, prompt
     of 8 source tokens, max_len_b 16 (random weights rarely emit EOS: the worst case of 17 decoder steps) -> captions/s."""
     from musketeer_b200.sequence_generator import SequenceGenerator
