@@ -110,6 +110,10 @@ class SequenceGenerator(torch.nn.Module):
                 static = self._static[sig] = {
                     # two token buffers: a step's bookkeeping gathers the surviving hypotheses from one into the other
                     "tokens": [torch.empty((bsz * beam, max_len + 2), dtype=torch.long, device=dev) for _ in range(2)],
+                    "scores": [torch.zeros(bsz * beam, max_len + 1, device=dev) for _ in range(2)],
+                    "ignore": [torch.zeros(bsz, beam, dtype=torch.bool, device=dev) for _ in range(2)],
+                    "active": [torch.empty(bsz * beam, dtype=torch.long, device=dev) for _ in range(2)],
+                    "eos_n": torch.zeros(bsz, dtype=torch.int32, device=dev),
                     "order": torch.zeros(bsz * beam, dtype=torch.long, device=dev),
                     "inc": {"_ofa_b200": {"reuse": True}}, "graphs": {}, "calls": 0, "pool": None}
             static["calls"] += 1
@@ -122,14 +126,21 @@ class SequenceGenerator(torch.nn.Module):
         for t_ in tok_bufs:
             t_[:, 0] = self.bos
         tokens, alt_tokens = tok_bufs
-        alt_scores = torch.zeros_like(scores)
         bsz0 = bsz
-        cands_to_ignore = torch.zeros(bsz, beam, dtype=torch.bool, device=dev)
-        alt_ignore = torch.zeros_like(cands_to_ignore)
         fused = dev.type == "cuda"                      # one-launch bookkeeping (csrc/beam.cu beam_advance_kernel)
-        if fused:
+        if static is not None:                          # persistent buffers: captured steps hold pointers into them
+            scores, alt_scores = static["scores"]
+            cands_to_ignore, alt_ignore = static["ignore"]
+            for t_ in (scores, alt_scores, cands_to_ignore, alt_ignore):
+                t_.zero_()
+            active_buf, eos_n = static["active"], static["eos_n"]
+        else:
+            alt_scores = torch.zeros_like(scores)
+            cands_to_ignore = torch.zeros(bsz, beam, dtype=torch.bool, device=dev)
+            alt_ignore = torch.zeros_like(cands_to_ignore)
             active_buf = [torch.empty(bsz * beam, dtype=torch.long, device=dev) for _ in range(2)]
             eos_n = torch.zeros(bsz, dtype=torch.int32, device=dev)
+        if fused:
             if getattr(self, "_eos_host", None) is None or self._eos_host.numel() < bsz:
                 self._eos_host = torch.zeros(max(bsz, 64), dtype=torch.int32).pin_memory()      # (page-locking is slow: once)
             eos_host = self._eos_host
@@ -159,32 +170,58 @@ class SequenceGenerator(torch.nn.Module):
                 reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
             graphable = (static is not None and step >= 1 and bsz == bsz0 and batch_idxs is None and static["calls"] >= 2
                          and (tokens is static["tokens"][0] or tokens is static["tokens"][1]))
-            if graphable:
-                logits = self._graphed_step(model, static, step, tokens, enc, inc, reorder_state)
+            # the whole step as one graph (decoder + fused tail + bookkeeping) when every buffer it touches is persistent
+            whole = graphable and fused and step < max_len and node is None and scores is static["scores"][
+                0 if tokens is static["tokens"][0] else 1]
+            if whole and not (cands_to_ignore is static["ignore"][0] or cands_to_ignore is static["ignore"][1]):
+                par = 0 if tokens is static["tokens"][0] else 1
+                static["ignore"][par].copy_(cands_to_ignore)       # (left behind by a finalisation step)
+                cands_to_ignore, alt_ignore = static["ignore"][par], static["ignore"][1 - par]
+
+            def tail(logits, ws, tokens=tokens, scores=scores, step=step):
+                """fused tail: temperature, constraints, log-softmax, masks, n-gram blocking, + beam scores, top 2*beam.
+                `ws`: workspace of an earlier eager call or None -- a captured step must NOT hold a pointer to an eager tensor
+                that dies with this generate call, so the graph path allocates its own inside the capture."""
+                lg = logits[:, -1, :]
+                prev = scores.view(bsz, beam, -1)[:, :, step - 1].reshape(-1).contiguous() if step > 0 else None
+                return ops.beam_topk(
+                    lg, beam, min(cand_size, beam * V - 1), self.temperature, prev, step0=(step == 0), eos=self.eos, pad=self.pad,
+                    unk=self.unk, unk_penalty=self.unk_penalty, block_eos=step < self.min_len, force_eos=step >= max_len,
+                    eos_one=self.ignore_eos,
+                    crange=(self.constraint_start, self.constraint_end) if self.constraint_start is not None else None,
+                    range_post=self.zero_shot, trie=trie, node=node, trie_post=self.zero_shot, tokens=tokens, step=step,
+                    ngram=self.no_repeat_ngram_size, ws=ws)
+
+            def advance(cand_scores, idx, act):
+                ops.beam_advance(cand_scores, idx, cands_to_ignore.contiguous(), tokens, scores, alt_tokens, alt_scores, alt_ignore,
+                                 act, eos_n[:bsz], beam, V, self.eos, step)
+
+            act = active_buf[step & 1][:bsz * beam] if fused else None
+            advanced = False
+            if whole:
+                alt_tokens = static["tokens"][1 if tokens is static["tokens"][0] else 0]
+                alt_scores = static["scores"][1 if scores is static["scores"][0] else 0]
+                logits, cand_scores, idx = self._graphed_step(model, static, step, tokens, enc, inc, reorder_state,
+                                                              tail=tail, advance=lambda cs_, ix_: advance(cs_, ix_, act))
+                advanced = True
             else:
-                if reorder_state is not None:
-                    model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
-                logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc, padded_logits=True)
-            # fused tail: temperature, constraints, log-softmax, masks, n-gram blocking, + beam scores, top 2*beam (csrc/beam.cu)
-            lg = logits[:, -1, :]
-            prev = scores.view(bsz, beam, -1)[:, :, step - 1].reshape(-1).contiguous() if step > 0 else None
-            cand_scores, idx, topk_ws = ops.beam_topk(
-                lg, beam, min(cand_size, beam * V - 1), self.temperature, prev, step0=(step == 0), eos=self.eos, pad=self.pad,
-                unk=self.unk, unk_penalty=self.unk_penalty, block_eos=step < self.min_len, force_eos=step >= max_len,
-                eos_one=self.ignore_eos, crange=(self.constraint_start, self.constraint_end) if self.constraint_start is not None else None,
-                range_post=self.zero_shot, trie=trie, node=node, trie_post=self.zero_shot, tokens=tokens, step=step,
-                ngram=self.no_repeat_ngram_size, ws=topk_ws)
+                if graphable:
+                    logits = self._graphed_step(model, static, step, tokens, enc, inc, reorder_state)
+                else:
+                    if reorder_state is not None:
+                        model.decoder.reorder_incremental_state_scripting(inc, reorder_state)
+                    logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc, padded_logits=True)
+                cand_scores, idx, topk_ws = tail(logits, topk_ws)
             if fused and step < max_len:
                 # the common step -- no hypothesis ends: one launch gathers the surviving hypotheses into the other buffers and
                 # counts the eos candidates; the count is the one host synchronisation of the step (the reference synchronises in
                 # masked_select, :447-450).  Any eos candidate -> the reference's own sequence of operations below, on the
                 # untouched inputs.
-                if alt_tokens.shape != tokens.shape:
-                    alt_tokens = torch.full_like(tokens, self.pad)
-                    alt_scores, alt_ignore = torch.zeros_like(scores), torch.zeros_like(cands_to_ignore)
-                act = active_buf[step & 1][:bsz * beam]
-                ops.beam_advance(cand_scores, idx, cands_to_ignore.contiguous(), tokens, scores, alt_tokens, alt_scores, alt_ignore,
-                                 act, eos_n[:bsz], beam, V, self.eos, step)
+                if not advanced:
+                    if alt_tokens.shape != tokens.shape:
+                        alt_tokens = torch.full_like(tokens, self.pad)
+                        alt_scores, alt_ignore = torch.zeros_like(scores), torch.zeros_like(cands_to_ignore)
+                    advance(cand_scores, idx, act)
                 eos_host[:bsz].copy_(eos_n[:bsz], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 if int(eos_host[:bsz].sum()) == 0:
@@ -243,30 +280,41 @@ class SequenceGenerator(torch.nn.Module):
                 node = ops.trie_advance(trie, node, active_bbsz_idx.contiguous(), tokens[:, step + 1])
             reorder_state = active_bbsz_idx
         for s in range(len(finalized)):
-            sc = torch.tensor([float(h["score"]) for h in finalized[s]])
+            # (:589-597 reads every score back with .item(): one device synchronisation per hypothesis; the host copies taken
+            # once per finalisation step in _finalize give the same order)
+            sc = torch.tensor([h.pop("_score_host") for h in finalized[s]])
             _, o = torch.sort(sc, descending=True)
             finalized[s] = [finalized[s][i] for i in o]
         return finalized
 
-    def _graphed_step(self, model, static, step, tokens, enc, inc, reorder_state):
-        """Beam reorder + one decoder step as a CUDA graph.  The graph holds pointers into the persistent token buffer, the
-        reorder-index buffer and the decoder's KV-cache state; the Python side of that state (ping-pong index, length, the
-        group -> sentence map tensor) is restored to its post-step value after every replay."""
+    def _graphed_step(self, model, static, step, tokens, enc, inc, reorder_state, tail=None, advance=None):
+        """Beam reorder + one decoder step (+ with `tail` / `advance` the fused beam tail and the bookkeeping launch) as a CUDA
+        graph.  The graph holds pointers into the persistent token / score / flag buffers, the reorder-index buffer and the
+        decoder's KV-cache state; the Python side of that state (ping-pong index, length, the group -> sentence map tensor) is
+        restored to its post-step value after every replay.  Returns logits, or (logits, cand_scores, cand_index) with a tail."""
         st = inc["_ofa_b200"]
         static["order"].copy_(reorder_state)
-        key = (step, st.get("layout", 0), st["tcur"], st["ppar"], 0 if tokens is static["tokens"][0] else 1)
+        key = (step, st.get("layout", 0), st["tcur"], st["ppar"], 0 if tokens is static["tokens"][0] else 1, tail is not None)
         g = static["graphs"].get(key)
         if g is None:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            cand = None
             with torch.cuda.graph(graph, pool=static["pool"]):
                 model.decoder.reorder_incremental_state_scripting(inc, static["order"])
                 logits, _ = model.decoder(tokens[:, :step + 1], encoder_out=enc, incremental_state=inc, padded_logits=True)
+                if tail is not None:
+                    cs_, ix_, _ws = tail(logits, None)
+                    advance(cs_, ix_)
+                    cand = (cs_, ix_)
             if static["pool"] is None:
                 static["pool"] = graph.pool()
-            g = static["graphs"][key] = {"graph": graph, "logits": logits, "post": {k: st[k] for k in self._STATE_KEYS}}
+            g = static["graphs"][key] = {"graph": graph, "logits": logits, "cand": cand,
+                                         "post": {k: st[k] for k in self._STATE_KEYS}}
         g["graph"].replay()
         st.update(g["post"])
+        if tail is not None:
+            return g["logits"], g["cand"][0], g["cand"][1]
         return g["logits"]
 
     _STATE_KEYS = ("tcur", "ppar", "len", "sent_row", "rows", "reordered_at")
@@ -289,11 +337,13 @@ class SequenceGenerator(torch.nn.Module):
         unfin_idx = bbsz_idx // beam
         sent = unfin_idx + cum.index_select(0, unfin_idx)
         sent_l, unfin_l = sent.tolist(), unfin_idx.tolist()
+        score_l = eos_scores.tolist()
+        toks, scs, poss = tokens_clone.unbind(0), eos_scores.unbind(0), pos_scores.unbind(0)     # one call each, not one per row
+        empty = torch.empty(0)
         for i in range(bbsz_idx.numel()):
             if len(finalized[sent_l[i]]) < beam:
-                finalized[sent_l[i]].append({"tokens": tokens_clone[i], "score": eos_scores[i],
-                                             "attention": torch.empty(0), "alignment": torch.empty(0),
-                                             "positional_scores": pos_scores[i]})
+                finalized[sent_l[i]].append({"tokens": toks[i], "score": scs[i], "_score_host": score_l[i],
+                                             "attention": empty, "alignment": empty, "positional_scores": poss[i]})
         newly = []
         for s, u in sorted(set(zip(sent_l, unfin_l))):
             if not finished[s] and (len(finalized[s]) == beam or step == max_len):
