@@ -95,6 +95,9 @@ class FusedAdam:
                   float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay), self.step_count,
                   float(grad_scale), float(self.clip_norm or 0.0), _dt(self.params[0]), _st(),
                   work=("byte", 30.0 * self.master.numel()))
+        # the kernel wrote the parameters through raw pointers: tell autograd's version counters, which key the caches derived
+        # from the weights (MultiheadAttention.qkv_eval's concatenated projection, the generator's captured decoder steps)
+        torch.autograd.graph.increment_version(self.params)
         return self.grad_norm
 
     def zero_grad(self, set_to_none=True):

@@ -104,6 +104,13 @@ class SequenceGenerator(torch.nn.Module):
         scores = torch.zeros(bsz * beam, max_len + 1, device=dev)
         static = None
         if self.cuda_graphs and dev.type == "cuda":
+            # captured decoder steps hold weights-derived tensors (the concatenated q|k|v projection of qkv_eval): a weights
+            # fingerprint (sum of the parameters' version counters: optimizers and load_state_dict bump them) retires the graphs
+            # of older weights
+            wv = sum(p._version for p in model.decoder.parameters())
+            if getattr(self, "_weights_version", wv) != wv:
+                self._static.clear()
+            self._weights_version = wv
             sig = (bsz, beam, max_len, enc["encoder_out"][0].shape[0], str(enc["encoder_out"][0].dtype))
             static = self._static.get(sig)
             if static is None:

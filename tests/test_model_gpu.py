@@ -268,6 +268,37 @@ def test_all_candidate_scorer_matches_reference(name, dtype):
                 assert abs(float(plain[b, c]) - want) < 2e-4, (b, c, float(plain[b, c]), want)
 
 
+def test_generator_follows_weight_updates():
+    """Caches derived from the weights (concatenated q|k|v projection, captured decoder steps) must not outlive an optimizer
+    step: FusedAdam writes the parameters through raw pointers, so it bumps their version counters itself."""
+    from musketeer_b200.optim import FusedAdam
+    from musketeer_b200.sequence_generator import SequenceGenerator
+    fx = load_golden("gen_micro_varied")
+    case = fx["case"]
+    cfg = synth.make_cfg(case["arch"], **case["cfg"])
+    sd = synth.synth_state_dict(cfg, seed=0, **{k: case[k] for k in ("emb_std", "w_std") if k in case})
+    model, task = build_product(cfg, sd, dtype=torch.float32)
+    model.eval()
+    sample = to_device(synth.make_batch(**case["batch"]), "cuda")
+    gen = SequenceGenerator([model], task.target_dictionary, **case["gen"])
+    for _ in range(3):                                   # eager, capture, replay
+        before = gen.generate([model], sample)
+    opt = FusedAdam(model.parameters(), lr=0.05, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clip_norm=0.0)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for p in model.parameters():
+        p.grad = torch.randn(p.shape, generator=g).to(p.device, p.dtype)
+    v0 = next(model.decoder.parameters())._version
+    opt.step()
+    assert next(model.decoder.parameters())._version > v0
+    after = gen.generate([model], sample)
+    fresh = SequenceGenerator([model], task.target_dictionary, cuda_graphs=False, **case["gen"]).generate([model], sample)
+    for hs, rs in zip(after, fresh):                     # the long-lived generator sees the new weights
+        for h, r in zip(hs, rs):
+            assert torch.equal(h["tokens"], r["tokens"]) and abs(float(h["score"]) - float(r["score"])) < 1e-5
+    assert any(not torch.equal(a[0]["tokens"], b[0]["tokens"]) or abs(float(a[0]["score"]) - float(b[0]["score"])) > 1e-3
+               for a, b in zip(after, before))           # (and the update did change the output)
+
+
 def test_incremental_decoder_matches_teacher_forcing():
     """Incremental decoding (KV cache) must reproduce the teacher-forced logits position by position (fp32, 1e-4)."""
     fx = load_golden("micro_text_only")
