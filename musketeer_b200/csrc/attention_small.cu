@@ -1,5 +1,6 @@
-// bf16 attention backward for SHORT query sequences (T <= 16) against long key sequences without relative-position bias: the
-// cross-attention of the decoder passes over short targets (VG 5, caption 12, gigaword 12 tokens x 835 source positions in the
+// bf16 attention backward for SHORT query sequences (T <= 16) without image relative-position bias: the cross-attention (long key
+// sequence, no bias) and the causal self-attention (token relative-position LUT and its gradient) of the decoder passes over
+// short targets (VG 5, caption 12, gigaword 12 tokens x 835 source positions in the
 // bench step; unify_multihead_attention.py:345-398 under autograd).  attn_bwd_tc_kernel spends a whole 128-row query tile, a
 // 640-thread CTA with 225 KB of shared memory and a dQ' round trip through an fp32 accumulator on every (batch, head, 128-key
 // tile) -- 13 us per CTA, 4032 CTAs, 386 us per launch for 12 real query rows.  Here one 128-thread CTA owns a (batch, head):
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
   unsigned char* Os = Qs + TQ * KP;                            // [16][VP]  dO
   unsigned char* Ss = Os + TQ * VP;                            // [4 warps][16][SP]  dS^T scratch
   float* red = reinterpret_cast<float*>(ring);                 // [4][16][128] partial dQ', over the drained rings
+  __shared__ float tok_hist[2 * TQ];                           // d tok_lut of this (batch, head): bin (i - j) + TQ - 1
   static_assert(4 * TQ * 128 * 4 <= 4 * 2 * STAGE, "dQ' partials must fit the rings");
   const int b = blockIdx.y, h = blockIdx.x;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -112,6 +114,10 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
     dl[e] = g.delta[ridx];
   }
   const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  const AttnBias& bz = a.bias;
+  const float* lut = bz.tok_lut ? bz.tok_lut + (size_t)h * (2 * bz.tok_max - 1) + bz.tok_max - 1 : nullptr;   // indexed by i_t - j_t
+  const bool want_dtok = lut && g.dtok_lut;
+  if (t < 2 * TQ) tok_hist[t] = 0.f;
   __syncthreads();
   // ldmatrix lane offsets: A-type (rows (l & 7) + 8 * ((l >> 3) & 1), 8-column block l >> 4) and B-type for [row-block][col-half]
   // matrix order (rows (l & 7) + 8 * (l >> 4), 8-column block (l >> 3) & 1)
@@ -162,10 +168,16 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int qe = (e & 1) + nb * 2;                     // index into nl2 / dl
-          const bool ok = kok[e >> 1] && (nb * 8 + fc + (e & 1)) < Tn;
-          const float pv = ok ? ex2f(fmaf(st[nb][e], kLog2e, nl2[qe])) : 0.f;
+          const int qi = nb * 8 + fc + (e & 1), kj = j0 + fr + 8 * (e >> 1);
+          bool ok = kok[e >> 1] && qi < Tn && !(a.causal && kj > qi);
+          float x = st[nb][e];
+          const bool tok_el = lut && ok && qi >= bz.q_text_off && kj >= bz.k_text_off;
+          const int rel = (qi - bz.q_text_off) - (kj - bz.k_text_off);
+          if (tok_el) x += lut[rel];
+          const float pv = ok ? ex2f(fmaf(x, kLog2e, nl2[qe])) : 0.f;
           p[nb][e] = pv;
           ds[nb][e] = pv * fmaf(dp[nb][e], cs, -dl[qe]);
+          if (want_dtok && tok_el && rel > -TQ && rel < TQ) atomicAdd(&tok_hist[rel + TQ - 1], ds[nb][e]);
         }
       pa[0] = pk2(p[0][0], p[0][1]); pa[1] = pk2(p[0][2], p[0][3]); pa[2] = pk2(p[1][0], p[1][1]); pa[3] = pk2(p[1][2], p[1][3]);
       da[0] = pk2(ds[0][0], ds[0][1]); da[1] = pk2(ds[0][2], ds[0][3]); da[2] = pk2(ds[1][0], ds[1][1]); da[3] = pk2(ds[1][2], ds[1][3]);
@@ -243,6 +255,8 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
     r1[0] = dq[nb][2]; r1[1] = dq[nb][3];
   }
   __syncthreads();
+  if (want_dtok && t < 2 * TQ - 1 && tok_hist[t] != 0.f)
+    atomicAdd(g.dtok_lut + (size_t)h * (2 * bz.tok_max - 1) + bz.tok_max - 1 + (t - (TQ - 1)), tok_hist[t]);
   const float qsc = g.dq_scale == 0.f ? 1.f : g.dq_scale;
   for (int e = t; e < TQ * 64; e += kT) {                      // two adjacent dims per thread
     const int i = e / 64, d2 = (e % 64) * 2;
@@ -260,7 +274,9 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
 }  // namespace
 
 bool ofa_attn_bwd_small_applicable(const AttnArgs* a, const AttnGrads* g) {
-  return a->T <= TQ && !a->causal && a->bias.tok_lut == nullptr && a->bias.img_lut == nullptr && a->q_pos_off == 0 &&
+  // a token relative-position LUT needs |i_t - j_t| < 16 for every pair: self-attention (S = T) with equal text offsets
+  const bool lut_ok = a->bias.tok_lut == nullptr || (a->S <= TQ && a->bias.q_text_off == a->bias.k_text_off);
+  return a->T <= TQ && lut_ok && a->bias.img_lut == nullptr && a->q_pos_off == 0 &&
          a->ldq % 8 == 0 && a->ldpq % 8 == 0 && a->ldk % 8 == 0 && a->ldpk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 &&
          a->bsq % 8 == 0 && a->bspq % 8 == 0 && a->bsk % 8 == 0 && a->bspk % 8 == 0 && a->bsv % 8 == 0 && a->bso % 8 == 0 &&
          g->lddq % 2 == 0 && g->lddpq % 2 == 0 && g->lddk % 2 == 0 && g->lddpk % 2 == 0 && g->lddv % 2 == 0;

@@ -329,7 +329,9 @@ def _attn_inputs(B, T, S, H, P, dtype, seed, causal=False):
                                               (1, 130, 130, 1, 0, True),
                                               # short targets x long source (csrc/attention_small.cu): the 12-token decoder group
                                               # of the bench step, and the 16-row limit with a ragged last key tile
-                                              (3, 12, 835, 12, 0, False), (2, 16, 100, 4, 0, False)])
+                                              (3, 12, 835, 12, 0, False), (2, 16, 100, 4, 0, False),
+                                              # short causal self-attention with the token relative-position LUT and its gradient
+                                              (3, 12, 12, 12, 0, True), (2, 16, 16, 2, 0, True), (2, 7, 7, 4, 0, False)])
 def test_attention_fwd_bwd(dtype, use_tc, B, T, S, H, P, causal):
     ops = _ops()
     cross = T != S
