@@ -436,7 +436,7 @@ def main():
         if top == "ofa_gemm_bf16" and a.task_batch == 16 and a.arch == "ofa_base" and a.img == 384:
             # DRAM bytes per launch of the same kernel family in the same step, from the committed ncu pass (cannot be read
             # live): profiles/r02_ncu_launch_list_b16_step.txt, 638 gemm_tc* launches, cold-cache and serialised under ncu
-            roof["traffic"] = 89.45e6 + 20.83e6
+            roof["traffic"] = 89.18e6 + 20.97e6
             roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's 638 GEMM launches)"
             roof["traffic_source"] = "profiles/r02_ncu_launch_list_b16_step.txt"
             roof["algorithmic_bytes_per_launch"] = w["byte_alg"] / n if w.get("byte_alg") else None
