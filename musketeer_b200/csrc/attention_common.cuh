@@ -10,6 +10,8 @@ typedef OfaAttnGrads AttnGrads;
 // csrc/attention_small.cu: bf16 backward for T <= 16 query rows without relative-position bias (short-target cross-attention)
 bool ofa_attn_bwd_small_applicable(const AttnArgs* a, const AttnGrads* g);
 int ofa_attn_bwd_small_launch(const AttnArgs* a, const AttnGrads* g, cudaStream_t st);
+bool ofa_attn_fwd_small_applicable(const AttnArgs* a);
+int ofa_attn_fwd_small_launch(const AttnArgs* a, cudaStream_t st);
 
 #ifdef __CUDACC__
 // index into the per-head image LUT for position ids (1-based, row-major over an ibs x ibs grid):

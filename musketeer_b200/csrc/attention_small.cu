@@ -271,6 +271,167 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
   }
 }
 
+// ---- forward for the same shapes: S = Q' K'^T per 16-key tile, online softmax per warp (running max / sum of the two query rows
+// a thread holds), O += P V with P re-used as the A fragment; the four warps' (max, sum, O) are merged through shared memory.
+__global__ void __launch_bounds__(kT) attn_fwd_smallq_kernel(AttnArgs a) {
+  using T = __nv_bfloat16;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned char* ring = dsm;
+  unsigned char* Qs = dsm + 4 * 2 * STAGE;
+  float* ow = reinterpret_cast<float*>(ring);                  // [4][16][64] partial outputs, over the drained rings
+  __shared__ float mw[4][TQ], lw[4][TQ];
+  static_assert(4 * TQ * HD * 4 <= 4 * 2 * STAGE, "partial outputs must fit the rings");
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int Tn = a.T, S = a.S;
+  pdl_sync();
+  for (int e = t; e < TQ * 16; e += kT) {
+    const int i = e / 16, c = e % 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < Tn) {
+      const T* src = c < 8 ? (const T*)a.q + (size_t)b * a.bsq + (size_t)i * a.ldq + h * HD + c * 8
+                           : (const T*)a.pq + (size_t)b * a.bspq + (size_t)i * a.ldpq + h * HD + (c - 8) * 8;
+      v = *reinterpret_cast<const uint4*>(src);
+    }
+    *reinterpret_cast<uint4*>(Qs + i * KP + c * 16) = v;
+  }
+  const unsigned char* Kb = reinterpret_cast<const unsigned char*>((const T*)a.k + (size_t)b * a.bsk + h * HD);
+  const unsigned char* PKb = reinterpret_cast<const unsigned char*>((const T*)a.pk + (size_t)b * a.bspk + h * HD);
+  const unsigned char* Vb = reinterpret_cast<const unsigned char*>((const T*)a.v + (size_t)b * a.bsv + h * HD);
+  const size_t ldk = (size_t)a.ldk * 2, ldpk = (size_t)a.ldpk * 2, ldv = (size_t)a.ldv * 2;
+  const unsigned char* kpm = a.kpm ? a.kpm + (size_t)b * S : nullptr;
+  const int ntile = (S + TKW - 1) / TKW;
+  const int nw = ntile > warp ? (ntile - warp + 3) / 4 : 0;
+  const uint32_t wring = smem_u32(ring) + warp * 2 * STAGE;
+  auto issue = [&](int n) {
+    if (n < nw) {
+      const int j0 = (warp + 4 * n) * TKW;
+      const uint32_t st = wring + (n & 1) * STAGE;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int c = lane + 32 * i, key = c / 24, part = c % 24;
+        const int j = j0 + key, ok = j < S ? 16 : 0;
+        const size_t jj = ok ? j : 0;
+        if (part < 8) cp16(st + key * KP + part * 16, Kb + jj * ldk + part * 16, ok);
+        else if (part < 16) cp16(st + key * KP + part * 16, PKb + jj * ldpk + (part - 8) * 16, ok);
+        else cp16(st + TKW * KP + key * VP + (part - 16) * 16, Vb + jj * ldv + (part - 16) * 16, ok);
+      }
+    }
+    cp_commit();
+  };
+  issue(0);
+  const int fr = lane >> 2, fc = (lane & 3) * 2;
+  const AttnBias& bz = a.bias;
+  const float* lut = bz.tok_lut ? bz.tok_lut + (size_t)h * (2 * bz.tok_max - 1) + bz.tok_max - 1 : nullptr;
+  __syncthreads();
+  const int rowA = (lane & 7) + ((lane >> 3) & 1) * 8, colA = (lane >> 4) * 16;
+  const int rowB = (lane & 7) + (lane >> 4) * 8, colB = ((lane >> 3) & 1) * 16;
+  const uint32_t qs_u = smem_u32(Qs);
+  uint32_t qa[8][4];                                           // A fragments of Q' (16 queries x 128 dims), loaded once
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) ldsm4(qa[ks], qs_u + rowA * KP + colA + ks * 32);
+  float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+  for (int n = 0; n < nw; ++n) {
+    __syncwarp();
+    issue(n + 1);
+    cp_wait<1>();
+    __syncwarp();
+    const uint32_t kt = wring + (n & 1) * STAGE, vt = kt + TKW * KP;
+    const int j0 = (warp + 4 * n) * TKW;
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // block nb: keys nb * 8 + fc + (e & 1); rows fr + 8 * (e >> 1)
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t bf[4];
+      ldsm4(bf, kt + rowB * KP + colB + ks * 32);
+      mma16816(s[0], qa[ks], bf[0], bf[1]);
+      mma16816(s[1], qa[ks], bf[2], bf[3]);
+    }
+    float tmx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = fr + 8 * (e >> 1), kj = j0 + nb * 8 + fc + (e & 1);
+        const bool ok = kj < S && !(kpm && kpm[kj]) && !(a.causal && kj > qi);
+        float x = s[nb][e];
+        if (lut && qi >= bz.q_text_off && kj >= bz.k_text_off && ok) x += lut[(qi - bz.q_text_off) - (kj - bz.k_text_off)];
+        x = ok ? x * kLog2e : -CUDART_INF_F;
+        s[nb][e] = x;
+        tmx[e >> 1] = fmaxf(tmx[e >> 1], x);
+      }
+    float alpha[2], mu[2];
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      tmx[r2] = fmaxf(tmx[r2], __shfl_xor_sync(0xffffffffu, tmx[r2], 1));
+      tmx[r2] = fmaxf(tmx[r2], __shfl_xor_sync(0xffffffffu, tmx[r2], 2));
+      const float mn = fmaxf(m[r2], tmx[r2]);
+      mu[r2] = mn == -CUDART_INF_F ? 0.f : mn;
+      alpha[r2] = ex2f(m[r2] - mu[r2]);
+      m[r2] = mn;
+    }
+    float ps[2] = {0.f, 0.f};
+    uint32_t pa[4];
+    {
+      float p[2][4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p[nb][e] = ex2f(s[nb][e] - mu[e >> 1]);
+          ps[e >> 1] += p[nb][e];
+        }
+      pa[0] = pk2(p[0][0], p[0][1]); pa[1] = pk2(p[0][2], p[0][3]); pa[2] = pk2(p[1][0], p[1][1]); pa[3] = pk2(p[1][2], p[1][3]);
+    }
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      ps[r2] += __shfl_xor_sync(0xffffffffu, ps[r2], 1);
+      ps[r2] += __shfl_xor_sync(0xffffffffu, ps[r2], 2);
+      l[r2] = l[r2] * alpha[r2] + ps[r2];
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { o[nb][0] *= alpha[0]; o[nb][1] *= alpha[0]; o[nb][2] *= alpha[1]; o[nb][3] *= alpha[1]; }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bf[4];
+      ldsm4t(bf, vt + rowA * VP + colA + np * 32);
+      mma16816(o[2 * np], pa, bf[0], bf[1]);
+      mma16816(o[2 * np + 1], pa, bf[2], bf[3]);
+    }
+  }
+  cp_wait<0>();
+  __syncthreads();
+  if ((lane & 3) == 0) { mw[warp][fr] = m[0]; mw[warp][fr + 8] = m[1]; lw[warp][fr] = l[0]; lw[warp][fr + 8] = l[1]; }
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    float* r0 = ow + ((size_t)warp * TQ + fr) * HD + nb * 8 + fc;
+    float* r1 = ow + ((size_t)warp * TQ + fr + 8) * HD + nb * 8 + fc;
+    r0[0] = o[nb][0]; r0[1] = o[nb][1];
+    r1[0] = o[nb][2]; r1[1] = o[nb][3];
+  }
+  __syncthreads();
+  const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  for (int e = t; e < TQ * (HD / 2); e += kT) {
+    const int i = e / (HD / 2), d2 = (e % (HD / 2)) * 2;
+    if (i >= Tn) continue;
+    const float M = fmaxf(fmaxf(mw[0][i], mw[1][i]), fmaxf(mw[2][i], mw[3][i]));
+    const float Mu = M == -CUDART_INF_F ? 0.f : M;
+    float L = 0.f, v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float f = ex2f(mw[w][i] - Mu);
+      L = fmaf(lw[w][i], f, L);
+      v0 = fmaf(ow[((size_t)w * TQ + i) * HD + d2], f, v0);
+      v1 = fmaf(ow[((size_t)w * TQ + i) * HD + d2 + 1], f, v1);
+    }
+    const float inv = L > 0.f ? cs / L : 0.f;
+    *reinterpret_cast<uint32_t*>((T*)a.o + (size_t)b * a.bso + (size_t)i * a.ldo + h * HD + d2) = pk2(v0 * inv, v1 * inv);
+    if (d2 == 0) a.lse[((size_t)b * a.H + h) * Tn + i] = (Mu + log2f(L)) * 0.6931471805599453f;
+  }
+}
+
 }  // namespace
 
 bool ofa_attn_bwd_small_applicable(const AttnArgs* a, const AttnGrads* g) {
@@ -291,5 +452,26 @@ int ofa_attn_bwd_small_launch(const AttnArgs* a, const AttnGrads* g, cudaStream_
   }
   OFA_CUDA(ofa_launch_pdl(attn_bwd_smallq_kernel, dim3(a->H, a->B), kT, smem, st, *a, *g));
   OFA_LAUNCH_CHECK("attn_bwd_smallq_kernel");
+  return 0;
+}
+
+bool ofa_attn_fwd_small_applicable(const AttnArgs* a) {
+  const bool lut_ok = a->bias.tok_lut == nullptr || (a->S <= TQ && a->bias.q_text_off == a->bias.k_text_off);
+  // short key sequences only (decoder self-attention): over S = 835 source positions the warp-specialised tcgen05 forward
+  // (72.8 us at B = 48, T = 12) beats this one-tile-in-flight stream (79.7 us); over S = T = 12 it is 27.8 -> 14.7 us
+  return a->T <= TQ && a->S <= 4 * TKW && lut_ok && a->bias.img_lut == nullptr && a->q_pos_off == 0 &&
+         a->ldq % 8 == 0 && a->ldpq % 8 == 0 && a->ldk % 8 == 0 && a->ldpk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 2 == 0 &&
+         a->bsq % 8 == 0 && a->bspq % 8 == 0 && a->bsk % 8 == 0 && a->bspk % 8 == 0 && a->bsv % 8 == 0 && a->bso % 2 == 0;
+}
+
+int ofa_attn_fwd_small_launch(const AttnArgs* a, cudaStream_t st) {
+  const int smem = 4 * 2 * STAGE + TQ * KP;
+  static bool configured = false;
+  if (!configured) {
+    OFA_CUDA(cudaFuncSetAttribute(attn_fwd_smallq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  OFA_CUDA(ofa_launch_pdl(attn_fwd_smallq_kernel, dim3(a->H, a->B), kT, smem, st, *a));
+  OFA_LAUNCH_CHECK("attn_fwd_smallq_kernel");
   return 0;
 }

@@ -1313,6 +1313,8 @@ extern "C" int ofa_attn_fwd_tc(const AttnArgs* a, void* stream) {
                 a->ldo % 8 == 0 && a->bso % 8 == 0,
             "ofa_attn_fwd_tc: strides must be multiples of 8 elements");
   OFA_CHECK(a->bias.ibs < 256, "ofa_attn_fwd_tc: image bucket size must be < 256");
+  if (g_attn_bwd_small && ofa_attn_fwd_small_applicable(a))      // short targets: csrc/attention_small.cu
+    return ofa_attn_fwd_small_launch(a, (cudaStream_t)stream);
   CUtensorMap tq, tpq, tk, tpk, tv;
   if (int e = make_qkv_tmap(&tq, a->q, a->T, a->H, a->B, a->ldq, a->bsq, BQ)) return e;
   if (int e = make_qkv_tmap(&tpq, a->pq, a->T, a->H, a->B, a->ldpq, a->bspq, BQ)) return e;

@@ -43,11 +43,11 @@ def test_sass_is_blackwell_native(lib_path):
     assert "LDTM" in sass         # tcgen05.ld
     # no legacy mma.sync on the GEMM-shaped paths: the warp-level MMA users are the two attention kernels whose query side
     # cannot fill a 128-row tcgen05 tile -- the single-token decode attention (G <= 8 query rows per sentence, csrc/decode.cu)
-    # and the backward for T <= 16 target rows (csrc/attention_small.cu); both are streams over K / V
+    # and the forward / backward for T <= 16 target rows (csrc/attention_small.cu); all are streams over K / V
     for fn in sass.split("Function :")[1:]:
         if "HMMA." in fn.replace("UTCHMMA", ""):
             name = fn.split("\n", 1)[0]
-            assert "attn_decode_mma_kernel" in name or "attn_bwd_smallq_kernel" in name, name
+            assert any(k in name for k in ("attn_decode_mma_kernel", "attn_bwd_smallq_kernel", "attn_fwd_smallq_kernel")), name
     assert "UBLKCP" in sass       # 1-D bulk copies (the LayerNorm backward's shared-memory row ring)
     assert "FFMA2" in sass        # packed fp32x2 arithmetic (wide-row LayerNorm / GELU forward)
     # relative-position table gradients of the attention backward: native int32 shared atomics, no float CAS loops
