@@ -292,6 +292,10 @@ typedef struct {
   float* dS;                        /* SIMT path: [B,H,T,S] fp32 workspace */
   float dq_scale;                   /* tcgen05 path: dq (not dpq) is multiplied by this on its way out (the softmax scaling
                                        of a q that came unscaled-in-weights from a fused q|k|v projection); 0 means 1 */
+  int acc_pos;                      /* tcgen05 / short-target paths: 1 = dpq and dpk are ADDED to the buffers' contents (the
+                                       position projections pos_q / pos_k are shared by every layer of a stack,
+                                       unify_transformer.py:906-912: the layers' backward passes sum into one buffer instead of
+                                       autograd adding six tensors); 0 = overwritten */
 } OfaAttnGrads;
 
 int ofa_attn_fwd_simt(const OfaAttnArgs* args, int dtype, void* stream);

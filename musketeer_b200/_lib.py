@@ -29,7 +29,7 @@ class OfaAttnGrads(C.Structure):
     _fields_ = [("dout", c_p), ("dq", c_p), ("dpq", c_p), ("dk", c_p), ("dpk", c_p), ("dv", c_p),
                 ("lddq", c_ll), ("lddpq", c_ll), ("lddk", c_ll), ("lddpk", c_ll), ("lddv", c_ll),
                 ("bsdq", c_ll), ("bsdpq", c_ll), ("bsdk", c_ll), ("bsdpk", c_ll), ("bsdv", c_ll),
-                ("dtok_lut", c_p), ("dimg_lut", c_p), ("delta", c_p), ("P", c_p), ("dS", c_p), ("dq_scale", c_f)]
+                ("dtok_lut", c_p), ("dimg_lut", c_p), ("delta", c_p), ("P", c_p), ("dS", c_p), ("dq_scale", c_f), ("acc_pos", c_i)]
 
 
 class OfaDecodeArgs(C.Structure):

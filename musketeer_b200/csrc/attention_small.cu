@@ -224,9 +224,21 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
       T* base = half ? (T*)g.dpk + (size_t)b * g.bsdpk + h * HD + fc : (T*)g.dk + (size_t)b * g.bsdk + h * HD + fc;
       const long long ldd = half ? g.lddpk : g.lddk;
 #pragma unroll
+      const bool addto = half && g.acc_pos;                 // pos_k gradient summed over the layers that share pos_k
+#pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
-        if (jr0 < S) *reinterpret_cast<uint32_t*>(base + (size_t)jr0 * ldd + nb * 8) = pk2(dk[nb][0], dk[nb][1]);
-        if (jr1 < S) *reinterpret_cast<uint32_t*>(base + (size_t)jr1 * ldd + nb * 8) = pk2(dk[nb][2], dk[nb][3]);
+        if (jr0 < S) {
+          uint32_t* d = reinterpret_cast<uint32_t*>(base + (size_t)jr0 * ldd + nb * 8);
+          float2 o2 = make_float2(0.f, 0.f);
+          if (addto) o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d));
+          *d = pk2(dk[nb][0] + o2.x, dk[nb][1] + o2.y);
+        }
+        if (jr1 < S) {
+          uint32_t* d = reinterpret_cast<uint32_t*>(base + (size_t)jr1 * ldd + nb * 8);
+          float2 o2 = make_float2(0.f, 0.f);
+          if (addto) o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d));
+          *d = pk2(dk[nb][2] + o2.x, dk[nb][3] + o2.y);
+        }
       }
     }
     // ---- dQ' += dS K'   [16 queries x 128]: A = dS from the scratch (transposed load), B = K' tile (transposed load) ---------------
@@ -266,8 +278,11 @@ __global__ void __launch_bounds__(kT) attn_bwd_smallq_kernel(AttnArgs a, AttnGra
     for (int w = 0; w < 4; ++w) { v0 += red[((size_t)w * TQ + i) * 128 + d2]; v1 += red[((size_t)w * TQ + i) * 128 + d2 + 1]; }
     if (d2 < HD)
       *reinterpret_cast<uint32_t*>((T*)g.dq + (size_t)b * g.bsdq + (size_t)i * g.lddq + h * HD + d2) = pk2(v0 * qsc, v1 * qsc);
-    else
-      *reinterpret_cast<uint32_t*>((T*)g.dpq + (size_t)b * g.bsdpq + (size_t)i * g.lddpq + h * HD + d2 - HD) = pk2(v0, v1);
+    else {
+      uint32_t* d = reinterpret_cast<uint32_t*>((T*)g.dpq + (size_t)b * g.bsdpq + (size_t)i * g.lddpq + h * HD + d2 - HD);
+      if (g.acc_pos) { const float2 o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d)); v0 += o2.x; v1 += o2.y; }
+      *d = pk2(v0, v1);
+    }
   }
 }
 

@@ -1158,13 +1158,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j < a.S) {
         __nv_bfloat16* dst = qd < 2 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD + qd * 32
                                     : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD + (qd - 2) * 32;
+        const bool addto = g.acc_pos && qd >= 2;         // pos_k part: summed over the layers that share pos_k
 #pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4)
-          reinterpret_cast<uint4*>(dst)[v4] = make_uint4(
-              pack_bf16(__uint_as_float(rk[8 * v4]), __uint_as_float(rk[8 * v4 + 1])),
-              pack_bf16(__uint_as_float(rk[8 * v4 + 2]), __uint_as_float(rk[8 * v4 + 3])),
-              pack_bf16(__uint_as_float(rk[8 * v4 + 4]), __uint_as_float(rk[8 * v4 + 5])),
-              pack_bf16(__uint_as_float(rk[8 * v4 + 6]), __uint_as_float(rk[8 * v4 + 7])));
+        for (int v4 = 0; v4 < 4; ++v4) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(rk[8 * v4 + e]);
+          if (addto) {
+            const uint4 old = reinterpret_cast<const uint4*>(dst)[v4];
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 of = __bfloat1622float2(oh[e]); f[2 * e] += of.x; f[2 * e + 1] += of.y; }
+          }
+          reinterpret_cast<uint4*>(dst)[v4] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                                         pack_bf16(f[6], f[7]));
+        }
       }
     }
     {
@@ -1186,7 +1194,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint4 z = make_uint4(0, 0, 0, 0);
     __nv_bfloat16* d0 = qd < 2 ? (__nv_bfloat16*)g.dk + (size_t)b * g.bsdk + (size_t)j * g.lddk + h * HD + qd * 32
                                : (__nv_bfloat16*)g.dpk + (size_t)b * g.bsdpk + (size_t)j * g.lddpk + h * HD + (qd - 2) * 32;
-    for (int v4 = 0; v4 < 4; ++v4) reinterpret_cast<uint4*>(d0)[v4] = z;
+    if (!(g.acc_pos && qd >= 2))          // (an accumulated pos_k gradient receives nothing from this tile)
+      for (int v4 = 0; v4 < 4; ++v4) reinterpret_cast<uint4*>(d0)[v4] = z;
     __nv_bfloat16* d1 = (__nv_bfloat16*)g.dv + (size_t)b * g.bsdv + (size_t)j * g.lddv + h * HD + qd * 16;
     for (int v4 = 0; v4 < 2; ++v4) reinterpret_cast<uint4*>(d1)[v4] = z;
   }
@@ -1253,7 +1262,7 @@ __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16
 // dq_acc [B,T,H,128] fp32 -> dq, dpq [B,T,H*64] bf16
 __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
                                            __nv_bfloat16* __restrict__ dpq, long long lddq, long long bsdq,
-                                           long long lddpq, long long bsdpq, int B, int T, int H, float dq_scale) {
+                                           long long lddpq, long long bsdpq, int B, int T, int H, float dq_scale, int acc_pos) {
   pdl_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 elements
   const long long total = (long long)B * T * H * 16;
@@ -1261,6 +1270,12 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
   const int c8 = idx % 16, h = (idx / 16) % H, i = (idx / (16 * H)) % T, b = idx / (16LL * H * T);
   float4 x = reinterpret_cast<const float4*>(acc)[idx * 2], y = reinterpret_cast<const float4*>(acc)[idx * 2 + 1];
   if (c8 < 8) { x.x *= dq_scale; x.y *= dq_scale; x.z *= dq_scale; x.w *= dq_scale; y.x *= dq_scale; y.y *= dq_scale; y.z *= dq_scale; y.w *= dq_scale; }
+  if (c8 >= 8 && acc_pos) {               // pos_q part: summed over the layers that share pos_q
+    const uint4 old = *reinterpret_cast<const uint4*>(dpq + (size_t)b * bsdpq + (size_t)i * lddpq + h * HD + (c8 - 8) * 8);
+    const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+    const float2 o0 = __bfloat1622float2(oh[0]), o1 = __bfloat1622float2(oh[1]), o2 = __bfloat1622float2(oh[2]), o3 = __bfloat1622float2(oh[3]);
+    x.x += o0.x; x.y += o0.y; x.z += o1.x; x.w += o1.y; y.x += o2.x; y.y += o2.y; y.z += o3.x; y.w += o3.y;
+  }
   const uint4 pk = make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
   if (c8 < 8) *reinterpret_cast<uint4*>(dq + (size_t)b * bsdq + (size_t)i * lddq + h * HD + c8 * 8) = pk;
   else *reinterpret_cast<uint4*>(dpq + (size_t)b * bsdpq + (size_t)i * lddpq + h * HD + (c8 - 8) * 8) = pk;
@@ -1392,7 +1407,7 @@ extern "C" int ofa_attn_bwd_tc(const AttnArgs* a, const AttnGrads* g, float* dq_
   dim3 grid((a->S + BK2 - 1) / BK2, a->H, a->B);
   OFA_CUDA(ofa_launch_pdl(attn_bwd_tc_kernel, grid, kBwdThreads, smem, st, tq, tpq, tk, tpk, tv, tdo, tdq, *a, *g));
   OFA_LAUNCH_CHECK("attn_bwd_tc_kernel");
-  OFA_CUDA(ofa_launch_pdl(attn_bwd_dq_convert_kernel, (unsigned)((nrow * 16 + 255) / 256), 256, 0, st, dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H, g->dq_scale == 0.f ? 1.f : g->dq_scale));
+  OFA_CUDA(ofa_launch_pdl(attn_bwd_dq_convert_kernel, (unsigned)((nrow * 16 + 255) / 256), 256, 0, st, dq_acc, (__nv_bfloat16*)g->dq, (__nv_bfloat16*)g->dpq, g->lddq, g->bsdq, g->lddpq, g->bsdpq, a->B, a->T, a->H, g->dq_scale == 0.f ? 1.f : g->dq_scale, g->acc_pos));
   OFA_LAUNCH_CHECK("attn_bwd_dq_convert_kernel");
   return 0;
 }

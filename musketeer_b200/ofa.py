@@ -455,6 +455,8 @@ class TransformerEncoder(FairseqEncoder):
                         "q_pid": pid.int().contiguous() if pid is not None else None,
                         "k_pid": None, "n_img_q": P, "n_img_k": P}}
         cfg["bias"]["k_pid"] = cfg["bias"]["q_pid"]
+        if torch.is_grad_enabled() and pq.requires_grad and pk.requires_grad:
+            cfg["pos_sink"] = {"n": len(self.layers)}        # the layers' d pos_q / d pos_k are summed in the kernels (ops._Attention)
         rel1d = self.rel_bucket_1d()
         states = []
         for i, layer in enumerate(self.layers):
@@ -681,6 +683,9 @@ class TransformerDecoder(FairseqIncrementalDecoder):
             self_cfg = {"causal": True, "kpm": self_kpm, "q_pos_off": t0,
                         "bias": {"q_text_off": 0, "k_text_off": 0}}
             cross_cfg = {"causal": False, "kpm": enc_pad.contiguous().view(torch.uint8), "bias": {}, "fused_kv": True}
+            if torch.is_grad_enabled() and spq.requires_grad and spk.requires_grad and cpq.requires_grad and cpk.requires_grad:
+                self_cfg["pos_sink"] = {"n": len(self.layers)}
+                cross_cfg["pos_sink"] = {"n": len(self.layers)}
             if enc.shape[0] != B:           # un-replicated encoder output: rows b*G .. b*G + G - 1 belong to sentence b
                 if B % enc.shape[0] != 0:
                     raise ValueError("decoder rows (%d) must be a multiple of the encoder batch (%d)" % (B, enc.shape[0]))

@@ -1029,8 +1029,24 @@ class _Attention(torch.autograd.Function):
         a = _fill_args(q, pq, k, pk, v, o, lse, H, cfg["causal"], cfg.get("q_pos_off", 0), cfg.get("kpm"), hs,
                        ctx.bias, q.dtype == torch.bfloat16)
         g = OfaAttnGrads()
-        dpq = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
-        dpk = torch.empty(B, S, D, dtype=q.dtype, device=q.device)
+        # pos_q / pos_k are shared by every layer of a stack: with a `pos_sink` (one dict per forward pass of the stack, see
+        # ofa.py) the layers' backward kernels sum their contributions into ONE pair of buffers (first call writes, later calls
+        # add) and only the last call hands them to autograd -- instead of autograd adding 2 x (layers - 1) full tensors
+        sink = cfg.get("pos_sink") if (q.dtype == torch.bfloat16 and cfg.get("use_tc", True)) else None
+        last_of_stack = True
+        if sink is not None:
+            if sink.get("dpq") is None:
+                sink["dpq"] = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+                sink["dpk"] = torch.empty(B, S, D, dtype=q.dtype, device=q.device)
+                sink["seen"] = 0
+            else:
+                g.acc_pos = 1
+            dpq, dpk = sink["dpq"], sink["dpk"]
+            sink["seen"] += 1
+            last_of_stack = sink["seen"] == sink["n"]
+        else:
+            dpq = torch.empty(B, T, D, dtype=q.dtype, device=q.device)
+            dpk = torch.empty(B, S, D, dtype=q.dtype, device=q.device)
         dq_scale = float(cfg.get("dq_scale", 1.0))
         if cfg.get("fused_kv"):
             # cross-attention fed by the fused k|v projection: dk and dv side by side
@@ -1070,6 +1086,8 @@ class _Attention(torch.autograd.Function):
         dhs = None
         if head_scale is not None:
             dhs = (delta.sum(dim=(0, 2)) / hs).to(head_scale.dtype)
+        if not last_of_stack:
+            return dq, None, dk, None, dv, dtok, dimg, dhs, None
         return dq, dpq, dk, dpk, dv, dtok, dimg, dhs, None
 
 
