@@ -99,7 +99,10 @@ class _GradAccumulator:
                 self.arena_buf = torch.zeros(sum((p.numel() + 63) // 64 * 64 for p in self.params.values()),
                                              dtype=param.dtype, device=param.device)
                 self.buf, self.buf_used = {}, 0
-            if dense and not _capturing():
+            if dense and not _capturing() and k not in self.region:
+                # (a parameter that already owns an fp32 region -- the tied embedding: output-projection wgrad GEMM + embedding
+                # scatter-add -- gets its bf16 buffer OUTSIDE the arena: `finish` folds it into the fp32 region's cast, so it
+                # would only add 91 MB of already-merged bytes to the data-parallel all-reduce of the arena)
                 n = param.numel()       # same memory format as the parameter (channels_last conv weights)
                 b = self.arena_buf[self.buf_used:self.buf_used + n].as_strided(param.shape, param.stride())
                 self.buf_used += (n + 63) // 64 * 64
