@@ -167,6 +167,10 @@ typedef struct OfaBeamArgs {
   int range_lo, range_hi, range_post;  /* constraint range: keep tokens < 4 and [lo, hi); lo < 0: none; post: after the softmax */
   const int* trie_ptr; const int* trie_tok; const int* node; int trie_post;
   const long long* tokens; long long ldtok; int step; int ngram;   /* n-gram blocking over tokens[r][0..step]; ngram 0: off */
+  /* forced prefix (models/sequence_generator.py:600-613): prefix_tok[r] != pad keeps the log-prob of that token and sets every
+   * other entry of the row to *prefix_fill (device scalar: min over the rows of the prefix log-probs - 1) or, prefix_fill NULL,
+   * to -inf (the generator has a constraint trie).  NULL: none.  node[r] == -2: row not constrained by the trie (:867-868).   */
+  const long long* prefix_tok; const float* prefix_fill;
   float* row_val; int* row_idx;
   float* cand_scores; long long* cand_index;   /* [R/beam][K] */
 } OfaBeamArgs;

@@ -50,6 +50,7 @@ class OfaBeamArgs(C.Structure):
                 ("range_lo", c_i), ("range_hi", c_i), ("range_post", c_i),
                 ("trie_ptr", c_p), ("trie_tok", c_p), ("node", c_p), ("trie_post", c_i),
                 ("tokens", c_p), ("ldtok", c_ll), ("step", c_i), ("ngram", c_i),
+                ("prefix_tok", c_p), ("prefix_fill", c_p),
                 ("row_val", c_p), ("row_idx", c_p), ("cand_scores", c_p), ("cand_index", c_p)]
 
 

@@ -28,6 +28,7 @@ struct OfaBeamArgs {   // mirrored by musketeer_b200/_lib.py and include/ofa_b20
   int range_lo, range_hi, range_post;
   const int* trie_ptr; const int* trie_tok; const int* node; int trie_post;
   const long long* tokens; long long ldtok; int step; int ngram;
+  const long long* prefix_tok; const float* prefix_fill;
   float* row_val; int* row_idx;
   float* cand_scores; long long* cand_index;
 };
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   __shared__ float tmax[kT];
   __shared__ float lv[CAP];
   __shared__ int li[CAP];
-  __shared__ int cnt;
+  __shared__ int cnt, pfound;
   const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int V = a.V;
   float* out_v = a.row_val + (size_t)r * K;
@@ -86,21 +87,40 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   int eos_only = 0;
   if (a.node) {
     const int nd = a.node[r];
-    if (nd < 0) eos_only = 1, nal = 1;
+    if (nd == -2) nal = -1;                         // a row still inside its forced prefix: every token allowed (:867-868)
+    else if (nd < 0) eos_only = 1, nal = 1;
     else { al = a.trie_tok + a.trie_ptr[nd]; nal = a.trie_ptr[nd + 1] - a.trie_ptr[nd]; }
   }
+  // forced prefix token of this row (:604-613): every other entry takes the fill value
+  const long long ptok = a.prefix_tok ? a.prefix_tok[r] : (long long)a.pad;
+  const bool has_prefix = ptok != (long long)a.pad;
+  const float pfill = has_prefix && a.prefix_fill ? *a.prefix_fill : -CUDART_INF_F;
+  // the V - 1 filler entries of such a row tie: torch.topk takes them in no defined order; the highest indices go first here
+  // (the lowest ones would put eos among the candidates of every prefix step)
+  const bool flip = has_prefix && pfill > -CUDART_INF_F;
   const bool pre_list = nal >= 0 && !a.trie_post;
   const bool pre_range = a.range_lo >= 0 && !a.range_post;
   // ---- ban mask -----------------------------------------------------------------------------------------------------
-  const bool post_list = nal >= 0 && a.trie_post;
+  // (a forced-prefix row overrides every entry but its prefix token AFTER the post-softmax masks, :372-380 after :878-889: only
+  // the prefix token itself can still be masked by them)
+  const bool post_list = nal >= 0 && a.trie_post && !has_prefix;
+  if (t == 0) pfound = 0;
   for (int w = t; w < nw; w += kT) ban[w] = post_list ? 0xffffffffu : 0u;
   __syncthreads();
   if (post_list) {
     for (int e = t; e < nal; e += kT) { const int tok = eos_only ? a.eos : al[e]; atomicAnd(&ban[tok >> 5], ~(1u << (tok & 31))); }
     __syncthreads();
+  } else if (has_prefix && nal >= 0 && a.trie_post) {
+    for (int e = t; e < nal; e += kT) if ((eos_only ? a.eos : al[e]) == (int)ptok) pfound = 1;
+    __syncthreads();
+    if (t == 0 && !pfound) atomicOr(&ban[(int)ptok >> 5], 1u << ((int)ptok & 31));
   }
   if (a.range_lo >= 0 && a.range_post) {
-    for (int v = 4 + t; v < V; v += kT) if (v < a.range_lo || v >= a.range_hi) atomicOr(&ban[v >> 5], 1u << (v & 31));
+    if (has_prefix) {
+      if (t == 0 && ptok >= 4 && (ptok < a.range_lo || ptok >= a.range_hi)) atomicOr(&ban[(int)ptok >> 5], 1u << ((int)ptok & 31));
+    } else {
+      for (int v = 4 + t; v < V; v += kT) if (v < a.range_lo || v >= a.range_hi) atomicOr(&ban[v >> 5], 1u << (v & 31));
+    }
   }
   if (t == 0) {
     atomicOr(&ban[a.pad >> 5], 1u << (a.pad & 31));
@@ -172,6 +192,7 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   const float prev = a.prev_scores ? a.prev_scores[r] : 0.f;
   auto final_val = [&](int v, float s) {
     float lp = s - lse;
+    if (has_prefix && v != (int)ptok) lp = pfill;
     if (lp != lp) lp = -CUDART_INF_F;                                   // sequence_generator.py:386
     if ((ban[v >> 5] >> (v & 31)) & 1u) lp = -CUDART_INF_F;
     if (v == a.unk) lp -= a.unk_penalty;
@@ -183,7 +204,7 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   // K-th best (K different entries reach it).  B2: the few entries >= tau go to a list in shared memory, warp 0 sorts out the
   // K best of the list.  (Keeping K sorted entries per thread, the general path below, costs a K-deep insertion chain per
   // element for the whole warp: 260 us per launch at 320 rows x 59457 against 25 us for this path.)
-  bool general = a.force_eos || pre_list;
+  bool general = a.force_eos || pre_list || flip;
   if (!general) {
     float tm = -CUDART_INF_F;
     for_each([&](int v, float s) { tm = fmaxf(tm, final_val(v, s)); });
@@ -242,7 +263,7 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   float val[K]; int idx[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { val[k] = -CUDART_INF_F; idx[k] = 0x7fffffff; }
-  auto consider = [&](int v, float s) { insert<K>(val, idx, final_val(v, s), v); };
+  auto consider = [&](int v, float s) { insert<K>(val, idx, final_val(v, s), flip ? V - 1 - v : v); };
   if (a.force_eos && !pre_list) {
     if (t == 0 && in_domain(a.eos)) consider(a.eos, ldf(x, a.eos) * inv_t);
   } else {
@@ -285,7 +306,7 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
         const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
         if (better(ov, oi, bv, bi) || (ov == bv && oi == bi && ol < bl)) { bv = ov; bi = oi; bl = ol; }
       }
-      if (lane == 0) { out_v[k] = bv; out_i[k] = bi; }
+      if (lane == 0) { out_v[k] = bv; out_i[k] = (flip && bi != 0x7fffffff) ? V - 1 - bi : bi; }
       if (lane == bl) ++pos;
     }
   }

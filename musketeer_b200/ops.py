@@ -1171,9 +1171,10 @@ def page_write(pool, table, k, v, layer, page, off, page_len):
 
 def beam_topk(logits, beam, K, temperature=1.0, prev_scores=None, step0=False, eos=2, pad=1, unk=3, unk_penalty=0.0,
               block_eos=False, force_eos=False, eos_one=False, crange=None, range_post=False, trie=None, node=None,
-              trie_post=False, tokens=None, step=0, ngram=0, ws=None):
+              trie_post=False, tokens=None, step=0, ngram=0, ws=None, prefix_tok=None, prefix_fill=None):
     """Fused tail of a beam-search step (csrc/beam.cu): logits [R, V] -> (cand_scores [R/beam, K] fp32, cand_index int64).
-    trie = (ptr, tok, child) int32 CSR tensors; node int32 [R]; tokens int64 [R, L] for n-gram blocking."""
+    trie = (ptr, tok, child) int32 CSR tensors; node int32 [R] (-2: row not constrained); tokens int64 [R, L] for n-gram
+    blocking; prefix_tok int64 [R] (pad: none) + prefix_fill fp32 [1] or None (-inf): forced prefix tokens."""
     from ._lib import OfaBeamArgs
     _need_cuda(logits)
     R, V = logits.shape
@@ -1192,6 +1193,12 @@ def beam_topk(logits, beam, K, temperature=1.0, prev_scores=None, step0=False, e
         a.trie_ptr, a.trie_tok, a.node, a.trie_post = trie[0].data_ptr(), trie[1].data_ptr(), node.data_ptr(), int(trie_post)
     if ngram > 0:
         a.tokens, a.ldtok, a.step, a.ngram = tokens.data_ptr(), tokens.stride(0), int(step), int(ngram)
+    if prefix_tok is not None:
+        assert prefix_tok.dtype == torch.long and prefix_tok.numel() == R and prefix_tok.is_contiguous()
+        a.prefix_tok = prefix_tok.data_ptr()
+        if prefix_fill is not None:
+            assert prefix_fill.dtype == torch.float32 and prefix_fill.numel() == 1
+            a.prefix_fill = prefix_fill.data_ptr()
     kw = _lib.load().ofa_beam_topk_width(int(K))
     if ws is None or ws[0].numel() < R * kw:
         ws = (torch.empty(R * kw, dtype=torch.float32, device=logits.device),

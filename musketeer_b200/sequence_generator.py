@@ -5,10 +5,12 @@ positional_scores).  Per step, on the kernels of libofa_b200.so: one token per b
 KV cache, cross-attention K / V projected once per sentence, csrc/decode.cu), then ONE fused launch pair for the tail --
 temperature, constraint range / constraint trie, fp32 log-softmax, min-len / max-len / pad / unk masks, n-gram blocking,
 previous beam scores and the top 2*beam selection (csrc/beam.cu).  The constraint trie (utils/trie.py; built by the tasks,
-tasks/mm_tasks/vqa_gen.py:158-167) is flattened to CSR once and walked on the device; the beam bookkeeping stays in torch
-index ops on the device.
+tasks/mm_tasks/vqa_gen.py:158-167) is flattened to CSR once and walked on the device; a step in which no hypothesis ends
+does its beam bookkeeping in one launch (beam_advance_kernel), a step with finished hypotheses follows the reference's own
+sequence of index operations.  Forced prefixes (`prefix_tokens`, the decoder prompt of the VQA beam-search evaluation:
+tasks/mm_tasks/vqa_gen.py:311, utils/eval_utils.py:152) are applied inside the same fused tail.
 
-Out of scope here (raises): prefix tokens, image-code / box generation, LM fusion, ensembles > 1."""
+Out of scope here (raises): lexical constraints, image-code / box generation, LM fusion, ensembles > 1."""
 import math
 from typing import Dict, List, Optional
 
@@ -88,8 +90,10 @@ class SequenceGenerator(torch.nn.Module):
         return self._generate(models, sample, **kwargs)
 
     def _generate(self, models, sample, prefix_tokens=None, constraints=None, bos_token=None):
-        if prefix_tokens is not None or constraints is not None:
-            raise NotImplementedError("prefix tokens / lexical constraints are outside the hot-path scope")
+        if constraints is not None:
+            raise NotImplementedError("lexical constraints are outside the hot-path scope")
+        if prefix_tokens is not None and self.constraint_start is not None:
+            raise NotImplementedError("prefix tokens together with a constraint range (no caller in the reference)")
         model = models[0] if isinstance(models, (list, tuple)) else models
         net_input = sample["net_input"]
         src_tokens = net_input["src_tokens"]
@@ -169,35 +173,69 @@ class SequenceGenerator(torch.nn.Module):
             trie = self._trie_csr
             root = torch.zeros(bsz * beam, dtype=torch.int32, device=dev)
             node = ops.trie_advance(trie, root, None, torch.zeros(bsz * beam, dtype=torch.long, device=dev))
+        plen = node0 = None
+        if prefix_tokens is not None:
+            prefix_tokens = prefix_tokens.to(dev)
+            if node is not None and not self.zero_shot:
+                # the pre-softmax trie mask skips each sentence's forced prefix and walks [bos] + tokens[prefix_len + 1:]
+                # (:862-868): -2 = unconstrained while the row is inside its prefix, the bos node at its end
+                plen = prefix_tokens.ne(self.pad).sum(1).repeat_interleave(beam).to(torch.int32)
+                node0 = node
+                node = torch.where(plen > 0, torch.full_like(node0, -2), node0)
         if self.constraint_start is not None and trie is not None:
             raise ValueError("constraint_trie and constraint_range are mutually exclusive (sequence_generator.py:858,871)")
         for step in range(max_len + 1):
             if reorder_state is not None and batch_idxs is not None:
                 corr = batch_idxs - torch.arange(batch_idxs.numel(), device=dev)
                 reorder_state.view(-1, beam).add_(corr.unsqueeze(-1) * beam)
+            # forced prefix tokens of this step (possibly of different lengths: pad = none for that sentence; :372-380)
+            ptoks = None
+            if prefix_tokens is not None and step < prefix_tokens.size(1) and step < max_len:
+                ptoks = prefix_tokens[:, step].unsqueeze(-1).repeat(1, beam).view(-1).contiguous()
             graphable = (static is not None and step >= 1 and bsz == bsz0 and batch_idxs is None and static["calls"] >= 2
                          and (tokens is static["tokens"][0] or tokens is static["tokens"][1]))
             # the whole step as one graph (decoder + fused tail + bookkeeping) when every buffer it touches is persistent
-            whole = graphable and fused and step < max_len and node is None and scores is static["scores"][
+            # (a prefix step keeps its tail eager -- the tail may synchronise -- but its decoder pass is captured like any other:
+            # a captured step reads the cache state its predecessor left in the graph pool)
+            whole = graphable and fused and step < max_len and node is None and ptoks is None and scores is static["scores"][
                 0 if tokens is static["tokens"][0] else 1]
             if whole and not (cands_to_ignore is static["ignore"][0] or cands_to_ignore is static["ignore"][1]):
                 par = 0 if tokens is static["tokens"][0] else 1
                 static["ignore"][par].copy_(cands_to_ignore)       # (left behind by a finalisation step)
                 cands_to_ignore, alt_ignore = static["ignore"][par], static["ignore"][1 - par]
 
-            def tail(logits, ws, tokens=tokens, scores=scores, step=step):
+            def tail(logits, ws, tokens=tokens, scores=scores, step=step, ptoks=ptoks):
                 """fused tail: temperature, constraints, log-softmax, masks, n-gram blocking, + beam scores, top 2*beam.
                 `ws`: workspace of an earlier eager call or None -- a captured step must NOT hold a pointer to an eager tensor
                 that dies with this generate call, so the graph path allocates its own inside the capture."""
                 lg = logits[:, -1, :]
+                pfill = None
+                if ptoks is not None:
+                    if bool(ptoks.eq(self.eos).any()):
+                        # a prefix that ends here: every beam of that sentence continues from the first one (:614-634); the
+                        # log-probs follow from the replicated logits row (same prefix token for every beam of a sentence)
+                        eb = ptoks.eq(self.eos).view(-1, beam)[:, 0]
+                        first = tokens.view(bsz, beam, -1)[eb][:, 0, 1:step + 1]
+                        assert bool((first == prefix_tokens[eb][:, :step]).all())
+                        for t_ in (tokens, scores, lg):
+                            v_ = t_.view(bsz, beam, -1)
+                            v_[eb] = v_[eb][:, :1, :].expand(-1, beam, -1).clone()
+                    if trie is None:
+                        # every other token of a prefixed row: min over ALL rows of the prefix log-probs - 1 (:607-608)
+                        lt = lg if self.temperature == 1.0 else lg.float() / self.temperature
+                        R_ = lt.shape[0]
+                        plp = ops.trie_score(lt, torch.arange(R_ + 1, dtype=torch.int32, device=dev),
+                                             torch.full((R_,), -1, dtype=torch.int32, device=dev), ptoks, None, -1)
+                        pfill = (plp.min() - 1).reshape(1)
                 prev = scores.view(bsz, beam, -1)[:, :, step - 1].reshape(-1).contiguous() if step > 0 else None
                 return ops.beam_topk(
                     lg, beam, min(cand_size, beam * V - 1), self.temperature, prev, step0=(step == 0), eos=self.eos, pad=self.pad,
-                    unk=self.unk, unk_penalty=self.unk_penalty, block_eos=step < self.min_len, force_eos=step >= max_len,
+                    unk=self.unk, unk_penalty=self.unk_penalty, block_eos=step < self.min_len and ptoks is None,
+                    force_eos=step >= max_len,
                     eos_one=self.ignore_eos,
                     crange=(self.constraint_start, self.constraint_end) if self.constraint_start is not None else None,
                     range_post=self.zero_shot, trie=trie, node=node, trie_post=self.zero_shot, tokens=tokens, step=step,
-                    ngram=self.no_repeat_ngram_size, ws=ws)
+                    ngram=self.no_repeat_ngram_size, ws=ws, prefix_tok=ptoks, prefix_fill=pfill)
 
             def advance(cand_scores, idx, act):
                 ops.beam_advance(cand_scores, idx, cands_to_ignore.contiguous(), tokens, scores, alt_tokens, alt_scores, alt_ignore,
@@ -236,7 +274,7 @@ class SequenceGenerator(torch.nn.Module):
                     scores, alt_scores = alt_scores, scores
                     cands_to_ignore, alt_ignore = alt_ignore, cands_to_ignore
                     if node is not None:
-                        node = ops.trie_advance(trie, node, act, tokens[:, step + 1])
+                        node = self._next_nodes(trie, node, act, tokens[:, step + 1], plen, node0, step + 1)
                     reorder_state, batch_idxs = act, None
                     continue
             cand_beams = idx // V
@@ -268,6 +306,11 @@ class SequenceGenerator(torch.nn.Module):
                 cands_to_ignore = cands_to_ignore[batch_idxs]
                 if node is not None:
                     node = node.view(bsz, beam)[batch_idxs].reshape(-1).contiguous()
+                if plen is not None:
+                    plen = plen.view(bsz, beam)[batch_idxs].reshape(-1).contiguous()
+                    node0 = node0[:new_bsz * beam]
+                if prefix_tokens is not None:
+                    prefix_tokens = prefix_tokens[batch_idxs]                     # :507-508
                 scores = scores.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
                 tokens = tokens.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
                 bsz = new_bsz
@@ -284,7 +327,7 @@ class SequenceGenerator(torch.nn.Module):
                 scores[:, :step] = torch.index_select(scores[:, :step], 0, active_bbsz_idx)
             scores.view(bsz, beam, -1)[:, :, step] = torch.gather(cand_scores, 1, active_hypos)
             if node is not None:       # trie node of every surviving hypothesis: its parent's node advanced by the chosen token
-                node = ops.trie_advance(trie, node, active_bbsz_idx.contiguous(), tokens[:, step + 1])
+                node = self._next_nodes(trie, node, active_bbsz_idx.contiguous(), tokens[:, step + 1], plen, node0, step + 1)
             reorder_state = active_bbsz_idx
         for s in range(len(finalized)):
             # (:589-597 reads every score back with .item(): one device synchronisation per hypothesis; the host copies taken
@@ -323,6 +366,15 @@ class SequenceGenerator(torch.nn.Module):
         if tail is not None:
             return g["logits"], g["cand"][0], g["cand"][1]
         return g["logits"]
+
+    @staticmethod
+    def _next_nodes(trie, node, parent, tok, plen, node0, n_tokens):
+        """Trie node of every surviving hypothesis: its parent's node advanced by the chosen token; with forced prefixes the
+        walk starts at the end of the sentence's prefix (n_tokens = generated tokens so far, bos excluded; :862-868)."""
+        nxt = ops.trie_advance(trie, node, parent, tok)
+        if plen is not None:
+            nxt = torch.where(plen > n_tokens, torch.full_like(nxt, -2), torch.where(plen == n_tokens, node0, nxt))
+        return nxt
 
     _STATE_KEYS = ("tcur", "ppar", "len", "sent_row", "rows", "reordered_at")
 

@@ -116,6 +116,16 @@ GEN_CASES = {
                                      batch=dict(bsz=2, src_len=9, tgt_len=2, img=64, seed=29, vocab=4099, n_pad=0),
                                      gen=dict(beam_size=3, max_len_a=0, max_len_b=6, min_len=2, constraint_range="100,900",
                                               zero_shot=True, temperature=0.8, unk_penalty=0.5)),
+    # forced decoder prefixes (prefix_tokens: the VQA beam-search evaluation passes the decoder prompt, tasks/mm_tasks/vqa_gen.py:311,
+    # utils/eval_utils.py:152) of different lengths, with the answer trie walked from the end of each prefix
+    # (models/sequence_generator.py:862-868) and without a trie (:607-608: every other token at min(prefix lprobs) - 1)
+    "gen_micro_prefix_trie": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                                  batch=dict(bsz=4, src_len=9, tgt_len=2, img=64, seed=36, vocab=4099, n_pad=1),
+                                  gen=dict(beam_size=5, max_len_a=0, max_len_b=10, min_len=1), trie=dict(n=40, max_len=4, seed=5),
+                                  prefix=dict(lens=[2, 0, 3, 1], seed=11)),
+    "gen_micro_prefix": dict(arch="ofa_micro", cfg=dict(vocab_size=4099), emb_std=0.05, w_std=0.3,
+                             batch=dict(bsz=3, src_len=9, tgt_len=2, img=64, seed=37, vocab=4099, n_pad=0),
+                             gen=dict(beam_size=4, max_len_a=0, max_len_b=8, min_len=1), prefix=dict(lens=[3, 1, 2], seed=12)),
     # BASELINE.json configs[4] scaled to ofa_tiny / batch 2 (the oracle finishes in seconds)
     "gen_tiny": dict(arch="ofa_tiny", cfg={}, emb_std=0.1,
                      batch=dict(bsz=2, src_len=8, tgt_len=2, img=256, seed=22, n_pad=0),
@@ -266,14 +276,16 @@ def run_gen_case(name, case):
         for w in synth.trie_words(vocab=cfg.vocab_size, **case["trie"]):
             ref_trie.insert(w)
             our_trie.insert(w)
+    prefix = synth.prefix_tokens(vocab=cfg.vocab_size, **case["prefix"]) if "prefix" in case else None
     gen = rh.build_generator(model, task, constraint_trie=ref_trie, **case["gen"])
-    hyp = gen.generate([model], copy.deepcopy(sample))
+    hyp = gen.generate([model], copy.deepcopy(sample), **({"prefix_tokens": prefix.clone()} if prefix is not None else {}))
     g = dict(case["gen"])
     ours = oo.generate(sd, cfg, sample["net_input"], beam=g["beam_size"], max_len_a=g["max_len_a"],
                        max_len_b=g["max_len_b"], min_len=g["min_len"],
                        no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0), temperature=g.get("temperature", 1.0),
                        unk_penalty=g.get("unk_penalty", 0.0), constraint_trie=our_trie,
-                       constraint_range=g.get("constraint_range"), zero_shot=g.get("zero_shot", False))
+                       constraint_range=g.get("constraint_range"), zero_shot=g.get("zero_shot", False),
+                       prefix_tokens=prefix.clone() if prefix is not None else None)
     fx = {"recipe": json.dumps(case), "tokens": [], "scores": [], "pos_scores": []}
     for s in range(len(hyp)):
         assert len(hyp[s]) == len(ours[s])

@@ -434,9 +434,16 @@ class Trie:
         return list(cur.keys())
 
 
+def _first_beam(t, mask, beam):
+    # replicate_first_beam :636-639
+    t = t.view(-1, beam, t.size(-1))
+    t[mask] = t[mask][:, :1, :]
+    return t.view(-1, t.size(-1))
+
+
 def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, len_penalty=1.0,
              temperature=1.0, no_repeat_ngram_size=0, unk_penalty=0.0, constraint_trie=None, constraint_range=None,
-             zero_shot=False):
+             zero_shot=False, prefix_tokens=None):
     cstart = cend = None
     if constraint_range is not None:                                                            # :82-86
         cstart, cend = (int(v) for v in constraint_range.split(","))
@@ -477,7 +484,12 @@ def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, l
         if constraint_trie is not None:                                                         # :857-868, :878-885
             allowed = torch.zeros(lg.shape, dtype=torch.bool)
             for r, pref in enumerate(tokens[:, :step + 1].tolist()):
-                allowed[r, constraint_trie.get_next_layer([0] + pref[1:])] = True
+                # (the pre-softmax mask skips the forced prefix of the sentence, :862-868; the zero-shot one does not, :881-884)
+                plen = int(prefix_tokens[r // beam].ne(PAD).sum()) if prefix_tokens is not None and not zero_shot else 0
+                if len(pref) > plen:
+                    allowed[r, constraint_trie.get_next_layer([0] + pref[plen + 1:])] = True
+                else:
+                    allowed[r] = True
         if not zero_shot:
             if allowed is not None:
                 lg = lg.masked_fill(~allowed, -math.inf)
@@ -491,7 +503,19 @@ def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, l
             if cstart is not None:                                                              # :886-889
                 lprobs[:, 4:cstart] = -math.inf
                 lprobs[:, cend:] = -math.inf
-        if step < min_len:
+        if prefix_tokens is not None and step < prefix_tokens.size(1) and step < max_len:       # :373-380, :600-634
+            ptoks = prefix_tokens[:, step].unsqueeze(-1).repeat(1, beam).view(-1)
+            plp = lprobs.gather(-1, ptoks.unsqueeze(-1))
+            pmask = ptoks.ne(PAD)
+            lprobs[pmask] = (torch.min(plp) - 1) if constraint_trie is None else -math.inf
+            lprobs[pmask] = lprobs[pmask].scatter(-1, ptoks[pmask].unsqueeze(-1), plp[pmask])
+            emask = ptoks.eq(EOS)
+            if emask.any():           # a prefix that ends here: every beam of the sentence continues from the first one
+                eb = emask.view(-1, beam)[:, 0]
+                first = tokens[emask].view(-1, beam, tokens.size(-1))[:, 0, 1:step + 1]
+                assert (first == prefix_tokens[eb][:, :step]).all()
+                tokens, scores, lprobs = (_first_beam(t, eb, beam) for t in (tokens, scores, lprobs))
+        elif step < min_len:
             lprobs[:, EOS] = -math.inf                                                          # :381-383
         lprobs[lprobs != lprobs] = -math.inf
         lprobs[:, PAD] = -math.inf                                                              # :387
@@ -536,6 +560,8 @@ def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, l
             cand_scores = cand_scores[batch_idxs]
             cand_indices = cand_indices[batch_idxs]
             cands_to_ignore = cands_to_ignore[batch_idxs]
+            if prefix_tokens is not None:
+                prefix_tokens = prefix_tokens[batch_idxs]                                       # :507-508
             scores = scores.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
             tokens = tokens.view(bsz, -1)[batch_idxs].view(new_bsz * beam, -1)
             bsz = new_bsz

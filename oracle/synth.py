@@ -327,6 +327,17 @@ def trie_words(n, max_len, seed, vocab=VOCAB, alphabet=12):
     return words
 
 
+def prefix_tokens(lens, seed, vocab=VOCAB):
+    """Forced decoder prefixes as data/mm_data/vqa_gen_dataset.py:228-231 collates them (the decoder prompt without its bos,
+    right-padded with pad): one row per sentence, lens[i] random tokens (0 = no prefix for that sentence)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7000 + seed)
+    out = torch.full((len(lens), max(max(lens), 1)), PAD, dtype=torch.long)
+    for i, n in enumerate(lens):
+        out[i, :n] = torch.randint(4, min(50265, vocab), (n,), generator=g)
+    return out
+
+
 def candidate_answers(n, max_len, seed, vocab=VOCAB, alphabet=12):
     """n DISTINCT answers (token tensors without bos / eos) over a small alphabet, as ans2label_dict's keys would encode."""
     seen, out = set(), []

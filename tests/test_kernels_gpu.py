@@ -775,6 +775,60 @@ def test_beam_topk_matches_torch(dtype, step, ngram, crange, post):
         assert bool((ci[b, 1:n][tie] > ci[b, :n - 1][tie]).all())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("step,fill,post", [(0, False, False), (2, False, False), (2, True, False), (0, True, False),
+                                            (3, False, True)])
+def test_beam_topk_forced_prefix(dtype, step, fill, post):
+    """Forced prefix tokens inside the fused tail (models/sequence_generator.py:372-380,600-613): a prefixed row keeps the
+    log-prob of its prefix token, every other entry takes -inf (generator with a trie) or min(prefix log-probs) - 1; rows whose
+    prefix is pad are untouched; the min-length rule is off in such a step; a post-softmax range mask (zero-shot) can only
+    still remove the prefix token itself."""
+    ops = _ops()
+    bsz, beam, V = 4, 3, 4099
+    g = torch.Generator(device="cpu").manual_seed(100 + step)
+    logits = (torch.randn(bsz * beam, V, generator=g) * 3).cuda().to(dtype)
+    if step == 0:
+        logits = logits.view(bsz, beam, V)[:, :1].expand(-1, beam, -1).reshape(bsz * beam, V).contiguous()
+    prev = torch.randn(bsz * beam, generator=g).cuda()
+    ptok = torch.tensor([77, 1, 2500, 2], dtype=torch.long).repeat_interleave(beam).cuda()      # sentence 1: no prefix; 3: eos
+    crange = (50, 400) if post else None
+    lp = torch.log_softmax(logits.float(), -1)
+    if post:
+        lp[:, 4:crange[0]] = -math.inf
+        lp[:, crange[1]:] = -math.inf
+    plp = lp.gather(-1, ptok.unsqueeze(-1))
+    pm = ptok.ne(1)
+    pfill = (plp.min() - 1).reshape(1) if fill else None
+    lp[pm] = (plp.min() - 1) if fill else -math.inf
+    lp[pm] = lp[pm].scatter(-1, ptok[pm].unsqueeze(-1), plp[pm])
+    lp[:, 1] = -math.inf
+    cs, ci, _ = ops.beam_topk(logits, beam, 2 * beam, 1.0, prev if step > 0 else None, step0=(step == 0), eos=2, pad=1, unk=3,
+                              block_eos=False, crange=crange, range_post=post, prefix_tok=ptok, prefix_fill=pfill)
+    l3 = lp.view(bsz, beam, V)
+    l3 = l3[:, ::beam, :].contiguous() if step == 0 else l3 + prev.view(bsz, beam, 1)
+    flat = l3.view(bsz, -1)
+    rs, ri = torch.topk(flat, k=2 * beam)
+    finite = torch.isfinite(rs)
+    tol = 1e-5 if dtype == torch.float32 else 1e-4
+    assert torch.equal(torch.isfinite(cs), finite)
+    assert (cs[finite] - rs[finite]).abs().max().item() < tol
+    assert (flat.gather(1, ci)[finite] - rs[finite]).abs().max().item() < tol
+    for b in range(bsz):
+        n = int(finite[b].sum())
+        assert len(set(ci[b, :n].tolist())) == n
+        clear = rs[b, :n] > rs[b, n - 1] + tol
+        assert set(ri[b, :n][clear].tolist()) <= set(ci[b, :n].tolist())
+        if fill and b != 1:
+            # the tying filler entries are taken from the top of the vocabulary: never eos / bos / unk
+            assert all(int(i) % V > 3 or int(i) % V == int(ptok[b * beam]) for i in ci[b, :n].tolist())
+    if not fill and not post:
+        # exactly one finite candidate per live beam row of a prefixed sentence, and it is the prefix token
+        live = 1 if step == 0 else beam
+        for b in (0, 2, 3):
+            assert int(finite[b].sum()) == live
+            assert set(int(i) % V for i in ci[b, :live].tolist()) == {int(ptok[b * beam])}
+
+
 def test_attention_decode_paged_and_bias_hoist():
     """Decode attention (csrc/decode.cu): (a) K / V read through a page table == the same keys stored contiguously; (b) the
     position term written once by a score_out launch and added as bias_in == the fused q.k + pos_q.pos_k launch."""

@@ -160,7 +160,7 @@ def test_state_dict_contract():
 
 @pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny", "gen_micro_varied", "gen_micro_varied_ngram",
                                   "gen_base_b8", "gen_micro_trie", "gen_micro_trie_zeroshot", "gen_micro_range",
-                                  "gen_micro_range_zeroshot"])
+                                  "gen_micro_range_zeroshot", "gen_micro_prefix_trie", "gen_micro_prefix"])
 def test_beam_search_tokens_bit_exact_fp32(name):
     """fp32 mode: beam-search output token ids must equal the reference's bit for bit; scores within 1e-4."""
     from musketeer_b200.sequence_generator import SequenceGenerator
@@ -177,10 +177,12 @@ def test_beam_search_tokens_bit_exact_fp32(name):
         for w in synth.trie_words(vocab=cfg.vocab_size, **case["trie"]):
             gkw["constraint_trie"].insert(w)
     gen = SequenceGenerator([model], task.target_dictionary, **gkw)
+    # forced decoder prefixes of different lengths (models/sequence_generator.py:372-380,600-634,862-868)
+    pkw = {"prefix_tokens": synth.prefix_tokens(vocab=cfg.vocab_size, **case["prefix"]).cuda()} if "prefix" in case else {}
     # call 1 runs every decoder step eagerly, call 2 captures the steps as CUDA graphs (and replays them), call 3 replays:
     # all three must reproduce the reference's tokens
     for call in range(3):
-        hyp = gen.generate([model], sample)
+        hyp = gen.generate([model], sample, **pkw)
         assert len(hyp) == len(fx["tokens"])
         for s in range(len(hyp)):
             assert len(hyp[s]) == len(fx["tokens"][s])

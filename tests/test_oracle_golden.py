@@ -62,7 +62,7 @@ def test_train_case(name):
 
 
 @pytest.mark.parametrize("name", ["gen_micro", "gen_micro_ngram", "gen_tiny", "gen_micro_trie", "gen_micro_trie_zeroshot",
-                                  "gen_micro_range", "gen_micro_range_zeroshot"])
+                                  "gen_micro_range", "gen_micro_range_zeroshot", "gen_micro_prefix_trie", "gen_micro_prefix"])
 def test_beam_search(name):
     fx = load_golden(name)
     case = fx["case"]
@@ -79,7 +79,8 @@ def test_beam_search(name):
                       max_len_b=g["max_len_b"], min_len=g["min_len"],
                       no_repeat_ngram_size=g.get("no_repeat_ngram_size", 0), temperature=g.get("temperature", 1.0),
                       unk_penalty=g.get("unk_penalty", 0.0), constraint_trie=trie,
-                      constraint_range=g.get("constraint_range"), zero_shot=g.get("zero_shot", False))
+                      constraint_range=g.get("constraint_range"), zero_shot=g.get("zero_shot", False),
+                      prefix_tokens=synth.prefix_tokens(vocab=cfg.vocab_size, **case["prefix"]) if "prefix" in case else None)
     assert len(hyp) == len(fx["tokens"])
     for s in range(len(hyp)):
         assert len(hyp[s]) == len(fx["tokens"][s])
