@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   __shared__ float lv[CAP];
   __shared__ int li[CAP];
   __shared__ int cnt, pfound;
+  __shared__ int redi[kT / 32];
   const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int V = a.V;
   float* out_v = a.row_val + (size_t)r * K;
@@ -163,12 +164,58 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
     }
     for (int v = nv * VE + t; v < V; v += kT) if (in_domain(v)) fn(v, ldf(x, v) * inv_t);
   };
+  // whole-vocabulary rows on 16-byte groups: fn(first index, values / temperature, count); entries outside a constraint range
+  // arrive as -inf (they are outside the softmax domain and never candidates), so a group costs no per-element branch
+  const bool grouped = vec_ok && !pre_list;
+  auto for_groups = [&](auto&& fn) {
+    const int nv = V / VE;
+    for (int i = t; i < nv; i += kT) {
+      const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+      float f[VE];
+      if constexpr (sizeof(T) == 2) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 p2 = __bfloat1622float2(h2[e]); f[2 * e] = p2.x; f[2 * e + 1] = p2.y; }
+      } else {
+        f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+      }
+#pragma unroll
+      for (int e = 0; e < VE; ++e) f[e] *= inv_t;
+      if (pre_range) {
+#pragma unroll
+        for (int e = 0; e < VE; ++e) if (!in_domain(i * VE + e)) f[e] = -CUDART_INF_F;
+      }
+      fn(i * VE, f, VE);
+    }
+    for (int v = nv * VE + t; v < V; v += kT) {
+      float f[VE];
+      f[0] = in_domain(v) ? ldf(x, v) * inv_t : -CUDART_INF_F;
+      fn(v, f, 1);
+    }
+  };
   float mx = -CUDART_INF_F, sum = 0.f;
-  for_each([&](int, float s) {
-    if (s > mx) { sum = sum * __expf(mx - s) + 1.f; mx = s; }          // (exp(-inf) = 0 on the first entry)
-    else if (s > -CUDART_INF_F) sum += __expf(s - mx);
-    else if (s != s) sum = s;                                           // a NaN logit poisons the row like F.log_softmax: all -inf below
-  });
+  if (grouped) {
+    for_groups([&](int, const float (&f)[VE], int n) {
+      float m = f[0];
+#pragma unroll
+      for (int e = 1; e < VE; ++e) if (e < n) m = fmaxf(m, f[e]);      // (fmaxf drops NaNs: they poison the sum below)
+      if (m > mx) { sum *= __expf(mx - m); mx = m; }                    // (exp(-inf) = 0 on the first finite group)
+      if (mx > -CUDART_INF_F) {
+#pragma unroll
+        for (int e = 0; e < VE; ++e) if (e < n) sum += __expf(f[e] - mx);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VE; ++e) if (e < n && f[e] != f[e]) sum = f[e];
+      }
+    });
+  } else {
+    for_each([&](int, float s) {
+      if (s > mx) { sum = sum * __expf(mx - s) + 1.f; mx = s; }          // (exp(-inf) = 0 on the first entry)
+      else if (s > -CUDART_INF_F) sum += __expf(s - mx);
+      else if (s != s) sum = s;                                           // a NaN logit poisons the row like F.log_softmax: all -inf below
+    });
+  }
+  const float tmx = mx;            // this thread's largest logit / temperature (threshold of the fast candidate filter below)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
@@ -205,7 +252,66 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
   // K best of the list.  (Keeping K sorted entries per thread, the general path below, costs a K-deep insertion chain per
   // element for the whole warp: 260 us per launch at 320 rows x 59457 against 25 us for this path.)
   bool general = a.force_eos || pre_list || flip;
-  if (!general) {
+  // Fast filter (no post-softmax list / range, no forced prefix): log-prob + beam score is monotonic in the logit except for the
+  // nb banned entries (pad, eos below min-len, n-gram bans) and unk (penalty), so the (K + nb)-th largest of the thread maxima
+  // of PASS A bounds the row's K-th best candidate -- no second max pass, and the filter pass compares raw logits per 16-byte
+  // group (3 instructions per element instead of the full candidate value).
+  bool fast = !general && grouped && !has_prefix && !(nal >= 0 && a.trie_post) && !(a.range_lo >= 0 && a.range_post);
+  if (fast) {
+    int nb = 0;
+    for (int w = t; w < nw; w += kT) nb += __popc(ban[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    if (lane == 0) redi[warp] = nb;
+    tmax[t] = tmx;
+    if (t == 0) cnt = 0;
+    __syncthreads();
+    nb = a.unk_penalty != 0.f ? 1 : 0;
+    for (int w = 0; w < kT / 32; ++w) nb += redi[w];
+    const int rank = K + nb;
+    if (rank > 64) {
+      fast = false;                        // (many banned entries: the exact two-pass filter below)
+    } else {
+      if (warp == 0) {
+        float tau = -CUDART_INF_F;
+        for (int k = 0; k < rank; ++k) {
+          float bv = -CUDART_INF_F; int be = lane;
+          for (int e = lane; e < kT; e += 32) if (tmax[e] > bv) { bv = tmax[e]; be = e; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+            if (ov > bv || (ov == bv && oe < be)) { bv = ov; be = oe; }
+          }
+          tau = bv;
+          if ((be & 31) == lane) tmax[be] = -CUDART_INF_F;
+          __syncwarp();
+        }
+        if (lane == 0) bcast = tau;
+      }
+      __syncthreads();
+      const float tau = bcast;
+      const int unk_group = a.unk_penalty != 0.f ? a.unk / VE * VE : -1;
+      for_groups([&](int v0, const float (&f)[VE], int n) {
+        float m = f[0];
+#pragma unroll
+        for (int e = 1; e < VE; ++e) if (e < n) m = fmaxf(m, f[e]);
+        if (!(m >= tau) && v0 != unk_group) return;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          if (e < n && (f[e] >= tau || v0 + e == a.unk)) {
+            const float fv = final_val(v0 + e, f[e]);
+            if (fv > -CUDART_INF_F) {
+              const int pos = atomicAdd(&cnt, 1);
+              if (pos < CAP) { lv[pos] = fv; li[pos] = v0 + e; }
+            }
+          }
+        }
+      });
+      __syncthreads();
+    }
+  }
+  if (!general && !fast) {
     float tm = -CUDART_INF_F;
     for_each([&](int v, float s) { tm = fmaxf(tm, final_val(v, s)); });
     tmax[t] = tm;
@@ -238,6 +344,8 @@ __global__ void __launch_bounds__(kT) beam_row_kernel(OfaBeamArgs a) {
       }
     });
     __syncthreads();
+  }
+  if (!general) {
     const int n = cnt;
     if (n > CAP) {
       general = true;                      // (a row of equal logits, say): the exact general path
