@@ -139,6 +139,8 @@ typedef struct OfaDecodeArgs {
   const int* page_table; int page_len, max_pages; long long page_stride;
 } OfaDecodeArgs;
 int ofa_attn_decode(const OfaDecodeArgs* args, int dtype, void* stream);
+/* A/B switch: 0 = the (group, head) decode kernel also for short self-attention problems; returns the previous setting */
+int ofa_attn_decode_set_short(int on);
 int ofa_cache_gather(const void* src, void* dst, const long long* order, int rows, int L, int D, long long row_stride,
                      long long plane_stride, int planes, int dtype, void* stream);
 /* paged self-attention cache of the incremental decoder: pool [slot][plane = 2*layer + (k|v)][page_len][D].  A beam reorder

@@ -40,6 +40,7 @@ namespace {
 constexpr int HD = 64;
 constexpr int kT = 128;
 constexpr int GMAX = 8;
+int g_decode_short = 1;     // A/B switch (ofa_attn_decode_set_short): 0 = the (group, head) kernel for every shape
 
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
@@ -211,6 +212,125 @@ __global__ void __launch_bounds__(kT) attn_decode_kernel(OfaDecodeArgs a) {
       oo = fmaf(wo[w][g][d], f, oo);
     }
     reinterpret_cast<T*>(a.o)[(size_t)(row0 + g) * a.ldo + h * HD + d] = (T)((ll > 0.f ? oo / ll : 0.f) * cs);
+  }
+}
+
+// ---- short-key decode attention (incremental self-attention: S <= 32 keys, one query per row) ------------------------------
+// One WARP = one (row, head), four per CTA, no block-level synchronisation: lane j owns key j (its whole 64-dim K row and
+// position-key row: 128-byte lines fetched in two batches of four 16-byte chunks), the softmax is three warp reductions, and
+// for P.V every lane owns two output dims and walks the <= 32 value rows (one coalesced 128-byte line per key, all requested
+// before the arithmetic).  The (group, head) kernel above spends ~20 us on 3840 such problems (CTA-wide merges through
+// shared memory, two dependent tiles per warp): here the whole launch is one wave of independent warps.
+template <typename T>
+__global__ void __launch_bounds__(kT, sizeof(T) == 2 ? 7 : 4) attn_decode_short_kernel(OfaDecodeArgs a) {     // (960 CTAs at 320 rows x 12 heads: one wave)
+  pdl_sync();
+  __shared__ __align__(16) float qs[kT / 32][2][HD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (kT / 32) + warp;
+  if (item >= a.R * a.H) return;
+  const int r = item / a.H, h = item % a.H;
+  const int S = a.S;
+  const int krow = a.kv_row ? a.kv_row[r] : r;
+  const int prow = a.pk_row ? a.pk_row[r] : krow;
+  const bool has_pk = a.pk != nullptr && a.pq != nullptr;
+  {
+    const float2 q2 = load2<T>(reinterpret_cast<const T*>(a.q) + (size_t)r * a.ldq + h * HD + lane * 2);
+    qs[warp][0][lane * 2] = q2.x; qs[warp][0][lane * 2 + 1] = q2.y;
+    if (has_pk) {
+      const float2 p2 = load2<T>(reinterpret_cast<const T*>(a.pq) + (size_t)r * a.ldpq + h * HD + lane * 2);
+      qs[warp][1][lane * 2] = p2.x; qs[warp][1][lane * 2 + 1] = p2.y;
+    }
+  }
+  __syncwarp();
+  const int* ptab = a.page_table ? a.page_table + (size_t)krow * a.max_pages : nullptr;
+  const T* Vb = reinterpret_cast<const T*>(a.v) + h * HD + lane * 2;
+  auto v_off = [&](int ju) {
+    return ptab ? (size_t)ptab[ju / a.page_len] * a.page_stride + (size_t)(ju % a.page_len) * a.ldv
+                : (size_t)krow * a.bsv + (size_t)ju * a.ldv;
+  };
+  // value rows of the first VH keys: requested before anything else (they depend on neither q nor the scores), so the launch
+  // pays one DRAM round trip for K and V together
+  constexpr int VH = sizeof(T) == 2 ? 16 : 0;
+  float2 vh[VH > 0 ? VH : 1];
+#pragma unroll
+  for (int u = 0; u < VH; ++u) {
+    vh[u] = make_float2(0.f, 0.f);
+    if (u < S) vh[u] = load2<T>(Vb + v_off(u));
+  }
+  const int j = lane;
+  const bool valid = j < S;
+  const bool masked = !valid || (a.kpm && a.kpm[(size_t)krow * a.kpm_stride + j]);
+  float s = 0.f;
+  if (!masked) {
+    const size_t off = ptab ? (size_t)ptab[j / a.page_len] * a.page_stride + (size_t)(j % a.page_len) * a.ldk
+                            : (size_t)krow * a.bsk + (size_t)j * a.ldk;
+    const T* kp = reinterpret_cast<const T*>(a.k) + h * HD + off;
+    const T* pp = has_pk ? reinterpret_cast<const T*>(a.pk) + (size_t)prow * a.bspk + h * HD + (size_t)j * a.ldpk : nullptr;
+#pragma unroll
+    for (int half = 0; half < 4; ++half) {      // (chunks of one 128-byte line: only the first batch waits for DRAM)
+      float kv[2][8], pv[2][8];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        load8<T>(kp + (half * 2 + c) * 8, kv[c]);
+        if (has_pk) load8<T>(pp + (half * 2 + c) * 8, pv[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 q0 = *reinterpret_cast<const float4*>(&qs[warp][0][(half * 2 + c) * 8]);
+        const float4 q1 = *reinterpret_cast<const float4*>(&qs[warp][0][(half * 2 + c) * 8 + 4]);
+        s = fmaf(q0.x, kv[c][0], s); s = fmaf(q0.y, kv[c][1], s); s = fmaf(q0.z, kv[c][2], s); s = fmaf(q0.w, kv[c][3], s);
+        s = fmaf(q1.x, kv[c][4], s); s = fmaf(q1.y, kv[c][5], s); s = fmaf(q1.z, kv[c][6], s); s = fmaf(q1.w, kv[c][7], s);
+        if (has_pk) {
+          const float4 p0 = *reinterpret_cast<const float4*>(&qs[warp][1][(half * 2 + c) * 8]);
+          const float4 p1 = *reinterpret_cast<const float4*>(&qs[warp][1][(half * 2 + c) * 8 + 4]);
+          s = fmaf(p0.x, pv[c][0], s); s = fmaf(p0.y, pv[c][1], s); s = fmaf(p0.z, pv[c][2], s); s = fmaf(p0.w, pv[c][3], s);
+          s = fmaf(p1.x, pv[c][4], s); s = fmaf(p1.y, pv[c][5], s); s = fmaf(p1.z, pv[c][6], s); s = fmaf(p1.w, pv[c][7], s);
+        }
+      }
+    }
+    if (a.tok_lut) {
+      const int rel = a.q_pos - j + a.tok_max - 1;
+      if (rel >= 0 && rel < 2 * a.tok_max - 1) s += a.tok_lut[(size_t)h * (2 * a.tok_max - 1) + rel];
+    }
+    if (a.bias_in) s += a.bias_in[((size_t)r * a.H + h) * a.bias_ld + j];
+  } else {
+    s = -CUDART_INF_F;
+  }
+  float mx = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float mu = mx == -CUDART_INF_F ? 0.f : mx;
+  const float p = __expf(s - mu);               // (masked: exp(-inf) = 0)
+  float l = p;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < VH; ++u) {
+    const float pu = __shfl_sync(0xffffffffu, p, u);
+    if (u < S) { o0 = fmaf(pu, vh[u].x, o0); o1 = fmaf(pu, vh[u].y, o1); }
+  }
+  for (int j0 = VH; j0 < S; j0 += 8) {
+    float2 vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ju = j0 + u;
+      vv[u] = make_float2(0.f, 0.f);
+      if (ju < S) vv[u] = load2<T>(Vb + v_off(ju));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float pu = __shfl_sync(0xffffffffu, p, (j0 + u) & 31);
+      if (j0 + u < S) { o0 = fmaf(pu, vv[u].x, o0); o1 = fmaf(pu, vv[u].y, o1); }
+    }
+  }
+  const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  const float inv = l > 0.f ? cs / l : 0.f;
+  T* op = reinterpret_cast<T*>(a.o) + (size_t)r * a.ldo + h * HD + lane * 2;
+  if constexpr (sizeof(T) == 2) {
+    *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  } else {
+    *reinterpret_cast<float2*>(op) = make_float2(o0 * inv, o1 * inv);
   }
 }
 
@@ -587,6 +707,10 @@ int launch_decode_long(const OfaDecodeArgs& a, cudaStream_t st) {
 template <typename T>
 int launch_decode(const OfaDecodeArgs& a, cudaStream_t st) {
   dim3 grid((a.R + a.G - 1) / a.G, a.H);
+  // incremental self-attention (one query per row, a key per lane): independent warps
+  if (g_decode_short && a.G == 1 && a.S <= 32 && !a.score_out && a.v && a.o && (a.ldo % 2) == 0 && (a.ldq % 2) == 0 &&
+      (!a.pq || (a.ldpq % 2) == 0))
+    return (int)ofa_launch_pdl(attn_decode_short_kernel<T>, dim3((a.R * a.H + kT / 32 - 1) / (kT / 32)), kT, 0, st, a);
   // long key ranges without the self-attention extras (position keys, rel-pos LUT, pages): the staged two-pass kernel
   if (a.S >= 64 && !a.pk && !a.tok_lut && !a.page_table) {
     int rc = -1;
@@ -697,6 +821,12 @@ extern "C" int ofa_page_write(void* pool, const int* tab, const void* k, const v
     OFA_CUDA(ofa_launch_pdl(page_write_kernel<float>, dim3(rows), 128, 0, st, (float*)pool, tab, (const float*)k, (const float*)v, ldk, ldv, max_pages, page, off, page_len, D, planes, plane_k));
   OFA_LAUNCH_CHECK("page_write_kernel");
   return 0;
+}
+
+extern "C" int ofa_attn_decode_set_short(int on) {
+  const int old = g_decode_short;
+  g_decode_short = on;
+  return old;
 }
 
 // see include/ofa_b200.h

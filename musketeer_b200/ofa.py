@@ -693,7 +693,17 @@ class TransformerDecoder(FairseqIncrementalDecoder):
         rel1d = self.rel_bucket_1d()
         inner_states = [x.transpose(0, 1)]
         for i, layer in enumerate(self.layers):
-            tok_lut = _tok_lut(self.token_rel_pos_table_list[i].weight, rel1d)
+            w_rel = self.token_rel_pos_table_list[i].weight
+            if incremental and not self.training and not torch.is_grad_enabled():
+                # inference: the gathered table is a function of the weights only -- kept per layer until they change (their
+                # version counter: optimizers and load_state_dict bump it), instead of 3 small launches per layer and step
+                memo = self.__dict__.setdefault("_tok_lut_memo", {})
+                key = (w_rel.data_ptr(), w_rel._version, w_rel.dtype)
+                if memo.get(i, (None, None))[0] != key:
+                    memo[i] = (key, _tok_lut(w_rel, rel1d))
+                tok_lut = memo[i][1]
+            else:
+                tok_lut = _tok_lut(w_rel, rel1d)
 
             def self_kv(attn, h, i=i):
                 q, k, v = attn.qkv_eval(h)

@@ -877,6 +877,48 @@ def test_attention_decode_paged_and_bias_hoist():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("S", [1, 7, 17, 32])
+def test_attention_decode_short_keys(dtype, S):
+    """Incremental self-attention (one query per row, S <= 32 keys: the warp-per-(row, head) kernel of csrc/decode.cu) with the
+    shared position-key row, the token relative-position table, a key-padding mask and the per-head scale: against the fp64
+    restatement and against the (group, head) kernel it replaces for these shapes."""
+    from musketeer_b200 import _lib
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(40 + S)
+    H, D, R, cap, tok_max = 12, 768, 11, 32, 1024          # (the LUT layout of ofa._tok_lut: [H, 2 * 1024 - 1])
+    mk = lambda *s_: (torch.randn(*s_, generator=g) * 0.5).cuda().to(dtype)
+    q, pq = mk(R, 1, D) * 0.3, mk(R, 1, D) * 0.3
+    k, v, spk = mk(R, cap, D), mk(R, cap, D), mk(1, cap, D)
+    zero = torch.zeros(R, dtype=torch.int32).cuda()
+    lut = torch.randn(H, 2 * tok_max - 1, generator=g).cuda()
+    hs = (torch.rand(H, generator=g) + 0.5).cuda()
+    kpm = torch.zeros(R, cap, dtype=torch.uint8).cuda()
+    if S > 2:
+        kpm[3, 1] = 1
+        kpm[5, :S] = 1                       # a fully masked row gives zeros
+    q_pos = S - 1
+    got = ops.attention_decode(q, pq, k, spk, v, S, H, 1, None, zero, kpm, hs, tok_lut=lut, q_pos=q_pos)
+    lib = _lib.load()
+    old = lib.ofa_attn_decode_set_short(0)
+    try:
+        ref = ops.attention_decode(q, pq, k, spk, v, S, H, 1, None, zero, kpm, hs, tok_lut=lut, q_pos=q_pos)
+    finally:
+        lib.ofa_attn_decode_set_short(old)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (got.float() - ref.float()).abs().max().item() < tol
+    f = lambda t_: t_.double().view(-1, cap, H, 64)[:, :S]
+    sc = torch.einsum("rhd,rjhd->rhj", q.double().view(R, H, 64), f(k)) + \
+        torch.einsum("rhd,jhd->rhj", pq.double().view(R, H, 64), f(spk)[0])
+    rel = q_pos - torch.arange(S).cuda() + tok_max - 1
+    sc = sc + lut.double()[:, rel].unsqueeze(0)
+    sc = sc.masked_fill(kpm.bool()[:, None, :S], -math.inf)
+    pr = torch.softmax(sc, -1)
+    pr = torch.where(torch.isnan(pr), torch.zeros_like(pr), pr)
+    o = torch.einsum("rhj,rjhd->rhd", pr, f(v)) * hs.double().view(1, H, 1)
+    assert (got.double().view(R, H, 64) - o).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(3, 64, 64), (2, 17, 23), (1, 384, 384)])
 def test_device_normalise_matches_host_transforms(dtype, shape):
     """uint8 HWC pixels normalised on the device == ToTensor + Normalize on the host (data/mm_data/
