@@ -877,6 +877,40 @@ def test_attention_decode_paged_and_bias_hoist():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("G,S,EB", [(5, 908, 3), (5, 100, 4), (1, 835, 2), (8, 64, 2), (3, 333, 5)])
+def test_attention_decode_cross_long_keys(dtype, G, S, EB):
+    """Cross-attention of a decoder step over the per-sentence K / V cache (csrc/decode.cu: the cp.async-ring kernels -- warp
+    MMA tiles in bf16, staged SIMT in fp32 -- for S >= 64): G beams of a sentence share cache row kv_row[group], the position
+    term arrives as bias_in, padded encoder positions are masked, per-head scale; against the fp64 restatement of
+    unify_multihead_attention.py:345-398 for one query token.  Includes BASELINE configs[4]'s shape (G = 5, S = 908)."""
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(G * 1000 + S)
+    H, D = 12, 768
+    R = EB * G
+    cap = (S + 7) // 8 * 8
+    mk = lambda *s_: torch.randn(*s_, generator=g).cuda().to(dtype)
+    q = mk(R, 1, D) * 0.25
+    k, v = mk(EB + 1, cap, D), mk(EB + 1, cap, D)          # one spare cache row: kv_row is a real indirection
+    rows = torch.randperm(EB + 1, generator=g)[:EB].to(torch.int32).cuda()
+    bias = torch.randn(R, H, (S + 3) // 4 * 4, generator=g).cuda()
+    hs = (torch.rand(H, generator=g) + 0.5).cuda()
+    kpm = torch.zeros(EB + 1, cap, dtype=torch.uint8).cuda()
+    kpm[int(rows[0]), S - 9:] = 1                           # padded tail of one sentence
+    if EB > 1:
+        kpm[int(rows[1]), 3] = 1
+    got = ops.attention_decode(q, None, k, None, v, S, H, G, rows, None, kpm, hs, bias_in=bias)
+    kr = rows.long().repeat_interleave(G)
+    kk = k.double().view(EB + 1, cap, H, 64)[kr][:, :S]
+    vv = v.double().view(EB + 1, cap, H, 64)[kr][:, :S]
+    sc = torch.einsum("rhd,rjhd->rhj", q.double().view(R, H, 64), kk) + bias.double()[:, :, :S]
+    sc = sc.masked_fill(kpm.bool()[kr][:, None, :S], -math.inf)
+    o = torch.einsum("rhj,rjhd->rhd", torch.softmax(sc, -1), vv) * hs.double().view(1, H, 1)
+    err = (got.double().view(R, H, 64) - o).abs().max().item()
+    print("decode cross-attention G=%d S=%d %s: max-abs error %.2e" % (G, S, dtype, err))
+    assert err < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("S", [1, 7, 17, 32])
 def test_attention_decode_short_keys(dtype, S):
     """Incremental self-attention (one query per row, S <= 32 keys: the warp-per-(row, head) kernel of csrc/decode.cu) with the
