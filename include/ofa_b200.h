@@ -141,6 +141,8 @@ typedef struct OfaDecodeArgs {
 int ofa_attn_decode(const OfaDecodeArgs* args, int dtype, void* stream);
 /* A/B switch: 0 = the (group, head) decode kernel also for short self-attention problems; returns the previous setting */
 int ofa_attn_decode_set_short(int on);
+/* A/B switch: 0 = the two-pass warp-MMA kernel (score buffer in shared memory) for bf16 long-key decode attention */
+int ofa_attn_decode_set_online(int on);
 int ofa_cache_gather(const void* src, void* dst, const long long* order, int rows, int L, int D, long long row_stride,
                      long long plane_stride, int planes, int dtype, void* stream);
 /* paged self-attention cache of the incremental decoder: pool [slot][plane = 2*layer + (k|v)][page_len][D].  A beam reorder

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ofa_gemm_set_wgrad_bn256": [c_i],
     "ofa_gemm_set_small64": [c_i],
     "ofa_attn_decode_set_short": [c_i],
+    "ofa_attn_decode_set_online": [c_i],
     "ofa_gemm_set_pair_min_tiles": [c_i],
     "ofa_split3_bf16": [c_p, c_ll, c_i, c_i, c_p, c_ll, c_ll, c_i, c_p],
     "ofa_layernorm_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_i, c_i, c_p],
@@ -152,6 +153,8 @@ def load(path=None):
         lib.ofa_attn_set_bwd_small(int(os.environ["OFA_ATTN_BWD_SMALL"]))
     if os.environ.get("OFA_GEMM_SMALL64") is not None:      # A/B switch: 128 x 64 tiles for small-M GEMMs
         lib.ofa_gemm_set_small64(int(os.environ["OFA_GEMM_SMALL64"]))
+    if os.environ.get("OFA_DECODE_ONLINE") is not None:     # A/B switch: one-pass (online softmax) long-key decode attention
+        lib.ofa_attn_decode_set_online(int(os.environ["OFA_DECODE_ONLINE"]))
     if os.environ.get("OFA_DECODE_SHORT") is not None:      # A/B switch: warp-per-(row, head) self-attention decode kernel
         lib.ofa_attn_decode_set_short(int(os.environ["OFA_DECODE_SHORT"]))
     if os.environ.get("OFA_PDL") is not None:       # A/B switch for programmatic dependent launch

@@ -40,6 +40,7 @@ namespace {
 constexpr int HD = 64;
 constexpr int kT = 128;
 constexpr int GMAX = 8;
+int g_decode_online = 1;    // A/B switch (ofa_attn_decode_set_online): 0 = the two-pass warp-MMA kernel for the long key ranges
 int g_decode_short = 1;     // A/B switch (ofa_attn_decode_set_short): 0 = the (group, head) kernel for every shape
 
 template <typename T>
@@ -690,6 +691,186 @@ int launch_decode_mma(const OfaDecodeArgs& a, cudaStream_t st) {
   return (int)ofa_launch_pdl(attn_decode_mma_kernel<G>, grid, kT, smem, st, a);
 }
 
+// ---- bf16 long-key decode attention, one streamed pass (online softmax in registers) --------------------------------------------
+// The two-pass kernel above keeps G x S fp32 scores in shared memory (18 KB at G = 5, S = 908: half of the CTA's budget), so
+// its rings hold one 2 KB tile in flight per warp and the launch sits at 2.6 TB/s on bytes in flight.  Here a stage is the K
+// AND the V tile of 16 keys (4 KB, 128-byte rows XOR-swizzled by key so that ldmatrix is conflict-free without padding), the
+// scores never leave registers: S = Q K^T with the queries as the M side (rows 0..G-1 of 16), so the C fragment of a tile is
+// already the A fragment of P V (rows = queries, columns = keys), running max / sum per query row, O rescaled per tile.  Three
+// warps with three stages each = 36 KB per CTA (six CTAs per SM: the whole grid of 64 x 12 in one wave) with 8 KB per warp in
+// flight and no drain between passes: 69 -> 52 us per launch at the captioning shape (ncu: 193.6 MB in 50.2 us = 3.86 TB/s, 59 %
+// of the copy peak; four warps x two stages measured the same).  bias_in / key padding of the NEXT tile are fetched into
+// registers while the current one is computed -- that fetch is now the top stall (long scoreboard, 53 % of the samples); a
+// three-tile-deep register prefetch spilled and was slower.
+constexpr int OSTAGE = TKW * HD * 2 * 2;       // K tile + V tile, bf16
+constexpr int OW = 3;        // warps per CTA
+constexpr int ONST = 3;      // stages per warp: 3 x 3 x 4 KB = 36 KB per CTA, two of three stages (8 KB per warp) in flight
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int G>
+__global__ void __launch_bounds__(OW * 32, 6) attn_decode_online_kernel(OfaDecodeArgs a) {
+  using T = __nv_bfloat16;
+  static_assert(G <= 8, "the queries of a group are rows 0..7 of the M = 16 tile");
+  extern __shared__ __align__(128) unsigned char dsm[];
+  float (*wo)[G][HD] = reinterpret_cast<float(*)[G][HD]>(dsm);           // partial outputs, over the drained rings
+  static_assert(sizeof(float) * OW * G * HD <= (size_t)OW * ONST * OSTAGE, "partial outputs must fit the rings");
+  __shared__ float mw[OW][8], lw[OW][8];
+  const int grp = blockIdx.x, h = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int row0 = grp * G, S = a.S;
+  constexpr float kL2E = 1.4426950408889634f;
+  pdl_sync();
+  const int krow = a.kv_row ? a.kv_row[grp] : grp;
+  const unsigned char* Kb = reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(a.k) + (size_t)krow * a.bsk + h * HD);
+  const unsigned char* Vb = reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(a.v) + (size_t)krow * a.bsv + h * HD);
+  const size_t ldk_b = (size_t)a.ldk * sizeof(T), ldv_b = (size_t)a.ldv * sizeof(T);
+  const unsigned char* kpm = a.kpm ? a.kpm + (size_t)krow * a.kpm_stride : nullptr;
+  const int ntile = (S + TKW - 1) / TKW;
+  const int nw = ntile > warp ? (ntile - warp + OW - 1) / OW : 0;      // tiles of this warp: warp, warp + OW, ...
+  const uint32_t wring = smem_u32(dsm) + warp * ONST * OSTAGE;
+  // this lane copies four 16-byte chunks of the K row and of the V row of key lane / 2; the two lanes of a key take ADJACENT
+  // chunks in every instruction, so a warp-wide copy asks L2 for whole 32-byte sectors (cp.async.cg goes to L2 per request:
+  // half-sector requests would read every sector twice)
+  const int ckey = lane >> 1, cch = lane & 1;
+  auto issue = [&](int n) {
+    if (n < nw) {
+      const int j = (warp + OW * n) * TKW + ckey;
+      const int ok = j < S ? 16 : 0;
+      const size_t jj = ok ? j : 0;
+      const uint32_t dk = wring + (n % ONST) * OSTAGE + ckey * 128, dv = dk + TKW * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ch = 2 * c + cch;
+        const uint32_t sw = (uint32_t)((ch ^ (ckey & 7)) * 16);
+        cp_async16(dk + sw, Kb + jj * ldk_b + ch * 16, ok);
+        cp_async16(dv + sw, Vb + jj * ldv_b + ch * 16, ok);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int n = 0; n < ONST - 1; ++n) issue(n);
+  const int fr = lane >> 2, fc = (lane & 3) * 2;
+  const bool qrow = fr < G && row0 + fr < a.R;
+  // A fragments of q (16 x 64, rows >= G zero): a0 = (row fr, dims ks*16 + fc, +1), a2 = (row fr, dims ks*16 + 8 + fc, +1)
+  uint32_t qa[4][4];
+  {
+    const T* qp = reinterpret_cast<const T*>(a.q) + (size_t)(qrow ? row0 + fr : 0) * a.ldq + h * HD;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa[ks][0] = qrow ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + fc) : 0u;
+      qa[ks][2] = qrow ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8 + fc) : 0u;
+      qa[ks][1] = 0u; qa[ks][3] = 0u;
+    }
+  }
+  const float* brow = a.bias_in && qrow ? a.bias_in + ((size_t)(row0 + fr) * a.H + h) * a.bias_ld : nullptr;
+  // additive term of this thread's four keys of a tile (keys j0 + nb * 8 + fc + e): bias, -inf on padded keys and beyond S
+  auto fetch_bias = [&](int n, float (&b)[4]) {
+    const int j0 = (warp + OW * n) * TKW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kj = j0 + (i >> 1) * 8 + fc + (i & 1);
+      const bool inb = n < nw && kj < S;
+      const float bv = inb && brow ? brow[kj] : 0.f;                   // (two independent loads, not mask -> bias)
+      const unsigned char pm = inb && kpm ? kpm[kj] : (unsigned char)0;
+      b[i] = (!inb || pm) ? -CUDART_INF_F : bv;
+    }
+  };
+  float bn[4];
+  fetch_bias(0, bn);
+  // ldmatrix lane addressing inside a tile of 128-byte rows, chunk (16 bytes) c of key r stored at chunk c ^ (r & 7)
+  const int rowB = (lane & 7) + (lane >> 4) * 8, chB = (lane >> 3) & 1;        // K as the B operand (keys x dims)
+  const int rowA = (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;        // V through ldmatrix.trans (keys x dims)
+  float m = -CUDART_INF_F, l = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+  for (int n = 0; n < nw; ++n) {
+    __syncwarp();
+    issue(n + ONST - 1);
+    float bc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bc[i] = bn[i];
+    fetch_bias(n + 1, bn);
+    cp_async_wait<ONST - 1>();
+    __syncwarp();
+    const uint32_t kt = wring + (n % ONST) * OSTAGE, vt = kt + TKW * 128;
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};       // block nb: keys nb * 8 + fc + (e & 1); row fr (e < 2)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bf[4];
+      ldmatrix_x4(bf, kt + rowB * 128 + (((chB + 2 * ks) ^ (rowB & 7)) * 16));
+      mma_bf16_16816(s[0], qa[ks], bf[0], bf[1]);
+      mma_bf16_16816(s[1], qa[ks], bf[2], bf[3]);
+    }
+    // row fr only (rows 8..15 of the tile are no queries): x = (s + bias) * log2 e
+    float x[4];
+    x[0] = (s[0][0] + bc[0]) * kL2E; x[1] = (s[0][1] + bc[1]) * kL2E;
+    x[2] = (s[1][0] + bc[2]) * kL2E; x[3] = (s[1][1] + bc[3]) * kL2E;
+    float tm = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
+    const float mn = fmaxf(m, tm);
+    const float mu = mn == -CUDART_INF_F ? 0.f : mn;
+    const float alpha = ex2_approx(m - mu);
+    m = mn;
+    float p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = ex2_approx(x[i] - mu);
+    float ps = (p[0] + p[1]) + (p[2] + p[3]);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+    l = l * alpha + ps;
+    uint32_t pa[4];
+    pa[0] = pack_bf16(p[0], p[1]); pa[2] = pack_bf16(p[2], p[3]); pa[1] = 0u; pa[3] = 0u;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { o[nb][0] *= alpha; o[nb][1] *= alpha; }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {                   // dims np * 16 .. + 16: two n-blocks of 8
+      uint32_t bf[4];
+      ldmatrix_x4_trans(bf, vt + rowA * 128 + (((chA + 2 * np) ^ (rowA & 7)) * 16));
+      mma_bf16_16816(o[2 * np], pa, bf[0], bf[1]);
+      mma_bf16_16816(o[2 * np + 1], pa, bf[2], bf[3]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                     // everybody is done with the rings
+  if (fr < G) {
+    if ((lane & 3) == 0) { mw[warp][fr] = m; lw[warp][fr] = l; }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { wo[warp][fr][nb * 8 + fc] = o[nb][0]; wo[warp][fr][nb * 8 + fc + 1] = o[nb][1]; }
+  }
+  __syncthreads();
+  const float cs = a.head_scale ? a.head_scale[h] : 1.f;
+  for (int e = t; e < G * HD; e += OW * 32) {
+    const int g = e / HD, d = e % HD;
+    if (row0 + g >= a.R) continue;
+    float mm = -CUDART_INF_F;
+#pragma unroll
+    for (int w = 0; w < OW; ++w) mm = fmaxf(mm, mw[w][g]);
+    const float mu = mm == -CUDART_INF_F ? 0.f : mm;
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int w = 0; w < OW; ++w) {
+      const float f = ex2_approx(mw[w][g] - mu);
+      ll = fmaf(lw[w][g], f, ll);
+      oo = fmaf(wo[w][g][d], f, oo);
+    }
+    reinterpret_cast<T*>(a.o)[(size_t)(row0 + g) * a.ldo + h * HD + d] = (T)((ll > 0.f ? oo / ll : 0.f) * cs);
+  }
+}
+
+template <int G>
+int launch_decode_online(const OfaDecodeArgs& a, cudaStream_t st) {
+  dim3 grid((a.R + G - 1) / G, a.H);
+  return (int)ofa_launch_pdl(attn_decode_online_kernel<G>, grid, OW * 32, (size_t)OW * ONST * OSTAGE, st, a);
+}
+
 template <typename T, int G>
 int launch_decode_long(const OfaDecodeArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)NST * TK * (HD * sizeof(T) + 16) + (size_t)G * ((a.S + TK - 1) / TK * TK) * sizeof(float);
@@ -716,7 +897,9 @@ int launch_decode(const OfaDecodeArgs& a, cudaStream_t st) {
     int rc = -1;
     switch (a.G) {
 #define OFA_DEC_CASE(g) case g: \
-        if constexpr (sizeof(T) == 2) rc = launch_decode_mma<g>(a, st); else rc = launch_decode_long<T, g>(a, st); \
+        if constexpr (sizeof(T) == 2) \
+          rc = (g_decode_online && !a.score_out && a.v && (a.ldq % 2) == 0) ? launch_decode_online<g>(a, st) : launch_decode_mma<g>(a, st); \
+        else rc = launch_decode_long<T, g>(a, st); \
         break;
       OFA_DEC_CASE(1) OFA_DEC_CASE(2) OFA_DEC_CASE(3) OFA_DEC_CASE(4) OFA_DEC_CASE(5) OFA_DEC_CASE(6) OFA_DEC_CASE(7) OFA_DEC_CASE(8)
 #undef OFA_DEC_CASE
@@ -821,6 +1004,12 @@ extern "C" int ofa_page_write(void* pool, const int* tab, const void* k, const v
     OFA_CUDA(ofa_launch_pdl(page_write_kernel<float>, dim3(rows), 128, 0, st, (float*)pool, tab, (const float*)k, (const float*)v, ldk, ldv, max_pages, page, off, page_len, D, planes, plane_k));
   OFA_LAUNCH_CHECK("page_write_kernel");
   return 0;
+}
+
+extern "C" int ofa_attn_decode_set_online(int on) {
+  const int old = g_decode_online;
+  g_decode_online = on;
+  return old;
 }
 
 extern "C" int ofa_attn_decode_set_short(int on) {

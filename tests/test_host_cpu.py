@@ -47,7 +47,8 @@ def test_sass_is_blackwell_native(lib_path):
     for fn in sass.split("Function :")[1:]:
         if "HMMA." in fn.replace("UTCHMMA", ""):
             name = fn.split("\n", 1)[0]
-            assert any(k in name for k in ("attn_decode_mma_kernel", "attn_bwd_smallq_kernel", "attn_fwd_smallq_kernel")), name
+            assert any(k in name for k in ("attn_decode_mma_kernel", "attn_decode_online_kernel", "attn_bwd_smallq_kernel",
+                                                 "attn_fwd_smallq_kernel")), name
     assert "UBLKCP" in sass       # 1-D bulk copies (the LayerNorm backward's shared-memory row ring)
     assert "FFMA2" in sass        # packed fp32x2 arithmetic (wide-row LayerNorm / GELU forward)
     # relative-position table gradients of the attention backward: native int32 shared atomics, no float CAS loops
