@@ -414,7 +414,6 @@ def criterion_forward(sd, cfg, sample, epsilon=0.1, use_rdrop=False, reg_alpha=1
 # ------------------------------------------------------------------------------------------------
 # beam search     models/sequence_generator.py:209-598,637-746 ; models/search.py:109-144
 # ------------------------------------------------------------------------------------------------
-@torch.no_grad()
 class Trie:
     # utils/trie.py:9-30 restated with plain dicts: insert a token list; next layer of a prefix ([eos] once the prefix left the trie)
     def __init__(self, eos):
@@ -441,6 +440,7 @@ def _first_beam(t, mask, beam):
     return t.view(-1, t.size(-1))
 
 
+@torch.no_grad()
 def generate(sd, cfg, net_input, beam=5, max_len_a=0, max_len_b=16, min_len=1, len_penalty=1.0,
              temperature=1.0, no_repeat_ngram_size=0, unk_penalty=0.0, constraint_trie=None, constraint_range=None,
              zero_shot=False, prefix_tokens=None):

@@ -157,3 +157,59 @@ def test_grad_accumulator_keeps_running_sum_over_micro_steps():
     lin.weight.grad = torch.ones_like(lin.weight)                    # a foreign gradient tensor is added to, not replaced
     micro_step(1.0)
     assert float(lin.weight.grad[0, 0]) == 2
+
+
+def test_flatten_trie_matches_the_trie_walk():
+    """Host side of constrained decoding: the CSR form of utils/trie.py's Trie (root = node 0, children in
+    insertion order) answers get_next_layer for every prefix exactly like the object trie; dead prefixes have no node."""
+    from musketeer_b200.sequence_generator import flatten_trie
+    from oracle import ofa_oracle as oo, synth
+    trie = oo.Trie(2)
+    words = synth.trie_words(n=40, max_len=4, seed=3, vocab=4099)
+    for w in words:
+        trie.insert(w)
+    (ptr, tok, child), index = flatten_trie(trie, "cpu", return_index=True)
+    ptr, tok, child = ptr.tolist(), tok.tolist(), child.tolist()
+    assert ptr[0] == 0 and len(ptr) == max(child) + 2 and len(tok) == len(child) == ptr[-1]
+    assert len(index) == len(ptr) - 1 and sorted(index.values()) == list(range(len(ptr) - 1))
+
+    def walk(prefix):
+        node = 0
+        for t in prefix:
+            nxt = [child[e] for e in range(ptr[node], ptr[node + 1]) if tok[e] == t]
+            if not nxt:
+                return None
+            node = nxt[0]
+        return node
+
+    seen = set()
+    for w in words:
+        for n in range(1, len(w) + 1):
+            pre = tuple(w[:n])
+            if pre in seen:
+                continue
+            seen.add(pre)
+            node = walk(pre)
+            assert node is not None
+            assert [tok[e] for e in range(ptr[node], ptr[node + 1])] == list(trie.get_next_layer(list(pre)))
+    assert walk([0, 4098, 4097]) is None                    # a prefix outside the trie: the kernels fall back to [eos]
+    assert trie.get_next_layer([0, 4098, 4097]) == [2]
+
+
+def test_generator_argument_checks():
+    """Options the hot path does not carry fail at the call, naming the option (no silent fallback)."""
+    from musketeer_b200.sequence_generator import SequenceGenerator
+    from oracle import synth
+    from tests.helpers import build_product
+    cfg = synth.make_cfg("ofa_micro", vocab_size=4099)
+    model, task = build_product(cfg, synth.synth_state_dict(cfg, seed=0), device="cpu")
+    with pytest.raises(NotImplementedError):
+        SequenceGenerator([model], task.target_dictionary, beam_size=9)
+    with pytest.raises(NotImplementedError):
+        SequenceGenerator([model, model], task.target_dictionary)
+    gen = SequenceGenerator([model], task.target_dictionary, beam_size=2, constraint_range="10,20")
+    sample = synth.make_batch(2, 9, 2, img=64, seed=1, vocab=4099)
+    with pytest.raises(NotImplementedError):
+        gen.generate([model], sample, prefix_tokens=torch.full((2, 1), 5))
+    with pytest.raises(NotImplementedError):
+        gen.generate([model], sample, constraints=torch.zeros(2, 1))
