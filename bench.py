@@ -6,10 +6,13 @@
 One "step" = one Musketeer micro-step: five sequential task forwards (caption / VQA / VG / SNLI-VE / gigaword, per-task
 batch b, 384x384 images) through the criterion + one backward, on random-init OFA-base in bf16 (synthetic data).
 `value` = samples/s with the batches resident in HBM; `e2e` = the same step including the pinned-host -> device copy of
-every batch and the device -> host read of the loss.  N > 1: one rank per GPU, batch-sharded (weak scaling), gradients
-all-reduced over NCCL by musketeer_b200.dp.GradReducer (bucketed, overlapped with backward).
-`--impl reference`: the reference's algorithm (the CPU oracle: the reference itself is pure Python/PyTorch and cannot
-travel to the GPU box) timed on the host cores on a bounded sample (per-task batch 1).
+every batch and the device -> host read of the loss.  N > 1: one rank per GPU, batch-sharded (weak scaling); the step is a
+CUDA-graph replay, after which the flat gradient arenas are all-reduced in place over NCCL (one collective per arena,
+musketeer_b200.dp.GradReducer.reduce_flat; the eager path overlaps bucketed all-reduces with backward instead).
+`--impl reference`: the reference's own CPU implementation of the same step, timed on the host cores with all threads on a
+bounded sample (per-task batch 2, the script's): the UNMODIFIED reference modules from baseline/_ref (placed there by
+tools/install_reference.py; they travel to the GPU box) through the fairseq stand-ins of oracle/ref_shim -- `kind:
+"reference"` -- or, where that tree is absent, the oracle port (`kind: "port"`).  Rank 0 alone runs it under torchrun.
 """
 import argparse
 import json
